@@ -1,0 +1,80 @@
+"""ctypes binding of libdgp_b200.so (C ABI: include/dgp_b200.h).
+
+There is no fallback: if the shared library is missing or the device is not sm_100 every entry point raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdgp_b200.so")
+
+DGP_OK = 0
+STATUS_NAMES = {0: "DGP_OK", -1: "DGP_ERR_INVALID", -2: "DGP_ERR_CUDA", -3: "DGP_ERR_UNSUPPORTED",
+                -4: "DGP_ERR_STATE", -5: "DGP_ERR_NOMEM"}
+
+
+class DgpError(RuntimeError):
+    def __init__(self, status, message):
+        self.status = status
+        super().__init__("%s: %s" % (STATUS_NAMES.get(status, status), message))
+
+
+class DgpConfig(C.Structure):
+    _fields_ = [
+        ("num_joints", C.c_int32),
+        ("location_refinement", C.c_int32),
+        ("device", C.c_int32),
+        ("stride", C.c_float),
+        ("locref_stdev", C.c_float),
+        ("mean_pixel", C.c_float * 3),
+        ("bn_epsilon", C.c_float),
+    ]
+
+
+# name -> (restype, argtypes); kept in one table so the CPU test-suite can check every exported symbol.
+_vp, _i, _f, _sz, _i64p = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.POINTER(C.c_int64)
+SIGNATURES = {
+    "dgp_create": (_i, [C.POINTER(DgpConfig), C.POINTER(_vp)]),
+    "dgp_destroy": (None, [_vp]),
+    "dgp_last_error": (C.c_char_p, [_vp]),
+    "dgp_load_weights": (_i, [_vp, C.c_char_p, _vp, _i64p, _i, _i]),
+    "dgp_finalize_weights": (_i, [_vp]),
+    "dgp_output_dims": (_i, [_i, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+    "dgp_forward": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "dgp_softargmax": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "dgp_sigmoid": (_i, [_vp, _vp, _vp, _sz, _vp]),
+    "dgp_potentials": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp]),
+    "dgp_estimate_pose_host": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp]),
+    "dgp_debug_keep_activations": (_i, [_vp, _i]),
+    "dgp_debug_get_activation": (_i, [_vp, C.c_char_p, _vp, _sz, _i64p]),
+    "dgp_conv2d": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp,
+                        _i, _i, _vp]),
+    "dgp_launch_count": (C.c_int64, [_vp]),
+    "dgp_num_sms": (_i, [_vp]),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen libdgp_b200.so (built by deepgraphpose_b200/build.py or __graft_entry__.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "libdgp_b200.so is not built (%s). Run `python -m deepgraphpose_b200.build`; "
+            "deepgraphpose_b200 has no CPU or PyTorch fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status, handle=None):
+    if status != DGP_OK:
+        msg = load().dgp_last_error(handle)
+        raise DgpError(status, msg.decode() if msg else "")

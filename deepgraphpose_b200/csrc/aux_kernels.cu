@@ -1,0 +1,154 @@
+// Bandwidth-class helper kernels around the tcgen05 conv GEMM (sm_100a).
+//   prep_s2d      : u8 frames -> (pixel - mean_pixel) -> explicit conv2d_same padding (3 px) -> 2x2 space-to-depth,
+//                   so that slim's 7x7 stride-2 conv1 becomes a stride-1 GEMM with K = 4 rows x 64.
+//                   Reference: pose_net.py:38-40 (mean subtraction), slim resnet_utils.conv2d_same (pad 3/3 + VALID).
+//   maxpool3x3s2  : slim.max_pool2d([3,3], stride=2, padding='SAME') of resnet_v1's root block.
+//   deconv_col2im : scatter-free col2im of the 3x3 stride-2 transposed-conv heads (pose_net.py:18-26):
+//                   out[2i+kh, 2j+kw] += x[i,j] * w[kh,kw], cropped to (2h, 2w), plus bias.
+#include "kernels.cuh"
+
+namespace dgp {
+
+namespace {
+
+__global__ void prep_s2d_kernel(const uint8_t* __restrict__ frames, int N, int H, int W, float m0, float m1, float m2,
+                                __nv_bfloat16* __restrict__ out, int Hs, int Ws) {
+  const size_t total = (size_t)N * Hs * Ws;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(t % Ws);
+    const size_t r = t / Ws;
+    const int i = (int)(r % Hs);
+    const int n = (int)(r / Hs);
+    const float mean[3] = {m0, m1, m2};
+    __align__(16) __nv_bfloat16 v[16];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int y = 2 * i + u - 3;
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+        const int x = 2 * j + w - 3;
+        const bool ok = (y >= 0) && (y < H) && (x >= 0) && (x < W);
+        const uint8_t* px = frames + (((size_t)n * H + (ok ? y : 0)) * W + (ok ? x : 0)) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float f = ok ? (float)px[c] - mean[c] : 0.0f;
+          v[(u * 2 + w) * 3 + c] = __float2bfloat16_rn(f);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 12; c < 16; ++c) v[c] = __float2bfloat16_rn(0.0f);
+    uint4* dst = reinterpret_cast<uint4*>(out + t * 16);
+    dst[0] = reinterpret_cast<const uint4*>(v)[0];
+    dst[1] = reinterpret_cast<const uint4*>(v)[1];
+  }
+}
+
+__device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
+  __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+
+__global__ void maxpool3x3s2_kernel(const uint4* __restrict__ in, int N, int H, int W, int C8, uint4* __restrict__ out,
+                                    int Ho, int Wo, int pad_t, int pad_l) {
+  const size_t total = (size_t)N * Ho * Wo * C8;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(t % C8);
+    size_t r = t / C8;
+    const int q = (int)(r % Wo);
+    r /= Wo;
+    const int p = (int)(r % Ho);
+    const int n = (int)(r / Ho);
+    uint4 m;
+    bool have = false;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int y = 2 * p - pad_t + dy;
+      if (y < 0 || y >= H) continue;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int x = 2 * q - pad_l + dx;
+        if (x < 0 || x >= W) continue;
+        const uint4 v = __ldg(in + (((size_t)n * H + y) * W + x) * C8 + c);
+        if (!have) {
+          m = v;
+          have = true;
+        } else {
+          m.x = bf16x2_max(m.x, v.x); m.y = bf16x2_max(m.y, v.y);
+          m.z = bf16x2_max(m.z, v.z); m.w = bf16x2_max(m.w, v.w);
+        }
+      }
+    }
+    out[t] = m;
+  }
+}
+
+__global__ void deconv_col2im_kernel(const float* __restrict__ contrib, int N, int h, int w, int ldn, int ctot, int nj,
+                                     const float* __restrict__ bias, float* __restrict__ logits,
+                                     float* __restrict__ locref) {
+  const int Ho = 2 * h, Wo = 2 * w;
+  const size_t total = (size_t)N * Ho * Wo * ctot;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int co = (int)(t % ctot);
+    size_t r = t / ctot;
+    const int x = (int)(r % Wo);
+    r /= Wo;
+    const int y = (int)(r % Ho);
+    const int n = (int)(r / Ho);
+    // y = 2i + kh: even y <- (i=y/2, kh=0) and (i=y/2-1, kh=2); odd y <- (i=(y-1)/2, kh=1).  Same for x.
+    int is[2], khs[2], ny = 0;
+    if (y & 1) { is[0] = y >> 1; khs[0] = 1; ny = 1; }
+    else {
+      is[0] = y >> 1; khs[0] = 0; ny = 1;
+      if ((y >> 1) >= 1) { is[1] = (y >> 1) - 1; khs[1] = 2; ny = 2; }
+    }
+    int js[2], kws[2], nx = 0;
+    if (x & 1) { js[0] = x >> 1; kws[0] = 1; nx = 1; }
+    else {
+      js[0] = x >> 1; kws[0] = 0; nx = 1;
+      if ((x >> 1) >= 1) { js[1] = (x >> 1) - 1; kws[1] = 2; nx = 2; }
+    }
+    float acc = bias ? bias[co] : 0.0f;
+    for (int a = 0; a < ny; ++a)
+      for (int b = 0; b < nx; ++b) {
+        const size_t m = ((size_t)n * h + is[a]) * w + js[b];
+        acc += contrib[m * ldn + (khs[a] * 3 + kws[b]) * ctot + co];
+      }
+    if (co < nj) logits[(((size_t)n * Ho + y) * Wo + x) * nj + co] = acc;
+    else if (locref) locref[(((size_t)n * Ho + y) * Wo + x) * (size_t)(ctot - nj) + (co - nj)] = acc;
+  }
+}
+
+int grid_for(size_t total, int threads) {
+  size_t g = (total + threads - 1) / threads;
+  if (g > 148 * 16) g = 148 * 16;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace
+
+cudaError_t launch_prep_s2d(const uint8_t* frames, int N, int H, int W, const float* mean3, __nv_bfloat16* out,
+                            int Hs, int Ws, cudaStream_t stream) {
+  const size_t total = (size_t)N * Hs * Ws;
+  prep_s2d_kernel<<<grid_for(total, 256), 256, 0, stream>>>(frames, N, H, W, mean3[0], mean3[1], mean3[2], out, Hs, Ws);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_maxpool3x3s2(const __nv_bfloat16* in, int N, int H, int W, int C, __nv_bfloat16* out, int Ho,
+                                int Wo, int pad_t, int pad_l, cudaStream_t stream) {
+  if (C % 8) return cudaErrorInvalidValue;
+  const size_t total = (size_t)N * Ho * Wo * (C / 8);
+  maxpool3x3s2_kernel<<<grid_for(total, 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(in), N, H, W, C / 8,
+                                                                reinterpret_cast<uint4*>(out), Ho, Wo, pad_t, pad_l);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_deconv_col2im(const float* contrib, int N, int h, int w, int ldn, int ctot, int nj,
+                                 const float* bias, float* logits, float* locref, cudaStream_t stream) {
+  const size_t total = (size_t)N * 4 * h * w * ctot;
+  deconv_col2im_kernel<<<grid_for(total, 256), 256, 0, stream>>>(contrib, N, h, w, ldn, ctot, nj, bias, logits, locref);
+  return cudaGetLastError();
+}
+
+}  // namespace dgp

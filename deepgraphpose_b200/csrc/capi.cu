@@ -1,0 +1,856 @@
+// libdgp_b200.so -- handle, weight conversion, per-shape execution plans and the C ABI of include/dgp_b200.h.
+#include "../../include/dgp_b200.h"
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <memory>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "conv_gemm_sm100.cuh"
+#include "kernels.cuh"
+
+using namespace dgp;
+
+namespace {
+
+char g_create_error[512] = "";
+
+struct HostVar {
+  std::vector<float> data;
+  std::vector<int64_t> shape;
+};
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+struct ConvLayer {
+  std::string scope;
+  int R = 1, S = 1, Cin = 0, Cout = 0, stride = 1, dil = 1;
+  bool relu = true;
+  int K = 0;        // GEMM K (multiple of 64)
+  int Npad = 0;     // rows of the weight matrix (multiple of block_n)
+  int block_n = 0;
+  __nv_bfloat16* w = nullptr;  // [Npad][K]
+  float* scale = nullptr;      // [Npad] or nullptr
+  float* shift = nullptr;
+};
+
+struct UnitDesc {
+  std::string scope;
+  int depth, base, stride, rate;
+  int shortcut = -1, conv1 = -1, conv2 = -1, conv3 = -1;  // indices into layers
+};
+
+enum StepKind { STEP_PREP = 0, STEP_GEMM = 1, STEP_POOL = 2, STEP_COL2IM = 3 };
+
+struct Step {
+  StepKind kind;
+  ConvGemmParams gp;      // STEP_GEMM
+  std::string end_point;  // name under which the output is kept in debug mode ("" = none)
+  const void* out_ptr = nullptr;
+  int oN = 0, oH = 0, oW = 0, oC = 0;  // output shape (bf16 NHWC) for debug dumps
+  // pool
+  const __nv_bfloat16* pin = nullptr;
+  int pH = 0, pW = 0, pC = 0, pad_t = 0, pad_l = 0;
+};
+
+struct Plan {
+  int B = 0, H = 0, W = 0;
+  int H1 = 0, W1 = 0, Hs = 0, Ws = 0;  // conv1 output / s2d dims
+  int hf = 0, wf = 0;                  // feature map (stride 16)
+  std::vector<DevBuf> bufs;
+  __nv_bfloat16* s2d = nullptr;
+  float* contrib = nullptr;
+  int contrib_ld = 0;
+  std::vector<Step> steps;
+};
+
+}  // namespace
+
+struct dgp_handle {
+  dgp_config cfg;
+  int device = 0;
+  int num_sms = 0;
+  char err[512] = "";
+  std::map<std::string, HostVar> host_vars;
+  bool finalized = false;
+  std::vector<ConvLayer> layers;
+  int conv1_layer = -1, head_layer = -1;
+  std::vector<UnitDesc> units;
+  float* head_bias = nullptr;
+  int ctot = 0;
+  std::map<std::tuple<int, int, int>, std::unique_ptr<Plan>> plans;
+  bool debug_keep = false;
+  struct Kept {
+    void* p;
+    int N, H, W, C;
+  };
+  std::map<std::string, Kept> kept;
+  int64_t launches = 0;
+  // softargmax workspace
+  SaPartial* sa_ws = nullptr;
+  size_t sa_ws_bytes = 0;
+  // estimate_pose_host staging
+  cudaStream_t stream = nullptr;
+  DevBuf st_frames, st_logits, st_mu, st_peak, st_lik;
+};
+
+namespace {
+
+int fail(dgp_handle* h, int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(h ? h->err : g_create_error, 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CU_OK(h, expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess)                                                                      \
+      return fail(h, DGP_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+void same_pad(int in, int k, int stride, int rate, int* beg, int* out) {
+  const int o = ceil_div(in, stride);
+  const int keff = (k - 1) * rate + 1;
+  int total = (o - 1) * stride + keff - in;
+  if (total < 0) total = 0;
+  *beg = total / 2;
+  *out = o;
+}
+
+int pick_block_n(int n) {
+  // largest UMMA N (multiple of 16, <= 256) that tiles n with the least padding
+  const int nb = ceil_div(n, 256);
+  int bn = ceil_div(ceil_div(n, nb), 16) * 16;
+  if (bn > 256) bn = 256;
+  return bn;
+}
+
+int tmem_cols_for(int block_n) {
+  int need = 2 * block_n, c = 32;
+  while (c < need) c <<= 1;
+  return c;
+}
+
+const HostVar* find_var(dgp_handle* h, const std::string& name) {
+  auto it = h->host_vars.find(name);
+  return it == h->host_vars.end() ? nullptr : &it->second;
+}
+
+int upload_layer(dgp_handle* h, ConvLayer& L, const std::vector<__nv_bfloat16>& wmat, const std::vector<float>* scale,
+                 const std::vector<float>* shift) {
+  CU_OK(h, cudaMalloc(&L.w, wmat.size() * sizeof(__nv_bfloat16)));
+  CU_OK(h, cudaMemcpy(L.w, wmat.data(), wmat.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+  if (scale) {
+    CU_OK(h, cudaMalloc(&L.scale, scale->size() * sizeof(float)));
+    CU_OK(h, cudaMemcpy(L.scale, scale->data(), scale->size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  if (shift) {
+    CU_OK(h, cudaMalloc(&L.shift, shift->size() * sizeof(float)));
+    CU_OK(h, cudaMemcpy(L.shift, shift->data(), shift->size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  return DGP_OK;
+}
+
+// Frozen batch norm folded to fp32 scale/shift (applied in the GEMM epilogue, never into the bf16 weights).
+int bn_scale_shift(dgp_handle* h, const std::string& scope, int C, std::vector<float>* scale, std::vector<float>* shift) {
+  const HostVar* g = find_var(h, scope + "/BatchNorm/gamma");
+  const HostVar* b = find_var(h, scope + "/BatchNorm/beta");
+  const HostVar* m = find_var(h, scope + "/BatchNorm/moving_mean");
+  const HostVar* v = find_var(h, scope + "/BatchNorm/moving_variance");
+  if (!b || !m || !v) return fail(h, DGP_ERR_STATE, "missing BatchNorm variables for %s", scope.c_str());
+  scale->resize(C);
+  shift->resize(C);
+  for (int c = 0; c < C; ++c) {
+    const float gamma = g ? g->data[c] : 1.0f;
+    const float s = gamma / sqrtf(v->data[c] + h->cfg.bn_epsilon);
+    (*scale)[c] = s;
+    (*shift)[c] = b->data[c] - m->data[c] * s;
+  }
+  return DGP_OK;
+}
+
+int build_conv_layer(dgp_handle* h, const std::string& scope, int R, int S, int Cin, int Cout, int stride, int dil,
+                     bool relu, int* index) {
+  const HostVar* w = find_var(h, scope + "/weights");
+  if (!w) return fail(h, DGP_ERR_STATE, "missing variable %s/weights", scope.c_str());
+  if (w->shape.size() != 4 || w->shape[0] != R || w->shape[1] != S || w->shape[2] != Cin || w->shape[3] != Cout)
+    return fail(h, DGP_ERR_INVALID, "%s/weights has the wrong shape (want [%d,%d,%d,%d])", scope.c_str(), R, S, Cin, Cout);
+  if (Cin % 64 != 0 || Cout % 16 != 0) return fail(h, DGP_ERR_UNSUPPORTED, "%s: channels not tileable", scope.c_str());
+  ConvLayer L;
+  L.scope = scope; L.R = R; L.S = S; L.Cin = Cin; L.Cout = Cout; L.stride = stride; L.dil = dil; L.relu = relu;
+  L.K = R * S * Cin;
+  L.block_n = Cout >= 256 ? 256 : Cout;
+  L.Npad = Cout;
+  std::vector<__nv_bfloat16> wm((size_t)Cout * L.K);
+  for (int t = 0; t < R * S; ++t)
+    for (int c = 0; c < Cin; ++c) {
+      const float* src = &w->data[((size_t)t * Cin + c) * Cout];
+      for (int o = 0; o < Cout; ++o) wm[(size_t)o * L.K + (size_t)t * Cin + c] = __float2bfloat16_rn(src[o]);
+    }
+  std::vector<float> scale, shift;
+  int rc = bn_scale_shift(h, scope, Cout, &scale, &shift);
+  if (rc) return rc;
+  rc = upload_layer(h, L, wm, &scale, &shift);
+  if (rc) return rc;
+  *index = (int)h->layers.size();
+  h->layers.push_back(L);
+  return DGP_OK;
+}
+
+// conv1: 7x7 stride 2 on 3 channels == 4x4 stride-1 conv on the 2x2 space-to-depth image (12 -> 16 channels);
+// one TMA "pixel" is a window of 4 horizontally adjacent s2d pixels (64 channels), the 4 window rows are the taps.
+int build_conv1_layer(dgp_handle* h) {
+  const std::string scope = "resnet_v1_50/conv1";
+  const HostVar* w = find_var(h, scope + "/weights");
+  if (!w) return fail(h, DGP_ERR_STATE, "missing variable %s/weights", scope.c_str());
+  if (w->shape.size() != 4 || w->shape[0] != 7 || w->shape[1] != 7 || w->shape[2] != 3 || w->shape[3] != 64)
+    return fail(h, DGP_ERR_INVALID, "%s/weights must be [7,7,3,64]", scope.c_str());
+  ConvLayer L;
+  L.scope = scope; L.R = 4; L.S = 1; L.Cin = 64; L.Cout = 64; L.stride = 1; L.dil = 1; L.relu = true;
+  L.K = 256; L.block_n = 64; L.Npad = 64;
+  std::vector<__nv_bfloat16> wm((size_t)64 * 256, __float2bfloat16_rn(0.0f));
+  for (int a = 0; a < 4; ++a)
+    for (int b = 0; b < 4; ++b)
+      for (int u = 0; u < 2; ++u)
+        for (int v = 0; v < 2; ++v) {
+          const int kh = 2 * a + u, kw = 2 * b + v;
+          if (kh >= 7 || kw >= 7) continue;
+          for (int c = 0; c < 3; ++c)
+            for (int o = 0; o < 64; ++o)
+              wm[(size_t)o * 256 + a * 64 + b * 16 + (u * 2 + v) * 3 + c] =
+                  __float2bfloat16_rn(w->data[(((size_t)kh * 7 + kw) * 3 + c) * 64 + o]);
+        }
+  std::vector<float> scale, shift;
+  int rc = bn_scale_shift(h, scope, 64, &scale, &shift);
+  if (rc) return rc;
+  rc = upload_layer(h, L, wm, &scale, &shift);
+  if (rc) return rc;
+  h->conv1_layer = (int)h->layers.size();
+  h->layers.push_back(L);
+  return DGP_OK;
+}
+
+// Both deconv heads as ONE GEMM over input pixels: column (kh*3+kw)*ctot + co, co = [part_pred | locref_pred].
+int build_head_layer(dgp_handle* h) {
+  const int nj = h->cfg.num_joints;
+  const int ctot = h->cfg.location_refinement ? 3 * nj : nj;
+  const HostVar* wp = find_var(h, "pose/part_pred/block4/weights");
+  const HostVar* bp = find_var(h, "pose/part_pred/block4/biases");
+  if (!wp || !bp) return fail(h, DGP_ERR_STATE, "missing pose/part_pred/block4 variables");
+  if (wp->shape.size() != 4 || wp->shape[0] != 3 || wp->shape[1] != 3 || wp->shape[2] != nj || wp->shape[3] != 2048)
+    return fail(h, DGP_ERR_INVALID, "pose/part_pred/block4/weights must be [3,3,%d,2048]", nj);
+  const HostVar* wl = nullptr;
+  const HostVar* bl = nullptr;
+  if (h->cfg.location_refinement) {
+    wl = find_var(h, "pose/locref_pred/block4/weights");
+    bl = find_var(h, "pose/locref_pred/block4/biases");
+    if (!wl || !bl) return fail(h, DGP_ERR_STATE, "missing pose/locref_pred/block4 variables");
+    if (wl->shape.size() != 4 || wl->shape[2] != 2 * nj || wl->shape[3] != 2048)
+      return fail(h, DGP_ERR_INVALID, "pose/locref_pred/block4/weights must be [3,3,%d,2048]", 2 * nj);
+  }
+  ConvLayer L;
+  L.scope = "pose/heads"; L.R = 1; L.S = 1; L.Cin = 2048; L.Cout = 9 * ctot; L.relu = false;
+  L.K = 2048;
+  L.block_n = pick_block_n(9 * ctot);
+  L.Npad = ceil_div(9 * ctot, L.block_n) * L.block_n;
+  std::vector<__nv_bfloat16> wm((size_t)L.Npad * 2048, __float2bfloat16_rn(0.0f));
+  for (int t = 0; t < 9; ++t)
+    for (int co = 0; co < ctot; ++co) {
+      const HostVar* src = co < nj ? wp : wl;
+      const int cc = co < nj ? co : co - nj;
+      const int cn = co < nj ? nj : 2 * nj;
+      const float* s = &src->data[((size_t)t * cn + cc) * 2048];
+      __nv_bfloat16* d = &wm[(size_t)(t * ctot + co) * 2048];
+      for (int c = 0; c < 2048; ++c) d[c] = __float2bfloat16_rn(s[c]);
+    }
+  int rc = upload_layer(h, L, wm, nullptr, nullptr);
+  if (rc) return rc;
+  std::vector<float> bias(ctot);
+  for (int co = 0; co < ctot; ++co) bias[co] = co < nj ? bp->data[co] : bl->data[co - nj];
+  CU_OK(h, cudaMalloc(&h->head_bias, ctot * sizeof(float)));
+  CU_OK(h, cudaMemcpy(h->head_bias, bias.data(), ctot * sizeof(float), cudaMemcpyHostToDevice));
+  h->ctot = ctot;
+  h->head_layer = (int)h->layers.size();
+  h->layers.push_back(L);
+  return DGP_OK;
+}
+
+int alloc_buf(dgp_handle* h, Plan* pl, size_t bytes, void** out) {
+  DevBuf b;
+  b.bytes = bytes;
+  CU_OK(h, cudaMalloc(&b.p, bytes));
+  pl->bufs.push_back(b);
+  *out = b.p;
+  return DGP_OK;
+}
+
+// Fill the GEMM params of one conv layer. x: input NHWC bf16 (N,H,W,Cin). Returns output dims via Ho/Wo.
+int make_gemm_step(dgp_handle* h, const ConvLayer& L, const void* x, int N, int H, int W, int pad_mode, void* out,
+                   bool out_f32, const __nv_bfloat16* residual, int res_sub, int res_H, int res_W, int block_n_override,
+                   Step* st, int* Ho, int* Wo) {
+  memset(&st->gp, 0, sizeof(st->gp));
+  ConvGemmParams& g = st->gp;
+  int P, Q, lower_h = 0, lower_w = 0, upper_h = 0, upper_w = 0;
+  const int keff_h = (L.R - 1) * L.dil + 1, keff_w = (L.S - 1) * L.dil + 1;
+  if (pad_mode == 0) {  // TF SAME
+    same_pad(H, L.R, L.stride, L.dil, &lower_h, &P);
+    same_pad(W, L.S, L.stride, L.dil, &lower_w, &Q);
+    const int tot_h = (P - 1) * L.stride + keff_h - H, tot_w = (Q - 1) * L.stride + keff_w - W;
+    upper_h = (tot_h > 0 ? tot_h : 0) - lower_h;
+    upper_w = (tot_w > 0 ? tot_w : 0) - lower_w;
+  } else if (pad_mode == 1) {  // slim conv2d_same: explicit (keff-1) padding, beg = (keff-1)/2, then VALID
+    if (L.stride == 1) {
+      same_pad(H, L.R, 1, L.dil, &lower_h, &P);
+      same_pad(W, L.S, 1, L.dil, &lower_w, &Q);
+      upper_h = (keff_h - 1) - lower_h;
+      upper_w = (keff_w - 1) - lower_w;
+    } else {
+      lower_h = (keff_h - 1) / 2; upper_h = (keff_h - 1) - lower_h;
+      lower_w = (keff_w - 1) / 2; upper_w = (keff_w - 1) - lower_w;
+      P = (H + keff_h - 1 - keff_h) / L.stride + 1;
+      Q = (W + keff_w - 1 - keff_w) / L.stride + 1;
+    }
+  } else {  // VALID
+    P = (H - keff_h) / L.stride + 1;
+    Q = (W - keff_w) / L.stride + 1;
+  }
+  *Ho = P;
+  *Wo = Q;
+  const int bn = block_n_override > 0 ? block_n_override : L.block_n;
+  if (L.Npad % bn) return fail(h, DGP_ERR_INVALID, "%s: block_n %d does not divide N %d", L.scope.c_str(), bn, L.Npad);
+  g.M = N * P * Q;
+  g.N = L.Npad;
+  g.block_n = bn;
+  g.num_k_blocks = L.K / kBlockK;
+  g.P = P; g.Q = Q;
+  g.conv_stride = L.stride;
+  g.lower_h = -lower_h; g.lower_w = -lower_w;
+  g.S = L.S; g.dil = L.dil; g.cblocks = L.Cin / kBlockK;
+  g.scale = L.scale; g.shift = L.shift;
+  g.residual = residual; g.res_sub = res_sub; g.res_H = res_H; g.res_W = res_W; g.ldres = L.Npad;
+  g.relu = L.relu ? 1 : 0;
+  g.out = out; g.out_f32 = out_f32 ? 1 : 0; g.ldc = L.Npad;
+  g.num_m_blocks = ceil_div(g.M, kBlockM);
+  g.num_n_blocks = L.Npad / bn;
+  g.num_stages = conv_gemm_pick_stages(bn);
+  g.tmem_cols = tmem_cols_for(bn);
+  const char* e = nullptr;
+  const bool pointwise = (L.R == 1 && L.S == 1 && L.stride == 1);
+  if (pointwise) {
+    g.a_mode = 0;
+    e = make_tmap_2d(&g.tmap_a, x, (uint64_t)g.M, (uint64_t)L.K, (uint64_t)L.K * 2, kBlockM);
+  } else {
+    g.a_mode = 1;
+    const int up_h = upper_h - (L.R - 1) * L.dil, up_w = upper_w - (L.S - 1) * L.dil;
+    e = make_tmap_im2col(&g.tmap_a, x, (uint64_t)L.Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N, (uint64_t)L.Cin * 2,
+                         (uint64_t)W * L.Cin * 2, (uint64_t)H * W * L.Cin * 2, -lower_w, -lower_h, up_w, up_h, L.stride,
+                         (uint64_t)N * H * W * L.Cin * 2);
+  }
+  if (e) return fail(h, DGP_ERR_CUDA, "%s: %s", L.scope.c_str(), e);
+  e = make_tmap_2d(&g.tmap_b, L.w, (uint64_t)L.Npad, (uint64_t)L.K, (uint64_t)L.K * 2, (uint32_t)bn);
+  if (e) return fail(h, DGP_ERR_CUDA, "%s: %s", L.scope.c_str(), e);
+  st->kind = STEP_GEMM;
+  st->out_ptr = out;
+  st->oN = N; st->oH = P; st->oW = Q; st->oC = L.Npad;
+  return DGP_OK;
+}
+
+int build_plan(dgp_handle* h, int B, int H, int W, Plan** out) {
+  auto key = std::make_tuple(B, H, W);
+  auto it = h->plans.find(key);
+  if (it != h->plans.end()) {
+    *out = it->second.get();
+    return DGP_OK;
+  }
+  std::unique_ptr<Plan> pl(new Plan());
+  pl->B = B; pl->H = H; pl->W = W;
+  pl->H1 = ceil_div(H, 2); pl->W1 = ceil_div(W, 2);
+  pl->Hs = pl->H1 + 3; pl->Ws = pl->W1 + 3;
+  int rc;
+  void* p = nullptr;
+  // ---- conv1 (s2d + windowed im2col GEMM)
+  rc = alloc_buf(h, pl.get(), (size_t)B * pl->Hs * pl->Ws * 16 * 2, &p);
+  if (rc) return rc;
+  pl->s2d = (__nv_bfloat16*)p;
+  {
+    Step st; st.kind = STEP_PREP;
+    pl->steps.push_back(st);
+  }
+  // ---- shape pre-pass: sizes of the rotating activation buffers
+  size_t max_x = 0, max_t = 0, max_sc = 0;
+  {
+    int hh, ww, d;
+    same_pad(pl->H1, 3, 2, 1, &d, &hh);
+    same_pad(pl->W1, 3, 2, 1, &d, &ww);
+    max_x = (size_t)hh * ww * 64;
+    int cin = 64;
+    for (const UnitDesc& u : h->units) {
+      const int ho = ceil_div(hh, u.stride), wo = ceil_div(ww, u.stride);
+      if ((size_t)hh * ww * u.base > max_t) max_t = (size_t)hh * ww * u.base;
+      if (cin != u.depth && (size_t)hh * ww * u.depth > max_sc) max_sc = (size_t)hh * ww * u.depth;
+      if ((size_t)ho * wo * u.depth > max_x) max_x = (size_t)ho * wo * u.depth;
+      hh = ho; ww = wo; cin = u.depth;
+    }
+  }
+  const size_t big = (size_t)B * pl->H1 * pl->W1 * 64 * 2;
+  const size_t x_bytes = (size_t)B * max_x * 2 + 1024, t_bytes = (size_t)B * max_t * 2 + 1024,
+               sc_bytes = (size_t)B * max_sc * 2 + 1024;
+  void *c1 = nullptr, *xa = nullptr, *xb = nullptr, *t1 = nullptr, *t2 = nullptr, *sc = nullptr;
+  if ((rc = alloc_buf(h, pl.get(), big, &c1))) return rc;
+  {
+    const ConvLayer& L = h->layers[h->conv1_layer];
+    Step st;
+    memset(&st.gp, 0, sizeof(st.gp));
+    ConvGemmParams& g = st.gp;
+    g.M = B * pl->H1 * pl->W1; g.N = 64; g.block_n = 64; g.num_k_blocks = 4; g.a_mode = 1;
+    g.P = pl->H1; g.Q = pl->W1; g.conv_stride = 1; g.lower_h = 0; g.lower_w = 0; g.S = 1; g.dil = 1; g.cblocks = 1;
+    g.scale = L.scale; g.shift = L.shift; g.residual = nullptr; g.res_sub = 1; g.relu = 1;
+    g.out = c1; g.out_f32 = 0; g.ldc = 64;
+    g.num_m_blocks = ceil_div(g.M, kBlockM); g.num_n_blocks = 1;
+    g.num_stages = conv_gemm_pick_stages(64); g.tmem_cols = tmem_cols_for(64);
+    const char* e = make_tmap_im2col(&g.tmap_a, pl->s2d, 64, (uint64_t)pl->W1, (uint64_t)pl->Hs, (uint64_t)B, 32,
+                                     (uint64_t)pl->Ws * 32, (uint64_t)pl->Hs * pl->Ws * 32, 0, 0, 0, -3, 1,
+                                     (uint64_t)B * pl->Hs * pl->Ws * 32);
+    if (e) return fail(h, DGP_ERR_CUDA, "conv1: %s", e);
+    e = make_tmap_2d(&g.tmap_b, L.w, 64, 256, 512, 64);
+    if (e) return fail(h, DGP_ERR_CUDA, "conv1: %s", e);
+    st.kind = STEP_GEMM; st.end_point = "resnet_v1_50/conv1"; st.out_ptr = c1;
+    st.oN = B; st.oH = pl->H1; st.oW = pl->W1; st.oC = 64;
+    pl->steps.push_back(st);
+  }
+  // ---- pool1
+  int Hc, Wc, pad_t, pad_l;
+  same_pad(pl->H1, 3, 2, 1, &pad_t, &Hc);
+  same_pad(pl->W1, 3, 2, 1, &pad_l, &Wc);
+  if ((rc = alloc_buf(h, pl.get(), x_bytes, &xa))) return rc;
+  if ((rc = alloc_buf(h, pl.get(), x_bytes, &xb))) return rc;
+  if ((rc = alloc_buf(h, pl.get(), sc_bytes, &sc))) return rc;
+  if ((rc = alloc_buf(h, pl.get(), t_bytes, &t1))) return rc;
+  if ((rc = alloc_buf(h, pl.get(), t_bytes, &t2))) return rc;
+  {
+    Step st; st.kind = STEP_POOL;
+    st.pin = (const __nv_bfloat16*)c1; st.pH = pl->H1; st.pW = pl->W1; st.pC = 64; st.pad_t = pad_t; st.pad_l = pad_l;
+    st.end_point = "resnet_v1_50/pool1"; st.out_ptr = xa; st.oN = B; st.oH = Hc; st.oW = Wc; st.oC = 64;
+    pl->steps.push_back(st);
+  }
+  // ---- bottleneck units
+  void* x = xa;
+  void* y = xb;
+  int Cin = 64;
+  for (const UnitDesc& u : h->units) {
+    const void* shortcut = nullptr;
+    int res_sub = 1, res_H = Hc, res_W = Wc;
+    int Ho, Wo, dh, dw;
+    if (u.shortcut >= 0) {
+      Step st;
+      rc = make_gemm_step(h, h->layers[u.shortcut], x, B, Hc, Wc, 0, sc, false, nullptr, 1, 0, 0, 0, &st, &dh, &dw);
+      if (rc) return rc;
+      st.end_point = u.scope + "/shortcut";
+      pl->steps.push_back(st);
+      shortcut = sc;
+    } else {
+      shortcut = x;
+      res_sub = u.stride;
+    }
+    {
+      Step st;
+      rc = make_gemm_step(h, h->layers[u.conv1], x, B, Hc, Wc, 0, t1, false, nullptr, 1, 0, 0, 0, &st, &dh, &dw);
+      if (rc) return rc;
+      st.end_point = u.scope + "/conv1";
+      pl->steps.push_back(st);
+    }
+    {
+      Step st;
+      rc = make_gemm_step(h, h->layers[u.conv2], t1, B, Hc, Wc, 1, t2, false, nullptr, 1, 0, 0, 0, &st, &Ho, &Wo);
+      if (rc) return rc;
+      st.end_point = u.scope + "/conv2";
+      pl->steps.push_back(st);
+    }
+    {
+      Step st;
+      rc = make_gemm_step(h, h->layers[u.conv3], t2, B, Ho, Wo, 0, y, false, (const __nv_bfloat16*)shortcut, res_sub,
+                          res_H, res_W, 0, &st, &dh, &dw);
+      if (rc) return rc;
+      st.end_point = u.scope;
+      pl->steps.push_back(st);
+    }
+    Hc = Ho; Wc = Wo; Cin = u.depth;
+    std::swap(x, y);
+  }
+  (void)Cin;
+  pl->hf = Hc; pl->wf = Wc;
+  // ---- heads: GEMM over feature pixels + col2im
+  {
+    const ConvLayer& L = h->layers[h->head_layer];
+    if ((rc = alloc_buf(h, pl.get(), (size_t)B * Hc * Wc * L.Npad * 4, &p))) return rc;
+    pl->contrib = (float*)p;
+    pl->contrib_ld = L.Npad;
+    Step st;
+    int dh, dw;
+    rc = make_gemm_step(h, L, x, B, Hc, Wc, 0, pl->contrib, true, nullptr, 1, 0, 0, 0, &st, &dh, &dw);
+    if (rc) return rc;
+    pl->steps.push_back(st);
+    Step c; c.kind = STEP_COL2IM;
+    pl->steps.push_back(c);
+  }
+  *out = pl.get();
+  h->plans[key] = std::move(pl);
+  return DGP_OK;
+}
+
+int keep_activation(dgp_handle* h, const Step& st, cudaStream_t s) {
+  if (!h->debug_keep || st.end_point.empty() || !st.out_ptr) return DGP_OK;
+  const size_t bytes = (size_t)st.oN * st.oH * st.oW * st.oC * 2;
+  auto it = h->kept.find(st.end_point);
+  if (it != h->kept.end()) {
+    cudaFree(it->second.p);
+    h->kept.erase(it);
+  }
+  dgp_handle::Kept k;
+  k.N = st.oN; k.H = st.oH; k.W = st.oW; k.C = st.oC;
+  CU_OK(h, cudaMalloc(&k.p, bytes));
+  CU_OK(h, cudaMemcpyAsync(k.p, st.out_ptr, bytes, cudaMemcpyDeviceToDevice, s));
+  h->kept[st.end_point] = k;
+  return DGP_OK;
+}
+
+int ensure(dgp_handle* h, DevBuf* b, size_t bytes) {
+  if (b->bytes >= bytes) return DGP_OK;
+  if (b->p) cudaFree(b->p);
+  b->p = nullptr;
+  b->bytes = 0;
+  CU_OK(h, cudaMalloc(&b->p, bytes));
+  b->bytes = bytes;
+  return DGP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dgp_create(const dgp_config* cfg, dgp_handle** out) {
+  if (!cfg || !out) return fail(nullptr, DGP_ERR_INVALID, "dgp_create: null argument");
+  if (cfg->num_joints < 1 || cfg->num_joints > 256) return fail(nullptr, DGP_ERR_INVALID, "dgp_create: num_joints out of range");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, DGP_ERR_CUDA, "dgp_create: no CUDA device (%s); this library has no CPU fallback",
+                cudaGetErrorString(e));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, DGP_ERR_INVALID, "dgp_create: bad device ordinal");
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, cfg->device);
+  if (e != cudaSuccess) return fail(nullptr, DGP_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10)
+    return fail(nullptr, DGP_ERR_UNSUPPORTED, "dgp_create: device is sm_%d%d; this library only runs on sm_100 (B200)",
+                prop.major, prop.minor);
+  e = cudaSetDevice(cfg->device);
+  if (e != cudaSuccess) return fail(nullptr, DGP_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  if (const char* te = tma_init()) return fail(nullptr, DGP_ERR_CUDA, "dgp_create: %s", te);
+  dgp_handle* h = new dgp_handle();
+  h->cfg = *cfg;
+  if (h->cfg.bn_epsilon <= 0) h->cfg.bn_epsilon = 1e-5f;
+  h->device = cfg->device;
+  h->num_sms = prop.multiProcessorCount;
+  e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete h;
+    return fail(nullptr, DGP_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+  }
+  *out = h;
+  return DGP_OK;
+}
+
+void dgp_destroy(dgp_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  for (auto& L : h->layers) {
+    cudaFree(L.w);
+    cudaFree(L.scale);
+    cudaFree(L.shift);
+  }
+  cudaFree(h->head_bias);
+  for (auto& kv : h->plans)
+    for (auto& b : kv.second->bufs) cudaFree(b.p);
+  for (auto& kv : h->kept) cudaFree(kv.second.p);
+  cudaFree(h->sa_ws);
+  cudaFree(h->st_frames.p);
+  cudaFree(h->st_logits.p);
+  cudaFree(h->st_mu.p);
+  cudaFree(h->st_peak.p);
+  cudaFree(h->st_lik.p);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+const char* dgp_last_error(const dgp_handle* h) { return h ? h->err : g_create_error; }
+
+int dgp_load_weights(dgp_handle* h, const char* name, const void* host_ptr, const int64_t* shape, int ndim, int dtype) {
+  if (!h) return DGP_ERR_INVALID;
+  if (!name || !host_ptr || !shape || ndim < 1 || ndim > 4) return fail(h, DGP_ERR_INVALID, "dgp_load_weights: bad argument");
+  if (dtype != 0) return fail(h, DGP_ERR_UNSUPPORTED, "dgp_load_weights: only float32 (dtype 0) is accepted");
+  if (h->finalized) return fail(h, DGP_ERR_STATE, "dgp_load_weights after dgp_finalize_weights");
+  HostVar v;
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) {
+    if (shape[i] <= 0) return fail(h, DGP_ERR_INVALID, "dgp_load_weights: bad shape for %s", name);
+    v.shape.push_back(shape[i]);
+    n *= (size_t)shape[i];
+  }
+  v.data.assign((const float*)host_ptr, (const float*)host_ptr + n);
+  h->host_vars[name] = std::move(v);
+  return DGP_OK;
+}
+
+int dgp_finalize_weights(dgp_handle* h) {
+  if (!h) return DGP_ERR_INVALID;
+  if (h->finalized) return fail(h, DGP_ERR_STATE, "weights already finalized");
+  CU_OK(h, cudaSetDevice(h->device));
+  int rc = build_conv1_layer(h);
+  if (rc) return rc;
+  // slim resnet_v1_50 + stack_blocks_dense(output_stride=16): see oracle/resnet_v1.py::unit_plan
+  static const struct { const char* name; int base, units, stride; } blocks[4] = {
+      {"block1", 64, 3, 2}, {"block2", 128, 4, 2}, {"block3", 256, 6, 2}, {"block4", 512, 3, 1}};
+  int cin = 64, current_stride = 1, rate = 1;
+  const int target = 4;
+  for (const auto& b : blocks)
+    for (int u = 0; u < b.units; ++u) {
+      const int ustride = (u == b.units - 1) ? b.stride : 1;
+      UnitDesc ud;
+      char sc[128];
+      snprintf(sc, sizeof(sc), "resnet_v1_50/%s/unit_%d/bottleneck_v1", b.name, u + 1);
+      ud.scope = sc; ud.depth = b.base * 4; ud.base = b.base;
+      if (current_stride == target) { ud.stride = 1; ud.rate = rate; rate *= ustride; }
+      else { ud.stride = ustride; ud.rate = 1; current_stride *= ustride; }
+      if (cin != ud.depth) {
+        if (ud.stride != 1) return fail(h, DGP_ERR_UNSUPPORTED, "strided projection shortcut not on this path");
+        if ((rc = build_conv_layer(h, ud.scope + "/shortcut", 1, 1, cin, ud.depth, 1, 1, false, &ud.shortcut))) return rc;
+      }
+      if ((rc = build_conv_layer(h, ud.scope + "/conv1", 1, 1, cin, ud.base, 1, 1, true, &ud.conv1))) return rc;
+      if ((rc = build_conv_layer(h, ud.scope + "/conv2", 3, 3, ud.base, ud.base, ud.stride, ud.rate, true, &ud.conv2))) return rc;
+      if ((rc = build_conv_layer(h, ud.scope + "/conv3", 1, 1, ud.base, ud.depth, 1, 1, true, &ud.conv3))) return rc;
+      cin = ud.depth;
+      h->units.push_back(ud);
+    }
+  if ((rc = build_head_layer(h))) return rc;
+  h->host_vars.clear();
+  h->finalized = true;
+  return DGP_OK;
+}
+
+int dgp_output_dims(int H, int W, int* h_feat, int* w_feat, int* h_out, int* w_out) {
+  if (H < 1 || W < 1) return DGP_ERR_INVALID;
+  int a = H, b = W;
+  for (int i = 0; i < 4; ++i) { a = (a + 1) / 2; b = (b + 1) / 2; }
+  if (h_feat) *h_feat = a;
+  if (w_feat) *w_feat = b;
+  if (h_out) *h_out = 2 * a;
+  if (w_out) *w_out = 2 * b;
+  return DGP_OK;
+}
+
+int dgp_forward(dgp_handle* h, const uint8_t* frames_dev, int B, int H, int W, float* logits_dev, float* locref_dev,
+                void* stream) {
+  if (!h) return DGP_ERR_INVALID;
+  if (!h->finalized) return fail(h, DGP_ERR_STATE, "dgp_forward before dgp_finalize_weights");
+  if (!frames_dev || !logits_dev || B < 1 || H < 32 || W < 32) return fail(h, DGP_ERR_INVALID, "dgp_forward: bad argument");
+  if (locref_dev && !h->cfg.location_refinement) return fail(h, DGP_ERR_INVALID, "dgp_forward: locref requested but the head was not built");
+  CU_OK(h, cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  Plan* pl = nullptr;
+  int rc = build_plan(h, B, H, W, &pl);
+  if (rc) return rc;
+  for (const Step& st : pl->steps) {
+    switch (st.kind) {
+      case STEP_PREP:
+        CU_OK(h, launch_prep_s2d(frames_dev, B, H, W, h->cfg.mean_pixel, pl->s2d, pl->Hs, pl->Ws, s));
+        break;
+      case STEP_GEMM:
+        CU_OK(h, launch_conv_gemm(st.gp, h->num_sms, s));
+        break;
+      case STEP_POOL:
+        CU_OK(h, launch_maxpool3x3s2(st.pin, B, st.pH, st.pW, st.pC, (__nv_bfloat16*)st.out_ptr, st.oH, st.oW, st.pad_t,
+                                     st.pad_l, s));
+        break;
+      case STEP_COL2IM:
+        CU_OK(h, launch_deconv_col2im(pl->contrib, B, pl->hf, pl->wf, pl->contrib_ld, h->ctot, h->cfg.num_joints,
+                                      h->head_bias, logits_dev, locref_dev, s));
+        break;
+    }
+    h->launches++;
+    if ((rc = keep_activation(h, st, s))) return rc;
+  }
+  return DGP_OK;
+}
+
+int dgp_softargmax(dgp_handle* h, const float* logits_dev, const float* locref_dev, int B, int H, int W, int nj,
+                   float gamma, float gauss_len, float* mu_dev, int32_t* peak_dev, float* lik_dev,
+                   int32_t* dlc_peak_dev, float* dlc_pose_dev, void* stream) {
+  if (!h) return DGP_ERR_INVALID;
+  if (B == 0) return DGP_OK;
+  if (!logits_dev || B < 0 || H < 2 || W < 2 || nj < 1) return fail(h, DGP_ERR_INVALID, "dgp_softargmax: bad argument");
+  if ((H & 1) || (W & 1)) return fail(h, DGP_ERR_INVALID, "dgp_softargmax: scoremap dims must be even (they are 2*ceil(./16))");
+  if (gauss_len < 1.0f) return fail(h, DGP_ERR_INVALID, "dgp_softargmax: gauss_len must be >= 1");
+  if (((uintptr_t)logits_dev & 15) != 0) return fail(h, DGP_ERR_INVALID, "dgp_softargmax: logits must be 16-byte aligned");
+  CU_OK(h, cudaSetDevice(h->device));
+  const int splits = softargmax_splits(B, H, h->num_sms);
+  const size_t need = (size_t)B * splits * nj * sizeof(SaPartial);
+  if (need > h->sa_ws_bytes) {
+    if (h->sa_ws) CU_OK(h, cudaFree(h->sa_ws));
+    h->sa_ws = nullptr;
+    h->sa_ws_bytes = 0;
+    CU_OK(h, cudaMalloc(&h->sa_ws, need));
+    h->sa_ws_bytes = need;
+  }
+  CU_OK(h, launch_softargmax(logits_dev, locref_dev, B, H, W, nj, gamma, gauss_len, h->cfg.stride, h->cfg.locref_stdev,
+                             h->sa_ws, splits, mu_dev, peak_dev, lik_dev, dlc_peak_dev, dlc_pose_dev,
+                             (cudaStream_t)stream));
+  h->launches += 2;
+  return DGP_OK;
+}
+
+int dgp_sigmoid(dgp_handle* h, const float* logits_dev, float* prob_dev, size_t n, void* stream) {
+  if (!h) return DGP_ERR_INVALID;
+  if (!logits_dev || !prob_dev || (n % 4)) return fail(h, DGP_ERR_INVALID, "dgp_sigmoid: bad argument");
+  if (n == 0) return DGP_OK;
+  CU_OK(h, cudaSetDevice(h->device));
+  CU_OK(h, launch_sigmoid_map(logits_dev, prob_dev, n, h->num_sms, (cudaStream_t)stream));
+  h->launches++;
+  return DGP_OK;
+}
+
+int dgp_potentials(dgp_handle* h, const float* mu_dev, const float* mu_halo_next_dev, int T, int nj,
+                   const int32_t* edges_dev, int nl, const float* ws_dev, const float* ws_max_dev, float wt_max,
+                   float* skel_dist_dev, float* temporal_dev, float* e_skel_dev, float* e_temp_dev, void* stream) {
+  if (!h) return DGP_ERR_INVALID;
+  if (T == 0) return DGP_OK;
+  if (!mu_dev || T < 0 || nj < 1 || nl < 0 || (nl > 0 && !edges_dev)) return fail(h, DGP_ERR_INVALID, "dgp_potentials: bad argument");
+  if ((ws_dev == nullptr) != (ws_max_dev == nullptr)) return fail(h, DGP_ERR_INVALID, "dgp_potentials: ws and ws_max go together");
+  CU_OK(h, cudaSetDevice(h->device));
+  CU_OK(h, launch_potentials(mu_dev, mu_halo_next_dev, T, nj, edges_dev, nl, h->cfg.stride, ws_dev, ws_max_dev, wt_max,
+                             skel_dist_dev, temporal_dev, e_skel_dev, e_temp_dev, (cudaStream_t)stream));
+  h->launches++;
+  return DGP_OK;
+}
+
+int dgp_estimate_pose_host(dgp_handle* h, const uint8_t* frames_host, int T, int H, int W, int batch, float gamma,
+                           float gauss_len, float* mu_host, int32_t* peak_host, float* lik_host) {
+  if (!h) return DGP_ERR_INVALID;
+  if (!h->finalized) return fail(h, DGP_ERR_STATE, "dgp_estimate_pose_host before dgp_finalize_weights");
+  if (!frames_host || T < 0 || batch < 1 || !mu_host) return fail(h, DGP_ERR_INVALID, "dgp_estimate_pose_host: bad argument");
+  if (T == 0) return DGP_OK;
+  CU_OK(h, cudaSetDevice(h->device));
+  const int nj = h->cfg.num_joints;
+  int hf, wf, ho, wo;
+  dgp_output_dims(H, W, &hf, &wf, &ho, &wo);
+  const size_t frame_bytes = (size_t)H * W * 3;
+  int rc;
+  if ((rc = ensure(h, &h->st_frames, frame_bytes * batch))) return rc;
+  if ((rc = ensure(h, &h->st_logits, (size_t)batch * ho * wo * nj * 4))) return rc;
+  if ((rc = ensure(h, &h->st_mu, (size_t)batch * nj * 2 * 4))) return rc;
+  if ((rc = ensure(h, &h->st_peak, (size_t)batch * nj * 2 * 4))) return rc;
+  if ((rc = ensure(h, &h->st_lik, (size_t)batch * nj * 4))) return rc;
+  cudaStream_t s = h->stream;
+  for (int t0 = 0; t0 < T; t0 += batch) {
+    const int b = (T - t0) < batch ? (T - t0) : batch;
+    CU_OK(h, cudaMemcpyAsync(h->st_frames.p, frames_host + (size_t)t0 * frame_bytes, frame_bytes * b,
+                             cudaMemcpyHostToDevice, s));
+    if ((rc = dgp_forward(h, (const uint8_t*)h->st_frames.p, b, H, W, (float*)h->st_logits.p, nullptr, s))) return rc;
+    if ((rc = dgp_softargmax(h, (const float*)h->st_logits.p, nullptr, b, ho, wo, nj, gamma, gauss_len,
+                             (float*)h->st_mu.p, (int32_t*)h->st_peak.p, (float*)h->st_lik.p, nullptr, nullptr, s)))
+      return rc;
+    CU_OK(h, cudaMemcpyAsync(mu_host + (size_t)t0 * nj * 2, h->st_mu.p, (size_t)b * nj * 2 * 4, cudaMemcpyDeviceToHost, s));
+    if (peak_host)
+      CU_OK(h, cudaMemcpyAsync(peak_host + (size_t)t0 * nj * 2, h->st_peak.p, (size_t)b * nj * 2 * 4, cudaMemcpyDeviceToHost, s));
+    if (lik_host)
+      CU_OK(h, cudaMemcpyAsync(lik_host + (size_t)t0 * nj, h->st_lik.p, (size_t)b * nj * 4, cudaMemcpyDeviceToHost, s));
+  }
+  CU_OK(h, cudaStreamSynchronize(s));
+  return DGP_OK;
+}
+
+int dgp_debug_keep_activations(dgp_handle* h, int enable) {
+  if (!h) return DGP_ERR_INVALID;
+  h->debug_keep = enable != 0;
+  return DGP_OK;
+}
+
+int dgp_debug_get_activation(dgp_handle* h, const char* end_point, float* host_out, size_t max_elems, int64_t* shape4) {
+  if (!h || !end_point) return DGP_ERR_INVALID;
+  auto it = h->kept.find(end_point);
+  if (it == h->kept.end()) return fail(h, DGP_ERR_INVALID, "no kept activation named %s", end_point);
+  const auto& k = it->second;
+  const size_t n = (size_t)k.N * k.H * k.W * k.C;
+  if (shape4) { shape4[0] = k.N; shape4[1] = k.H; shape4[2] = k.W; shape4[3] = k.C; }
+  if (!host_out) return DGP_OK;
+  if (n > max_elems) return fail(h, DGP_ERR_INVALID, "buffer too small for %s", end_point);
+  CU_OK(h, cudaSetDevice(h->device));
+  CU_OK(h, cudaDeviceSynchronize());
+  std::vector<__nv_bfloat16> tmp(n);
+  CU_OK(h, cudaMemcpy(tmp.data(), k.p, n * 2, cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < n; ++i) host_out[i] = __bfloat162float(tmp[i]);
+  return DGP_OK;
+}
+
+int dgp_conv2d(dgp_handle* h, const void* x_dev, int N, int H, int W, int Cin, const float* w_host, int R, int S,
+               int Cout, int stride, int dilation, int pad_mode, const float* scale_host, const float* shift_host,
+               const void* residual_dev, int res_sub, int res_H, int res_W, int relu, void* out_dev, int out_f32,
+               int block_n, void* stream) {
+  if (!h) return DGP_ERR_INVALID;
+  if (!x_dev || !w_host || !out_dev) return fail(h, DGP_ERR_INVALID, "dgp_conv2d: null argument");
+  if (Cin % 64 || Cout % 16) return fail(h, DGP_ERR_UNSUPPORTED, "dgp_conv2d: Cin must be a multiple of 64 and Cout of 16");
+  CU_OK(h, cudaSetDevice(h->device));
+  ConvLayer L;
+  L.scope = "dgp_conv2d"; L.R = R; L.S = S; L.Cin = Cin; L.Cout = Cout; L.stride = stride; L.dil = dilation;
+  L.relu = relu != 0;
+  L.K = R * S * Cin;
+  L.block_n = block_n > 0 ? block_n : pick_block_n(Cout);
+  L.Npad = ceil_div(Cout, L.block_n) * L.block_n;
+  if (L.Npad != Cout) return fail(h, DGP_ERR_INVALID, "dgp_conv2d: block_n must divide Cout");
+  std::vector<__nv_bfloat16> wm((size_t)L.Npad * L.K, __float2bfloat16_rn(0.0f));
+  for (int t = 0; t < R * S; ++t)
+    for (int c = 0; c < Cin; ++c)
+      for (int o = 0; o < Cout; ++o)
+        wm[(size_t)o * L.K + (size_t)t * Cin + c] = __float2bfloat16_rn(w_host[((size_t)t * Cin + c) * Cout + o]);
+  std::vector<float> sc, sh;
+  if (scale_host) sc.assign(scale_host, scale_host + Cout);
+  if (shift_host) sh.assign(shift_host, shift_host + Cout);
+  int rc = upload_layer(h, L, wm, scale_host ? &sc : nullptr, shift_host ? &sh : nullptr);
+  if (rc) return rc;
+  Step st;
+  int Ho, Wo;
+  rc = make_gemm_step(h, L, x_dev, N, H, W, pad_mode, out_dev, out_f32 != 0, (const __nv_bfloat16*)residual_dev,
+                      res_sub > 0 ? res_sub : 1, res_H, res_W, 0, &st, &Ho, &Wo);
+  if (rc == DGP_OK) {
+    cudaError_t e = launch_conv_gemm(st.gp, h->num_sms, (cudaStream_t)stream);
+    h->launches++;
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+    if (e != cudaSuccess) rc = fail(h, DGP_ERR_CUDA, "dgp_conv2d launch: %s", cudaGetErrorString(e));
+  }
+  cudaFree(L.w);
+  cudaFree(L.scale);
+  cudaFree(L.shift);
+  return rc;
+}
+
+int64_t dgp_launch_count(const dgp_handle* h) { return h ? h->launches : 0; }
+int dgp_num_sms(const dgp_handle* h) { return h ? h->num_sms : 0; }
+
+}  // extern "C"

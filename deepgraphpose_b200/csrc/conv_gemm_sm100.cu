@@ -1,0 +1,339 @@
+// Implicit-GEMM convolution on tcgen05 / TMEM / TMA (sm_100a).  See conv_gemm_sm100.cuh.
+//
+// CTA = 192 threads, persistent over (m_blk, n_blk) tiles:
+//   warp 0      TMA producer   (one lane): A tile 128 x 64 (tiled or im2col) + B tile block_n x 64 per stage
+//   warp 1      MMA issuer     (one lane): 4 x tcgen05.mma (K=16) per stage into a double-buffered TMEM accumulator
+//   warps 2..5  epilogue: tcgen05.ld -> fp32 BN scale/shift (+residual)(+ReLU) -> bf16/fp32 global stores
+// Pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty pair (MMA <-> epilogue).
+#include "conv_gemm_sm100.cuh"
+
+#include <stdio.h>
+
+#include "ptx_sm100.cuh"
+
+namespace dgp {
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KiB
+constexpr int kMaxStages = 8;
+
+__device__ __forceinline__ float bf16lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf16hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int stages = p.num_stages;
+  const int b_bytes = p.block_n * kBlockK * 2;
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + stages * kABytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + stages * b_bytes);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tmem_full_bar = empty_bar + kMaxStages;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&p.tmap_a);
+    ptx::prefetch_tmap(&p.tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < stages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tmem_full_bar[a], 1);
+      ptx::mbar_init(&tmem_empty_bar[a], 4);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ TMA producer
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = (uint32_t)(kABytes + b_bytes);
+      const int PQ = p.P * p.Q;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / p.num_n_blocks;
+        const int n_blk = tile - m_blk * p.num_n_blocks;
+        const int m0 = m_blk * kBlockM;
+        const int n0 = n_blk * p.block_n;
+        int img = 0, cw = 0, ch = 0;
+        if (p.a_mode == 1) {
+          img = m0 / PQ;
+          const int rem = m0 - img * PQ;
+          const int pp = rem / p.Q;
+          const int qq = rem - pp * p.Q;
+          cw = qq * p.conv_stride + p.lower_w;
+          ch = pp * p.conv_stride + p.lower_h;
+        }
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+          if (p.a_mode == 0) {
+            ptx::tma_load_2d(smem_a + stage * kABytes, &p.tmap_a, &full_bar[stage], kb * kBlockK, m0);
+          } else {
+            const int tap = kb / p.cblocks;
+            const int c0 = (kb - tap * p.cblocks) * kBlockK;
+            const int r = tap / p.S;
+            const int s = tap - r * p.S;
+            ptx::tma_load_im2col_4d(smem_a + stage * kABytes, &p.tmap_a, &full_bar[stage], c0, cw, ch, img,
+                                    (uint16_t)(s * p.dil), (uint16_t)(r * p.dil));
+          }
+          ptx::tma_load_2d(smem_b + stage * b_bytes, &p.tmap_b, &full_bar[stage], kb * kBlockK, n0);
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ MMA issuer
+      const uint32_t idesc = ptx::make_idesc_bf16_f32(kBlockM, p.block_n);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.block_n);
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint64_t adesc = ptx::make_desc_k_sw128(ptx::smem_u32(smem_a + stage * kABytes));
+          const uint64_t bdesc = ptx::make_desc_k_sw128(ptx::smem_u32(smem_b + stage * b_bytes));
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
+            ptx::umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          }
+          ptx::umma_commit(&empty_bar[stage]);
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        ptx::umma_commit(&tmem_full_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // -------------------------------------------------------------- epilogue (warps 2..5)
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int PQ = p.P * p.Q;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / p.num_n_blocks;
+      const int n_blk = tile - m_blk * p.num_n_blocks;
+      const int row = m_blk * kBlockM + quad * 32 + lane;
+      const int n0 = n_blk * p.block_n;
+      const bool row_ok = row < p.M;
+      size_t res_row = 0;
+      if (p.residual != nullptr && row_ok) {
+        if (p.res_sub == 1) {
+          res_row = (size_t)row;
+        } else {
+          const int img = row / PQ;
+          const int rem = row - img * PQ;
+          const int pp = rem / p.Q;
+          const int qq = rem - pp * p.Q;
+          res_row = ((size_t)img * p.res_H + (size_t)pp * p.res_sub) * p.res_W + (size_t)qq * p.res_sub;
+        }
+      }
+      ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.block_n);
+      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+        uint32_t v[16];
+        ptx::tmem_ld_x16(taddr + (uint32_t)c0, v);
+        ptx::tmem_ld_wait();
+        if (row_ok) {
+          float f[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+          const int n = n0 + c0;
+          if (p.scale != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + n + i));
+              f[i] *= sc.x; f[i + 1] *= sc.y; f[i + 2] *= sc.z; f[i + 3] *= sc.w;
+            }
+          }
+          if (p.shift != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + n + i));
+              f[i] += sh.x; f[i + 1] += sh.y; f[i + 2] += sh.z; f[i + 3] += sh.w;
+            }
+          }
+          if (p.residual != nullptr) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + res_row * (size_t)p.ldres + n);
+            const uint4 r0 = __ldg(rp);
+            const uint4 r1 = __ldg(rp + 1);
+            const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              f[2 * i] += bf16lo(rr[i]);
+              f[2 * i + 1] += bf16hi(rr[i]);
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.0f);
+          }
+          if (p.out_f32) {
+            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)row * p.ldc + n);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) op[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+          } else {
+            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldc + n);
+            op[0] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+            op[1] = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]),
+                               pack_bf16(f[14], f[15]));
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*,
+                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                   CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode_tiled = nullptr;
+EncodeIm2colFn g_encode_im2col = nullptr;
+char g_err[256];
+
+}  // namespace
+
+const char* tma_init() {
+  if (g_encode_tiled && g_encode_im2col) return nullptr;
+  cudaDriverEntryPointQueryResult q;
+  void* fn = nullptr;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) return "cuTensorMapEncodeTiled not available";
+  g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
+  fn = nullptr;
+  e = cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &q);
+  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) return "cuTensorMapEncodeIm2col not available";
+  g_encode_im2col = reinterpret_cast<EncodeIm2colFn>(fn);
+  return nullptr;
+}
+
+const char* make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t k, uint64_t row_stride_bytes,
+                         uint32_t box_rows) {
+  if (const char* e = tma_init()) return e;
+  cuuint64_t dims[2] = {k, rows};
+  cuuint64_t strides[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)kBlockK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode_tiled(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_err, sizeof(g_err), "cuTensorMapEncodeTiled failed: %d (rows=%llu k=%llu stride=%llu box_rows=%u)", (int)r,
+             (unsigned long long)rows, (unsigned long long)k, (unsigned long long)row_stride_bytes, box_rows);
+    return g_err;
+  }
+  return nullptr;
+}
+
+const char* make_tmap_im2col(CUtensorMap* out, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t N,
+                             uint64_t stride_w_bytes, uint64_t stride_h_bytes, uint64_t stride_n_bytes, int lower_w,
+                             int lower_h, int upper_w, int upper_h, int conv_stride, uint64_t total_bytes) {
+  if (const char* e = tma_init()) return e;
+  cuuint64_t dims[4] = {C, W, H, N};
+  cuuint64_t strides[3] = {stride_w_bytes, stride_h_bytes, stride_n_bytes};
+  int lower[2] = {lower_w, lower_h};
+  int upper[2] = {upper_w, upper_h};
+  cuuint32_t estr[4] = {1, (cuuint32_t)conv_stride, (cuuint32_t)conv_stride, 1};
+  CUresult r = g_encode_im2col(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, lower,
+                               upper, (cuuint32_t)kBlockK, (cuuint32_t)kBlockM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_err, sizeof(g_err),
+             "cuTensorMapEncodeIm2col failed: %d (C=%llu W=%llu H=%llu N=%llu sw=%llu sh=%llu sn=%llu lo=(%d,%d) up=(%d,%d) s=%d)",
+             (int)r, (unsigned long long)C, (unsigned long long)W, (unsigned long long)H, (unsigned long long)N,
+             (unsigned long long)stride_w_bytes, (unsigned long long)stride_h_bytes, (unsigned long long)stride_n_bytes,
+             lower_w, lower_h, upper_w, upper_h, conv_stride);
+    return g_err;
+  }
+  // Same driver quirk CUTLASS works around (copy_traits_sm90_im2col.hpp): for tensors < 128 KiB, drivers <= 13.1
+  // set a descriptor bit that breaks im2col loads.
+  int drv = 0;
+  cudaDriverGetVersion(&drv);
+  if (drv <= 13010 && total_bytes < 131072) reinterpret_cast<uint64_t*>(out)[1] &= ~(1ull << 21);
+  return nullptr;
+}
+
+size_t conv_gemm_smem_bytes(int block_n, int num_stages) {
+  return 1024 + (size_t)num_stages * (kABytes + (size_t)block_n * kBlockK * 2) + (2 * kMaxStages + 4) * 8 + 16;
+}
+
+int conv_gemm_pick_stages(int block_n) {
+  const size_t budget = 227 * 1024;
+  int s = kMaxStages;
+  while (s > 2 && conv_gemm_smem_bytes(block_n, s) > budget) --s;
+  return s;
+}
+
+cudaError_t launch_conv_gemm(const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int tiles = p.num_m_blocks * p.num_n_blocks;
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  const size_t smem = conv_gemm_smem_bytes(p.block_n, p.num_stages);
+  conv_gemm_kernel<<<grid, kThreads, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace dgp

@@ -1,0 +1,69 @@
+// Implicit-GEMM convolution on tcgen05 tensor cores (sm_100a) -- host-visible declarations.
+//
+// One kernel serves every GEMM-shaped layer of the DLC ResNet-50 pose net
+// (reference: slim resnet_v1_50 called at
+//  /root/reference/src/DeepLabCut/deeplabcut/pose_estimation_tensorflow/nnet/pose_net.py:50-52 and the
+//  deconv heads at pose_net.py:18-26):
+//    D[m, n] = sum_k A[m, k] * B[n, k],  m = output pixel (n_img, p, q) linearised, n = output channel,
+//    k = (r, s, c) with the channel innermost.
+//  A is fetched by TMA either as a plain [M, K] matrix (1x1 convs, deconv-as-GEMM) or in im2col mode
+//  (3x3 convs with stride / dilation / TF padding, and conv1 after the space-to-depth transform);
+//  B (weights, [Cout, K] K-major bf16) is a plain 2-D TMA tile.  Accumulation is fp32 in TMEM; the
+//  epilogue applies the frozen-BN scale/shift in fp32, adds the (optionally 2x-subsampled) residual,
+//  applies ReLU and stores bf16 (or fp32 for the head GEMM).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dgp {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
+
+struct ConvGemmParams {
+  CUtensorMap tmap_a;
+  CUtensorMap tmap_b;
+  int M;             // output pixels
+  int N;             // output channels (multiple of block_n)
+  int block_n;       // UMMA N (multiple of 16, 16..256)
+  int num_k_blocks;  // K / 64
+  int a_mode;        // 0 = tiled [M,K], 1 = im2col
+  // im2col geometry (a_mode == 1)
+  int P, Q;          // output height / width
+  int conv_stride;
+  int lower_h, lower_w;  // TMA lower corner = -pad_beg
+  int S;             // filter width (taps are enumerated r-major: tap = r * S + s)
+  int dil;
+  int cblocks;       // Cin / 64
+  // epilogue
+  const float* scale;  // [N] or nullptr (=1)
+  const float* shift;  // [N] or nullptr (=0)
+  const __nv_bfloat16* residual;  // nullptr = none
+  int res_sub;       // 1 = same pixel grid as the output, 2 = residual grid is (res_H, res_W), read at (2p, 2q)
+  int res_H, res_W;
+  int ldres;         // residual row stride (elements)
+  int relu;
+  void* out;         // bf16 or fp32, row-major [M, ldc]
+  int out_f32;
+  int ldc;
+  int num_m_blocks, num_n_blocks;
+  int num_stages;
+  int tmem_cols;     // power of two >= 2 * block_n
+};
+
+// Host helpers (conv_gemm_sm100.cu)
+const char* tma_init();  // resolves the driver's tensor-map encoders; returns nullptr on success, else an error string
+// [rows, k] row-major bf16 matrix, box = [box_rows, 64], SWIZZLE_128B.
+const char* make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t k, uint64_t row_stride_bytes,
+                         uint32_t box_rows);
+// NHWC-like activation tensor for im2col loads: dims (C, W, H, N) with explicit byte strides for W, H, N.
+const char* make_tmap_im2col(CUtensorMap* out, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t N,
+                             uint64_t stride_w_bytes, uint64_t stride_h_bytes, uint64_t stride_n_bytes, int lower_w,
+                             int lower_h, int upper_w, int upper_h, int conv_stride, uint64_t total_bytes);
+size_t conv_gemm_smem_bytes(int block_n, int num_stages);
+int conv_gemm_pick_stages(int block_n);
+cudaError_t launch_conv_gemm(const ConvGemmParams& p, int num_sms, cudaStream_t stream);
+
+}  // namespace dgp

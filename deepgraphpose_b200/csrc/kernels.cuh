@@ -1,0 +1,36 @@
+// Launchers of the bandwidth-class kernels (softargmax.cu, aux_kernels.cu).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dgp {
+
+struct SaPartial {  // per (frame, row-split, joint) partial of the online softmax + DLC peak search
+  float m, s0, sr, sc, bsig;
+  int bidx;
+  int pad0, pad1;
+};
+
+int softargmax_tact(int nj);
+int softargmax_splits(int B, int H, int num_sms);
+cudaError_t launch_softargmax(const float* logits, const float* locref, int B, int H, int W, int nj, float gamma,
+                              float gauss_len, float stride, float locref_stdev, SaPartial* workspace, int splits,
+                              float* mu, int* peak, float* lik, int* dlc_peak, float* dlc_pose, cudaStream_t stream);
+cudaError_t launch_sigmoid_map(const float* x, float* y, size_t n, int num_sms, cudaStream_t stream);
+cudaError_t launch_potentials(const float* mu, const float* halo_next, int T, int nj, const int* edges, int nl,
+                              float stride, const float* ws, const float* ws_max, float wt_max, float* skel,
+                              float* temporal, float* e_skel, float* e_temp, cudaStream_t stream);
+
+// u8 RGB frames (N,H,W,3) -> mean-subtracted, zero-padded, space-to-depth bf16 (N,Hs,Ws,16), Hs=ceil(H/2)+3.
+cudaError_t launch_prep_s2d(const uint8_t* frames, int N, int H, int W, const float* mean3, __nv_bfloat16* out,
+                            int Hs, int Ws, cudaStream_t stream);
+// 3x3 stride-2 max-pool with TF SAME padding on NHWC bf16 (C multiple of 8).
+cudaError_t launch_maxpool3x3s2(const __nv_bfloat16* in, int N, int H, int W, int C, __nv_bfloat16* out, int Ho,
+                                int Wo, int pad_t, int pad_l, cudaStream_t stream);
+// col2im of the head GEMM: contrib (N*h*w, ldn) fp32 with column (kh*3+kw)*ctot + co ->
+// part logits (N,2h,2w,nj) [+ locref (N,2h,2w,2nj)] with bias.
+cudaError_t launch_deconv_col2im(const float* contrib, int N, int h, int w, int ldn, int ctot, int nj,
+                                 const float* bias, float* logits, float* locref, cudaStream_t stream);
+
+}  // namespace dgp

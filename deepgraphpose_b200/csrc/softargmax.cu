@@ -1,0 +1,366 @@
+// Fused DGP soft-argmax / peak / likelihood read-out and pairwise potentials (bandwidth-class kernels, sm_100a).
+//
+// Reference semantics (citations relative to /root/reference):
+//   argmax_2d_from_cm        src/deepgraphpose/models/fitdgp_util.py:342-402  (softmax -> zero-padded Gaussian blur ->
+//                            renormalise -> expectation of (row, col))
+//   estimate_pose read-out   src/deepgraphpose/models/eval.py:331-343         (<=2x2 window around mu, literal
+//                            exp(x)/(exp(x)+1) sigmoid, first-max peak, likelihood)
+//   argmax_pose_predict      src/DeepLabCut/deeplabcut/pose_estimation_tensorflow/nnet/predict.py:62-77
+//   skeleton / temporal      src/deepgraphpose/models/fitdgp.py:1063-1069, 1079-1083
+//
+// The blur is never materialised: sum_ij blur(p)[i,j] * f(i,j) == sum_ij p[i,j] * (K^T f)[i,j], and for f in
+// {1, row, col} the transposed blur of f is separable and equals f in the interior, so one pass over the logits
+// with per-row / per-column border weights gives all three sums.  The logit map is read exactly once from HBM
+// (128-bit loads); the softmax is computed online (running max).
+#include "kernels.cuh"
+
+#include <math_constants.h>
+
+namespace dgp {
+
+namespace {
+
+constexpr int kSaThreads = 256;
+
+struct Acc {
+  float m, s0, sr, sc, bsig;
+  int bidx;
+};
+
+__device__ __forceinline__ float sigmoid_tf(float x) { return 1.0f / (1.0f + expf(-x)); }
+// eval.py:335-336 -- the literal formula (NaN for x > ~88.7, exactly like numpy fp32)
+__device__ __forceinline__ float sigmoid_literal(float x) {
+  const float e = expf(x);
+  return e / (e + 1.0f);
+}
+
+__device__ __forceinline__ void acc_init(Acc& a) {
+  a.m = -CUDART_INF_F;
+  a.s0 = a.sr = a.sc = 0.0f;
+  a.bsig = -1.0f;
+  a.bidx = 0x7fffffff;
+}
+
+__device__ __forceinline__ void acc_merge(Acc& a, const Acc& b) {
+  if (b.m != -CUDART_INF_F) {
+    if (a.m == -CUDART_INF_F) {
+      a.m = b.m; a.s0 = b.s0; a.sr = b.sr; a.sc = b.sc;
+    } else {
+      const float m = fmaxf(a.m, b.m);
+      const float fa = __expf(a.m - m), fb = __expf(b.m - m);
+      a.s0 = a.s0 * fa + b.s0 * fb;
+      a.sr = a.sr * fa + b.sr * fb;
+      a.sc = a.sc * fa + b.sc * fb;
+      a.m = m;
+    }
+  }
+  if (b.bsig > a.bsig || (b.bsig == a.bsig && b.bidx < a.bidx)) {
+    a.bsig = b.bsig;
+    a.bidx = b.bidx;
+  }
+}
+
+// One CTA handles rows [r0, r1) of one frame for ALL joints (NHWC: the joint is the fastest axis).
+// `tact` threads are active with 4*tact % nj == 0, so every thread's four float4 lanes keep a fixed joint.
+__global__ void __launch_bounds__(kSaThreads) softargmax_partial_kernel(
+    const float* __restrict__ logits, int H, int W, int nj, float gamma, int radius, float sigma, int rows_per_split,
+    int splits, int tact, SaPartial* __restrict__ part) {
+  extern __shared__ float sm[];
+  float* Ah = sm;          // [H]  sum of valid taps
+  float* Rh = Ah + H;      // [H]  sum of valid taps * source row
+  float* Aw = Rh + H;      // [W]
+  float* Rw = Aw + W;      // [W]
+  float* red = Rw + W;     // [4*tact][6]
+
+  const int b = blockIdx.x / splits;
+  const int sp = blockIdx.x - b * splits;
+  const int r0 = sp * rows_per_split;
+  const int r1 = min(H, r0 + rows_per_split);
+  const int tid = threadIdx.x;
+
+  // 1-D Gaussian taps (make_gaussian_2d_kernel: exp(-0.5 (d/sigma)^2) normalised), border-aware sums.
+  float knorm = 0.0f;
+  for (int d = -radius; d <= radius; ++d) knorm += expf(-0.5f * (d / sigma) * (d / sigma));
+  for (int i = tid; i < H + W; i += blockDim.x) {
+    const bool is_h = i < H;
+    const int pos = is_h ? i : i - H;
+    const int n = is_h ? H : W;
+    float a = 0.0f, r = 0.0f;
+    for (int d = -radius; d <= radius; ++d) {
+      const int dst = pos - d;  // blurred-map index that receives source `pos` through tap d
+      if (dst >= 0 && dst < n) {
+        const float k = expf(-0.5f * (d / sigma) * (d / sigma)) / knorm;
+        a += k;
+        r += k * (float)dst;
+      }
+    }
+    if (is_h) { Ah[pos] = a; Rh[pos] = r; } else { Aw[pos] = a; Rw[pos] = r; }
+  }
+  __syncthreads();
+
+  Acc acc[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) acc_init(acc[q]);
+
+  const int L = 4 * tact;
+  if (tid < tact) {
+    const int dP = L / nj;
+    const int dPr = dP / W, dPc = dP - dPr * W;
+    int row[4], col[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int e = 4 * tid + q;
+      const int pix = e / nj;
+      row[q] = r0 + pix / W;
+      col[q] = pix - (pix / W) * W;
+    }
+    const long long n_elems = (long long)(r1 - r0) * W * nj;
+    const float4* src = reinterpret_cast<const float4*>(logits + ((size_t)b * H + r0) * (size_t)W * nj);
+    for (long long off = 4 * tid; off < n_elems; off += 4LL * L) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long o = off + (long long)u * L;
+        if (o < n_elems) v[u] = __ldcs(src + (o >> 2));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long o = off + (long long)u * L;
+        if (o < n_elems) {
+          const float xs[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            Acc& a = acc[q];
+            const float x = xs[q];
+            const float xg = x * gamma;
+            if (xg > a.m) {
+              const float f = __expf(a.m - xg);  // exp(-inf) = 0 on the first element
+              a.s0 *= f; a.sr *= f; a.sc *= f;
+              a.m = xg;
+            }
+            const float e = __expf(xg - a.m);
+            const float ah = Ah[row[q]], aw = Aw[col[q]];
+            a.s0 += e * ah * aw;
+            a.sr += e * Rh[row[q]] * aw;
+            a.sc += e * ah * Rw[col[q]];
+            // DLC global peak: first max of sigmoid(x).  Only elements that can still tie with the running
+            // maximum need the exact sigmoid (see DESIGN.md "peak candidates").
+            const float xbest_floor = fminf(a.bsig >= 0.0f ? a.m / gamma - 2.0f : -CUDART_INF_F, 14.0f);
+            if (gamma <= 0.0f || x >= xbest_floor) {
+              const float s = sigmoid_tf(x);
+              const int idx = row[q] * W + col[q];
+              if (s > a.bsig || (s == a.bsig && idx < a.bidx)) { a.bsig = s; a.bidx = idx; }
+            }
+            col[q] += dPc; row[q] += dPr;
+            if (col[q] >= W) { col[q] -= W; row[q] += 1; }
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            col[q] += dPc; row[q] += dPr;
+            if (col[q] >= W) { col[q] -= W; row[q] += 1; }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float* r = red + (size_t)(4 * tid + q) * 6;
+      r[0] = acc[q].m; r[1] = acc[q].s0; r[2] = acc[q].sr; r[3] = acc[q].sc; r[4] = acc[q].bsig;
+      r[5] = __int_as_float(acc[q].bidx);
+    }
+  }
+  __syncthreads();
+
+  const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+  for (int j = warp; j < nj; j += nwarps) {
+    Acc a;
+    acc_init(a);
+    for (int e = j + nj * lane; e < L; e += nj * 32) {
+      const float* r = red + (size_t)e * 6;
+      Acc t;
+      t.m = r[0]; t.s0 = r[1]; t.sr = r[2]; t.sc = r[3]; t.bsig = r[4]; t.bidx = __float_as_int(r[5]);
+      acc_merge(a, t);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      Acc t;
+      t.m = __shfl_xor_sync(0xffffffffu, a.m, o);
+      t.s0 = __shfl_xor_sync(0xffffffffu, a.s0, o);
+      t.sr = __shfl_xor_sync(0xffffffffu, a.sr, o);
+      t.sc = __shfl_xor_sync(0xffffffffu, a.sc, o);
+      t.bsig = __shfl_xor_sync(0xffffffffu, a.bsig, o);
+      t.bidx = __shfl_xor_sync(0xffffffffu, a.bidx, o);
+      acc_merge(a, t);
+    }
+    if (lane == 0) {
+      SaPartial& o = part[((size_t)b * splits + sp) * nj + j];
+      o.m = a.m; o.s0 = a.s0; o.sr = a.sr; o.sc = a.sc; o.bsig = a.bsig; o.bidx = a.bidx;
+    }
+  }
+}
+
+// One thread per (frame, joint): merge the row-split partials, then the O(1) read-outs.
+__global__ void softargmax_finalize_kernel(const float* __restrict__ logits, const float* __restrict__ locref, int B,
+                                           int H, int W, int nj, int splits, const SaPartial* __restrict__ part,
+                                           float stride, float locref_stdev, float* __restrict__ mu,
+                                           int* __restrict__ peak, float* __restrict__ lik, int* __restrict__ dlc_peak,
+                                           float* __restrict__ dlc_pose) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B * nj) return;
+  const int b = t / nj, j = t - b * nj;
+  Acc a;
+  acc_init(a);
+  for (int sp = 0; sp < splits; ++sp) {
+    const SaPartial& p = part[((size_t)b * splits + sp) * nj + j];
+    Acc q;
+    q.m = p.m; q.s0 = p.s0; q.sr = p.sr; q.sc = p.sc; q.bsig = p.bsig; q.bidx = p.bidx;
+    acc_merge(a, q);
+  }
+  const float mur = a.sr / a.s0, muc = a.sc / a.s0;  // 0/0 -> NaN, as softmax_tensor / (sum + 1e-100) in fp32
+  if (mu) { mu[2 * t] = mur; mu[2 * t + 1] = muc; }
+  const float* fr = logits + (size_t)b * H * W * nj + j;
+
+  if (peak || lik) {
+    int pr = -1, pc = -1;
+    float best = CUDART_NAN_F;
+    if (mur == mur && muc == muc) {
+      // numpy slice [floor : ceil+1] clipped to the array
+      const int rlo = max((int)floorf(mur), 0), rhi = min((int)ceilf(mur) + 1, H);
+      const int clo = max((int)floorf(muc), 0), chi = min((int)ceilf(muc) + 1, W);
+      bool have = false, have_nan = false;
+      for (int r = rlo; r < rhi && !have_nan; ++r)
+        for (int c = clo; c < chi; ++c) {
+          const float s = sigmoid_literal(fr[((size_t)r * W + c) * nj]);
+          if (s != s) { pr = r; pc = c; best = s; have_nan = true; break; }  // np.argmax: first NaN wins
+          if (!have || s > best) { best = s; pr = r; pc = c; have = true; }
+        }
+    }
+    if (peak) { peak[2 * t] = pr; peak[2 * t + 1] = pc; }
+    if (lik) lik[t] = best;
+  }
+  if (dlc_peak || dlc_pose) {
+    const int r = a.bidx / W, c = a.bidx - r * W;
+    if (dlc_peak) { dlc_peak[2 * t] = r; dlc_peak[2 * t + 1] = c; }
+    if (dlc_pose) {
+      float dx = 0.0f, dy = 0.0f;
+      if (locref) {
+        const float* lp = locref + (((size_t)b * H + r) * W + c) * (size_t)(2 * nj) + 2 * j;
+        dx = lp[0] * locref_stdev;
+        dy = lp[1] * locref_stdev;
+      }
+      dlc_pose[3 * t] = (float)c * stride + 0.5f * stride + dx;
+      dlc_pose[3 * t + 1] = (float)r * stride + 0.5f * stride + dy;
+      dlc_pose[3 * t + 2] = a.bsig;
+    }
+  }
+}
+
+// sigmoid scoremap (PoseNet.test, pose_net.py:84-90) -- only materialised when a caller asks for it.
+__global__ void sigmoid_map_kernel(const float4* __restrict__ x, float4* __restrict__ y, size_t n4) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldcs(x + i);
+    y[i] = make_float4(sigmoid_tf(v.x), sigmoid_tf(v.y), sigmoid_tf(v.z), sigmoid_tf(v.w));
+  }
+}
+
+// Skeleton distances and temporal differences on the soft-argmax coordinates.  One thread per frame.
+__global__ void potentials_kernel(const float* __restrict__ mu, const float* __restrict__ halo_next, int T, int nj,
+                                  const int* __restrict__ edges, int nl, float stride, const float* __restrict__ ws,
+                                  const float* __restrict__ ws_max, float wt_max, float* __restrict__ skel,
+                                  float* __restrict__ temporal, float* __restrict__ e_skel,
+                                  float* __restrict__ e_temp) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const float* m = mu + (size_t)t * nj * 2;
+  float es = 0.0f;
+  for (int l = 0; l < nl; ++l) {
+    const int a = edges[2 * l], b = edges[2 * l + 1];
+    // S (mu*stride + stride/2): the +stride/2 cancels between the +1 and -1 entries only in exact arithmetic;
+    // keep the reference's order of operations.
+    const float dr = (m[2 * a] * stride + 0.5f * stride) - (m[2 * b] * stride + 0.5f * stride);
+    const float dc = (m[2 * a + 1] * stride + 0.5f * stride) - (m[2 * b + 1] * stride + 0.5f * stride);
+    const float d = sqrtf(dr * dr + dc * dc);
+    if (skel) skel[(size_t)l * T + t] = d;
+    if (ws) es += ws[l] * (fmaxf(d - ws_max[l], 0.0f) + ws_max[l]);
+  }
+  if (e_skel) e_skel[t] = es;
+  const float* mn = (t + 1 < T) ? m + (size_t)nj * 2 : halo_next;
+  if (mn != nullptr) {
+    float et = 0.0f;
+    for (int j = 0; j < nj; ++j) {
+      const float dr = (m[2 * j] * stride + 0.5f * stride) - (mn[2 * j] * stride + 0.5f * stride);
+      const float dc = (m[2 * j + 1] * stride + 0.5f * stride) - (mn[2 * j + 1] * stride + 0.5f * stride);
+      const float d = sqrtf(dr * dr + dc * dc);
+      if (temporal) temporal[(size_t)t * nj + j] = d;
+      const float dth = fmaxf(d - wt_max, 0.0f) + wt_max;
+      et += dth * dth;
+    }
+    if (e_temp) e_temp[t] = et;
+  } else if (e_temp) {
+    e_temp[t] = 0.0f;
+  }
+}
+
+}  // namespace
+
+int softargmax_tact(int nj) {
+  // largest thread count <= 256 with 4*t % nj == 0
+  int g = nj;
+  for (int a = 4, b = nj; b;) { int r = a % b; a = b; b = r; g = a; }
+  const int step = nj / g;  // t must be a multiple of nj / gcd(nj, 4)
+  int t = (kSaThreads / step) * step;
+  return t;
+}
+
+int softargmax_splits(int B, int H, int num_sms) {
+  int splits = (3 * num_sms + B - 1) / B;
+  const int max_splits = (H + 7) / 8;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  return splits;
+}
+
+cudaError_t launch_softargmax(const float* logits, const float* locref, int B, int H, int W, int nj, float gamma,
+                              float gauss_len, float stride, float locref_stdev, SaPartial* workspace, int splits,
+                              float* mu, int* peak, float* lik, int* dlc_peak, float* dlc_pose, cudaStream_t stream) {
+  if (B <= 0) return cudaSuccess;
+  const int tact = softargmax_tact(nj);
+  if (tact <= 0 || (H & 1) || (W & 1)) return cudaErrorInvalidValue;
+  int rows_per_split = (H + splits - 1) / splits;
+  rows_per_split = (rows_per_split + 1) & ~1;  // even row boundaries keep the float4 loads 16 B aligned
+  const int real_splits = (H + rows_per_split - 1) / rows_per_split;
+  const int radius = (int)gauss_len;
+  const size_t smem = (size_t)(2 * H + 2 * W) * 4 + (size_t)4 * tact * 6 * 4;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(softargmax_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  softargmax_partial_kernel<<<B * real_splits, kSaThreads, smem, stream>>>(logits, H, W, nj, gamma, radius, gauss_len,
+                                                                          rows_per_split, real_splits, tact, workspace);
+  const int n = B * nj;
+  softargmax_finalize_kernel<<<(n + 127) / 128, 128, 0, stream>>>(logits, locref, B, H, W, nj, real_splits, workspace,
+                                                                  stride, locref_stdev, mu, peak, lik, dlc_peak, dlc_pose);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sigmoid_map(const float* x, float* y, size_t n, int num_sms, cudaStream_t stream) {
+  if (n % 4) return cudaErrorInvalidValue;
+  const size_t n4 = n / 4;
+  int grid = (int)((n4 + 255) / 256);
+  if (grid > num_sms * 8) grid = num_sms * 8;
+  if (grid < 1) grid = 1;
+  sigmoid_map_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y), n4);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_potentials(const float* mu, const float* halo_next, int T, int nj, const int* edges, int nl,
+                              float stride, const float* ws, const float* ws_max, float wt_max, float* skel,
+                              float* temporal, float* e_skel, float* e_temp, cudaStream_t stream) {
+  if (T <= 0) return cudaSuccess;
+  potentials_kernel<<<(T + 127) / 128, 128, 0, stream>>>(mu, halo_next, T, nj, edges, nl, stride, ws, ws_max, wt_max,
+                                                         skel, temporal, e_skel, e_temp);
+  return cudaGetLastError();
+}
+
+}  // namespace dgp

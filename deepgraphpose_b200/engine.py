@@ -1,0 +1,203 @@
+"""Thin host-side wrapper of the C ABI: PyTorch supplies device memory and streams, nothing else.
+
+``Engine`` is the object behind the reference-shaped shims (``pose_net.PoseNet``, ``fitdgp_util.argmax_2d_from_cm``,
+``eval.setup_dgp_eval_graph`` / ``estimate_pose``).  Every method ends in a call into libdgp_b200.so.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import DgpConfig, DgpError, check
+
+MEAN_PIXEL = (123.68, 116.779, 103.939)  # PTF/default_config.py:23
+STRIDE = 8.0                             # PTF/default_config.py:18
+LOCREF_STDEV = 7.2801                    # PTF/default_config.py:29
+
+
+def output_dims(H, W):
+    """(h_feat, w_feat), (h_out, w_out) -- closed form of Dataset._compute_pred_dims (dataset.py:348-371)."""
+    lib = _lib.load()
+    a, b, c, d = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    check(lib.dgp_output_dims(int(H), int(W), C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+    return (a.value, b.value), (c.value, d.value)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class Engine:
+    def __init__(self, num_joints, location_refinement=True, device=None, stride=STRIDE, locref_stdev=LOCREF_STDEV,
+                 mean_pixel=MEAN_PIXEL):
+        if not torch.cuda.is_available():
+            raise DgpError(-2, "no CUDA device: deepgraphpose_b200 has no CPU fallback")
+        self.lib = _lib.load()
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
+        self.nj = int(num_joints)
+        self.location_refinement = bool(location_refinement)
+        cfg = DgpConfig()
+        cfg.num_joints = self.nj
+        cfg.location_refinement = int(self.location_refinement)
+        cfg.device = self.device.index
+        cfg.stride = stride
+        cfg.locref_stdev = locref_stdev
+        cfg.mean_pixel = (C.c_float * 3)(*mean_pixel)
+        cfg.bn_epsilon = 1e-5
+        self.stride = float(stride)
+        self.locref_stdev = float(locref_stdev)
+        h = C.c_void_p()
+        check(self.lib.dgp_create(C.byref(cfg), C.byref(h)))
+        self.h = h
+        self.weights_loaded = False
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.dgp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, status):
+        check(status, self.h)
+
+    # ------------------------------------------------------------------ weights (Saver.restore replacement)
+    def load_weights(self, variables):
+        """variables: {tf_var_name: float32 ndarray in TF layout}."""
+        for name, arr in variables.items():
+            a = np.ascontiguousarray(arr, dtype=np.float32)
+            shape = (C.c_int64 * a.ndim)(*a.shape)
+            self._check(self.lib.dgp_load_weights(self.h, name.encode(), a.ctypes.data_as(C.c_void_p), shape, a.ndim, 0))
+        self._check(self.lib.dgp_finalize_weights(self.h))
+        self.weights_loaded = True
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, frames, want_locref=None):
+        """frames: uint8 cuda tensor (B,H,W,3). Returns (logits (B,2h,2w,nj) f32, locref (B,2h,2w,2nj) f32 | None)."""
+        if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[-1] != 3 or not frames.is_cuda:
+            raise ValueError("frames must be a uint8 CUDA tensor of shape (B,H,W,3)")
+        frames = frames.contiguous()
+        B, H, W, _ = frames.shape
+        _, (ho, wo) = output_dims(H, W)
+        if want_locref is None:
+            want_locref = self.location_refinement
+        logits = torch.empty((B, ho, wo, self.nj), dtype=torch.float32, device=frames.device)
+        locref = torch.empty((B, ho, wo, 2 * self.nj), dtype=torch.float32, device=frames.device) if want_locref else None
+        self._check(self.lib.dgp_forward(self.h, _ptr(frames), B, H, W, _ptr(logits), _ptr(locref), _stream(frames.device)))
+        return logits, locref
+
+    def softargmax(self, logits, locref=None, gamma=1.0, gauss_len=1.0, want=("mu", "peak", "lik", "dlc_peak", "dlc_pose")):
+        """Fused argmax_2d_from_cm + estimate_pose read-out + DLC argmax pose. Returns a dict of cuda tensors."""
+        if logits.dtype != torch.float32 or logits.dim() != 4 or not logits.is_cuda:
+            raise ValueError("logits must be a float32 CUDA tensor (B,H,W,nj)")
+        logits = logits.contiguous()
+        B, H, W, nj = logits.shape
+        dev = logits.device
+        out = {}
+        out["mu"] = torch.empty((B, nj, 2), dtype=torch.float32, device=dev) if "mu" in want else None
+        out["peak"] = torch.empty((B, nj, 2), dtype=torch.int32, device=dev) if "peak" in want else None
+        out["lik"] = torch.empty((B, nj), dtype=torch.float32, device=dev) if "lik" in want else None
+        out["dlc_peak"] = torch.empty((B, nj, 2), dtype=torch.int32, device=dev) if "dlc_peak" in want else None
+        out["dlc_pose"] = torch.empty((B, nj, 3), dtype=torch.float32, device=dev) if "dlc_pose" in want else None
+        if locref is not None:
+            locref = locref.contiguous()
+            if locref.shape != (B, H, W, 2 * nj) or locref.dtype != torch.float32:
+                raise ValueError("locref must be float32 (B,H,W,2*nj)")
+        self._check(self.lib.dgp_softargmax(self.h, _ptr(logits), _ptr(locref), B, H, W, nj, float(gamma), float(gauss_len),
+                                            _ptr(out["mu"]), _ptr(out["peak"]), _ptr(out["lik"]), _ptr(out["dlc_peak"]),
+                                            _ptr(out["dlc_pose"]), _stream(dev)))
+        return {k: v for k, v in out.items() if v is not None}
+
+    def sigmoid(self, logits):
+        logits = logits.contiguous()
+        out = torch.empty_like(logits)
+        self._check(self.lib.dgp_sigmoid(self.h, _ptr(logits), _ptr(out), logits.numel(), _stream(logits.device)))
+        return out
+
+    def potentials(self, mu, edges, halo_next=None, ws=None, ws_max=None, wt_max=0.0):
+        """mu (T,nj,2) f32 cuda; edges int32 (nl,2). Returns dict(skel (nl,T), temporal (T or T-1, nj), e_skel (T), e_temp (T))."""
+        mu = mu.contiguous()
+        T, nj, _ = mu.shape
+        dev = mu.device
+        edges = torch.as_tensor(np.asarray(edges, dtype=np.int32).reshape(-1, 2), device=dev)
+        nl = edges.shape[0]
+        skel = torch.empty((nl, T), dtype=torch.float32, device=dev)
+        temporal = torch.full((T, nj), float("nan"), dtype=torch.float32, device=dev)
+        e_skel = torch.empty((T,), dtype=torch.float32, device=dev) if ws is not None else None
+        e_temp = torch.empty((T,), dtype=torch.float32, device=dev)
+        ws_t = torch.as_tensor(np.asarray(ws, dtype=np.float32), device=dev) if ws is not None else None
+        wsm_t = torch.as_tensor(np.asarray(ws_max, dtype=np.float32), device=dev) if ws_max is not None else None
+        if halo_next is not None:
+            halo_next = halo_next.contiguous()
+        self._check(self.lib.dgp_potentials(self.h, _ptr(mu), _ptr(halo_next), T, nj, _ptr(edges), nl, _ptr(ws_t), _ptr(wsm_t),
+                                            float(wt_max), _ptr(skel), _ptr(temporal), _ptr(e_skel), _ptr(e_temp), _stream(dev)))
+        n_t = T if halo_next is not None else T - 1
+        return {"skel": skel, "temporal": temporal[:n_t], "e_skel": e_skel, "e_temp": e_temp}
+
+    def estimate_pose_host(self, frames_host, batch=16, gamma=1.0, gauss_len=1.0):
+        """End-to-end with HOST buffers (H2D + forward + soft-argmax + D2H inside). frames_host: uint8 (T,H,W,3) CPU tensor."""
+        if frames_host.is_cuda or frames_host.dtype != torch.uint8:
+            raise ValueError("frames_host must be a uint8 CPU tensor (pinned for async copies)")
+        frames_host = frames_host.contiguous()
+        T, H, W, _ = frames_host.shape
+        mu = torch.empty((T, self.nj, 2), dtype=torch.float32).pin_memory()
+        peak = torch.empty((T, self.nj, 2), dtype=torch.int32).pin_memory()
+        lik = torch.empty((T, self.nj), dtype=torch.float32).pin_memory()
+        self._check(self.lib.dgp_estimate_pose_host(self.h, _ptr(frames_host), T, H, W, int(batch), float(gamma), float(gauss_len),
+                                                    _ptr(mu), _ptr(peak), _ptr(lik)))
+        return mu, peak, lik
+
+    # ------------------------------------------------------------------ test hooks
+    def keep_activations(self, enable=True):
+        self._check(self.lib.dgp_debug_keep_activations(self.h, int(enable)))
+
+    def get_activation(self, end_point):
+        shape = (C.c_int64 * 4)()
+        self._check(self.lib.dgp_debug_get_activation(self.h, end_point.encode(), None, 0, shape))
+        n = int(np.prod(list(shape)))
+        out = np.empty(n, np.float32)
+        self._check(self.lib.dgp_debug_get_activation(self.h, end_point.encode(), out.ctypes.data_as(C.c_void_p), n, shape))
+        return out.reshape(tuple(shape))
+
+    def conv2d(self, x, w_hwio, stride=1, dilation=1, pad_mode=0, scale=None, shift=None, residual=None, res_sub=1,
+               relu=False, out_f32=False, block_n=0):
+        """One conv through the tcgen05 implicit-GEMM kernel. x: bf16 cuda NHWC; w_hwio: float32 ndarray HWIO."""
+        x = x.contiguous()
+        N, H, W, Cin = x.shape
+        w = np.ascontiguousarray(w_hwio, dtype=np.float32)
+        R, S, _, Cout = w.shape
+        if pad_mode == 2:
+            Ho = (H - ((R - 1) * dilation + 1)) // stride + 1
+            Wo = (W - ((S - 1) * dilation + 1)) // stride + 1
+        else:
+            Ho, Wo = -(-H // stride), -(-W // stride)
+        out = torch.empty((N, Ho, Wo, Cout), dtype=torch.float32 if out_f32 else torch.bfloat16, device=x.device)
+        sc = np.ascontiguousarray(scale, dtype=np.float32) if scale is not None else None
+        sh = np.ascontiguousarray(shift, dtype=np.float32) if shift is not None else None
+        res_H = res_W = 0
+        if residual is not None:
+            residual = residual.contiguous()
+            res_H, res_W = residual.shape[1], residual.shape[2]
+        self._check(self.lib.dgp_conv2d(
+            self.h, _ptr(x), N, H, W, Cin, w.ctypes.data_as(C.c_void_p), R, S, Cout, stride, dilation, pad_mode,
+            sc.ctypes.data_as(C.c_void_p) if sc is not None else None,
+            sh.ctypes.data_as(C.c_void_p) if sh is not None else None,
+            _ptr(residual), res_sub, res_H, res_W, int(relu), _ptr(out), int(out_f32), int(block_n), _stream(x.device)))
+        return out
+
+    def launch_count(self):
+        return int(self.lib.dgp_launch_count(self.h))
+
+    def num_sms(self):
+        return int(self.lib.dgp_num_sms(self.h))

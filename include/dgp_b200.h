@@ -1,0 +1,128 @@
+/*
+ * dgp_b200.h -- C ABI of libdgp_b200.so: the B200-native (sm_100a) implementation of Deep Graph Pose's
+ * per-frame scoremap-and-graph hot path.
+ *
+ * The reference (paninski-lab/deepgraphpose) has no FFI: its boundary is the TF1 graph-handle tuple returned by
+ * `setup_dgp_eval_graph` / `dgp_loss` plus `sess.run(fetches, feed_dict)`.  Each entry point below names the
+ * reference interface it replaces (paths relative to the reference root).  The Python shims in
+ * `deepgraphpose_b200/` bind these with ctypes and re-create the reference call surface on top of them; see
+ * INTEGRATION.md for the stub a reference maintainer would add.
+ *
+ * Conventions
+ *  - All `*_dev` pointers are CUDA device pointers owned by the caller (PyTorch tensors in the shims);
+ *    all tensors are dense, NHWC, (row, col) coordinate order, exactly as the reference's TF tensors.
+ *  - `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default stream).  Calls are asynchronous on it.
+ *  - Return value: DGP_OK (0) or a negative dgp_status; `dgp_last_error` gives the message.
+ *  - There is NO CPU fallback and no alternate backend: a device that is not sm_100 is DGP_ERR_UNSUPPORTED.
+ *  - A handle is bound to one device and is not thread-safe (one handle per GPU / rank).
+ */
+#ifndef DGP_B200_H_
+#define DGP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum dgp_status {
+  DGP_OK = 0,
+  DGP_ERR_INVALID = -1,      /* bad argument / shape */
+  DGP_ERR_CUDA = -2,         /* CUDA runtime or driver error */
+  DGP_ERR_UNSUPPORTED = -3,  /* not an sm_100 device, or a configuration outside the path */
+  DGP_ERR_STATE = -4,        /* call order (e.g. forward before finalize_weights) */
+  DGP_ERR_NOMEM = -5
+} dgp_status;
+
+typedef struct dgp_handle dgp_handle;
+
+/* Constants of PTF/default_config.py:16-59 and pose_cfg.yaml that parameterise the path. */
+typedef struct dgp_config {
+  int32_t num_joints;          /* cfg.num_joints */
+  int32_t location_refinement; /* build the locref_pred head (pose_net.py:66-68) */
+  int32_t device;              /* CUDA device ordinal */
+  float stride;                /* default_config.py:18  (8.0) */
+  float locref_stdev;          /* default_config.py:29  (7.2801) */
+  float mean_pixel[3];         /* default_config.py:23  (123.68, 116.779, 103.939), RGB */
+  float bn_epsilon;            /* slim resnet_arg_scope batch_norm_epsilon (1e-5) */
+} dgp_config;
+
+/* Replaces the graph construction in setup_dgp_eval_graph (src/deepgraphpose/models/eval.py:147-214) and in
+ * dgp_loss (src/deepgraphpose/models/fitdgp.py:934-944): PoseNet(cfg) + prediction layers. */
+int dgp_create(const dgp_config* cfg, dgp_handle** out);
+void dgp_destroy(dgp_handle* h);
+/* Message of the last failing call on `h` (or of the last failing dgp_create when h == NULL). */
+const char* dgp_last_error(const dgp_handle* h);
+
+/* Replaces TF.train.Saver.restore (eval.py:194-211, fitdgp.py:689-720): hand over one variable under its TF/slim
+ * name and TF layout (conv HWIO [kh,kw,cin,cout]; deconv [kh,kw,cout,cin]; BN vectors [c]; biases [c]).
+ * dtype: 0 = float32.  The data is copied; call dgp_finalize_weights once all variables are loaded. */
+int dgp_load_weights(dgp_handle* h, const char* tf_var_name, const void* host_ptr, const int64_t* shape, int ndim,
+                     int dtype);
+/* Converts to kernel layouts (bf16 [cout][kh*kw*cin] K-major, fp32 BN scale/shift) and uploads. */
+int dgp_finalize_weights(dgp_handle* h);
+
+/* Closed form of Dataset._compute_pred_dims (src/deepgraphpose/dataset.py:348-371). */
+int dgp_output_dims(int H, int W, int* h_feat, int* w_feat, int* h_out, int* w_out);
+
+/* Replaces sess.run([scmap(, locref)], {inputs: frames}) (eval.py:328, 746): PoseNet.extract_features
+ * (pose_net.py:36-54: mean subtraction + slim resnet_v1_50 OS16, frozen BN) and the 3x3 stride-2 deconv heads
+ * (pose_net.py:18-26).  frames_dev: uint8 (B,H,W,3) RGB.  logits_dev: float32 (B,2h,2w,nj) part_pred logits.
+ * locref_dev: float32 (B,2h,2w,2nj) or NULL. */
+int dgp_forward(dgp_handle* h, const uint8_t* frames_dev, int B, int H, int W, float* logits_dev, float* locref_dev,
+                void* stream);
+
+/* Replaces argmax_2d_from_cm (src/deepgraphpose/models/fitdgp_util.py:342-402) fused with the per-frame read-outs
+ * that consume it: estimate_pose's windowed peak + likelihood (eval.py:331-343) and DLC's global-argmax pose
+ * (PTF/nnet/predict.py:62-77, pose_net.py:92-163).  Any output pointer may be NULL.
+ *  mu_dev       float32 (B,nj,2)  soft-argmax (row, col) in scoremap pixels
+ *  peak_dev     int32   (B,nj,2)  estimate_pose `mu_likelihoods` (row, col)
+ *  lik_dev      float32 (B,nj)    estimate_pose `likelihoods`
+ *  dlc_peak_dev int32   (B,nj,2)  argmax_pose_predict integer peak (row, col)
+ *  dlc_pose_dev float32 (B,nj,3)  argmax_pose_predict (x, y, likelihood), locref offset applied iff locref_dev */
+int dgp_softargmax(dgp_handle* h, const float* logits_dev, const float* locref_dev, int B, int H, int W, int nj,
+                   float gamma, float gauss_len, float* mu_dev, int32_t* peak_dev, float* lik_dev,
+                   int32_t* dlc_peak_dev, float* dlc_pose_dev, void* stream);
+
+/* Replaces PoseNet.test's tf.sigmoid(part_pred) (pose_net.py:84-90). n = number of floats (multiple of 4). */
+int dgp_sigmoid(dgp_handle* h, const float* logits_dev, float* prob_dev, size_t n, void* stream);
+
+/* Replaces the clique distance terms of dgp_loss: skeleton d[l,t] = ||S (mu_t*stride + stride/2)||_2
+ * (fitdgp.py:1063-1069) and temporal delta[t,j] = ||mu_t - mu_{t+1}||_2 * stride (fitdgp.py:1079-1083).
+ *  mu_dev (T,nj,2); mu_halo_next_dev (nj,2) = first frame of the next shard or NULL (then row T-1 of temporal is
+ *  not written); edges_dev int32 (nl,2) = (+1 joint, -1 joint) rows of S0 (fitdgp.py:607-617);
+ *  ws_dev / ws_max_dev (nl) or NULL; skel_dist_dev (nl,T); temporal_dev (T,nj);
+ *  e_skel_dev (T) = sum_l ws_l * max(d, ws_max_l); e_temp_dev (T) = sum_j max(delta, wt_max)^2.  Outputs may be NULL. */
+int dgp_potentials(dgp_handle* h, const float* mu_dev, const float* mu_halo_next_dev, int T, int nj,
+                   const int32_t* edges_dev, int nl, const float* ws_dev, const float* ws_max_dev, float wt_max,
+                   float* skel_dist_dev, float* temporal_dev, float* e_skel_dev, float* e_temp_dev, void* stream);
+
+/* Replaces the estimate_pose frame loop (eval.py:306-345) end to end with HOST buffers: per batch of `batch`
+ * frames H2D copy, dgp_forward, dgp_softargmax, D2H of the results.  frames_host uint8 (T,H,W,3) (pinned memory
+ * gives asynchronous copies); mu_host float32 (T,nj,2); peak_host int32 (T,nj,2); lik_host float32 (T,nj). */
+int dgp_estimate_pose_host(dgp_handle* h, const uint8_t* frames_host, int T, int H, int W, int batch, float gamma,
+                           float gauss_len, float* mu_host, int32_t* peak_host, float* lik_host);
+
+/* ---- test / profiling hooks (not part of the reference surface) ---- */
+/* Keep every end_point (slim names, e.g. "resnet_v1_50/block1/unit_1/bottleneck_v1") of the next dgp_forward. */
+int dgp_debug_keep_activations(dgp_handle* h, int enable);
+/* Copy a kept end_point to host as float32 NHWC; shape4 receives (N,H,W,C). Returns DGP_ERR_INVALID if unknown. */
+int dgp_debug_get_activation(dgp_handle* h, const char* end_point, float* host_out, size_t max_elems,
+                             int64_t* shape4);
+/* One conv layer through the tcgen05 implicit-GEMM kernel (unit tests): x_dev bf16 NHWC (N,H,W,Cin), w_host float32
+ * HWIO, scale/shift host float32 [Cout] or NULL, residual_dev bf16 or NULL (res_sub 1|2), out_dev bf16 or fp32.
+ * pad_mode: 0 = TF SAME (stride 1), 1 = slim conv2d_same explicit padding, 2 = VALID. */
+int dgp_conv2d(dgp_handle* h, const void* x_dev, int N, int H, int W, int Cin, const float* w_host, int R, int S,
+               int Cout, int stride, int dilation, int pad_mode, const float* scale_host, const float* shift_host,
+               const void* residual_dev, int res_sub, int res_H, int res_W, int relu, void* out_dev, int out_f32,
+               int block_n, void* stream);
+/* Number of kernels this handle has launched since creation. */
+int64_t dgp_launch_count(const dgp_handle* h);
+/* Number of SMs of the handle's device. */
+int dgp_num_sms(const dgp_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DGP_B200_H_ */
