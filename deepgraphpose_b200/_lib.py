@@ -42,6 +42,7 @@ SIGNATURES = {
     "dgp_output_dims": (_i, [_i, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "dgp_forward": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "dgp_softargmax": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "dgp_softmax_map": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _f, _vp, _vp]),
     "dgp_sigmoid": (_i, [_vp, _vp, _vp, _sz, _vp]),
     "dgp_potentials": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp]),
     "dgp_estimate_pose_host": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp]),
@@ -49,6 +50,8 @@ SIGNATURES = {
     "dgp_debug_get_activation": (_i, [_vp, C.c_char_p, _vp, _sz, _i64p]),
     "dgp_conv2d": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp,
                         _i, _i, _vp]),
+    "dgp_set_profiling": (_i, [_vp, _i]),
+    "dgp_get_profile": (_i, [_vp, C.POINTER(C.c_double), _i64p, _i]),
     "dgp_launch_count": (C.c_int64, [_vp]),
     "dgp_num_sms": (_i, [_vp]),
 }

@@ -98,6 +98,14 @@ struct dgp_handle {
   };
   std::map<std::string, Kept> kept;
   int64_t launches = 0;
+  // per-kernel-family CUDA-event profiling (bench.py roofline numbers)
+  bool profiling = false;
+  struct ProfRec {
+    int kind;
+    cudaEvent_t a, b;
+  };
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> ev_pool;
   // softargmax workspace
   SaPartial* sa_ws = nullptr;
   size_t sa_ws_bytes = 0;
@@ -541,6 +549,36 @@ int ensure(dgp_handle* h, DevBuf* b, size_t bytes) {
   return DGP_OK;
 }
 
+cudaEvent_t prof_event(dgp_handle* h) {
+  if (!h->ev_pool.empty()) {
+    cudaEvent_t e = h->ev_pool.back();
+    h->ev_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+struct ProfScope {
+  dgp_handle* h;
+  cudaStream_t s;
+  int idx = -1;
+  ProfScope(dgp_handle* h_, int kind, cudaStream_t s_) : h(h_), s(s_) {
+    if (!h->profiling) return;
+    dgp_handle::ProfRec r;
+    r.kind = kind;
+    r.a = prof_event(h);
+    r.b = prof_event(h);
+    cudaEventRecord(r.a, s);
+    idx = (int)h->prof.size();
+    h->prof.push_back(r);
+  }
+  ~ProfScope() {
+    if (idx >= 0) cudaEventRecord(h->prof[idx].b, s);
+  }
+};
+
 }  // namespace
 
 extern "C" {
@@ -596,6 +634,8 @@ void dgp_destroy(dgp_handle* h) {
   cudaFree(h->st_mu.p);
   cudaFree(h->st_peak.p);
   cudaFree(h->st_lik.p);
+  for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (auto e : h->ev_pool) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -678,6 +718,7 @@ int dgp_forward(dgp_handle* h, const uint8_t* frames_dev, int B, int H, int W, f
   int rc = build_plan(h, B, H, W, &pl);
   if (rc) return rc;
   for (const Step& st : pl->steps) {
+    ProfScope prof(h, (int)st.kind, s);
     switch (st.kind) {
       case STEP_PREP:
         CU_OK(h, launch_prep_s2d(frames_dev, B, H, W, h->cfg.mean_pixel, pl->s2d, pl->Hs, pl->Ws, s));
@@ -719,10 +760,35 @@ int dgp_softargmax(dgp_handle* h, const float* logits_dev, const float* locref_d
     CU_OK(h, cudaMalloc(&h->sa_ws, need));
     h->sa_ws_bytes = need;
   }
+  ProfScope prof(h, 4, (cudaStream_t)stream);
   CU_OK(h, launch_softargmax(logits_dev, locref_dev, B, H, W, nj, gamma, gauss_len, h->cfg.stride, h->cfg.locref_stdev,
-                             h->sa_ws, splits, mu_dev, peak_dev, lik_dev, dlc_peak_dev, dlc_pose_dev,
+                             h->sa_ws, splits, mu_dev, peak_dev, lik_dev, dlc_peak_dev, dlc_pose_dev, nullptr,
                              (cudaStream_t)stream));
   h->launches += 2;
+  return DGP_OK;
+}
+
+int dgp_softmax_map(dgp_handle* h, const float* logits_dev, int B, int H, int W, int nj, float gamma, float gauss_len,
+                    float* map_dev, void* stream) {
+  if (!h) return DGP_ERR_INVALID;
+  if (B == 0) return DGP_OK;
+  if (!logits_dev || !map_dev || B < 0 || nj < 1 || (H & 1) || (W & 1) || gauss_len < 1.0f || gauss_len >= 5.0f)
+    return fail(h, DGP_ERR_INVALID, "dgp_softmax_map: bad argument");
+  CU_OK(h, cudaSetDevice(h->device));
+  const int splits = softargmax_splits(B, H, h->num_sms);
+  const size_t need = (size_t)B * splits * nj * sizeof(SaPartial) + (size_t)B * nj * 2 * sizeof(float);
+  if (need > h->sa_ws_bytes) {
+    if (h->sa_ws) CU_OK(h, cudaFree(h->sa_ws));
+    h->sa_ws = nullptr;
+    h->sa_ws_bytes = 0;
+    CU_OK(h, cudaMalloc(&h->sa_ws, need));
+    h->sa_ws_bytes = need;
+  }
+  float* norm = reinterpret_cast<float*>(h->sa_ws + (size_t)B * splits * nj);
+  CU_OK(h, launch_softargmax(logits_dev, nullptr, B, H, W, nj, gamma, gauss_len, h->cfg.stride, h->cfg.locref_stdev,
+                             h->sa_ws, splits, nullptr, nullptr, nullptr, nullptr, nullptr, norm, (cudaStream_t)stream));
+  CU_OK(h, launch_softmax_map(logits_dev, norm, B, H, W, nj, gamma, gauss_len, map_dev, h->num_sms, (cudaStream_t)stream));
+  h->launches += 3;
   return DGP_OK;
 }
 
@@ -848,6 +914,30 @@ int dgp_conv2d(dgp_handle* h, const void* x_dev, int N, int H, int W, int Cin, c
   cudaFree(L.scale);
   cudaFree(L.shift);
   return rc;
+}
+
+int dgp_set_profiling(dgp_handle* h, int enable) {
+  if (!h) return DGP_ERR_INVALID;
+  h->profiling = enable != 0;
+  return DGP_OK;
+}
+
+int dgp_get_profile(dgp_handle* h, double* ms_by_kind, int64_t* count_by_kind, int nkinds) {
+  if (!h || !ms_by_kind || !count_by_kind || nkinds < 1) return DGP_ERR_INVALID;
+  CU_OK(h, cudaSetDevice(h->device));
+  CU_OK(h, cudaDeviceSynchronize());
+  for (int i = 0; i < nkinds; ++i) { ms_by_kind[i] = 0.0; count_by_kind[i] = 0; }
+  for (auto& r : h->prof) {
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess && r.kind < nkinds) {
+      ms_by_kind[r.kind] += ms;
+      count_by_kind[r.kind] += 1;
+    }
+    h->ev_pool.push_back(r.a);
+    h->ev_pool.push_back(r.b);
+  }
+  h->prof.clear();
+  return DGP_OK;
 }
 
 int64_t dgp_launch_count(const dgp_handle* h) { return h ? h->launches : 0; }

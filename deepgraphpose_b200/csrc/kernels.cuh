@@ -16,7 +16,10 @@ int softargmax_tact(int nj);
 int softargmax_splits(int B, int H, int num_sms);
 cudaError_t launch_softargmax(const float* logits, const float* locref, int B, int H, int W, int nj, float gamma,
                               float gauss_len, float stride, float locref_stdev, SaPartial* workspace, int splits,
-                              float* mu, int* peak, float* lik, int* dlc_peak, float* dlc_pose, cudaStream_t stream);
+                              float* mu, int* peak, float* lik, int* dlc_peak, float* dlc_pose, float* norm,
+                              cudaStream_t stream);
+cudaError_t launch_softmax_map(const float* logits, const float* norm, int B, int H, int W, int nj, float gamma,
+                               float gauss_len, float* out, int num_sms, cudaStream_t stream);
 cudaError_t launch_sigmoid_map(const float* x, float* y, size_t n, int num_sms, cudaStream_t stream);
 cudaError_t launch_potentials(const float* mu, const float* halo_next, int T, int nj, const int* edges, int nl,
                               float stride, const float* ws, const float* ws_max, float wt_max, float* skel,

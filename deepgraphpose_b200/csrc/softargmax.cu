@@ -205,7 +205,7 @@ __global__ void softargmax_finalize_kernel(const float* __restrict__ logits, con
                                            int H, int W, int nj, int splits, const SaPartial* __restrict__ part,
                                            float stride, float locref_stdev, float* __restrict__ mu,
                                            int* __restrict__ peak, float* __restrict__ lik, int* __restrict__ dlc_peak,
-                                           float* __restrict__ dlc_pose) {
+                                           float* __restrict__ dlc_pose, float* __restrict__ norm) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= B * nj) return;
   const int b = t / nj, j = t - b * nj;
@@ -219,6 +219,7 @@ __global__ void softargmax_finalize_kernel(const float* __restrict__ logits, con
   }
   const float mur = a.sr / a.s0, muc = a.sc / a.s0;  // 0/0 -> NaN, as softmax_tensor / (sum + 1e-100) in fp32
   if (mu) { mu[2 * t] = mur; mu[2 * t + 1] = muc; }
+  if (norm) { norm[2 * t] = a.m; norm[2 * t + 1] = a.s0; }
   const float* fr = logits + (size_t)b * H * W * nj + j;
 
   if (peak || lik) {
@@ -253,6 +254,37 @@ __global__ void softargmax_finalize_kernel(const float* __restrict__ logits, con
       dlc_pose[3 * t + 1] = (float)r * stride + 0.5f * stride + dy;
       dlc_pose[3 * t + 2] = a.bsig;
     }
+  }
+}
+
+// Second output of argmax_2d_from_cm (fitdgp_util.py:391): the blurred, renormalised softmax map (N,H,W,C).
+// out = (K * exp(gamma*x - m)) / s0 with zero padding; m, s0 come from the soft-argmax pass.
+__global__ void softmax_map_kernel(const float* __restrict__ logits, const float* __restrict__ norm, int B, int H, int W,
+                                   int nj, float gamma, int radius, float sigma, float* __restrict__ out) {
+  float k[9];
+  float knorm = 0.0f;
+  for (int d = -radius; d <= radius; ++d) knorm += expf(-0.5f * (d / sigma) * (d / sigma));
+  for (int d = -radius; d <= radius && d + radius < 9; ++d) k[d + radius] = expf(-0.5f * (d / sigma) * (d / sigma)) / knorm;
+  const size_t total = (size_t)B * H * W * nj;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(t % nj);
+    size_t r = t / nj;
+    const int x = (int)(r % W);
+    r /= W;
+    const int y = (int)(r % H);
+    const int b = (int)(r / H);
+    const float m = norm[2 * ((size_t)b * nj + c)], s0 = norm[2 * ((size_t)b * nj + c) + 1];
+    float acc = 0.0f;
+    for (int dy = -radius; dy <= radius; ++dy) {
+      const int yy = y + dy;
+      if (yy < 0 || yy >= H) continue;
+      for (int dx = -radius; dx <= radius; ++dx) {
+        const int xx = x + dx;
+        if (xx < 0 || xx >= W) continue;
+        acc += k[dy + radius] * k[dx + radius] * __expf(logits[(((size_t)b * H + yy) * W + xx) * nj + c] * gamma - m);
+      }
+    }
+    out[t] = acc / s0;
   }
 }
 
@@ -323,7 +355,8 @@ int softargmax_splits(int B, int H, int num_sms) {
 
 cudaError_t launch_softargmax(const float* logits, const float* locref, int B, int H, int W, int nj, float gamma,
                               float gauss_len, float stride, float locref_stdev, SaPartial* workspace, int splits,
-                              float* mu, int* peak, float* lik, int* dlc_peak, float* dlc_pose, cudaStream_t stream) {
+                              float* mu, int* peak, float* lik, int* dlc_peak, float* dlc_pose, float* norm,
+                              cudaStream_t stream) {
   if (B <= 0) return cudaSuccess;
   const int tact = softargmax_tact(nj);
   if (tact <= 0 || (H & 1) || (W & 1)) return cudaErrorInvalidValue;
@@ -340,7 +373,19 @@ cudaError_t launch_softargmax(const float* logits, const float* locref, int B, i
                                                                           rows_per_split, real_splits, tact, workspace);
   const int n = B * nj;
   softargmax_finalize_kernel<<<(n + 127) / 128, 128, 0, stream>>>(logits, locref, B, H, W, nj, real_splits, workspace,
-                                                                  stride, locref_stdev, mu, peak, lik, dlc_peak, dlc_pose);
+                                                                  stride, locref_stdev, mu, peak, lik, dlc_peak, dlc_pose,
+                                                                  norm);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_softmax_map(const float* logits, const float* norm, int B, int H, int W, int nj, float gamma,
+                               float gauss_len, float* out, int num_sms, cudaStream_t stream) {
+  const int radius = (int)gauss_len;
+  if (radius > 4) return cudaErrorInvalidValue;
+  const size_t total = (size_t)B * H * W * nj;
+  size_t grid = (total + 255) / 256;
+  if (grid > (size_t)num_sms * 16) grid = (size_t)num_sms * 16;
+  softmax_map_kernel<<<(int)grid, 256, 0, stream>>>(logits, norm, B, H, W, nj, gamma, radius, gauss_len, out);
   return cudaGetLastError();
 }
 

@@ -119,6 +119,15 @@ class Engine:
                                             _ptr(out["dlc_pose"]), _stream(dev)))
         return {k: v for k, v in out.items() if v is not None}
 
+    def softmax_map(self, logits, gamma=1.0, gauss_len=1.0):
+        """Second output of argmax_2d_from_cm: blurred, renormalised spatial softmax (B,H,W,nj)."""
+        logits = logits.contiguous()
+        B, H, W, nj = logits.shape
+        out = torch.empty_like(logits)
+        self._check(self.lib.dgp_softmax_map(self.h, _ptr(logits), B, H, W, nj, float(gamma), float(gauss_len), _ptr(out),
+                                             _stream(logits.device)))
+        return out
+
     def sigmoid(self, logits):
         logits = logits.contiguous()
         out = torch.empty_like(logits)
@@ -195,6 +204,19 @@ class Engine:
             sh.ctypes.data_as(C.c_void_p) if sh is not None else None,
             _ptr(residual), res_sub, res_H, res_W, int(relu), _ptr(out), int(out_f32), int(block_n), _stream(x.device)))
         return out
+
+    PROFILE_KINDS = ("prep_s2d", "conv_gemm", "maxpool", "deconv_col2im", "softargmax")
+
+    def set_profiling(self, enable=True):
+        self._check(self.lib.dgp_set_profiling(self.h, int(enable)))
+
+    def get_profile(self):
+        """{kind: (total_ms, launches)} since the last call (synchronises the device)."""
+        n = len(self.PROFILE_KINDS)
+        ms = (C.c_double * n)()
+        cnt = (C.c_int64 * n)()
+        self._check(self.lib.dgp_get_profile(self.h, ms, cnt, n))
+        return {k: (ms[i], int(cnt[i])) for i, k in enumerate(self.PROFILE_KINDS)}
 
     def launch_count(self):
         return int(self.lib.dgp_launch_count(self.h))

@@ -1,0 +1,137 @@
+"""Drop-in for the hot-path part of deepgraphpose.models.eval (reference: src/deepgraphpose/models/eval.py).
+
+``setup_dgp_eval_graph`` :147-214 and ``estimate_pose`` :217-372 keep their names, argument meaning and return
+values; the TF graph/session are replaced by the sm_100a engine behind the C ABI.  Video decode (moviepy in the
+reference) and the csv/h5 export are outside the path: ``estimate_pose`` takes a video path (decoded
+with OpenCV when present) or an in-memory uint8 array of frames.
+"""
+import os
+
+import numpy as np
+import torch
+
+from . import synthetic
+from .engine import Engine
+from .session import Handle, Session
+
+
+def _cfg_get(cfg, key, default=None):
+    if isinstance(cfg, dict):
+        return cfg.get(key, default)
+    return getattr(cfg, key, default)
+
+
+def load_variables(dgp_model_file, num_joints, location_refinement):
+    """Weights for the graph.  Accepts a ``{tf_var_name: ndarray}`` dict, a ``.npz`` of such arrays, or
+    ``"synthetic"`` / ``"synthetic:<seed>"`` (random-init weights, BASELINE.json configs).  Reading TF checkpoint
+    bundles (``snapshot-*.index/.data``) is a "next" row of SURVEY.md 8(f) and raises here."""
+    if isinstance(dgp_model_file, dict):
+        return dgp_model_file
+    name = str(dgp_model_file)
+    if name.startswith("synthetic"):
+        seed = int(name.split(":")[1]) if ":" in name else 0
+        return synthetic.make_weights(num_joints, seed=seed, location_refinement=location_refinement)
+    if name.endswith(".npz") and os.path.exists(name):
+        with np.load(name) as z:
+            return {k: z[k] for k in z.files}
+    raise NotImplementedError(
+        "TF checkpoint bundles are not readable yet (SURVEY.md 8f rank 3); pass a .npz / dict of TF-named variables")
+
+
+def setup_dgp_eval_graph(dlc_cfg, dgp_model_file, loc_ref=False, gauss_len=1, gamma=1, device=None):
+    """eval.py:147-214.  Returns (sess, mu_n, softmax_tensor, scmap, locref, inputs)."""
+    nj = int(_cfg_get(dlc_cfg, "num_joints"))
+    net_type = _cfg_get(dlc_cfg, "net_type", "resnet_50")
+    if net_type != "resnet_50":
+        raise ValueError("only net_type='resnet_50' is on the B200 path (got %r)" % (net_type,))
+    eng = Engine(nj, location_refinement=bool(loc_ref), device=device,
+                 stride=float(_cfg_get(dlc_cfg, "stride", 8.0)),
+                 locref_stdev=float(_cfg_get(dlc_cfg, "locref_stdev", 7.2801)),
+                 mean_pixel=tuple(_cfg_get(dlc_cfg, "mean_pixel", (123.68, 116.779, 103.939))))
+    eng.load_weights(load_variables(dgp_model_file, nj, bool(loc_ref)))
+    handles = {
+        "inputs": Handle("Placeholder:0", "inputs"),
+        "mu_n": Handle("Sum:0", "mu_n"),
+        "softmax_tensor": Handle("truediv:0", "softmax_tensor"),
+        "scmap": Handle("pose/part_pred/block4/BiasAdd:0", "scmap"),
+        "locref": Handle("pose/locref_pred/block4/BiasAdd:0", "locref") if loc_ref else None,
+    }
+    sess = Session(eng, handles, gamma=gamma, gauss_len=gauss_len)
+    return sess, handles["mu_n"], handles["softmax_tensor"], handles["scmap"], handles["locref"], handles["inputs"]
+
+
+def _iter_video(video_file):
+    import cv2
+    cap = cv2.VideoCapture(str(video_file))
+    if not cap.isOpened():
+        raise IOError("cannot open video %s" % video_file)
+    while True:
+        ok, frame = cap.read()
+        if not ok:
+            break
+        yield frame[:, :, ::-1]  # BGR -> RGB, as moviepy delivers
+    cap.release()
+
+
+def estimate_pose_frames(engine, frames, batch=16, gamma=1.0, gauss_len=1.0, stride=None):
+    """The estimate_pose frame loop (eval.py:306-357) on in-memory frames: uint8 (T,H,W,3), numpy or CPU tensor.
+
+    Host buffers in, host arrays out; the H2D copy of every batch and the D2H copy of its results happen inside.
+    Returns dict(x, y, likelihoods, mu_likelihoods, markers) with the reference's shapes.
+    """
+    ft = frames if isinstance(frames, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(frames))
+    mu, peak, lik = engine.estimate_pose_host(ft, batch=batch, gamma=gamma, gauss_len=gauss_len)
+    stride = engine.stride if stride is None else stride
+    markers = mu.numpy().astype(np.float64)
+    xr = markers[:, :, 1] * stride + 0.5 * stride
+    yr = markers[:, :, 0] * stride + 0.5 * stride
+    return {"x": xr, "y": yr, "likelihoods": lik.numpy().astype(np.float64),
+            "mu_likelihoods": peak.numpy().astype("int"), "markers": markers}
+
+
+def estimate_pose(proj_cfg_file, dgp_model_file, video_file, output_dir, shuffle=1, save_pose=True, save_str="",
+                  new_size=None, crop_size=None, batch=16):
+    """eval.py:217-372.  ``proj_cfg_file`` may be a dict-like dlc_cfg (num_joints, stride, ...) or a DLC project yaml with
+    ``bodyparts``; ``video_file`` a path or a uint8 array (T,H,W,3).  Returns {'x','y','likelihoods'} (T,nj) each."""
+    if isinstance(proj_cfg_file, (dict,)) or hasattr(proj_cfg_file, "num_joints"):
+        dlc_cfg = proj_cfg_file
+    else:
+        import yaml
+        with open(proj_cfg_file, "r") as stream:
+            proj = yaml.safe_load(stream)
+        dlc_cfg = {"num_joints": len(proj["bodyparts"]), "all_joints_names": list(proj["bodyparts"]), "stride": 8.0}
+    save_file = None
+    if isinstance(video_file, (str, os.PathLike)):
+        f = os.path.basename(str(video_file)).rsplit(".", 1)
+        save_file = os.path.join(str(output_dir), f[0] + "_labeled%s" % save_str)
+        if os.path.exists(save_file + ".csv"):
+            print("labels already exist! video at %s will not be processed" % video_file)
+            return save_file + ".csv"
+        frames = np.stack(list(_iter_video(video_file)))
+    else:
+        frames = np.asarray(video_file)
+    scale_x = scale_y = 1.0
+    if new_size is not None or crop_size is not None:
+        from PIL import Image
+        out = []
+        for fr in frames:
+            im = Image.fromarray(fr)
+            if new_size is not None:
+                scale_x = im.width / new_size[1]
+                scale_y = im.height / new_size[0]
+                im = im.resize(size=(new_size[1], new_size[0]))
+            if crop_size is not None:
+                im = im.crop(crop_size)
+            out.append(np.asarray(im))
+        frames = np.stack(out)
+    sess, mu_n, _, scmap, _, inputs = setup_dgp_eval_graph(dlc_cfg, dgp_model_file)
+    res = estimate_pose_frames(sess.engine, frames, batch=batch)
+    sess.close()
+    labels = {"x": res["x"] * scale_x, "y": res["y"] * scale_y, "likelihoods": res["likelihoods"]}
+    if save_pose and save_file is not None:
+        os.makedirs(os.path.dirname(save_file) or ".", exist_ok=True)
+        names = _cfg_get(dlc_cfg, "all_joints_names", ["joint%d" % i for i in range(labels["x"].shape[1])])
+        header = ",".join("%s_%s" % (n, c) for n in names for c in ("x", "y", "likelihood"))
+        table = np.stack([labels["x"], labels["y"], labels["likelihoods"]], axis=2).reshape(labels["x"].shape[0], -1)
+        np.savetxt(save_file + ".csv", table, delimiter=",", header=header, comments="")
+    return labels

@@ -85,6 +85,11 @@ int dgp_softargmax(dgp_handle* h, const float* logits_dev, const float* locref_d
                    float gamma, float gauss_len, float* mu_dev, int32_t* peak_dev, float* lik_dev,
                    int32_t* dlc_peak_dev, float* dlc_pose_dev, void* stream);
 
+/* Second return value of argmax_2d_from_cm (fitdgp_util.py:391, consumed by evaluate_dgp eval.py:752): the
+ * Gaussian-blurred, renormalised spatial softmax, float32 (B,H,W,nj). */
+int dgp_softmax_map(dgp_handle* h, const float* logits_dev, int B, int H, int W, int nj, float gamma, float gauss_len,
+                    float* map_dev, void* stream);
+
 /* Replaces PoseNet.test's tf.sigmoid(part_pred) (pose_net.py:84-90). n = number of floats (multiple of 4). */
 int dgp_sigmoid(dgp_handle* h, const float* logits_dev, float* prob_dev, size_t n, void* stream);
 
@@ -117,6 +122,11 @@ int dgp_conv2d(dgp_handle* h, const void* x_dev, int N, int H, int W, int Cin, c
                int Cout, int stride, int dilation, int pad_mode, const float* scale_host, const float* shift_host,
                const void* residual_dev, int res_sub, int res_H, int res_W, int relu, void* out_dev, int out_f32,
                int block_n, void* stream);
+/* CUDA-event timing per kernel family, recorded on the launching stream around every launch while enabled.
+ * kinds: 0 = u8->bf16 space-to-depth prep, 1 = tcgen05 conv GEMM, 2 = max-pool, 3 = deconv col2im, 4 = soft-argmax.
+ * dgp_get_profile synchronises the device, sums the elapsed ms and launch counts per kind and clears the records. */
+int dgp_set_profiling(dgp_handle* h, int enable);
+int dgp_get_profile(dgp_handle* h, double* ms_by_kind, int64_t* count_by_kind, int nkinds);
 /* Number of kernels this handle has launched since creation. */
 int64_t dgp_launch_count(const dgp_handle* h);
 /* Number of SMs of the handle's device. */
