@@ -110,8 +110,10 @@ struct dgp_handle {
   SaPartial* sa_ws = nullptr;
   size_t sa_ws_bytes = 0;
   // estimate_pose_host staging
-  cudaStream_t stream = nullptr;
-  DevBuf st_frames, st_logits, st_mu, st_peak, st_lik;
+  cudaStream_t stream = nullptr;       // compute stream of dgp_estimate_pose_host
+  cudaStream_t copy_stream = nullptr;  // H2D of the next batch overlaps the current batch's kernels
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+  DevBuf st_frames2[2], st_logits, st_mu, st_peak, st_lik;
 };
 
 namespace {
@@ -309,6 +311,35 @@ int alloc_buf(dgp_handle* h, Plan* pl, size_t bytes, void** out) {
   return DGP_OK;
 }
 
+// Epilogue configuration: bf16 outputs whose tile width is a multiple of 64 go through the TMA-staged epilogue
+// (TMA store of the output, TMA load of the residual); everything else uses direct register->global stores.
+int setup_epilogue(dgp_handle* h, ConvGemmParams& g, const char* scope, int n_img) {
+  const bool staged = !g.out_f32 && (g.block_n % kEpiChunkCols == 0);
+  if (!staged) {
+    if (g.residual) return fail(h, DGP_ERR_UNSUPPORTED, "%s: residual needs a bf16 output with block_n %% 64 == 0", scope);
+    g.epi_mode = 0;
+    g.epi_bufs = 0;
+  } else {
+    g.epi_mode = 1;
+    g.epi_bufs = g.residual ? 4 : 2;
+    const char* e = make_tmap_2d(&g.tmap_out, g.out, (uint64_t)g.M, (uint64_t)g.N, (uint64_t)g.ldc * 2, 32);
+    if (e) return fail(h, DGP_ERR_CUDA, "%s (out map): %s", scope, e);
+    if (g.residual) {
+      if (g.res_sub == 1) {
+        e = make_tmap_2d(&g.tmap_res, g.residual, (uint64_t)g.M, (uint64_t)g.N, (uint64_t)g.ldres * 2, 32);
+      } else {
+        e = make_tmap_im2col(&g.tmap_res, g.residual, (uint64_t)g.N, (uint64_t)g.res_W, (uint64_t)g.res_H, (uint64_t)n_img,
+                             (uint64_t)g.ldres * 2, (uint64_t)g.res_W * g.ldres * 2,
+                             (uint64_t)g.res_H * g.res_W * g.ldres * 2, 0, 0, 0, 0, g.res_sub,
+                             (uint64_t)n_img * g.res_H * g.res_W * g.ldres * 2, 32);
+      }
+      if (e) return fail(h, DGP_ERR_CUDA, "%s (residual map): %s", scope, e);
+    }
+  }
+  g.num_stages = conv_gemm_pick_stages(g.block_n, g.epi_bufs);
+  return DGP_OK;
+}
+
 // Fill the GEMM params of one conv layer. x: input NHWC bf16 (N,H,W,Cin). Returns output dims via Ho/Wo.
 int make_gemm_step(dgp_handle* h, const ConvLayer& L, const void* x, int N, int H, int W, int pad_mode, void* out,
                    bool out_f32, const __nv_bfloat16* residual, int res_sub, int res_H, int res_W, int block_n_override,
@@ -357,8 +388,8 @@ int make_gemm_step(dgp_handle* h, const ConvLayer& L, const void* x, int N, int 
   g.out = out; g.out_f32 = out_f32 ? 1 : 0; g.ldc = L.Npad;
   g.num_m_blocks = ceil_div(g.M, kBlockM);
   g.num_n_blocks = L.Npad / bn;
-  g.num_stages = conv_gemm_pick_stages(bn);
   g.tmem_cols = tmem_cols_for(bn);
+  if (int rc = setup_epilogue(h, g, L.scope.c_str(), N)) return rc;
   const char* e = nullptr;
   const bool pointwise = (L.R == 1 && L.S == 1 && L.stride == 1);
   if (pointwise) {
@@ -432,7 +463,8 @@ int build_plan(dgp_handle* h, int B, int H, int W, Plan** out) {
     g.scale = L.scale; g.shift = L.shift; g.residual = nullptr; g.res_sub = 1; g.relu = 1;
     g.out = c1; g.out_f32 = 0; g.ldc = 64;
     g.num_m_blocks = ceil_div(g.M, kBlockM); g.num_n_blocks = 1;
-    g.num_stages = conv_gemm_pick_stages(64); g.tmem_cols = tmem_cols_for(64);
+    g.tmem_cols = tmem_cols_for(64);
+    if ((rc = setup_epilogue(h, g, "conv1", B))) return rc;
     const char* e = make_tmap_im2col(&g.tmap_a, pl->s2d, 64, (uint64_t)pl->W1, (uint64_t)pl->Hs, (uint64_t)B, 32,
                                      (uint64_t)pl->Ws * 32, (uint64_t)pl->Hs * pl->Ws * 32, 0, 0, 0, -3, 1,
                                      (uint64_t)B * pl->Hs * pl->Ws * 32);
@@ -629,7 +661,13 @@ void dgp_destroy(dgp_handle* h) {
     for (auto& b : kv.second->bufs) cudaFree(b.p);
   for (auto& kv : h->kept) cudaFree(kv.second.p);
   cudaFree(h->sa_ws);
-  cudaFree(h->st_frames.p);
+  cudaFree(h->st_frames2[0].p);
+  cudaFree(h->st_frames2[1].p);
+  for (int i = 0; i < 2; ++i) {
+    if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
+    if (h->ev_consumed[i]) cudaEventDestroy(h->ev_consumed[i]);
+  }
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   cudaFree(h->st_logits.p);
   cudaFree(h->st_mu.p);
   cudaFree(h->st_peak.p);
@@ -828,17 +866,32 @@ int dgp_estimate_pose_host(dgp_handle* h, const uint8_t* frames_host, int T, int
   dgp_output_dims(H, W, &hf, &wf, &ho, &wo);
   const size_t frame_bytes = (size_t)H * W * 3;
   int rc;
-  if ((rc = ensure(h, &h->st_frames, frame_bytes * batch))) return rc;
+  if ((rc = ensure(h, &h->st_frames2[0], frame_bytes * batch))) return rc;
+  if ((rc = ensure(h, &h->st_frames2[1], frame_bytes * batch))) return rc;
   if ((rc = ensure(h, &h->st_logits, (size_t)batch * ho * wo * nj * 4))) return rc;
   if ((rc = ensure(h, &h->st_mu, (size_t)batch * nj * 2 * 4))) return rc;
   if ((rc = ensure(h, &h->st_peak, (size_t)batch * nj * 2 * 4))) return rc;
   if ((rc = ensure(h, &h->st_lik, (size_t)batch * nj * 4))) return rc;
-  cudaStream_t s = h->stream;
-  for (int t0 = 0; t0 < T; t0 += batch) {
+  if (!h->copy_stream) {
+    CU_OK(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CU_OK(h, cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming));
+      CU_OK(h, cudaEventCreateWithFlags(&h->ev_consumed[i], cudaEventDisableTiming));
+    }
+  }
+  cudaStream_t s = h->stream, cs = h->copy_stream;
+  int it = 0;
+  for (int t0 = 0; t0 < T; t0 += batch, ++it) {
     const int b = (T - t0) < batch ? (T - t0) : batch;
-    CU_OK(h, cudaMemcpyAsync(h->st_frames.p, frames_host + (size_t)t0 * frame_bytes, frame_bytes * b,
-                             cudaMemcpyHostToDevice, s));
-    if ((rc = dgp_forward(h, (const uint8_t*)h->st_frames.p, b, H, W, (float*)h->st_logits.p, nullptr, s))) return rc;
+    const int slot = it & 1;
+    // H2D of this batch on the copy stream, as soon as the batch that last used this slot has been consumed
+    if (it >= 2) CU_OK(h, cudaStreamWaitEvent(cs, h->ev_consumed[slot], 0));
+    CU_OK(h, cudaMemcpyAsync(h->st_frames2[slot].p, frames_host + (size_t)t0 * frame_bytes, frame_bytes * b,
+                             cudaMemcpyHostToDevice, cs));
+    CU_OK(h, cudaEventRecord(h->ev_copied[slot], cs));
+    CU_OK(h, cudaStreamWaitEvent(s, h->ev_copied[slot], 0));
+    if ((rc = dgp_forward(h, (const uint8_t*)h->st_frames2[slot].p, b, H, W, (float*)h->st_logits.p, nullptr, s))) return rc;
+    CU_OK(h, cudaEventRecord(h->ev_consumed[slot], s));
     if ((rc = dgp_softargmax(h, (const float*)h->st_logits.p, nullptr, b, ho, wo, nj, gamma, gauss_len,
                              (float*)h->st_mu.p, (int32_t*)h->st_peak.p, (float*)h->st_lik.p, nullptr, nullptr, s)))
       return rc;

@@ -3,8 +3,11 @@
 // CTA = 192 threads, persistent over (m_blk, n_blk) tiles:
 //   warp 0      TMA producer   (one lane): A tile 128 x 64 (tiled or im2col) + B tile block_n x 64 per stage
 //   warp 1      MMA issuer     (one lane): 4 x tcgen05.mma (K=16) per stage into a double-buffered TMEM accumulator
-//   warps 2..5  epilogue: tcgen05.ld -> fp32 BN scale/shift (+residual)(+ReLU) -> bf16/fp32 global stores
-// Pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty pair (MMA <-> epilogue).
+//   warps 2..5  epilogue: tcgen05.ld -> fp32 BN scale/shift (+residual)(+ReLU) -> bf16
+// Pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty pair (MMA <-> epilogue), and per epilogue warp a
+// ring of 4 KB staging buffers (32 rows x 64 channels, SWIZZLE_128B): the residual tile is TMA-loaded into a buffer
+// ahead of time, the warp adds it to the accumulator in place and the buffer is TMA-stored to the output, so that
+// every byte of residual / output traffic moves as full 128 B lines issued by the copy engine, not by the LSU.
 #include "conv_gemm_sm100.cuh"
 
 #include <stdio.h>
@@ -18,12 +21,31 @@ namespace {
 constexpr int kThreads = 192;
 constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KiB
 constexpr int kMaxStages = 8;
+constexpr int kMaxEpiBufs = 4;
 
 __device__ __forceinline__ float bf16lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__device__ __forceinline__ void apply_scale_shift(float (&f)[16], const float* __restrict__ scale,
+                                                  const float* __restrict__ shift, int n) {
+  if (scale != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) {
+      const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + n + i));
+      f[i] *= sc.x; f[i + 1] *= sc.y; f[i + 2] *= sc.z; f[i + 3] *= sc.w;
+    }
+  }
+  if (shift != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) {
+      const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + n + i));
+      f[i] += sh.x; f[i + 1] += sh.y; f[i + 2] += sh.z; f[i + 3] += sh.w;
+    }
+  }
 }
 
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
@@ -33,11 +55,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   const int b_bytes = p.block_n * kBlockK * 2;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + stages * kABytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + stages * b_bytes);
+  uint8_t* smem_epi = smem_b + stages * b_bytes;  // [4 warps][epi_bufs][4 KiB], 1024 B aligned
+  const int epi_bufs = p.epi_mode == 1 ? p.epi_bufs : 0;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_epi + 4 * epi_bufs * kEpiChunkBytes);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tmem_full_bar = empty_bar + kMaxStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* res_bar = tmem_empty_bar + 2;  // [4 warps][kMaxEpiBufs]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 4 * kMaxEpiBufs);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -45,6 +70,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&p.tmap_a);
     ptx::prefetch_tmap(&p.tmap_b);
+    if (p.epi_mode == 1) {
+      ptx::prefetch_tmap(&p.tmap_out);
+      if (p.residual != nullptr) ptx::prefetch_tmap(&p.tmap_res);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < stages; ++s) {
@@ -55,6 +84,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       ptx::mbar_init(&tmem_full_bar[a], 1);
       ptx::mbar_init(&tmem_empty_bar[a], 4);
     }
+    for (int i = 0; i < 4 * kMaxEpiBufs; ++i) ptx::mbar_init(&res_bar[i], 1);
     ptx::fence_mbar_init();
   }
   if (warp == 2) {
@@ -143,30 +173,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         if (acc == 0) acc_phase ^= 1;
       }
     }
-  } else {
-    // -------------------------------------------------------------- epilogue (warps 2..5)
+  } else if (p.epi_mode == 0) {
+    // -------------------------------------------------------------- epilogue, direct stores (fp32 head GEMM)
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     int acc = 0;
     uint32_t acc_phase = 0;
-    const int PQ = p.P * p.Q;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / p.num_n_blocks;
       const int n_blk = tile - m_blk * p.num_n_blocks;
       const int row = m_blk * kBlockM + quad * 32 + lane;
       const int n0 = n_blk * p.block_n;
       const bool row_ok = row < p.M;
-      size_t res_row = 0;
-      if (p.residual != nullptr && row_ok) {
-        if (p.res_sub == 1) {
-          res_row = (size_t)row;
-        } else {
-          const int img = row / PQ;
-          const int rem = row - img * PQ;
-          const int pp = rem / p.Q;
-          const int qq = rem - pp * p.Q;
-          res_row = ((size_t)img * p.res_H + (size_t)pp * p.res_sub) * p.res_W + (size_t)qq * p.res_sub;
-        }
-      }
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.block_n);
@@ -179,31 +196,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 #pragma unroll
           for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
           const int n = n0 + c0;
-          if (p.scale != nullptr) {
-#pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + n + i));
-              f[i] *= sc.x; f[i + 1] *= sc.y; f[i + 2] *= sc.z; f[i + 3] *= sc.w;
-            }
-          }
-          if (p.shift != nullptr) {
-#pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + n + i));
-              f[i] += sh.x; f[i + 1] += sh.y; f[i + 2] += sh.z; f[i + 3] += sh.w;
-            }
-          }
-          if (p.residual != nullptr) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + res_row * (size_t)p.ldres + n);
-            const uint4 r0 = __ldg(rp);
-            const uint4 r1 = __ldg(rp + 1);
-            const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              f[2 * i] += bf16lo(rr[i]);
-              f[2 * i + 1] += bf16hi(rr[i]);
-            }
-          }
+          apply_scale_shift(f, p.scale, p.shift, n);
           if (p.relu) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.0f);
@@ -226,6 +219,116 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+  } else {
+    // -------------------------------------------------------------- epilogue, TMA-staged bf16 (+ TMA residual)
+    const int quad = warp & 3;
+    const int ew = warp - 2;  // 0..3: this warp's staging ring
+    const int nb = p.epi_bufs;
+    uint8_t* ebuf = smem_epi + (size_t)ew * nb * kEpiChunkBytes;
+    uint64_t* rbar = res_bar + ew * kMaxEpiBufs;
+    const bool has_res = p.residual != nullptr;
+    const int chunks_per_tile = p.block_n / kEpiChunkCols;
+    const int PQ = p.P * p.Q;
+    // my byte offset inside a 128 B swizzled staging row: 16 B unit (u ^ (lane & 7))
+    uint8_t* my_row = nullptr;
+
+    // residual prefetch for the g-th chunk of this CTA's chunk sequence (lane 0 only)
+    auto issue_residual = [&](int g) {
+      const int tile = blockIdx.x + (g / chunks_per_tile) * gridDim.x;
+      if (tile >= num_tiles) return;
+      const int c = g - (g / chunks_per_tile) * chunks_per_tile;
+      const int m_blk = tile / p.num_n_blocks;
+      const int n_blk = tile - m_blk * p.num_n_blocks;
+      const int row0 = m_blk * kBlockM + quad * 32;
+      const int col0 = n_blk * p.block_n + c * kEpiChunkCols;
+      const int buf = g % nb;
+      ptx::mbar_arrive_expect_tx(&rbar[buf], (uint32_t)kEpiChunkBytes);
+      if (p.res_sub == 1) {
+        ptx::tma_load_2d(ebuf + buf * kEpiChunkBytes, &p.tmap_res, &rbar[buf], col0, row0);
+      } else {
+        const int img = row0 / PQ;
+        const int rem = row0 - img * PQ;
+        const int pp = rem / p.Q;
+        const int qq = rem - pp * p.Q;
+        ptx::tma_load_im2col_4d(ebuf + buf * kEpiChunkBytes, &p.tmap_res, &rbar[buf], col0, qq * p.res_sub,
+                                pp * p.res_sub, img, 0, 0);
+      }
+    };
+
+    if (has_res && lane == 0) {
+      for (int g = 0; g < nb - 1; ++g) issue_residual(g);
+    }
+    int g = 0;  // chunk sequence number
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / p.num_n_blocks;
+      const int n_blk = tile - m_blk * p.num_n_blocks;
+      const int row0 = m_blk * kBlockM + quad * 32;
+      const int n0 = n_blk * p.block_n;
+      ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.block_n);
+      for (int c = 0; c < chunks_per_tile; ++c, ++g) {
+        const int buf = g % nb;
+        my_row = ebuf + buf * kEpiChunkBytes + lane * 128;
+        if (has_res) {
+          ptx::mbar_wait(&rbar[buf], (uint32_t)((g / nb) & 1));
+        } else {
+          // the store that last used this buffer (chunk g - nb) must have finished reading it
+          if (lane == 0) ptx::bulk_wait_group_read<1>();
+          __syncwarp();
+        }
+#pragma unroll
+        for (int sub = 0; sub < kEpiChunkCols / 16; ++sub) {
+          uint32_t v[16];
+          ptx::tmem_ld_x16(taddr + (uint32_t)(c * kEpiChunkCols + sub * 16), v);
+          ptx::tmem_ld_wait();
+          float f[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+          apply_scale_shift(f, p.scale, p.shift, n0 + c * kEpiChunkCols + sub * 16);
+          uint4* s0 = reinterpret_cast<uint4*>(my_row + (((2 * sub) ^ (lane & 7)) << 4));
+          uint4* s1 = reinterpret_cast<uint4*>(my_row + (((2 * sub + 1) ^ (lane & 7)) << 4));
+          if (has_res) {
+            const uint4 r0 = *s0;
+            const uint4 r1 = *s1;
+            const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              f[2 * i] += bf16lo(rr[i]);
+              f[2 * i + 1] += bf16hi(rr[i]);
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.0f);
+          }
+          *s0 = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+          *s1 = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]),
+                           pack_bf16(f[14], f[15]));
+        }
+        ptx::fence_proxy_async_smem();  // my generic-proxy smem writes -> visible to the TMA store (async proxy)
+        __syncwarp();
+        if (lane == 0) {
+          ptx::tma_store_2d(&p.tmap_out, ebuf + buf * kEpiChunkBytes, n0 + c * kEpiChunkCols, row0);
+          ptx::bulk_commit_group();
+          if (has_res) {
+            // chunk g+nb-1 reuses the buffer of chunk g-1: its store may be the only one still pending besides mine
+            if (g >= 1) ptx::bulk_wait_group_read<1>();
+            issue_residual(g + nb - 1);
+          }
+        }
+        __syncwarp();
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (lane == 0) ptx::bulk_wait_group_read<0>();
+    __syncwarp();
   }
 
   ptx::tc_fence_before();
@@ -284,7 +387,8 @@ const char* make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint
 
 const char* make_tmap_im2col(CUtensorMap* out, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t N,
                              uint64_t stride_w_bytes, uint64_t stride_h_bytes, uint64_t stride_n_bytes, int lower_w,
-                             int lower_h, int upper_w, int upper_h, int conv_stride, uint64_t total_bytes) {
+                             int lower_h, int upper_w, int upper_h, int conv_stride, uint64_t total_bytes,
+                             uint32_t pixels_per_column) {
   if (const char* e = tma_init()) return e;
   cuuint64_t dims[4] = {C, W, H, N};
   cuuint64_t strides[3] = {stride_w_bytes, stride_h_bytes, stride_n_bytes};
@@ -292,9 +396,9 @@ const char* make_tmap_im2col(CUtensorMap* out, const void* base, uint64_t C, uin
   int upper[2] = {upper_w, upper_h};
   cuuint32_t estr[4] = {1, (cuuint32_t)conv_stride, (cuuint32_t)conv_stride, 1};
   CUresult r = g_encode_im2col(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, lower,
-                               upper, (cuuint32_t)kBlockK, (cuuint32_t)kBlockM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                               upper, (cuuint32_t)kBlockK, (cuuint32_t)pixels_per_column, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     snprintf(g_err, sizeof(g_err),
              "cuTensorMapEncodeIm2col failed: %d (C=%llu W=%llu H=%llu N=%llu sw=%llu sh=%llu sn=%llu lo=(%d,%d) up=(%d,%d) s=%d)",
@@ -311,14 +415,15 @@ const char* make_tmap_im2col(CUtensorMap* out, const void* base, uint64_t C, uin
   return nullptr;
 }
 
-size_t conv_gemm_smem_bytes(int block_n, int num_stages) {
-  return 1024 + (size_t)num_stages * (kABytes + (size_t)block_n * kBlockK * 2) + (2 * kMaxStages + 4) * 8 + 16;
+size_t conv_gemm_smem_bytes(int block_n, int num_stages, int epi_bufs) {
+  return 1024 + (size_t)num_stages * (kABytes + (size_t)block_n * kBlockK * 2) + (size_t)4 * epi_bufs * kEpiChunkBytes +
+         (2 * kMaxStages + 4 + 4 * kMaxEpiBufs) * 8 + 16;
 }
 
-int conv_gemm_pick_stages(int block_n) {
+int conv_gemm_pick_stages(int block_n, int epi_bufs) {
   const size_t budget = 227 * 1024;
   int s = kMaxStages;
-  while (s > 2 && conv_gemm_smem_bytes(block_n, s) > budget) --s;
+  while (s > 2 && conv_gemm_smem_bytes(block_n, s, epi_bufs) > budget) --s;
   return s;
 }
 
@@ -331,7 +436,7 @@ cudaError_t launch_conv_gemm(const ConvGemmParams& p, int num_sms, cudaStream_t 
   }
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   const int grid = tiles < num_sms ? tiles : num_sms;
-  const size_t smem = conv_gemm_smem_bytes(p.block_n, p.num_stages);
+  const size_t smem = conv_gemm_smem_bytes(p.block_n, p.num_stages, p.epi_mode == 1 ? p.epi_bufs : 0);
   conv_gemm_kernel<<<grid, kThreads, smem, stream>>>(p);
   return cudaGetLastError();
 }
