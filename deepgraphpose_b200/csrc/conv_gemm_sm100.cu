@@ -30,22 +30,30 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-__device__ __forceinline__ void apply_scale_shift(float (&f)[16], const float* __restrict__ scale,
-                                                  const float* __restrict__ shift, int n) {
-  if (scale != nullptr) {
+// BN scale/shift of 16 consecutive channels from this warp's shared-memory copy (broadcast LDS.128).
+__device__ __forceinline__ void apply_scale_shift(float (&f)[16], const float* ss_scale, const float* ss_shift, int c) {
 #pragma unroll
-    for (int i = 0; i < 16; i += 4) {
-      const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + n + i));
-      f[i] *= sc.x; f[i + 1] *= sc.y; f[i + 2] *= sc.z; f[i + 3] *= sc.w;
-    }
+  for (int i = 0; i < 16; i += 4) {
+    const float4 sc = *reinterpret_cast<const float4*>(ss_scale + c + i);
+    const float4 sh = *reinterpret_cast<const float4*>(ss_shift + c + i);
+    f[i] = fmaf(f[i], sc.x, sh.x);
+    f[i + 1] = fmaf(f[i + 1], sc.y, sh.y);
+    f[i + 2] = fmaf(f[i + 2], sc.z, sh.z);
+    f[i + 3] = fmaf(f[i + 3], sc.w, sh.w);
   }
-  if (shift != nullptr) {
-#pragma unroll
-    for (int i = 0; i < 16; i += 4) {
-      const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + n + i));
-      f[i] += sh.x; f[i + 1] += sh.y; f[i + 2] += sh.z; f[i + 3] += sh.w;
-    }
+}
+
+// Each epilogue warp keeps its own copy of the tile's scale/shift ([2][256] floats): with 227 KB of shared memory
+// carved out there is no L1 left, so a per-use __ldg would put an L2 round trip on the epilogue's critical path.
+__device__ __forceinline__ void load_scale_shift(float* ss, const float* __restrict__ scale,
+                                                 const float* __restrict__ shift, int n0, int block_n, int lane) {
+  for (int i = lane * 4; i < block_n; i += 128) {
+    const float4 sc = scale ? __ldg(reinterpret_cast<const float4*>(scale + n0 + i)) : make_float4(1.f, 1.f, 1.f, 1.f);
+    const float4 sh = shift ? __ldg(reinterpret_cast<const float4*>(shift + n0 + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(ss + i) = sc;
+    *reinterpret_cast<float4*>(ss + 256 + i) = sh;
   }
+  __syncwarp();
 }
 
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
@@ -57,7 +65,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   uint8_t* smem_b = smem + stages * kABytes;
   uint8_t* smem_epi = smem_b + stages * b_bytes;  // [4 warps][epi_bufs][4 KiB], 1024 B aligned
   const int epi_bufs = p.epi_mode == 1 ? p.epi_bufs : 0;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_epi + 4 * epi_bufs * kEpiChunkBytes);
+  float* smem_ss = reinterpret_cast<float*>(smem_epi + 4 * epi_bufs * kEpiChunkBytes);  // [4 warps][2][256]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_ss + 4 * 512);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tmem_full_bar = empty_bar + kMaxStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
@@ -99,83 +108,95 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   const int num_tiles = p.num_m_blocks * p.num_n_blocks;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ------------------------------------------------------------ TMA producer
-      int stage = 0;
-      uint32_t phase = 0;
-      const uint32_t tx_bytes = (uint32_t)(kABytes + b_bytes);
-      const int PQ = p.P * p.Q;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / p.num_n_blocks;
-        const int n_blk = tile - m_blk * p.num_n_blocks;
-        const int m0 = m_blk * kBlockM;
-        const int n0 = n_blk * p.block_n;
-        int img = 0, cw = 0, ch = 0;
-        if (p.a_mode == 1) {
-          img = m0 / PQ;
-          const int rem = m0 - img * PQ;
-          const int pp = rem / p.Q;
-          const int qq = rem - pp * p.Q;
-          cw = qq * p.conv_stride + p.lower_w;
-          ch = pp * p.conv_stride + p.lower_h;
-        }
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+    // ------------------------------------------------------------ TMA producer (whole warp loops, one lane issues)
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t tx_bytes = (uint32_t)(kABytes + b_bytes);
+    const int PQ = p.P * p.Q;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / p.num_n_blocks;
+      const int n_blk = tile - m_blk * p.num_n_blocks;
+      const int m0 = m_blk * kBlockM;
+      const int n0 = n_blk * p.block_n;
+      int img = 0, cw = 0, ch = 0;
+      if (p.a_mode == 1) {
+        img = m0 / PQ;
+        const int rem = m0 - img * PQ;
+        const int pp = rem / p.Q;
+        const int qq = rem - pp * p.Q;
+        cw = qq * p.conv_stride + p.lower_w;
+        ch = pp * p.conv_stride + p.lower_h;
+      }
+      int cb = 0, off_w = 0, off_h = 0, tap_s = 0;  // incremental (channel block, tap) counters: no divides in the loop
+      for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (ptx::elect_one()) {
           ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
           if (p.a_mode == 0) {
             ptx::tma_load_2d(smem_a + stage * kABytes, &p.tmap_a, &full_bar[stage], kb * kBlockK, m0);
           } else {
-            const int tap = kb / p.cblocks;
-            const int c0 = (kb - tap * p.cblocks) * kBlockK;
-            const int r = tap / p.S;
-            const int s = tap - r * p.S;
-            ptx::tma_load_im2col_4d(smem_a + stage * kABytes, &p.tmap_a, &full_bar[stage], c0, cw, ch, img,
-                                    (uint16_t)(s * p.dil), (uint16_t)(r * p.dil));
+            ptx::tma_load_im2col_4d(smem_a + stage * kABytes, &p.tmap_a, &full_bar[stage], cb * kBlockK, cw, ch, img,
+                                    (uint16_t)off_w, (uint16_t)off_h);
           }
           ptx::tma_load_2d(smem_b + stage * b_bytes, &p.tmap_b, &full_bar[stage], kb * kBlockK, n0);
-          if (++stage == stages) {
-            stage = 0;
-            phase ^= 1;
+        }
+        __syncwarp();
+        if (++cb == p.cblocks) {
+          cb = 0;
+          off_w += p.dil;
+          if (++tap_s == p.S) {
+            tap_s = 0;
+            off_w = 0;
+            off_h += p.dil;
           }
+        }
+        if (++stage == stages) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ------------------------------------------------------------ MMA issuer
-      const uint32_t idesc = ptx::make_idesc_bf16_f32(kBlockM, p.block_n);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+    // ------------------------------------------------------------ MMA issuer (whole warp loops, one lane issues)
+    const uint32_t idesc = ptx::make_idesc_bf16_f32(kBlockM, p.block_n);
+    const uint64_t adesc0 = ptx::make_desc_k_sw128(ptx::smem_u32(smem_a));
+    const uint64_t bdesc0 = ptx::make_desc_k_sw128(ptx::smem_u32(smem_b));
+    const uint32_t a_step = kABytes >> 4, b_step = (uint32_t)b_bytes >> 4;
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.block_n);
+      for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.block_n);
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-          ptx::mbar_wait(&full_bar[stage], phase);
-          ptx::tc_fence_after();
-          const uint64_t adesc = ptx::make_desc_k_sw128(ptx::smem_u32(smem_a + stage * kABytes));
-          const uint64_t bdesc = ptx::make_desc_k_sw128(ptx::smem_u32(smem_b + stage * b_bytes));
+        if (ptx::elect_one()) {
+          const uint64_t adesc = adesc0 + (uint64_t)(stage * a_step);
+          const uint64_t bdesc = bdesc0 + (uint64_t)(stage * b_step);
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
             ptx::umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
           }
           ptx::umma_commit(&empty_bar[stage]);
-          if (++stage == stages) {
-            stage = 0;
-            phase ^= 1;
-          }
+          if (kb == p.num_k_blocks - 1) ptx::umma_commit(&tmem_full_bar[acc]);
         }
-        ptx::umma_commit(&tmem_full_bar[acc]);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        __syncwarp();
+        if (++stage == stages) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
   } else if (p.epi_mode == 0) {
     // -------------------------------------------------------------- epilogue, direct stores (fp32 head GEMM)
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    float* ss = smem_ss + (warp - 2) * 512;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -184,6 +205,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       const int row = m_blk * kBlockM + quad * 32 + lane;
       const int n0 = n_blk * p.block_n;
       const bool row_ok = row < p.M;
+      load_scale_shift(ss, p.scale, p.shift, n0, p.block_n, lane);
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.block_n);
@@ -196,7 +218,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 #pragma unroll
           for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
           const int n = n0 + c0;
-          apply_scale_shift(f, p.scale, p.shift, n);
+          apply_scale_shift(f, ss, ss + 256, c0);
           if (p.relu) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.0f);
@@ -229,6 +251,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     const bool has_res = p.residual != nullptr;
     const int chunks_per_tile = p.block_n / kEpiChunkCols;
     const int PQ = p.P * p.Q;
+    float* ss = smem_ss + ew * 512;
+    int ss_n0 = -1;
     // my byte offset inside a 128 B swizzled staging row: 16 B unit (u ^ (lane & 7))
     uint8_t* my_row = nullptr;
 
@@ -266,6 +290,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       const int n_blk = tile - m_blk * p.num_n_blocks;
       const int row0 = m_blk * kBlockM + quad * 32;
       const int n0 = n_blk * p.block_n;
+      if (n0 != ss_n0) {
+        load_scale_shift(ss, p.scale, p.shift, n0, p.block_n, lane);
+        ss_n0 = n0;
+      }
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.block_n);
@@ -287,7 +315,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           float f[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-          apply_scale_shift(f, p.scale, p.shift, n0 + c * kEpiChunkCols + sub * 16);
+          apply_scale_shift(f, ss, ss + 256, c * kEpiChunkCols + sub * 16);
           uint4* s0 = reinterpret_cast<uint4*>(my_row + (((2 * sub) ^ (lane & 7)) << 4));
           uint4* s1 = reinterpret_cast<uint4*>(my_row + (((2 * sub + 1) ^ (lane & 7)) << 4));
           if (has_res) {
@@ -417,7 +445,7 @@ const char* make_tmap_im2col(CUtensorMap* out, const void* base, uint64_t C, uin
 
 size_t conv_gemm_smem_bytes(int block_n, int num_stages, int epi_bufs) {
   return 1024 + (size_t)num_stages * (kABytes + (size_t)block_n * kBlockK * 2) + (size_t)4 * epi_bufs * kEpiChunkBytes +
-         (2 * kMaxStages + 4 + 4 * kMaxEpiBufs) * 8 + 16;
+         4 * 512 * sizeof(float) + (2 * kMaxStages + 4 + 4 * kMaxEpiBufs) * 8 + 16;
 }
 
 int conv_gemm_pick_stages(int block_n, int epi_bufs) {
