@@ -256,31 +256,48 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     // my byte offset inside a 128 B swizzled staging row: 16 B unit (u ^ (lane & 7))
     uint8_t* my_row = nullptr;
 
-    // residual prefetch for the g-th chunk of this CTA's chunk sequence (lane 0 only)
-    auto issue_residual = [&](int g) {
-      const int tile = blockIdx.x + (g / chunks_per_tile) * gridDim.x;
-      if (tile >= num_tiles) return;
-      const int c = g - (g / chunks_per_tile) * chunks_per_tile;
-      const int m_blk = tile / p.num_n_blocks;
-      const int n_blk = tile - m_blk * p.num_n_blocks;
-      const int row0 = m_blk * kBlockM + quad * 32;
-      const int col0 = n_blk * p.block_n + c * kEpiChunkCols;
-      const int buf = g % nb;
-      ptx::mbar_arrive_expect_tx(&rbar[buf], (uint32_t)kEpiChunkBytes);
-      if (p.res_sub == 1) {
-        ptx::tma_load_2d(ebuf + buf * kEpiChunkBytes, &p.tmap_res, &rbar[buf], col0, row0);
-      } else {
-        const int img = row0 / PQ;
-        const int rem = row0 - img * PQ;
+    const int nb_mask = nb - 1;              // nb is 2 or 4
+    const int nb_shift = nb == 4 ? 2 : 1;
+
+    // Residual prefetch cursor: walks this CTA's (tile, chunk) sequence nb-1 chunks ahead of the consumer.
+    // All lanes keep the (uniform) cursor; lane 0 issues.  Divisions happen once per tile, not per chunk.
+    int pf_g = 0, pf_tile = blockIdx.x, pf_c = 0, pf_row0 = 0, pf_col0 = 0, pf_img = 0, pf_w = 0, pf_h = 0;
+    auto pf_setup_tile = [&]() {
+      const int m_blk = pf_tile / p.num_n_blocks;
+      const int n_blk = pf_tile - m_blk * p.num_n_blocks;
+      pf_row0 = m_blk * kBlockM + quad * 32;
+      pf_col0 = n_blk * p.block_n;
+      if (p.res_sub != 1) {
+        pf_img = pf_row0 / PQ;
+        const int rem = pf_row0 - pf_img * PQ;
         const int pp = rem / p.Q;
-        const int qq = rem - pp * p.Q;
-        ptx::tma_load_im2col_4d(ebuf + buf * kEpiChunkBytes, &p.tmap_res, &rbar[buf], col0, qq * p.res_sub,
-                                pp * p.res_sub, img, 0, 0);
+        pf_h = pp * p.res_sub;
+        pf_w = (rem - pp * p.Q) * p.res_sub;
+      }
+    };
+    auto issue_residual = [&]() {
+      if (pf_tile >= num_tiles) return;
+      if (lane == 0) {
+        const int buf = pf_g & nb_mask;
+        ptx::mbar_arrive_expect_tx(&rbar[buf], (uint32_t)kEpiChunkBytes);
+        if (p.res_sub == 1) {
+          ptx::tma_load_2d(ebuf + buf * kEpiChunkBytes, &p.tmap_res, &rbar[buf], pf_col0 + pf_c * kEpiChunkCols, pf_row0);
+        } else {
+          ptx::tma_load_im2col_4d(ebuf + buf * kEpiChunkBytes, &p.tmap_res, &rbar[buf], pf_col0 + pf_c * kEpiChunkCols,
+                                  pf_w, pf_h, pf_img, 0, 0);
+        }
+      }
+      ++pf_g;
+      if (++pf_c == chunks_per_tile) {
+        pf_c = 0;
+        pf_tile += gridDim.x;
+        if (pf_tile < num_tiles) pf_setup_tile();
       }
     };
 
-    if (has_res && lane == 0) {
-      for (int g = 0; g < nb - 1; ++g) issue_residual(g);
+    if (has_res) {
+      if (pf_tile < num_tiles) pf_setup_tile();
+      for (int i = 0; i < nb - 1; ++i) issue_residual();
     }
     int g = 0;  // chunk sequence number
     int acc = 0;
@@ -298,23 +315,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.block_n);
       for (int c = 0; c < chunks_per_tile; ++c, ++g) {
-        const int buf = g % nb;
+        const int buf = g & nb_mask;
         my_row = ebuf + buf * kEpiChunkBytes + lane * 128;
+        // all four TMEM loads of the chunk are in flight before the single wait (LDTM latency paid once per chunk)
+        uint32_t v[kEpiChunkCols / 16][16];
+#pragma unroll
+        for (int sub = 0; sub < kEpiChunkCols / 16; ++sub)
+          ptx::tmem_ld_x16(taddr + (uint32_t)(c * kEpiChunkCols + sub * 16), v[sub]);
         if (has_res) {
-          ptx::mbar_wait(&rbar[buf], (uint32_t)((g / nb) & 1));
+          ptx::mbar_wait(&rbar[buf], (uint32_t)((g >> nb_shift) & 1));
         } else {
           // the store that last used this buffer (chunk g - nb) must have finished reading it
           if (lane == 0) ptx::bulk_wait_group_read<1>();
           __syncwarp();
         }
+        ptx::tmem_ld_wait();
 #pragma unroll
         for (int sub = 0; sub < kEpiChunkCols / 16; ++sub) {
-          uint32_t v[16];
-          ptx::tmem_ld_x16(taddr + (uint32_t)(c * kEpiChunkCols + sub * 16), v);
-          ptx::tmem_ld_wait();
           float f[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[sub][i]);
           apply_scale_shift(f, ss, ss + 256, c * kEpiChunkCols + sub * 16);
           uint4* s0 = reinterpret_cast<uint4*>(my_row + (((2 * sub) ^ (lane & 7)) << 4));
           uint4* s1 = reinterpret_cast<uint4*>(my_row + (((2 * sub + 1) ^ (lane & 7)) << 4));
@@ -341,12 +361,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         if (lane == 0) {
           ptx::tma_store_2d(&p.tmap_out, ebuf + buf * kEpiChunkBytes, n0 + c * kEpiChunkCols, row0);
           ptx::bulk_commit_group();
-          if (has_res) {
-            // chunk g+nb-1 reuses the buffer of chunk g-1: its store may be the only one still pending besides mine
-            if (g >= 1) ptx::bulk_wait_group_read<1>();
-            issue_residual(g + nb - 1);
-          }
+          // chunk g+nb-1 reuses the buffer of chunk g-1: its store may be the only one still pending besides mine
+          if (has_res && g >= 1) ptx::bulk_wait_group_read<1>();
         }
+        if (has_res) issue_residual();
         __syncwarp();
       }
       ptx::tc_fence_before();
