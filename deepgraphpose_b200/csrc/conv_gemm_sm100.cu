@@ -3,7 +3,7 @@
 // CTA = 192 threads, persistent over (m_blk, n_blk) tiles:
 //   warp 0      TMA producer   (one lane): A tile 128 x 64 (tiled or im2col) + B tile block_n x 64 per stage
 //   warp 1      MMA issuer     (one lane): 4 x tcgen05.mma (K=16) per stage into a double-buffered TMEM accumulator
-//   warps 2..5  epilogue: tcgen05.ld -> fp32 BN scale/shift (+residual)(+ReLU) -> bf16
+//   warps 2..9  epilogue: tcgen05.ld -> fp32 BN scale/shift (+residual)(+ReLU) -> bf16 (two warps per TMEM quadrant)
 // Pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty pair (MMA <-> epilogue), and per epilogue warp a
 // ring of 4 KB staging buffers (32 rows x 64 channels, SWIZZLE_128B): the residual tile is TMA-loaded into a buffer
 // ahead of time, the warp adds it to the accumulator in place and the buffer is TMA-stored to the output, so that
@@ -18,7 +18,7 @@ namespace dgp {
 
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;  // TMA warp + MMA warp + 8 epilogue warps
 constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KiB
 constexpr int kMaxStages = 8;
 constexpr int kMaxEpiBufs = 4;
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full_bar[a], 1);
-      ptx::mbar_init(&tmem_empty_bar[a], 4);
+      ptx::mbar_init(&tmem_empty_bar[a], 8);
     }
     for (int i = 0; i < 4 * kMaxEpiBufs; ++i) ptx::mbar_init(&res_bar[i], 1);
     ptx::fence_mbar_init();
@@ -195,8 +195,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     }
   } else if (p.epi_mode == 0) {
     // -------------------------------------------------------------- epilogue, direct stores (fp32 head GEMM)
+    // 8 epilogue warps: two per TMEM lane quadrant, taking alternate 16-column groups.
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
-    float* ss = smem_ss + (warp - 2) * 512;
+    const int half = (warp - 2) >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -205,11 +206,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       const int row = m_blk * kBlockM + quad * 32 + lane;
       const int n0 = n_blk * p.block_n;
       const bool row_ok = row < p.M;
-      load_scale_shift(ss, p.scale, p.shift, n0, p.block_n, lane);
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.block_n);
-      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+      for (int c0 = half * 16; c0 < p.block_n; c0 += 32) {
         uint32_t v[16];
         ptx::tmem_ld_x16(taddr + (uint32_t)c0, v);
         ptx::tmem_ld_wait();
@@ -218,7 +218,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 #pragma unroll
           for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
           const int n = n0 + c0;
-          apply_scale_shift(f, ss, ss + 256, c0);
+          if (p.scale != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] *= __ldg(p.scale + n + i);
+          }
+          if (p.shift != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] += __ldg(p.shift + n + i);
+          }
           if (p.relu) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.0f);
@@ -243,24 +250,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     }
   } else {
     // -------------------------------------------------------------- epilogue, TMA-staged bf16 (+ TMA residual)
+    // 8 epilogue warps = 4 pairs, one pair per TMEM lane quadrant (32 rows).  The pair shares a ring of 4 KB staging
+    // buffers (32 rows x 64 channels): the leader warp (half 0) handles channels 0..31 of each chunk and issues all
+    // TMA traffic, the follower handles channels 32..63; they meet on a 64-thread named barrier before the store.
     const int quad = warp & 3;
-    const int ew = warp - 2;  // 0..3: this warp's staging ring
+    const int half = (warp - 2) >> 2;
+    const bool leader = half == 0;
     const int nb = p.epi_bufs;
-    uint8_t* ebuf = smem_epi + (size_t)ew * nb * kEpiChunkBytes;
-    uint64_t* rbar = res_bar + ew * kMaxEpiBufs;
+    uint8_t* ebuf = smem_epi + (size_t)quad * nb * kEpiChunkBytes;
+    uint64_t* rbar = res_bar + quad * kMaxEpiBufs;
+    const uint32_t pair_bar = 1u + (uint32_t)quad;
     const bool has_res = p.residual != nullptr;
     const int chunks_per_tile = p.block_n / kEpiChunkCols;
     const int PQ = p.P * p.Q;
-    float* ss = smem_ss + ew * 512;
+    float* ss = smem_ss + (warp - 2) * 256;  // this warp's [2][128] scale/shift (its 32 channels of every chunk)
     int ss_n0 = -1;
-    // my byte offset inside a 128 B swizzled staging row: 16 B unit (u ^ (lane & 7))
-    uint8_t* my_row = nullptr;
-
     const int nb_mask = nb - 1;              // nb is 2 or 4
     const int nb_shift = nb == 4 ? 2 : 1;
 
-    // Residual prefetch cursor: walks this CTA's (tile, chunk) sequence nb-1 chunks ahead of the consumer.
-    // All lanes keep the (uniform) cursor; lane 0 issues.  Divisions happen once per tile, not per chunk.
+    // Residual prefetch cursor (leader warp only): walks this CTA's (tile, chunk) sequence nb-1 chunks ahead of the
+    // consumer.  All leader lanes keep the (uniform) cursor; lane 0 issues.  Divisions happen once per tile.
     int pf_g = 0, pf_tile = blockIdx.x, pf_c = 0, pf_row0 = 0, pf_col0 = 0, pf_img = 0, pf_w = 0, pf_h = 0;
     auto pf_setup_tile = [&]() {
       const int m_blk = pf_tile / p.num_n_blocks;
@@ -295,9 +304,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       }
     };
 
-    if (has_res) {
+    if (has_res && leader) {
       if (pf_tile < num_tiles) pf_setup_tile();
       for (int i = 0; i < nb - 1; ++i) issue_residual();
+      __syncwarp();
     }
     int g = 0;  // chunk sequence number
     int acc = 0;
@@ -308,36 +318,44 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       const int row0 = m_blk * kBlockM + quad * 32;
       const int n0 = n_blk * p.block_n;
       if (n0 != ss_n0) {
-        load_scale_shift(ss, p.scale, p.shift, n0, p.block_n, lane);
+        // my 32 channels of chunk cc live at ss[cc*32 ..] (scale) and ss[128 + cc*32 ..] (shift)
+        for (int i = lane * 4; i < (p.block_n >> 1); i += 128) {
+          const int col = n0 + (i >> 5) * kEpiChunkCols + half * 32 + (i & 31);
+          const float4 sc = p.scale ? __ldg(reinterpret_cast<const float4*>(p.scale + col)) : make_float4(1.f, 1.f, 1.f, 1.f);
+          const float4 sh = p.shift ? __ldg(reinterpret_cast<const float4*>(p.shift + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(ss + i) = sc;
+          *reinterpret_cast<float4*>(ss + 128 + i) = sh;
+        }
+        __syncwarp();
         ss_n0 = n0;
       }
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.block_n);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.block_n + half * 32);
       for (int c = 0; c < chunks_per_tile; ++c, ++g) {
         const int buf = g & nb_mask;
-        my_row = ebuf + buf * kEpiChunkBytes + lane * 128;
-        // all four TMEM loads of the chunk are in flight before the single wait (LDTM latency paid once per chunk)
-        uint32_t v[kEpiChunkCols / 16][16];
-#pragma unroll
-        for (int sub = 0; sub < kEpiChunkCols / 16; ++sub)
-          ptx::tmem_ld_x16(taddr + (uint32_t)(c * kEpiChunkCols + sub * 16), v[sub]);
+        uint8_t* my_row = ebuf + buf * kEpiChunkBytes + lane * 128;
+        // both TMEM loads of my half-chunk are in flight before the single wait
+        uint32_t v[2][16];
+        ptx::tmem_ld_x16(taddr + (uint32_t)(c * kEpiChunkCols), v[0]);
+        ptx::tmem_ld_x16(taddr + (uint32_t)(c * kEpiChunkCols + 16), v[1]);
         if (has_res) {
           ptx::mbar_wait(&rbar[buf], (uint32_t)((g >> nb_shift) & 1));
         } else {
           // the store that last used this buffer (chunk g - nb) must have finished reading it
-          if (lane == 0) ptx::bulk_wait_group_read<1>();
-          __syncwarp();
+          if (leader && lane == 0) ptx::bulk_wait_group_read<1>();
+          ptx::named_bar_sync(pair_bar, 64);
         }
         ptx::tmem_ld_wait();
 #pragma unroll
-        for (int sub = 0; sub < kEpiChunkCols / 16; ++sub) {
+        for (int s2 = 0; s2 < 2; ++s2) {
           float f[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[sub][i]);
-          apply_scale_shift(f, ss, ss + 256, c * kEpiChunkCols + sub * 16);
-          uint4* s0 = reinterpret_cast<uint4*>(my_row + (((2 * sub) ^ (lane & 7)) << 4));
-          uint4* s1 = reinterpret_cast<uint4*>(my_row + (((2 * sub + 1) ^ (lane & 7)) << 4));
+          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[s2][i]);
+          apply_scale_shift(f, ss, ss + 128, c * 32 + s2 * 16);
+          const int u = 4 * half + 2 * s2;  // 16-byte unit inside the 128 B staging row (SWIZZLE_128B: u ^ (row & 7))
+          uint4* s0 = reinterpret_cast<uint4*>(my_row + ((u ^ (lane & 7)) << 4));
+          uint4* s1 = reinterpret_cast<uint4*>(my_row + (((u + 1) ^ (lane & 7)) << 4));
           if (has_res) {
             const uint4 r0 = *s0;
             const uint4 r1 = *s1;
@@ -357,15 +375,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                            pack_bf16(f[14], f[15]));
         }
         ptx::fence_proxy_async_smem();  // my generic-proxy smem writes -> visible to the TMA store (async proxy)
-        __syncwarp();
-        if (lane == 0) {
-          ptx::tma_store_2d(&p.tmap_out, ebuf + buf * kEpiChunkBytes, n0 + c * kEpiChunkCols, row0);
-          ptx::bulk_commit_group();
-          // chunk g+nb-1 reuses the buffer of chunk g-1: its store may be the only one still pending besides mine
-          if (has_res && g >= 1) ptx::bulk_wait_group_read<1>();
+        ptx::named_bar_sync(pair_bar, 64);
+        if (leader) {
+          if (lane == 0) {
+            ptx::tma_store_2d(&p.tmap_out, ebuf + buf * kEpiChunkBytes, n0 + c * kEpiChunkCols, row0);
+            ptx::bulk_commit_group();
+            // chunk g+nb-1 reuses the buffer of chunk g-1: its store may be the only one still pending besides mine
+            if (has_res && g >= 1) ptx::bulk_wait_group_read<1>();
+          }
+          if (has_res) issue_residual();
+          __syncwarp();
         }
-        if (has_res) issue_residual();
-        __syncwarp();
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -373,7 +393,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-    if (lane == 0) ptx::bulk_wait_group_read<0>();
+    if (leader && lane == 0) ptx::bulk_wait_group_read<0>();
     __syncwarp();
   }
 
