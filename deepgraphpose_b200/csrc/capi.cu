@@ -336,7 +336,12 @@ int setup_epilogue(dgp_handle* h, ConvGemmParams& g, const char* scope, int n_im
       if (e) return fail(h, DGP_ERR_CUDA, "%s (residual map): %s", scope, e);
     }
   }
-  g.num_stages = conv_gemm_pick_stages(g.block_n, g.epi_bufs);
+  // narrow layers (N tile <= 128) run 256-row CTA tiles: one TMA + two UMMAs per k-step halves the per-k-block
+  // issue overhead of the single-warp producer / MMA loops (see DESIGN.md "BLOCK_M = 256")
+  g.msub = (g.epi_mode == 1 && g.block_n <= 128 && g.M > kBlockM) ? 2 : 1;
+  g.num_m_blocks = ceil_div(g.M, kBlockM * g.msub);
+  g.tmem_cols = tmem_cols_for(g.block_n * g.msub);
+  g.num_stages = conv_gemm_pick_stages(g.block_n, g.epi_bufs, g.msub);
   return DGP_OK;
 }
 
@@ -394,13 +399,13 @@ int make_gemm_step(dgp_handle* h, const ConvLayer& L, const void* x, int N, int 
   const bool pointwise = (L.R == 1 && L.S == 1 && L.stride == 1);
   if (pointwise) {
     g.a_mode = 0;
-    e = make_tmap_2d(&g.tmap_a, x, (uint64_t)g.M, (uint64_t)L.K, (uint64_t)L.K * 2, kBlockM);
+    e = make_tmap_2d(&g.tmap_a, x, (uint64_t)g.M, (uint64_t)L.K, (uint64_t)L.K * 2, kBlockM * g.msub);
   } else {
     g.a_mode = 1;
     const int up_h = upper_h - (L.R - 1) * L.dil, up_w = upper_w - (L.S - 1) * L.dil;
     e = make_tmap_im2col(&g.tmap_a, x, (uint64_t)L.Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N, (uint64_t)L.Cin * 2,
                          (uint64_t)W * L.Cin * 2, (uint64_t)H * W * L.Cin * 2, -lower_w, -lower_h, up_w, up_h, L.stride,
-                         (uint64_t)N * H * W * L.Cin * 2);
+                         (uint64_t)N * H * W * L.Cin * 2, kBlockM * g.msub);
   }
   if (e) return fail(h, DGP_ERR_CUDA, "%s: %s", L.scope.c_str(), e);
   e = make_tmap_2d(&g.tmap_b, L.w, (uint64_t)L.Npad, (uint64_t)L.K, (uint64_t)L.K * 2, (uint32_t)bn);
@@ -467,7 +472,7 @@ int build_plan(dgp_handle* h, int B, int H, int W, Plan** out) {
     if ((rc = setup_epilogue(h, g, "conv1", B))) return rc;
     const char* e = make_tmap_im2col(&g.tmap_a, pl->s2d, 64, (uint64_t)pl->W1, (uint64_t)pl->Hs, (uint64_t)B, 32,
                                      (uint64_t)pl->Ws * 32, (uint64_t)pl->Hs * pl->Ws * 32, 0, 0, 0, -3, 1,
-                                     (uint64_t)B * pl->Hs * pl->Ws * 32);
+                                     (uint64_t)B * pl->Hs * pl->Ws * 32, kBlockM * g.msub);
     if (e) return fail(h, DGP_ERR_CUDA, "conv1: %s", e);
     e = make_tmap_2d(&g.tmap_b, L.w, 64, 256, 512, 64);
     if (e) return fail(h, DGP_ERR_CUDA, "conv1: %s", e);

@@ -60,9 +60,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stages = p.num_stages;
+  const int msub = p.msub;                     // 128-row sub-tiles per CTA tile (BLOCK_M = 128 * msub)
+  const int a_bytes = msub * kABytes;
   const int b_bytes = p.block_n * kBlockK * 2;
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + stages * kABytes;
+  uint8_t* smem_b = smem + stages * a_bytes;
   uint8_t* smem_epi = smem_b + stages * b_bytes;  // [4 warps][epi_bufs][4 KiB], 1024 B aligned
   const int epi_bufs = p.epi_mode == 1 ? p.epi_bufs : 0;
   float* smem_ss = reinterpret_cast<float*>(smem_epi + 4 * epi_bufs * kEpiChunkBytes);  // [4 warps][2][256]
@@ -109,45 +111,49 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (whole warp loops, one lane issues)
+    // Kernel parameters used inside the k loop are copied to registers first: every c[0x0][..] re-read is a
+    // ~10-cycle uniform load on the single-warp critical path.
     int stage = 0;
     uint32_t phase = 0;
-    const uint32_t tx_bytes = (uint32_t)(kABytes + b_bytes);
-    const int PQ = p.P * p.Q;
+    const uint32_t tx_bytes = (uint32_t)(a_bytes + b_bytes);
+    const int PQ = p.P * p.Q, Q = p.Q, nnb = p.num_n_blocks, nkb = p.num_k_blocks, block_n = p.block_n;
+    const int a_mode = p.a_mode, cblocks = p.cblocks, S = p.S, dil = p.dil, cstride = p.conv_stride;
+    const int lower_w = p.lower_w, lower_h = p.lower_h, block_m = kBlockM * msub;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / p.num_n_blocks;
-      const int n_blk = tile - m_blk * p.num_n_blocks;
-      const int m0 = m_blk * kBlockM;
-      const int n0 = n_blk * p.block_n;
+      const int m_blk = tile / nnb;
+      const int n_blk = tile - m_blk * nnb;
+      const int m0 = m_blk * block_m;
+      const int n0 = n_blk * block_n;
       int img = 0, cw = 0, ch = 0;
-      if (p.a_mode == 1) {
+      if (a_mode == 1) {
         img = m0 / PQ;
         const int rem = m0 - img * PQ;
-        const int pp = rem / p.Q;
-        const int qq = rem - pp * p.Q;
-        cw = qq * p.conv_stride + p.lower_w;
-        ch = pp * p.conv_stride + p.lower_h;
+        const int pp = rem / Q;
+        const int qq = rem - pp * Q;
+        cw = qq * cstride + lower_w;
+        ch = pp * cstride + lower_h;
       }
       int cb = 0, off_w = 0, off_h = 0, tap_s = 0;  // incremental (channel block, tap) counters: no divides in the loop
-      for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+      for (int kb = 0; kb < nkb; ++kb) {
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
         if (ptx::elect_one()) {
           ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-          if (p.a_mode == 0) {
-            ptx::tma_load_2d(smem_a + stage * kABytes, &p.tmap_a, &full_bar[stage], kb * kBlockK, m0);
+          if (a_mode == 0) {
+            ptx::tma_load_2d(smem_a + stage * a_bytes, &p.tmap_a, &full_bar[stage], kb * kBlockK, m0);
           } else {
-            ptx::tma_load_im2col_4d(smem_a + stage * kABytes, &p.tmap_a, &full_bar[stage], cb * kBlockK, cw, ch, img,
+            ptx::tma_load_im2col_4d(smem_a + stage * a_bytes, &p.tmap_a, &full_bar[stage], cb * kBlockK, cw, ch, img,
                                     (uint16_t)off_w, (uint16_t)off_h);
           }
           ptx::tma_load_2d(smem_b + stage * b_bytes, &p.tmap_b, &full_bar[stage], kb * kBlockK, n0);
         }
         __syncwarp();
-        if (++cb == p.cblocks) {
+        if (++cb == cblocks) {
           cb = 0;
-          off_w += p.dil;
-          if (++tap_s == p.S) {
+          off_w += dil;
+          if (++tap_s == S) {
             tap_s = 0;
             off_w = 0;
-            off_h += p.dil;
+            off_h += dil;
           }
         }
         if (++stage == stages) {
@@ -158,10 +164,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (whole warp loops, one lane issues)
-    const uint32_t idesc = ptx::make_idesc_bf16_f32(kBlockM, p.block_n);
+    const int block_n = p.block_n, nkb = p.num_k_blocks;
+    const uint32_t idesc = ptx::make_idesc_bf16_f32(kBlockM, block_n);
     const uint64_t adesc0 = ptx::make_desc_k_sw128(ptx::smem_u32(smem_a));
     const uint64_t bdesc0 = ptx::make_desc_k_sw128(ptx::smem_u32(smem_b));
-    const uint32_t a_step = kABytes >> 4, b_step = (uint32_t)b_bytes >> 4;
+    const uint32_t a_step = (uint32_t)a_bytes >> 4, b_step = (uint32_t)b_bytes >> 4;
+    const uint32_t acc_cols = (uint32_t)(msub * block_n);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -169,8 +177,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
       ptx::tc_fence_after();
-      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.block_n);
-      for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+      const uint32_t tmem_d = tmem_base + (uint32_t)acc * acc_cols;
+      for (int kb = 0; kb < nkb; ++kb) {
         ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
@@ -180,9 +188,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           for (int k = 0; k < kBlockK / 16; ++k) {
             // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
             ptx::umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            if (msub == 2)  // second 128-row half of a 256-row tile: A rows 128..255 sit 16 KiB further, D BN columns further
+              ptx::umma_bf16(tmem_d + (uint32_t)block_n, adesc + (uint64_t)((kABytes >> 4) + k * 2),
+                             bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
           }
           ptx::umma_commit(&empty_bar[stage]);
-          if (kb == p.num_k_blocks - 1) ptx::umma_commit(&tmem_full_bar[acc]);
+          if (kb == nkb - 1) ptx::umma_commit(&tmem_full_bar[acc]);
         }
         __syncwarp();
         if (++stage == stages) {
@@ -270,11 +281,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 
     // Residual prefetch cursor (leader warp only): walks this CTA's (tile, chunk) sequence nb-1 chunks ahead of the
     // consumer.  All leader lanes keep the (uniform) cursor; lane 0 issues.  Divisions happen once per tile.
-    int pf_g = 0, pf_tile = blockIdx.x, pf_c = 0, pf_row0 = 0, pf_col0 = 0, pf_img = 0, pf_w = 0, pf_h = 0;
+    int pf_g = 0, pf_tile = blockIdx.x, pf_c = 0, pf_sub = 0, pf_row0 = 0, pf_col0 = 0, pf_img = 0, pf_w = 0, pf_h = 0;
     auto pf_setup_tile = [&]() {
       const int m_blk = pf_tile / p.num_n_blocks;
       const int n_blk = pf_tile - m_blk * p.num_n_blocks;
-      pf_row0 = m_blk * kBlockM + quad * 32;
+      pf_row0 = (m_blk * msub + pf_sub) * kBlockM + quad * 32;
       pf_col0 = n_blk * p.block_n;
       if (p.res_sub != 1) {
         pf_img = pf_row0 / PQ;
@@ -299,7 +310,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       ++pf_g;
       if (++pf_c == chunks_per_tile) {
         pf_c = 0;
-        pf_tile += gridDim.x;
+        if (++pf_sub == msub) {
+          pf_sub = 0;
+          pf_tile += gridDim.x;
+        }
         if (pf_tile < num_tiles) pf_setup_tile();
       }
     };
@@ -315,7 +329,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / p.num_n_blocks;
       const int n_blk = tile - m_blk * p.num_n_blocks;
-      const int row0 = m_blk * kBlockM + quad * 32;
       const int n0 = n_blk * p.block_n;
       if (n0 != ss_n0) {
         // my 32 channels of chunk cc live at ss[cc*32 ..] (scale) and ss[128 + cc*32 ..] (shift)
@@ -331,7 +344,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       }
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.block_n + half * 32);
+      for (int sub = 0; sub < msub; ++sub) {
+      const int row0 = (m_blk * msub + sub) * kBlockM + quad * 32;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) +
+                             (uint32_t)((acc * msub + sub) * p.block_n + half * 32);
       for (int c = 0; c < chunks_per_tile; ++c, ++g) {
         const int buf = g & nb_mask;
         uint8_t* my_row = ebuf + buf * kEpiChunkBytes + lane * 128;
@@ -387,6 +403,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           __syncwarp();
         }
       }
+      }  // sub
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
@@ -481,15 +498,15 @@ const char* make_tmap_im2col(CUtensorMap* out, const void* base, uint64_t C, uin
   return nullptr;
 }
 
-size_t conv_gemm_smem_bytes(int block_n, int num_stages, int epi_bufs) {
-  return 1024 + (size_t)num_stages * (kABytes + (size_t)block_n * kBlockK * 2) + (size_t)4 * epi_bufs * kEpiChunkBytes +
+size_t conv_gemm_smem_bytes(int block_n, int num_stages, int epi_bufs, int msub) {
+  return 1024 + (size_t)num_stages * ((size_t)msub * kABytes + (size_t)block_n * kBlockK * 2) + (size_t)4 * epi_bufs * kEpiChunkBytes +
          4 * 512 * sizeof(float) + (2 * kMaxStages + 4 + 4 * kMaxEpiBufs) * 8 + 16;
 }
 
-int conv_gemm_pick_stages(int block_n, int epi_bufs) {
+int conv_gemm_pick_stages(int block_n, int epi_bufs, int msub) {
   const size_t budget = 227 * 1024;
   int s = kMaxStages;
-  while (s > 2 && conv_gemm_smem_bytes(block_n, s, epi_bufs) > budget) --s;
+  while (s > 2 && conv_gemm_smem_bytes(block_n, s, epi_bufs, msub) > budget) --s;
   return s;
 }
 
@@ -502,7 +519,7 @@ cudaError_t launch_conv_gemm(const ConvGemmParams& p, int num_sms, cudaStream_t 
   }
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   const int grid = tiles < num_sms ? tiles : num_sms;
-  const size_t smem = conv_gemm_smem_bytes(p.block_n, p.num_stages, p.epi_mode == 1 ? p.epi_bufs : 0);
+  const size_t smem = conv_gemm_smem_bytes(p.block_n, p.num_stages, p.epi_mode == 1 ? p.epi_bufs : 0, p.msub);
   conv_gemm_kernel<<<grid, kThreads, smem, stream>>>(p);
   return cudaGetLastError();
 }

@@ -33,6 +33,7 @@ struct ConvGemmParams {
   int M;             // output pixels
   int N;             // output channels (multiple of block_n)
   int block_n;       // UMMA N (multiple of 16, 16..256)
+  int msub;          // 128-row sub-tiles per CTA tile: 1, or 2 (BLOCK_M = 256) for narrow layers (block_n <= 128)
   int num_k_blocks;  // K / 64
   int a_mode;        // 0 = tiled [M,K], 1 = im2col
   // im2col geometry (a_mode == 1)
@@ -70,8 +71,8 @@ const char* make_tmap_im2col(CUtensorMap* out, const void* base, uint64_t C, uin
                              uint64_t stride_w_bytes, uint64_t stride_h_bytes, uint64_t stride_n_bytes, int lower_w,
                              int lower_h, int upper_w, int upper_h, int conv_stride, uint64_t total_bytes,
                              uint32_t pixels_per_column = kBlockM);
-size_t conv_gemm_smem_bytes(int block_n, int num_stages, int epi_bufs);
-int conv_gemm_pick_stages(int block_n, int epi_bufs);
+size_t conv_gemm_smem_bytes(int block_n, int num_stages, int epi_bufs, int msub);
+int conv_gemm_pick_stages(int block_n, int epi_bufs, int msub);
 cudaError_t launch_conv_gemm(const ConvGemmParams& p, int num_sms, cudaStream_t stream);
 
 }  // namespace dgp
