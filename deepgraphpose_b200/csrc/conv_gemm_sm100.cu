@@ -12,6 +12,8 @@
 
 #include <stdio.h>
 
+#include <type_traits>
+
 #include "ptx_sm100.cuh"
 
 namespace dgp {
@@ -174,36 +176,42 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
-      ptx::tc_fence_after();
-      const uint32_t tmem_d = tmem_base + (uint32_t)acc * acc_cols;
-      for (int kb = 0; kb < nkb; ++kb) {
-        ptx::mbar_wait(&full_bar[stage], phase);
+    // The two tile heights get separate, branch-free issue loops (a predicate between UTCHMMAs costs issue slots).
+    auto run = [&](auto msub_tag) {
+      constexpr int kMsub = decltype(msub_tag)::value;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
-        if (ptx::elect_one()) {
-          const uint64_t adesc = adesc0 + (uint64_t)(stage * a_step);
-          const uint64_t bdesc = bdesc0 + (uint64_t)(stage * b_step);
+        const uint32_t tmem_d = tmem_base + (uint32_t)acc * acc_cols;
+        for (int kb = 0; kb < nkb; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            const uint64_t adesc = adesc0 + (uint64_t)(stage * a_step);
+            const uint64_t bdesc = bdesc0 + (uint64_t)(stage * b_step);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
-            ptx::umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-            if (msub == 2)  // second 128-row half of a 256-row tile: A rows 128..255 sit 16 KiB further, D BN columns further
-              ptx::umma_bf16(tmem_d + (uint32_t)block_n, adesc + (uint64_t)((kABytes >> 4) + k * 2),
-                             bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
+              ptx::umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+              if (kMsub == 2)  // rows 128..255 of a 256-row tile: A 16 KiB further, D block_n columns further
+                ptx::umma_bf16(tmem_d + (uint32_t)block_n, adesc + (uint64_t)((kABytes >> 4) + k * 2),
+                               bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            }
+            ptx::umma_commit(&empty_bar[stage]);
+            if (kb == nkb - 1) ptx::umma_commit(&tmem_full_bar[acc]);
           }
-          ptx::umma_commit(&empty_bar[stage]);
-          if (kb == nkb - 1) ptx::umma_commit(&tmem_full_bar[acc]);
+          __syncwarp();
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
-        __syncwarp();
-        if (++stage == stages) {
-          stage = 0;
-          phase ^= 1;
-        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
       }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
-    }
+    };
+    if (msub == 2) run(std::integral_constant<int, 2>{});
+    else run(std::integral_constant<int, 1>{});
   } else if (p.epi_mode == 0) {
     // -------------------------------------------------------------- epilogue, direct stores (fp32 head GEMM)
     // 8 epilogue warps: two per TMEM lane quadrant, taking alternate 16-column groups.
