@@ -31,6 +31,22 @@ class DgpConfig(C.Structure):
     ]
 
 
+class DgpLossCfg(C.Structure):
+    _fields_ = [("gamma", C.c_float), ("gauss_len", C.c_float), ("lengthscale", C.c_float), ("wt", C.c_float),
+                ("wt_max", C.c_float), ("wn_visible", C.c_float), ("wn_hidden", C.c_float),
+                ("locref_loss_weight", C.c_float), ("n_frames_total", C.c_float), ("n_visible_frames_total", C.c_float),
+                ("gm2", C.c_int32), ("gm3", C.c_int32)]
+
+
+class DgpLossBatch(C.Structure):
+    _fields_ = [("pred_dev", C.c_void_p), ("locref_dev", C.c_void_p), ("nt", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+                ("targets_dev", C.c_void_p), ("nv", C.c_int32), ("locref_map_dev", C.c_void_p),
+                ("locref_mask_dev", C.c_void_p), ("visible_marker_dev", C.c_void_p), ("nbv", C.c_int32),
+                ("hidden_marker_dev", C.c_void_p), ("nbh", C.c_int32), ("visible_marker_in_targets_dev", C.c_void_p),
+                ("edges_dev", C.c_void_p), ("nl", C.c_int32), ("ws_dev", C.c_void_p), ("ws_max_dev", C.c_void_p),
+                ("vector_field_dev", C.c_void_p), ("Hin", C.c_int32), ("Win", C.c_int32), ("wt_batch_dev", C.c_void_p)]
+
+
 # name -> (restype, argtypes); kept in one table so the CPU test-suite can check every exported symbol.
 _vp, _i, _f, _sz, _i64p = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.POINTER(C.c_int64)
 SIGNATURES = {
@@ -43,6 +59,7 @@ SIGNATURES = {
     "dgp_forward": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "dgp_softargmax": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dgp_softmax_map": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _f, _vp, _vp]),
+    "dgp_loss_forward": (_i, [_vp, C.POINTER(DgpLossCfg), C.POINTER(DgpLossBatch), _vp, _vp, _vp]),
     "dgp_sigmoid": (_i, [_vp, _vp, _vp, _sz, _vp]),
     "dgp_potentials": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp]),
     "dgp_estimate_pose_host": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp]),

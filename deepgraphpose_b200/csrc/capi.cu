@@ -109,6 +109,7 @@ struct dgp_handle {
   // softargmax workspace
   SaPartial* sa_ws = nullptr;
   size_t sa_ws_bytes = 0;
+  DevBuf loss_ws;
   // estimate_pose_host staging
   cudaStream_t stream = nullptr;       // compute stream of dgp_estimate_pose_host
   cudaStream_t copy_stream = nullptr;  // H2D of the next batch overlaps the current batch's kernels
@@ -666,6 +667,7 @@ void dgp_destroy(dgp_handle* h) {
     for (auto& b : kv.second->bufs) cudaFree(b.p);
   for (auto& kv : h->kept) cudaFree(kv.second.p);
   cudaFree(h->sa_ws);
+  cudaFree(h->loss_ws.p);
   cudaFree(h->st_frames2[0].p);
   cudaFree(h->st_frames2[1].p);
   for (int i = 0; i < 2; ++i) {
@@ -832,6 +834,58 @@ int dgp_softmax_map(dgp_handle* h, const float* logits_dev, int B, int H, int W,
                              h->sa_ws, splits, nullptr, nullptr, nullptr, nullptr, nullptr, norm, (cudaStream_t)stream));
   CU_OK(h, launch_softmax_map(logits_dev, norm, B, H, W, nj, gamma, gauss_len, map_dev, h->num_sms, (cudaStream_t)stream));
   h->launches += 3;
+  return DGP_OK;
+}
+
+int dgp_loss_forward(dgp_handle* h, const dgp_loss_cfg* cfg, const dgp_loss_batch* b, float* losses_dev,
+                     float* targets_all_dev, void* stream) {
+  if (!h) return DGP_ERR_INVALID;
+  if (!cfg || !b || !losses_dev || !b->pred_dev) return fail(h, DGP_ERR_INVALID, "dgp_loss_forward: null argument");
+  const int nj = h->cfg.num_joints;
+  if (b->nt < 1 || b->nbv < 0 || b->nbh < 0 || b->nbv + b->nbh > b->nt * nj)
+    return fail(h, DGP_ERR_INVALID, "dgp_loss_forward: bad marker counts");
+  if (cfg->gm2 < 0 || cfg->gm2 > 2 || (cfg->gm3 != 0 && cfg->gm3 != 3))
+    return fail(h, DGP_ERR_INVALID, "dgp_loss_forward: Not implemented (gm2 in {0,1,2}, gm3 in {0,3}; fitdgp.py:1021,1037)");
+  if (cfg->gm3 == 3 && cfg->gm2 == 0)
+    return fail(h, DGP_ERR_INVALID, "dgp_loss_forward: gm3=3 needs gm2 in {1,2} (pred_h_scaled1 is undefined in the reference)");
+  if (b->nbv > 0 && (!b->targets_dev || !b->visible_marker_dev || !b->visible_marker_in_targets_dev))
+    return fail(h, DGP_ERR_INVALID, "dgp_loss_forward: visible markers without targets");
+  if (b->locref_dev && (!b->locref_map_dev || !b->locref_mask_dev))
+    return fail(h, DGP_ERR_INVALID, "dgp_loss_forward: locref without map/mask");
+  if (b->nl > 0 && (!b->edges_dev || !b->ws_dev || !b->ws_max_dev))
+    return fail(h, DGP_ERR_INVALID, "dgp_loss_forward: skeleton without ws/ws_max");
+  CU_OK(h, cudaSetDevice(h->device));
+  const int nm = b->nt * nj;
+  const size_t need = (size_t)nm * 2 * 4 * 2 + (size_t)(b->nbv + b->nbh + 1) * 16 + (size_t)nm * 4 + 256;
+  int rc = ensure(h, &h->loss_ws, need);
+  if (rc) return rc;
+  char* w = (char*)h->loss_ws.p;
+  float* mu = (float*)w; w += (size_t)nm * 2 * 4;
+  float* all = (float*)w; w += (size_t)nm * 2 * 4;
+  w = (char*)(((uintptr_t)w + 15) & ~(uintptr_t)15);
+  float4* partials = (float4*)w; w += (size_t)(b->nbv + b->nbh + 1) * 16;
+  float* meanflow = (float*)w;
+  rc = dgp_softargmax(h, b->pred_dev, nullptr, b->nt, b->H, b->W, nj, cfg->gamma, cfg->gauss_len, mu, nullptr, nullptr,
+                      nullptr, nullptr, stream);
+  if (rc) return rc;
+  LossArgs a;
+  a.pred = b->pred_dev; a.locref = b->locref_dev; a.mu = mu;
+  a.nt = b->nt; a.H = b->H; a.W = b->W; a.nj = nj;
+  a.targets = b->targets_dev; a.locref_map = b->locref_map_dev; a.locref_mask = b->locref_mask_dev;
+  a.visible = b->visible_marker_dev; a.nbv = b->nbv; a.hidden = b->hidden_marker_dev; a.nbh = b->nbh;
+  a.vis_in_targets = b->visible_marker_in_targets_dev;
+  a.edges = b->edges_dev; a.nl = b->nl; a.ws = b->ws_dev; a.ws_max = b->ws_max_dev;
+  a.flow = b->vector_field_dev; a.Hin = b->Hin; a.Win = b->Win; a.wt_batch = b->wt_batch_dev;
+  a.stride = h->cfg.stride; a.lengthscale = cfg->lengthscale; a.wt = cfg->wt; a.wt_max = cfg->wt_max;
+  a.wn_visible = cfg->wn_visible; a.wn_hidden = cfg->wn_hidden; a.locref_weight = cfg->locref_loss_weight;
+  a.n_vis_total = cfg->n_visible_frames_total; a.n_hid_total = cfg->n_frames_total - cfg->n_visible_frames_total;
+  a.gm2 = cfg->gm2; a.gm3 = cfg->gm3;
+  a.all_markers = all; a.partials = partials; a.meanflow = meanflow; a.out = losses_dev;
+  if (a.wt > 0.0f && a.flow != nullptr && !a.wt_batch) return fail(h, DGP_ERR_INVALID, "dgp_loss_forward: wt > 0 needs wt_batch");
+  CU_OK(h, launch_dgp_loss(a, (cudaStream_t)stream));
+  h->launches += 4;
+  if (targets_all_dev)
+    CU_OK(h, cudaMemcpyAsync(targets_all_dev, all, (size_t)nm * 2 * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return DGP_OK;
 }
 

@@ -36,4 +36,22 @@ cudaError_t launch_maxpool3x3s2(const __nv_bfloat16* in, int N, int H, int W, in
 cudaError_t launch_deconv_col2im(const float* contrib, int N, int h, int w, int ldn, int ctot, int nj,
                                  const float* bias, float* logits, float* locref, cudaStream_t stream);
 
+// Forward DGP loss on the head outputs (loss_kernels.cu).  All pointers are device pointers.
+struct LossArgs {
+  const float* pred; const float* locref; const float* mu;  // (nt,H,W,nj), (nt,H,W,2nj) or null, (nt,nj,2)
+  int nt, H, W, nj;
+  const float* targets;                                     // (nv,nj,2), NaN = missing label
+  const float* locref_map; const float* locref_mask;        // (nt,H,W,2nj)
+  const int* visible; int nbv; const int* hidden; int nbh; const int* vis_in_targets;
+  const int* edges; int nl; const float* ws; const float* ws_max;
+  const float* flow; int Hin, Win; const float* wt_batch;   // (nt-1,Hin,Win), (nt-1) = wt * mask
+  float stride, lengthscale, wt, wt_max, wn_visible, wn_hidden, locref_weight, n_vis_total, n_hid_total;
+  int gm2, gm3;
+  float* all_markers;   // scratch (nt*nj,2): targets_all_marker
+  float4* partials;     // scratch (nbv+nbh)
+  float* meanflow;      // scratch ((nt-1)*nj)
+  float* out;           // [6]
+};
+cudaError_t launch_dgp_loss(const LossArgs& a, cudaStream_t stream);
+
 }  // namespace dgp

@@ -1,0 +1,257 @@
+// Forward pass of the DGP loss (reference: src/deepgraphpose/models/fitdgp.py:947-1128) on the head outputs.
+//
+// The reference materialises ~10 tensors of shape (nt*nj, H, W) (Gaussian targets, sigmoids, scaled logits, CE maps).
+// Here every marker (frame, joint) is one CTA that recomputes its Gaussian target on the fly from the soft-argmax /
+// label coordinate and reduces its cross-entropy, confidence and locref-Huber sums with warp shuffles; a final
+// single-warp kernel adds the per-marker partials in a fixed order (deterministic) together with the skeleton
+// (spatial clique) and temporal clique terms.  Bandwidth class: 4*H*W*nj*nt bytes of logits read twice (max pass +
+// loss pass, second pass from L2) + 3*8*H*W bytes per visible marker for the locref term.
+#include "kernels.cuh"
+
+#include <math_constants.h>
+
+namespace dgp {
+
+namespace {
+
+constexpr int kLossThreads = 256;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ float block_sum(float v, float* sh) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = 0.0f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) r += sh[i];  // fixed order -> deterministic
+  return r;
+}
+__device__ float block_max(float v, float* sh) {
+  v = warp_max(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = -CUDART_INF_F;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) r = fmaxf(r, sh[i]);
+  return r;
+}
+
+// tf.nn.sigmoid_cross_entropy_with_logits
+__device__ __forceinline__ float bce(float z, float x) { return fmaxf(x, 0.0f) - x * z + log1pf(expf(-fabsf(x))); }
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// combine_all_marker (fitdgp_util.py:232-272): scatter-add of hidden predictions and visible labels.
+__global__ void combine_markers_kernel(const float* __restrict__ mu, const float* __restrict__ targets,
+                                       const int* __restrict__ visible, int nbv, const int* __restrict__ hidden, int nbh,
+                                       const int* __restrict__ vis_in_targets, float* __restrict__ all) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nbh) {
+    const int m = hidden[i];
+    atomicAdd(&all[2 * m], mu[2 * m]);
+    atomicAdd(&all[2 * m + 1], mu[2 * m + 1]);
+  } else if (i < nbh + nbv) {
+    const int k = i - nbh;
+    const int m = visible[k];
+    const int s = vis_in_targets[k];
+    const float a = targets[2 * s], b = targets[2 * s + 1];
+    atomicAdd(&all[2 * m], a == a ? a : 0.0f);      // targets_nonan (fitdgp.py:898)
+    atomicAdd(&all[2 * m + 1], b == b ? b : 0.0f);
+  }
+}
+
+// One CTA per listed marker: blocks [0, nbv) are the visible markers, [nbv, nbv + nbh) the hidden ones.
+// part[blk] = {ce_sum, weight_count, huber_sum, mask_count}
+__global__ void __launch_bounds__(kLossThreads) marker_loss_kernel(
+    const float* __restrict__ pred, const float* __restrict__ locref, const float* __restrict__ locref_map,
+    const float* __restrict__ locref_mask, const float* __restrict__ all, const int* __restrict__ visible, int nbv,
+    const int* __restrict__ hidden, int H, int W, int nj, float inv2l2, int gm2, int gm3, float4* __restrict__ part) {
+  __shared__ float sh[kLossThreads / 32];
+  const bool is_vis = (int)blockIdx.x < nbv;
+  const int m = is_vis ? visible[blockIdx.x] : hidden[blockIdx.x - nbv];
+  const int t = m / nj, j = m - t * nj;
+  const float mur = all[2 * m], muc = all[2 * m + 1];
+  const float* x0 = pred + (size_t)t * H * W * nj + j;
+  const int HW = H * W;
+
+  // pass A: max of the Gaussian bump (+1e-5, fitdgp.py:973) and, for hidden markers, the confidence max sigmoid
+  float gmax = 0.0f, cmax = -CUDART_INF_F;
+  for (int p = threadIdx.x; p < HW; p += blockDim.x) {
+    const int r = p / W, c = p - r * W;
+    const float dr = (float)r - mur, dc = (float)c - muc;
+    gmax = fmaxf(gmax, expf(-(dr * dr + dc * dc) * inv2l2));
+    if (!is_vis && gm2 != 0) cmax = fmaxf(cmax, sigmoidf_(x0[(size_t)p * nj]));
+  }
+  gmax = block_max(gmax, sh) + 1e-5f;
+  float conf = 1.0f;
+  if (!is_vis && gm2 != 0) conf = block_max(cmax, sh);
+
+  // pass B: cross entropy against the on-the-fly target
+  float ce = 0.0f;
+  for (int p = threadIdx.x; p < HW; p += blockDim.x) {
+    const int r = p / W, c = p - r * W;
+    const float dr = (float)r - mur, dc = (float)c - muc;
+    float tg = expf(-(dr * dr + dc * dc) * inv2l2) / gmax;
+    float x = x0[(size_t)p * nj];
+    if (!is_vis && gm2 != 0) {
+      if (gm2 == 1) tg *= conf;                       // fitdgp.py:1000
+      if (gm3 == 3) {                                 // confidence-scaled logits (fitdgp.py:1002-1004)
+        const float ps = sigmoidf_(x) * conf;
+        x = -logf(1.0f - ps + 1e-20f) + logf(ps + 1e-20f);
+      }
+    }
+    ce += bce(tg, x);
+  }
+  ce = block_sum(ce, sh);
+  float wcount = (float)HW;
+  if (!is_vis && gm3 == 3) {
+    const float w = 1.0f - conf;                      // SUM_BY_NONZERO_WEIGHTS over the broadcast weights
+    ce *= w;
+    wcount = (w != 0.0f) ? (float)HW : 0.0f;
+  }
+
+  // locref Huber (PTF/nnet/losses.py:16-45), visible markers only: channels 2j, 2j+1
+  float hub = 0.0f, mcount = 0.0f;
+  if (is_vis && locref != nullptr) {
+    const size_t base = (size_t)t * HW * 2 * nj + 2 * j;
+    for (int p = threadIdx.x; p < 2 * HW; p += blockDim.x) {
+      const int pix = p >> 1, ch = p & 1;
+      const size_t o = base + (size_t)pix * 2 * nj + ch;
+      const float w = locref_mask[o];
+      const float d = locref[o] - locref_map[o];
+      const float a = fabsf(d);
+      const float l = a < 1.0f ? 0.5f * d * d : a - 0.5f;
+      hub += l * w;
+      mcount += (w != 0.0f) ? 1.0f : 0.0f;
+    }
+    hub = block_sum(hub, sh);
+    mcount = block_sum(mcount, sh);
+  }
+  if (threadIdx.x == 0) part[blockIdx.x] = make_float4(ce, wcount, hub, mcount);
+}
+
+// mean over tf.image.crop_and_resize(flow, box, [Hin, Win]) per (t, j) (fitdgp.py:1085-1110), bilinear, extrapolation 0.
+__global__ void __launch_bounds__(kLossThreads) flow_box_mean_kernel(const float* __restrict__ flow, const float* __restrict__ all,
+                                                                   int nt, int nj, int Hin, int Win, float stride,
+                                                                   float* __restrict__ meanflow) {
+  __shared__ float sh[kLossThreads / 32];
+  const int t = blockIdx.x / nj, j = blockIdx.x - t * nj;
+  const float* a0 = all + ((size_t)t * nj + j) * 2;
+  const float* a1 = all + ((size_t)(t + 1) * nj + j) * 2;
+  const float r0 = a0[0] * stride + 0.5f * stride, c0 = a0[1] * stride + 0.5f * stride;
+  const float r1 = a1[0] * stride + 0.5f * stride, c1 = a1[1] * stride + 0.5f * stride;
+  const float nx = (float)Hin, ny = (float)Win;
+  const float rmin = fmaxf(0.0f, fminf(r0, r1) - 10.0f), rmax = fminf(nx, fmaxf(r0, r1) + 10.0f);
+  const float cmin = fmaxf(0.0f, fminf(c0, c1) - 10.0f), cmax = fminf(ny, fmaxf(c0, c1) + 10.0f);
+  const float y1 = rmin / nx, x1 = cmin / ny, y2 = rmax / nx, x2 = cmax / ny;
+  const float sy = Hin > 1 ? (y2 - y1) * (float)(Hin - 1) / (float)(Hin - 1) : 0.0f;
+  const float sx = Win > 1 ? (x2 - x1) * (float)(Win - 1) / (float)(Win - 1) : 0.0f;
+  const float* img = flow + (size_t)t * Hin * Win;
+  float acc = 0.0f;
+  for (int p = threadIdx.x; p < Hin * Win; p += blockDim.x) {
+    const int yy = p / Win, xx = p - yy * Win;
+    const float ys = Hin > 1 ? y1 * (float)(Hin - 1) + (float)yy * sy : 0.5f * (y1 + y2) * (float)(Hin - 1);
+    const float xs = Win > 1 ? x1 * (float)(Win - 1) + (float)xx * sx : 0.5f * (x1 + x2) * (float)(Win - 1);
+    if (ys < 0.0f || ys > (float)(Hin - 1) || xs < 0.0f || xs > (float)(Win - 1)) continue;
+    const int yl = (int)floorf(ys), yh = min((int)ceilf(ys), Hin - 1);
+    const int xl = (int)floorf(xs), xh = min((int)ceilf(xs), Win - 1);
+    const float ly = ys - floorf(ys), lx = xs - floorf(xs);
+    const float tl = img[yl * Win + xl], tr = img[yl * Win + xh], bl = img[yh * Win + xl], br = img[yh * Win + xh];
+    const float top = tl + (tr - tl) * lx, bot = bl + (br - bl) * lx;
+    acc += top + (bot - top) * ly;
+  }
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) meanflow[blockIdx.x] = acc / (float)(Hin * Win);
+}
+
+// Final fixed-order reduction + clique terms.  out[6] = {visible_loss_pred, hidden_loss_pred, visible_loss_locref,
+// ws_loss, wt_loss, total_loss}.  Single thread: O(nb + nl*nt + nt*nj) work.
+__global__ void loss_finalize_kernel(const float4* __restrict__ part, int nbv, int nbh, const float* __restrict__ all,
+                                     int nt, int nj, int H, int W, const int* __restrict__ edges, int nl,
+                                     const float* __restrict__ ws, const float* __restrict__ ws_max,
+                                     const float* __restrict__ meanflow, const float* __restrict__ wt_batch, float wt,
+                                     float wt_max, float stride, float n_vis_total, float n_hid_total, float wn_visible,
+                                     float wn_hidden, float locref_weight, float* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float ce_v = 0.0f, cnt_v = 0.0f, hub = 0.0f, mcnt = 0.0f, ce_h = 0.0f, cnt_h = 0.0f;
+  for (int i = 0; i < nbv; ++i) { ce_v += part[i].x; cnt_v += part[i].y; hub += part[i].z; mcnt += part[i].w; }
+  for (int i = nbv; i < nbv + nbh; ++i) { ce_h += part[i].x; cnt_h += part[i].y; }
+  const float fnbh = (float)nbh;
+  const float fnbv = nbv > 0 ? (float)nbv : fnbh;   // fitdgp.py:982-984
+  const float visible_loss = cnt_v > 0.0f ? ce_v / cnt_v : 0.0f;
+  float hidden_loss = cnt_h > 0.0f ? ce_h / cnt_h : 0.0f;
+  hidden_loss = hidden_loss * n_vis_total / n_hid_total * fnbh / fnbv * wn_hidden / wn_visible;
+  const float locref_loss = locref_weight * (mcnt > 0.0f ? hub / mcnt : 0.0f);
+  float total = visible_loss + hidden_loss + locref_loss;
+  float ws_loss = 0.0f, wt_loss = 0.0f;
+  if (nl > 0) {
+    float acc = 0.0f;
+    for (int l = 0; l < nl; ++l) {
+      const int a = edges[2 * l], b = edges[2 * l + 1];
+      for (int t = 0; t < nt; ++t) {
+        const float* m = all + (size_t)t * nj * 2;
+        const float dr = (m[2 * a] * stride + 0.5f * stride) - (m[2 * b] * stride + 0.5f * stride);
+        const float dc = (m[2 * a + 1] * stride + 0.5f * stride) - (m[2 * b + 1] * stride + 0.5f * stride);
+        const float d = sqrtf(dr * dr + dc * dc);
+        acc += (fmaxf(d - ws_max[l], 0.0f) + ws_max[l]) * ws[l];
+      }
+    }
+    ws_loss = acc / (float)H / (float)W * n_vis_total / fnbv / (n_vis_total + n_hid_total) / wn_visible;
+    total += ws_loss;
+  }
+  if (wt > 0.0f && meanflow != nullptr) {
+    float acc = 0.0f;
+    for (int t = 0; t + 1 < nt; ++t)
+      for (int j = 0; j < nj; ++j) {
+        const float* m0 = all + ((size_t)t * nj + j) * 2;
+        const float* m1 = all + ((size_t)(t + 1) * nj + j) * 2;
+        const float dr = (m0[0] * stride + 0.5f * stride) - (m1[0] * stride + 0.5f * stride);
+        const float dc = (m0[1] * stride + 0.5f * stride) - (m1[1] * stride + 0.5f * stride);
+        const float d = sqrtf(dr * dr + dc * dc);
+        float inv = fminf(1.0f / (meanflow[t * nj + j] + 1e-10f), 1.0f);
+        inv = fminf(expf(logf(inv) * 3.0f), 1.0f);
+        inv = inv * wt_batch[t] / (float)H / (float)W;
+        const float v = (fmaxf(d - wt_max, 0.0f) + wt_max) * inv;
+        acc += v * v;
+      }
+    wt_loss = sqrtf(acc) * n_vis_total / fnbv / (n_vis_total + n_hid_total) / wn_visible;
+    total += wt_loss;
+  }
+  out[0] = visible_loss; out[1] = hidden_loss; out[2] = locref_loss; out[3] = ws_loss; out[4] = wt_loss; out[5] = total;
+}
+
+}  // namespace
+
+cudaError_t launch_dgp_loss(const LossArgs& a, cudaStream_t stream) {
+  const int nm = a.nt * a.nj;
+  cudaError_t e = cudaMemsetAsync(a.all_markers, 0, (size_t)nm * 2 * sizeof(float), stream);
+  if (e != cudaSuccess) return e;
+  const int nb = a.nbv + a.nbh;
+  if (nb > 0) {
+    combine_markers_kernel<<<(nb + 127) / 128, 128, 0, stream>>>(a.mu, a.targets, a.visible, a.nbv, a.hidden, a.nbh,
+                                                                 a.vis_in_targets, a.all_markers);
+    marker_loss_kernel<<<nb, kLossThreads, 0, stream>>>(a.pred, a.locref, a.locref_map, a.locref_mask, a.all_markers,
+                                                        a.visible, a.nbv, a.hidden, a.H, a.W, a.nj,
+                                                        1.0f / (2.0f * a.lengthscale * a.lengthscale), a.gm2, a.gm3,
+                                                        a.partials);
+  }
+  const bool temporal = a.wt > 0.0f && a.flow != nullptr && a.nt > 1;
+  if (temporal)
+    flow_box_mean_kernel<<<(a.nt - 1) * a.nj, kLossThreads, 0, stream>>>(a.flow, a.all_markers, a.nt, a.nj, a.Hin, a.Win,
+                                                                        a.stride, a.meanflow);
+  loss_finalize_kernel<<<1, 32, 0, stream>>>(a.partials, a.nbv, a.nbh, a.all_markers, a.nt, a.nj, a.H, a.W, a.edges, a.nl,
+                                             a.ws, a.ws_max, temporal ? a.meanflow : nullptr, a.wt_batch, a.wt, a.wt_max,
+                                             a.stride, a.n_vis_total, a.n_hid_total, a.wn_visible, a.wn_hidden,
+                                             a.locref_weight, a.out);
+  return cudaGetLastError();
+}
+
+}  // namespace dgp

@@ -1,0 +1,171 @@
+"""Drop-in for the hot-path part of deepgraphpose.models.fitdgp (reference: src/deepgraphpose/models/fitdgp.py).
+
+``dgp_loss(data_batcher, dgp_cfg)`` keeps the reference's signature and 4-tuple return
+``(loss, total_loss, total_loss_visible, placeholders)`` (:848-1144); the handles are evaluated by ``TrainSession.run``
+with the reference's feed_dict keys.  This round implements the FORWARD of the loss on the GPU (network forward +
+fused loss kernels); the backward pass / Momentum step (fitdgp.py:706-713) is the next row of SURVEY.md section 8.
+"""
+import ctypes as C
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+from . import _lib
+from .engine import Engine, _ptr, _stream
+from .session import Handle
+
+LOSS_KEYS = ("visible_loss_pred", "hidden_loss_pred", "visible_loss_locref", "ws_loss", "wt_loss", "total_loss")
+PLACEHOLDER_KEYS = ("inputs", "targets", "locref_map", "locref_mask", "visible_marker_pl", "hidden_marker_pl",
+                    "visible_marker_in_targets_pl", "wt_batch_mask_pl", "vector_field_tf", "nt_batch_pl", "wt_batch_pl",
+                    "alpha_tf")
+
+
+def _get(cfg, key, default=None):
+    if isinstance(cfg, dict):
+        return cfg.get(key, default)
+    return getattr(cfg, key, default)
+
+
+def skeleton_edges(S0):
+    """Rows of the reference's S0 incidence matrix (fitdgp.py:607-617) -> (+1 joint, -1 joint) pairs."""
+    S0 = np.asarray(S0)
+    edges = []
+    for row in S0:
+        a, b = np.where(row > 0)[0], np.where(row < 0)[0]
+        if len(a) != 1 or len(b) != 1:
+            raise ValueError("S0 rows must hold exactly one +1 and one -1")
+        edges.append((int(a[0]), int(b[0])))
+    return edges
+
+
+def spatial_clique_params(joint_locs, S0, stride, ws, ws_max):
+    """Host precompute of dgp_loss (fitdgp.py:874-892, float64 numpy): per-limb weight ws_l and upper bound ws_max_l,
+    including the reference's quirk that a missing limb contributes stride/2 to the mean length."""
+    S0 = np.asarray(S0, dtype=np.float64)
+    nj = S0.shape[1]
+    full = np.empty((0, nj, 2))
+    for j in joint_locs:
+        if len(j) > 0:
+            full = np.vstack((j, full))
+    f1 = np.copy(full).swapaxes(1, 2).reshape(-1, nj)
+    f1[np.isnan(f1)] = 1e10
+    limb = np.matmul(f1, S0.T)
+    limb[np.abs(limb) > 1e5] = 0
+    limb = np.reshape(limb, [full.shape[0], 2, -1])
+    limb = np.sqrt(np.sum(np.square(limb), 1))
+    limb = limb.T * stride + stride / 2
+    out_max = np.max(np.nan_to_num(limb), 1) * ws_max
+    with np.errstate(invalid="ignore", divide="ignore"):
+        mean = np.true_divide(limb.sum(1), (limb != 0).sum(1))
+    out_ws = 1 / (np.nan_to_num(mean) + 1e-20) * ws
+    return out_ws.astype(np.float32), out_max.astype(np.float32)
+
+
+def loss_forward(engine, pred, locref, feed, cfg, edges, ws, ws_max, n_frames_total, n_visible_frames_total):
+    """One call into dgp_loss_forward.  pred/locref: CUDA tensors from Engine.forward; feed: reference feed_dict values."""
+    dev = pred.device
+    nt, H, W, nj = pred.shape
+    f32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32), device=dev)
+    i32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32), device=dev)
+    targets = f32(np.asarray(feed["targets"]).reshape(-1, nj, 2))
+    vis, hid, vit = i32(feed["visible_marker_pl"]), i32(feed["hidden_marker_pl"]), i32(feed["visible_marker_in_targets_pl"])
+    keep = [targets, vis, hid, vit]
+    b = _lib.DgpLossBatch()
+    b.pred_dev, b.nt, b.H, b.W = pred.data_ptr(), nt, H, W
+    b.targets_dev, b.nv = targets.data_ptr(), targets.shape[0]
+    if locref is not None:
+        lm, lk = f32(feed["locref_map"]), f32(feed["locref_mask"])
+        keep += [lm, lk]
+        b.locref_dev, b.locref_map_dev, b.locref_mask_dev = locref.data_ptr(), lm.data_ptr(), lk.data_ptr()
+    b.visible_marker_dev, b.nbv = vis.data_ptr(), vis.numel()
+    b.hidden_marker_dev, b.nbh = hid.data_ptr(), hid.numel()
+    b.visible_marker_in_targets_dev = vit.data_ptr()
+    if len(edges) > 0:
+        e, w1, w2 = i32(np.asarray(edges).reshape(-1, 2)), f32(ws), f32(ws_max)
+        keep += [e, w1, w2]
+        b.edges_dev, b.nl, b.ws_dev, b.ws_max_dev = e.data_ptr(), len(edges), w1.data_ptr(), w2.data_ptr()
+    wt = float(_get(cfg, "wt", 0.0))
+    if wt > 0:
+        vf = f32(feed["vector_field_tf"])
+        wb = f32(np.asarray(feed["wt_batch_pl"], dtype=np.float32) * np.asarray(feed["wt_batch_mask_pl"], dtype=np.float32))
+        keep += [vf, wb]
+        b.vector_field_dev, b.Hin, b.Win, b.wt_batch_dev = vf.data_ptr(), vf.shape[1], vf.shape[2], wb.data_ptr()
+    c = _lib.DgpLossCfg(float(_get(cfg, "gamma", 1)), float(_get(cfg, "gauss_len", 1)), float(_get(cfg, "lengthscale", 1)),
+                        wt, float(_get(cfg, "wt_max", 0)), float(_get(cfg, "wn_visible", 5)), float(_get(cfg, "wn_hidden", 3)),
+                        float(_get(cfg, "locref_loss_weight", 0.05)), float(n_frames_total), float(n_visible_frames_total),
+                        int(_get(cfg, "gm2", 1)), int(_get(cfg, "gm3", 3)))
+    out = torch.empty(6, dtype=torch.float32, device=dev)
+    all_markers = torch.empty((nt * nj, 2), dtype=torch.float32, device=dev)
+    engine._check(engine.lib.dgp_loss_forward(engine.h, C.byref(c), C.byref(b), _ptr(out), _ptr(all_markers), _stream(dev)))
+    vals = out.cpu().numpy()
+    del keep
+    return dict(zip(LOSS_KEYS, [np.float32(v) for v in vals])), all_markers
+
+
+def dgp_loss(data_batcher, dgp_cfg, variables="synthetic", device=None):
+    """fitdgp.py:848-1144.  Returns (loss, total_loss, total_loss_visible, placeholders) of handles; evaluate them with
+    ``TrainSession(...)``.run(fetches, feed_dict) using the reference's placeholder keys."""
+    from .eval import load_variables
+    S0 = np.asarray(data_batcher.S0)
+    nj = int(data_batcher.nj)
+    gm2, gm3 = int(_get(dgp_cfg, "gm2", 1)), int(_get(dgp_cfg, "gm3", 3))
+    if gm2 not in (0, 1, 2) or gm3 not in (0, 3):
+        raise Exception("Not implemented")  # fitdgp.py:1021, 1037
+    stride = float(_get(dgp_cfg, "stride", 8.0))
+    ws, ws_max = spatial_clique_params([d.labels for d in data_batcher.datasets], S0, stride,
+                                       float(_get(dgp_cfg, "ws", 1000.0)), float(_get(dgp_cfg, "ws_max", 1.2)))
+    eng = Engine(nj, location_refinement=True, device=device, stride=stride,
+                 locref_stdev=float(_get(dgp_cfg, "locref_stdev", 7.2801)))
+    eng.load_weights(load_variables(variables, nj, True))
+    graph = SimpleNamespace(engine=eng, cfg=dgp_cfg, edges=skeleton_edges(S0) if S0.shape[0] else [], ws=ws, ws_max=ws_max,
+                            n_frames_total=float(data_batcher.n_frames_total),
+                            n_visible_frames_total=float(data_batcher.n_visible_frames_total))
+    keys = [k for k in LOSS_KEYS if (k != "wt_loss" or float(_get(dgp_cfg, "wt", 0)) > 0) and (k != "ws_loss" or S0.shape[0] > 0)]
+    loss = {k: Handle(k, k) for k in keys}
+    for hd in loss.values():
+        hd.graph = graph
+    total_loss_visible = Handle("total_loss_visible", "total_loss_visible")
+    total_loss_visible.graph = graph
+    placeholders = {k: Handle(k, k) for k in PLACEHOLDER_KEYS}
+    return loss, loss["total_loss"], total_loss_visible, placeholders
+
+
+class TrainSession:
+    """``sess.run([loss, ...], feed_dict)`` for the handles of ``dgp_loss`` (forward only in this round)."""
+
+    def __init__(self, placeholders):
+        self.ph = placeholders
+
+    def run(self, fetches, feed_dict):
+        feed = {}
+        for k, v in feed_dict.items():
+            for name, hd in self.ph.items():
+                if k is hd:
+                    feed[name] = v
+        flat = []
+        def collect(f):
+            if isinstance(f, dict):
+                for v in f.values():
+                    collect(v)
+            elif isinstance(f, (list, tuple)):
+                for v in f:
+                    collect(v)
+            else:
+                flat.append(f)
+        collect(fetches)
+        g = flat[0].graph
+        frames = np.asarray(feed["inputs"])
+        if frames.dtype != np.uint8:
+            frames = np.clip(np.round(frames), 0, 255).astype(np.uint8)
+        pred, locref = g.engine.forward(torch.from_numpy(np.ascontiguousarray(frames)).to(g.engine.device))
+        vals, _ = loss_forward(g.engine, pred, locref, feed, g.cfg, g.edges, g.ws, g.ws_max, g.n_frames_total,
+                               g.n_visible_frames_total)
+        vals["total_loss_visible"] = np.float32(vals["visible_loss_pred"] + vals["visible_loss_locref"])
+        def build(f):
+            if isinstance(f, dict):
+                return {k: build(v) for k, v in f.items()}
+            if isinstance(f, (list, tuple)):
+                return type(f)(build(v) for v in f)
+            return vals[f.kind]
+        return build(fetches)

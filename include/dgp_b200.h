@@ -103,6 +103,42 @@ int dgp_potentials(dgp_handle* h, const float* mu_dev, const float* mu_halo_next
                    const int32_t* edges_dev, int nl, const float* ws_dev, const float* ws_max_dev, float wt_max,
                    float* skel_dist_dev, float* temporal_dev, float* e_skel_dev, float* e_temp_dev, void* stream);
 
+/* Hyper-parameters fit_dgp writes onto dlc_cfg (fitdgp.py:637-654) plus the demo's gm2/gm3 flags. */
+typedef struct dgp_loss_cfg {
+  float gamma, gauss_len, lengthscale;       /* 1, 1, 1 */
+  float wt, wt_max;                          /* temporal clique (0 = off), upper bound */
+  float wn_visible, wn_hidden;               /* 5, 3 */
+  float locref_loss_weight;                  /* 0.05 */
+  float n_frames_total, n_visible_frames_total;
+  int32_t gm2, gm3;                          /* {0,1,2}, {0,3} */
+} dgp_loss_cfg;
+
+/* The feeds of dgp_loss's placeholders (fitdgp.py:1130-1142), as device pointers.  Index vectors are int32. */
+typedef struct dgp_loss_batch {
+  const float* pred_dev;        /* (nt,H,W,nj) part_pred logits (output of dgp_forward) */
+  const float* locref_dev;      /* (nt,H,W,2nj) locref_pred, or NULL to skip the locref term */
+  int32_t nt, H, W;
+  const float* targets_dev;     /* (nv,nj,2) labels in scoremap (row, col) units, NaN = missing */
+  int32_t nv;
+  const float* locref_map_dev;  /* (nt,H,W,2nj) */
+  const float* locref_mask_dev; /* (nt,H,W,2nj) */
+  const int32_t* visible_marker_dev; int32_t nbv;
+  const int32_t* hidden_marker_dev;  int32_t nbh;
+  const int32_t* visible_marker_in_targets_dev;
+  const int32_t* edges_dev; int32_t nl;   /* skeleton: rows of S0 as (+1 joint, -1 joint) */
+  const float* ws_dev; const float* ws_max_dev;  /* (nl) from the host precompute fitdgp.py:874-892 */
+  const float* vector_field_dev; int32_t Hin, Win;  /* (nt-1,Hin,Win) optical-flow magnitude, or NULL */
+  const float* wt_batch_dev;    /* (nt-1) = wt_batch_pl * wt_batch_mask_pl */
+} dgp_loss_batch;
+
+/* Replaces the loss part of sess.run([loss, ...]) in fit_dgp (fitdgp.py:817-818, graph :947-1128): soft-argmax of
+ * the hidden markers, visible/hidden marker scatter, Gaussian-target sigmoid cross-entropies with the gm2/gm3
+ * confidence scaling, locref Huber, skeleton (spatial) and temporal cliques.  FORWARD ONLY in this round.
+ * losses_dev[6] = {visible_loss_pred, hidden_loss_pred, visible_loss_locref, ws_loss, wt_loss, total_loss};
+ * targets_all_dev (nt*nj,2) optionally receives targets_all_marker. */
+int dgp_loss_forward(dgp_handle* h, const dgp_loss_cfg* cfg, const dgp_loss_batch* batch, float* losses_dev,
+                     float* targets_all_dev, void* stream);
+
 /* Replaces the estimate_pose frame loop (eval.py:306-345) end to end with HOST buffers: per batch of `batch`
  * frames H2D copy, dgp_forward, dgp_softargmax, D2H of the results.  frames_host uint8 (T,H,W,3) (pinned memory
  * gives asynchronous copies); mu_host float32 (T,nj,2); peak_host int32 (T,nj,2); lik_host float32 (T,nj). */
