@@ -7,7 +7,6 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
-#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -344,7 +343,6 @@ int setup_epilogue(dgp_handle* h, ConvGemmParams& g, const char* scope, int n_im
   g.num_m_blocks = ceil_div(g.M, kBlockM * g.msub);
   g.tmem_cols = tmem_cols_for(g.block_n * g.msub);
   g.num_stages = conv_gemm_pick_stages(g.block_n, g.epi_bufs, g.msub);
-  g.l2_prefetch = getenv("DGP_NO_L2_PREFETCH") ? 0 : 1;
   return DGP_OK;
 }
 

@@ -135,18 +135,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         cw = qq * cstride + lower_w;
         ch = pp * cstride + lower_h;
       }
-      // 1x1 convs have short k loops (1..32 k-blocks) whose A rows come straight from HBM: start pulling the NEXT
-      // tile's rows into L2 now, so that its loads are L2 hits by the time the smem ring gets to them.
-      if (a_mode == 0 && p.l2_prefetch) {
-        const int nt = tile + gridDim.x;
-        if (nt < num_tiles) {
-          const int nm = nt / nnb;
-          if (nm != m_blk && ptx::elect_one()) {
-            for (int kb = 0; kb < nkb; ++kb) ptx::tma_prefetch_l2_2d(&p.tmap_a, kb * kBlockK, nm * block_m);
-          }
-          __syncwarp();
-        }
-      }
       int cb = 0, off_w = 0, off_h = 0, tap_s = 0;  // incremental (channel block, tap) counters: no divides in the loop
       for (int kb = 0; kb < nkb; ++kb) {
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);

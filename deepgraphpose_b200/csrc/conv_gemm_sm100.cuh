@@ -36,7 +36,6 @@ struct ConvGemmParams {
   int msub;          // 128-row sub-tiles per CTA tile: 1, or 2 (BLOCK_M = 256) for narrow layers (block_n <= 128)
   int num_k_blocks;  // K / 64
   int a_mode;        // 0 = tiled [M,K], 1 = im2col
-  int l2_prefetch;   // tiled mode: prefetch the next tile's A rows into L2 (set DGP_NO_L2_PREFETCH=1 to disable)
   // im2col geometry (a_mode == 1)
   int P, Q;          // output height / width
   int conv_stride;

@@ -93,14 +93,6 @@ __device__ __forceinline__ void tma_load_im2col_4d(void* smem_dst, const void* t
       : "memory");
 }
 
-// Prefetch a 2-D tile into L2 only (no shared memory, no barrier): used to pull the NEXT tile's activation rows out of
-// HBM while the current tile is still being multiplied.
-__device__ __forceinline__ void tma_prefetch_l2_2d(const void* tmap, int c0, int c1) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
-               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1)
-               : "memory");
-}
-
 // 2-D tile store smem -> global (bulk async group; out-of-bounds rows/cols are clipped by the hardware).
 __device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
