@@ -28,6 +28,7 @@ class DgpConfig(C.Structure):
         ("locref_stdev", C.c_float),
         ("mean_pixel", C.c_float * 3),
         ("bn_epsilon", C.c_float),
+        ("precision", C.c_int32),
     ]
 
 

@@ -7,12 +7,20 @@
 //                   out[2i+kh, 2j+kw] += x[i,j] * w[kh,kw], cropped to (2h, 2w), plus bias.
 #include "kernels.cuh"
 
+#include <cuda_fp16.h>
+
 namespace dgp {
 
 namespace {
 
+__device__ __forceinline__ uint16_t to_half_bits(float f, int fp16) {
+  if (fp16) { __half h = __float2half_rn(f); return *reinterpret_cast<uint16_t*>(&h); }
+  __nv_bfloat16 b = __float2bfloat16_rn(f);
+  return *reinterpret_cast<uint16_t*>(&b);
+}
+
 __global__ void prep_s2d_kernel(const uint8_t* __restrict__ frames, int N, int H, int W, float m0, float m1, float m2,
-                                __nv_bfloat16* __restrict__ out, int Hs, int Ws) {
+                                uint16_t* __restrict__ out, int Hs, int Ws, int fp16) {
   const size_t total = (size_t)N * Hs * Ws;
   for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
     const int j = (int)(t % Ws);
@@ -20,7 +28,7 @@ __global__ void prep_s2d_kernel(const uint8_t* __restrict__ frames, int N, int H
     const int i = (int)(r % Hs);
     const int n = (int)(r / Hs);
     const float mean[3] = {m0, m1, m2};
-    __align__(16) __nv_bfloat16 v[16];
+    __align__(16) uint16_t v[16];
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const int y = 2 * i + u - 3;
@@ -32,25 +40,29 @@ __global__ void prep_s2d_kernel(const uint8_t* __restrict__ frames, int N, int H
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           const float f = ok ? (float)px[c] - mean[c] : 0.0f;
-          v[(u * 2 + w) * 3 + c] = __float2bfloat16_rn(f);
+          v[(u * 2 + w) * 3 + c] = to_half_bits(f, fp16);
         }
       }
     }
 #pragma unroll
-    for (int c = 12; c < 16; ++c) v[c] = __float2bfloat16_rn(0.0f);
+    for (int c = 12; c < 16; ++c) v[c] = 0;
     uint4* dst = reinterpret_cast<uint4*>(out + t * 16);
     dst[0] = reinterpret_cast<const uint4*>(v)[0];
     dst[1] = reinterpret_cast<const uint4*>(v)[1];
   }
 }
 
-__device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
+__device__ __forceinline__ uint32_t half2_max(uint32_t a, uint32_t b, int fp16) {
+  if (fp16) {
+    __half2 r = __hmax2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
   __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
   return *reinterpret_cast<uint32_t*>(&r);
 }
 
 __global__ void maxpool3x3s2_kernel(const uint4* __restrict__ in, int N, int H, int W, int C8, uint4* __restrict__ out,
-                                    int Ho, int Wo, int pad_t, int pad_l) {
+                                    int Ho, int Wo, int pad_t, int pad_l, int fp16) {
   const size_t total = (size_t)N * Ho * Wo * C8;
   for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(t % C8);
@@ -74,8 +86,8 @@ __global__ void maxpool3x3s2_kernel(const uint4* __restrict__ in, int N, int H, 
           m = v;
           have = true;
         } else {
-          m.x = bf16x2_max(m.x, v.x); m.y = bf16x2_max(m.y, v.y);
-          m.z = bf16x2_max(m.z, v.z); m.w = bf16x2_max(m.w, v.w);
+          m.x = half2_max(m.x, v.x, fp16); m.y = half2_max(m.y, v.y, fp16);
+          m.z = half2_max(m.z, v.z, fp16); m.w = half2_max(m.w, v.w, fp16);
         }
       }
     }
@@ -129,18 +141,19 @@ int grid_for(size_t total, int threads) {
 }  // namespace
 
 cudaError_t launch_prep_s2d(const uint8_t* frames, int N, int H, int W, const float* mean3, __nv_bfloat16* out,
-                            int Hs, int Ws, cudaStream_t stream) {
+                            int Hs, int Ws, int fp16, cudaStream_t stream) {
   const size_t total = (size_t)N * Hs * Ws;
-  prep_s2d_kernel<<<grid_for(total, 256), 256, 0, stream>>>(frames, N, H, W, mean3[0], mean3[1], mean3[2], out, Hs, Ws);
+  prep_s2d_kernel<<<grid_for(total, 256), 256, 0, stream>>>(frames, N, H, W, mean3[0], mean3[1], mean3[2],
+                                                            reinterpret_cast<uint16_t*>(out), Hs, Ws, fp16);
   return cudaGetLastError();
 }
 
 cudaError_t launch_maxpool3x3s2(const __nv_bfloat16* in, int N, int H, int W, int C, __nv_bfloat16* out, int Ho,
-                                int Wo, int pad_t, int pad_l, cudaStream_t stream) {
+                                int Wo, int pad_t, int pad_l, int fp16, cudaStream_t stream) {
   if (C % 8) return cudaErrorInvalidValue;
   const size_t total = (size_t)N * Ho * Wo * (C / 8);
   maxpool3x3s2_kernel<<<grid_for(total, 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(in), N, H, W, C / 8,
-                                                                reinterpret_cast<uint4*>(out), Ho, Wo, pad_t, pad_l);
+                                                                reinterpret_cast<uint4*>(out), Ho, Wo, pad_t, pad_l, fp16);
   return cudaGetLastError();
 }
 

@@ -3,6 +3,7 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdarg.h>
@@ -82,6 +83,7 @@ struct dgp_handle {
   dgp_config cfg;
   int device = 0;
   int num_sms = 0;
+  int fp16 = 0;  // storage precision of activations / weights: 0 = bf16, 1 = fp16
   char err[512] = "";
   std::map<std::string, HostVar> host_vars;
   bool finalized = false;
@@ -118,6 +120,27 @@ struct dgp_handle {
 };
 
 namespace {
+
+typedef __nv_bfloat16 W16;  // opaque 16-bit storage element (bf16 or fp16 bits)
+W16 cvt16(const dgp_handle* h, float f) {
+  W16 out;
+  if (h->fp16) {
+    const float c = f > 65504.0f ? 65504.0f : (f < -65504.0f ? -65504.0f : f);
+    __half v = __float2half_rn(c);
+    memcpy(&out, &v, 2);
+  } else {
+    out = __float2bfloat16_rn(f);
+  }
+  return out;
+}
+float cvt16_to_float(const dgp_handle* h, W16 v) {
+  if (h->fp16) {
+    __half x;
+    memcpy(&x, &v, 2);
+    return __half2float(x);
+  }
+  return __bfloat162float(v);
+}
 
 int fail(dgp_handle* h, int code, const char* fmt, ...) {
   va_list ap;
@@ -213,7 +236,7 @@ int build_conv_layer(dgp_handle* h, const std::string& scope, int R, int S, int 
   for (int t = 0; t < R * S; ++t)
     for (int c = 0; c < Cin; ++c) {
       const float* src = &w->data[((size_t)t * Cin + c) * Cout];
-      for (int o = 0; o < Cout; ++o) wm[(size_t)o * L.K + (size_t)t * Cin + c] = __float2bfloat16_rn(src[o]);
+      for (int o = 0; o < Cout; ++o) wm[(size_t)o * L.K + (size_t)t * Cin + c] = cvt16(h, src[o]);
     }
   std::vector<float> scale, shift;
   int rc = bn_scale_shift(h, scope, Cout, &scale, &shift);
@@ -236,7 +259,7 @@ int build_conv1_layer(dgp_handle* h) {
   ConvLayer L;
   L.scope = scope; L.R = 4; L.S = 1; L.Cin = 64; L.Cout = 64; L.stride = 1; L.dil = 1; L.relu = true;
   L.K = 256; L.block_n = 64; L.Npad = 64;
-  std::vector<__nv_bfloat16> wm((size_t)64 * 256, __float2bfloat16_rn(0.0f));
+  std::vector<__nv_bfloat16> wm((size_t)64 * 256, cvt16(h, 0.0f));
   for (int a = 0; a < 4; ++a)
     for (int b = 0; b < 4; ++b)
       for (int u = 0; u < 2; ++u)
@@ -246,7 +269,7 @@ int build_conv1_layer(dgp_handle* h) {
           for (int c = 0; c < 3; ++c)
             for (int o = 0; o < 64; ++o)
               wm[(size_t)o * 256 + a * 64 + b * 16 + (u * 2 + v) * 3 + c] =
-                  __float2bfloat16_rn(w->data[(((size_t)kh * 7 + kw) * 3 + c) * 64 + o]);
+                  cvt16(h, w->data[(((size_t)kh * 7 + kw) * 3 + c) * 64 + o]);
         }
   std::vector<float> scale, shift;
   int rc = bn_scale_shift(h, scope, 64, &scale, &shift);
@@ -281,7 +304,7 @@ int build_head_layer(dgp_handle* h) {
   L.K = 2048;
   L.block_n = pick_block_n(9 * ctot);
   L.Npad = ceil_div(9 * ctot, L.block_n) * L.block_n;
-  std::vector<__nv_bfloat16> wm((size_t)L.Npad * 2048, __float2bfloat16_rn(0.0f));
+  std::vector<__nv_bfloat16> wm((size_t)L.Npad * 2048, cvt16(h, 0.0f));
   for (int t = 0; t < 9; ++t)
     for (int co = 0; co < ctot; ++co) {
       const HostVar* src = co < nj ? wp : wl;
@@ -289,7 +312,7 @@ int build_head_layer(dgp_handle* h) {
       const int cn = co < nj ? nj : 2 * nj;
       const float* s = &src->data[((size_t)t * cn + cc) * 2048];
       __nv_bfloat16* d = &wm[(size_t)(t * ctot + co) * 2048];
-      for (int c = 0; c < 2048; ++c) d[c] = __float2bfloat16_rn(s[c]);
+      for (int c = 0; c < 2048; ++c) d[c] = cvt16(h, s[c]);
     }
   int rc = upload_layer(h, L, wm, nullptr, nullptr);
   if (rc) return rc;
@@ -352,6 +375,8 @@ int make_gemm_step(dgp_handle* h, const ConvLayer& L, const void* x, int N, int 
                    Step* st, int* Ho, int* Wo) {
   memset(&st->gp, 0, sizeof(st->gp));
   ConvGemmParams& g = st->gp;
+  g.fp16 = h->fp16;
+  tmap_set_fp16(h->fp16);
   int P, Q, lower_h = 0, lower_w = 0, upper_h = 0, upper_w = 0;
   const int keff_h = (L.R - 1) * L.dil + 1, keff_w = (L.S - 1) * L.dil + 1;
   if (pad_mode == 0) {  // TF SAME
@@ -464,6 +489,8 @@ int build_plan(dgp_handle* h, int B, int H, int W, Plan** out) {
     Step st;
     memset(&st.gp, 0, sizeof(st.gp));
     ConvGemmParams& g = st.gp;
+    g.fp16 = h->fp16;
+    tmap_set_fp16(h->fp16);
     g.M = B * pl->H1 * pl->W1; g.N = 64; g.block_n = 64; g.num_k_blocks = 4; g.a_mode = 1;
     g.P = pl->H1; g.Q = pl->W1; g.conv_stride = 1; g.lower_h = 0; g.lower_w = 0; g.S = 1; g.dil = 1; g.cblocks = 1;
     g.scale = L.scale; g.shift = L.shift; g.residual = nullptr; g.res_sub = 1; g.relu = 1;
@@ -624,6 +651,7 @@ extern "C" {
 int dgp_create(const dgp_config* cfg, dgp_handle** out) {
   if (!cfg || !out) return fail(nullptr, DGP_ERR_INVALID, "dgp_create: null argument");
   if (cfg->num_joints < 1 || cfg->num_joints > 256) return fail(nullptr, DGP_ERR_INVALID, "dgp_create: num_joints out of range");
+  if (cfg->precision != 0 && cfg->precision != 1) return fail(nullptr, DGP_ERR_INVALID, "dgp_create: precision must be 0 (bf16) or 1 (fp16)");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -641,6 +669,7 @@ int dgp_create(const dgp_config* cfg, dgp_handle** out) {
   if (const char* te = tma_init()) return fail(nullptr, DGP_ERR_CUDA, "dgp_create: %s", te);
   dgp_handle* h = new dgp_handle();
   h->cfg = *cfg;
+  h->fp16 = cfg->precision == 1 ? 1 : 0;
   if (h->cfg.bn_epsilon <= 0) h->cfg.bn_epsilon = 1e-5f;
   h->device = cfg->device;
   h->num_sms = prop.multiProcessorCount;
@@ -766,14 +795,14 @@ int dgp_forward(dgp_handle* h, const uint8_t* frames_dev, int B, int H, int W, f
     ProfScope prof(h, (int)st.kind, s);
     switch (st.kind) {
       case STEP_PREP:
-        CU_OK(h, launch_prep_s2d(frames_dev, B, H, W, h->cfg.mean_pixel, pl->s2d, pl->Hs, pl->Ws, s));
+        CU_OK(h, launch_prep_s2d(frames_dev, B, H, W, h->cfg.mean_pixel, pl->s2d, pl->Hs, pl->Ws, h->fp16, s));
         break;
       case STEP_GEMM:
         CU_OK(h, launch_conv_gemm(st.gp, h->num_sms, s));
         break;
       case STEP_POOL:
         CU_OK(h, launch_maxpool3x3s2(st.pin, B, st.pH, st.pW, st.pC, (__nv_bfloat16*)st.out_ptr, st.oH, st.oW, st.pad_t,
-                                     st.pad_l, s));
+                                     st.pad_l, h->fp16, s));
         break;
       case STEP_COL2IM:
         CU_OK(h, launch_deconv_col2im(pl->contrib, B, pl->hf, pl->wf, pl->contrib_ld, h->ctot, h->cfg.num_joints,
@@ -983,7 +1012,7 @@ int dgp_debug_get_activation(dgp_handle* h, const char* end_point, float* host_o
   CU_OK(h, cudaDeviceSynchronize());
   std::vector<__nv_bfloat16> tmp(n);
   CU_OK(h, cudaMemcpy(tmp.data(), k.p, n * 2, cudaMemcpyDeviceToHost));
-  for (size_t i = 0; i < n; ++i) host_out[i] = __bfloat162float(tmp[i]);
+  for (size_t i = 0; i < n; ++i) host_out[i] = cvt16_to_float(h, tmp[i]);
   return DGP_OK;
 }
 
@@ -1002,11 +1031,11 @@ int dgp_conv2d(dgp_handle* h, const void* x_dev, int N, int H, int W, int Cin, c
   L.block_n = block_n > 0 ? block_n : pick_block_n(Cout);
   L.Npad = ceil_div(Cout, L.block_n) * L.block_n;
   if (L.Npad != Cout) return fail(h, DGP_ERR_INVALID, "dgp_conv2d: block_n must divide Cout");
-  std::vector<__nv_bfloat16> wm((size_t)L.Npad * L.K, __float2bfloat16_rn(0.0f));
+  std::vector<__nv_bfloat16> wm((size_t)L.Npad * L.K, cvt16(h, 0.0f));
   for (int t = 0; t < R * S; ++t)
     for (int c = 0; c < Cin; ++c)
       for (int o = 0; o < Cout; ++o)
-        wm[(size_t)o * L.K + (size_t)t * Cin + c] = __float2bfloat16_rn(w_host[((size_t)t * Cin + c) * Cout + o]);
+        wm[(size_t)o * L.K + (size_t)t * Cin + c] = cvt16(h, w_host[((size_t)t * Cin + c) * Cout + o]);
   std::vector<float> sc, sh;
   if (scale_host) sc.assign(scale_host, scale_host + Cout);
   if (shift_host) sh.assign(shift_host, shift_host + Cout);

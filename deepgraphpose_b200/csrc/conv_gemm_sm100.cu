@@ -31,6 +31,25 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+// fp16 storage mode (same tcgen05 kind::f16 path, 11-bit mantissa): saturate instead of overflowing to inf
+__device__ __forceinline__ uint32_t pack_fp16(float a, float b) {
+  __half2 h = __floats2half2_rn(fminf(fmaxf(a, -65504.0f), 65504.0f), fminf(fmaxf(b, -65504.0f), 65504.0f));
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint4 pack8(const float* f, int fp16) {
+  if (fp16) return make_uint4(pack_fp16(f[0], f[1]), pack_fp16(f[2], f[3]), pack_fp16(f[4], f[5]), pack_fp16(f[6], f[7]));
+  return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+}
+__device__ __forceinline__ void add_residual2(float& a, float& b, uint32_t v, int fp16) {
+  if (fp16) {
+    const float2 r = __half22float2(*reinterpret_cast<const __half2*>(&v));
+    a += r.x;
+    b += r.y;
+  } else {
+    a += bf16lo(v);
+    b += bf16hi(v);
+  }
+}
 
 // BN scale/shift of 16 consecutive channels from this warp's shared-memory copy (broadcast LDS.128).
 __device__ __forceinline__ void apply_scale_shift(float (&f)[16], const float* ss_scale, const float* ss_shift, int c) {
@@ -167,7 +186,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (whole warp loops, one lane issues)
     const int block_n = p.block_n, nkb = p.num_k_blocks;
-    const uint32_t idesc = ptx::make_idesc_bf16_f32(kBlockM, block_n);
+    const uint32_t idesc = ptx::make_idesc_bf16_f32(kBlockM, block_n, p.fp16);
     const uint64_t adesc0 = ptx::make_desc_k_sw128(ptx::smem_u32(smem_a));
     const uint64_t bdesc0 = ptx::make_desc_k_sw128(ptx::smem_u32(smem_b));
     const uint32_t a_step = (uint32_t)a_bytes >> 4, b_step = (uint32_t)b_bytes >> 4;
@@ -255,9 +274,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             for (int i = 0; i < 4; ++i) op[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
           } else {
             uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldc + n);
-            op[0] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-            op[1] = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]),
-                               pack_bf16(f[14], f[15]));
+            op[0] = pack8(f, p.fp16);
+            op[1] = pack8(f + 8, p.fp16);
           }
         }
       }
@@ -386,17 +404,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              f[2 * i] += bf16lo(rr[i]);
-              f[2 * i + 1] += bf16hi(rr[i]);
+              add_residual2(f[2 * i], f[2 * i + 1], rr[i], p.fp16);
             }
           }
           if (p.relu) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.0f);
           }
-          *s0 = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-          *s1 = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]),
-                           pack_bf16(f[14], f[15]));
+          *s0 = pack8(f, p.fp16);
+          *s1 = pack8(f + 8, p.fp16);
         }
         ptx::fence_proxy_async_smem();  // my generic-proxy smem writes -> visible to the TMA store (async proxy)
         ptx::named_bar_sync(pair_bar, 64);
@@ -458,6 +474,9 @@ const char* tma_init() {
   return nullptr;
 }
 
+namespace { int g_tmap_fp16 = 0; }
+void tmap_set_fp16(int fp16) { g_tmap_fp16 = fp16; }
+
 const char* make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t k, uint64_t row_stride_bytes,
                          uint32_t box_rows) {
   if (const char* e = tma_init()) return e;
@@ -465,7 +484,7 @@ const char* make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint
   cuuint64_t strides[1] = {row_stride_bytes};
   cuuint32_t box[2] = {(cuuint32_t)kBlockK, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode_tiled(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+  CUresult r = g_encode_tiled(out, g_tmap_fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
                               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -486,7 +505,7 @@ const char* make_tmap_im2col(CUtensorMap* out, const void* base, uint64_t C, uin
   int lower[2] = {lower_w, lower_h};
   int upper[2] = {upper_w, upper_h};
   cuuint32_t estr[4] = {1, (cuuint32_t)conv_stride, (cuuint32_t)conv_stride, 1};
-  CUresult r = g_encode_im2col(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, lower,
+  CUresult r = g_encode_im2col(out, g_tmap_fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, lower,
                                upper, (cuuint32_t)kBlockK, (cuuint32_t)pixels_per_column, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

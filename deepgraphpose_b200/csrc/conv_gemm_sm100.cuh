@@ -36,6 +36,7 @@ struct ConvGemmParams {
   int msub;          // 128-row sub-tiles per CTA tile: 1, or 2 (BLOCK_M = 256) for narrow layers (block_n <= 128)
   int num_k_blocks;  // K / 64
   int a_mode;        // 0 = tiled [M,K], 1 = im2col
+  int fp16;          // 0 = bf16 activations/weights (default), 1 = fp16 storage (same kind::f16 MMA, fp32 accumulate)
   // im2col geometry (a_mode == 1)
   int P, Q;          // output height / width
   int conv_stride;
@@ -62,6 +63,7 @@ struct ConvGemmParams {
 };
 
 // Host helpers (conv_gemm_sm100.cu)
+void tmap_set_fp16(int fp16);  // element type of subsequently encoded tensor maps
 const char* tma_init();  // resolves the driver's tensor-map encoders; returns nullptr on success, else an error string
 // [rows, k] row-major bf16 matrix, box = [box_rows, 64], SWIZZLE_128B.
 const char* make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t k, uint64_t row_stride_bytes,

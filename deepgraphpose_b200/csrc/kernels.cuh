@@ -27,10 +27,10 @@ cudaError_t launch_potentials(const float* mu, const float* halo_next, int T, in
 
 // u8 RGB frames (N,H,W,3) -> mean-subtracted, zero-padded, space-to-depth bf16 (N,Hs,Ws,16), Hs=ceil(H/2)+3.
 cudaError_t launch_prep_s2d(const uint8_t* frames, int N, int H, int W, const float* mean3, __nv_bfloat16* out,
-                            int Hs, int Ws, cudaStream_t stream);
+                            int Hs, int Ws, int fp16, cudaStream_t stream);
 // 3x3 stride-2 max-pool with TF SAME padding on NHWC bf16 (C multiple of 8).
 cudaError_t launch_maxpool3x3s2(const __nv_bfloat16* in, int N, int H, int W, int C, __nv_bfloat16* out, int Ho,
-                                int Wo, int pad_t, int pad_l, cudaStream_t stream);
+                                int Wo, int pad_t, int pad_l, int fp16, cudaStream_t stream);
 // col2im of the head GEMM: contrib (N*h*w, ldn) fp32 with column (kh*3+kw)*ctot + co ->
 // part logits (N,2h,2w,nj) [+ locref (N,2h,2w,2nj)] with bias.
 cudaError_t launch_deconv_col2im(const float* contrib, int N, int h, int w, int ldn, int ctot, int nj,

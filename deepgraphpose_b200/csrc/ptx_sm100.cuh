@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace dgp {
@@ -160,8 +161,9 @@ __device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t smem_addr) {
 
 // Instruction descriptor for kind::f16, A=B=bf16 (K-major both), D=fp32, M x N tile.
 // Bit layout: cute::UMMA::InstrDescriptor.
-__host__ __device__ __forceinline__ uint32_t make_idesc_bf16_f32(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+__host__ __device__ __forceinline__ uint32_t make_idesc_bf16_f32(int M, int N, int fp16 = 0) {
+  const uint32_t fmt = fp16 ? 0u : 1u;  // a_format / b_format: 0 = F16, 1 = BF16
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 }  // namespace ptx

@@ -34,7 +34,7 @@ def _stream(device):
 
 class Engine:
     def __init__(self, num_joints, location_refinement=True, device=None, stride=STRIDE, locref_stdev=LOCREF_STDEV,
-                 mean_pixel=MEAN_PIXEL):
+                 mean_pixel=MEAN_PIXEL, precision="bf16"):
         if not torch.cuda.is_available():
             raise DgpError(-2, "no CUDA device: deepgraphpose_b200 has no CPU fallback")
         self.lib = _lib.load()
@@ -51,6 +51,11 @@ class Engine:
         cfg.locref_stdev = locref_stdev
         cfg.mean_pixel = (C.c_float * 3)(*mean_pixel)
         cfg.bn_epsilon = 1e-5
+        if precision not in ("bf16", "fp16"):
+            raise ValueError("precision must be 'bf16' or 'fp16'")
+        cfg.precision = 1 if precision == "fp16" else 0
+        self.precision = precision
+        self.act_dtype = torch.float16 if precision == "fp16" else torch.bfloat16
         self.stride = float(stride)
         self.locref_stdev = float(locref_stdev)
         h = C.c_void_p()
@@ -191,7 +196,9 @@ class Engine:
             Wo = (W - ((S - 1) * dilation + 1)) // stride + 1
         else:
             Ho, Wo = -(-H // stride), -(-W // stride)
-        out = torch.empty((N, Ho, Wo, Cout), dtype=torch.float32 if out_f32 else torch.bfloat16, device=x.device)
+        if x.dtype != self.act_dtype:
+            raise ValueError("x must be %s for this engine" % self.act_dtype)
+        out = torch.empty((N, Ho, Wo, Cout), dtype=torch.float32 if out_f32 else self.act_dtype, device=x.device)
         sc = np.ascontiguousarray(scale, dtype=np.float32) if scale is not None else None
         sh = np.ascontiguousarray(shift, dtype=np.float32) if shift is not None else None
         res_H = res_W = 0

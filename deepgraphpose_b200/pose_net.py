@@ -30,7 +30,7 @@ class PoseNet:
         self.location_refinement = bool(_get(cfg, "location_refinement", True))
         self.engine = Engine(self.num_joints, self.location_refinement, device,
                              float(_get(cfg, "stride", STRIDE)), float(_get(cfg, "locref_stdev", LOCREF_STDEV)),
-                             tuple(_get(cfg, "mean_pixel", MEAN_PIXEL)))
+                             tuple(_get(cfg, "mean_pixel", MEAN_PIXEL)), _get(cfg, "precision", "bf16"))
         if variables is not None:
             self.restore(variables)
 

@@ -46,6 +46,8 @@ typedef struct dgp_config {
   float locref_stdev;          /* default_config.py:29  (7.2801) */
   float mean_pixel[3];         /* default_config.py:23  (123.68, 116.779, 103.939), RGB */
   float bn_epsilon;            /* slim resnet_arg_scope batch_norm_epsilon (1e-5) */
+  int32_t precision;           /* storage type of activations/weights fed to the tensor cores: 0 = bf16 (default; range-safe),
+                                  1 = fp16 (same tcgen05 kind::f16 path and speed, 8x tighter parity, saturates at 65504) */
 } dgp_config;
 
 /* Replaces the graph construction in setup_dgp_eval_graph (src/deepgraphpose/models/eval.py:147-214) and in

@@ -73,6 +73,23 @@ def test_conv_matches_oracle(eng, case):
     assert err < (2e-5 if out_f32 else 6e-3), err
 
 
+def test_conv_fp16_storage():
+    from deepgraphpose_b200.engine import Engine
+    e = Engine(4, precision="fp16")
+    rng = np.random.default_rng(5)
+    x = torch.from_numpy(rng.standard_normal((2, 13, 17, 128)).astype(np.float32)).half()
+    w = (rng.standard_normal((3, 3, 128, 256)) * np.sqrt(1.0 / (9 * 128))).astype(np.float32)
+    scale = rng.uniform(0.5, 1.5, 256).astype(np.float32)
+    shift = rng.normal(0, 0.2, 256).astype(np.float32)
+    res = torch.from_numpy(rng.standard_normal((2, 13, 17, 256)).astype(np.float32)).half()
+    wq = torch.from_numpy(w).half().float()
+    ref = torch.relu(tf_ops.conv2d(x.float(), wq, 1, 1, "SAME") * torch.from_numpy(scale) + torch.from_numpy(shift) + res.float())
+    got = e.conv2d(x.cuda(), w, 1, 1, 1, scale, shift, res.cuda(), 1, True, False, 0)
+    assert got.dtype == torch.float16
+    assert (got.float().cpu() - ref).abs().max().item() / ref.abs().max().item() < 1e-3
+    e.close()
+
+
 def test_conv_rejects_bad_channels(eng):
     from deepgraphpose_b200._lib import DgpError
     x = torch.zeros(1, 8, 8, 48, dtype=torch.bfloat16, device="cuda")

@@ -57,6 +57,28 @@ def test_forward_layerwise(setup, shape):
     assert (out["mu"].cpu() - mu_ref).abs().max().item() < MU_TOL_SCOREMAP_PX
 
 
+def test_forward_fp16_storage_meets_baseline_tolerances(setup):
+    """precision='fp16' (same tcgen05 kind::f16 kernels, fp16 instead of bf16 storage): BASELINE.json's tolerances hold --
+    sigmoid scoremaps <= 1e-2 max-abs, soft-argmax <= 0.5 image px (0.0625 scoremap px)."""
+    from deepgraphpose_b200.engine import Engine
+    _, W, Wt, nj = setup
+    eng = Engine(nj, location_refinement=True, precision="fp16")
+    eng.load_weights(W)
+    for (T, H, Wd) in [(2, 235, 301), (1, 470, 640)]:
+        frames, _ = synthetic.make_video(T, H, Wd, nj, seed=H)
+        with torch.no_grad():
+            net = pose_net.extract_features(torch.from_numpy(frames.astype(np.float32)), Wt)
+            pred = pose_net.prediction_layer(net, Wt, "part_pred")
+            loc = pose_net.prediction_layer(net, Wt, "locref_pred")
+        logits, locref = eng.forward(torch.from_numpy(frames).cuda())
+        assert (logits.cpu() - pred).abs().max().item() / pred.abs().max().item() < 4e-3
+        assert (locref.cpu() - loc).abs().max().item() / loc.abs().max().item() < 4e-3
+        assert (torch.sigmoid(logits.cpu()) - torch.sigmoid(pred)).abs().max().item() < 1e-2
+        mu_ref, _ = dgp_ops.argmax_2d_from_cm(pred, nj, 1.0, 1.0)
+        assert (eng.softargmax(logits)["mu"].cpu() - mu_ref).abs().max().item() < 0.0625
+    eng.close()
+
+
 def test_batch_invariance(setup):
     """A frame's outputs do not depend on the batch it is processed in (needed for bit-exact frame sharding)."""
     eng, W, Wt, nj = setup
