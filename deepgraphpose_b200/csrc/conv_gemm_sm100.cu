@@ -77,6 +77,8 @@ __device__ __forceinline__ void load_scale_shift(float* ss, const float* __restr
   __syncwarp();
 }
 
+// kFp16 selects the 16-bit storage type at compile time (bf16 default / fp16): no dtype branches in the epilogue.
+template <bool kFp16>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -127,6 +129,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (smem carve-up, barrier init, TMEM alloc, descriptor prefetch)
+  // overlapped the previous layer's tail; from here on we touch its output, so wait for it to complete and flush.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   const int num_tiles = p.num_m_blocks * p.num_n_blocks;
 
@@ -186,7 +192,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (whole warp loops, one lane issues)
     const int block_n = p.block_n, nkb = p.num_k_blocks;
-    const uint32_t idesc = ptx::make_idesc_bf16_f32(kBlockM, block_n, p.fp16);
+    const uint32_t idesc = ptx::make_idesc_bf16_f32(kBlockM, block_n, kFp16 ? 1 : 0);
     const uint64_t adesc0 = ptx::make_desc_k_sw128(ptx::smem_u32(smem_a));
     const uint64_t bdesc0 = ptx::make_desc_k_sw128(ptx::smem_u32(smem_b));
     const uint32_t a_step = (uint32_t)a_bytes >> 4, b_step = (uint32_t)b_bytes >> 4;
@@ -274,8 +280,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             for (int i = 0; i < 4; ++i) op[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
           } else {
             uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldc + n);
-            op[0] = pack8(f, p.fp16);
-            op[1] = pack8(f + 8, p.fp16);
+            op[0] = pack8(f, kFp16);
+            op[1] = pack8(f + 8, kFp16);
           }
         }
       }
@@ -404,15 +410,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              add_residual2(f[2 * i], f[2 * i + 1], rr[i], p.fp16);
+              add_residual2(f[2 * i], f[2 * i + 1], rr[i], kFp16);
             }
           }
           if (p.relu) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.0f);
           }
-          *s0 = pack8(f, p.fp16);
-          *s1 = pack8(f + 8, p.fp16);
+          *s0 = pack8(f, kFp16);
+          *s1 = pack8(f + 8, kFp16);
         }
         ptx::fence_proxy_async_smem();  // my generic-proxy smem writes -> visible to the TMA store (async proxy)
         ptx::named_bar_sync(pair_bar, 64);
@@ -540,15 +546,27 @@ int conv_gemm_pick_stages(int block_n, int epi_bufs, int msub) {
 cudaError_t launch_conv_gemm(const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   const int grid = tiles < num_sms ? tiles : num_sms;
   const size_t smem = conv_gemm_smem_bytes(p.block_n, p.num_stages, p.epi_mode == 1 ? p.epi_bufs : 0, p.msub);
-  conv_gemm_kernel<<<grid, kThreads, smem, stream>>>(p);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (p.fp16) return cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true>, p);
+  return cudaLaunchKernelEx(&cfg, conv_gemm_kernel<false>, p);
 }
 
 }  // namespace dgp

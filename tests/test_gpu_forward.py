@@ -79,6 +79,37 @@ def test_forward_fp16_storage_meets_baseline_tolerances(setup):
     eng.close()
 
 
+@pytest.mark.parametrize("cfg", [dict(nj=16, H=1024, W=1280, locref=False, skel="chain"),   # BASELINE configs[2] shape
+                                 dict(nj=20, H=480, W=640, locref=True, skel="dense"),      # BASELINE configs[4] shape
+                                 dict(nj=5, H=747, W=832, locref=True, skel="demo")])       # BASELINE configs[0] shape
+def test_baseline_config_shapes(cfg):
+    """One frame of each BASELINE.json configuration through the whole path (head widths 16 / 60 / 15 channels)."""
+    from deepgraphpose_b200.engine import Engine
+    nj = cfg["nj"]
+    W = synthetic.make_weights(nj, seed=2, location_refinement=cfg["locref"])
+    Wt = {k: torch.from_numpy(v) for k, v in W.items()}
+    eng = Engine(nj, location_refinement=cfg["locref"])
+    eng.load_weights(W)
+    frames, _ = synthetic.make_video(1, cfg["H"], cfg["W"], nj, seed=11)
+    with torch.no_grad():
+        net = pose_net.extract_features(torch.from_numpy(frames.astype(np.float32)), Wt)
+        pred = pose_net.prediction_layer(net, Wt, "part_pred")
+        loc = pose_net.prediction_layer(net, Wt, "locref_pred") if cfg["locref"] else None
+    logits, locref = eng.forward(torch.from_numpy(frames).cuda())
+    assert logits.shape == pred.shape
+    assert (logits.cpu() - pred).abs().max().item() / pred.abs().max().item() < LOGIT_REL_TOL
+    if cfg["locref"]:
+        assert (locref.cpu() - loc).abs().max().item() / loc.abs().max().item() < LOGIT_REL_TOL
+    out = eng.softargmax(logits, locref)
+    mu_ref, _ = dgp_ops.argmax_2d_from_cm(logits.cpu(), nj, 1.0, 1.0)    # same fp32 maps -> tight
+    assert (out["mu"].cpu() - mu_ref).abs().max().item() < 1e-3
+    edges = {"chain": synthetic.chain_skeleton(nj), "dense": synthetic.dense_skeleton(nj), "demo": [(0, 1), (3, 4)]}[cfg["skel"]]
+    pot = eng.potentials(out["mu"], edges)
+    d_ref = dgp_ops.skeleton_distances(out["mu"].cpu(), dgp_ops.skeleton_matrix(edges, nj))
+    assert (pot["skel"].cpu() - d_ref).abs().max().item() < 1e-3
+    eng.close()
+
+
 def test_batch_invariance(setup):
     """A frame's outputs do not depend on the batch it is processed in (needed for bit-exact frame sharding)."""
     eng, W, Wt, nj = setup
