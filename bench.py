@@ -288,6 +288,15 @@ def main():
         achieved_tf = flops_frame * frames_timed / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
         peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
         sa_bytes = 4 * hs * ws * NJ * frames_timed
+        traffic, traffic_note = None, "no ncu capture committed"
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tpath) and B == 32:
+            with open(tpath) as f:
+                tj = json.load(f)
+            traffic = tj["traffic_bytes_per_launch"]
+            traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum per conv_gemm launch (mean of the 54 layers, B=32) from the "
+                            "committed ncu capture profiles/r01_launches.csv; algorithmic minimum %.0f MB/launch" %
+                            (tj["minimum_bytes_per_frame_bf16"] * 32 / 54 / 1e6))
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -302,7 +311,8 @@ def main():
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM, %d launches)" % gemm_n,
                          "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": (achieved_tf / peak_tf) if achieved_tf else None, "traffic": None,
+                         "frac": (achieved_tf / peak_tf) if achieved_tf else None, "traffic": traffic,
+                         "traffic_note": traffic_note,
                          "peak_source": peak_src + ", bf16 sustained", "share_of_step": gemm_ms / ms_prof,
                          "timing": "CUDA events around each of the %d launches in a second pass over the same steps (%.3f ms/step with events, %.3f without)" % (gemm_n, ms_prof / args.steps, ms / args.steps),
                          "algorithmic_gflop_per_frame": flops_frame / 1e9},
