@@ -47,7 +47,7 @@ __device__ __forceinline__ void acc_merge(Acc& a, const Acc& b) {
       a.m = b.m; a.s0 = b.s0; a.sr = b.sr; a.sc = b.sc;
     } else {
       const float m = fmaxf(a.m, b.m);
-      const float fa = __expf(a.m - m), fb = __expf(b.m - m);
+      const float fa = exp2f(a.m - m), fb = exp2f(b.m - m);  // m is kept in the log2 domain
       a.s0 = a.s0 * fa + b.s0 * fb;
       a.sr = a.sr * fa + b.sr * fb;
       a.sc = a.sc * fa + b.sc * fb;
@@ -62,6 +62,10 @@ __device__ __forceinline__ void acc_merge(Acc& a, const Acc& b) {
 
 // One CTA handles rows [r0, r1) of one frame for ALL joints (NHWC: the joint is the fastest axis).
 // `tact` threads are active with 4*tact % nj == 0, so every thread's four float4 lanes keep a fixed joint.
+// kSamePixel: nj % 4 == 0, i.e. the four lanes of a float4 belong to ONE pixel (one row/col/border test per 16 bytes).
+// Softmax numerators are kept in the log2 domain (m = max of x*gamma*log2e) so that an element costs one FFMA + EX2;
+// the running max is updated once per 4-float4 batch, not per element.
+template <bool kSamePixel>
 __global__ void __launch_bounds__(kSaThreads) softargmax_partial_kernel(
     const float* __restrict__ logits, int H, int W, int nj, float gamma, int radius, float sigma, int rows_per_split,
     int splits, int tact, SaPartial* __restrict__ part) {
@@ -98,67 +102,105 @@ __global__ void __launch_bounds__(kSaThreads) softargmax_partial_kernel(
   }
   __syncthreads();
 
-  Acc acc[4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) acc_init(acc[q]);
-
   const int L = 4 * tact;
   if (tid < tact) {
+    const float g2 = gamma * 1.4426950408889634f;
+    float m2[4], s0[4], sr[4], sc[4], thr[4], bsig[4];
+    int bidx[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      m2[q] = -CUDART_INF_F; s0[q] = sr[q] = sc[q] = 0.0f; thr[q] = -CUDART_INF_F; bsig[q] = -1.0f; bidx[q] = 0x7fffffff;
+    }
     const int dP = L / nj;
-    const int dPr = dP / W, dPc = dP - dPr * W;
-    int row[4], col[4];
+    const float dPr = (float)(dP / W), dPc = (float)(dP - (dP / W) * W);
+    const float Wf = (float)W, lo = (float)radius, hi_r = (float)(H - radius), hi_c = (float)(W - radius);
+    float frow[4], fcol[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int e = 4 * tid + q;
       const int pix = e / nj;
-      row[q] = r0 + pix / W;
-      col[q] = pix - (pix / W) * W;
+      frow[q] = (float)(r0 + pix / W);
+      fcol[q] = (float)(pix - (pix / W) * W);
     }
     const long long n_elems = (long long)(r1 - r0) * W * nj;
     const float4* src = reinterpret_cast<const float4*>(logits + ((size_t)b * H + r0) * (size_t)W * nj);
     for (long long off = 4 * tid; off < n_elems; off += 4LL * L) {
-      float4 v[4];
+      float xs[4][4];
+      bool ok[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const long long o = off + (long long)u * L;
-        if (o < n_elems) v[u] = __ldcs(src + (o >> 2));
+        ok[u] = o < n_elems;
+        if (ok[u]) {
+          const float4 v = __ldcs(src + (o >> 2));
+          xs[u][0] = v.x; xs[u][1] = v.y; xs[u][2] = v.z; xs[u][3] = v.w;
+        } else {
+          xs[u][0] = xs[u][1] = xs[u][2] = xs[u][3] = -CUDART_INF_F;
+        }
+      }
+      // running max per lane, once per batch
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float bm = fmaxf(fmaxf(xs[0][q], xs[1][q]), fmaxf(xs[2][q], xs[3][q]));
+        const float mq = bm * g2;
+        if (mq > m2[q]) {
+          const float f = exp2f(m2[q] - mq);  // exp2(-inf) = 0 on the first batch
+          s0[q] *= f; sr[q] *= f; sc[q] *= f;
+          m2[q] = mq;
+          // DLC global peak: only elements that can still tie with the running maximum need the exact sigmoid
+          // (DESIGN.md "peak candidates"): below min(max - 2, 14) fp32 sigmoids are >= 12 ulp apart.
+          thr[q] = fminf(bm - 2.0f, 14.0f);
+        }
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const long long o = off + (long long)u * L;
-        if (o < n_elems) {
-          const float xs[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+        if (ok[u]) {
+          float ah = 1.0f, aw = 1.0f, rh = 0.0f, rw = 0.0f;
+          bool border = false;
+          if (kSamePixel) {
+            rh = frow[0]; rw = fcol[0];
+            border = (frow[0] < lo) | (frow[0] >= hi_r) | (fcol[0] < lo) | (fcol[0] >= hi_c);
+            if (border) {
+              const int ri = (int)frow[0], ci = (int)fcol[0];
+              ah = Ah[ri]; rh = Rh[ri]; aw = Aw[ci]; rw = Rw[ci];
+            }
+          }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            Acc& a = acc[q];
-            const float x = xs[q];
-            const float xg = x * gamma;
-            if (xg > a.m) {
-              const float f = __expf(a.m - xg);  // exp(-inf) = 0 on the first element
-              a.s0 *= f; a.sr *= f; a.sc *= f;
-              a.m = xg;
+            if (!kSamePixel) {
+              ah = 1.0f; aw = 1.0f; rh = frow[q]; rw = fcol[q];
+              border = (frow[q] < lo) | (frow[q] >= hi_r) | (fcol[q] < lo) | (fcol[q] >= hi_c);
+              if (border) {
+                const int ri = (int)frow[q], ci = (int)fcol[q];
+                ah = Ah[ri]; rh = Rh[ri]; aw = Aw[ci]; rw = Rw[ci];
+              }
             }
-            const float e = __expf(xg - a.m);
-            const float ah = Ah[row[q]], aw = Aw[col[q]];
-            a.s0 += e * ah * aw;
-            a.sr += e * Rh[row[q]] * aw;
-            a.sc += e * ah * Rw[col[q]];
-            // DLC global peak: first max of sigmoid(x).  Only elements that can still tie with the running
-            // maximum need the exact sigmoid (see DESIGN.md "peak candidates").
-            const float xbest_floor = fminf(a.bsig >= 0.0f ? a.m / gamma - 2.0f : -CUDART_INF_F, 14.0f);
-            if (gamma <= 0.0f || x >= xbest_floor) {
+            const float x = xs[u][q];
+            const float e = exp2f(fmaf(x, g2, -m2[q]));
+            if (border) {
+              s0[q] = fmaf(e, ah * aw, s0[q]);
+              sr[q] = fmaf(e, rh * aw, sr[q]);
+              sc[q] = fmaf(e, ah * rw, sc[q]);
+            } else {
+              s0[q] += e;
+              sr[q] = fmaf(e, rh, sr[q]);
+              sc[q] = fmaf(e, rw, sc[q]);
+            }
+            if (x >= thr[q]) {
               const float s = sigmoid_tf(x);
-              const int idx = row[q] * W + col[q];
-              if (s > a.bsig || (s == a.bsig && idx < a.bidx)) { a.bsig = s; a.bidx = idx; }
+              const int idx = (int)(kSamePixel ? frow[0] : frow[q]) * W + (int)(kSamePixel ? fcol[0] : fcol[q]);
+              if (s > bsig[q] || (s == bsig[q] && idx < bidx[q])) { bsig[q] = s; bidx[q] = idx; }
             }
-            col[q] += dPc; row[q] += dPr;
-            if (col[q] >= W) { col[q] -= W; row[q] += 1; }
           }
+        }
+        if (kSamePixel) {
+          fcol[0] += dPc; frow[0] += dPr;
+          if (fcol[0] >= Wf) { fcol[0] -= Wf; frow[0] += 1.0f; }
         } else {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            col[q] += dPc; row[q] += dPr;
-            if (col[q] >= W) { col[q] -= W; row[q] += 1; }
+            fcol[q] += dPc; frow[q] += dPr;
+            if (fcol[q] >= Wf) { fcol[q] -= Wf; frow[q] += 1.0f; }
           }
         }
       }
@@ -166,8 +208,8 @@ __global__ void __launch_bounds__(kSaThreads) softargmax_partial_kernel(
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       float* r = red + (size_t)(4 * tid + q) * 6;
-      r[0] = acc[q].m; r[1] = acc[q].s0; r[2] = acc[q].sr; r[3] = acc[q].sc; r[4] = acc[q].bsig;
-      r[5] = __int_as_float(acc[q].bidx);
+      r[0] = m2[q]; r[1] = s0[q]; r[2] = sr[q]; r[3] = sc[q]; r[4] = bsig[q];
+      r[5] = __int_as_float(bidx[q]);
     }
   }
   __syncthreads();
@@ -281,7 +323,8 @@ __global__ void softmax_map_kernel(const float* __restrict__ logits, const float
       for (int dx = -radius; dx <= radius; ++dx) {
         const int xx = x + dx;
         if (xx < 0 || xx >= W) continue;
-        acc += k[dy + radius] * k[dx + radius] * __expf(logits[(((size_t)b * H + yy) * W + xx) * nj + c] * gamma - m);
+        acc += k[dy + radius] * k[dx + radius] *
+               exp2f(fmaf(logits[(((size_t)b * H + yy) * W + xx) * nj + c], gamma * 1.4426950408889634f, -m));
       }
     }
     out[t] = acc / s0;
@@ -366,11 +409,17 @@ cudaError_t launch_softargmax(const float* logits, const float* locref, int B, i
   const int radius = (int)gauss_len;
   const size_t smem = (size_t)(2 * H + 2 * W) * 4 + (size_t)4 * tact * 6 * 4;
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(softargmax_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(softargmax_partial_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(softargmax_partial_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  softargmax_partial_kernel<<<B * real_splits, kSaThreads, smem, stream>>>(logits, H, W, nj, gamma, radius, gauss_len,
-                                                                          rows_per_split, real_splits, tact, workspace);
+  if (nj % 4 == 0)
+    softargmax_partial_kernel<true><<<B * real_splits, kSaThreads, smem, stream>>>(logits, H, W, nj, gamma, radius, gauss_len,
+                                                                                  rows_per_split, real_splits, tact, workspace);
+  else
+    softargmax_partial_kernel<false><<<B * real_splits, kSaThreads, smem, stream>>>(logits, H, W, nj, gamma, radius, gauss_len,
+                                                                                   rows_per_split, real_splits, tact, workspace);
   const int n = B * nj;
   softargmax_finalize_kernel<<<(n + 127) / 128, 128, 0, stream>>>(logits, locref, B, H, W, nj, real_splits, workspace,
                                                                   stride, locref_stdev, mu, peak, lik, dlc_peak, dlc_pose,

@@ -139,25 +139,38 @@ class Engine:
         self._check(self.lib.dgp_sigmoid(self.h, _ptr(logits), _ptr(out), logits.numel(), _stream(logits.device)))
         return out
 
-    def potentials(self, mu, edges, halo_next=None, ws=None, ws_max=None, wt_max=0.0):
-        """mu (T,nj,2) f32 cuda; edges int32 (nl,2). Returns dict(skel (nl,T), temporal (T or T-1, nj), e_skel (T), e_temp (T))."""
+    def potentials(self, mu, edges, halo_next=None, ws=None, ws_max=None, wt_max=0.0, out=None):
+        """mu (T,nj,2) f32 cuda; edges int32 (nl,2). Returns dict(skel (nl,T), temporal (T or T-1, nj), e_skel (T), e_temp (T)).
+        ``out`` may carry the dict of a previous call to reuse its buffers (steady-state loops allocate nothing)."""
         mu = mu.contiguous()
         T, nj, _ = mu.shape
         dev = mu.device
-        edges = torch.as_tensor(np.asarray(edges, dtype=np.int32).reshape(-1, 2), device=dev)
-        nl = edges.shape[0]
-        skel = torch.empty((nl, T), dtype=torch.float32, device=dev)
-        temporal = torch.full((T, nj), float("nan"), dtype=torch.float32, device=dev)
-        e_skel = torch.empty((T,), dtype=torch.float32, device=dev) if ws is not None else None
-        e_temp = torch.empty((T,), dtype=torch.float32, device=dev)
-        ws_t = torch.as_tensor(np.asarray(ws, dtype=np.float32), device=dev) if ws is not None else None
-        wsm_t = torch.as_tensor(np.asarray(ws_max, dtype=np.float32), device=dev) if ws_max is not None else None
+        key = (tuple(map(tuple, np.asarray(edges, dtype=np.int64).reshape(-1, 2).tolist())), str(dev))
+        cache = self.__dict__.setdefault("_edge_cache", {})
+        if key not in cache:
+            cache[key] = torch.as_tensor(np.asarray(edges, dtype=np.int32).reshape(-1, 2), device=dev)
+        edges_t = cache[key]
+        nl = edges_t.shape[0]
+        if out is not None and out["_T"] == T and out["_nl"] == nl:
+            skel, temporal, e_skel, e_temp = out["skel"], out["_temporal_full"], out["e_skel"], out["e_temp"]
+        else:
+            skel = torch.empty((nl, T), dtype=torch.float32, device=dev)
+            temporal = torch.empty((T, nj), dtype=torch.float32, device=dev)
+            e_skel = torch.empty((T,), dtype=torch.float32, device=dev) if ws is not None else None
+            e_temp = torch.empty((T,), dtype=torch.float32, device=dev)
+        wkey = ("ws", None if ws is None else tuple(np.asarray(ws, dtype=np.float32).tolist()),
+                None if ws_max is None else tuple(np.asarray(ws_max, dtype=np.float32).tolist()), str(dev))
+        if wkey not in cache:
+            cache[wkey] = (torch.as_tensor(np.asarray(ws, dtype=np.float32), device=dev) if ws is not None else None,
+                           torch.as_tensor(np.asarray(ws_max, dtype=np.float32), device=dev) if ws_max is not None else None)
+        ws_t, wsm_t = cache[wkey]
         if halo_next is not None:
             halo_next = halo_next.contiguous()
-        self._check(self.lib.dgp_potentials(self.h, _ptr(mu), _ptr(halo_next), T, nj, _ptr(edges), nl, _ptr(ws_t), _ptr(wsm_t),
+        self._check(self.lib.dgp_potentials(self.h, _ptr(mu), _ptr(halo_next), T, nj, _ptr(edges_t), nl, _ptr(ws_t), _ptr(wsm_t),
                                             float(wt_max), _ptr(skel), _ptr(temporal), _ptr(e_skel), _ptr(e_temp), _stream(dev)))
         n_t = T if halo_next is not None else T - 1
-        return {"skel": skel, "temporal": temporal[:n_t], "e_skel": e_skel, "e_temp": e_temp}
+        return {"skel": skel, "temporal": temporal[:n_t], "e_skel": e_skel, "e_temp": e_temp, "_temporal_full": temporal,
+                "_T": T, "_nl": nl}
 
     def estimate_pose_host(self, frames_host, batch=16, gamma=1.0, gauss_len=1.0):
         """End-to-end with HOST buffers (H2D + forward + soft-argmax + D2H inside). frames_host: uint8 (T,H,W,3) CPU tensor."""
