@@ -34,6 +34,14 @@ __device__ __forceinline__ float sigmoid_literal(float x) {
   return e / (e + 1.0f);
 }
 
+// 2^x for x <= 0 on the SFU (one MUFU.EX2; results below the normal range flush to zero, which is what a softmax
+// numerator that small contributes anyway)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ void acc_init(Acc& a) {
   a.m = -CUDART_INF_F;
   a.s0 = a.sr = a.sc = 0.0f;
@@ -103,13 +111,47 @@ __global__ void __launch_bounds__(kSaThreads) softargmax_partial_kernel(
   __syncthreads();
 
   const int L = 4 * tact;
+  const long long n_elems = (long long)(r1 - r0) * W * nj;
+  const float4* src = reinterpret_cast<const float4*>(logits + ((size_t)b * H + r0) * (size_t)W * nj);
+  float* jmax = red + (size_t)4 * tact * 6;  // [nj] per-joint max logit of this CTA's rows
+
+  // ---- pass 1: per-joint max of the CTA's rows (HBM read; leaves the rows in L2 for pass 2)
+  {
+    float mx[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+    if (tid < tact) {
+      for (long long off = 4 * tid; off < n_elems; off += L) {
+        const float4 v = __ldg(src + (off >> 2));
+        mx[0] = fmaxf(mx[0], v.x); mx[1] = fmaxf(mx[1], v.y); mx[2] = fmaxf(mx[2], v.z); mx[3] = fmaxf(mx[3], v.w);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) red[4 * tid + q] = mx[q];
+    }
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+    for (int j = warp; j < nj; j += nwarps) {
+      float m = -CUDART_INF_F;
+      for (int e = j + nj * lane; e < L; e += nj * 32) m = fmaxf(m, red[e]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if (lane == 0) jmax[j] = m;
+    }
+    __syncthreads();
+  }
+
+  // ---- pass 2: softmax numerators against the known max (one FFMA + EX2 per element, no rescaling), border-aware
+  // blur weights, and the exact sigmoid only for the few elements that can tie with the maximum
   if (tid < tact) {
     const float g2 = gamma * 1.4426950408889634f;
     float m2[4], s0[4], sr[4], sc[4], thr[4], bsig[4];
     int bidx[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      m2[q] = -CUDART_INF_F; s0[q] = sr[q] = sc[q] = 0.0f; thr[q] = -CUDART_INF_F; bsig[q] = -1.0f; bidx[q] = 0x7fffffff;
+      const float xm = jmax[(4 * tid + q) % nj];
+      m2[q] = xm * g2;
+      // DLC global peak: only elements that can still tie with the maximum need the exact sigmoid
+      // (DESIGN.md "peak candidates"): below min(max - 2, 14) fp32 sigmoids are >= 12 ulp apart.
+      thr[q] = fminf(xm - 2.0f, 14.0f);
+      s0[q] = sr[q] = sc[q] = 0.0f; bsig[q] = -1.0f; bidx[q] = 0x7fffffff;
     }
     const int dP = L / nj;
     const float dPr = (float)(dP / W), dPc = (float)(dP - (dP / W) * W);
@@ -122,8 +164,6 @@ __global__ void __launch_bounds__(kSaThreads) softargmax_partial_kernel(
       frow[q] = (float)(r0 + pix / W);
       fcol[q] = (float)(pix - (pix / W) * W);
     }
-    const long long n_elems = (long long)(r1 - r0) * W * nj;
-    const float4* src = reinterpret_cast<const float4*>(logits + ((size_t)b * H + r0) * (size_t)W * nj);
     for (long long off = 4 * tid; off < n_elems; off += 4LL * L) {
       float xs[4][4];
       bool ok[4];
@@ -134,22 +174,6 @@ __global__ void __launch_bounds__(kSaThreads) softargmax_partial_kernel(
         if (ok[u]) {
           const float4 v = __ldcs(src + (o >> 2));
           xs[u][0] = v.x; xs[u][1] = v.y; xs[u][2] = v.z; xs[u][3] = v.w;
-        } else {
-          xs[u][0] = xs[u][1] = xs[u][2] = xs[u][3] = -CUDART_INF_F;
-        }
-      }
-      // running max per lane, once per batch
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float bm = fmaxf(fmaxf(xs[0][q], xs[1][q]), fmaxf(xs[2][q], xs[3][q]));
-        const float mq = bm * g2;
-        if (mq > m2[q]) {
-          const float f = exp2f(m2[q] - mq);  // exp2(-inf) = 0 on the first batch
-          s0[q] *= f; sr[q] *= f; sc[q] *= f;
-          m2[q] = mq;
-          // DLC global peak: only elements that can still tie with the running maximum need the exact sigmoid
-          // (DESIGN.md "peak candidates"): below min(max - 2, 14) fp32 sigmoids are >= 12 ulp apart.
-          thr[q] = fminf(bm - 2.0f, 14.0f);
         }
       }
 #pragma unroll
@@ -176,7 +200,7 @@ __global__ void __launch_bounds__(kSaThreads) softargmax_partial_kernel(
               }
             }
             const float x = xs[u][q];
-            const float e = exp2f(fmaf(x, g2, -m2[q]));
+            const float e = ex2_approx(fmaf(x, g2, -m2[q]));
             if (border) {
               s0[q] = fmaf(e, ah * aw, s0[q]);
               sr[q] = fmaf(e, rh * aw, sr[q]);
@@ -339,41 +363,71 @@ __global__ void sigmoid_map_kernel(const float4* __restrict__ x, float4* __restr
   }
 }
 
-// Skeleton distances and temporal differences on the soft-argmax coordinates.  One thread per frame.
-__global__ void potentials_kernel(const float* __restrict__ mu, const float* __restrict__ halo_next, int T, int nj,
-                                  const int* __restrict__ edges, int nl, float stride, const float* __restrict__ ws,
-                                  const float* __restrict__ ws_max, float wt_max, float* __restrict__ skel,
-                                  float* __restrict__ temporal, float* __restrict__ e_skel,
-                                  float* __restrict__ e_temp) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= T) return;
-  const float* m = mu + (size_t)t * nj * 2;
-  float es = 0.0f;
-  for (int l = 0; l < nl; ++l) {
-    const int a = edges[2 * l], b = edges[2 * l + 1];
-    // S (mu*stride + stride/2): the +stride/2 cancels between the +1 and -1 entries only in exact arithmetic;
-    // keep the reference's order of operations.
-    const float dr = (m[2 * a] * stride + 0.5f * stride) - (m[2 * b] * stride + 0.5f * stride);
-    const float dc = (m[2 * a + 1] * stride + 0.5f * stride) - (m[2 * b + 1] * stride + 0.5f * stride);
-    const float d = sqrtf(dr * dr + dc * dc);
-    if (skel) skel[(size_t)l * T + t] = d;
-    if (ws) es += ws[l] * (fmaxf(d - ws_max[l], 0.0f) + ws_max[l]);
+// Skeleton distances and temporal differences on the soft-argmax coordinates.  One thread per frame, 128 frames per
+// CTA; the CTA's (128 + 1 halo) x nj x 2 coordinates are staged in shared memory with coalesced 128-bit loads
+// (a per-thread walk over its own 8*nj-byte row would cost one L1 wavefront per 4 bytes), and the temporal rows go
+// back through shared memory so that global stores are coalesced too.
+constexpr int kPotFrames = 128;
+__global__ void __launch_bounds__(kPotFrames) potentials_kernel(
+    const float* __restrict__ mu, const float* __restrict__ halo_next, int T, int nj, const int* __restrict__ edges,
+    int nl, float stride, const float* __restrict__ ws, const float* __restrict__ ws_max, float wt_max,
+    float* __restrict__ skel, float* __restrict__ temporal, float* __restrict__ e_skel, float* __restrict__ e_temp) {
+  extern __shared__ float psm[];
+  const int row = 2 * nj + 1;                       // +1: conflict-free column walks
+  float* sm_mu = psm;                               // [kPotFrames + 1][row]
+  float* sm_t = psm + (kPotFrames + 1) * row;       // [kPotFrames][nj + 1]
+  const int t0 = blockIdx.x * kPotFrames;
+  const int nf = min(kPotFrames, T - t0);
+  const int nload = (t0 + nf < T) ? nf + 1 : nf;    // + first frame of the next CTA's range
+  const float* src = mu + (size_t)t0 * nj * 2;
+  for (int i = threadIdx.x; i < nload * 2 * nj; i += blockDim.x) {
+    const int f = i / (2 * nj);
+    sm_mu[f * row + (i - f * 2 * nj)] = src[i];
   }
-  if (e_skel) e_skel[t] = es;
-  const float* mn = (t + 1 < T) ? m + (size_t)nj * 2 : halo_next;
-  if (mn != nullptr) {
-    float et = 0.0f;
-    for (int j = 0; j < nj; ++j) {
-      const float dr = (m[2 * j] * stride + 0.5f * stride) - (mn[2 * j] * stride + 0.5f * stride);
-      const float dc = (m[2 * j + 1] * stride + 0.5f * stride) - (mn[2 * j + 1] * stride + 0.5f * stride);
+  const bool have_next_global = (t0 + nf < T);
+  if (!have_next_global && halo_next != nullptr)
+    for (int i = threadIdx.x; i < 2 * nj; i += blockDim.x) sm_mu[nf * row + i] = halo_next[i];
+  __syncthreads();
+  const int lt = threadIdx.x;
+  const int t = t0 + lt;
+  const bool active = lt < nf;
+  const bool has_next = active && (lt + 1 < nf || have_next_global || halo_next != nullptr);
+  if (active) {
+    const float* m = sm_mu + lt * row;
+    float es = 0.0f;
+    for (int l = 0; l < nl; ++l) {
+      const int a = __ldg(edges + 2 * l), b = __ldg(edges + 2 * l + 1);
+      // S (mu*stride + stride/2): keep the reference's order of operations
+      const float dr = (m[2 * a] * stride + 0.5f * stride) - (m[2 * b] * stride + 0.5f * stride);
+      const float dc = (m[2 * a + 1] * stride + 0.5f * stride) - (m[2 * b + 1] * stride + 0.5f * stride);
       const float d = sqrtf(dr * dr + dc * dc);
-      if (temporal) temporal[(size_t)t * nj + j] = d;
-      const float dth = fmaxf(d - wt_max, 0.0f) + wt_max;
-      et += dth * dth;
+      if (skel) skel[(size_t)l * T + t] = d;
+      if (ws) es += __ldg(ws + l) * (fmaxf(d - __ldg(ws_max + l), 0.0f) + __ldg(ws_max + l));
+    }
+    if (e_skel) e_skel[t] = es;
+    float et = 0.0f;
+    if (has_next) {
+      const float* mn = m + row;
+      for (int j = 0; j < nj; ++j) {
+        const float dr = (m[2 * j] * stride + 0.5f * stride) - (mn[2 * j] * stride + 0.5f * stride);
+        const float dc = (m[2 * j + 1] * stride + 0.5f * stride) - (mn[2 * j + 1] * stride + 0.5f * stride);
+        const float d = sqrtf(dr * dr + dc * dc);
+        sm_t[lt * (nj + 1) + j] = d;
+        const float dth = fmaxf(d - wt_max, 0.0f) + wt_max;
+        et += dth * dth;
+      }
     }
     if (e_temp) e_temp[t] = et;
-  } else if (e_temp) {
-    e_temp[t] = 0.0f;
+  }
+  __syncthreads();
+  if (temporal) {
+    // rows [t0, t0 + nvalid) of temporal are contiguous in global memory
+    const int nvalid = (have_next_global || halo_next != nullptr) ? nf : nf - 1;
+    float* dst = temporal + (size_t)t0 * nj;
+    for (int i = threadIdx.x; i < nvalid * nj; i += blockDim.x) {
+      const int f = i / nj;
+      dst[i] = sm_t[f * (nj + 1) + (i - f * nj)];
+    }
   }
 }
 
@@ -407,7 +461,7 @@ cudaError_t launch_softargmax(const float* logits, const float* locref, int B, i
   rows_per_split = (rows_per_split + 1) & ~1;  // even row boundaries keep the float4 loads 16 B aligned
   const int real_splits = (H + rows_per_split - 1) / rows_per_split;
   const int radius = (int)gauss_len;
-  const size_t smem = (size_t)(2 * H + 2 * W) * 4 + (size_t)4 * tact * 6 * 4;
+  const size_t smem = (size_t)(2 * H + 2 * W) * 4 + (size_t)4 * tact * 6 * 4 + (size_t)nj * 4;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(softargmax_partial_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)
@@ -452,8 +506,14 @@ cudaError_t launch_potentials(const float* mu, const float* halo_next, int T, in
                               float stride, const float* ws, const float* ws_max, float wt_max, float* skel,
                               float* temporal, float* e_skel, float* e_temp, cudaStream_t stream) {
   if (T <= 0) return cudaSuccess;
-  potentials_kernel<<<(T + 127) / 128, 128, 0, stream>>>(mu, halo_next, T, nj, edges, nl, stride, ws, ws_max, wt_max,
-                                                         skel, temporal, e_skel, e_temp);
+  const size_t smem = ((size_t)(kPotFrames + 1) * (2 * nj + 1) + (size_t)kPotFrames * (nj + 1)) * sizeof(float);
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(potentials_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  potentials_kernel<<<(T + kPotFrames - 1) / kPotFrames, kPotFrames, smem, stream>>>(mu, halo_next, T, nj, edges, nl, stride, ws,
+                                                                                   ws_max, wt_max, skel, temporal, e_skel, e_temp);
   return cudaGetLastError();
 }
 
