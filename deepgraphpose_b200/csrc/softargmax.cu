@@ -119,9 +119,17 @@ __global__ void __launch_bounds__(kSaThreads) softargmax_partial_kernel(
   {
     float mx[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
     if (tid < tact) {
-      for (long long off = 4 * tid; off < n_elems; off += L) {
-        const float4 v = __ldg(src + (off >> 2));
-        mx[0] = fmaxf(mx[0], v.x); mx[1] = fmaxf(mx[1], v.y); mx[2] = fmaxf(mx[2], v.z); mx[3] = fmaxf(mx[3], v.w);
+      for (long long off = 4 * tid; off < n_elems; off += 8LL * L) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {  // 8 independent 128-bit loads in flight per thread
+          const long long o = off + (long long)u * L;
+          v[u] = o < n_elems ? __ldg(src + (o >> 2)) : make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          mx[0] = fmaxf(mx[0], v[u].x); mx[1] = fmaxf(mx[1], v[u].y); mx[2] = fmaxf(mx[2], v[u].z); mx[3] = fmaxf(mx[3], v[u].w);
+        }
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q) red[4 * tid + q] = mx[q];
@@ -164,6 +172,12 @@ __global__ void __launch_bounds__(kSaThreads) softargmax_partial_kernel(
       frow[q] = (float)(r0 + pix / W);
       fcol[q] = (float)(pix - (pix / W) * W);
     }
+    float4 nxt[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long o = 4LL * tid + (long long)u * L;
+      if (o < n_elems) nxt[u] = __ldcs(src + (o >> 2));
+    }
     for (long long off = 4 * tid; off < n_elems; off += 4LL * L) {
       float xs[4][4];
       bool ok[4];
@@ -171,10 +185,13 @@ __global__ void __launch_bounds__(kSaThreads) softargmax_partial_kernel(
       for (int u = 0; u < 4; ++u) {
         const long long o = off + (long long)u * L;
         ok[u] = o < n_elems;
-        if (ok[u]) {
-          const float4 v = __ldcs(src + (o >> 2));
-          xs[u][0] = v.x; xs[u][1] = v.y; xs[u][2] = v.z; xs[u][3] = v.w;
-        }
+        xs[u][0] = nxt[u].x; xs[u][1] = nxt[u].y; xs[u][2] = nxt[u].z; xs[u][3] = nxt[u].w;
+      }
+      // the next batch's loads are issued before this batch is consumed (the rows come from L2 after pass 1)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long o = off + 4LL * L + (long long)u * L;
+        if (o < n_elems) nxt[u] = __ldcs(src + (o >> 2));
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
