@@ -111,19 +111,20 @@ __global__ void __launch_bounds__(kSaThreads) softargmax_partial_kernel(
   __syncthreads();
 
   const int L = 4 * tact;
-  const long long n_elems = (long long)(r1 - r0) * W * nj;
+  const int n_elems = (r1 - r0) * W * nj;  // < 2^31: one frame's rows
   const float4* src = reinterpret_cast<const float4*>(logits + ((size_t)b * H + r0) * (size_t)W * nj);
   float* jmax = red + (size_t)4 * tact * 6;  // [nj] per-joint max logit of this CTA's rows
+  const float g2 = gamma * 1.4426950408889634f;
 
   // ---- pass 1: per-joint max of the CTA's rows (HBM read; leaves the rows in L2 for pass 2)
   {
     float mx[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
     if (tid < tact) {
-      for (long long off = 4 * tid; off < n_elems; off += 8LL * L) {
+      for (int off = 4 * tid; off < n_elems; off += 8 * L) {
         float4 v[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {  // 8 independent 128-bit loads in flight per thread
-          const long long o = off + (long long)u * L;
+          const int o = off + u * L;
           v[u] = o < n_elems ? __ldg(src + (o >> 2)) : make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
         }
 #pragma unroll
@@ -146,24 +147,23 @@ __global__ void __launch_bounds__(kSaThreads) softargmax_partial_kernel(
     __syncthreads();
   }
 
-  // ---- pass 2: softmax numerators against the known max (one FFMA + EX2 per element, no rescaling), border-aware
-  // blur weights, and the exact sigmoid only for the few elements that can tie with the maximum
+  // ---- pass 2: softmax numerators against the known max -- per element one FFMA + EX2 and three accumulates with the
+  // INTERIOR weights (1, row, col); the few border pixels are corrected afterwards.  The exact sigmoid is evaluated
+  // only for elements that can still tie with the maximum (one branch per 16 bytes).
   if (tid < tact) {
-    const float g2 = gamma * 1.4426950408889634f;
     float m2[4], s0[4], sr[4], sc[4], thr[4], bsig[4];
     int bidx[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const float xm = jmax[(4 * tid + q) % nj];
       m2[q] = xm * g2;
-      // DLC global peak: only elements that can still tie with the maximum need the exact sigmoid
-      // (DESIGN.md "peak candidates"): below min(max - 2, 14) fp32 sigmoids are >= 12 ulp apart.
+      // DLC global peak (DESIGN.md "peak candidates"): below min(max - 2, 14) fp32 sigmoids are >= 12 ulp apart.
       thr[q] = fminf(xm - 2.0f, 14.0f);
       s0[q] = sr[q] = sc[q] = 0.0f; bsig[q] = -1.0f; bidx[q] = 0x7fffffff;
     }
     const int dP = L / nj;
     const float dPr = (float)(dP / W), dPc = (float)(dP - (dP / W) * W);
-    const float Wf = (float)W, lo = (float)radius, hi_r = (float)(H - radius), hi_c = (float)(W - radius);
+    const float Wf = (float)W;
     float frow[4], fcol[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -175,62 +175,38 @@ __global__ void __launch_bounds__(kSaThreads) softargmax_partial_kernel(
     float4 nxt[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const long long o = 4LL * tid + (long long)u * L;
+      const int o = 4 * tid + u * L;
       if (o < n_elems) nxt[u] = __ldcs(src + (o >> 2));
     }
-    for (long long off = 4 * tid; off < n_elems; off += 4LL * L) {
+    for (int off = 4 * tid; off < n_elems; off += 4 * L) {
       float xs[4][4];
-      bool ok[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const long long o = off + (long long)u * L;
-        ok[u] = o < n_elems;
-        xs[u][0] = nxt[u].x; xs[u][1] = nxt[u].y; xs[u][2] = nxt[u].z; xs[u][3] = nxt[u].w;
-      }
+      for (int u = 0; u < 4; ++u) { xs[u][0] = nxt[u].x; xs[u][1] = nxt[u].y; xs[u][2] = nxt[u].z; xs[u][3] = nxt[u].w; }
       // the next batch's loads are issued before this batch is consumed (the rows come from L2 after pass 1)
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const long long o = off + 4LL * L + (long long)u * L;
+        const int o = off + (4 + u) * L;
         if (o < n_elems) nxt[u] = __ldcs(src + (o >> 2));
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        if (ok[u]) {
-          float ah = 1.0f, aw = 1.0f, rh = 0.0f, rw = 0.0f;
-          bool border = false;
-          if (kSamePixel) {
-            rh = frow[0]; rw = fcol[0];
-            border = (frow[0] < lo) | (frow[0] >= hi_r) | (fcol[0] < lo) | (fcol[0] >= hi_c);
-            if (border) {
-              const int ri = (int)frow[0], ci = (int)fcol[0];
-              ah = Ah[ri]; rh = Rh[ri]; aw = Aw[ci]; rw = Rw[ci];
-            }
-          }
+        if (off + u * L < n_elems) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            if (!kSamePixel) {
-              ah = 1.0f; aw = 1.0f; rh = frow[q]; rw = fcol[q];
-              border = (frow[q] < lo) | (frow[q] >= hi_r) | (fcol[q] < lo) | (fcol[q] >= hi_c);
-              if (border) {
-                const int ri = (int)frow[q], ci = (int)fcol[q];
-                ah = Ah[ri]; rh = Rh[ri]; aw = Aw[ci]; rw = Rw[ci];
+            const float rh = kSamePixel ? frow[0] : frow[q], rw = kSamePixel ? fcol[0] : fcol[q];
+            const float e = ex2_approx(fmaf(xs[u][q], g2, -m2[q]));
+            s0[q] += e;
+            sr[q] = fmaf(e, rh, sr[q]);
+            sc[q] = fmaf(e, rw, sc[q]);
+          }
+          if ((xs[u][0] >= thr[0]) | (xs[u][1] >= thr[1]) | (xs[u][2] >= thr[2]) | (xs[u][3] >= thr[3])) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (xs[u][q] >= thr[q]) {
+                const float s = sigmoid_tf(xs[u][q]);
+                const int idx = (int)(kSamePixel ? frow[0] : frow[q]) * W + (int)(kSamePixel ? fcol[0] : fcol[q]);
+                if (s > bsig[q] || (s == bsig[q] && idx < bidx[q])) { bsig[q] = s; bidx[q] = idx; }
               }
-            }
-            const float x = xs[u][q];
-            const float e = ex2_approx(fmaf(x, g2, -m2[q]));
-            if (border) {
-              s0[q] = fmaf(e, ah * aw, s0[q]);
-              sr[q] = fmaf(e, rh * aw, sr[q]);
-              sc[q] = fmaf(e, ah * rw, sc[q]);
-            } else {
-              s0[q] += e;
-              sr[q] = fmaf(e, rh, sr[q]);
-              sc[q] = fmaf(e, rw, sc[q]);
-            }
-            if (x >= thr[q]) {
-              const float s = sigmoid_tf(x);
-              const int idx = (int)(kSamePixel ? frow[0] : frow[q]) * W + (int)(kSamePixel ? fcol[0] : fcol[q]);
-              if (s > bsig[q] || (s == bsig[q] && idx < bidx[q])) { bsig[q] = s; bidx[q] = idx; }
             }
           }
         }
@@ -256,6 +232,7 @@ __global__ void __launch_bounds__(kSaThreads) softargmax_partial_kernel(
   __syncthreads();
 
   const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+  const bool all_border = (W <= 2 * radius) || (H <= 2 * radius);
   for (int j = warp; j < nj; j += nwarps) {
     Acc a;
     acc_init(a);
@@ -264,6 +241,34 @@ __global__ void __launch_bounds__(kSaThreads) softargmax_partial_kernel(
       Acc t;
       t.m = r[0]; t.s0 = r[1]; t.sr = r[2]; t.sc = r[3]; t.bsig = r[4]; t.bidx = __float_as_int(r[5]);
       acc_merge(a, t);
+    }
+    // ---- border correction (fixed order -> deterministic): pixels within `radius` of an edge lose the taps that fall
+    // outside, so their weights are (Ah*Aw, Rh*Aw, Ah*Rw) instead of (1, row, col).
+    {
+      const float m2j = jmax[j] * g2;
+      const float* fj = logits + (size_t)b * H * W * nj + j;
+      float d0 = 0.0f, dr = 0.0f, dc = 0.0f;
+      auto add_px = [&](int r, int c) {
+        const float e = ex2_approx(fmaf(__ldg(fj + ((size_t)r * W + c) * nj), g2, -m2j));
+        const float ah = Ah[r], aw = Aw[c];
+        d0 += e * (ah * aw - 1.0f);
+        dr += e * (Rh[r] * aw - (float)r);
+        dc += e * (ah * Rw[c] - (float)c);
+      };
+      for (int r = r0; r < r1; ++r)
+        if (all_border || r < radius || r >= H - radius)
+          for (int c = lane; c < W; c += 32) add_px(r, c);
+      if (!all_border) {
+        const int nb_lo = max(r0, radius), nb_hi = min(r1, H - radius);
+        const int nside = max(nb_hi - nb_lo, 0) * 2 * radius;
+        for (int k = lane; k < nside; k += 32) {
+          const int rr = nb_lo + k / (2 * radius);
+          const int sidx = k - (k / (2 * radius)) * (2 * radius);
+          add_px(rr, sidx < radius ? sidx : W - 2 * radius + sidx);
+        }
+      }
+      a.m = m2j;  // every partial of joint j carries the same max; a lane that merged nothing still holds -inf
+      a.s0 += d0; a.sr += dr; a.sc += dc;   // per-lane partials join the shuffle reduction below
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
