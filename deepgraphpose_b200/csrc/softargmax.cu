@@ -78,37 +78,15 @@ __global__ void __launch_bounds__(kSaThreads) softargmax_partial_kernel(
     const float* __restrict__ logits, int H, int W, int nj, float gamma, int radius, float sigma, int rows_per_split,
     int splits, int tact, SaPartial* __restrict__ part) {
   extern __shared__ float sm[];
-  float* Ah = sm;          // [H]  sum of valid taps
-  float* Rh = Ah + H;      // [H]  sum of valid taps * source row
-  float* Aw = Rh + H;      // [W]
-  float* Rw = Aw + W;      // [W]
-  float* red = Rw + W;     // [4*tact][6]
+  float* red = sm;         // [4*tact][6] (+ [nj] per-joint max)
 
   const int b = blockIdx.x / splits;
   const int sp = blockIdx.x - b * splits;
   const int r0 = sp * rows_per_split;
   const int r1 = min(H, r0 + rows_per_split);
   const int tid = threadIdx.x;
-
-  // 1-D Gaussian taps (make_gaussian_2d_kernel: exp(-0.5 (d/sigma)^2) normalised), border-aware sums.
-  float knorm = 0.0f;
-  for (int d = -radius; d <= radius; ++d) knorm += expf(-0.5f * (d / sigma) * (d / sigma));
-  for (int i = tid; i < H + W; i += blockDim.x) {
-    const bool is_h = i < H;
-    const int pos = is_h ? i : i - H;
-    const int n = is_h ? H : W;
-    float a = 0.0f, r = 0.0f;
-    for (int d = -radius; d <= radius; ++d) {
-      const int dst = pos - d;  // blurred-map index that receives source `pos` through tap d
-      if (dst >= 0 && dst < n) {
-        const float k = expf(-0.5f * (d / sigma) * (d / sigma)) / knorm;
-        a += k;
-        r += k * (float)dst;
-      }
-    }
-    if (is_h) { Ah[pos] = a; Rh[pos] = r; } else { Aw[pos] = a; Rw[pos] = r; }
-  }
-  __syncthreads();
+  (void)radius;
+  (void)sigma;
 
   const int L = 4 * tact;
   const int n_elems = (r1 - r0) * W * nj;  // < 2^31: one frame's rows
@@ -232,7 +210,6 @@ __global__ void __launch_bounds__(kSaThreads) softargmax_partial_kernel(
   __syncthreads();
 
   const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
-  const bool all_border = (W <= 2 * radius) || (H <= 2 * radius);
   for (int j = warp; j < nj; j += nwarps) {
     Acc a;
     acc_init(a);
@@ -241,34 +218,6 @@ __global__ void __launch_bounds__(kSaThreads) softargmax_partial_kernel(
       Acc t;
       t.m = r[0]; t.s0 = r[1]; t.sr = r[2]; t.sc = r[3]; t.bsig = r[4]; t.bidx = __float_as_int(r[5]);
       acc_merge(a, t);
-    }
-    // ---- border correction (fixed order -> deterministic): pixels within `radius` of an edge lose the taps that fall
-    // outside, so their weights are (Ah*Aw, Rh*Aw, Ah*Rw) instead of (1, row, col).
-    {
-      const float m2j = jmax[j] * g2;
-      const float* fj = logits + (size_t)b * H * W * nj + j;
-      float d0 = 0.0f, dr = 0.0f, dc = 0.0f;
-      auto add_px = [&](int r, int c) {
-        const float e = ex2_approx(fmaf(__ldg(fj + ((size_t)r * W + c) * nj), g2, -m2j));
-        const float ah = Ah[r], aw = Aw[c];
-        d0 += e * (ah * aw - 1.0f);
-        dr += e * (Rh[r] * aw - (float)r);
-        dc += e * (ah * Rw[c] - (float)c);
-      };
-      for (int r = r0; r < r1; ++r)
-        if (all_border || r < radius || r >= H - radius)
-          for (int c = lane; c < W; c += 32) add_px(r, c);
-      if (!all_border) {
-        const int nb_lo = max(r0, radius), nb_hi = min(r1, H - radius);
-        const int nside = max(nb_hi - nb_lo, 0) * 2 * radius;
-        for (int k = lane; k < nside; k += 32) {
-          const int rr = nb_lo + k / (2 * radius);
-          const int sidx = k - (k / (2 * radius)) * (2 * radius);
-          add_px(rr, sidx < radius ? sidx : W - 2 * radius + sidx);
-        }
-      }
-      a.m = m2j;  // every partial of joint j carries the same max; a lane that merged nothing still holds -inf
-      a.s0 += d0; a.sr += dr; a.sc += dc;   // per-lane partials join the shuffle reduction below
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -288,27 +237,96 @@ __global__ void __launch_bounds__(kSaThreads) softargmax_partial_kernel(
   }
 }
 
-// One thread per (frame, joint): merge the row-split partials, then the O(1) read-outs.
+// Blur border weights of source index `pos` on an axis of length n (zero padding, VALID conv, then renormalisation):
+// a = sum of the taps that stay inside, r = sum of those taps times the blurred-map index they land on.
+__device__ __forceinline__ void border_weights(int pos, int n, int radius, float sigma, float knorm, float& a, float& r) {
+  a = 0.0f;
+  r = 0.0f;
+  for (int d = -radius; d <= radius; ++d) {
+    const int dst = pos - d;
+    if (dst >= 0 && dst < n) {
+      const float k = expf(-0.5f * (d / sigma) * (d / sigma)) / knorm;
+      a += k;
+      r += k * (float)dst;
+    }
+  }
+}
+
+// One WARP per (frame, joint): merge the row-split partials (interior weights), add the border correction
+// (pixels within `radius` of an edge lose the taps that fall outside: weights (Ah*Aw, Rh*Aw, Ah*Rw) instead of
+// (1, row, col); fixed lane order -> deterministic), then lane 0 does the O(1) read-outs.
 __global__ void softargmax_finalize_kernel(const float* __restrict__ logits, const float* __restrict__ locref, int B,
                                            int H, int W, int nj, int splits, const SaPartial* __restrict__ part,
-                                           float stride, float locref_stdev, float* __restrict__ mu,
-                                           int* __restrict__ peak, float* __restrict__ lik, int* __restrict__ dlc_peak,
-                                           float* __restrict__ dlc_pose, float* __restrict__ norm) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+                                           float gamma, int radius, float sigma, float stride, float locref_stdev,
+                                           float* __restrict__ mu, int* __restrict__ peak, float* __restrict__ lik,
+                                           int* __restrict__ dlc_peak, float* __restrict__ dlc_pose,
+                                           float* __restrict__ norm) {
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (t >= B * nj) return;
   const int b = t / nj, j = t - b * nj;
   Acc a;
   acc_init(a);
-  for (int sp = 0; sp < splits; ++sp) {
+  for (int sp = lane; sp < splits; sp += 32) {
     const SaPartial& p = part[((size_t)b * splits + sp) * nj + j];
     Acc q;
     q.m = p.m; q.s0 = p.s0; q.sr = p.sr; q.sc = p.sc; q.bsig = p.bsig; q.bidx = p.bidx;
     acc_merge(a, q);
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    Acc q;
+    q.m = __shfl_xor_sync(0xffffffffu, a.m, o);
+    q.s0 = __shfl_xor_sync(0xffffffffu, a.s0, o);
+    q.sr = __shfl_xor_sync(0xffffffffu, a.sr, o);
+    q.sc = __shfl_xor_sync(0xffffffffu, a.sc, o);
+    q.bsig = __shfl_xor_sync(0xffffffffu, a.bsig, o);
+    q.bidx = __shfl_xor_sync(0xffffffffu, a.bidx, o);
+    acc_merge(a, q);
+  }
+  const float* fr = logits + (size_t)b * H * W * nj + j;
+  {
+    const float g2 = gamma * 1.4426950408889634f;
+    float knorm = 0.0f;
+    for (int d = -radius; d <= radius; ++d) knorm += expf(-0.5f * (d / sigma) * (d / sigma));
+    const bool all_border = (W <= 2 * radius) || (H <= 2 * radius);
+    float d0 = 0.0f, dr = 0.0f, dc = 0.0f;
+    auto add_px = [&](int r, int c) {
+      const float e = ex2_approx(fmaf(__ldg(fr + ((size_t)r * W + c) * nj), g2, -a.m));
+      float ah, rh, aw, rw;
+      border_weights(r, H, radius, sigma, knorm, ah, rh);
+      border_weights(c, W, radius, sigma, knorm, aw, rw);
+      d0 += e * (ah * aw - 1.0f);
+      dr += e * (rh * aw - (float)r);
+      dc += e * (ah * rw - (float)c);
+    };
+    if (all_border) {
+      for (int k = lane; k < H * W; k += 32) add_px(k / W, k - (k / W) * W);
+    } else {
+      const int nrow = 2 * radius * W;                 // full top / bottom rows
+      for (int k = lane; k < nrow; k += 32) {
+        const int rr = k / W;
+        add_px(rr < radius ? rr : H - 2 * radius + rr, k - rr * W);
+      }
+      const int nside = (H - 2 * radius) * 2 * radius;  // left / right columns of the remaining rows
+      for (int k = lane; k < nside; k += 32) {
+        const int rr = radius + k / (2 * radius);
+        const int sidx = k - (k / (2 * radius)) * (2 * radius);
+        add_px(rr, sidx < radius ? sidx : W - 2 * radius + sidx);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      d0 += __shfl_xor_sync(0xffffffffu, d0, o);
+      dr += __shfl_xor_sync(0xffffffffu, dr, o);
+      dc += __shfl_xor_sync(0xffffffffu, dc, o);
+    }
+    a.s0 += d0; a.sr += dr; a.sc += dc;
+  }
+  if (lane != 0) return;
   const float mur = a.sr / a.s0, muc = a.sc / a.s0;  // 0/0 -> NaN, as softmax_tensor / (sum + 1e-100) in fp32
   if (mu) { mu[2 * t] = mur; mu[2 * t + 1] = muc; }
   if (norm) { norm[2 * t] = a.m; norm[2 * t + 1] = a.s0; }
-  const float* fr = logits + (size_t)b * H * W * nj + j;
 
   if (peak || lik) {
     int pr = -1, pc = -1;
@@ -483,7 +501,7 @@ cudaError_t launch_softargmax(const float* logits, const float* locref, int B, i
   rows_per_split = (rows_per_split + 1) & ~1;  // even row boundaries keep the float4 loads 16 B aligned
   const int real_splits = (H + rows_per_split - 1) / rows_per_split;
   const int radius = (int)gauss_len;
-  const size_t smem = (size_t)(2 * H + 2 * W) * 4 + (size_t)4 * tact * 6 * 4 + (size_t)nj * 4;
+  const size_t smem = (size_t)4 * tact * 6 * 4 + (size_t)nj * 4;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(softargmax_partial_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)
@@ -497,9 +515,9 @@ cudaError_t launch_softargmax(const float* logits, const float* locref, int B, i
     softargmax_partial_kernel<false><<<B * real_splits, kSaThreads, smem, stream>>>(logits, H, W, nj, gamma, radius, gauss_len,
                                                                                    rows_per_split, real_splits, tact, workspace);
   const int n = B * nj;
-  softargmax_finalize_kernel<<<(n + 127) / 128, 128, 0, stream>>>(logits, locref, B, H, W, nj, real_splits, workspace,
-                                                                  stride, locref_stdev, mu, peak, lik, dlc_peak, dlc_pose,
-                                                                  norm);
+  softargmax_finalize_kernel<<<(n + 3) / 4, 128, 0, stream>>>(logits, locref, B, H, W, nj, real_splits, workspace, gamma,
+                                                              radius, gauss_len, stride, locref_stdev, mu, peak, lik,
+                                                              dlc_peak, dlc_pose, norm);
   return cudaGetLastError();
 }
 
