@@ -822,7 +822,7 @@ int dgp_softargmax(dgp_handle* h, const float* logits_dev, const float* locref_d
   if (B == 0) return DGP_OK;
   if (!logits_dev || B < 0 || H < 2 || W < 2 || nj < 1) return fail(h, DGP_ERR_INVALID, "dgp_softargmax: bad argument");
   if ((H & 1) || (W & 1)) return fail(h, DGP_ERR_INVALID, "dgp_softargmax: scoremap dims must be even (they are 2*ceil(./16))");
-  if (gauss_len < 1.0f) return fail(h, DGP_ERR_INVALID, "dgp_softargmax: gauss_len must be >= 1");
+  if (gauss_len < 1.0f || gauss_len >= 5.0f) return fail(h, DGP_ERR_INVALID, "dgp_softargmax: gauss_len must be in [1, 5)");
   if (!(gamma > 0.0f)) return fail(h, DGP_ERR_INVALID, "dgp_softargmax: gamma must be > 0");
   if (((uintptr_t)logits_dev & 15) != 0) return fail(h, DGP_ERR_INVALID, "dgp_softargmax: logits must be 16-byte aligned");
   CU_OK(h, cudaSetDevice(h->device));

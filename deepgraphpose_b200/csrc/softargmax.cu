@@ -239,15 +239,14 @@ __global__ void __launch_bounds__(kSaThreads) softargmax_partial_kernel(
 
 // Blur border weights of source index `pos` on an axis of length n (zero padding, VALID conv, then renormalisation):
 // a = sum of the taps that stay inside, r = sum of those taps times the blurred-map index they land on.
-__device__ __forceinline__ void border_weights(int pos, int n, int radius, float sigma, float knorm, float& a, float& r) {
+__device__ __forceinline__ void border_weights(int pos, int n, int radius, const float* kt, float& a, float& r) {
   a = 0.0f;
   r = 0.0f;
   for (int d = -radius; d <= radius; ++d) {
     const int dst = pos - d;
     if (dst >= 0 && dst < n) {
-      const float k = expf(-0.5f * (d / sigma) * (d / sigma)) / knorm;
-      a += k;
-      r += k * (float)dst;
+      a += kt[d + radius];
+      r += kt[d + radius] * (float)dst;
     }
   }
 }
@@ -289,13 +288,19 @@ __global__ void softargmax_finalize_kernel(const float* __restrict__ logits, con
     const float g2 = gamma * 1.4426950408889634f;
     float knorm = 0.0f;
     for (int d = -radius; d <= radius; ++d) knorm += expf(-0.5f * (d / sigma) * (d / sigma));
+    float kt[9];  // normalised 1-D taps (radius <= 4)
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const float d = (float)(i - radius);
+      kt[i] = i <= 2 * radius ? expf(-0.5f * (d / sigma) * (d / sigma)) / knorm : 0.0f;
+    }
     const bool all_border = (W <= 2 * radius) || (H <= 2 * radius);
     float d0 = 0.0f, dr = 0.0f, dc = 0.0f;
     auto add_px = [&](int r, int c) {
       const float e = ex2_approx(fmaf(__ldg(fr + ((size_t)r * W + c) * nj), g2, -a.m));
       float ah, rh, aw, rw;
-      border_weights(r, H, radius, sigma, knorm, ah, rh);
-      border_weights(c, W, radius, sigma, knorm, aw, rw);
+      border_weights(r, H, radius, kt, ah, rh);
+      border_weights(c, W, radius, kt, aw, rw);
       d0 += e * (ah * aw - 1.0f);
       dr += e * (rh * aw - (float)r);
       dc += e * (ah * rw - (float)c);
