@@ -68,6 +68,20 @@ __device__ __forceinline__ void acc_merge(Acc& a, const Acc& b) {
   }
 }
 
+// Blur border weights of source index `pos` on an axis of length n (zero padding, VALID conv, then renormalisation):
+// a = sum of the taps that stay inside, r = sum of those taps times the blurred-map index they land on.
+__device__ __forceinline__ void border_weights(int pos, int n, int radius, const float* kt, float& a, float& r) {
+  a = 0.0f;
+  r = 0.0f;
+  for (int d = -radius; d <= radius; ++d) {
+    const int dst = pos - d;
+    if (dst >= 0 && dst < n) {
+      a += kt[d + radius];
+      r += kt[d + radius] * (float)dst;
+    }
+  }
+}
+
 // One CTA handles rows [r0, r1) of one frame for ALL joints (NHWC: the joint is the fastest axis).
 // `tact` threads are active with 4*tact % nj == 0, so every thread's four float4 lanes keep a fixed joint.
 // kSamePixel: nj % 4 == 0, i.e. the four lanes of a float4 belong to ONE pixel (one row/col/border test per 16 bytes).
@@ -85,8 +99,6 @@ __global__ void __launch_bounds__(kSaThreads) softargmax_partial_kernel(
   const int r0 = sp * rows_per_split;
   const int r1 = min(H, r0 + rows_per_split);
   const int tid = threadIdx.x;
-  (void)radius;
-  (void)sigma;
 
   const int L = 4 * tact;
   const int n_elems = (r1 - r0) * W * nj;  // < 2^31: one frame's rows
@@ -200,6 +212,55 @@ __global__ void __launch_bounds__(kSaThreads) softargmax_partial_kernel(
         }
       }
     }
+    if (kSamePixel) {
+      // ---- border correction, nj % 4 == 0: pixels within `radius` of an edge lose the taps that fall outside, so their
+      // weights are (Ah*Aw, Rh*Aw, Ah*Rw) instead of (1, row, col).  Every float4 of a border pixel goes to a thread whose
+      // lanes hold the same joints (nj | 4*tact and (nj/4) | tact), so the deltas land in the right accumulators.
+      float knorm = 0.0f;
+      for (int d = -radius; d <= radius; ++d) knorm += expf(-0.5f * (d / sigma) * (d / sigma));
+      float kt[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+        const float d = (float)(i - radius);
+        kt[i] = i <= 2 * radius ? expf(-0.5f * (d / sigma) * (d / sigma)) / knorm : 0.0f;
+      }
+      const bool all_border = (W <= 2 * radius) || (H <= 2 * radius);
+      const int q4n = nj >> 2, f4_per_row = W * q4n;
+      auto fix = [&](const float4 v, float ah, float rh, float aw, float rw, float fr_, float fc_) {
+        const float xs4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float e = ex2_approx(fmaf(xs4[q], g2, -m2[q]));
+          s0[q] = fmaf(e, ah * aw - 1.0f, s0[q]);
+          sr[q] = fmaf(e, rh * aw - fr_, sr[q]);
+          sc[q] = fmaf(e, ah * rw - fc_, sc[q]);
+        }
+      };
+      for (int r = r0; r < r1; ++r) {
+        if (!(all_border || r < radius || r >= H - radius)) continue;
+        float ah, rh;
+        border_weights(r, H, radius, kt, ah, rh);
+        for (int f = tid; f < f4_per_row; f += tact) {
+          const int c = f / q4n;
+          float aw, rw;
+          border_weights(c, W, radius, kt, aw, rw);
+          fix(__ldg(src + (size_t)(r - r0) * f4_per_row + f), ah, rh, aw, rw, (float)r, (float)c);
+        }
+      }
+      if (!all_border) {
+        const int nb_lo = max(r0, radius), nb_hi = min(r1, H - radius);
+        const int nside = max(nb_hi - nb_lo, 0) * 2 * radius * q4n;
+        for (int k = tid; k < nside; k += tact) {
+          const int pk = k / q4n, q4 = k - pk * q4n;
+          const int rr = nb_lo + pk / (2 * radius);
+          const int sidx = pk - (pk / (2 * radius)) * (2 * radius);
+          const int c = sidx < radius ? sidx : W - 2 * radius + sidx;
+          float aw, rw;
+          border_weights(c, W, radius, kt, aw, rw);
+          fix(__ldg(src + ((size_t)(rr - r0) * W + c) * q4n + q4), 1.0f, (float)rr, aw, rw, (float)rr, (float)c);
+        }
+      }
+    }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       float* r = red + (size_t)(4 * tid + q) * 6;
@@ -237,20 +298,6 @@ __global__ void __launch_bounds__(kSaThreads) softargmax_partial_kernel(
   }
 }
 
-// Blur border weights of source index `pos` on an axis of length n (zero padding, VALID conv, then renormalisation):
-// a = sum of the taps that stay inside, r = sum of those taps times the blurred-map index they land on.
-__device__ __forceinline__ void border_weights(int pos, int n, int radius, const float* kt, float& a, float& r) {
-  a = 0.0f;
-  r = 0.0f;
-  for (int d = -radius; d <= radius; ++d) {
-    const int dst = pos - d;
-    if (dst >= 0 && dst < n) {
-      a += kt[d + radius];
-      r += kt[d + radius] * (float)dst;
-    }
-  }
-}
-
 // One WARP per (frame, joint): merge the row-split partials (interior weights), add the border correction
 // (pixels within `radius` of an edge lose the taps that fall outside: weights (Ah*Aw, Rh*Aw, Ah*Rw) instead of
 // (1, row, col); fixed lane order -> deterministic), then lane 0 does the O(1) read-outs.
@@ -284,7 +331,7 @@ __global__ void softargmax_finalize_kernel(const float* __restrict__ logits, con
     acc_merge(a, q);
   }
   const float* fr = logits + (size_t)b * H * W * nj + j;
-  {
+  if ((nj & 3) != 0) {  // nj % 4 == 0: the streaming kernel already applied the border correction
     const float g2 = gamma * 1.4426950408889634f;
     float knorm = 0.0f;
     for (int d = -radius; d <= radius; ++d) knorm += expf(-0.5f * (d / sigma) * (d / sigma));
@@ -425,9 +472,11 @@ __global__ void __launch_bounds__(kPotFrames) potentials_kernel(
   const int nf = min(kPotFrames, T - t0);
   const int nload = (t0 + nf < T) ? nf + 1 : nf;    // + first frame of the next CTA's range
   const float* src = mu + (size_t)t0 * nj * 2;
-  for (int i = threadIdx.x; i < nload * 2 * nj; i += blockDim.x) {
-    const int f = i / (2 * nj);
-    sm_mu[f * row + (i - f * 2 * nj)] = src[i];
+  {
+    // division-free 2-D copy: each warp takes whole rows, lanes walk the 2*nj coordinates of a row
+    const int w = threadIdx.x >> 5, ln = threadIdx.x & 31;
+    for (int f = w; f < nload; f += (int)(blockDim.x >> 5))
+      for (int c = ln; c < 2 * nj; c += 32) sm_mu[f * row + c] = src[f * 2 * nj + c];
   }
   const bool have_next_global = (t0 + nf < T);
   if (!have_next_global && halo_next != nullptr)
@@ -469,9 +518,14 @@ __global__ void __launch_bounds__(kPotFrames) potentials_kernel(
     // rows [t0, t0 + nvalid) of temporal are contiguous in global memory
     const int nvalid = (have_next_global || halo_next != nullptr) ? nf : nf - 1;
     float* dst = temporal + (size_t)t0 * nj;
-    for (int i = threadIdx.x; i < nvalid * nj; i += blockDim.x) {
-      const int f = i / nj;
-      dst[i] = sm_t[f * (nj + 1) + (i - f * nj)];
+    const int w = threadIdx.x >> 5, ln = threadIdx.x & 31;
+    if (nj <= 16) {  // two rows per warp pass keep all 32 lanes busy
+      const int half = ln >> 4, jj = ln & 15;
+      for (int f = 2 * w + half; f < nvalid; f += 2 * (int)(blockDim.x >> 5))
+        if (jj < nj) dst[f * nj + jj] = sm_t[f * (nj + 1) + jj];
+    } else {
+      for (int f = w; f < nvalid; f += (int)(blockDim.x >> 5))
+        for (int jj = ln; jj < nj; jj += 32) dst[f * nj + jj] = sm_t[f * (nj + 1) + jj];
     }
   }
 }
