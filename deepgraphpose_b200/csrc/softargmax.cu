@@ -82,6 +82,14 @@ __device__ __forceinline__ void border_weights(int pos, int n, int radius, const
   }
 }
 
+// Border pixels lose the blur taps that fall outside the map: replace the interior weights (1, row, col) already
+// accumulated for this element by (Ah*Aw, Rh*Aw, Ah*Rw).  Out of line on purpose.
+__device__ __noinline__ float3 border_fix(float e, int r, int c, const float* Ah, const float* Rh, const float* Aw,
+                                          const float* Rw) {
+  const float ah = Ah[r], aw = Aw[c];
+  return make_float3(e * (ah * aw - 1.0f), e * (Rh[r] * aw - (float)r), e * (ah * Rw[c] - (float)c));
+}
+
 // One CTA handles rows [r0, r1) of one frame for ALL joints (NHWC: the joint is the fastest axis).
 // `tact` threads are active with 4*tact % nj == 0, so every thread's four float4 lanes keep a fixed joint.
 // kSamePixel: nj % 4 == 0, i.e. the four lanes of a float4 belong to ONE pixel (one row/col/border test per 16 bytes).
@@ -92,7 +100,11 @@ __global__ void __launch_bounds__(kSaThreads) softargmax_partial_kernel(
     const float* __restrict__ logits, int H, int W, int nj, float gamma, int radius, float sigma, int rows_per_split,
     int splits, int tact, SaPartial* __restrict__ part) {
   extern __shared__ float sm[];
-  float* red = sm;         // [4*tact][6] (+ [nj] per-joint max)
+  float* Ah = sm;          // [H]  border-aware blur weights: sum of the taps that stay inside
+  float* Rh = Ah + H;      // [H]  sum of those taps times the blurred-map row they land on
+  float* Aw = Rh + H;      // [W]
+  float* Rw = Aw + W;      // [W]
+  float* red = Rw + W;     // [4*tact][6] (+ [nj] per-joint max)
 
   const int b = blockIdx.x / splits;
   const int sp = blockIdx.x - b * splits;
@@ -100,6 +112,25 @@ __global__ void __launch_bounds__(kSaThreads) softargmax_partial_kernel(
   const int r1 = min(H, r0 + rows_per_split);
   const int tid = threadIdx.x;
 
+  {  // tables are ready long before pass 2 (two __syncthreads in between)
+    float knorm = 0.0f;
+    for (int d = -radius; d <= radius; ++d) knorm += expf(-0.5f * (d / sigma) * (d / sigma));
+    for (int i = tid; i < H + W; i += blockDim.x) {
+      const bool is_h = i < H;
+      const int pos = is_h ? i : i - H;
+      const int n = is_h ? H : W;
+      float a = 0.0f, r = 0.0f;
+      for (int d = -radius; d <= radius; ++d) {
+        const int dst = pos - d;
+        if (dst >= 0 && dst < n) {
+          const float k = expf(-0.5f * (d / sigma) * (d / sigma)) / knorm;
+          a += k;
+          r += k * (float)dst;
+        }
+      }
+      if (is_h) { Ah[pos] = a; Rh[pos] = r; } else { Aw[pos] = a; Rw[pos] = r; }
+    }
+  }
   const int L = 4 * tact;
   const int n_elems = (r1 - r0) * W * nj;  // < 2^31: one frame's rows
   const float4* src = reinterpret_cast<const float4*>(logits + ((size_t)b * H + r0) * (size_t)W * nj);
@@ -153,7 +184,7 @@ __global__ void __launch_bounds__(kSaThreads) softargmax_partial_kernel(
     }
     const int dP = L / nj;
     const float dPr = (float)(dP / W), dPc = (float)(dP - (dP / W) * W);
-    const float Wf = (float)W;
+    const float Wf = (float)W, lo = (float)radius, hi_r = (float)(H - radius), hi_c = (float)(W - radius);
     float frow[4], fcol[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -188,6 +219,18 @@ __global__ void __launch_bounds__(kSaThreads) softargmax_partial_kernel(
             s0[q] += e;
             sr[q] = fmaf(e, rh, sr[q]);
             sc[q] = fmaf(e, rw, sc[q]);
+            if (!kSamePixel && ((rh < lo) | (rh >= hi_r) | (rw < lo) | (rw >= hi_c))) {
+              const float3 d = border_fix(e, (int)rh, (int)rw, Ah, Rh, Aw, Rw);
+              s0[q] += d.x; sr[q] += d.y; sc[q] += d.z;
+            }
+          }
+          if (kSamePixel && ((frow[0] < lo) | (frow[0] >= hi_r) | (fcol[0] < lo) | (fcol[0] >= hi_c))) {
+            // rare (a few % of the pixels): a real branch to an out-of-line fix-up keeps the hot loop short
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float3 d = border_fix(ex2_approx(fmaf(xs[u][q], g2, -m2[q])), (int)frow[0], (int)fcol[0], Ah, Rh, Aw, Rw);
+              s0[q] += d.x; sr[q] += d.y; sc[q] += d.z;
+            }
           }
           if ((xs[u][0] >= thr[0]) | (xs[u][1] >= thr[1]) | (xs[u][2] >= thr[2]) | (xs[u][3] >= thr[3])) {
 #pragma unroll
@@ -209,55 +252,6 @@ __global__ void __launch_bounds__(kSaThreads) softargmax_partial_kernel(
             fcol[q] += dPc; frow[q] += dPr;
             if (fcol[q] >= Wf) { fcol[q] -= Wf; frow[q] += 1.0f; }
           }
-        }
-      }
-    }
-    if (kSamePixel) {
-      // ---- border correction, nj % 4 == 0: pixels within `radius` of an edge lose the taps that fall outside, so their
-      // weights are (Ah*Aw, Rh*Aw, Ah*Rw) instead of (1, row, col).  Every float4 of a border pixel goes to a thread whose
-      // lanes hold the same joints (nj | 4*tact and (nj/4) | tact), so the deltas land in the right accumulators.
-      float knorm = 0.0f;
-      for (int d = -radius; d <= radius; ++d) knorm += expf(-0.5f * (d / sigma) * (d / sigma));
-      float kt[9];
-#pragma unroll
-      for (int i = 0; i < 9; ++i) {
-        const float d = (float)(i - radius);
-        kt[i] = i <= 2 * radius ? expf(-0.5f * (d / sigma) * (d / sigma)) / knorm : 0.0f;
-      }
-      const bool all_border = (W <= 2 * radius) || (H <= 2 * radius);
-      const int q4n = nj >> 2, f4_per_row = W * q4n;
-      auto fix = [&](const float4 v, float ah, float rh, float aw, float rw, float fr_, float fc_) {
-        const float xs4[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float e = ex2_approx(fmaf(xs4[q], g2, -m2[q]));
-          s0[q] = fmaf(e, ah * aw - 1.0f, s0[q]);
-          sr[q] = fmaf(e, rh * aw - fr_, sr[q]);
-          sc[q] = fmaf(e, ah * rw - fc_, sc[q]);
-        }
-      };
-      for (int r = r0; r < r1; ++r) {
-        if (!(all_border || r < radius || r >= H - radius)) continue;
-        float ah, rh;
-        border_weights(r, H, radius, kt, ah, rh);
-        for (int f = tid; f < f4_per_row; f += tact) {
-          const int c = f / q4n;
-          float aw, rw;
-          border_weights(c, W, radius, kt, aw, rw);
-          fix(__ldg(src + (size_t)(r - r0) * f4_per_row + f), ah, rh, aw, rw, (float)r, (float)c);
-        }
-      }
-      if (!all_border) {
-        const int nb_lo = max(r0, radius), nb_hi = min(r1, H - radius);
-        const int nside = max(nb_hi - nb_lo, 0) * 2 * radius * q4n;
-        for (int k = tid; k < nside; k += tact) {
-          const int pk = k / q4n, q4 = k - pk * q4n;
-          const int rr = nb_lo + pk / (2 * radius);
-          const int sidx = pk - (pk / (2 * radius)) * (2 * radius);
-          const int c = sidx < radius ? sidx : W - 2 * radius + sidx;
-          float aw, rw;
-          border_weights(c, W, radius, kt, aw, rw);
-          fix(__ldg(src + ((size_t)(rr - r0) * W + c) * q4n + q4), 1.0f, (float)rr, aw, rw, (float)rr, (float)c);
         }
       }
     }
@@ -331,7 +325,7 @@ __global__ void softargmax_finalize_kernel(const float* __restrict__ logits, con
     acc_merge(a, q);
   }
   const float* fr = logits + (size_t)b * H * W * nj + j;
-  if ((nj & 3) != 0) {  // nj % 4 == 0: the streaming kernel already applied the border correction
+  if (false) {  // the streaming kernel applies the border correction in-line
     const float g2 = gamma * 1.4426950408889634f;
     float knorm = 0.0f;
     for (int d = -radius; d <= radius; ++d) knorm += expf(-0.5f * (d / sigma) * (d / sigma));
@@ -560,7 +554,7 @@ cudaError_t launch_softargmax(const float* logits, const float* locref, int B, i
   rows_per_split = (rows_per_split + 1) & ~1;  // even row boundaries keep the float4 loads 16 B aligned
   const int real_splits = (H + rows_per_split - 1) / rows_per_split;
   const int radius = (int)gauss_len;
-  const size_t smem = (size_t)4 * tact * 6 * 4 + (size_t)nj * 4;
+  const size_t smem = (size_t)(2 * H + 2 * W) * 4 + (size_t)4 * tact * 6 * 4 + (size_t)nj * 4;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(softargmax_partial_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)
