@@ -68,28 +68,6 @@ __device__ __forceinline__ void acc_merge(Acc& a, const Acc& b) {
   }
 }
 
-// Blur border weights of source index `pos` on an axis of length n (zero padding, VALID conv, then renormalisation):
-// a = sum of the taps that stay inside, r = sum of those taps times the blurred-map index they land on.
-__device__ __forceinline__ void border_weights(int pos, int n, int radius, const float* kt, float& a, float& r) {
-  a = 0.0f;
-  r = 0.0f;
-  for (int d = -radius; d <= radius; ++d) {
-    const int dst = pos - d;
-    if (dst >= 0 && dst < n) {
-      a += kt[d + radius];
-      r += kt[d + radius] * (float)dst;
-    }
-  }
-}
-
-// Border pixels lose the blur taps that fall outside the map: replace the interior weights (1, row, col) already
-// accumulated for this element by (Ah*Aw, Rh*Aw, Ah*Rw).  Out of line on purpose.
-__device__ __noinline__ float3 border_fix(float e, int r, int c, const float* Ah, const float* Rh, const float* Aw,
-                                          const float* Rw) {
-  const float ah = Ah[r], aw = Aw[c];
-  return make_float3(e * (ah * aw - 1.0f), e * (Rh[r] * aw - (float)r), e * (ah * Rw[c] - (float)c));
-}
-
 // One CTA handles rows [r0, r1) of one frame for ALL joints (NHWC: the joint is the fastest axis).
 // `tact` threads are active with 4*tact % nj == 0, so every thread's four float4 lanes keep a fixed joint.
 // kSamePixel: nj % 4 == 0, i.e. the four lanes of a float4 belong to ONE pixel (one row/col/border test per 16 bytes).
@@ -100,37 +78,16 @@ __global__ void __launch_bounds__(kSaThreads) softargmax_partial_kernel(
     const float* __restrict__ logits, int H, int W, int nj, float gamma, int radius, float sigma, int rows_per_split,
     int splits, int tact, SaPartial* __restrict__ part) {
   extern __shared__ float sm[];
-  float* Ah = sm;          // [H]  border-aware blur weights: sum of the taps that stay inside
-  float* Rh = Ah + H;      // [H]  sum of those taps times the blurred-map row they land on
-  float* Aw = Rh + H;      // [W]
-  float* Rw = Aw + W;      // [W]
-  float* red = Rw + W;     // [4*tact][6] (+ [nj] per-joint max)
+  float* red = sm;         // [4*tact][6] (+ [nj] per-joint max)
 
   const int b = blockIdx.x / splits;
   const int sp = blockIdx.x - b * splits;
   const int r0 = sp * rows_per_split;
   const int r1 = min(H, r0 + rows_per_split);
   const int tid = threadIdx.x;
+  (void)radius;
+  (void)sigma;
 
-  {  // tables are ready long before pass 2 (two __syncthreads in between)
-    float knorm = 0.0f;
-    for (int d = -radius; d <= radius; ++d) knorm += expf(-0.5f * (d / sigma) * (d / sigma));
-    for (int i = tid; i < H + W; i += blockDim.x) {
-      const bool is_h = i < H;
-      const int pos = is_h ? i : i - H;
-      const int n = is_h ? H : W;
-      float a = 0.0f, r = 0.0f;
-      for (int d = -radius; d <= radius; ++d) {
-        const int dst = pos - d;
-        if (dst >= 0 && dst < n) {
-          const float k = expf(-0.5f * (d / sigma) * (d / sigma)) / knorm;
-          a += k;
-          r += k * (float)dst;
-        }
-      }
-      if (is_h) { Ah[pos] = a; Rh[pos] = r; } else { Aw[pos] = a; Rw[pos] = r; }
-    }
-  }
   const int L = 4 * tact;
   const int n_elems = (r1 - r0) * W * nj;  // < 2^31: one frame's rows
   const float4* src = reinterpret_cast<const float4*>(logits + ((size_t)b * H + r0) * (size_t)W * nj);
@@ -184,7 +141,7 @@ __global__ void __launch_bounds__(kSaThreads) softargmax_partial_kernel(
     }
     const int dP = L / nj;
     const float dPr = (float)(dP / W), dPc = (float)(dP - (dP / W) * W);
-    const float Wf = (float)W, lo = (float)radius, hi_r = (float)(H - radius), hi_c = (float)(W - radius);
+    const float Wf = (float)W;
     float frow[4], fcol[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -219,18 +176,6 @@ __global__ void __launch_bounds__(kSaThreads) softargmax_partial_kernel(
             s0[q] += e;
             sr[q] = fmaf(e, rh, sr[q]);
             sc[q] = fmaf(e, rw, sc[q]);
-            if (!kSamePixel && ((rh < lo) | (rh >= hi_r) | (rw < lo) | (rw >= hi_c))) {
-              const float3 d = border_fix(e, (int)rh, (int)rw, Ah, Rh, Aw, Rw);
-              s0[q] += d.x; sr[q] += d.y; sc[q] += d.z;
-            }
-          }
-          if (kSamePixel && ((frow[0] < lo) | (frow[0] >= hi_r) | (fcol[0] < lo) | (fcol[0] >= hi_c))) {
-            // rare (a few % of the pixels): a real branch to an out-of-line fix-up keeps the hot loop short
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float3 d = border_fix(ex2_approx(fmaf(xs[u][q], g2, -m2[q])), (int)frow[0], (int)fcol[0], Ah, Rh, Aw, Rw);
-              s0[q] += d.x; sr[q] += d.y; sc[q] += d.z;
-            }
           }
           if ((xs[u][0] >= thr[0]) | (xs[u][1] >= thr[1]) | (xs[u][2] >= thr[2]) | (xs[u][3] >= thr[3])) {
 #pragma unroll
@@ -292,6 +237,20 @@ __global__ void __launch_bounds__(kSaThreads) softargmax_partial_kernel(
   }
 }
 
+// Blur border weights of source index `pos` on an axis of length n (zero padding, VALID conv, then renormalisation):
+// a = sum of the taps that stay inside, r = sum of those taps times the blurred-map index they land on.
+__device__ __forceinline__ void border_weights(int pos, int n, int radius, const float* kt, float& a, float& r) {
+  a = 0.0f;
+  r = 0.0f;
+  for (int d = -radius; d <= radius; ++d) {
+    const int dst = pos - d;
+    if (dst >= 0 && dst < n) {
+      a += kt[d + radius];
+      r += kt[d + radius] * (float)dst;
+    }
+  }
+}
+
 // One WARP per (frame, joint): merge the row-split partials (interior weights), add the border correction
 // (pixels within `radius` of an edge lose the taps that fall outside: weights (Ah*Aw, Rh*Aw, Ah*Rw) instead of
 // (1, row, col); fixed lane order -> deterministic), then lane 0 does the O(1) read-outs.
@@ -325,7 +284,7 @@ __global__ void softargmax_finalize_kernel(const float* __restrict__ logits, con
     acc_merge(a, q);
   }
   const float* fr = logits + (size_t)b * H * W * nj + j;
-  if (false) {  // the streaming kernel applies the border correction in-line
+  {
     const float g2 = gamma * 1.4426950408889634f;
     float knorm = 0.0f;
     for (int d = -radius; d <= radius; ++d) knorm += expf(-0.5f * (d / sigma) * (d / sigma));
@@ -350,11 +309,13 @@ __global__ void softargmax_finalize_kernel(const float* __restrict__ logits, con
       for (int k = lane; k < H * W; k += 32) add_px(k / W, k - (k / W) * W);
     } else {
       const int nrow = 2 * radius * W;                 // full top / bottom rows
+#pragma unroll 4
       for (int k = lane; k < nrow; k += 32) {
         const int rr = k / W;
         add_px(rr < radius ? rr : H - 2 * radius + rr, k - rr * W);
       }
       const int nside = (H - 2 * radius) * 2 * radius;  // left / right columns of the remaining rows
+#pragma unroll 4
       for (int k = lane; k < nside; k += 32) {
         const int rr = radius + k / (2 * radius);
         const int sidx = k - (k / (2 * radius)) * (2 * radius);
@@ -513,14 +474,8 @@ __global__ void __launch_bounds__(kPotFrames) potentials_kernel(
     const int nvalid = (have_next_global || halo_next != nullptr) ? nf : nf - 1;
     float* dst = temporal + (size_t)t0 * nj;
     const int w = threadIdx.x >> 5, ln = threadIdx.x & 31;
-    if (nj <= 16) {  // two rows per warp pass keep all 32 lanes busy
-      const int half = ln >> 4, jj = ln & 15;
-      for (int f = 2 * w + half; f < nvalid; f += 2 * (int)(blockDim.x >> 5))
-        if (jj < nj) dst[f * nj + jj] = sm_t[f * (nj + 1) + jj];
-    } else {
-      for (int f = w; f < nvalid; f += (int)(blockDim.x >> 5))
-        for (int jj = ln; jj < nj; jj += 32) dst[f * nj + jj] = sm_t[f * (nj + 1) + jj];
-    }
+    for (int f = w; f < nvalid; f += (int)(blockDim.x >> 5))
+      for (int jj = ln; jj < nj; jj += 32) dst[f * nj + jj] = sm_t[f * (nj + 1) + jj];
   }
 }
 
@@ -554,7 +509,7 @@ cudaError_t launch_softargmax(const float* logits, const float* locref, int B, i
   rows_per_split = (rows_per_split + 1) & ~1;  // even row boundaries keep the float4 loads 16 B aligned
   const int real_splits = (H + rows_per_split - 1) / rows_per_split;
   const int radius = (int)gauss_len;
-  const size_t smem = (size_t)(2 * H + 2 * W) * 4 + (size_t)4 * tact * 6 * 4 + (size_t)nj * 4;
+  const size_t smem = (size_t)4 * tact * 6 * 4 + (size_t)nj * 4;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(softargmax_partial_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)
