@@ -428,10 +428,17 @@ __global__ void __launch_bounds__(kPotFrames) potentials_kernel(
   const int nload = (t0 + nf < T) ? nf + 1 : nf;    // + first frame of the next CTA's range
   const float* src = mu + (size_t)t0 * nj * 2;
   {
-    // division-free 2-D copy: each warp takes whole rows, lanes walk the 2*nj coordinates of a row
-    const int w = threadIdx.x >> 5, ln = threadIdx.x & 31;
-    for (int f = w; f < nload; f += (int)(blockDim.x >> 5))
-      for (int c = ln; c < 2 * nj; c += 32) sm_mu[f * row + c] = src[f * 2 * nj + c];
+    // flat coalesced copy with an incrementally maintained (frame, coordinate) pair: no division in the loop and all
+    // of a thread's loads are independent
+    const int rl = 2 * nj;
+    int f = (int)threadIdx.x / rl, c = (int)threadIdx.x - f * rl;
+    const int df = (int)blockDim.x / rl, dc = (int)blockDim.x - df * rl;
+#pragma unroll 8
+    for (int i = threadIdx.x; i < nload * rl; i += blockDim.x) {
+      sm_mu[f * row + c] = src[i];
+      f += df; c += dc;
+      if (c >= rl) { c -= rl; f += 1; }
+    }
   }
   const bool have_next_global = (t0 + nf < T);
   if (!have_next_global && halo_next != nullptr)
@@ -473,9 +480,14 @@ __global__ void __launch_bounds__(kPotFrames) potentials_kernel(
     // rows [t0, t0 + nvalid) of temporal are contiguous in global memory
     const int nvalid = (have_next_global || halo_next != nullptr) ? nf : nf - 1;
     float* dst = temporal + (size_t)t0 * nj;
-    const int w = threadIdx.x >> 5, ln = threadIdx.x & 31;
-    for (int f = w; f < nvalid; f += (int)(blockDim.x >> 5))
-      for (int jj = ln; jj < nj; jj += 32) dst[f * nj + jj] = sm_t[f * (nj + 1) + jj];
+    int f = (int)threadIdx.x / nj, c = (int)threadIdx.x - f * nj;
+    const int df = (int)blockDim.x / nj, dc = (int)blockDim.x - df * nj;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < nvalid * nj; i += blockDim.x) {
+      dst[i] = sm_t[f * (nj + 1) + c];
+      f += df; c += dc;
+      if (c >= nj) { c -= nj; f += 1; }
+    }
   }
 }
 
