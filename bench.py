@@ -177,7 +177,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--batch", type=int, default=0, help="frames per step per GPU (0 = engine.suggest_batch)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=12)
@@ -203,7 +203,8 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    B = args.batch
+    from deepgraphpose_b200.engine import suggest_batch
+    B = args.batch if args.batch > 0 else suggest_batch(H, W)
     eng = Engine(NJ, location_refinement=False, device=local_rank)
     eng.load_weights(synthetic.make_weights(NJ, seed=0, location_refinement=False))
     edges = synthetic.chain_skeleton(NJ)
@@ -290,19 +291,20 @@ def main():
         sa_bytes = 4 * hs * ws * NJ * frames_timed
         traffic, traffic_note = None, "no ncu capture committed"
         tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(tpath) and B == 32:
+        if os.path.exists(tpath):
             with open(tpath) as f:
                 tj = json.load(f)
-            traffic = tj["traffic_bytes_per_launch"]
-            traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum per conv_gemm launch (mean of the 54 layers, B=32) from the "
-                            "committed ncu capture profiles/r01_launches.csv; algorithmic minimum %.0f MB/launch" %
-                            (tj["minimum_bytes_per_frame_bf16"] * 32 / 54 / 1e6))
+            traffic = tj["traffic_bytes_per_frame"] * B / 54
+            traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum per conv_gemm launch (mean of the 54 layers) scaled from the "
+                            "committed ncu capture profiles/r01_launches.csv (B=%d there); algorithmic minimum %.0f MB/launch" %
+                            (tj["batch"], tj["minimum_bytes_per_frame_bf16"] * B / 54 / 1e6))
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": B, "frame": [H, W, 3], "num_joints": NJ,
                        "skeleton": "chain", "l2": "4 rotating input batches (%d MB) and per-layer activations (>600 MB/step) exceed the 126 MB L2" % (n_pool * B * H * W * 3 // 2 ** 20),
+                       "batch_choice": "engine.suggest_batch: tile counts of the persistent GEMM grid land on multiples of the SM count",
                        "parallelism": "frame shards x%d, 1-frame halo all_gather" % world if world > 1 else "single GPU"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": B * H * W * 3,

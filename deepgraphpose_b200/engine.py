@@ -24,6 +24,47 @@ def output_dims(H, W):
     return (a.value, b.value), (c.value, d.value)
 
 
+def suggest_batch(H, W, lo=24, hi=64, num_sms=148):
+    """Frames per batch that minimise wave quantisation of the persistent conv-GEMM grid (one CTA per SM).
+
+    Every GEMM layer runs ceil(B*pixels/tile_rows) * n_blocks tiles on `num_sms` CTAs; a batch size for which the
+    dominant layers' tile counts are (just under) a multiple of the SM count avoids a nearly empty last wave.  Layers are
+    weighted by their roofline bound (max of bf16 tensor time and HBM time), tile shapes follow csrc/capi.cu."""
+    c2 = lambda v: -(-v // 2)
+    layers = []  # (pixels per frame, tile rows, n_blocks, weight)
+    hh, ww = c2(H), c2(W)
+    def add(px, cin_k, cout, bytes_per_px):
+        bn = min(cout, 256)
+        rows = 256 if bn <= 128 else 128
+        wgt = max(2.0 * px * cin_k * cout / 1414e12, px * bytes_per_px / 6464e9)
+        layers.append((px, rows, -(-cout // bn), wgt))
+    add(hh * ww, 256, 64, 32 + 128)
+    hh, ww = c2(hh), c2(ww)
+    cin = 64
+    for base, units, bstride in ((64, 3, 2), (128, 4, 2), (256, 6, 1), (512, 3, 1)):
+        for u in range(units):
+            s_ = bstride if u == units - 1 else 1
+            depth = 4 * base
+            ho, wo = (c2(hh), c2(ww)) if s_ == 2 else (hh, ww)
+            if cin != depth:
+                add(hh * ww, cin, depth, 2 * (cin + depth))
+            add(hh * ww, cin, base, 2 * (cin + base))
+            add(ho * wo, 9 * base, base, 4 * base)
+            add(ho * wo, base, depth, 2 * (base + 2 * depth))
+            hh, ww, cin = ho, wo, depth
+    best, best_b = None, lo
+    for B in range(lo, hi + 1):
+        t = 0.0
+        for px, rows, nb, wgt in layers:
+            tiles = -(-(px * B) // rows) * nb
+            waves = -(-tiles // num_sms)
+            t += wgt * waves * num_sms / tiles
+        t /= B ** 0.0  # weights are per frame already
+        if best is None or t < best - 1e-12:
+            best, best_b = t, B
+    return best_b
+
+
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
