@@ -24,7 +24,7 @@ def output_dims(H, W):
     return (a.value, b.value), (c.value, d.value)
 
 
-def suggest_batch(H, W, lo=24, hi=64, num_sms=148):
+def suggest_batch(H, W, lo=24, hi=48, num_sms=148):
     """Frames per batch that minimise wave quantisation of the persistent conv-GEMM grid (one CTA per SM).
 
     Every GEMM layer runs ceil(B*pixels/tile_rows) * n_blocks tiles on `num_sms` CTAs; a batch size for which the
