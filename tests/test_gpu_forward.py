@@ -110,6 +110,36 @@ def test_baseline_config_shapes(cfg):
     eng.close()
 
 
+def test_real_demo_frame():
+    """BASELINE configs[0]: a labelled frame of the bundled Reaching-Mackenzie demo project (5 bodyparts, skeleton
+    Hand-Finger1 / Joystick1-Joystick2, data/.../config.yaml:6-31) through the whole path vs the oracle."""
+    import os
+    from PIL import Image
+    from deepgraphpose_b200.engine import Engine
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "demo_frame_img119.png")
+    frame = np.ascontiguousarray(np.asarray(Image.open(path).convert("RGB")))[None]
+    nj = 5
+    W = synthetic.make_weights(nj, seed=0)
+    Wt = {k: torch.from_numpy(v) for k, v in W.items()}
+    with torch.no_grad():
+        net = pose_net.extract_features(torch.from_numpy(frame.astype(np.float32)), Wt)
+        pred = pose_net.prediction_layer(net, Wt, "part_pred")
+    eng = Engine(nj)
+    eng.load_weights(W)
+    logits, locref = eng.forward(torch.from_numpy(frame).cuda())
+    assert logits.shape == pred.shape
+    assert (logits.cpu() - pred).abs().max().item() / pred.abs().max().item() < LOGIT_REL_TOL
+    out = eng.softargmax(logits, locref)
+    mu_ref, _ = dgp_ops.argmax_2d_from_cm(logits.cpu(), nj, 1.0, 1.0)
+    assert (out["mu"].cpu() - mu_ref).abs().max().item() < 1e-3
+    _, pk, lk = dgp_ops.estimate_pose_readout(out["mu"].cpu().numpy(), logits.cpu().numpy())
+    assert (pk == out["peak"][0].cpu().numpy()).all()
+    pot = eng.potentials(out["mu"], [(0, 1), (3, 4)])
+    d_ref = dgp_ops.skeleton_distances(out["mu"].cpu(), dgp_ops.skeleton_matrix([(0, 1), (3, 4)], nj))
+    assert (pot["skel"].cpu() - d_ref).abs().max().item() < 1e-3
+    eng.close()
+
+
 def test_batch_invariance(setup):
     """A frame's outputs do not depend on the batch it is processed in (needed for bit-exact frame sharding)."""
     eng, W, Wt, nj = setup
