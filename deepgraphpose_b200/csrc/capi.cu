@@ -867,10 +867,12 @@ int dgp_softmax_map(dgp_handle* h, const float* logits_dev, int B, int H, int W,
   return DGP_OK;
 }
 
-int dgp_loss_forward(dgp_handle* h, const dgp_loss_cfg* cfg, const dgp_loss_batch* b, float* losses_dev,
-                     float* targets_all_dev, void* stream) {
+static int run_loss(dgp_handle* h, const dgp_loss_cfg* cfg, const dgp_loss_batch* b, float* losses_dev,
+                    float* targets_all_dev, float* grad_pred_dev, float* grad_locref_dev, int visible_only, void* stream) {
   if (!h) return DGP_ERR_INVALID;
   if (!cfg || !b || !losses_dev || !b->pred_dev) return fail(h, DGP_ERR_INVALID, "dgp_loss_forward: null argument");
+  if (grad_pred_dev && cfg->wt > 0.0f)
+    return fail(h, DGP_ERR_UNSUPPORTED, "dgp_loss_backward: the temporal clique (wt > 0) has no backward yet");
   const int nj = h->cfg.num_joints;
   if (b->nt < 1 || b->nbv < 0 || b->nbh < 0 || b->nbv + b->nbh > b->nt * nj)
     return fail(h, DGP_ERR_INVALID, "dgp_loss_forward: bad marker counts");
@@ -886,18 +888,33 @@ int dgp_loss_forward(dgp_handle* h, const dgp_loss_cfg* cfg, const dgp_loss_batc
     return fail(h, DGP_ERR_INVALID, "dgp_loss_forward: skeleton without ws/ws_max");
   CU_OK(h, cudaSetDevice(h->device));
   const int nm = b->nt * nj;
-  const size_t need = (size_t)nm * 2 * 4 * 2 + (size_t)(b->nbv + b->nbh + 1) * 16 + (size_t)nm * 4 + 256;
+  const size_t need = (size_t)nm * 2 * 4 * 3 + (size_t)(b->nbv + b->nbh + 1) * 16 + (size_t)nm * 4 + 256;
   int rc = ensure(h, &h->loss_ws, need);
   if (rc) return rc;
   char* w = (char*)h->loss_ws.p;
   float* mu = (float*)w; w += (size_t)nm * 2 * 4;
   float* all = (float*)w; w += (size_t)nm * 2 * 4;
+  float* norm = (float*)w; w += (size_t)nm * 2 * 4;
   w = (char*)(((uintptr_t)w + 15) & ~(uintptr_t)15);
   float4* partials = (float4*)w; w += (size_t)(b->nbv + b->nbh + 1) * 16;
   float* meanflow = (float*)w;
-  rc = dgp_softargmax(h, b->pred_dev, nullptr, b->nt, b->H, b->W, nj, cfg->gamma, cfg->gauss_len, mu, nullptr, nullptr,
-                      nullptr, nullptr, stream);
-  if (rc) return rc;
+  if ((b->H & 1) || (b->W & 1) || cfg->gauss_len < 1.0f || cfg->gauss_len >= 5.0f || !(cfg->gamma > 0.0f))
+    return fail(h, DGP_ERR_INVALID, "dgp_loss: scoremap dims must be even, gauss_len in [1,5), gamma > 0");
+  {
+    const int splits = softargmax_splits(b->nt, b->H, h->num_sms);
+    const size_t sa_need = (size_t)b->nt * splits * nj * sizeof(SaPartial);
+    if (sa_need > h->sa_ws_bytes) {
+      if (h->sa_ws) CU_OK(h, cudaFree(h->sa_ws));
+      h->sa_ws = nullptr;
+      h->sa_ws_bytes = 0;
+      CU_OK(h, cudaMalloc(&h->sa_ws, sa_need));
+      h->sa_ws_bytes = sa_need;
+    }
+    CU_OK(h, launch_softargmax(b->pred_dev, nullptr, b->nt, b->H, b->W, nj, cfg->gamma, cfg->gauss_len, h->cfg.stride,
+                               h->cfg.locref_stdev, h->sa_ws, splits, mu, nullptr, nullptr, nullptr, nullptr, norm,
+                               (cudaStream_t)stream));
+    h->launches += 2;
+  }
   LossArgs a;
   a.pred = b->pred_dev; a.locref = b->locref_dev; a.mu = mu;
   a.nt = b->nt; a.H = b->H; a.W = b->W; a.nj = nj;
@@ -916,7 +933,23 @@ int dgp_loss_forward(dgp_handle* h, const dgp_loss_cfg* cfg, const dgp_loss_batc
   h->launches += 4;
   if (targets_all_dev)
     CU_OK(h, cudaMemcpyAsync(targets_all_dev, all, (size_t)nm * 2 * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  if (grad_pred_dev) {
+    CU_OK(h, launch_dgp_loss_backward(a, norm, cfg->gamma, cfg->gauss_len, visible_only, grad_pred_dev, grad_locref_dev,
+                                      (cudaStream_t)stream));
+    h->launches += 1;
+  }
   return DGP_OK;
+}
+
+int dgp_loss_forward(dgp_handle* h, const dgp_loss_cfg* cfg, const dgp_loss_batch* b, float* losses_dev,
+                     float* targets_all_dev, void* stream) {
+  return run_loss(h, cfg, b, losses_dev, targets_all_dev, nullptr, nullptr, 0, stream);
+}
+
+int dgp_loss_backward(dgp_handle* h, const dgp_loss_cfg* cfg, const dgp_loss_batch* b, float* losses_dev,
+                      float* grad_pred_dev, float* grad_locref_dev, int visible_only, void* stream) {
+  if (h && !grad_pred_dev) return fail(h, DGP_ERR_INVALID, "dgp_loss_backward: grad_pred_dev is required");
+  return run_loss(h, cfg, b, losses_dev, nullptr, grad_pred_dev, grad_locref_dev, visible_only, stream);
 }
 
 int dgp_sigmoid(dgp_handle* h, const float* logits_dev, float* prob_dev, size_t n, void* stream) {

@@ -53,5 +53,8 @@ struct LossArgs {
   float* out;           // [6]
 };
 cudaError_t launch_dgp_loss(const LossArgs& a, cudaStream_t stream);
+// Gradients of total_loss (or total_loss_visible) w.r.t. pred / locref; needs launch_dgp_loss's partials + all_markers.
+cudaError_t launch_dgp_loss_backward(const LossArgs& a, const float* norm, float gamma, float gauss_len, int visible_only,
+                                     float* g_pred, float* g_locref, cudaStream_t stream);
 
 }  // namespace dgp

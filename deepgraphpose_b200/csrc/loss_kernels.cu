@@ -228,6 +228,203 @@ __global__ void loss_finalize_kernel(const float4* __restrict__ part, int nbv, i
   out[0] = visible_loss; out[1] = hidden_loss; out[2] = locref_loss; out[3] = ws_loss; out[4] = wt_loss; out[5] = total;
 }
 
+
+// ------------------------------------------------------------------------------------------------ backward
+__device__ void block_max_idx(float v, int idx, float* shv, int* shi, float& out_v, int& out_i) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) { shv[threadIdx.x >> 5] = v; shi[threadIdx.x >> 5] = idx; }
+  __syncthreads();
+  out_v = shv[0];
+  out_i = shi[0];
+  for (int i = 1; i < (int)(blockDim.x >> 5); ++i)
+    if (shv[i] > out_v || (shv[i] == out_v && shi[i] < out_i)) { out_v = shv[i]; out_i = shi[i]; }
+}
+
+__device__ __forceinline__ void blur_weights(int pos, int n, int radius, const float* kt, float& a, float& r) {
+  a = 0.0f;
+  r = 0.0f;
+  for (int d = -radius; d <= radius; ++d) {
+    const int dst = pos - d;
+    if (dst >= 0 && dst < n) { a += kt[d + radius]; r += kt[d + radius] * (float)dst; }
+  }
+}
+
+// d total_loss / d pred and d total_loss / d locref (wt == 0).  One CTA per listed marker, three passes over its plane:
+//   A  max of the Gaussian bump (value + pixel) and of sigmoid(x) (confidence c + its pixel)
+//   B  the marker-level sums that multiply dc and d mu
+//   C  per-pixel gradient = direct term + (pixel == argmax) * confidence term + soft-argmax backward of dL/dmu
+// Gradients flow through the labels of the cross entropy, the confidence max and the loss weights exactly as TF's
+// graph does (no stop_gradient anywhere in fitdgp.py:947-1128).
+__global__ void __launch_bounds__(kLossThreads) marker_loss_bwd_kernel(
+    const float* __restrict__ pred, const float* __restrict__ locref, const float* __restrict__ locref_map,
+    const float* __restrict__ locref_mask, const float* __restrict__ all, const float* __restrict__ mu,
+    const float* __restrict__ norm, const int* __restrict__ visible, int nbv, const int* __restrict__ hidden, int nbh,
+    const float4* __restrict__ part, int nt, int H, int W, int nj, float inv2l2, int gm2, int gm3, float gamma, int radius,
+    float sigma, const int* __restrict__ edges, int nl, const float* __restrict__ ws, const float* __restrict__ ws_max,
+    float stride, float n_vis_total, float n_hid_total, float wn_visible, float wn_hidden, float locref_weight,
+    int visible_only, float* __restrict__ g_pred, float* __restrict__ g_locref) {
+  __shared__ float shf[kLossThreads / 32];
+  __shared__ int shi[kLossThreads / 32];
+  __shared__ float s_cnt[3];
+  const bool is_vis = (int)blockIdx.x < nbv;
+  const int m = is_vis ? visible[blockIdx.x] : hidden[blockIdx.x - nbv];
+  const int t = m / nj, j = m - t * nj;
+  const int HW = H * W;
+  const float* x0 = pred + (size_t)t * HW * nj + j;
+  float* g0 = g_pred + (size_t)t * HW * nj + j;
+  const float fnbv = nbv > 0 ? (float)nbv : (float)nbh;
+
+  // global normalisers from the forward partials (fixed order)
+  if (threadIdx.x == 0) {
+    float cv = 0.0f, ch = 0.0f, mc = 0.0f;
+    for (int i = 0; i < nbv; ++i) { cv += part[i].y; mc += part[i].w; }
+    for (int i = nbv; i < nbv + nbh; ++i) ch += part[i].y;
+    s_cnt[0] = cv; s_cnt[1] = ch; s_cnt[2] = mc;
+  }
+  __syncthreads();
+  const float cnt_v = s_cnt[0], cnt_h = s_cnt[1], mcnt = s_cnt[2];
+  const float tr = all[2 * m], tc = all[2 * m + 1];   // Gaussian target centre (label or soft-argmax)
+
+  // ---- pass A
+  float gm = -1.0f, cm = -CUDART_INF_F;
+  int gi = 0x7fffffff, ci = 0x7fffffff;
+  for (int p = threadIdx.x; p < HW; p += blockDim.x) {
+    const int r = p / W, c = p - r * W;
+    const float dr = (float)r - tr, dc = (float)c - tc;
+    const float g = expf(-(dr * dr + dc * dc) * inv2l2);
+    if (g > gm) { gm = g; gi = p; }
+    if (!is_vis && gm2 != 0) {
+      const float sg = sigmoidf_(x0[(size_t)p * nj]);
+      if (sg > cm) { cm = sg; ci = p; }
+    }
+  }
+  float gmax; int pg;
+  block_max_idx(gm, gi, shf, shi, gmax, pg);
+  const float gm5 = gmax + 1e-5f;
+  float conf = 1.0f; int pstar = -1;
+  if (!is_vis && gm2 != 0) block_max_idx(cm, ci, shf, shi, conf, pstar);
+
+  if (is_vis) {
+    const float kv = cnt_v > 0.0f ? 1.0f / cnt_v : 0.0f;
+    for (int p = threadIdx.x; p < HW; p += blockDim.x) {
+      const int r = p / W, c = p - r * W;
+      const float dr = (float)r - tr, dc = (float)c - tc;
+      const float tg = expf(-(dr * dr + dc * dc) * inv2l2) / gm5;
+      g0[(size_t)p * nj] = kv * (sigmoidf_(x0[(size_t)p * nj]) - tg);
+    }
+    if (locref != nullptr && g_locref != nullptr) {
+      const float kl = mcnt > 0.0f ? locref_weight / mcnt : 0.0f;
+      const size_t base = (size_t)t * HW * 2 * nj + 2 * j;
+      for (int p = threadIdx.x; p < 2 * HW; p += blockDim.x) {
+        const size_t o = base + (size_t)(p >> 1) * 2 * nj + (p & 1);
+        const float d = locref[o] - locref_map[o];
+        g_locref[o] = kl * locref_mask[o] * (fabsf(d) < 1.0f ? d : (d > 0.0f ? 1.0f : -1.0f));
+      }
+    }
+    return;
+  }
+  if (visible_only) {  // fit_dgp_labeledonly optimises total_loss_visible (fitdgp.py:416): hidden markers get no gradient
+    for (int p = threadIdx.x; p < HW; p += blockDim.x) g0[(size_t)p * nj] = 0.0f;
+    return;
+  }
+
+  // ---- hidden marker
+  const bool scaled = gm3 == 3;                 // confidence-scaled logits + (1 - c) weights
+  const float cs = gm2 == 1 ? conf : 1.0f;      // target scale
+  const float w = scaled ? 1.0f - conf : 1.0f;
+  const float khid = cnt_h > 0.0f ? (n_vis_total / n_hid_total * (float)nbh / fnbv * wn_hidden / wn_visible) / cnt_h : 0.0f;
+  const float l2inv = 2.0f * inv2l2;            // 1 / lengthscale^2
+  // pass B
+  float S = 0.0f, Cc = 0.0f, Ur = 0.0f, Uc = 0.0f, V = 0.0f;
+  for (int p = threadIdx.x; p < HW; p += blockDim.x) {
+    const int r = p / W, c = p - r * W;
+    const float dr = (float)r - tr, dc = (float)c - tc;
+    const float G = expf(-(dr * dr + dc * dc) * inv2l2);
+    const float tg = G / gm5;
+    const float x = x0[(size_t)p * nj];
+    const float sg = sigmoidf_(x);
+    float xl = x, D = 0.0f;
+    if (scaled) {
+      const float ps = sg * conf;
+      xl = -logf(1.0f - ps + 1e-20f) + logf(ps + 1e-20f);
+      D = 1.0f / (1.0f - ps + 1e-20f) + 1.0f / (ps + 1e-20f);
+    }
+    const float z = tg * cs;
+    S += bce(z, xl);
+    Cc += (gm2 == 1 ? -xl * tg : 0.0f) + (scaled ? (sigmoidf_(xl) - z) * D * sg : 0.0f);
+    Ur += -xl * G * dr;   // d G / d mu_r = G * (r - mu_r) / l^2
+    Uc += -xl * G * dc;
+    V += -xl * G;
+  }
+  S = block_sum(S, shf); Cc = block_sum(Cc, shf); Ur = block_sum(Ur, shf); Uc = block_sum(Uc, shf); V = block_sum(V, shf);
+  const float coef_c = (scaled ? -S : 0.0f) + w * Cc;       // multiplies dc = sigma'(x[p*]) dx[p*]
+  const int rg = pg / W, cg = pg - rg * W;
+  // d L_m / d mu through the Gaussian target (incl. its max normaliser)
+  float Lr = w * cs * (Ur * l2inv / gm5 - V * gmax * ((float)rg - tr) * l2inv / (gm5 * gm5));
+  float Lc = w * cs * (Uc * l2inv / gm5 - V * gmax * ((float)cg - tc) * l2inv / (gm5 * gm5));
+  Lr *= khid; Lc *= khid;
+  // + spatial clique: d ws_loss / d mu of this (hidden) marker
+  if (nl > 0) {
+    const float kws = 1.0f / (float)H / (float)W * n_vis_total / fnbv / (n_vis_total + n_hid_total) / wn_visible;
+    const float* mf = all + (size_t)t * nj * 2;
+    for (int l = 0; l < nl; ++l) {
+      const int a = edges[2 * l], b = edges[2 * l + 1];
+      if (a != j && b != j) continue;
+      const float er = (mf[2 * a] * stride + 0.5f * stride) - (mf[2 * b] * stride + 0.5f * stride);
+      const float ec = (mf[2 * a + 1] * stride + 0.5f * stride) - (mf[2 * b + 1] * stride + 0.5f * stride);
+      const float d = sqrtf(er * er + ec * ec);
+      if (d > ws_max[l] && d > 0.0f) {
+        const float sgn = (a == j) ? 1.0f : -1.0f;
+        Lr += kws * ws[l] * sgn * stride * er / d;
+        Lc += kws * ws[l] * sgn * stride * ec / d;
+      }
+    }
+  }
+  // pass C
+  const float g2 = gamma * 1.4426950408889634f;
+  const float m2 = norm[2 * m], s0 = norm[2 * m + 1];
+  const float mur = mu[2 * m], muc = mu[2 * m + 1];
+  float knorm = 0.0f;
+  for (int d = -radius; d <= radius; ++d) knorm += expf(-0.5f * (d / sigma) * (d / sigma));
+  float kt[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    const float d = (float)(i - radius);
+    kt[i] = i <= 2 * radius ? expf(-0.5f * (d / sigma) * (d / sigma)) / knorm : 0.0f;
+  }
+  for (int p = threadIdx.x; p < HW; p += blockDim.x) {
+    const int r = p / W, c = p - r * W;
+    const float dr = (float)r - tr, dc = (float)c - tc;
+    const float tg = expf(-(dr * dr + dc * dc) * inv2l2) / gm5;
+    const float x = x0[(size_t)p * nj];
+    const float sg = sigmoidf_(x);
+    float direct;
+    if (scaled) {
+      const float ps = sg * conf;
+      const float xl = -logf(1.0f - ps + 1e-20f) + logf(ps + 1e-20f);
+      const float D = 1.0f / (1.0f - ps + 1e-20f) + 1.0f / (ps + 1e-20f);
+      direct = w * (sigmoidf_(xl) - tg * cs) * D * sg * (1.0f - sg) * conf;
+    } else {
+      direct = w * (sg - tg * cs);
+    }
+    float g = khid * direct;
+    if (p == pstar) g += khid * coef_c * sg * (1.0f - sg);
+    // soft-argmax backward: mu = (sum e * R) / (sum e * A) with border-aware blur weights
+    float ah = 1.0f, rh = (float)r, aw = 1.0f, rw = (float)c;
+    if (r < radius || r >= H - radius) blur_weights(r, H, radius, kt, ah, rh);
+    if (c < radius || c >= W - radius) blur_weights(c, W, radius, kt, aw, rw);
+    const float e = exp2f(fmaf(x, g2, -m2));
+    g += gamma * e / s0 * ((rh * aw - mur * ah * aw) * Lr + (ah * rw - muc * ah * aw) * Lc);
+    g0[(size_t)p * nj] = g;
+  }
+}
+
 }  // namespace
 
 cudaError_t launch_dgp_loss(const LossArgs& a, cudaStream_t stream) {
@@ -251,6 +448,24 @@ cudaError_t launch_dgp_loss(const LossArgs& a, cudaStream_t stream) {
                                              a.ws, a.ws_max, temporal ? a.meanflow : nullptr, a.wt_batch, a.wt, a.wt_max,
                                              a.stride, a.n_vis_total, a.n_hid_total, a.wn_visible, a.wn_hidden,
                                              a.locref_weight, a.out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_dgp_loss_backward(const LossArgs& a, const float* norm, float gamma, float gauss_len, int visible_only,
+                                     float* g_pred, float* g_locref, cudaStream_t stream) {
+  const int nb = a.nbv + a.nbh;
+  cudaError_t e = cudaMemsetAsync(g_pred, 0, (size_t)a.nt * a.H * a.W * a.nj * sizeof(float), stream);
+  if (e != cudaSuccess) return e;
+  if (g_locref) {
+    e = cudaMemsetAsync(g_locref, 0, (size_t)a.nt * a.H * a.W * 2 * a.nj * sizeof(float), stream);
+    if (e != cudaSuccess) return e;
+  }
+  if (nb > 0)
+    marker_loss_bwd_kernel<<<nb, kLossThreads, 0, stream>>>(
+        a.pred, a.locref, a.locref_map, a.locref_mask, a.all_markers, a.mu, norm, a.visible, a.nbv, a.hidden, a.nbh,
+        a.partials, a.nt, a.H, a.W, a.nj, 1.0f / (2.0f * a.lengthscale * a.lengthscale), a.gm2, a.gm3, gamma,
+        (int)gauss_len, gauss_len, a.edges, a.nl, a.ws, a.ws_max, a.stride, a.n_vis_total, a.n_hid_total, a.wn_visible,
+        a.wn_hidden, a.locref_weight, visible_only, g_pred, g_locref);
   return cudaGetLastError();
 }
 

@@ -62,8 +62,10 @@ def spatial_clique_params(joint_locs, S0, stride, ws, ws_max):
     return out_ws.astype(np.float32), out_max.astype(np.float32)
 
 
-def loss_forward(engine, pred, locref, feed, cfg, edges, ws, ws_max, n_frames_total, n_visible_frames_total):
-    """One call into dgp_loss_forward.  pred/locref: CUDA tensors from Engine.forward; feed: reference feed_dict values."""
+def loss_forward(engine, pred, locref, feed, cfg, edges, ws, ws_max, n_frames_total, n_visible_frames_total,
+                 backward=False, visible_only=False):
+    """One call into dgp_loss_forward (or dgp_loss_backward).  pred/locref: CUDA tensors from Engine.forward; feed:
+    reference feed_dict values.  With backward=True returns (losses, (grad_pred, grad_locref))."""
     dev = pred.device
     nt, H, W, nj = pred.shape
     f32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32), device=dev)
@@ -96,6 +98,14 @@ def loss_forward(engine, pred, locref, feed, cfg, edges, ws, ws_max, n_frames_to
                         float(_get(cfg, "locref_loss_weight", 0.05)), float(n_frames_total), float(n_visible_frames_total),
                         int(_get(cfg, "gm2", 1)), int(_get(cfg, "gm3", 3)))
     out = torch.empty(6, dtype=torch.float32, device=dev)
+    if backward:
+        g_pred = torch.empty_like(pred)
+        g_loc = torch.empty_like(locref) if locref is not None else None
+        engine._check(engine.lib.dgp_loss_backward(engine.h, C.byref(c), C.byref(b), _ptr(out), _ptr(g_pred), _ptr(g_loc),
+                                                   int(visible_only), _stream(dev)))
+        vals = out.cpu().numpy()
+        del keep
+        return dict(zip(LOSS_KEYS, [np.float32(v) for v in vals])), (g_pred, g_loc)
     all_markers = torch.empty((nt * nj, 2), dtype=torch.float32, device=dev)
     engine._check(engine.lib.dgp_loss_forward(engine.h, C.byref(c), C.byref(b), _ptr(out), _ptr(all_markers), _stream(dev)))
     vals = out.cpu().numpy()

@@ -141,6 +141,15 @@ typedef struct dgp_loss_batch {
 int dgp_loss_forward(dgp_handle* h, const dgp_loss_cfg* cfg, const dgp_loss_batch* batch, float* losses_dev,
                      float* targets_all_dev, void* stream);
 
+/* Forward + the loss-side half of the backward pass of fit_dgp's train_op (fitdgp.py:706-713 differentiates total_loss;
+ * fit_dgp_labeledonly differentiates total_loss_visible, fitdgp.py:416 -> visible_only = 1): gradients of the loss
+ * w.r.t. the head outputs, float32 (nt,H,W,nj) and (nt,H,W,2nj) (grad_locref_dev may be NULL).  They flow through the
+ * cross-entropy labels (Gaussian targets -> soft-argmax), the confidence max and the (1 - c) weights exactly as in the
+ * TF graph.  wt > 0 (temporal clique) is DGP_ERR_UNSUPPORTED here.  The network backward (dgrad / wgrad of the 53
+ * convs) and the Momentum step are not implemented yet. */
+int dgp_loss_backward(dgp_handle* h, const dgp_loss_cfg* cfg, const dgp_loss_batch* batch, float* losses_dev,
+                      float* grad_pred_dev, float* grad_locref_dev, int visible_only, void* stream);
+
 /* Replaces the estimate_pose frame loop (eval.py:306-345) end to end with HOST buffers: per batch of `batch`
  * frames H2D copy, dgp_forward, dgp_softargmax, D2H of the results.  frames_host uint8 (T,H,W,3) (pinned memory
  * gives asynchronous copies); mu_host float32 (T,nj,2); peak_host int32 (T,nj,2); lik_host float32 (T,nj). */

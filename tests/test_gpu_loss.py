@@ -65,6 +65,37 @@ def test_loss_forward_matches_oracle(case):
     eng.close()
 
 
+@pytest.mark.parametrize("case", [dict(gm2=1, gm3=3), dict(gm2=2, gm3=3), dict(gm2=0, gm3=0), dict(gm2=1, gm3=0),
+                                  dict(gm2=1, gm3=3, visible_only=True)])
+def test_loss_backward_matches_oracle_autograd(case):
+    """d total_loss / d pred and d locref from dgp_loss_backward vs torch autograd through the oracle graph (gradients
+    flow through the Gaussian targets into the soft-argmax, through the confidence max and the (1-c) weights)."""
+    from deepgraphpose_b200 import fitdgp
+    from deepgraphpose_b200.engine import Engine
+    rng = np.random.default_rng(23)
+    nt, H, W, nj = 4, 16, 20, 4
+    labels, batch = make_batch(rng, nt, H, W, nj, [0, 2], ((0, 1),))
+    pred = torch.from_numpy((rng.standard_normal((nt, H, W, nj)) * 2).astype(np.float32)).requires_grad_(True)
+    loc = torch.from_numpy(rng.standard_normal((nt, H, W, 2 * nj)).astype(np.float32)).requires_grad_(True)
+    edges = synthetic.chain_skeleton(nj)
+    S0 = dgp_ops.skeleton_matrix(edges, nj)
+    cfg = oracle_loss.default_dgp_cfg(gm2=case["gm2"], gm3=case["gm3"], wt=0.0)
+    ws, ws_max = oracle_loss.spatial_clique_params(labels, S0, cfg)
+    ws_max = ws_max * 0.3   # make the skeleton hinge active for some limbs so its gradient is exercised
+    ref, ref_total, ref_vis = oracle_loss.dgp_loss_from_heads(pred, loc, batch, cfg, S0, ws, ws_max, 200, 20)
+    vis_only = case.get("visible_only", False)
+    (ref_vis if vis_only else ref_total).backward()
+    eng = Engine(nj)
+    got, (g_pred, g_loc) = fitdgp.loss_forward(eng, pred.detach().cuda(), loc.detach().cuda(), batch, cfg, edges, ws, ws_max,
+                                               200, 20, backward=True, visible_only=vis_only)
+    assert abs(float(got["total_loss"]) - float(ref_total)) <= LOSS_REL_TOL * abs(float(ref_total))
+    gp, gl = pred.grad, loc.grad
+    assert (g_pred.cpu() - gp).abs().max().item() <= 2e-3 * gp.abs().max().item() + 1e-9, \
+        ((g_pred.cpu() - gp).abs().max().item(), gp.abs().max().item())
+    assert (g_loc.cpu() - gl).abs().max().item() <= 1e-4 * gl.abs().max().item() + 1e-12
+    eng.close()
+
+
 def test_loss_rejects_bad_flags():
     from deepgraphpose_b200 import fitdgp
     from deepgraphpose_b200._lib import DgpError
