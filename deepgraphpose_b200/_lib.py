@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdgp_b200.so")
+LIB_PATH = os.environ.get("DGP_B200_LIB") or os.path.join(_HERE, "libdgp_b200.so")  # env: alternate build
 
 DGP_OK = 0
 STATUS_NAMES = {0: "DGP_OK", -1: "DGP_ERR_INVALID", -2: "DGP_ERR_CUDA", -3: "DGP_ERR_UNSUPPORTED",

@@ -826,7 +826,7 @@ int dgp_softargmax(dgp_handle* h, const float* logits_dev, const float* locref_d
   if (!(gamma > 0.0f)) return fail(h, DGP_ERR_INVALID, "dgp_softargmax: gamma must be > 0");
   if (((uintptr_t)logits_dev & 15) != 0) return fail(h, DGP_ERR_INVALID, "dgp_softargmax: logits must be 16-byte aligned");
   CU_OK(h, cudaSetDevice(h->device));
-  const int splits = softargmax_splits(B, H, h->num_sms);
+  const int splits = softargmax_splits(H, W, nj);
   const size_t need = (size_t)B * splits * nj * sizeof(SaPartial);
   if (need > h->sa_ws_bytes) {
     if (h->sa_ws) CU_OK(h, cudaFree(h->sa_ws));
@@ -850,7 +850,7 @@ int dgp_softmax_map(dgp_handle* h, const float* logits_dev, int B, int H, int W,
   if (!logits_dev || !map_dev || B < 0 || nj < 1 || (H & 1) || (W & 1) || gauss_len < 1.0f || gauss_len >= 5.0f)
     return fail(h, DGP_ERR_INVALID, "dgp_softmax_map: bad argument");
   CU_OK(h, cudaSetDevice(h->device));
-  const int splits = softargmax_splits(B, H, h->num_sms);
+  const int splits = softargmax_splits(H, W, nj);
   const size_t need = (size_t)B * splits * nj * sizeof(SaPartial) + (size_t)B * nj * 2 * sizeof(float);
   if (need > h->sa_ws_bytes) {
     if (h->sa_ws) CU_OK(h, cudaFree(h->sa_ws));
@@ -901,7 +901,7 @@ static int run_loss(dgp_handle* h, const dgp_loss_cfg* cfg, const dgp_loss_batch
   if ((b->H & 1) || (b->W & 1) || cfg->gauss_len < 1.0f || cfg->gauss_len >= 5.0f || !(cfg->gamma > 0.0f))
     return fail(h, DGP_ERR_INVALID, "dgp_loss: scoremap dims must be even, gauss_len in [1,5), gamma > 0");
   {
-    const int splits = softargmax_splits(b->nt, b->H, h->num_sms);
+    const int splits = softargmax_splits(b->H, b->W, nj);
     const size_t sa_need = (size_t)b->nt * splits * nj * sizeof(SaPartial);
     if (sa_need > h->sa_ws_bytes) {
       if (h->sa_ws) CU_OK(h, cudaFree(h->sa_ws));

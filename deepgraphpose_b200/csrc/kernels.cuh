@@ -13,7 +13,7 @@ struct SaPartial {  // per (frame, row-split, joint) partial of the online softm
 };
 
 int softargmax_tact(int nj);
-int softargmax_splits(int B, int H, int num_sms);
+int softargmax_splits(int H, int W, int nj);  // segments per frame (workspace = B * splits * nj SaPartial)
 cudaError_t launch_softargmax(const float* logits, const float* locref, int B, int H, int W, int nj, float gamma,
                               float gauss_len, float stride, float locref_stdev, SaPartial* workspace, int splits,
                               float* mu, int* peak, float* lik, int* dlc_peak, float* dlc_pose, float* norm,

@@ -35,10 +35,12 @@ def main():
     for (B, H, W, nj, tag) in [(4096, 94, 104, 4, "configs[1] scoremaps, 4096 frames"), (1024, 128, 160, 16, "configs[2] scoremaps, 1024 frames"),
                                (2048, 60, 80, 20, "configs[4] scoremaps, 2048 frames")]:
         x = torch.randn(B, H, W, nj, device="cuda") * 3
-        ms = timeit(lambda: eng.softargmax(x, None, 1.0, 1.0, want=("mu", "peak", "lik", "dlc_peak", "dlc_pose")))
         gb = x.numel() * 4 / 1e9
-        out.append({"kernel": "softargmax (partial+finalize)", "workload": tag, "bytes": x.numel() * 4, "ms": ms,
-                    "achieved_gbs": gb / (ms / 1e3), "peak_gbs": hbm, "frac": gb / (ms / 1e3) / hbm})
+        for wants, name in ((("mu", "peak", "lik"), "softargmax, estimate_pose read-out (mu, peak, lik)"),
+                            (("mu", "peak", "lik", "dlc_peak", "dlc_pose"), "softargmax + DLC global peak")):
+            ms = timeit(lambda: eng.softargmax(x, None, 1.0, 1.0, want=wants))
+            out.append({"kernel": name, "workload": tag, "bytes": x.numel() * 4, "ms": ms,
+                        "achieved_gbs": gb / (ms / 1e3), "peak_gbs": hbm, "frac": gb / (ms / 1e3) / hbm})
         del x
     T, nj = 4_000_000, 16
     mu = torch.rand(T, nj, 2, device="cuda") * 100
