@@ -101,33 +101,26 @@ __device__ __forceinline__ int enc_ordered(float x) {
 __device__ __forceinline__ float dec_ordered(int b) { return __int_as_float(b >= 0 ? b : b ^ 0x7fffffff); }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Streaming soft-argmax partials.  Persistent CTAs (one per SM); the logit maps are pulled through a 4-stage ring of
-// 40 KB shared-memory buffers with 1-D bulk async copies (cp.async.bulk + mbarrier complete_tx), so every byte crosses
-// HBM -> SM exactly once and ~160 KB per SM are in flight independent of what the math warps are doing.
-//   warp 12      : producer (one elected lane): waits empty[s], issues the bulk copy of the next chunk
-//   warps 8..11  : scouts: per-joint max of a landed chunk (shared-memory atomicMax on order-preserving ints) -> ready[s]
-//   warps 0..7   : math: one pass over the chunk against the running max (FFMA + EX2 + 3 accumulates per element,
-//                  log2 domain), DLC peak candidates (x >= min(max-2, 14)), then the blur border correction for the
-//                  few pixels within `radius` of an edge, all from shared memory; arrive on empty[s]
-// A job is one SEGMENT (<= kSegChunks chunks) of one frame; the segmentation depends only on (H, W, nj), so a frame's
-// arithmetic and its merge order never depend on the batch size or the grid (bit-exact batch invariance).
-// `tact` math threads are active with 4*tact % nj == 0: every thread's four float4 lanes keep a fixed joint.
-// kSamePixel: nj % 4 == 0, the four lanes of a float4 belong to ONE pixel.  kDlc: track the DLC global sigmoid peak.
-#ifndef DGP_SA_MAIN
-#define DGP_SA_MAIN 512
-#endif
-constexpr int kStMain = DGP_SA_MAIN;       // math threads
-constexpr int kStScout = 128;
-constexpr int kStThreads = kStMain + kStScout + 32;
-constexpr int kStStages = 4;
-constexpr int kStStageFloats = 10240;  // 40 KB
-constexpr int kSegChunks = 4;
+// Streaming soft-argmax partials.  Persistent CTAs (one per SM).  The logit maps are cut into 8 KB CHUNKS (a function
+// of (H, W, nj) only, so a frame's arithmetic never depends on the batch size or the grid: bit-exact batch invariance);
+// the CTA's contiguous chunk range goes through a 22-stage shared-memory ring filled by 1-D bulk async copies
+// (cp.async.bulk + mbarrier complete_tx): every byte crosses HBM -> SM exactly once and ~80 KB per SM are in flight no
+// matter what the math is doing.  Each of the 12 warps owns every 12th chunk and is fully autonomous -- no CTA-wide
+// barrier, no producer warp (the warp that drains a stage refills it):
+//   wait full[s] -> pass 1 (per-joint max, from shared memory) -> pass 2 (packed fp32x2: FFMA2 + EX2 + FADD2 + FFMA2 per
+//   element pair, log2 domain; blur border correction for pixels within `radius` of an edge; DLC peak candidates)
+//   -> release the stage -> warp-level reduction over the lanes that share a joint -> one partial per (chunk, joint).
+// Lane l reads float4s l, l + tw, ...; `tw` <= 32 lanes are active with 4*tw % nj == 0, so a lane's four float4 slots
+// keep a fixed joint.  kSamePixel: nj % 4 == 0, the four slots belong to ONE pixel.  kShfl: the lanes that share a
+// joint are an xor-closed set (nj in {4, 8, ..., 128}) and reduce with shuffles; otherwise through a per-warp scratch.
+constexpr int kWWarps = 12;
+constexpr int kWThreads = kWWarps * 32;
+constexpr int kWChunkFloats = 2048;  // 8 KB
+constexpr int kWStages = 22;
 constexpr int kMaxJoints = 128;
-constexpr int kRedFloats = 4 * kStMain * 5;
-constexpr int kRedbFloats = kStMain * 3;
-constexpr size_t kStSmemBytes = (size_t)kStStages * kStStageFloats * 4 + kRedFloats * 4 + kRedbFloats * 4 +
-                                3 * kStStages * kMaxJoints * 4 + kStStages * kMaxJoints * 4 + kMaxJoints * 4 + 64 * 4 +
-                                3 * kStStages * 8 + 128;
+constexpr int kWScratchFloats = 128 * 5 + kMaxJoints;   // per warp: [4*32][5] partial entries + [nj] results
+constexpr size_t kWSmemBytes = (size_t)kWStages * kWChunkFloats * 4 + (size_t)kWWarps * kWScratchFloats * 4 + 64 * 4 +
+                               kWStages * 8 + kWStages * 4 + 128;
 
 // blur border weights computed from scratch (degenerate maps no larger than the kernel, where every pixel is border)
 __device__ __noinline__ void border_weights_slow(int pos, int n, int radius, float sigma, float& a, float& r) {
@@ -146,147 +139,31 @@ __device__ __noinline__ void border_weights_slow(int pos, int n, int radius, flo
 }
 
 // exact sigmoid of one DLC peak candidate; out of line: the call is rare and the expf + divide would otherwise be
-// replicated 20x in the unrolled hot loop
+// replicated in the unrolled hot loop
 __device__ __noinline__ float dlc_sigmoid(float x) { return sigmoid_tf(x); }
 
-// Slices per joint of the job-end reduction (each becomes its own partial): all 16 math warps get work.
-__host__ __device__ __forceinline__ int reduce_slices(int nj) { return nj <= (kStMain / 32) ? (kStMain / 32) / nj : 1; }
-
-template <bool kSamePixel, bool kDlc>
-__global__ void __launch_bounds__(kStThreads, 1) softargmax_stream_kernel(
+template <bool kSamePixel, bool kShfl, bool kDlc>
+__global__ void __launch_bounds__(kWThreads, 1) softargmax_stream_kernel(
     const float* __restrict__ logits, int B, int H, int W, int nj, float gamma, int radius, float sigma, int chunk_px,
-    int nseg, int tact, int stact, SaPartial* __restrict__ part) {
+    int cpf, int tw, SaPartial* __restrict__ part) {
   extern __shared__ __align__(128) unsigned char st_smem[];
   float* stage = reinterpret_cast<float*>(st_smem);
-  float* red = stage + kStStages * kStStageFloats;      // [4*kStMain][5]: s0, sr, sc, bsig, bidx per lane
-  float* redb = red + kRedFloats;                       // [kStMain][3]: border corrections
-  float* pm2 = redb + kRedbFloats;                      // [stages][kMaxJoints]: running max * gamma * log2e after the chunk
-  float* pf = pm2 + kStStages * kMaxJoints;             // [stages][kMaxJoints]: rescale factor 2^(old - new) of the sums
-  float* pthr = pf + kStStages * kMaxJoints;            // [stages][kMaxJoints]: DLC candidate threshold
-  int* cmax = reinterpret_cast<int*>(pthr + kStStages * kMaxJoints);  // [stages][kMaxJoints]: chunk max, ordered ints
-  float* jm = reinterpret_cast<float*>(cmax + kStStages * kMaxJoints);  // [kMaxJoints]: final m of the job
-  float* btab = jm + kMaxJoints;                        // border weights: [4][16] (Ah, Rh, Aw, Rw) x 2*radius entries
+  float* scratch = stage + kWStages * kWChunkFloats;    // [kWWarps][kWScratchFloats]
+  float* btab = scratch + kWWarps * kWScratchFloats;    // border weights: [4][16] (Ah, Rh, Aw, Rw) x 2*radius entries
   uint64_t* full = reinterpret_cast<uint64_t*>(btab + 64);
-  uint64_t* ready = full + kStStages;
-  uint64_t* empty = ready + kStStages;
+  volatile int* issued = reinterpret_cast<volatile int*>(full + kWStages);   // loads issued into each stage so far
 
   const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const bool all_border = (W <= 2 * radius) || (H <= 2 * radius);
+  const int R2 = 2 * radius;
   if (tid == 0) {
-    for (int s = 0; s < kStStages; ++s) {
+    for (int s = 0; s < kWStages; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&ready[s], kStScout);
-      mbar_init(&empty[s], kStMain);
+      issued[s] = 0;
     }
     fence_mbar_init();
   }
-  __syncthreads();
-
-  const int HW = H * W;
-  const int seg_px = chunk_px * kSegChunks;
-  const int njobs = B * nseg;
-  const float g2 = gamma * 1.4426950408889634f;
-
-  if (tid >= kStMain + kStScout) {
-    // ------------------------------------------------------------------ producer
-    if (tid != kStMain + kStScout) return;
-    int it = 0;
-    for (int job = blockIdx.x; job < njobs; job += gridDim.x) {
-      const int b = job / nseg, seg = job - b * nseg;
-      const int p_beg = seg * seg_px, p_end = min(HW, p_beg + seg_px);
-      const float* frame = logits + (size_t)b * HW * nj;
-      for (int c0 = p_beg; c0 < p_end; c0 += chunk_px, ++it) {
-        const int c1 = min(c0 + chunk_px, p_end);
-        const int s = it % kStStages, use = it / kStStages;
-        if (use > 0) mbar_wait_backoff(&empty[s], (use - 1) & 1);
-        const uint32_t bytes = (uint32_t)(c1 - c0) * nj * 4u;
-        mbar_arrive_expect_tx(&full[s], bytes);
-        bulk_load_1d(stage + s * kStStageFloats, frame + (size_t)c0 * nj, bytes, &full[s]);
-      }
-    }
-    return;
-  }
-
-  if (tid >= kStMain) {
-    // ------------------------------------------------------------------ scouts
-    // Per chunk: per-joint max (float4 reads with a fixed joint per lane, REDUX across the lanes of a warp that share
-    // their joints, then shared-memory atomicMax on order-preserving ints); the first nj scouts then fold it into the
-    // job's running max and publish (m2, rescale factor, DLC threshold) for the math warps.
-    const int stid = tid - kStMain;
-    const int lane = stid & 31;
-    int P = nj;
-    for (int a = 4, bb = nj; bb;) { const int r = a % bb; a = bb; bb = r; P = nj / a; }
-    unsigned mask = 0;
-    if (32 % P == 0)
-      for (int l = lane % P; l < 32; l += P) mask |= 1u << l;
-    const bool full_warp = ((stid | 31) < stact);  // REDUX needs every lane of the mask to be active
-    int jq[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) jq[q] = (4 * stid + q) % nj;
-    int it = 0;
-    for (int job = blockIdx.x; job < njobs; job += gridDim.x) {
-      const int seg = job % nseg;
-      const int p_beg = seg * seg_px, p_end = min(HW, p_beg + seg_px);
-      float run_x = -CUDART_INF_F, run_m2 = -CUDART_INF_F;
-      for (int c0 = p_beg; c0 < p_end; c0 += chunk_px, ++it) {
-        const int n4 = (min(c0 + chunk_px, p_end) - c0) * nj / 4;
-        const int s = it % kStStages, ph = (it / kStStages) & 1;
-        // full[s] of this use implies empty[s] of the previous one: the math warps are done with stage s's tables
-        mbar_wait_backoff(&full[s], ph);
-        int* cm = cmax + s * kMaxJoints;
-        if (stid < nj) cm[stid] = enc_ordered(-CUDART_INF_F);
-        named_bar_sync(2, kStScout);
-        if (stid < stact) {
-          const float4* st4 = reinterpret_cast<const float4*>(stage + s * kStStageFloats);
-          float4 m = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
-          int f = stid;
-          for (; f + 3 * stact < n4; f += 4 * stact) {
-            const float4 v0 = st4[f], v1 = st4[f + stact], v2 = st4[f + 2 * stact], v3 = st4[f + 3 * stact];
-            m.x = fmaxf(fmaxf(m.x, v0.x), fmaxf(v1.x, fmaxf(v2.x, v3.x)));
-            m.y = fmaxf(fmaxf(m.y, v0.y), fmaxf(v1.y, fmaxf(v2.y, v3.y)));
-            m.z = fmaxf(fmaxf(m.z, v0.z), fmaxf(v1.z, fmaxf(v2.z, v3.z)));
-            m.w = fmaxf(fmaxf(m.w, v0.w), fmaxf(v1.w, fmaxf(v2.w, v3.w)));
-          }
-          for (; f < n4; f += stact) {
-            const float4 v = st4[f];
-            m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
-          }
-          int e[4] = {enc_ordered(m.x), enc_ordered(m.y), enc_ordered(m.z), enc_ordered(m.w)};
-          if (mask != 0 && full_warp) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) e[q] = __reduce_max_sync(mask, e[q]);
-            if (lane < P) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) atomicMax(&cm[jq[q]], e[q]);
-            }
-          } else {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) atomicMax(&cm[jq[q]], e[q]);
-          }
-        }
-        named_bar_sync(2, kStScout);
-        if (stid < nj) {
-          const float nx = fmaxf(run_x, dec_ordered(cm[stid]));
-          const float nm2 = nx * g2;
-          pm2[s * kMaxJoints + stid] = nm2;
-          pf[s * kMaxJoints + stid] = (nm2 == run_m2) ? 1.0f : ex2_approx(run_m2 - nm2);  // first chunk: 2^-inf = 0
-          if (kDlc) pthr[s * kMaxJoints + stid] = dlc_candidate_threshold(nx);
-          run_x = nx;
-          run_m2 = nm2;
-        }
-        mbar_arrive(&ready[s]);
-      }
-    }
-    return;
-  }
-
-  // -------------------------------------------------------------------- math warps
-  const int L = 4 * tact;
-  const bool lane_act = tid < tact;
-  const int Gb = kStMain / nj;                   // border-pass pixel classes per joint
-  const bool b_act = tid < Gb * nj;
-  const int jb = tid % nj, gb = tid / nj;
-  const bool all_border = (W <= 2 * radius) || (H <= 2 * radius);
-  const int R2 = 2 * radius;
   // border weight tables: entry i < radius is position i, entry i >= radius is position n - 2*radius + i
   if (tid < 2 * R2 && !all_border) {
     float knorm = 0.0f;
@@ -306,89 +183,180 @@ __global__ void __launch_bounds__(kStThreads, 1) softargmax_stream_kernel(
     btab[(2 * axis) * 16 + i] = a;
     btab[(2 * axis + 1) * 16 + i] = r;
   }
-  named_bar_sync(1, kStMain);
-  // border side-column walk: item k = gb + i*Gb -> (row offset k / R2, side index k % R2), kept incrementally
-  const int bq0 = R2 > 0 ? gb / R2 : 0, bs0 = R2 > 0 ? gb - bq0 * R2 : 0;
-  const int bdq = R2 > 0 ? Gb / R2 : 0, bds = R2 > 0 ? Gb - bdq * R2 : 0;
+  __syncthreads();
+
+  const int HW = H * W;
+  const long long nchunks = (long long)B * cpf;
+  const int g0 = (int)(nchunks * blockIdx.x / gridDim.x), g1 = (int)(nchunks * (blockIdx.x + 1) / gridDim.x);
+  const int nloc = g1 - g0;
+
+  // There is no producer warp and no "empty" barrier: the warp that finishes chunk i refills its stage with chunk
+  // i + kWStages right away (it knows the stage is free), so a slow warp never blocks the loads of the others.
+  auto issue_load = [&](int i) {   // one lane
+    const int g = g0 + i;
+    const int b = g / cpf, c = g - b * cpf;
+    const int c0 = c * chunk_px, npx = min(chunk_px, HW - c0);
+    const int s = i % kWStages;
+    const uint32_t bytes = (uint32_t)npx * nj * 4u;
+    mbar_arrive_expect_tx(&full[s], bytes);
+    bulk_load_1d(stage + s * kWChunkFloats, logits + ((size_t)b * HW + c0) * nj, bytes, &full[s]);
+    // A parity wait cannot tell "phase u pending" from "phase u-2 pending": the consumer of use u first checks this
+    // counter, i.e. that use u's transaction has been registered on the barrier.
+    __threadfence_block();
+    issued[s] = i / kWStages + 1;
+  };
+  if (lane == 0)
+    for (int i = warp; i < min(nloc, kWStages); i += kWWarps) issue_load(i);
+
+  // -------------------------------------------------------------------- math warps
+  const float g2 = gamma * 1.4426950408889634f;
+  const bool act = lane < tw;
+  int P = nj;                                   // lanes l, l' share their joints iff l == l' (mod P)
+  for (int a = 4, bb = nj; bb;) { const int r = a % bb; a = bb; bb = r; P = nj / a; }
   int jq[4];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) jq[q] = (4 * tid + q) % nj;
-  const int dP = L / nj;                         // pixels between a thread's consecutive float4s
+  for (int q = 0; q < 4; ++q) jq[q] = (4 * lane + q) % nj;
+  const int dP = 4 * tw / nj;                    // pixels between a lane's consecutive float4s
   const float dPr = (float)(dP / W), dPc = (float)(dP - (dP / W) * W);
-  const int cqW = chunk_px / W, crW = chunk_px - cqW * W;   // chunk advance in (rows, cols)
-  const float Wf = (float)W;
-  const int warp = tid >> 5, lane = tid & 31;
-  constexpr int kLanes = kSamePixel ? 1 : 4;     // (row, col) trackers per thread
+  const float Wf = (float)W, invW = 1.0f / (float)W;
+  const float Rf = (float)radius, HmR = (float)(H - radius), WmR = (float)(W - radius);
+  constexpr int kPos = kSamePixel ? 1 : 4;       // (row, col) trackers per lane
   const f32x2 g2g2 = pk2(g2, g2), dpos = pk2(dPr, dPc), wrapfix = pk2(1.0f, -Wf);
-  const int nslice = reduce_slices(nj);
+  float* scr = scratch + warp * kWScratchFloats;
 
-  int it = 0;
-  for (int job = blockIdx.x; job < njobs; job += gridDim.x) {
-    const int b = job / nseg, seg = job - b * nseg;
-    const int p_beg = seg * seg_px, p_end = min(HW, p_beg + seg_px);
-    // per-lane state; the packed variants hold (joint 0, joint 1) / (joint 2, joint 3) or (row-sum, col-sum) pairs
-    float m2[4], s0[4], sr[4], sc[4], thr[4], bsig[4];
+  // (Ah*Aw - 1, Rh*Aw - r, Ah*Rw - c) of a border pixel: what its blur weights differ from the interior (1, r, c) by
+  auto border_corr = [&](float pr, float pc, float& k0, float& kr, float& kc) {
+    const int r = (int)pr, c = (int)pc;
+    float ah = 1.0f, rh = pr, aw = 1.0f, rw = pc;
+    if (all_border) {
+      border_weights_slow(r, H, radius, sigma, ah, rh);
+      border_weights_slow(c, W, radius, sigma, aw, rw);
+    } else {
+      const int ir = r < radius ? r : (r >= H - radius ? r - (H - R2) : -1);
+      const int ic = c < radius ? c : (c >= W - radius ? c - (W - R2) : -1);
+      if (ir >= 0) { ah = btab[ir]; rh = btab[16 + ir]; }
+      if (ic >= 0) { aw = btab[32 + ic]; rw = btab[48 + ic]; }
+    }
+    k0 = ah * aw - 1.0f;
+    kr = rh * aw - pr;
+    kc = ah * rw - pc;
+  };
+
+  // lanes that share this lane's joints (REDUX masks); kShfl guarantees 32 % P == 0
+  unsigned cls_mask = 0;
+  if (kShfl)
+    for (int l = lane % P; l < 32; l += P) cls_mask |= 1u << l;
+  const int bslot = lane / P, bcls = lane - (lane / P) * P, blanes = tw / P;   // border pass: pixel slot / granule class
+
+  int cb = 0, cc = 0;                            // (frame, chunk in frame) of this warp's current chunk
+  if (warp < nloc) { cb = (g0 + warp) / cpf; cc = (g0 + warp) - cb * cpf; }
+  for (int i = warp; i < nloc; i += kWWarps) {
+    const int b = cb, c = cc;
+    cc += kWWarps;
+    while (cc >= cpf) { cc -= cpf; ++cb; }
+    const int c0 = c * chunk_px, npx = min(chunk_px, HW - c0);
+    const int n4 = npx * nj / 4;
+    const int s = i % kWStages, ph = (i / kWStages) & 1;
+    const float4* st4 = reinterpret_cast<const float4*>(stage + s * kWChunkFloats);
+    if (issued[s] <= i / kWStages) {
+      const uint64_t t0 = globaltimer_ns();
+      while (issued[s] <= i / kWStages) {
+        if (globaltimer_ns() - t0 > 4000000000ull) {
+          printf("dgp_b200: soft-argmax stage %d never refilled (block %d warp %d chunk %d)\n", s, blockIdx.x, warp, i);
+          __trap();
+        }
+      }
+    }
+    __threadfence_block();
+    mbar_wait(&full[s], ph);
+
+    float xm[4], m2[4], mout[4], thr[4], s0[4], sr[4], sc[4], bsig[4];
     int bidx[4];
-    f32x2 s0p[2], rcp[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      m2[q] = 0.0f; thr[q] = CUDART_INF_F;
-      s0[q] = sr[q] = sc[q] = 0.0f; bsig[q] = -1.0f; bidx[q] = 0x7fffffff;
-      rcp[q] = pk2(0.0f, 0.0f);
-    }
-    s0p[0] = s0p[1] = pk2(0.0f, 0.0f);
-    float mb = 0.0f, d0 = 0.0f, dr = 0.0f, dc = 0.0f;
-    // (row, col) of the chunk origin (ints) and of this thread's first pixel in the current chunk (floats)
-    int crow_i = p_beg / W, ccol_i = p_beg - crow_i * W;
-    float crow[kLanes], ccol[kLanes];
-#pragma unroll
-    for (int q = 0; q < kLanes; ++q) {
-      const int pix = p_beg + (4 * tid + q) / nj;
-      crow[q] = (float)(pix / W);
-      ccol[q] = (float)(pix - (pix / W) * W);
-    }
-
-    for (int c0 = p_beg; c0 < p_end; c0 += chunk_px, ++it) {
-      const int c1 = min(c0 + chunk_px, p_end);
-      const int s = it % kStStages, ph = (it / kStStages) & 1;
-      mbar_wait(&full[s], ph);
-      mbar_wait(&ready[s], ph);
-      const float* st = stage + s * kStStageFloats;
-      const int n4 = (c1 - c0) * nj / 4;
-      const float4* st4 = reinterpret_cast<const float4*>(st);
-
-      if (lane_act) {
-        if constexpr (kSamePixel) {
-          // the thread's four joints are consecutive and 16 B aligned in the published tables
-          const float4 M = *reinterpret_cast<const float4*>(pm2 + s * kMaxJoints + jq[0]);
-          const float4 F = *reinterpret_cast<const float4*>(pf + s * kMaxJoints + jq[0]);
-          const f32x2 nm01 = pk2(-M.x, -M.y), nm23 = pk2(-M.z, -M.w);
-          s0p[0] = mul2(s0p[0], pk2(F.x, F.y));
-          s0p[1] = mul2(s0p[1], pk2(F.z, F.w));
-          rcp[0] = mul2(rcp[0], pk2(F.x, F.x));
-          rcp[1] = mul2(rcp[1], pk2(F.y, F.y));
-          rcp[2] = mul2(rcp[2], pk2(F.z, F.z));
-          rcp[3] = mul2(rcp[3], pk2(F.w, F.w));
-          m2[0] = M.x; m2[1] = M.y; m2[2] = M.z; m2[3] = M.w;
-          if (kDlc) {
-            const float4 T = *reinterpret_cast<const float4*>(pthr + s * kMaxJoints + jq[0]);
-            thr[0] = T.x; thr[1] = T.y; thr[2] = T.z; thr[3] = T.w;
+    // Attempt 0 (no DLC peak wanted): no max pass at all -- softmax numerators 2^(x*g2) against the fixed reference 0,
+    // valid while the largest exponent of the chunk stays inside [-90, 90] (any |logit*gamma| < 62).  Otherwise, and
+    // whenever the DLC peak needs the true maximum, attempt 1: exact per-joint max first, then the same pass.
+    for (int attempt = kDlc ? 1 : 0; attempt < 2; ++attempt) {
+      if (attempt == 1) {
+        // ---- pass 1: per-joint max of the chunk
+        float4 m = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+        if (act) {
+          int f = lane;
+          for (; f + 3 * tw < n4; f += 4 * tw) {
+            const float4 v0 = st4[f], v1 = st4[f + tw], v2 = st4[f + 2 * tw], v3 = st4[f + 3 * tw];
+            m.x = fmaxf(fmaxf(m.x, v0.x), fmaxf(v1.x, fmaxf(v2.x, v3.x)));
+            m.y = fmaxf(fmaxf(m.y, v0.y), fmaxf(v1.y, fmaxf(v2.y, v3.y)));
+            m.z = fmaxf(fmaxf(m.z, v0.z), fmaxf(v1.z, fmaxf(v2.z, v3.z)));
+            m.w = fmaxf(fmaxf(m.w, v0.w), fmaxf(v1.w, fmaxf(v2.w, v3.w)));
           }
-          f32x2 pos = pk2(crow[0], ccol[0]);
+          for (; f < n4; f += tw) {
+            const float4 v = st4[f];
+            m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+          }
+        }
+        xm[0] = m.x; xm[1] = m.y; xm[2] = m.z; xm[3] = m.w;
+        if constexpr (kShfl) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) xm[q] = dec_ordered(__reduce_max_sync(cls_mask, enc_ordered(xm[q])));
+        } else {
+          __syncwarp();
+          if (act) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) scr[4 * lane + q] = xm[q];
+          }
+          __syncwarp();
+          for (int j = lane; j < nj; j += 32) {
+            float mj = -CUDART_INF_F;
+            for (int e = j; e < 4 * tw; e += nj) mj = fmaxf(mj, scr[e]);
+            scr[640 + j] = mj;
+          }
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < 4; ++q) xm[q] = scr[640 + jq[q]];
+          __syncwarp();
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        // an all -inf chunk contributes nothing: a finite reference keeps 2^(x*g2 - m2) at 0 instead of NaN
+        const bool empty_joint = attempt == 1 && xm[q] == -CUDART_INF_F;
+        m2[q] = (attempt == 0 || empty_joint) ? 0.0f : xm[q] * g2;
+        mout[q] = empty_joint ? -CUDART_INF_F : m2[q];   // the merge skips partials whose reference is -inf
+        thr[q] = kDlc ? dlc_candidate_threshold(xm[q]) : 0.0f;
+        s0[q] = sr[q] = sc[q] = 0.0f; bsig[q] = -1.0f; bidx[q] = 0x7fffffff;
+      }
+      float tmax = -CUDART_INF_F;               // largest exponent seen (attempt 0 only)
+
+      // ---- pass 2
+      if (act) {
+        float prow[kPos], pcol[kPos];
+#pragma unroll
+        for (int q = 0; q < kPos; ++q) {
+          const int pix = c0 + (4 * lane + q) / nj;
+          int r = (int)((float)pix * invW);
+          if (r * W > pix) --r;
+          if ((r + 1) * W <= pix) ++r;
+          prow[q] = (float)r;
+          pcol[q] = (float)(pix - r * W);
+        }
+        if constexpr (kSamePixel) {
+          const f32x2 nm01 = pk2(-m2[0], -m2[1]), nm23 = pk2(-m2[2], -m2[3]);
+          f32x2 s0p0 = pk2(0.0f, 0.0f), s0p1 = s0p0, rc0 = s0p0, rc1 = s0p0, rc2 = s0p0, rc3 = s0p0;
+          f32x2 pos = pk2(prow[0], pcol[0]);
+          float tm0 = -CUDART_INF_F, tm1 = -CUDART_INF_F;
           auto consume = [&](const float4& v) {
-            float t0, t1, t2, t3;
+            float t0, t1, t2, t3, pr, pc;
             upk2(fma2(pk2(v.x, v.y), g2g2, nm01), t0, t1);
             upk2(fma2(pk2(v.z, v.w), g2g2, nm23), t2, t3);
+            if (!kDlc) { tm0 = fmaxf(tm0, fmaxf(t0, t1)); tm1 = fmaxf(tm1, fmaxf(t2, t3)); }
             const float e0 = ex2_approx(t0), e1 = ex2_approx(t1), e2 = ex2_approx(t2), e3 = ex2_approx(t3);
-            s0p[0] = add2(s0p[0], pk2(e0, e1));
-            s0p[1] = add2(s0p[1], pk2(e2, e3));
-            rcp[0] = fma2(pos, pk2(e0, e0), rcp[0]);
-            rcp[1] = fma2(pos, pk2(e1, e1), rcp[1]);
-            rcp[2] = fma2(pos, pk2(e2, e2), rcp[2]);
-            rcp[3] = fma2(pos, pk2(e3, e3), rcp[3]);
+            s0p0 = add2(s0p0, pk2(e0, e1));
+            s0p1 = add2(s0p1, pk2(e2, e3));
+            rc0 = fma2(pos, pk2(e0, e0), rc0);
+            rc1 = fma2(pos, pk2(e1, e1), rc1);
+            rc2 = fma2(pos, pk2(e2, e2), rc2);
+            rc3 = fma2(pos, pk2(e3, e3), rc3);
             if (kDlc) {
               if ((v.x >= thr[0]) | (v.y >= thr[1]) | (v.z >= thr[2]) | (v.w >= thr[3])) {
-                float pr, pc;
                 upk2(pos, pr, pc);
                 const int idx = (int)pr * W + (int)pc;
                 const float xs[4] = {v.x, v.y, v.z, v.w};
@@ -402,181 +370,169 @@ __global__ void __launch_bounds__(kStThreads, 1) softargmax_stream_kernel(
               }
             }
             pos = add2(pos, dpos);
-            float pr, pc;
             upk2(pos, pr, pc);
             if (pc >= Wf) pos = add2(pos, wrapfix);
           };
-          int f = tid;
-          for (; f + 3 * tact < n4; f += 4 * tact) {
-            const float4 v0 = st4[f], v1 = st4[f + tact], v2 = st4[f + 2 * tact], v3 = st4[f + 3 * tact];
+          int f = lane;
+          for (; f + 3 * tw < n4; f += 4 * tw) {
+            const float4 v0 = st4[f], v1 = st4[f + tw], v2 = st4[f + 2 * tw], v3 = st4[f + 3 * tw];
             consume(v0); consume(v1); consume(v2); consume(v3);
           }
-          for (; f < n4; f += tact) consume(st4[f]);
-        } else {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float f = pf[s * kMaxJoints + jq[q]];
-            m2[q] = pm2[s * kMaxJoints + jq[q]];
-            s0[q] *= f; sr[q] *= f; sc[q] *= f;
-            if (kDlc) thr[q] = pthr[s * kMaxJoints + jq[q]];
+          for (; f < n4; f += tw) consume(st4[f]);
+          tmax = fmaxf(tm0, tm1);
+
+          // blur border correction: pixels within `radius` of an edge lose the taps that fall outside, i.e. their
+          // weights are (Ah*Aw, Rh*Aw, Ah*Rw) instead of the interior (1, row, col) added above.  Lane (slot, class)
+          // takes every blanes-th border pixel and, of its nj/4 float4s, the one holding this lane's joints.
+          {
+            int ra = (int)((float)c0 * invW);
+            if (ra * W > c0) --ra;
+            if ((ra + 1) * W <= c0) ++ra;
+            const int pl = c0 + npx - 1;
+            int rb = (int)((float)pl * invW);
+            if (rb * W > pl) --rb;
+            if ((rb + 1) * W <= pl) ++rb;
+            auto fix_px = [&](int r, int cpx) {
+              const int p = r * W + cpx;
+              if (p < c0 || p >= c0 + npx) return;
+              const float4 v = st4[(p - c0) * P + bcls];
+              float t0, t1, t2, t3, k0, kr, kc;
+              upk2(fma2(pk2(v.x, v.y), g2g2, nm01), t0, t1);
+              upk2(fma2(pk2(v.z, v.w), g2g2, nm23), t2, t3);
+              const float e0 = ex2_approx(t0), e1 = ex2_approx(t1), e2 = ex2_approx(t2), e3 = ex2_approx(t3);
+              border_corr((float)r, (float)cpx, k0, kr, kc);
+              const f32x2 k00 = pk2(k0, k0), krc = pk2(kr, kc);
+              s0p0 = fma2(pk2(e0, e1), k00, s0p0);
+              s0p1 = fma2(pk2(e2, e3), k00, s0p1);
+              rc0 = fma2(krc, pk2(e0, e0), rc0);
+              rc1 = fma2(krc, pk2(e1, e1), rc1);
+              rc2 = fma2(krc, pk2(e2, e2), rc2);
+              rc3 = fma2(krc, pk2(e3, e3), rc3);
+            };
+            if (!all_border) {
+              const int nside = (rb - ra + 1) * R2;        // left / right columns of every row of the chunk
+              for (int k = bslot; k < nside; k += blanes) {
+                const int rr = k / R2, sx = k - rr * R2;
+                fix_px(ra + rr, sx < radius ? sx : W - R2 + sx);
+              }
+              for (int r = ra; r <= rb; ++r) {               // top / bottom rows: the span between the side columns
+                if (r >= radius && r < H - radius) continue;
+                for (int cpx = radius + bslot; cpx < W - radius; cpx += blanes) fix_px(r, cpx);
+              }
+            } else {
+              for (int r = ra; r <= rb; ++r)
+                for (int cpx = bslot; cpx < W; cpx += blanes) fix_px(r, cpx);
+            }
           }
-          float frow[kLanes], fcol[kLanes];
-#pragma unroll
-          for (int q = 0; q < kLanes; ++q) { frow[q] = crow[q]; fcol[q] = ccol[q]; }
+          upk2(s0p0, s0[0], s0[1]);
+          upk2(s0p1, s0[2], s0[3]);
+          upk2(rc0, sr[0], sc[0]);
+          upk2(rc1, sr[1], sc[1]);
+          upk2(rc2, sr[2], sc[2]);
+          upk2(rc3, sr[3], sc[3]);
+        } else {
           auto consume = [&](const float4& v) {
             const float xs[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const float e = ex2_approx(fmaf(xs[q], g2, -m2[q]));
-              s0[q] += e;
-              sr[q] = fmaf(e, frow[q % kLanes], sr[q]);
-              sc[q] = fmaf(e, fcol[q % kLanes], sc[q]);
-            }
-            if (kDlc) {
-              if ((xs[0] >= thr[0]) | (xs[1] >= thr[1]) | (xs[2] >= thr[2]) | (xs[3] >= thr[3])) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  if (xs[q] >= thr[q]) {
-                    const float sg = dlc_sigmoid(xs[q]);
-                    const int idx = (int)frow[q % kLanes] * W + (int)fcol[q % kLanes];
-                    if (sg > bsig[q] || (sg == bsig[q] && idx < bidx[q])) { bsig[q] = sg; bidx[q] = idx; }
-                  }
+              const float pr = prow[q % kPos], pc = pcol[q % kPos];
+              const float t = fmaf(xs[q], g2, -m2[q]);
+              if (!kDlc) tmax = fmaxf(tmax, t);
+              const float e = ex2_approx(t);
+              float w0 = 1.0f, wr = pr, wc = pc;
+              if (all_border | (pr < Rf) | (pr >= HmR) | (pc < Rf) | (pc >= WmR)) {
+                float k0, kr, kc;
+                border_corr(pr, pc, k0, kr, kc);
+                w0 += k0; wr += kr; wc += kc;
+              }
+              s0[q] = fmaf(e, w0, s0[q]);
+              sr[q] = fmaf(e, wr, sr[q]);
+              sc[q] = fmaf(e, wc, sc[q]);
+              if (kDlc) {
+                if (xs[q] >= thr[q]) {
+                  const float sg = dlc_sigmoid(xs[q]);
+                  const int idx = (int)pr * W + (int)pc;
+                  if (sg > bsig[q] || (sg == bsig[q] && idx < bidx[q])) { bsig[q] = sg; bidx[q] = idx; }
                 }
               }
             }
 #pragma unroll
-            for (int q = 0; q < kLanes; ++q) {
-              fcol[q] += dPc; frow[q] += dPr;
-              if (fcol[q] >= Wf) { fcol[q] -= Wf; frow[q] += 1.0f; }
+            for (int q = 0; q < kPos; ++q) {
+              pcol[q] += dPc; prow[q] += dPr;
+              if (pcol[q] >= Wf) { pcol[q] -= Wf; prow[q] += 1.0f; }
             }
           };
-          int f = tid;
-          for (; f + 3 * tact < n4; f += 4 * tact) {
-            const float4 v0 = st4[f], v1 = st4[f + tact], v2 = st4[f + 2 * tact], v3 = st4[f + 3 * tact];
-            consume(v0); consume(v1); consume(v2); consume(v3);
+          int f = lane;
+          for (; f + 1 * tw < n4; f += 2 * tw) {
+            const float4 v0 = st4[f], v1 = st4[f + tw];
+            consume(v0); consume(v1);
           }
-          for (; f < n4; f += tact) consume(st4[f]);
-        }
-        // advance this thread's chunk origin
-#pragma unroll
-        for (int q = 0; q < kLanes; ++q) {
-          ccol[q] += (float)crW; crow[q] += (float)cqW;
-          if (ccol[q] >= Wf) { ccol[q] -= Wf; crow[q] += 1.0f; }
+          for (; f < n4; f += tw) consume(st4[f]);
         }
       }
-
-      if (b_act) {
-        // blur border correction: pixels within `radius` of an edge lose the taps that fall outside, i.e. their weights
-        // are (Ah*Aw, Rh*Aw, Ah*Rw) instead of the interior (1, row, col) added above
-        {
-          const float f = pf[s * kMaxJoints + jb];
-          mb = pm2[s * kMaxJoints + jb];
-          d0 *= f; dr *= f; dc *= f;
-        }
-        auto add_px = [&](int r, int c) {
-          const int p = r * W + c;
-          if (p < c0 || p >= c1) return;
-          const float e = ex2_approx(fmaf(st[(p - c0) * nj + jb], g2, -mb));
-          float ah = 1.0f, rh = (float)r, aw = 1.0f, rw = (float)c;
-          if (all_border) {
-            border_weights_slow(r, H, radius, sigma, ah, rh);
-            border_weights_slow(c, W, radius, sigma, aw, rw);
-          } else {
-            const int ir = r < radius ? r : (r >= H - radius ? r - (H - R2) : -1);
-            const int ic = c < radius ? c : (c >= W - radius ? c - (W - R2) : -1);
-            if (ir >= 0) { ah = btab[ir]; rh = btab[16 + ir]; }
-            if (ic >= 0) { aw = btab[32 + ic]; rw = btab[48 + ic]; }
-          }
-          d0 += e * (ah * aw - 1.0f);
-          dr += e * (rh * aw - (float)r);
-          dc += e * (ah * rw - (float)c);
-        };
-        const int ra = crow_i;
-        int rb;
-        if (c1 - c0 == chunk_px) rb = ra + cqW + ((ccol_i + crW - 1 >= W) ? 1 : 0) - (crW == 0 && ccol_i == 0 ? 1 : 0);
-        else rb = (c1 - 1) / W;
-        if (!all_border) {
-          int rq = bq0, sx = bs0;                       // left / right columns of every row of the chunk
-          for (; ra + rq <= rb; ) {
-            add_px(ra + rq, sx < radius ? sx : W - R2 + sx);
-            rq += bdq; sx += bds;
-            if (sx >= R2) { sx -= R2; rq += 1; }
-          }
-          // top / bottom rows: the full span between the side columns
-          for (int r = ra; r <= min(rb, radius - 1); ++r)
-            for (int c = radius + gb; c < W - radius; c += Gb) add_px(r, c);
-          for (int r = max(ra, H - radius); r <= rb; ++r)
-            for (int c = radius + gb; c < W - radius; c += Gb) add_px(r, c);
-        } else {
-          for (int r = ra; r <= rb; ++r)
-            for (int c = gb; c < W; c += Gb) add_px(r, c);
-        }
+      if (attempt == 0) {
+        // warp-uniform decision; NaN exponents fall through to the exact pass as well
+        const int tenc = __reduce_max_sync(0xffffffffu, enc_ordered(tmax));
+        const float tall = dec_ordered(tenc);
+        if (tall >= -90.0f && tall <= 90.0f) break;
       }
-      crow_i += cqW; ccol_i += crW;
-      if (ccol_i >= W) { ccol_i -= W; crow_i += 1; }
-      mbar_arrive(&empty[s]);
+    }
+    // the stage is free as soon as every lane has read its float4s: refill it
+    __syncwarp();
+    if (lane == 0 && i + kWStages < nloc) {
+      fence_proxy_async_smem();   // order the warp's generic-proxy reads before the async-proxy write
+      issue_load(i + kWStages);
     }
 
-    // ---- job end: deterministic block reduction (fixed order), nslice partials per (frame, segment, joint)
-    if (lane_act) {
-      if constexpr (kSamePixel) {
-        upk2(s0p[0], s0[0], s0[1]);
-        upk2(s0p[1], s0[2], s0[3]);
+    // ---- reduce over the lanes that share a joint; one partial per (chunk, joint), fixed order -> deterministic
+    SaPartial* out = part + ((size_t)b * cpf + c) * nj;
+    if constexpr (kShfl) {
+      for (int o = 16; o >= P; o >>= 1) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) upk2(rcp[q], sr[q], sc[q]);
+        for (int q = 0; q < 4; ++q) {
+          s0[q] += __shfl_xor_sync(0xffffffffu, s0[q], o);
+          sr[q] += __shfl_xor_sync(0xffffffffu, sr[q], o);
+          sc[q] += __shfl_xor_sync(0xffffffffu, sc[q], o);
+          if (kDlc) {
+            const float obs = __shfl_xor_sync(0xffffffffu, bsig[q], o);
+            const int obi = __shfl_xor_sync(0xffffffffu, bidx[q], o);
+            if (obs > bsig[q] || (obs == bsig[q] && obi < bidx[q])) { bsig[q] = obs; bidx[q] = obi; }
+          }
+        }
       }
+      if (lane < P) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float* r = red + (4 * tid + q) * 5;
-        r[0] = s0[q]; r[1] = sr[q]; r[2] = sc[q]; r[3] = bsig[q]; r[4] = __int_as_float(bidx[q]);
+        for (int q = 0; q < 4; ++q) {
+          float4* o4 = reinterpret_cast<float4*>(out + jq[q]);
+          o4[0] = make_float4(mout[q], s0[q], sr[q], sc[q]);
+          o4[1] = make_float4(bsig[q], __int_as_float(bidx[q]), 0.0f, 0.0f);
+        }
       }
-    }
-    if (b_act) {
-      float* r = redb + tid * 3;
-      r[0] = d0; r[1] = dr; r[2] = dc;
-      if (gb == 0) jm[jb] = mb;
-    }
-    named_bar_sync(1, kStMain);
-    {
-      const int per_joint = L / nj;                       // lanes holding joint j: e = j + nj * k, k < per_joint
-      const int kper = (per_joint + nslice - 1) / nslice;
-      for (int w = warp; w < nj * nslice; w += kStMain / 32) {
-        const int j = w % nj, sl = w / nj;
+    } else {
+      if (act) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float* r = scr + (4 * lane + q) * 5;
+          r[0] = s0[q]; r[1] = sr[q]; r[2] = sc[q]; r[3] = bsig[q]; r[4] = __int_as_float(bidx[q]);
+          if (4 * lane + q < nj) scr[640 + 4 * lane + q] = mout[q];   // slot e < nj holds joint e
+        }
+      }
+      __syncwarp();
+      for (int j = lane; j < nj; j += 32) {
         float a0 = 0.0f, ar = 0.0f, ac = 0.0f, bs = -1.0f;
         int bi = 0x7fffffff;
-        const int k1 = min(per_joint, (sl + 1) * kper);
-        for (int k = sl * kper + lane; k < k1; k += 32) {
-          const float* r = red + (j + nj * k) * 5;
+        for (int e = j; e < 4 * tw; e += nj) {
+          const float* r = scr + e * 5;
           a0 += r[0]; ar += r[1]; ac += r[2];
-          if (kDlc) {
-            const int idx = __float_as_int(r[4]);
-            if (r[3] > bs || (r[3] == bs && idx < bi)) { bs = r[3]; bi = idx; }
-          }
+          const int idx = __float_as_int(r[4]);
+          if (r[3] > bs || (r[3] == bs && idx < bi)) { bs = r[3]; bi = idx; }
         }
-        if (sl == 0) {
-          for (int g = lane; g < Gb; g += 32) {
-            const float* r = redb + (j + nj * g) * 3;
-            a0 += r[0]; ar += r[1]; ac += r[2];
-          }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-          ar += __shfl_xor_sync(0xffffffffu, ar, o);
-          ac += __shfl_xor_sync(0xffffffffu, ac, o);
-          if (kDlc) {
-            const float obs = __shfl_xor_sync(0xffffffffu, bs, o);
-            const int obi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (obs > bs || (obs == bs && obi < bi)) { bs = obs; bi = obi; }
-          }
-        }
-        if (lane == 0) {
-          SaPartial& o = part[(((size_t)b * nseg + seg) * nslice + sl) * nj + j];
-          o.m = jm[j]; o.s0 = a0; o.sr = ar; o.sc = ac; o.bsig = bs; o.bidx = bi;
-        }
+        float4* o4 = reinterpret_cast<float4*>(out + j);
+        o4[0] = make_float4(scr[640 + j], a0, ar, ac);
+        o4[1] = make_float4(bs, __int_as_float(bi), 0.0f, 0.0f);
       }
+      __syncwarp();
     }
-    named_bar_sync(1, kStMain);  // the next job's partials reuse red / redb / jm
   }
 }
 
@@ -775,47 +731,35 @@ __global__ void __launch_bounds__(kPotFrames) potentials_kernel(
 
 }  // namespace
 
+// active lanes per warp: the largest tw <= 32 with 4*tw % nj == 0 (0: unsupported joint count)
 int softargmax_tact(int nj) {
-  // largest thread count <= 256 with 4*t % nj == 0
   int g = nj;
   for (int a = 4, b = nj; b;) { int r = a % b; a = b; b = r; g = a; }
-  const int step = nj / g;  // t must be a multiple of nj / gcd(nj, 4)
-  int t = (kStMain / step) * step;
-  return t;
+  const int step = nj / g;  // tw must be a multiple of nj / gcd(nj, 4)
+  return (32 / step) * step;
 }
 
-static int scout_tact(int nj) {
-  int g = nj;
-  for (int a = 4, b = nj; b;) { int r = a % b; a = b; b = r; g = a; }
-  const int step = nj / g;
-  return (kStScout / step) * step;
-}
+static int softargmax_chunk_px(int nj) { return (kWChunkFloats / nj) & ~3; }
 
-static int softargmax_chunk_px(int nj) { return (kStStageFloats / nj) & ~3; }
-
-// Segments per frame: a function of the map shape only (never of the batch size) -> batch-invariant arithmetic.
-static int softargmax_segments(int H, int W, int nj) {
-  const int seg_px = softargmax_chunk_px(nj) * kSegChunks;
-  return (H * W + seg_px - 1) / seg_px;
-}
-
+// Chunks per frame: a function of the map shape only (never of the batch size) -> batch-invariant arithmetic.
 int softargmax_splits(int H, int W, int nj) {
   if (nj < 1 || nj > kMaxJoints) return 1;
-  return softargmax_segments(H, W, nj) * reduce_slices(nj);
+  const int cp = softargmax_chunk_px(nj);
+  return (H * W + cp - 1) / cp;
 }
 
-template <bool kSamePixel, bool kDlc>
+template <bool kSamePixel, bool kShfl, bool kDlc>
 static cudaError_t launch_stream(const float* logits, int B, int H, int W, int nj, float gamma, int radius, float sigma,
-                                 int chunk_px, int nseg, int tact, int stact, SaPartial* ws, int grid, cudaStream_t stream) {
+                                 int chunk_px, int cpf, int tw, SaPartial* ws, int grid, cudaStream_t stream) {
   static bool configured = false;  // per instantiation
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(softargmax_stream_kernel<kSamePixel, kDlc>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(softargmax_stream_kernel<kSamePixel, kShfl, kDlc>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWSmemBytes);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  softargmax_stream_kernel<kSamePixel, kDlc><<<grid, kStThreads, kStSmemBytes, stream>>>(
-      logits, B, H, W, nj, gamma, radius, sigma, chunk_px, nseg, tact, stact, ws);
+  softargmax_stream_kernel<kSamePixel, kShfl, kDlc><<<grid, kWThreads, kWSmemBytes, stream>>>(
+      logits, B, H, W, nj, gamma, radius, sigma, chunk_px, cpf, tw, ws);
   return cudaGetLastError();
 }
 
@@ -824,12 +768,13 @@ cudaError_t launch_softargmax(const float* logits, const float* locref, int B, i
                               float* mu, int* peak, float* lik, int* dlc_peak, float* dlc_pose, float* norm,
                               cudaStream_t stream) {
   if (B <= 0) return cudaSuccess;
-  const int tact = softargmax_tact(nj);
   const int radius = (int)gauss_len;
-  if (tact <= 0 || nj > kMaxJoints || (H & 1) || (W & 1) || radius > 4 || ((uintptr_t)logits & 15))
+  if (nj < 1 || nj > kMaxJoints || (H & 1) || (W & 1) || radius > 4 || ((uintptr_t)logits & 15))
     return cudaErrorInvalidValue;
-  const int nseg = softargmax_segments(H, W, nj);
-  if (nseg * reduce_slices(nj) != splits) return cudaErrorInvalidValue;  // workspace sized with softargmax_splits()
+  const int tw = softargmax_tact(nj);
+  if (tw <= 0) return cudaErrorInvalidValue;
+  const int cpf = softargmax_splits(H, W, nj);
+  if (cpf != splits) return cudaErrorInvalidValue;  // the caller sized the workspace with softargmax_splits()
   static int num_sms = 0;
   if (num_sms == 0) {
     int dev = 0;
@@ -837,18 +782,22 @@ cudaError_t launch_softargmax(const float* logits, const float* locref, int B, i
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return e;
   }
-  const int njobs = B * nseg;
-  const int grid = njobs < num_sms ? njobs : num_sms;
+  const long long nchunks = (long long)B * cpf;
+  if (nchunks > 0x7fffffffLL) return cudaErrorInvalidValue;
+  // small batches: still give every math warp of a CTA a chunk before spreading over more SMs than needed
+  long long want = (nchunks + kWWarps - 1) / kWWarps;
+  const int grid = (int)(want < num_sms ? (want < 1 ? 1 : want) : num_sms);
   const int chunk_px = softargmax_chunk_px(nj);
-  const int stact = scout_tact(nj);
   const bool dlc = dlc_peak != nullptr || dlc_pose != nullptr;
+  const bool same = nj % 4 == 0;
+  const bool shfl = same && (128 % nj == 0);
   cudaError_t e;
-  if (nj % 4 == 0)
-    e = dlc ? launch_stream<true, true>(logits, B, H, W, nj, gamma, radius, gauss_len, chunk_px, nseg, tact, stact, workspace, grid, stream)
-            : launch_stream<true, false>(logits, B, H, W, nj, gamma, radius, gauss_len, chunk_px, nseg, tact, stact, workspace, grid, stream);
-  else
-    e = dlc ? launch_stream<false, true>(logits, B, H, W, nj, gamma, radius, gauss_len, chunk_px, nseg, tact, stact, workspace, grid, stream)
-            : launch_stream<false, false>(logits, B, H, W, nj, gamma, radius, gauss_len, chunk_px, nseg, tact, stact, workspace, grid, stream);
+#define DGP_SA_LAUNCH(SP, SH, DL) \
+  launch_stream<SP, SH, DL>(logits, B, H, W, nj, gamma, radius, gauss_len, chunk_px, cpf, tw, workspace, grid, stream)
+  if (shfl) e = dlc ? DGP_SA_LAUNCH(true, true, true) : DGP_SA_LAUNCH(true, true, false);
+  else if (same) e = dlc ? DGP_SA_LAUNCH(true, false, true) : DGP_SA_LAUNCH(true, false, false);
+  else e = dlc ? DGP_SA_LAUNCH(false, false, true) : DGP_SA_LAUNCH(false, false, false);
+#undef DGP_SA_LAUNCH
   if (e != cudaSuccess) return e;
   const int n = B * nj;
   softargmax_finalize_kernel<<<(n + 3) / 4, 128, 0, stream>>>(logits, locref, B, H, W, nj, splits, workspace, stride,
