@@ -142,7 +142,64 @@ __device__ __noinline__ void border_weights_slow(int pos, int n, int radius, flo
 // replicated in the unrolled hot loop
 __device__ __noinline__ float dlc_sigmoid(float x) { return sigmoid_tf(x); }
 
-template <bool kSamePixel, bool kShfl, bool kDlc>
+// Multi-value butterfly: reduces the 12 per-lane sums over the lanes that share a joint (xor offsets 16 .. kP) with
+// half of the values travelling each step (24 shuffles for 12 values over 32 lanes instead of 60).  On return lane l
+// holds value index `vi` (or -1) in `out0`, and for kP == 4 a second one (`vi1`, `out1`).  Fixed tree -> deterministic.
+template <int kP>
+__device__ __forceinline__ void butterfly12(const float (&v)[12], int lane, float (&fin)[12], int& cnt, int& base) {
+  constexpr unsigned F = 0xffffffffu;
+  cnt = 12; base = 0;
+#pragma unroll
+  for (int k = 0; k < 12; ++k) fin[k] = v[k];
+  if constexpr (kP <= 16) {
+    const bool up = lane & 16;
+    float w[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const float snd = up ? fin[k] : fin[6 + k], kp = up ? fin[6 + k] : fin[k];
+      w[k] = kp + __shfl_xor_sync(F, snd, 16);
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) fin[k] = w[k];
+    cnt = 6; base = up ? 6 : 0;
+  }
+  if constexpr (kP <= 8) {
+    const bool up = lane & 8;
+    float w[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float snd = up ? fin[k] : fin[3 + k], kp = up ? fin[3 + k] : fin[k];
+      w[k] = kp + __shfl_xor_sync(F, snd, 8);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) fin[k] = w[k];
+    cnt = 3; base += up ? 3 : 0;
+  }
+  if constexpr (kP <= 4) {
+    // 3 -> 2: the lower lanes keep {0, 1}, the upper lanes keep {2, (nothing)}
+    const bool up = lane & 4;
+    const float snd0 = up ? fin[0] : fin[2], kp0 = up ? fin[2] : fin[0];
+    const float snd1 = up ? fin[1] : 0.0f, kp1 = up ? 0.0f : fin[1];
+    const float w0 = kp0 + __shfl_xor_sync(F, snd0, 4), w1 = kp1 + __shfl_xor_sync(F, snd1, 4);
+    fin[0] = w0; fin[1] = w1;
+    cnt = up ? 1 : 2; base += up ? 2 : 0;
+  }
+  if constexpr (kP <= 2) {
+    const bool up = lane & 2;
+    const float snd = up ? fin[0] : fin[1], kp = up ? fin[1] : fin[0];
+    fin[0] = kp + __shfl_xor_sync(F, snd, 2);
+    // lanes that came in with one value: the lower one keeps it, the upper one holds nothing
+    if (cnt == 1) { cnt = up ? 0 : 1; } else { base += up ? 1 : 0; cnt = 1; }
+  }
+  if constexpr (kP <= 1) {
+    fin[0] += __shfl_xor_sync(F, fin[0], 1);
+    if (lane & 1) cnt = 0;   // the even lane writes
+  }
+}
+
+// kP > 0: the lanes sharing a joint are {l : l % kP == lane % kP} (nj == 4 * kP) and reduce with shuffles;
+// kP == 0: arbitrary joint count, reduction through the per-warp scratch.
+template <bool kSamePixel, int kP, bool kDlc>
 __global__ void __launch_bounds__(kWThreads, 1) softargmax_stream_kernel(
     const float* __restrict__ logits, int B, int H, int W, int nj, float gamma, int radius, float sigma, int chunk_px,
     int cpf, int tw, SaPartial* __restrict__ part) {
@@ -192,9 +249,7 @@ __global__ void __launch_bounds__(kWThreads, 1) softargmax_stream_kernel(
 
   // There is no producer warp and no "empty" barrier: the warp that finishes chunk i refills its stage with chunk
   // i + kWStages right away (it knows the stage is free), so a slow warp never blocks the loads of the others.
-  auto issue_load = [&](int i) {   // one lane
-    const int g = g0 + i;
-    const int b = g / cpf, c = g - b * cpf;
+  auto issue_load_at = [&](int i, int b, int c) {   // one lane
     const int c0 = c * chunk_px, npx = min(chunk_px, HW - c0);
     const int s = i % kWStages;
     const uint32_t bytes = (uint32_t)npx * nj * 4u;
@@ -206,13 +261,15 @@ __global__ void __launch_bounds__(kWThreads, 1) softargmax_stream_kernel(
     issued[s] = i / kWStages + 1;
   };
   if (lane == 0)
-    for (int i = warp; i < min(nloc, kWStages); i += kWWarps) issue_load(i);
+    for (int i = warp; i < min(nloc, kWStages); i += kWWarps) issue_load_at(i, (g0 + i) / cpf, (g0 + i) % cpf);
 
   // -------------------------------------------------------------------- math warps
+  constexpr bool kShfl = kP > 0;
   const float g2 = gamma * 1.4426950408889634f;
   const bool act = lane < tw;
-  int P = nj;                                   // lanes l, l' share their joints iff l == l' (mod P)
-  for (int a = 4, bb = nj; bb;) { const int r = a % bb; a = bb; bb = r; P = nj / a; }
+  int P = kP;                                   // lanes l, l' share their joints iff l == l' (mod P)
+  if (!kShfl)
+    for (int a = 4, bb = nj; bb;) { const int r = a % bb; a = bb; bb = r; P = nj / a; }
   int jq[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) jq[q] = (4 * lane + q) % nj;
@@ -247,6 +304,8 @@ __global__ void __launch_bounds__(kWThreads, 1) softargmax_stream_kernel(
   if (kShfl)
     for (int l = lane % P; l < 32; l += P) cls_mask |= 1u << l;
   const int bslot = lane / P, bcls = lane - (lane / P) * P, blanes = tw / P;   // border pass: pixel slot / granule class
+  const int brr0 = R2 > 0 ? bslot / R2 : 0, bsx0 = R2 > 0 ? bslot - brr0 * R2 : 0;   // side walk: (row offset, side index)
+  const int bdrr = R2 > 0 ? blanes / R2 : 0, bdsx = R2 > 0 ? blanes - bdrr * R2 : 0;
 
   int cb = 0, cc = 0;                            // (frame, chunk in frame) of this warp's current chunk
   if (warp < nloc) { cb = (g0 + warp) / cpf; cc = (g0 + warp) - cb * cpf; }
@@ -340,24 +399,28 @@ __global__ void __launch_bounds__(kWThreads, 1) softargmax_stream_kernel(
         }
         if constexpr (kSamePixel) {
           const f32x2 nm01 = pk2(-m2[0], -m2[1]), nm23 = pk2(-m2[2], -m2[3]);
-          f32x2 s0p0 = pk2(0.0f, 0.0f), s0p1 = s0p0, rc0 = s0p0, rc1 = s0p0, rc2 = s0p0, rc3 = s0p0;
-          f32x2 pos = pk2(prow[0], pcol[0]);
+          const f32x2 zero2 = pk2(0.0f, 0.0f);
+          // sums over joint PAIRS: (s0_0, s0_1), (s0_2, s0_3), likewise the row- and column-weighted ones
+          f32x2 s0a = zero2, s0b = zero2, sra = zero2, srb = zero2, sca = zero2, scb = zero2;
+          f32x2 rr = pk2(prow[0], prow[0]), cc2 = pk2(pcol[0], pcol[0]);   // (row, row), (col, col) of the float4
+          const f32x2 drr = pk2(dPr, dPr), dcc = pk2(dPc, dPc), wrapc = pk2(-Wf, -Wf), one2 = pk2(1.0f, 1.0f);
           float tm0 = -CUDART_INF_F, tm1 = -CUDART_INF_F;
           auto consume = [&](const float4& v) {
-            float t0, t1, t2, t3, pr, pc;
+            float t0, t1, t2, t3, pr, pc, dummy;
             upk2(fma2(pk2(v.x, v.y), g2g2, nm01), t0, t1);
             upk2(fma2(pk2(v.z, v.w), g2g2, nm23), t2, t3);
             if (!kDlc) { tm0 = fmaxf(tm0, fmaxf(t0, t1)); tm1 = fmaxf(tm1, fmaxf(t2, t3)); }
-            const float e0 = ex2_approx(t0), e1 = ex2_approx(t1), e2 = ex2_approx(t2), e3 = ex2_approx(t3);
-            s0p0 = add2(s0p0, pk2(e0, e1));
-            s0p1 = add2(s0p1, pk2(e2, e3));
-            rc0 = fma2(pos, pk2(e0, e0), rc0);
-            rc1 = fma2(pos, pk2(e1, e1), rc1);
-            rc2 = fma2(pos, pk2(e2, e2), rc2);
-            rc3 = fma2(pos, pk2(e3, e3), rc3);
+            const f32x2 ea = pk2(ex2_approx(t0), ex2_approx(t1)), eb = pk2(ex2_approx(t2), ex2_approx(t3));
+            s0a = add2(s0a, ea);
+            s0b = add2(s0b, eb);
+            sra = fma2(ea, rr, sra);
+            srb = fma2(eb, rr, srb);
+            sca = fma2(ea, cc2, sca);
+            scb = fma2(eb, cc2, scb);
             if (kDlc) {
               if ((v.x >= thr[0]) | (v.y >= thr[1]) | (v.z >= thr[2]) | (v.w >= thr[3])) {
-                upk2(pos, pr, pc);
+                upk2(rr, pr, dummy);
+                upk2(cc2, pc, dummy);
                 const int idx = (int)pr * W + (int)pc;
                 const float xs[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -369,9 +432,10 @@ __global__ void __launch_bounds__(kWThreads, 1) softargmax_stream_kernel(
                 }
               }
             }
-            pos = add2(pos, dpos);
-            upk2(pos, pr, pc);
-            if (pc >= Wf) pos = add2(pos, wrapfix);
+            rr = add2(rr, drr);
+            cc2 = add2(cc2, dcc);
+            upk2(cc2, pc, dummy);
+            if (pc >= Wf) { cc2 = add2(cc2, wrapc); rr = add2(rr, one2); }
           };
           int f = lane;
           for (; f + 3 * tw < n4; f += 4 * tw) {
@@ -399,37 +463,43 @@ __global__ void __launch_bounds__(kWThreads, 1) softargmax_stream_kernel(
               float t0, t1, t2, t3, k0, kr, kc;
               upk2(fma2(pk2(v.x, v.y), g2g2, nm01), t0, t1);
               upk2(fma2(pk2(v.z, v.w), g2g2, nm23), t2, t3);
-              const float e0 = ex2_approx(t0), e1 = ex2_approx(t1), e2 = ex2_approx(t2), e3 = ex2_approx(t3);
+              const f32x2 ea = pk2(ex2_approx(t0), ex2_approx(t1)), eb = pk2(ex2_approx(t2), ex2_approx(t3));
               border_corr((float)r, (float)cpx, k0, kr, kc);
-              const f32x2 k00 = pk2(k0, k0), krc = pk2(kr, kc);
-              s0p0 = fma2(pk2(e0, e1), k00, s0p0);
-              s0p1 = fma2(pk2(e2, e3), k00, s0p1);
-              rc0 = fma2(krc, pk2(e0, e0), rc0);
-              rc1 = fma2(krc, pk2(e1, e1), rc1);
-              rc2 = fma2(krc, pk2(e2, e2), rc2);
-              rc3 = fma2(krc, pk2(e3, e3), rc3);
+              const f32x2 k00 = pk2(k0, k0), krr = pk2(kr, kr), kcc = pk2(kc, kc);
+              s0a = fma2(ea, k00, s0a);
+              s0b = fma2(eb, k00, s0b);
+              sra = fma2(ea, krr, sra);
+              srb = fma2(eb, krr, srb);
+              sca = fma2(ea, kcc, sca);
+              scb = fma2(eb, kcc, scb);
             };
-            if (!all_border) {
-              const int nside = (rb - ra + 1) * R2;        // left / right columns of every row of the chunk
-              for (int k = bslot; k < nside; k += blanes) {
-                const int rr = k / R2, sx = k - rr * R2;
-                fix_px(ra + rr, sx < radius ? sx : W - R2 + sx);
+            if (R2 == 0) {
+              // radius 0: the blur is the identity, nothing to correct
+            } else if (!all_border) {
+              // left / right columns of every row of the chunk: item k = slot + n * blanes -> (row k / R2, side k % R2)
+              for (int rq = brr0, sx = bsx0; ra + rq <= rb;) {
+                fix_px(ra + rq, sx < radius ? sx : W - R2 + sx);
+                rq += bdrr; sx += bdsx;
+                if (sx >= R2) { sx -= R2; rq += 1; }
               }
-              for (int r = ra; r <= rb; ++r) {               // top / bottom rows: the span between the side columns
-                if (r >= radius && r < H - radius) continue;
-                for (int cpx = radius + bslot; cpx < W - radius; cpx += blanes) fix_px(r, cpx);
-              }
+              // top / bottom rows: the span between the side columns
+              if (ra < radius)
+                for (int r = ra; r <= min(rb, radius - 1); ++r)
+                  for (int cpx = radius + bslot; cpx < W - radius; cpx += blanes) fix_px(r, cpx);
+              if (rb >= H - radius)
+                for (int r = max(ra, H - radius); r <= rb; ++r)
+                  for (int cpx = radius + bslot; cpx < W - radius; cpx += blanes) fix_px(r, cpx);
             } else {
               for (int r = ra; r <= rb; ++r)
                 for (int cpx = bslot; cpx < W; cpx += blanes) fix_px(r, cpx);
             }
           }
-          upk2(s0p0, s0[0], s0[1]);
-          upk2(s0p1, s0[2], s0[3]);
-          upk2(rc0, sr[0], sc[0]);
-          upk2(rc1, sr[1], sc[1]);
-          upk2(rc2, sr[2], sc[2]);
-          upk2(rc3, sr[3], sc[3]);
+          upk2(s0a, s0[0], s0[1]);
+          upk2(s0b, s0[2], s0[3]);
+          upk2(sra, sr[0], sr[1]);
+          upk2(srb, sr[2], sr[3]);
+          upk2(sca, sc[0], sc[1]);
+          upk2(scb, sc[2], sc[3]);
         } else {
           auto consume = [&](const float4& v) {
             const float xs[4] = {v.x, v.y, v.z, v.w};
@@ -481,31 +551,45 @@ __global__ void __launch_bounds__(kWThreads, 1) softargmax_stream_kernel(
     __syncwarp();
     if (lane == 0 && i + kWStages < nloc) {
       fence_proxy_async_smem();   // order the warp's generic-proxy reads before the async-proxy write
-      issue_load(i + kWStages);
+      int nb = b, nc = c + kWStages;
+      while (nc >= cpf) { nc -= cpf; ++nb; }
+      issue_load_at(i + kWStages, nb, nc);
     }
 
     // ---- reduce over the lanes that share a joint; one partial per (chunk, joint), fixed order -> deterministic
     SaPartial* out = part + ((size_t)b * cpf + c) * nj;
     if constexpr (kShfl) {
-      for (int o = 16; o >= P; o >>= 1) {
+      const float v12[12] = {s0[0], s0[1], s0[2], s0[3], sr[0], sr[1], sr[2], sr[3], sc[0], sc[1], sc[2], sc[3]};
+      float fin[12];
+      int cnt, base;
+      butterfly12<kP>(v12, lane, fin, cnt, base);
+      if (kDlc) {
+        for (int o = 16; o >= kP; o >>= 1) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          s0[q] += __shfl_xor_sync(0xffffffffu, s0[q], o);
-          sr[q] += __shfl_xor_sync(0xffffffffu, sr[q], o);
-          sc[q] += __shfl_xor_sync(0xffffffffu, sc[q], o);
-          if (kDlc) {
+          for (int q = 0; q < 4; ++q) {
             const float obs = __shfl_xor_sync(0xffffffffu, bsig[q], o);
             const int obi = __shfl_xor_sync(0xffffffffu, bidx[q], o);
             if (obs > bsig[q] || (obs == bsig[q] && obi < bidx[q])) { bsig[q] = obs; bidx[q] = obi; }
           }
         }
       }
-      if (lane < P) {
+      // value index vi = 4 * field + q  (field 0: s0, 1: sr, 2: sc) of joint 4 * (lane % kP) + q
+      const int jbase = 4 * (lane % kP);
+#pragma unroll
+      for (int k = 0; k < 12; ++k) {
+        if (k < cnt) {
+          const int vi = base + k;
+          const int fld = vi >> 2, q = vi & 3;
+          reinterpret_cast<float*>(out + jbase + q)[1 + fld] = fin[k];
+        }
+      }
+      if (lane < kP) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          float4* o4 = reinterpret_cast<float4*>(out + jq[q]);
-          o4[0] = make_float4(mout[q], s0[q], sr[q], sc[q]);
-          o4[1] = make_float4(bsig[q], __int_as_float(bidx[q]), 0.0f, 0.0f);
+          float* o = reinterpret_cast<float*>(out + jq[q]);
+          o[0] = mout[q];
+          o[4] = bsig[q];
+          o[5] = __int_as_float(bidx[q]);
         }
       }
     } else {
@@ -748,17 +832,17 @@ int softargmax_splits(int H, int W, int nj) {
   return (H * W + cp - 1) / cp;
 }
 
-template <bool kSamePixel, bool kShfl, bool kDlc>
+template <bool kSamePixel, int kP, bool kDlc>
 static cudaError_t launch_stream(const float* logits, int B, int H, int W, int nj, float gamma, int radius, float sigma,
                                  int chunk_px, int cpf, int tw, SaPartial* ws, int grid, cudaStream_t stream) {
   static bool configured = false;  // per instantiation
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(softargmax_stream_kernel<kSamePixel, kShfl, kDlc>,
+    cudaError_t e = cudaFuncSetAttribute(softargmax_stream_kernel<kSamePixel, kP, kDlc>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWSmemBytes);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  softargmax_stream_kernel<kSamePixel, kShfl, kDlc><<<grid, kWThreads, kWSmemBytes, stream>>>(
+  softargmax_stream_kernel<kSamePixel, kP, kDlc><<<grid, kWThreads, kWSmemBytes, stream>>>(
       logits, B, H, W, nj, gamma, radius, sigma, chunk_px, cpf, tw, ws);
   return cudaGetLastError();
 }
@@ -792,11 +876,24 @@ cudaError_t launch_softargmax(const float* logits, const float* locref, int B, i
   const bool same = nj % 4 == 0;
   const bool shfl = same && (128 % nj == 0);
   cudaError_t e;
-#define DGP_SA_LAUNCH(SP, SH, DL) \
-  launch_stream<SP, SH, DL>(logits, B, H, W, nj, gamma, radius, gauss_len, chunk_px, cpf, tw, workspace, grid, stream)
-  if (shfl) e = dlc ? DGP_SA_LAUNCH(true, true, true) : DGP_SA_LAUNCH(true, true, false);
-  else if (same) e = dlc ? DGP_SA_LAUNCH(true, false, true) : DGP_SA_LAUNCH(true, false, false);
-  else e = dlc ? DGP_SA_LAUNCH(false, false, true) : DGP_SA_LAUNCH(false, false, false);
+#define DGP_SA_LAUNCH(SP, KP, DL) \
+  launch_stream<SP, KP, DL>(logits, B, H, W, nj, gamma, radius, gauss_len, chunk_px, cpf, tw, workspace, grid, stream)
+#define DGP_SA_SHFL(KP) (dlc ? DGP_SA_LAUNCH(true, KP, true) : DGP_SA_LAUNCH(true, KP, false))
+  if (shfl) {
+    switch (nj / 4) {
+      case 1: e = DGP_SA_SHFL(1); break;
+      case 2: e = DGP_SA_SHFL(2); break;
+      case 4: e = DGP_SA_SHFL(4); break;
+      case 8: e = DGP_SA_SHFL(8); break;
+      case 16: e = DGP_SA_SHFL(16); break;
+      default: e = DGP_SA_SHFL(32); break;
+    }
+  } else if (same) {
+    e = dlc ? DGP_SA_LAUNCH(true, 0, true) : DGP_SA_LAUNCH(true, 0, false);
+  } else {
+    e = dlc ? DGP_SA_LAUNCH(false, 0, true) : DGP_SA_LAUNCH(false, 0, false);
+  }
+#undef DGP_SA_SHFL
 #undef DGP_SA_LAUNCH
   if (e != cudaSuccess) return e;
   const int n = B * nj;
