@@ -635,21 +635,32 @@ __global__ void softargmax_finalize_kernel(const float* __restrict__ logits, con
   Acc a;
   acc_init(a);
   for (int sp = lane; sp < splits; sp += 32) {
-    const SaPartial& p = part[((size_t)b * splits + sp) * nj + j];
+    const float4* p4 = reinterpret_cast<const float4*>(part + ((size_t)b * splits + sp) * nj + j);
+    const float4 p0 = __ldg(p4), p1 = __ldg(p4 + 1);
     Acc q;
-    q.m = p.m; q.s0 = p.s0; q.sr = p.sr; q.sc = p.sc; q.bsig = p.bsig; q.bidx = p.bidx;
-    acc_merge(a, q);
+    q.m = p0.x; q.s0 = p0.y; q.sr = p0.z; q.sc = p0.w; q.bsig = p1.x; q.bidx = __float_as_int(p1.y);
+    if (sp < 32) a = q; else acc_merge(a, q);
   }
+  {
+    // one rescale per lane against the warp-wide reference, then plain sums (fixed xor tree -> deterministic)
+    const float m_all = dec_ordered(__reduce_max_sync(0xffffffffu, enc_ordered(a.m)));
+    const float f = (a.m == -CUDART_INF_F) ? 0.0f : exp2f(a.m - m_all);
+    a.s0 *= f; a.sr *= f; a.sc *= f;
+    a.m = m_all;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    Acc q;
-    q.m = __shfl_xor_sync(0xffffffffu, a.m, o);
-    q.s0 = __shfl_xor_sync(0xffffffffu, a.s0, o);
-    q.sr = __shfl_xor_sync(0xffffffffu, a.sr, o);
-    q.sc = __shfl_xor_sync(0xffffffffu, a.sc, o);
-    q.bsig = __shfl_xor_sync(0xffffffffu, a.bsig, o);
-    q.bidx = __shfl_xor_sync(0xffffffffu, a.bidx, o);
-    acc_merge(a, q);
+    for (int o = 16; o > 0; o >>= 1) {
+      a.s0 += __shfl_xor_sync(0xffffffffu, a.s0, o);
+      a.sr += __shfl_xor_sync(0xffffffffu, a.sr, o);
+      a.sc += __shfl_xor_sync(0xffffffffu, a.sc, o);
+    }
+    if (dlc_peak || dlc_pose) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float obs = __shfl_xor_sync(0xffffffffu, a.bsig, o);
+        const int obi = __shfl_xor_sync(0xffffffffu, a.bidx, o);
+        if (obs > a.bsig || (obs == a.bsig && obi < a.bidx)) { a.bsig = obs; a.bidx = obi; }
+      }
+    }
   }
   const float* fr = logits + (size_t)b * H * W * nj + j;
   if (lane != 0) return;
