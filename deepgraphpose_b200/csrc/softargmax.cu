@@ -761,16 +761,39 @@ __global__ void __launch_bounds__(kPotFrames) potentials_kernel(
   const int nload = (t0 + nf < T) ? nf + 1 : nf;    // + first frame of the next CTA's range
   const float* src = mu + (size_t)t0 * nj * 2;
   {
-    // flat coalesced copy with an incrementally maintained (frame, coordinate) pair: no division in the loop and all
-    // of a thread's loads are independent
+    // flat coalesced copy, 128 bits per load and every load of a thread issued before its first use (the staging is
+    // latency-bound otherwise); (frame, coordinate) of each element is maintained incrementally, no division in the loop
     const int rl = 2 * nj;
-    int f = (int)threadIdx.x / rl, c = (int)threadIdx.x - f * rl;
-    const int df = (int)blockDim.x / rl, dc = (int)blockDim.x - df * rl;
-#pragma unroll 8
-    for (int i = threadIdx.x; i < nload * rl; i += blockDim.x) {
-      sm_mu[f * row + c] = src[i];
-      f += df; c += dc;
-      if (c >= rl) { c -= rl; f += 1; }
+    const int total = nload * rl;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    const int n4 = vec_ok ? total / 4 : 0;
+    const float4* src4 = reinterpret_cast<const float4*>(src);
+    constexpr int kU = 9;   // covers (128 + 1) frames x 32 floats with 128 threads in one batch
+    for (int base = 0; base < n4; base += kU * (int)blockDim.x) {
+      float4 v[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int i4 = base + u * (int)blockDim.x + (int)threadIdx.x;
+        if (i4 < n4) v[u] = __ldcs(src4 + i4);
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int i4 = base + u * (int)blockDim.x + (int)threadIdx.x;
+        if (i4 < n4) {
+          const int i = 4 * i4;
+          int f = i / rl, c = i - f * rl;
+          const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            sm_mu[f * row + c] = e[k];
+            if (++c == rl) { c = 0; ++f; }
+          }
+        }
+      }
+    }
+    for (int i = 4 * n4 + (int)threadIdx.x; i < total; i += (int)blockDim.x) {
+      const int f = i / rl;
+      sm_mu[f * row + (i - f * rl)] = src[i];
     }
   }
   const bool have_next_global = (t0 + nf < T);
@@ -810,16 +833,26 @@ __global__ void __launch_bounds__(kPotFrames) potentials_kernel(
   }
   __syncthreads();
   if (temporal) {
-    // rows [t0, t0 + nvalid) of temporal are contiguous in global memory
+    // rows [t0, t0 + nvalid) of temporal are contiguous in global memory: 128-bit coalesced stores
     const int nvalid = (have_next_global || halo_next != nullptr) ? nf : nf - 1;
     float* dst = temporal + (size_t)t0 * nj;
-    int f = (int)threadIdx.x / nj, c = (int)threadIdx.x - f * nj;
-    const int df = (int)blockDim.x / nj, dc = (int)blockDim.x - df * nj;
-#pragma unroll 4
-    for (int i = threadIdx.x; i < nvalid * nj; i += blockDim.x) {
-      dst[i] = sm_t[f * (nj + 1) + c];
-      f += df; c += dc;
-      if (c >= nj) { c -= nj; f += 1; }
+    const int total = nvalid * nj;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+    const int n4 = vec_ok ? total / 4 : 0;
+    for (int i4 = threadIdx.x; i4 < n4; i4 += blockDim.x) {
+      const int i = 4 * i4;
+      int f = i / nj, c = i - f * nj;
+      float e[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        e[k] = sm_t[f * (nj + 1) + c];
+        if (++c == nj) { c = 0; ++f; }
+      }
+      __stcs(reinterpret_cast<float4*>(dst) + i4, make_float4(e[0], e[1], e[2], e[3]));
+    }
+    for (int i = 4 * n4 + (int)threadIdx.x; i < total; i += (int)blockDim.x) {
+      const int f = i / nj;
+      dst[i] = sm_t[f * (nj + 1) + (i - f * nj)];
     }
   }
 }
