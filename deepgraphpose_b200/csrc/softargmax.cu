@@ -756,6 +756,13 @@ __global__ void __launch_bounds__(kPotFrames) potentials_kernel(
   const int row = 2 * nj + 1;                       // +1: conflict-free column walks
   float* sm_mu = psm;                               // [kPotFrames + 1][row]
   float* sm_t = psm + (kPotFrames + 1) * row;       // [kPotFrames][nj + 1]
+  const int tab_off = ((kPotFrames + 1) * row + kPotFrames * (nj + 1) + 1) & ~1;   // 8-byte aligned
+  int2* sm_edge = reinterpret_cast<int2*>(psm + tab_off);   // [nl] (2a, 2b)
+  float2* sm_w = reinterpret_cast<float2*>(sm_edge + nl);                                                 // [nl] (ws, ws_max)
+  for (int l = threadIdx.x; l < nl; l += blockDim.x) {
+    sm_edge[l] = make_int2(2 * __ldg(edges + 2 * l), 2 * __ldg(edges + 2 * l + 1));
+    sm_w[l] = ws ? make_float2(__ldg(ws + l), __ldg(ws_max + l)) : make_float2(0.0f, 0.0f);
+  }
   const int t0 = blockIdx.x * kPotFrames;
   const int nf = min(kPotFrames, T - t0);
   const int nload = (t0 + nf < T) ? nf + 1 : nf;    // + first frame of the next CTA's range
@@ -785,7 +792,7 @@ __global__ void __launch_bounds__(kPotFrames) potentials_kernel(
           const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            sm_mu[f * row + c] = e[k];
+            sm_mu[f * row + c] = e[k] * stride + 0.5f * stride;
             if (++c == rl) { c = 0; ++f; }
           }
         }
@@ -793,12 +800,12 @@ __global__ void __launch_bounds__(kPotFrames) potentials_kernel(
     }
     for (int i = 4 * n4 + (int)threadIdx.x; i < total; i += (int)blockDim.x) {
       const int f = i / rl;
-      sm_mu[f * row + (i - f * rl)] = src[i];
+      sm_mu[f * row + (i - f * rl)] = src[i] * stride + 0.5f * stride;
     }
   }
   const bool have_next_global = (t0 + nf < T);
   if (!have_next_global && halo_next != nullptr)
-    for (int i = threadIdx.x; i < 2 * nj; i += blockDim.x) sm_mu[nf * row + i] = halo_next[i];
+    for (int i = threadIdx.x; i < 2 * nj; i += blockDim.x) sm_mu[nf * row + i] = halo_next[i] * stride + 0.5f * stride;
   __syncthreads();
   const int lt = threadIdx.x;
   const int t = t0 + lt;
@@ -806,25 +813,29 @@ __global__ void __launch_bounds__(kPotFrames) potentials_kernel(
   const bool has_next = active && (lt + 1 < nf || have_next_global || halo_next != nullptr);
   if (active) {
     const float* m = sm_mu + lt * row;
+    // sm_mu holds S-space coordinates mu * stride + stride / 2 (the reference's order of operations)
     float es = 0.0f;
     for (int l = 0; l < nl; ++l) {
-      const int a = __ldg(edges + 2 * l), b = __ldg(edges + 2 * l + 1);
-      // S (mu*stride + stride/2): keep the reference's order of operations
-      const float dr = (m[2 * a] * stride + 0.5f * stride) - (m[2 * b] * stride + 0.5f * stride);
-      const float dc = (m[2 * a + 1] * stride + 0.5f * stride) - (m[2 * b + 1] * stride + 0.5f * stride);
+      const int2 ab = sm_edge[l];
+      const float dr = m[ab.x] - m[ab.y];
+      const float dc = m[ab.x + 1] - m[ab.y + 1];
       const float d = sqrtf(dr * dr + dc * dc);
       if (skel) skel[(size_t)l * T + t] = d;
-      if (ws) es += __ldg(ws + l) * (fmaxf(d - __ldg(ws_max + l), 0.0f) + __ldg(ws_max + l));
+      if (ws) {
+        const float2 w = sm_w[l];
+        es += w.x * (fmaxf(d - w.y, 0.0f) + w.y);
+      }
     }
     if (e_skel) e_skel[t] = es;
     float et = 0.0f;
     if (has_next) {
       const float* mn = m + row;
+      float* trow = sm_t + lt * (nj + 1);
       for (int j = 0; j < nj; ++j) {
-        const float dr = (m[2 * j] * stride + 0.5f * stride) - (mn[2 * j] * stride + 0.5f * stride);
-        const float dc = (m[2 * j + 1] * stride + 0.5f * stride) - (mn[2 * j + 1] * stride + 0.5f * stride);
+        const float dr = m[2 * j] - mn[2 * j];
+        const float dc = m[2 * j + 1] - mn[2 * j + 1];
         const float d = sqrtf(dr * dr + dc * dc);
-        sm_t[lt * (nj + 1) + j] = d;
+        trow[j] = d;
         const float dth = fmaxf(d - wt_max, 0.0f) + wt_max;
         et += dth * dth;
       }
@@ -971,7 +982,8 @@ cudaError_t launch_potentials(const float* mu, const float* halo_next, int T, in
                               float stride, const float* ws, const float* ws_max, float wt_max, float* skel,
                               float* temporal, float* e_skel, float* e_temp, cudaStream_t stream) {
   if (T <= 0) return cudaSuccess;
-  const size_t smem = ((size_t)(kPotFrames + 1) * (2 * nj + 1) + (size_t)kPotFrames * (nj + 1)) * sizeof(float);
+  const size_t smem = ((size_t)(kPotFrames + 1) * (2 * nj + 1) + (size_t)kPotFrames * (nj + 1) + 2) * sizeof(float) +
+                      (size_t)nl * (sizeof(int2) + sizeof(float2));
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(potentials_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
