@@ -776,6 +776,11 @@ __global__ void __launch_bounds__(kPotFrames) potentials_kernel(
     const int n4 = vec_ok ? total / 4 : 0;
     const float4* src4 = reinterpret_cast<const float4*>(src);
     constexpr int kU = 9;   // covers (128 + 1) frames x 32 floats with 128 threads in one batch
+    // (frame, coordinate) of a thread's float4s advance by a fixed (df, dc) per step: one division per thread
+    const int step = 4 * (int)blockDim.x;
+    const int df = step / rl, dc = step - df * rl;
+    int f = (4 * (int)threadIdx.x) / rl, c = 4 * (int)threadIdx.x - f * rl;
+    const bool rows_whole = (rl & 3) == 0;   // a float4 never straddles two frames
     for (int base = 0; base < n4; base += kU * (int)blockDim.x) {
       float4 v[kU];
 #pragma unroll
@@ -787,15 +792,22 @@ __global__ void __launch_bounds__(kPotFrames) potentials_kernel(
       for (int u = 0; u < kU; ++u) {
         const int i4 = base + u * (int)blockDim.x + (int)threadIdx.x;
         if (i4 < n4) {
-          const int i = 4 * i4;
-          int f = i / rl, c = i - f * rl;
           const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+          float* d = sm_mu + f * row + c;
+          if (rows_whole) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            sm_mu[f * row + c] = e[k] * stride + 0.5f * stride;
-            if (++c == rl) { c = 0; ++f; }
+            for (int k = 0; k < 4; ++k) d[k] = e[k] * stride + 0.5f * stride;
+          } else {
+            int ff = f, cc = c;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              sm_mu[ff * row + cc] = e[k] * stride + 0.5f * stride;
+              if (++cc == rl) { cc = 0; ++ff; }
+            }
           }
         }
+        f += df; c += dc;
+        if (c >= rl) { c -= rl; ++f; }
       }
     }
     for (int i = 4 * n4 + (int)threadIdx.x; i < total; i += (int)blockDim.x) {
@@ -850,16 +862,27 @@ __global__ void __launch_bounds__(kPotFrames) potentials_kernel(
     const int total = nvalid * nj;
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
     const int n4 = vec_ok ? total / 4 : 0;
+    const int step = 4 * (int)blockDim.x;
+    const int df = step / nj, dc = step - df * nj;
+    int f = (4 * (int)threadIdx.x) / nj, c = 4 * (int)threadIdx.x - f * nj;
+    const bool rows_whole = (nj & 3) == 0;
     for (int i4 = threadIdx.x; i4 < n4; i4 += blockDim.x) {
-      const int i = 4 * i4;
-      int f = i / nj, c = i - f * nj;
       float e[4];
+      const float* srow = sm_t + f * (nj + 1) + c;
+      if (rows_whole) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        e[k] = sm_t[f * (nj + 1) + c];
-        if (++c == nj) { c = 0; ++f; }
+        for (int k = 0; k < 4; ++k) e[k] = srow[k];
+      } else {
+        int ff = f, cc = c;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          e[k] = sm_t[ff * (nj + 1) + cc];
+          if (++cc == nj) { cc = 0; ++ff; }
+        }
       }
       __stcs(reinterpret_cast<float4*>(dst) + i4, make_float4(e[0], e[1], e[2], e[3]));
+      f += df; c += dc;
+      if (c >= nj) { c -= nj; ++f; }
     }
     for (int i = 4 * n4 + (int)threadIdx.x; i < total; i += (int)blockDim.x) {
       const int f = i / nj;
