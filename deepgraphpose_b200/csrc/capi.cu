@@ -825,6 +825,8 @@ int dgp_softargmax(dgp_handle* h, const float* logits_dev, const float* locref_d
   if (gauss_len < 1.0f || gauss_len >= 5.0f) return fail(h, DGP_ERR_INVALID, "dgp_softargmax: gauss_len must be in [1, 5)");
   if (!(gamma > 0.0f)) return fail(h, DGP_ERR_INVALID, "dgp_softargmax: gamma must be > 0");
   if (((uintptr_t)logits_dev & 15) != 0) return fail(h, DGP_ERR_INVALID, "dgp_softargmax: logits must be 16-byte aligned");
+  if (nj > 128 || softargmax_tact(nj) <= 0)
+    return fail(h, DGP_ERR_UNSUPPORTED, "dgp_softargmax: num_joints must be <= 128 with num_joints / gcd(num_joints, 4) <= 32");
   CU_OK(h, cudaSetDevice(h->device));
   const int splits = softargmax_splits(H, W, nj);
   const size_t need = (size_t)B * splits * nj * sizeof(SaPartial);

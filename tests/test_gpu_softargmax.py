@@ -98,6 +98,75 @@ def test_softargmax_large_logits_no_overflow(eng):
     assert (out["mu"].cpu() - mu_ref).abs().max().item() < MU_TOL_PX
 
 
+@pytest.mark.parametrize("shape", [(3, 30, 38, 4, 3.0), (2, 94, 104, 5, 4.0), (2, 60, 80, 20, 2.0), (1, 128, 160, 16, 6.0),
+                                   (2, 20, 24, 8, 3.0), (2, 20, 24, 12, 3.0), (1, 16, 20, 32, 3.0), (1, 8, 12, 64, 3.0),
+                                   (1, 8, 12, 128, 3.0), (2, 30, 38, 3, 30.0), (1, 2, 2, 1, 1.0), (2, 6, 4, 7, 2.0)])
+def test_softargmax_estimate_pose_readout_only(eng, shape):
+    """The path estimate_pose takes (no DLC peak wanted): speculative single pass against the fixed reference 0, every
+    joint-count family of the kernel (shuffle classes 4..128, scratch reduction for 12 / 20, generic 1 / 3 / 5 / 7)."""
+    B, H, W, nj, scale = shape
+    rng = np.random.default_rng(B * 77 + nj)
+    logits = make_logits(rng, B, H, W, nj, scale)
+    lt = torch.from_numpy(logits)
+    mu_ref, _ = dgp_ops.argmax_2d_from_cm(lt, nj, 1.0, 1.0)
+    out = eng.softargmax(lt.cuda(), None, 1.0, 1.0, want=("mu", "peak", "lik"))
+    mu = out["mu"].cpu()
+    assert (mu - mu_ref).abs().max().item() < MU_TOL_PX
+    for b in range(B):
+        _, pk, lk = dgp_ops.estimate_pose_readout(mu[b:b + 1].numpy(), logits[b:b + 1])
+        assert (pk == out["peak"][b].cpu().numpy()).all()
+        assert np.allclose(lk, out["lik"][b].cpu().numpy(), atol=1e-6, equal_nan=True)
+    # and the two kernel variants agree on mu
+    mu_dlc = eng.softargmax(lt.cuda(), None, 1.0, 1.0, want=("mu", "dlc_peak"))["mu"].cpu()
+    assert (mu - mu_dlc).abs().max().item() < MU_TOL_PX
+
+
+@pytest.mark.parametrize("gauss_len", [1.0, 2.0, 3.0, 4.0])
+def test_softargmax_blur_radius_border(eng, gauss_len):
+    """Peaks sitting on the edges: the zero-padded blur + renormalisation bias must match for every radius."""
+    rng = np.random.default_rng(int(gauss_len))
+    H, W, nj = 20, 26, 4
+    x = (rng.standard_normal((3, H, W, nj)) * 0.5).astype(np.float32)
+    x[0, 0, 0, 0] += 9; x[0, H - 1, W - 1, 1] += 9; x[0, 0, W - 1, 2] += 9; x[0, H - 1, 0, 3] += 9
+    x[1, 1, 5, 0] += 9; x[1, H - 2, 7, 1] += 9; x[1, 9, 1, 2] += 9; x[1, 11, W - 2, 3] += 9
+    lt = torch.from_numpy(x)
+    mu_ref, _ = dgp_ops.argmax_2d_from_cm(lt, nj, 1.0, gauss_len)
+    for want in (("mu", "peak", "lik"), ("mu", "dlc_peak")):
+        mu = eng.softargmax(lt.cuda(), None, 1.0, gauss_len, want=want)["mu"].cpu()
+        assert (mu - mu_ref).abs().max().item() < MU_TOL_PX
+
+
+def test_softargmax_out_of_range_exponents_take_the_exact_pass(eng):
+    """|logit * gamma * log2(e)| > 90 leaves the speculative pass's safe range: the kernel must redo the chunk against
+    the true maximum (and an all -inf joint / a NaN must come out as NaN, like the reference)."""
+    rng = np.random.default_rng(3)
+    logits = make_logits(rng, 2, 10, 12, 4, 200.0)   # |x| up to ~1000
+    logits[1, :, :, 2] = -500.0 + rng.standard_normal((10, 12)).astype(np.float32)   # everything far below 2^-90
+    lt = torch.from_numpy(logits)
+    mu_ref, _ = dgp_ops.argmax_2d_from_cm(lt, 4, 1.0, 1.0)
+    out = eng.softargmax(lt.cuda(), None, 1.0, 1.0, want=("mu", "peak", "lik"))
+    assert torch.isfinite(out["mu"]).all()
+    assert (out["mu"].cpu() - mu_ref).abs().max().item() < MU_TOL_PX
+    bad = logits.copy()
+    bad[0, :, :, 1] = -np.inf
+    bad[1, 3, 4, 0] = np.nan
+    mu = eng.softargmax(torch.from_numpy(bad).cuda(), None, 1.0, 1.0, want=("mu",))["mu"].cpu()
+    assert torch.isnan(mu[0, 1]).all() and torch.isnan(mu[1, 0]).all()
+    assert torch.isfinite(mu[0, 0]).all() and torch.isfinite(mu[1, 1]).all()
+
+
+def test_softargmax_is_bitwise_batch_invariant(eng):
+    """The chunking depends on the map shape only: a frame's result does not depend on its batch or its position in it."""
+    rng = np.random.default_rng(11)
+    logits = torch.from_numpy(make_logits(rng, 9, 94, 104, 4, 3.0)).cuda()
+    full = eng.softargmax(logits, None, 1.0, 1.0, want=("mu", "peak", "lik"))
+    for b in (0, 4, 8):
+        one = eng.softargmax(logits[b:b + 1].contiguous(), None, 1.0, 1.0, want=("mu", "peak", "lik"))
+        assert torch.equal(one["mu"][0], full["mu"][b]) and torch.equal(one["lik"][0], full["lik"][b])
+    part = eng.softargmax(logits[3:8].contiguous(), None, 1.0, 1.0, want=("mu",))
+    assert torch.equal(part["mu"], full["mu"][3:8])
+
+
 def test_softmax_map_matches_oracle(eng):
     rng = np.random.default_rng(9)
     logits = make_logits(rng, 2, 20, 24, 5, 2.0)
@@ -119,6 +188,10 @@ def test_softargmax_argument_errors(eng):
     with pytest.raises(ValueError):
         eng.softargmax(torch.zeros(1, 6, 6, 2))                          # not on the GPU
     assert eng.softargmax(torch.zeros(0, 6, 6, 2, device="cuda"))["mu"].shape == (0, 2, 2)   # empty batch
+    with pytest.raises(DgpError):
+        eng.softargmax(torch.zeros(1, 6, 6, 33, device="cuda"))         # 33 joints: no lane mapping with a fixed joint
+    with pytest.raises(DgpError):
+        eng.softargmax(torch.zeros(1, 6, 6, 132, device="cuda"))        # > 128 joints
 
 
 def test_potentials_and_halo(eng):
