@@ -69,6 +69,7 @@ SIGNATURES = {
     "dgp_debug_get_activation": (_i, [_vp, C.c_char_p, _vp, _sz, _i64p]),
     "dgp_conv2d": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp,
                         _i, _i, _vp]),
+    "dgp_conv2d_wgrad": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "dgp_set_profiling": (_i, [_vp, _i]),
     "dgp_get_profile": (_i, [_vp, C.POINTER(C.c_double), _i64p, _i]),
     "dgp_launch_count": (C.c_int64, [_vp]),

@@ -369,6 +369,36 @@ int setup_epilogue(dgp_handle* h, ConvGemmParams& g, const char* scope, int n_im
   return DGP_OK;
 }
 
+// Output size and padding of one conv: pad_mode 0 = TF SAME, 1 = slim conv2d_same (explicit pad + VALID), 2 = VALID.
+void conv_geometry(int R, int S, int stride, int dil, int H, int W, int pad_mode, int* Pout, int* Qout, int* lower_h_,
+                   int* lower_w_, int* upper_h_, int* upper_w_) {
+  int P, Q, lower_h = 0, lower_w = 0, upper_h = 0, upper_w = 0;
+  const int keff_h = (R - 1) * dil + 1, keff_w = (S - 1) * dil + 1;
+  if (pad_mode == 0) {  // TF SAME
+    same_pad(H, R, stride, dil, &lower_h, &P);
+    same_pad(W, S, stride, dil, &lower_w, &Q);
+    const int tot_h = (P - 1) * stride + keff_h - H, tot_w = (Q - 1) * stride + keff_w - W;
+    upper_h = (tot_h > 0 ? tot_h : 0) - lower_h;
+    upper_w = (tot_w > 0 ? tot_w : 0) - lower_w;
+  } else if (pad_mode == 1) {  // slim conv2d_same: explicit (keff-1) padding, beg = (keff-1)/2, then VALID
+    if (stride == 1) {
+      same_pad(H, R, 1, dil, &lower_h, &P);
+      same_pad(W, S, 1, dil, &lower_w, &Q);
+      upper_h = (keff_h - 1) - lower_h;
+      upper_w = (keff_w - 1) - lower_w;
+    } else {
+      lower_h = (keff_h - 1) / 2; upper_h = (keff_h - 1) - lower_h;
+      lower_w = (keff_w - 1) / 2; upper_w = (keff_w - 1) - lower_w;
+      P = (H + keff_h - 1 - keff_h) / stride + 1;
+      Q = (W + keff_w - 1 - keff_w) / stride + 1;
+    }
+  } else {  // VALID
+    P = (H - keff_h) / stride + 1;
+    Q = (W - keff_w) / stride + 1;
+  }
+  *Pout = P; *Qout = Q; *lower_h_ = lower_h; *lower_w_ = lower_w; *upper_h_ = upper_h; *upper_w_ = upper_w;
+}
+
 // Fill the GEMM params of one conv layer. x: input NHWC bf16 (N,H,W,Cin). Returns output dims via Ho/Wo.
 int make_gemm_step(dgp_handle* h, const ConvLayer& L, const void* x, int N, int H, int W, int pad_mode, void* out,
                    bool out_f32, const __nv_bfloat16* residual, int res_sub, int res_H, int res_W, int block_n_override,
@@ -378,29 +408,7 @@ int make_gemm_step(dgp_handle* h, const ConvLayer& L, const void* x, int N, int 
   g.fp16 = h->fp16;
   tmap_set_fp16(h->fp16);
   int P, Q, lower_h = 0, lower_w = 0, upper_h = 0, upper_w = 0;
-  const int keff_h = (L.R - 1) * L.dil + 1, keff_w = (L.S - 1) * L.dil + 1;
-  if (pad_mode == 0) {  // TF SAME
-    same_pad(H, L.R, L.stride, L.dil, &lower_h, &P);
-    same_pad(W, L.S, L.stride, L.dil, &lower_w, &Q);
-    const int tot_h = (P - 1) * L.stride + keff_h - H, tot_w = (Q - 1) * L.stride + keff_w - W;
-    upper_h = (tot_h > 0 ? tot_h : 0) - lower_h;
-    upper_w = (tot_w > 0 ? tot_w : 0) - lower_w;
-  } else if (pad_mode == 1) {  // slim conv2d_same: explicit (keff-1) padding, beg = (keff-1)/2, then VALID
-    if (L.stride == 1) {
-      same_pad(H, L.R, 1, L.dil, &lower_h, &P);
-      same_pad(W, L.S, 1, L.dil, &lower_w, &Q);
-      upper_h = (keff_h - 1) - lower_h;
-      upper_w = (keff_w - 1) - lower_w;
-    } else {
-      lower_h = (keff_h - 1) / 2; upper_h = (keff_h - 1) - lower_h;
-      lower_w = (keff_w - 1) / 2; upper_w = (keff_w - 1) - lower_w;
-      P = (H + keff_h - 1 - keff_h) / L.stride + 1;
-      Q = (W + keff_w - 1 - keff_w) / L.stride + 1;
-    }
-  } else {  // VALID
-    P = (H - keff_h) / L.stride + 1;
-    Q = (W - keff_w) / L.stride + 1;
-  }
+  conv_geometry(L.R, L.S, L.stride, L.dil, H, W, pad_mode, &P, &Q, &lower_h, &lower_w, &upper_h, &upper_w);
   *Ho = P;
   *Wo = Q;
   const int bn = block_n_override > 0 ? block_n_override : L.block_n;
@@ -439,6 +447,36 @@ int make_gemm_step(dgp_handle* h, const ConvLayer& L, const void* x, int N, int 
   st->kind = STEP_GEMM;
   st->out_ptr = out;
   st->oN = N; st->oH = P; st->oW = Q; st->oC = L.Npad;
+  return DGP_OK;
+}
+
+// Weight-gradient GEMM params of one conv: x NHWC (N,H,W,Cin), dy (N,P,Q,Cout) 16-bit; the im2col geometry is the forward's.
+int make_wgrad_params(dgp_handle* h, const char* scope, int R, int S, int Cin, int Cout, int stride, int dil,
+                      const void* x, int N, int H, int W, int pad_mode, const void* dy, WgradParams* wp) {
+  memset(wp, 0, sizeof(*wp));
+  tmap_set_fp16(h->fp16);
+  wp->fp16 = h->fp16;
+  int P, Q, lower_h, lower_w, upper_h, upper_w;
+  conv_geometry(R, S, stride, dil, H, W, pad_mode, &P, &Q, &lower_h, &lower_w, &upper_h, &upper_w);
+  const int M = N * P * Q;
+  wp->Cout = Cout; wp->Kw = R * S * Cin;
+  wp->num_pix_blocks = ceil_div(M, 64);
+  wp->P = P; wp->Q = Q; wp->conv_stride = stride; wp->lower_h = -lower_h; wp->lower_w = -lower_w;
+  wp->S = S; wp->dil = dil; wp->cblocks = Cin / 64;
+  const char* e = make_tmap_2d(&wp->tmap_dy, dy, (uint64_t)M, (uint64_t)Cout, (uint64_t)Cout * 2, 64);
+  if (e) return fail(h, DGP_ERR_CUDA, "%s wgrad (dy map): %s", scope, e);
+  if (R == 1 && S == 1 && stride == 1) {
+    wp->x_mode = 0;
+    e = make_tmap_2d(&wp->tmap_x, x, (uint64_t)M, (uint64_t)Cin, (uint64_t)Cin * 2, 64);
+  } else {
+    wp->x_mode = 1;
+    const int up_h = upper_h - (R - 1) * dil, up_w = upper_w - (S - 1) * dil;
+    e = make_tmap_im2col(&wp->tmap_x, x, (uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N, (uint64_t)Cin * 2,
+                         (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2, -lower_w, -lower_h, up_w, up_h, stride,
+                         (uint64_t)N * H * W * Cin * 2, 64);
+  }
+  if (e) return fail(h, DGP_ERR_CUDA, "%s wgrad (x map): %s", scope, e);
+  wgrad_plan(wp, h->num_sms);
   return DGP_OK;
 }
 
@@ -1091,6 +1129,28 @@ int dgp_conv2d(dgp_handle* h, const void* x_dev, int N, int H, int W, int Cin, c
   cudaFree(L.scale);
   cudaFree(L.shift);
   return rc;
+}
+
+int dgp_conv2d_wgrad(dgp_handle* h, const void* x_dev, int N, int H, int W, int Cin, const void* dy_dev, int R, int S,
+                     int Cout, int stride, int dilation, int pad_mode, float* dw_dev, const int32_t* dbg3, void* stream) {
+  if (!h) return DGP_ERR_INVALID;
+  if (!x_dev || !dy_dev || !dw_dev) return fail(h, DGP_ERR_INVALID, "dgp_conv2d_wgrad: null argument");
+  if (Cin % 64 || Cout % 8) return fail(h, DGP_ERR_UNSUPPORTED, "dgp_conv2d_wgrad: Cin must be a multiple of 64 and Cout of 8");
+  CU_OK(h, cudaSetDevice(h->device));
+  WgradParams wp;
+  int rc = make_wgrad_params(h, "dgp_conv2d_wgrad", R, S, Cin, Cout, stride, dilation, x_dev, N, H, W, pad_mode, dy_dev, &wp);
+  if (rc) return rc;
+  if (dbg3) { wp.dbg_lbo = (uint32_t)dbg3[0]; wp.dbg_sbo = (uint32_t)dbg3[1]; wp.dbg_kstep = (uint32_t)dbg3[2]; }
+  void* ws = nullptr;
+  CU_OK(h, cudaMalloc(&ws, wgrad_workspace_bytes(wp)));
+  wp.partials = (float*)ws;
+  cudaError_t e = launch_wgrad_gemm(wp, h->num_sms, (cudaStream_t)stream);
+  if (e == cudaSuccess) e = launch_wgrad_reduce(wp, nullptr, nullptr, dw_dev, 0, (cudaStream_t)stream);
+  h->launches += 2;
+  if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+  cudaFree(ws);
+  if (e != cudaSuccess) return fail(h, DGP_ERR_CUDA, "dgp_conv2d_wgrad launch: %s", cudaGetErrorString(e));
+  return DGP_OK;
 }
 
 int dgp_set_profiling(dgp_handle* h, int enable) {

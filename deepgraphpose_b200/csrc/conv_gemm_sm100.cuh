@@ -62,6 +62,26 @@ struct ConvGemmParams {
   int tmem_cols;     // power of two >= 2 * block_n
 };
 
+// Weight-gradient GEMM (wgrad_gemm_sm100.cu): dW[co, kk] = sum_p dy[p, co] * xcol[p, kk], kk = (tap, ci).
+struct WgradParams {
+  CUtensorMap tmap_dy;  // [pixels, Cout] 16-bit, box 64 ch x 64 pixels, SWIZZLE_128B (rows/cols past the end read as zero)
+  CUtensorMap tmap_x;   // x_mode 0: [pixels, Cin] tiled; x_mode 1: im2col (same geometry as the forward conv), 64 pixels per column
+  int Cout, Kw;         // gradient matrix [Cout][Kw], Kw = taps * Cin (multiple of 64)
+  int num_pix_blocks;   // ceil(pixels / 64)
+  int x_mode;
+  int fp16;
+  int P, Q, conv_stride, lower_h, lower_w, S, dil, cblocks;  // im2col geometry (x_mode 1); cblocks = Cin / 64
+  int num_m_blocks, num_n_blocks, splits, kb_per_split;      // filled by wgrad_plan
+  float* partials;      // workspace: [num_m_blocks * num_n_blocks * splits][128][256] fp32
+  uint32_t dbg_lbo, dbg_sbo, dbg_kstep;  // 0 = defaults (descriptor bring-up hooks)
+};
+void wgrad_plan(WgradParams* p, int num_sms);
+size_t wgrad_workspace_bytes(const WgradParams& p);
+cudaError_t launch_wgrad_gemm(const WgradParams& p, int num_sms, cudaStream_t stream);
+// grad[co][kk] (=|+=) rowscale[co] * mask[co][kk] * sum over splits (fixed order); rowscale / mask may be null.
+cudaError_t launch_wgrad_reduce(const WgradParams& p, const float* rowscale, const float* mask, float* grad,
+                                int accumulate, cudaStream_t stream);
+
 // Host helpers (conv_gemm_sm100.cu)
 void tmap_set_fp16(int fp16);  // element type of subsequently encoded tensor maps
 const char* tma_init();  // resolves the driver's tensor-map encoders; returns nullptr on success, else an error string

@@ -266,6 +266,21 @@ class Engine:
             _ptr(residual), res_sub, res_H, res_W, int(relu), _ptr(out), int(out_f32), int(block_n), _stream(x.device)))
         return out
 
+    def conv2d_wgrad(self, x, dy, R, stride=1, dilation=1, pad_mode=0, dbg=None):
+        """Weight gradient of one conv through the tcgen05 wgrad GEMM: x (N,H,W,Cin), dy (N,P,Q,Cout) 16-bit NHWC ->
+        float32 (Cout, R*R*Cin) in the kernel's weight layout (tap-major, then input channel)."""
+        x = x.contiguous()
+        dy = dy.contiguous()
+        N, H, W, Cin = x.shape
+        Cout = dy.shape[-1]
+        if x.dtype != self.act_dtype or dy.dtype != self.act_dtype:
+            raise ValueError("x and dy must be %s for this engine" % self.act_dtype)
+        dw = torch.empty((Cout, R * R * Cin), dtype=torch.float32, device=x.device)
+        d3 = (C.c_int32 * 3)(*[int(v) for v in dbg]) if dbg is not None else None
+        self._check(self.lib.dgp_conv2d_wgrad(self.h, _ptr(x), N, H, W, Cin, _ptr(dy), R, R, Cout, stride, dilation, pad_mode,
+                                              _ptr(dw), d3, _stream(x.device)))
+        return dw
+
     PROFILE_KINDS = ("prep_s2d", "conv_gemm", "maxpool", "deconv_col2im", "softargmax")
 
     def set_profiling(self, enable=True):

@@ -169,6 +169,11 @@ int dgp_conv2d(dgp_handle* h, const void* x_dev, int N, int H, int W, int Cin, c
                int Cout, int stride, int dilation, int pad_mode, const float* scale_host, const float* shift_host,
                const void* residual_dev, int res_sub, int res_H, int res_W, int relu, void* out_dev, int out_f32,
                int block_n, void* stream);
+/* Weight gradient of one conv layer through the tcgen05 wgrad GEMM (unit tests): x_dev (N,H,W,Cin) and dy_dev
+ * (N,P,Q,Cout) 16-bit NHWC; dw_dev float32 [Cout][R*S*Cin] (the kernel's weight layout, tap-major then channel).
+ * dbg3 = NULL, or 3 descriptor overrides {LBO, SBO, k-step bytes} (0 = default) used during bring-up. */
+int dgp_conv2d_wgrad(dgp_handle* h, const void* x_dev, int N, int H, int W, int Cin, const void* dy_dev, int R, int S,
+                     int Cout, int stride, int dilation, int pad_mode, float* dw_dev, const int32_t* dbg3, void* stream);
 /* CUDA-event timing per kernel family, recorded on the launching stream around every launch while enabled.
  * kinds: 0 = u8->bf16 space-to-depth prep, 1 = tcgen05 conv GEMM, 2 = max-pool, 3 = deconv col2im, 4 = soft-argmax.
  * dgp_get_profile synchronises the device, sums the elapsed ms and launch counts per kind and clears the records. */
