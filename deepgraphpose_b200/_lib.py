@@ -70,6 +70,13 @@ SIGNATURES = {
     "dgp_conv2d": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp,
                         _i, _i, _vp]),
     "dgp_conv2d_wgrad": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "dgp_train_enable": (_i, [_vp]),
+    "dgp_train_forward_backward": (_i, [_vp, _vp, _i, _i, _i, C.POINTER(DgpLossCfg), C.POINTER(DgpLossBatch), _i, _vp, _vp]),
+    "dgp_optimizer_step": (_i, [_vp, _f, _f, _f, _f, _vp]),
+    "dgp_get_grad_buffer": (_i, [_vp, C.POINTER(_vp), C.POINTER(_sz)]),
+    "dgp_get_grad_norm": (_i, [_vp, C.POINTER(_f)]),
+    "dgp_train_outputs": (_i, [_vp, _i, _i, _i, C.POINTER(_vp), C.POINTER(_vp)]),
+    "dgp_get_variable": (_i, [_vp, C.c_char_p, _i, _vp, _sz, _i64p, C.POINTER(_i)]),
     "dgp_set_profiling": (_i, [_vp, _i]),
     "dgp_get_profile": (_i, [_vp, C.POINTER(C.c_double), _i64p, _i]),
     "dgp_launch_count": (C.c_int64, [_vp]),

@@ -1,0 +1,343 @@
+// Bandwidth-class kernels of the network backward pass (sm_100a); the GEMM-shaped parts (dgrad, wgrad) run on
+// conv_gemm_sm100.cu / wgrad_gemm_sm100.cu.  Reference: the gradients TF derives for
+// optimizer.compute_gradients(total_loss, TF.trainable_variables()) (src/deepgraphpose/models/fitdgp.py:706-713) through
+// slim resnet_v1_50 with is_training=False (frozen moving statistics; gamma, beta and conv weights trainable).
+//
+//   relu_bn_bwd   : dy = g * [a > 0] in place, plus the per-channel sums the frozen-BN parameter gradients need
+//                   (dbeta = sum dy, dgamma = sum dy * (y - beta) / gamma with y the BN output, recovered from the
+//                   stored post-ReLU activation where the mask is open).  At a bottleneck junction
+//                   out = relu(shortcut + bn3(conv3)) the same pass yields conv3's and the projection shortcut's sums.
+//   maxpool_bwd   : gradient of slim.max_pool2d(3x3, stride 2, SAME), routed to the first maximum of each window.
+//   upsample2     : zero insertion that turns the stride-2 3x3 dgrad into a stride-1 conv.
+//   scatter_add2  : gradient of resnet_utils.subsample (identity shortcut of a stride-2 unit): g_x[2p,2q] += d[p,q].
+//   col2im_bwd    : gradient of the deconv heads' col2im (gather of the head gradients per (pixel, tap, channel)).
+// Reductions are two-stage with a fixed order (bitwise reproducible).
+#include "kernels.cuh"
+
+#include <cuda_fp16.h>
+
+namespace dgp {
+
+namespace {
+
+__device__ __forceinline__ void unpack8(const uint4& v, float* f, int fp16) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (fp16) {
+      const float2 r = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      f[2 * i] = r.x;
+      f[2 * i + 1] = r.y;
+    } else {
+      f[2 * i] = __uint_as_float(w[i] << 16);
+      f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b, int fp16) {
+  if (fp16) {
+    __half2 h = __floats2half2_rn(fminf(fmaxf(a, -65504.0f), 65504.0f), fminf(fmaxf(b, -65504.0f), 65504.0f));
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint4 pack8v(const float* f, int fp16) {
+  return make_uint4(pack2(f[0], f[1], fp16), pack2(f[2], f[3], fp16), pack2(f[4], f[5], fp16), pack2(f[6], f[7], fp16));
+}
+
+// MODE 0: plain ReLU layer.  MODE 1: junction, shortcut on the same pixel grid.  MODE 2: junction, identity shortcut
+// subsampled by 2 (sc is the unit input (N,Hx,Wx,C), read at (2p, 2q)).
+template <int MODE>
+__global__ void __launch_bounds__(256) relu_bn_bwd_kernel(uint4* __restrict__ g, const uint4* __restrict__ act,
+                                                          const uint4* __restrict__ sc, int M, int C8, int P, int Q,
+                                                          int Hx, int Wx, float* __restrict__ partial, int fp16) {
+  constexpr int NS = MODE == 0 ? 2 : 3;
+  const int my_cg = threadIdx.x % C8;
+  const int my_r = threadIdx.x / C8;
+  const int rpb = 256 / C8;
+  float S[NS][8];
+#pragma unroll
+  for (int s = 0; s < NS; ++s)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) S[s][j] = 0.0f;
+  for (int r = blockIdx.x * rpb + my_r; r < M; r += gridDim.x * rpb) {
+    const size_t idx = (size_t)r * C8 + my_cg;
+    float gv[8], av[8], sv[8];
+    unpack8(g[idx], gv, fp16);
+    unpack8(__ldg(act + idx), av, fp16);
+    if (MODE == 1) {
+      unpack8(__ldg(sc + idx), sv, fp16);
+    } else if (MODE == 2) {
+      const int n = r / (P * Q);
+      const int rem = r - n * (P * Q);
+      const int pp = rem / Q;
+      const int qq = rem - pp * Q;
+      unpack8(__ldg(sc + (((size_t)n * Hx + 2 * pp) * Wx + 2 * qq) * C8 + my_cg), sv, fp16);
+    }
+    float d[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      d[j] = av[j] > 0.0f ? gv[j] : 0.0f;
+      S[0][j] += d[j];
+      if (MODE == 0) {
+        S[1][j] += d[j] * av[j];
+      } else {
+        S[1][j] += d[j] * (av[j] - sv[j]);
+        S[2][j] += d[j] * sv[j];
+      }
+    }
+    g[idx] = pack8v(d, fp16);
+  }
+  __shared__ float sm[256][NS * 8 + 1];
+#pragma unroll
+  for (int s = 0; s < NS; ++s)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sm[threadIdx.x][s * 8 + j] = S[s][j];
+  __syncthreads();
+  if (my_r == 0) {
+    const int C = C8 * 8;
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float acc = 0.0f;
+        for (int rr = 0; rr < rpb; ++rr) acc += sm[rr * C8 + my_cg][s * 8 + j];
+        partial[((size_t)blockIdx.x * NS + s) * C + my_cg * 8 + j] = acc;
+      }
+  }
+}
+
+// dbeta[c] (+)= S0;  dgamma[c] (+)= (S_which - beta * S0) / gamma   (sums over the blocks in index order)
+__global__ void bn_grad_finalize_kernel(const float* __restrict__ partial, int nblocks, int NS, int which, int C,
+                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                        float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s0 = 0.0f, s1 = 0.0f;
+  for (int b = 0; b < nblocks; ++b) {
+    s0 += partial[((size_t)b * NS + 0) * C + c];
+    s1 += partial[((size_t)b * NS + which) * C + c];
+  }
+  const float gm = gamma[c];
+  dbeta[c] = s0;
+  dgamma[c] = fabsf(gm) > 1e-20f ? (s1 - beta[c] * s0) / gm : 0.0f;
+}
+
+__global__ void maxpool_bwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ gout, int N, int H, int W, int C8,
+                                   int Ho, int Wo, int pad_t, int pad_l, uint4* __restrict__ gx, int fp16) {
+  const size_t total = (size_t)N * H * W * C8;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(t % C8);
+    size_t r = t / C8;
+    const int xx = (int)(r % W);
+    r /= W;
+    const int yy = (int)(r % H);
+    const int n = (int)(r / H);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+    // windows containing (yy, xx): 2p - pad_t <= yy <= 2p - pad_t + 2
+    const int p_lo = (yy + pad_t - 2 + 1) >> 1 < 0 ? 0 : (yy + pad_t - 2 + 1) >> 1;
+    int p_hi = (yy + pad_t) >> 1;
+    if (p_hi > Ho - 1) p_hi = Ho - 1;
+    const int q_lo = (xx + pad_l - 2 + 1) >> 1 < 0 ? 0 : (xx + pad_l - 2 + 1) >> 1;
+    int q_hi = (xx + pad_l) >> 1;
+    if (q_hi > Wo - 1) q_hi = Wo - 1;
+    for (int p = p_lo; p <= p_hi; ++p)
+      for (int q = q_lo; q <= q_hi; ++q) {
+        float best[8];
+        int arg[8];
+        bool have = false;
+        int mine = -1;
+        for (int dy = 0; dy < 3; ++dy) {
+          const int y = 2 * p - pad_t + dy;
+          if (y < 0 || y >= H) continue;
+          for (int dx = 0; dx < 3; ++dx) {
+            const int xq = 2 * q - pad_l + dx;
+            if (xq < 0 || xq >= W) continue;
+            float v[8];
+            unpack8(__ldg(x + (((size_t)n * H + y) * W + xq) * C8 + c), v, fp16);
+            const int pos = dy * 3 + dx;
+            if (y == yy && xq == xx) mine = pos;
+            if (!have) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { best[j] = v[j]; arg[j] = pos; }
+              have = true;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (v[j] > best[j]) { best[j] = v[j]; arg[j] = pos; }
+            }
+          }
+        }
+        float gv[8];
+        unpack8(__ldg(gout + (((size_t)n * Ho + p) * Wo + q) * C8 + c), gv, fp16);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (arg[j] == mine) acc[j] += gv[j];
+      }
+    gx[t] = pack8v(acc, fp16);
+  }
+}
+
+// out (N,H,W,C) = zero-inserted in (N,P,Q,C): out[n,2p,2q] = in[n,p,q]
+__global__ void upsample2_kernel(const uint4* __restrict__ in, int N, int P, int Q, int C8, uint4* __restrict__ out, int H,
+                                 int W) {
+  const size_t total = (size_t)N * H * W * C8;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(t % C8);
+    size_t r = t / C8;
+    const int x = (int)(r % W);
+    r /= W;
+    const int y = (int)(r % H);
+    const int n = (int)(r / H);
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (!(y & 1) && !(x & 1) && (y >> 1) < P && (x >> 1) < Q) v = __ldg(in + (((size_t)n * P + (y >> 1)) * Q + (x >> 1)) * C8 + c);
+    out[t] = v;
+  }
+}
+
+// gx (N,H,W,C)[n,2p,2q] += d (N,P,Q,C)[n,p,q]
+__global__ void scatter_add2_kernel(const uint4* __restrict__ d, int N, int P, int Q, int C8, uint4* __restrict__ gx, int H,
+                                    int W, int fp16) {
+  const size_t total = (size_t)N * P * Q * C8;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(t % C8);
+    size_t r = t / C8;
+    const int q = (int)(r % Q);
+    r /= Q;
+    const int p = (int)(r % P);
+    const int n = (int)(r / P);
+    const size_t o = (((size_t)n * H + 2 * p) * W + 2 * q) * C8 + c;
+    float a[8], b[8];
+    unpack8(__ldg(d + t), a, fp16);
+    unpack8(gx[o], b, fp16);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] += b[j];
+    gx[o] = pack8v(a, fp16);
+  }
+}
+
+// dG[m][kk] (16-bit, Kd columns) = head gradient at (2i+kh, 2j+kw), kk = (kh*3+kw)*ctot + co; zero outside / padding.
+__global__ void col2im_bwd_kernel(const float* __restrict__ g_logits, const float* __restrict__ g_locref, int N, int h, int w,
+                                  int ctot, int nj, uint16_t* __restrict__ dG, int Kd, int fp16) {
+  const size_t total = (size_t)N * h * w * Kd;
+  const int Ho = 2 * h, Wo = 2 * w;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int kk = (int)(t % (size_t)Kd);
+    size_t m = t / (size_t)Kd;
+    const int j = (int)(m % w);
+    m /= w;
+    const int i = (int)(m % h);
+    const int n = (int)(m / h);
+    float v = 0.0f;
+    if (kk < 9 * ctot) {
+      const int tap = kk / ctot;
+      const int co = kk - tap * ctot;
+      const int y = 2 * i + tap / 3, x = 2 * j + tap % 3;
+      if (y < Ho && x < Wo) {
+        if (co < nj) v = g_logits[(((size_t)n * Ho + y) * Wo + x) * nj + co];
+        else if (g_locref) v = g_locref[(((size_t)n * Ho + y) * Wo + x) * (size_t)(ctot - nj) + (co - nj)];
+      }
+    }
+    uint16_t o;
+    if (fp16) { __half hh = __float2half_rn(fminf(fmaxf(v, -65504.0f), 65504.0f)); o = *reinterpret_cast<uint16_t*>(&hh); }
+    else { __nv_bfloat16 bb = __float2bfloat16_rn(v); o = *reinterpret_cast<uint16_t*>(&bb); }
+    dG[t] = o;
+  }
+}
+
+// dbias[co] = sum over all pixels of the head gradient (one block per channel, fixed tree)
+__global__ void head_bias_grad_kernel(const float* __restrict__ g_logits, const float* __restrict__ g_locref, size_t npix,
+                                      int ctot, int nj, float* __restrict__ dbias) {
+  const int co = blockIdx.x;
+  const float* src = co < nj ? g_logits + co : (g_locref ? g_locref + (co - nj) : nullptr);
+  const int ld = co < nj ? nj : ctot - nj;
+  float acc = 0.0f;
+  if (src)
+    for (size_t i = threadIdx.x; i < npix; i += blockDim.x) acc += src[i * ld];
+  __shared__ float sm[256];
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) sm[threadIdx.x] += sm[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) dbias[co] = sm[0];
+}
+
+int flat_grid(size_t n, int threads) {
+  size_t g = (n + threads - 1) / threads;
+  if (g > 148 * 16) g = 148 * 16;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace
+
+int relu_bn_bwd_blocks(int M, int C) {
+  const int rpb = 256 / (C / 8);
+  int blocks = (M + rpb - 1) / rpb;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  return blocks < 1 ? 1 : blocks;
+}
+
+cudaError_t launch_relu_bn_bwd(int mode, void* g, const void* act, const void* sc, int M, int C, int P, int Q, int Hx,
+                               int Wx, float* partial, int fp16, cudaStream_t s) {
+  if (C % 8 || 256 % (C / 8) || C / 8 > 256) return cudaErrorInvalidValue;
+  const int blocks = relu_bn_bwd_blocks(M, C);
+  uint4* gg = reinterpret_cast<uint4*>(g);
+  const uint4* aa = reinterpret_cast<const uint4*>(act);
+  const uint4* ss = reinterpret_cast<const uint4*>(sc);
+  if (mode == 0) relu_bn_bwd_kernel<0><<<blocks, 256, 0, s>>>(gg, aa, ss, M, C / 8, P, Q, Hx, Wx, partial, fp16);
+  else if (mode == 1) relu_bn_bwd_kernel<1><<<blocks, 256, 0, s>>>(gg, aa, ss, M, C / 8, P, Q, Hx, Wx, partial, fp16);
+  else relu_bn_bwd_kernel<2><<<blocks, 256, 0, s>>>(gg, aa, ss, M, C / 8, P, Q, Hx, Wx, partial, fp16);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bn_grad_finalize(const float* partial, int nblocks, int ns, int which, int C, const float* gamma,
+                                    const float* beta, float* dgamma, float* dbeta, cudaStream_t s) {
+  bn_grad_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(partial, nblocks, ns, which, C, gamma, beta, dgamma, dbeta);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_maxpool_bwd(const void* x, const void* gout, int N, int H, int W, int C, int Ho, int Wo, int pad_t,
+                               int pad_l, void* gx, int fp16, cudaStream_t s) {
+  const size_t total = (size_t)N * H * W * (C / 8);
+  maxpool_bwd_kernel<<<flat_grid(total, 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(x),
+                                                           reinterpret_cast<const uint4*>(gout), N, H, W, C / 8, Ho, Wo,
+                                                           pad_t, pad_l, reinterpret_cast<uint4*>(gx), fp16);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_upsample2(const void* in, int N, int P, int Q, int C, void* out, int H, int W, cudaStream_t s) {
+  const size_t total = (size_t)N * H * W * (C / 8);
+  upsample2_kernel<<<flat_grid(total, 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(in), N, P, Q, C / 8,
+                                                         reinterpret_cast<uint4*>(out), H, W);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_scatter_add2(const void* d, int N, int P, int Q, int C, void* gx, int H, int W, int fp16,
+                                cudaStream_t s) {
+  const size_t total = (size_t)N * P * Q * (C / 8);
+  scatter_add2_kernel<<<flat_grid(total, 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(d), N, P, Q, C / 8,
+                                                            reinterpret_cast<uint4*>(gx), H, W, fp16);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_col2im_bwd(const float* g_logits, const float* g_locref, int N, int h, int w, int ctot, int nj,
+                              void* dG, int Kd, int fp16, cudaStream_t s) {
+  const size_t total = (size_t)N * h * w * Kd;
+  col2im_bwd_kernel<<<flat_grid(total, 256), 256, 0, s>>>(g_logits, g_locref, N, h, w, ctot, nj,
+                                                          reinterpret_cast<uint16_t*>(dG), Kd, fp16);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_head_bias_grad(const float* g_logits, const float* g_locref, size_t npix, int ctot, int nj,
+                                  float* dbias, cudaStream_t s) {
+  head_bias_grad_kernel<<<ctot, 256, 0, s>>>(g_logits, g_locref, npix, ctot, nj, dbias);
+  return cudaGetLastError();
+}
+
+}  // namespace dgp

@@ -16,112 +16,15 @@
 #include <tuple>
 #include <vector>
 
-#include "conv_gemm_sm100.cuh"
-#include "kernels.cuh"
+#include "handle.cuh"
 
 using namespace dgp;
 
-namespace {
+namespace dgp {
 
 char g_create_error[512] = "";
 
-struct HostVar {
-  std::vector<float> data;
-  std::vector<int64_t> shape;
-};
 
-struct DevBuf {
-  void* p = nullptr;
-  size_t bytes = 0;
-};
-
-struct ConvLayer {
-  std::string scope;
-  int R = 1, S = 1, Cin = 0, Cout = 0, stride = 1, dil = 1;
-  bool relu = true;
-  int K = 0;        // GEMM K (multiple of 64)
-  int Npad = 0;     // rows of the weight matrix (multiple of block_n)
-  int block_n = 0;
-  __nv_bfloat16* w = nullptr;  // [Npad][K]
-  float* scale = nullptr;      // [Npad] or nullptr
-  float* shift = nullptr;
-};
-
-struct UnitDesc {
-  std::string scope;
-  int depth, base, stride, rate;
-  int shortcut = -1, conv1 = -1, conv2 = -1, conv3 = -1;  // indices into layers
-};
-
-enum StepKind { STEP_PREP = 0, STEP_GEMM = 1, STEP_POOL = 2, STEP_COL2IM = 3 };
-
-struct Step {
-  StepKind kind;
-  ConvGemmParams gp;      // STEP_GEMM
-  std::string end_point;  // name under which the output is kept in debug mode ("" = none)
-  const void* out_ptr = nullptr;
-  int oN = 0, oH = 0, oW = 0, oC = 0;  // output shape (bf16 NHWC) for debug dumps
-  // pool
-  const __nv_bfloat16* pin = nullptr;
-  int pH = 0, pW = 0, pC = 0, pad_t = 0, pad_l = 0;
-};
-
-struct Plan {
-  int B = 0, H = 0, W = 0;
-  int H1 = 0, W1 = 0, Hs = 0, Ws = 0;  // conv1 output / s2d dims
-  int hf = 0, wf = 0;                  // feature map (stride 16)
-  std::vector<DevBuf> bufs;
-  __nv_bfloat16* s2d = nullptr;
-  float* contrib = nullptr;
-  int contrib_ld = 0;
-  std::vector<Step> steps;
-};
-
-}  // namespace
-
-struct dgp_handle {
-  dgp_config cfg;
-  int device = 0;
-  int num_sms = 0;
-  int fp16 = 0;  // storage precision of activations / weights: 0 = bf16, 1 = fp16
-  char err[512] = "";
-  std::map<std::string, HostVar> host_vars;
-  bool finalized = false;
-  std::vector<ConvLayer> layers;
-  int conv1_layer = -1, head_layer = -1;
-  std::vector<UnitDesc> units;
-  float* head_bias = nullptr;
-  int ctot = 0;
-  std::map<std::tuple<int, int, int>, std::unique_ptr<Plan>> plans;
-  bool debug_keep = false;
-  struct Kept {
-    void* p;
-    int N, H, W, C;
-  };
-  std::map<std::string, Kept> kept;
-  int64_t launches = 0;
-  // per-kernel-family CUDA-event profiling (bench.py roofline numbers)
-  bool profiling = false;
-  struct ProfRec {
-    int kind;
-    cudaEvent_t a, b;
-  };
-  std::vector<ProfRec> prof;
-  std::vector<cudaEvent_t> ev_pool;
-  // softargmax workspace
-  SaPartial* sa_ws = nullptr;
-  size_t sa_ws_bytes = 0;
-  DevBuf loss_ws;
-  // estimate_pose_host staging
-  cudaStream_t stream = nullptr;       // compute stream of dgp_estimate_pose_host
-  cudaStream_t copy_stream = nullptr;  // H2D of the next batch overlaps the current batch's kernels
-  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
-  DevBuf st_frames2[2], st_logits, st_mu, st_peak, st_lik;
-};
-
-namespace {
-
-typedef __nv_bfloat16 W16;  // opaque 16-bit storage element (bf16 or fp16 bits)
 W16 cvt16(const dgp_handle* h, float f) {
   W16 out;
   if (h->fp16) {
@@ -150,12 +53,6 @@ int fail(dgp_handle* h, int code, const char* fmt, ...) {
   return code;
 }
 
-#define CU_OK(h, expr)                                                                          \
-  do {                                                                                          \
-    cudaError_t _e = (expr);                                                                    \
-    if (_e != cudaSuccess)                                                                      \
-      return fail(h, DGP_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
-  } while (0)
 
 int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
@@ -202,20 +99,30 @@ int upload_layer(dgp_handle* h, ConvLayer& L, const std::vector<__nv_bfloat16>& 
   return DGP_OK;
 }
 
-// Frozen batch norm folded to fp32 scale/shift (applied in the GEMM epilogue, never into the bf16 weights).
-int bn_scale_shift(dgp_handle* h, const std::string& scope, int C, std::vector<float>* scale, std::vector<float>* shift) {
+// master fp32 -> 16-bit GEMM operands + BN scale/shift (after loading and after every optimizer step)
+int refresh_operands(dgp_handle* h, cudaStream_t s) {
+  CU_OK(h, launch_refresh_w16(h->master, h->w16, h->n_w, h->fp16, s));
+  CU_OK(h, launch_refresh_bn(h->master + h->n_w, h->master + h->n_w + h->n_ch, h->bn_mean, h->bn_var, h->cfg.bn_epsilon,
+                             (int)h->n_ch, h->bn_ss, h->bn_ss + h->n_ch, s));
+  h->launches += 2;
+  return DGP_OK;
+}
+
+// Frozen batch norm (slim batch_norm, is_training=False): gamma / beta are trainable and live in the parameter arena,
+// the moving statistics are constants; the fp32 scale/shift applied in the GEMM epilogue are derived on the device
+// (refresh_bn_kernel), never folded into the 16-bit weights.
+int append_bn(dgp_handle* h, const std::string& scope, int C, int* ch_off) {
   const HostVar* g = find_var(h, scope + "/BatchNorm/gamma");
   const HostVar* b = find_var(h, scope + "/BatchNorm/beta");
   const HostVar* m = find_var(h, scope + "/BatchNorm/moving_mean");
   const HostVar* v = find_var(h, scope + "/BatchNorm/moving_variance");
   if (!b || !m || !v) return fail(h, DGP_ERR_STATE, "missing BatchNorm variables for %s", scope.c_str());
-  scale->resize(C);
-  shift->resize(C);
+  *ch_off = (int)h->host_gamma.size();
   for (int c = 0; c < C; ++c) {
-    const float gamma = g ? g->data[c] : 1.0f;
-    const float s = gamma / sqrtf(v->data[c] + h->cfg.bn_epsilon);
-    (*scale)[c] = s;
-    (*shift)[c] = b->data[c] - m->data[c] * s;
+    h->host_gamma.push_back(g ? g->data[c] : 1.0f);
+    h->host_beta.push_back(b->data[c]);
+    h->host_mean.push_back(m->data[c]);
+    h->host_var.push_back(v->data[c]);
   }
   return DGP_OK;
 }
@@ -232,16 +139,15 @@ int build_conv_layer(dgp_handle* h, const std::string& scope, int R, int S, int 
   L.K = R * S * Cin;
   L.block_n = Cout >= 256 ? 256 : Cout;
   L.Npad = Cout;
-  std::vector<__nv_bfloat16> wm((size_t)Cout * L.K);
+  L.w_off = h->host_master.size();
+  h->host_master.resize(L.w_off + (size_t)Cout * L.K);
+  float* wm = h->host_master.data() + L.w_off;
   for (int t = 0; t < R * S; ++t)
     for (int c = 0; c < Cin; ++c) {
       const float* src = &w->data[((size_t)t * Cin + c) * Cout];
-      for (int o = 0; o < Cout; ++o) wm[(size_t)o * L.K + (size_t)t * Cin + c] = cvt16(h, src[o]);
+      for (int o = 0; o < Cout; ++o) wm[(size_t)o * L.K + (size_t)t * Cin + c] = src[o];
     }
-  std::vector<float> scale, shift;
-  int rc = bn_scale_shift(h, scope, Cout, &scale, &shift);
-  if (rc) return rc;
-  rc = upload_layer(h, L, wm, &scale, &shift);
+  int rc = append_bn(h, scope, Cout, &L.ch_off);
   if (rc) return rc;
   *index = (int)h->layers.size();
   h->layers.push_back(L);
@@ -259,7 +165,10 @@ int build_conv1_layer(dgp_handle* h) {
   ConvLayer L;
   L.scope = scope; L.R = 4; L.S = 1; L.Cin = 64; L.Cout = 64; L.stride = 1; L.dil = 1; L.relu = true;
   L.K = 256; L.block_n = 64; L.Npad = 64;
-  std::vector<__nv_bfloat16> wm((size_t)64 * 256, cvt16(h, 0.0f));
+  L.w_off = h->host_master.size();
+  h->host_master.resize(L.w_off + (size_t)64 * 256, 0.0f);
+  float* wm = h->host_master.data() + L.w_off;
+  h->host_conv1_mask.assign((size_t)64 * 256, 0.0f);
   for (int a = 0; a < 4; ++a)
     for (int b = 0; b < 4; ++b)
       for (int u = 0; u < 2; ++u)
@@ -267,14 +176,13 @@ int build_conv1_layer(dgp_handle* h) {
           const int kh = 2 * a + u, kw = 2 * b + v;
           if (kh >= 7 || kw >= 7) continue;
           for (int c = 0; c < 3; ++c)
-            for (int o = 0; o < 64; ++o)
-              wm[(size_t)o * 256 + a * 64 + b * 16 + (u * 2 + v) * 3 + c] =
-                  cvt16(h, w->data[(((size_t)kh * 7 + kw) * 3 + c) * 64 + o]);
+            for (int o = 0; o < 64; ++o) {
+              const size_t d = (size_t)o * 256 + a * 64 + b * 16 + (u * 2 + v) * 3 + c;
+              wm[d] = w->data[(((size_t)kh * 7 + kw) * 3 + c) * 64 + o];
+              h->host_conv1_mask[d] = 1.0f;
+            }
         }
-  std::vector<float> scale, shift;
-  int rc = bn_scale_shift(h, scope, 64, &scale, &shift);
-  if (rc) return rc;
-  rc = upload_layer(h, L, wm, &scale, &shift);
+  int rc = append_bn(h, scope, 64, &L.ch_off);
   if (rc) return rc;
   h->conv1_layer = (int)h->layers.size();
   h->layers.push_back(L);
@@ -304,25 +212,59 @@ int build_head_layer(dgp_handle* h) {
   L.K = 2048;
   L.block_n = pick_block_n(9 * ctot);
   L.Npad = ceil_div(9 * ctot, L.block_n) * L.block_n;
-  std::vector<__nv_bfloat16> wm((size_t)L.Npad * 2048, cvt16(h, 0.0f));
+  L.w_off = h->host_master.size();
+  h->host_master.resize(L.w_off + (size_t)L.Npad * 2048, 0.0f);
+  float* wm = h->host_master.data() + L.w_off;
   for (int t = 0; t < 9; ++t)
     for (int co = 0; co < ctot; ++co) {
       const HostVar* src = co < nj ? wp : wl;
       const int cc = co < nj ? co : co - nj;
       const int cn = co < nj ? nj : 2 * nj;
       const float* s = &src->data[((size_t)t * cn + cc) * 2048];
-      __nv_bfloat16* d = &wm[(size_t)(t * ctot + co) * 2048];
-      for (int c = 0; c < 2048; ++c) d[c] = cvt16(h, s[c]);
+      float* d = &wm[(size_t)(t * ctot + co) * 2048];
+      for (int c = 0; c < 2048; ++c) d[c] = s[c];
     }
-  int rc = upload_layer(h, L, wm, nullptr, nullptr);
-  if (rc) return rc;
-  std::vector<float> bias(ctot);
-  for (int co = 0; co < ctot; ++co) bias[co] = co < nj ? bp->data[co] : bl->data[co - nj];
-  CU_OK(h, cudaMalloc(&h->head_bias, ctot * sizeof(float)));
-  CU_OK(h, cudaMemcpy(h->head_bias, bias.data(), ctot * sizeof(float), cudaMemcpyHostToDevice));
+  h->host_bias.assign((size_t)ceil_div(ctot, 8) * 8, 0.0f);
+  for (int co = 0; co < ctot; ++co) h->host_bias[co] = co < nj ? bp->data[co] : bl->data[co - nj];
   h->ctot = ctot;
   h->head_layer = (int)h->layers.size();
   h->layers.push_back(L);
+  return DGP_OK;
+}
+
+// Uploads the parameter arena [weights | gamma | beta | head bias] (fp32 master copy) and derives the tensor-core
+// operands on the device.
+int upload_arena(dgp_handle* h) {
+  h->n_w = h->host_master.size();
+  h->n_ch = h->host_gamma.size();
+  h->n_bias = h->host_bias.size();
+  h->n_params = h->n_w + 2 * h->n_ch + h->n_bias;
+  if (h->n_w % 8 || h->n_ch % 4) return fail(h, DGP_ERR_STATE, "parameter arena is not vector aligned");
+  CU_OK(h, cudaMalloc(&h->master, h->n_params * sizeof(float)));
+  CU_OK(h, cudaMalloc(&h->w16, h->n_w * sizeof(W16)));
+  CU_OK(h, cudaMalloc(&h->bn_mean, h->n_ch * sizeof(float)));
+  CU_OK(h, cudaMalloc(&h->bn_var, h->n_ch * sizeof(float)));
+  CU_OK(h, cudaMalloc(&h->bn_ss, 2 * h->n_ch * sizeof(float)));
+  CU_OK(h, cudaMemcpy(h->master, h->host_master.data(), h->n_w * 4, cudaMemcpyHostToDevice));
+  CU_OK(h, cudaMemcpy(h->master + h->n_w, h->host_gamma.data(), h->n_ch * 4, cudaMemcpyHostToDevice));
+  CU_OK(h, cudaMemcpy(h->master + h->n_w + h->n_ch, h->host_beta.data(), h->n_ch * 4, cudaMemcpyHostToDevice));
+  CU_OK(h, cudaMemcpy(h->master + h->n_w + 2 * h->n_ch, h->host_bias.data(), h->n_bias * 4, cudaMemcpyHostToDevice));
+  CU_OK(h, cudaMemcpy(h->bn_mean, h->host_mean.data(), h->n_ch * 4, cudaMemcpyHostToDevice));
+  CU_OK(h, cudaMemcpy(h->bn_var, h->host_var.data(), h->n_ch * 4, cudaMemcpyHostToDevice));
+  CU_OK(h, cudaMalloc(&h->conv1_mask, h->host_conv1_mask.size() * 4));
+  CU_OK(h, cudaMemcpy(h->conv1_mask, h->host_conv1_mask.data(), h->host_conv1_mask.size() * 4, cudaMemcpyHostToDevice));
+  for (ConvLayer& L : h->layers) {
+    L.w = h->w16 + L.w_off;
+    if (L.ch_off >= 0) {
+      L.scale = h->bn_ss + L.ch_off;
+      L.shift = h->bn_ss + h->n_ch + L.ch_off;
+    }
+  }
+  h->head_bias = h->master + h->n_w + 2 * h->n_ch;
+  int rc = refresh_operands(h, nullptr);
+  if (rc) return rc;
+  CU_OK(h, cudaDeviceSynchronize());
+  std::vector<float>().swap(h->host_master);
   return DGP_OK;
 }
 
@@ -480,14 +422,18 @@ int make_wgrad_params(dgp_handle* h, const char* scope, int R, int S, int Cin, i
   return DGP_OK;
 }
 
-int build_plan(dgp_handle* h, int B, int H, int W, Plan** out) {
+int keep_activation(dgp_handle* h, const Step& st, cudaStream_t s);
+
+int build_plan(dgp_handle* h, int B, int H, int W, bool train, Plan** out) {
   auto key = std::make_tuple(B, H, W);
-  auto it = h->plans.find(key);
-  if (it != h->plans.end()) {
+  auto& plans = train ? h->train_plans : h->plans;
+  auto it = plans.find(key);
+  if (it != plans.end()) {
     *out = it->second.get();
     return DGP_OK;
   }
   std::unique_ptr<Plan> pl(new Plan());
+  pl->train = train;
   pl->B = B; pl->H = H; pl->W = W;
   pl->H1 = ceil_div(H, 2); pl->W1 = ceil_div(W, 2);
   pl->Hs = pl->H1 + 3; pl->Ws = pl->W1 + 3;
@@ -550,11 +496,17 @@ int build_plan(dgp_handle* h, int B, int H, int W, Plan** out) {
   int Hc, Wc, pad_t, pad_l;
   same_pad(pl->H1, 3, 2, 1, &pad_t, &Hc);
   same_pad(pl->W1, 3, 2, 1, &pad_l, &Wc);
-  if ((rc = alloc_buf(h, pl.get(), x_bytes, &xa))) return rc;
-  if ((rc = alloc_buf(h, pl.get(), x_bytes, &xb))) return rc;
-  if ((rc = alloc_buf(h, pl.get(), sc_bytes, &sc))) return rc;
-  if ((rc = alloc_buf(h, pl.get(), t_bytes, &t1))) return rc;
-  if ((rc = alloc_buf(h, pl.get(), t_bytes, &t2))) return rc;
+  if (!train) {
+    if ((rc = alloc_buf(h, pl.get(), x_bytes, &xa))) return rc;
+    if ((rc = alloc_buf(h, pl.get(), x_bytes, &xb))) return rc;
+    if ((rc = alloc_buf(h, pl.get(), sc_bytes, &sc))) return rc;
+    if ((rc = alloc_buf(h, pl.get(), t_bytes, &t1))) return rc;
+    if ((rc = alloc_buf(h, pl.get(), t_bytes, &t2))) return rc;
+  } else {
+    // training keeps every activation for the backward pass: each tensor gets its own buffer
+    if ((rc = alloc_buf(h, pl.get(), (size_t)B * Hc * Wc * 64 * 2 + 1024, &xa))) return rc;
+  }
+  pl->c1 = c1; pl->pool = xa; pl->Hp = Hc; pl->Wp = Wc; pl->pool_pad_t = pad_t; pl->pool_pad_l = pad_l;
   {
     Step st; st.kind = STEP_POOL;
     st.pin = (const __nv_bfloat16*)c1; st.pH = pl->H1; st.pW = pl->W1; st.pC = 64; st.pad_t = pad_t; st.pad_l = pad_l;
@@ -569,6 +521,17 @@ int build_plan(dgp_handle* h, int B, int H, int W, Plan** out) {
     const void* shortcut = nullptr;
     int res_sub = 1, res_H = Hc, res_W = Wc;
     int Ho, Wo, dh, dw;
+    if (train) {
+      const int ho = ceil_div(Hc, u.stride), wo = ceil_div(Wc, u.stride);
+      sc = nullptr;
+      if (u.shortcut >= 0 && (rc = alloc_buf(h, pl.get(), (size_t)B * Hc * Wc * u.depth * 2 + 1024, &sc))) return rc;
+      if ((rc = alloc_buf(h, pl.get(), (size_t)B * Hc * Wc * u.base * 2 + 1024, &t1))) return rc;
+      if ((rc = alloc_buf(h, pl.get(), (size_t)B * ho * wo * u.base * 2 + 1024, &t2))) return rc;
+      if ((rc = alloc_buf(h, pl.get(), (size_t)B * ho * wo * u.depth * 2 + 1024, &y))) return rc;
+      Plan::UnitBufs ub;
+      ub.x = x; ub.sc = sc; ub.t1 = t1; ub.t2 = t2; ub.out = y; ub.H = Hc; ub.W = Wc; ub.Ho = ho; ub.Wo = wo; ub.Cin = Cin;
+      pl->ub.push_back(ub);
+    }
     if (u.shortcut >= 0) {
       Step st;
       rc = make_gemm_step(h, h->layers[u.shortcut], x, B, Hc, Wc, 0, sc, false, nullptr, 1, 0, 0, 0, &st, &dh, &dw);
@@ -606,6 +569,7 @@ int build_plan(dgp_handle* h, int B, int H, int W, Plan** out) {
     std::swap(x, y);
   }
   (void)Cin;
+  pl->feat = x;
   pl->hf = Hc; pl->wf = Wc;
   // ---- heads: GEMM over feature pixels + col2im
   {
@@ -621,8 +585,44 @@ int build_plan(dgp_handle* h, int B, int H, int W, Plan** out) {
     Step c; c.kind = STEP_COL2IM;
     pl->steps.push_back(c);
   }
+  if (train) {
+    const int nj = h->cfg.num_joints;
+    if ((rc = alloc_buf(h, pl.get(), (size_t)B * 4 * Hc * Wc * nj * 4, &p))) return rc;
+    pl->logits = (float*)p;
+    if (h->cfg.location_refinement) {
+      if ((rc = alloc_buf(h, pl.get(), (size_t)B * 4 * Hc * Wc * 2 * nj * 4, &p))) return rc;
+      pl->locref = (float*)p;
+    }
+  }
   *out = pl.get();
-  h->plans[key] = std::move(pl);
+  plans[key] = std::move(pl);
+  return DGP_OK;
+}
+
+int run_forward_plan(dgp_handle* h, Plan* pl, const uint8_t* frames_dev, float* logits_dev, float* locref_dev,
+                     cudaStream_t s) {
+  int rc;
+  for (const Step& st : pl->steps) {
+    ProfScope prof(h, (int)st.kind, s);
+    switch (st.kind) {
+      case STEP_PREP:
+        CU_OK(h, launch_prep_s2d(frames_dev, pl->B, pl->H, pl->W, h->cfg.mean_pixel, pl->s2d, pl->Hs, pl->Ws, h->fp16, s));
+        break;
+      case STEP_GEMM:
+        CU_OK(h, launch_conv_gemm(st.gp, h->num_sms, s));
+        break;
+      case STEP_POOL:
+        CU_OK(h, launch_maxpool3x3s2(st.pin, pl->B, st.pH, st.pW, st.pC, (__nv_bfloat16*)st.out_ptr, st.oH, st.oW, st.pad_t,
+                                     st.pad_l, h->fp16, s));
+        break;
+      case STEP_COL2IM:
+        CU_OK(h, launch_deconv_col2im(pl->contrib, pl->B, pl->hf, pl->wf, pl->contrib_ld, h->ctot, h->cfg.num_joints,
+                                      h->head_bias, logits_dev, locref_dev, s));
+        break;
+    }
+    h->launches++;
+    if ((rc = keep_activation(h, st, s))) return rc;
+  }
   return DGP_OK;
 }
 
@@ -652,37 +652,7 @@ int ensure(dgp_handle* h, DevBuf* b, size_t bytes) {
   return DGP_OK;
 }
 
-cudaEvent_t prof_event(dgp_handle* h) {
-  if (!h->ev_pool.empty()) {
-    cudaEvent_t e = h->ev_pool.back();
-    h->ev_pool.pop_back();
-    return e;
-  }
-  cudaEvent_t e = nullptr;
-  cudaEventCreate(&e);
-  return e;
-}
-
-struct ProfScope {
-  dgp_handle* h;
-  cudaStream_t s;
-  int idx = -1;
-  ProfScope(dgp_handle* h_, int kind, cudaStream_t s_) : h(h_), s(s_) {
-    if (!h->profiling) return;
-    dgp_handle::ProfRec r;
-    r.kind = kind;
-    r.a = prof_event(h);
-    r.b = prof_event(h);
-    cudaEventRecord(r.a, s);
-    idx = (int)h->prof.size();
-    h->prof.push_back(r);
-  }
-  ~ProfScope() {
-    if (idx >= 0) cudaEventRecord(h->prof[idx].b, s);
-  }
-};
-
-}  // namespace
+}  // namespace dgp
 
 extern "C" {
 
@@ -724,13 +694,16 @@ void dgp_destroy(dgp_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
-  for (auto& L : h->layers) {
-    cudaFree(L.w);
-    cudaFree(L.scale);
-    cudaFree(L.shift);
-  }
-  cudaFree(h->head_bias);
+  train_destroy(h);
+  cudaFree(h->master);
+  cudaFree(h->w16);
+  cudaFree(h->bn_mean);
+  cudaFree(h->bn_var);
+  cudaFree(h->bn_ss);
+  cudaFree(h->conv1_mask);
   for (auto& kv : h->plans)
+    for (auto& b : kv.second->bufs) cudaFree(b.p);
+  for (auto& kv : h->train_plans)
     for (auto& b : kv.second->bufs) cudaFree(b.p);
   for (auto& kv : h->kept) cudaFree(kv.second.p);
   cudaFree(h->sa_ws);
@@ -802,6 +775,7 @@ int dgp_finalize_weights(dgp_handle* h) {
       h->units.push_back(ud);
     }
   if ((rc = build_head_layer(h))) return rc;
+  if ((rc = upload_arena(h))) return rc;
   h->host_vars.clear();
   h->finalized = true;
   return DGP_OK;
@@ -827,30 +801,9 @@ int dgp_forward(dgp_handle* h, const uint8_t* frames_dev, int B, int H, int W, f
   CU_OK(h, cudaSetDevice(h->device));
   cudaStream_t s = (cudaStream_t)stream;
   Plan* pl = nullptr;
-  int rc = build_plan(h, B, H, W, &pl);
+  int rc = build_plan(h, B, H, W, false, &pl);
   if (rc) return rc;
-  for (const Step& st : pl->steps) {
-    ProfScope prof(h, (int)st.kind, s);
-    switch (st.kind) {
-      case STEP_PREP:
-        CU_OK(h, launch_prep_s2d(frames_dev, B, H, W, h->cfg.mean_pixel, pl->s2d, pl->Hs, pl->Ws, h->fp16, s));
-        break;
-      case STEP_GEMM:
-        CU_OK(h, launch_conv_gemm(st.gp, h->num_sms, s));
-        break;
-      case STEP_POOL:
-        CU_OK(h, launch_maxpool3x3s2(st.pin, B, st.pH, st.pW, st.pC, (__nv_bfloat16*)st.out_ptr, st.oH, st.oW, st.pad_t,
-                                     st.pad_l, h->fp16, s));
-        break;
-      case STEP_COL2IM:
-        CU_OK(h, launch_deconv_col2im(pl->contrib, B, pl->hf, pl->wf, pl->contrib_ld, h->ctot, h->cfg.num_joints,
-                                      h->head_bias, logits_dev, locref_dev, s));
-        break;
-    }
-    h->launches++;
-    if ((rc = keep_activation(h, st, s))) return rc;
-  }
-  return DGP_OK;
+  return run_forward_plan(h, pl, frames_dev, logits_dev, locref_dev, s);
 }
 
 int dgp_softargmax(dgp_handle* h, const float* logits_dev, const float* locref_dev, int B, int H, int W, int nj,
@@ -907,7 +860,7 @@ int dgp_softmax_map(dgp_handle* h, const float* logits_dev, int B, int H, int W,
   return DGP_OK;
 }
 
-static int run_loss(dgp_handle* h, const dgp_loss_cfg* cfg, const dgp_loss_batch* b, float* losses_dev,
+int dgp_run_loss_impl(dgp_handle* h, const dgp_loss_cfg* cfg, const dgp_loss_batch* b, float* losses_dev,
                     float* targets_all_dev, float* grad_pred_dev, float* grad_locref_dev, int visible_only, void* stream) {
   if (!h) return DGP_ERR_INVALID;
   if (!cfg || !b || !losses_dev || !b->pred_dev) return fail(h, DGP_ERR_INVALID, "dgp_loss_forward: null argument");
@@ -983,13 +936,13 @@ static int run_loss(dgp_handle* h, const dgp_loss_cfg* cfg, const dgp_loss_batch
 
 int dgp_loss_forward(dgp_handle* h, const dgp_loss_cfg* cfg, const dgp_loss_batch* b, float* losses_dev,
                      float* targets_all_dev, void* stream) {
-  return run_loss(h, cfg, b, losses_dev, targets_all_dev, nullptr, nullptr, 0, stream);
+  return dgp_run_loss_impl(h, cfg, b, losses_dev, targets_all_dev, nullptr, nullptr, 0, stream);
 }
 
 int dgp_loss_backward(dgp_handle* h, const dgp_loss_cfg* cfg, const dgp_loss_batch* b, float* losses_dev,
                       float* grad_pred_dev, float* grad_locref_dev, int visible_only, void* stream) {
   if (h && !grad_pred_dev) return fail(h, DGP_ERR_INVALID, "dgp_loss_backward: grad_pred_dev is required");
-  return run_loss(h, cfg, b, losses_dev, nullptr, grad_pred_dev, grad_locref_dev, visible_only, stream);
+  return dgp_run_loss_impl(h, cfg, b, losses_dev, nullptr, grad_pred_dev, grad_locref_dev, visible_only, stream);
 }
 
 int dgp_sigmoid(dgp_handle* h, const float* logits_dev, float* prob_dev, size_t n, void* stream) {

@@ -57,4 +57,35 @@ cudaError_t launch_dgp_loss(const LossArgs& a, cudaStream_t stream);
 cudaError_t launch_dgp_loss_backward(const LossArgs& a, const float* norm, float gamma, float gauss_len, int visible_only,
                                      float* g_pred, float* g_locref, cudaStream_t stream);
 
+// ---- parameter arena / optimizer (param_kernels.cu)
+cudaError_t launch_refresh_w16(const float* master, void* w16, size_t n, int fp16, cudaStream_t s);
+cudaError_t launch_refresh_bn(const float* gamma, const float* beta, const float* mean, const float* var, float eps, int n,
+                              float* scale, float* shift, cudaStream_t s);
+// wd[ci][T-1-tap][co] = round16(w[co][tap][ci] * scale[co]); Kd = row length of wd (>= taps * Cout, zero padded)
+cudaError_t launch_build_dgrad_w(const float* w, const float* scale, int Cout, int taps, int Cin, int rows_w, void* wd,
+                                 int Kd, int fp16, cudaStream_t s);
+cudaError_t launch_build_head_dgrad_w(const float* wh, int rows, int C, void* whT, int Kd, int fp16, cudaStream_t s);
+int sqnorm_partials();
+// norm_clip[0] = |grad_scale| * ||g||_2, norm_clip[1] = clip / max(norm, clip) (1 if clip <= 0)
+cudaError_t launch_global_norm(const float* g, size_t n, float grad_scale, float clip, float* partial, float* norm_clip,
+                               cudaStream_t s);
+cudaError_t launch_momentum_step(float* w, float* accum, const float* g, size_t n, float lr, float momentum,
+                                 float grad_scale, const float* norm_clip, cudaStream_t s);
+
+// ---- network backward, bandwidth-class parts (bwd_kernels.cu)
+int relu_bn_bwd_blocks(int M, int C);  // rows of `partial` ([blocks][ns][C], ns = 2 for mode 0 else 3)
+cudaError_t launch_relu_bn_bwd(int mode, void* g, const void* act, const void* sc, int M, int C, int P, int Q, int Hx,
+                               int Wx, float* partial, int fp16, cudaStream_t s);
+cudaError_t launch_bn_grad_finalize(const float* partial, int nblocks, int ns, int which, int C, const float* gamma,
+                                    const float* beta, float* dgamma, float* dbeta, cudaStream_t s);
+cudaError_t launch_maxpool_bwd(const void* x, const void* gout, int N, int H, int W, int C, int Ho, int Wo, int pad_t,
+                               int pad_l, void* gx, int fp16, cudaStream_t s);
+cudaError_t launch_upsample2(const void* in, int N, int P, int Q, int C, void* out, int H, int W, cudaStream_t s);
+cudaError_t launch_scatter_add2(const void* d, int N, int P, int Q, int C, void* gx, int H, int W, int fp16,
+                                cudaStream_t s);
+cudaError_t launch_col2im_bwd(const float* g_logits, const float* g_locref, int N, int h, int w, int ctot, int nj,
+                              void* dG, int Kd, int fp16, cudaStream_t s);
+cudaError_t launch_head_bias_grad(const float* g_logits, const float* g_locref, size_t npix, int ctot, int nj,
+                                  float* dbias, cudaStream_t s);
+
 }  // namespace dgp

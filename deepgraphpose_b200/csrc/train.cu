@@ -1,0 +1,498 @@
+// Training step of fit_dgp on the GPU: network backward (dgrad / wgrad of the 53 convs + deconv heads), frozen-BN
+// parameter gradients, global-norm clipping and the Momentum update.
+// Reference: src/deepgraphpose/models/fitdgp.py:706-713
+//   optimizer = MomentumOptimizer(lr, 0.9); grads = compute_gradients(total_loss, TF.trainable_variables());
+//   grads, _ = clip_by_global_norm(grads, 10.0); train_op = apply_gradients(...)
+// with the graph of fitdgp.py:934-1128 (PoseNet with is_training=False -> frozen moving statistics, trainable
+// gamma / beta / conv weights / deconv weights + biases).
+//
+// Data flow per bottleneck unit (all tensors 16-bit NHWC, gradients w.r.t. BN outputs "dy"):
+//   junction  : d = g_out * [out > 0]                      (relu_bn_bwd, + BN sums of conv3 / projection shortcut)
+//   conv3     : wgrad(t2, d) ; g_t2 = dgrad(d)             (tcgen05 GEMMs)
+//   conv2     : dy2 = g_t2 * [t2 > 0] ; wgrad(t1, dy2) ; g_t1 = dgrad(dy2)   (stride 2: zero-inserted dy2, stride-1 conv)
+//   conv1     : dy1 = g_t1 * [t1 > 0] ; wgrad(x, dy1) ; g_x = dgrad(dy1) + shortcut path
+//   shortcut  : identity: + d (GEMM residual; stride 2: scatter-add)   projection: wgrad(x, d), g_x += dgrad(d)
+// The BN scale of a layer is folded into its dgrad operand (build_dgrad_w_kernel) and applied per output row in the
+// wgrad reduction, so every GEMM consumes the same dy tensor.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <functional>
+
+#include "handle.cuh"
+
+using namespace dgp;
+
+namespace dgp {
+
+struct BStep {
+  int kind;      // profiling family: 5 = dgrad GEMM, 6 = wgrad GEMM (+ reduce), 7 = bandwidth-class backward kernel
+  int launches;
+  std::function<cudaError_t(cudaStream_t)> run;
+};
+
+struct Backward {
+  std::vector<BStep> steps;
+  float *g_logits = nullptr, *g_locref = nullptr;
+};
+
+struct TrainState {
+  float* grads = nullptr;
+  float* accum = nullptr;
+  float* norm_partial = nullptr;
+  float* norm_clip = nullptr;  // [0] = global norm of the last step, [1] = clip factor
+  DevBuf bn_partial, wgrad_ws;
+  std::vector<W16*> wd;  // per layer: dgrad operand [Cin][taps*Cout] (nullptr for conv1 / head)
+  W16* head_wd = nullptr;
+  int head_Kd = 0;
+  bool wd_fresh = false;
+};
+
+void train_destroy(dgp_handle* h) {
+  TrainState* ts = h->train;
+  if (!ts) return;
+  cudaFree(ts->grads);
+  cudaFree(ts->accum);
+  cudaFree(ts->norm_partial);
+  cudaFree(ts->norm_clip);
+  cudaFree(ts->bn_partial.p);
+  cudaFree(ts->wgrad_ws.p);
+  for (W16* p : ts->wd) cudaFree(p);
+  cudaFree(ts->head_wd);
+  delete ts;
+  h->train = nullptr;
+}
+
+namespace {
+
+int refresh_dgrad_weights(dgp_handle* h, cudaStream_t s) {
+  TrainState* ts = h->train;
+  for (size_t i = 0; i < h->layers.size(); ++i) {
+    if (!ts->wd[i]) continue;
+    const ConvLayer& L = h->layers[i];
+    CU_OK(h, launch_build_dgrad_w(h->master + L.w_off, L.scale, L.Cout, L.R * L.S, L.Cin, L.Npad, ts->wd[i],
+                                  L.R * L.S * L.Cout, h->fp16, s));
+    h->launches++;
+  }
+  const ConvLayer& Lh = h->layers[h->head_layer];
+  CU_OK(h, launch_build_head_dgrad_w(h->master + Lh.w_off, 9 * h->ctot, 2048, ts->head_wd, ts->head_Kd, h->fp16, s));
+  h->launches++;
+  ts->wd_fresh = true;
+  return DGP_OK;
+}
+
+// dgrad of layer L as a stride-1 conv of dy (N,H,W,L.Cout) with the transposed / flipped operand -> out (N,H,W,L.Cin)
+int add_dgrad(dgp_handle* h, Backward* bw, const ConvLayer& L, W16* wd, const void* dy, int N, int H, int W, void* out,
+              const void* residual) {
+  ConvLayer D;
+  D.scope = L.scope + "/dgrad";
+  D.R = L.R; D.S = L.S; D.Cin = L.Cout; D.Cout = L.Cin; D.stride = 1; D.dil = L.dil; D.relu = false;
+  D.K = L.R * L.S * L.Cout;
+  D.Npad = L.Cin;
+  D.block_n = L.Cin >= 256 ? 256 : L.Cin;
+  D.w = wd;
+  Step st;
+  int Ho, Wo;
+  int rc = make_gemm_step(h, D, dy, N, H, W, (L.R == 1 && L.S == 1) ? 0 : 1, out, false, (const __nv_bfloat16*)residual, 1, H,
+                          W, 0, &st, &Ho, &Wo);
+  if (rc) return rc;
+  const ConvGemmParams gp = st.gp;
+  const int sms = h->num_sms;
+  bw->steps.push_back({5, 1, [gp, sms](cudaStream_t s) { return launch_conv_gemm(gp, sms, s); }});
+  return DGP_OK;
+}
+
+int add_wgrad_params(dgp_handle* h, Backward* bw, const WgradParams& wp0, const float* rowscale, const float* mask,
+                     float* grad, size_t* ws_need) {
+  TrainState* ts = h->train;
+  const size_t need = wgrad_workspace_bytes(wp0);
+  if (need > *ws_need) *ws_need = need;
+  const int sms = h->num_sms;
+  bw->steps.push_back({6, 2, [wp0, ts, sms, rowscale, mask, grad](cudaStream_t s) {
+                         WgradParams wp = wp0;
+                         wp.partials = (float*)ts->wgrad_ws.p;
+                         cudaError_t e = launch_wgrad_gemm(wp, sms, s);
+                         if (e != cudaSuccess) return e;
+                         return launch_wgrad_reduce(wp, rowscale, mask, grad, 0, s);
+                       }});
+  return DGP_OK;
+}
+
+int add_wgrad(dgp_handle* h, Backward* bw, const ConvLayer& L, const void* x, int N, int H, int W, int pad_mode,
+              const void* dy, size_t* ws_need) {
+  WgradParams wp;
+  int rc = make_wgrad_params(h, L.scope.c_str(), L.R, L.S, L.Cin, L.Cout, L.stride, L.dil, x, N, H, W, pad_mode, dy, &wp);
+  if (rc) return rc;
+  return add_wgrad_params(h, bw, wp, L.scale, nullptr, h->train->grads + L.w_off, ws_need);
+}
+
+// dy = g * [act > 0] in place + BN parameter gradients of up to two layers (la: which = 1, lb: which = 2)
+void add_mask(dgp_handle* h, Backward* bw, int mode, void* g, const void* act, const void* sc, int M, int C, int P, int Q,
+              int Hx, int Wx, const ConvLayer* la, const ConvLayer* lb, size_t* bn_need) {
+  TrainState* ts = h->train;
+  const int ns = mode == 0 ? 2 : 3;
+  const int blocks = relu_bn_bwd_blocks(M, C);
+  const size_t need = (size_t)blocks * ns * C * sizeof(float);
+  if (need > *bn_need) *bn_need = need;
+  const int fp16 = h->fp16;
+  const float* gam = h->master + h->n_w;
+  const float* bet = h->master + h->n_w + h->n_ch;
+  float* dgam = ts->grads + h->n_w;
+  float* dbet = ts->grads + h->n_w + h->n_ch;
+  const int offa = la ? la->ch_off : -1, offb = lb ? lb->ch_off : -1;
+  bw->steps.push_back({7, 1 + (la ? 1 : 0) + (lb ? 1 : 0),
+                       [=](cudaStream_t s) {
+                         float* partial = (float*)ts->bn_partial.p;
+                         cudaError_t e = launch_relu_bn_bwd(mode, g, act, sc, M, C, P, Q, Hx, Wx, partial, fp16, s);
+                         if (e != cudaSuccess) return e;
+                         if (offa >= 0) {
+                           e = launch_bn_grad_finalize(partial, blocks, ns, 1, C, gam + offa, bet + offa, dgam + offa,
+                                                       dbet + offa, s);
+                           if (e != cudaSuccess) return e;
+                         }
+                         if (offb >= 0)
+                           e = launch_bn_grad_finalize(partial, blocks, ns, 2, C, gam + offb, bet + offb, dgam + offb,
+                                                       dbet + offb, s);
+                         return e;
+                       }});
+}
+
+int build_backward(dgp_handle* h, Plan* pl) {
+  TrainState* ts = h->train;
+  std::shared_ptr<Backward> bw(new Backward());
+  const int B = pl->B, nj = h->cfg.num_joints, fp16 = h->fp16;
+  const int hf = pl->hf, wf = pl->wf;
+  int rc;
+  void* p = nullptr;
+  size_t ws_need = 0, bn_need = 0;
+  // ---- gradient buffers
+  size_t max_unit = (size_t)pl->Hp * pl->Wp * 64, max_t1 = 0, max_t2 = 0, max_up = 0;
+  for (size_t i = 0; i < h->units.size(); ++i) {
+    const UnitDesc& u = h->units[i];
+    const Plan::UnitBufs& ub = pl->ub[i];
+    max_unit = std::max(max_unit, (size_t)ub.Ho * ub.Wo * u.depth);
+    max_unit = std::max(max_unit, (size_t)ub.H * ub.W * ub.Cin);
+    max_t1 = std::max(max_t1, (size_t)ub.H * ub.W * u.base);
+    max_t2 = std::max(max_t2, (size_t)ub.Ho * ub.Wo * u.base);
+    if (u.stride == 2) max_up = std::max(max_up, (size_t)ub.H * ub.W * u.base);
+  }
+  void *gbuf[3], *gt1 = nullptr, *gt2 = nullptr, *gup = nullptr, *g_c1 = nullptr, *dG = nullptr;
+  for (int i = 0; i < 3; ++i)
+    if ((rc = alloc_buf(h, pl, (size_t)B * max_unit * 2 + 1024, &gbuf[i]))) return rc;
+  if ((rc = alloc_buf(h, pl, (size_t)B * max_t1 * 2 + 1024, &gt1))) return rc;
+  if ((rc = alloc_buf(h, pl, (size_t)B * max_t2 * 2 + 1024, &gt2))) return rc;
+  if (max_up && (rc = alloc_buf(h, pl, (size_t)B * max_up * 2 + 1024, &gup))) return rc;
+  if ((rc = alloc_buf(h, pl, (size_t)B * pl->H1 * pl->W1 * 64 * 2 + 1024, &g_c1))) return rc;
+  const int Kd = ts->head_Kd;
+  const int Mf = B * hf * wf;
+  if ((rc = alloc_buf(h, pl, (size_t)Mf * Kd * 2 + 1024, &dG))) return rc;
+  if ((rc = alloc_buf(h, pl, (size_t)B * 4 * hf * wf * nj * 4, &p))) return rc;
+  bw->g_logits = (float*)p;
+  if (pl->locref) {
+    if ((rc = alloc_buf(h, pl, (size_t)B * 4 * hf * wf * 2 * nj * 4, &p))) return rc;
+    bw->g_locref = (float*)p;
+  }
+  float* g_logits = bw->g_logits;
+  float* g_locref = bw->g_locref;
+  const int ctot = h->ctot;
+
+  // ---- heads: col2im gather, bias gradient, wgrad, dgrad
+  bw->steps.push_back({7, 1, [=](cudaStream_t s) { return launch_col2im_bwd(g_logits, g_locref, B, hf, wf, ctot, nj, dG, Kd, fp16, s); }});
+  {
+    float* dbias = ts->grads + h->n_w + 2 * h->n_ch;
+    const size_t npix = (size_t)B * 4 * hf * wf;
+    bw->steps.push_back({7, 1, [=](cudaStream_t s) { return launch_head_bias_grad(g_logits, g_locref, npix, ctot, nj, dbias, s); }});
+  }
+  {
+    const ConvLayer& Lh = h->layers[h->head_layer];
+    WgradParams wp;
+    // gradient rows = Npad rows of the head matrix; dy = dG (Kd >= Npad columns, zero beyond 9 * ctot)
+    rc = make_wgrad_params(h, "pose/heads", 1, 1, 2048, Kd, 1, 1, pl->feat, B, hf, wf, 0, dG, &wp);
+    if (rc) return rc;
+    wp.Cout = Lh.Npad;
+    wgrad_plan(&wp, h->num_sms);
+    if ((rc = add_wgrad_params(h, bw.get(), wp, nullptr, nullptr, ts->grads + Lh.w_off, &ws_need))) return rc;
+    ConvLayer D;
+    D.scope = "pose/heads/dgrad"; D.R = 1; D.S = 1; D.Cin = Kd; D.Cout = 2048; D.relu = false;
+    D.K = Kd; D.Npad = 2048; D.block_n = 256; D.w = ts->head_wd;
+    Step st;
+    int Ho, Wo;
+    rc = make_gemm_step(h, D, dG, B, hf, wf, 0, gbuf[0], false, nullptr, 1, 0, 0, 0, &st, &Ho, &Wo);
+    if (rc) return rc;
+    const ConvGemmParams gp = st.gp;
+    const int sms = h->num_sms;
+    bw->steps.push_back({5, 1, [gp, sms](cudaStream_t s) { return launch_conv_gemm(gp, sms, s); }});
+  }
+
+  // ---- bottleneck units, last to first.  G = gradient w.r.t. the unit output (then d in place).
+  int gi = 0;  // index of G in gbuf
+  for (int i = (int)h->units.size() - 1; i >= 0; --i) {
+    const UnitDesc& u = h->units[i];
+    const Plan::UnitBufs& ub = pl->ub[i];
+    const ConvLayer& L1 = h->layers[u.conv1];
+    const ConvLayer& L2 = h->layers[u.conv2];
+    const ConvLayer& L3 = h->layers[u.conv3];
+    const ConvLayer* Ls = u.shortcut >= 0 ? &h->layers[u.shortcut] : nullptr;
+    void* G = gbuf[gi];
+    void* Gx = gbuf[(gi + 1) % 3];
+    void* Gy = gbuf[(gi + 2) % 3];
+    const int Mo = B * ub.Ho * ub.Wo, Mi = B * ub.H * ub.W;
+    // junction
+    if (Ls) add_mask(h, bw.get(), 1, G, ub.out, ub.sc, Mo, u.depth, ub.Ho, ub.Wo, 0, 0, &L3, Ls, &bn_need);
+    else if (u.stride == 1) add_mask(h, bw.get(), 1, G, ub.out, ub.x, Mo, u.depth, ub.Ho, ub.Wo, 0, 0, &L3, nullptr, &bn_need);
+    else add_mask(h, bw.get(), 2, G, ub.out, ub.x, Mo, u.depth, ub.Ho, ub.Wo, ub.H, ub.W, &L3, nullptr, &bn_need);
+    // conv3
+    if ((rc = add_wgrad(h, bw.get(), L3, ub.t2, B, ub.Ho, ub.Wo, 0, G, &ws_need))) return rc;
+    if ((rc = add_dgrad(h, bw.get(), L3, ts->wd[u.conv3], G, B, ub.Ho, ub.Wo, gt2, nullptr))) return rc;
+    // conv2
+    add_mask(h, bw.get(), 0, gt2, ub.t2, nullptr, Mo, u.base, 0, 0, 0, 0, &L2, nullptr, &bn_need);
+    if ((rc = add_wgrad(h, bw.get(), L2, ub.t1, B, ub.H, ub.W, 1, gt2, &ws_need))) return rc;
+    if (u.stride == 1) {
+      if ((rc = add_dgrad(h, bw.get(), L2, ts->wd[u.conv2], gt2, B, ub.H, ub.W, gt1, nullptr))) return rc;
+    } else {
+      const int P = ub.Ho, Q = ub.Wo, H = ub.H, W = ub.W, C = u.base;
+      bw->steps.push_back({7, 1, [=](cudaStream_t s) { return launch_upsample2(gt2, B, P, Q, C, gup, H, W, s); }});
+      if ((rc = add_dgrad(h, bw.get(), L2, ts->wd[u.conv2], gup, B, ub.H, ub.W, gt1, nullptr))) return rc;
+    }
+    // conv1
+    add_mask(h, bw.get(), 0, gt1, ub.t1, nullptr, Mi, u.base, 0, 0, 0, 0, &L1, nullptr, &bn_need);
+    if ((rc = add_wgrad(h, bw.get(), L1, ub.x, B, ub.H, ub.W, 0, gt1, &ws_need))) return rc;
+    if (Ls) {
+      if ((rc = add_dgrad(h, bw.get(), L1, ts->wd[u.conv1], gt1, B, ub.H, ub.W, Gy, nullptr))) return rc;
+      if ((rc = add_wgrad(h, bw.get(), *Ls, ub.x, B, ub.H, ub.W, 0, G, &ws_need))) return rc;
+      if ((rc = add_dgrad(h, bw.get(), *Ls, ts->wd[u.shortcut], G, B, ub.H, ub.W, Gx, Gy))) return rc;
+    } else if (u.stride == 1) {
+      if ((rc = add_dgrad(h, bw.get(), L1, ts->wd[u.conv1], gt1, B, ub.H, ub.W, Gx, G))) return rc;
+    } else {
+      if ((rc = add_dgrad(h, bw.get(), L1, ts->wd[u.conv1], gt1, B, ub.H, ub.W, Gx, nullptr))) return rc;
+      const int P = ub.Ho, Q = ub.Wo, H = ub.H, W = ub.W, C = u.depth;
+      bw->steps.push_back({7, 1, [=](cudaStream_t s) { return launch_scatter_add2(G, B, P, Q, C, Gx, H, W, fp16, s); }});
+    }
+    gi = (gi + 1) % 3;
+  }
+  // ---- root: max-pool backward, conv1 ReLU/BN, conv1 wgrad (no dgrad: the input is the image)
+  {
+    void* Gp = gbuf[gi];
+    const void* c1 = pl->c1;
+    const int H1 = pl->H1, W1 = pl->W1, Hp = pl->Hp, Wp = pl->Wp, pt = pl->pool_pad_t, plft = pl->pool_pad_l;
+    bw->steps.push_back({7, 1, [=](cudaStream_t s) { return launch_maxpool_bwd(c1, Gp, B, H1, W1, 64, Hp, Wp, pt, plft, g_c1, fp16, s); }});
+    const ConvLayer& L = h->layers[h->conv1_layer];
+    add_mask(h, bw.get(), 0, g_c1, c1, nullptr, B * H1 * W1, 64, 0, 0, 0, 0, &L, nullptr, &bn_need);
+    WgradParams wp;
+    memset(&wp, 0, sizeof(wp));
+    tmap_set_fp16(h->fp16);
+    wp.fp16 = h->fp16;
+    const int M = B * H1 * W1;
+    wp.Cout = 64; wp.Kw = 256; wp.num_pix_blocks = ceil_div(M, 64);
+    wp.x_mode = 1; wp.P = H1; wp.Q = W1; wp.conv_stride = 1; wp.lower_h = 0; wp.lower_w = 0; wp.S = 1; wp.dil = 1; wp.cblocks = 1;
+    const char* e = make_tmap_2d(&wp.tmap_dy, g_c1, (uint64_t)M, 64, 128, 64);
+    if (e) return fail(h, DGP_ERR_CUDA, "conv1 wgrad (dy map): %s", e);
+    e = make_tmap_im2col(&wp.tmap_x, pl->s2d, 64, (uint64_t)W1, (uint64_t)pl->Hs, (uint64_t)B, 32, (uint64_t)pl->Ws * 32,
+                         (uint64_t)pl->Hs * pl->Ws * 32, 0, 0, 0, -3, 1, (uint64_t)B * pl->Hs * pl->Ws * 32, 64);
+    if (e) return fail(h, DGP_ERR_CUDA, "conv1 wgrad (x map): %s", e);
+    wgrad_plan(&wp, h->num_sms);
+    if ((rc = add_wgrad_params(h, bw.get(), wp, L.scale, h->conv1_mask, ts->grads + L.w_off, &ws_need))) return rc;
+  }
+  if ((rc = ensure(h, &ts->wgrad_ws, ws_need))) return rc;
+  if ((rc = ensure(h, &ts->bn_partial, bn_need))) return rc;
+  pl->bwd = bw;
+  return DGP_OK;
+}
+
+// host-side TF-layout view of one variable of the arena
+struct VarRef {
+  int kind = -1;  // 0 conv weights HWIO, 1 conv1 weights, 2 gamma, 3 beta, 4 head weights, 5 head bias
+  const ConvLayer* L = nullptr;
+  int head_part = 0;  // 0 = part_pred, 1 = locref_pred
+};
+
+bool find_variable(dgp_handle* h, const std::string& name, VarRef* r) {
+  const std::string pp = "pose/part_pred/block4/", pl = "pose/locref_pred/block4/";
+  for (int part = 0; part < 2; ++part) {
+    const std::string& pre = part ? pl : pp;
+    if (name.compare(0, pre.size(), pre) == 0) {
+      if (part == 1 && !h->cfg.location_refinement) return false;
+      r->head_part = part;
+      r->L = &h->layers[h->head_layer];
+      const std::string leaf = name.substr(pre.size());
+      if (leaf == "weights") { r->kind = 4; return true; }
+      if (leaf == "biases") { r->kind = 5; return true; }
+      return false;
+    }
+  }
+  for (const ConvLayer& L : h->layers) {
+    if (name.compare(0, L.scope.size(), L.scope) != 0 || name.size() <= L.scope.size() || name[L.scope.size()] != '/') continue;
+    const std::string leaf = name.substr(L.scope.size() + 1);
+    r->L = &L;
+    if (leaf == "weights") { r->kind = (&L == &h->layers[h->conv1_layer]) ? 1 : 0; return true; }
+    if (leaf == "BatchNorm/gamma") { r->kind = 2; return true; }
+    if (leaf == "BatchNorm/beta") { r->kind = 3; return true; }
+  }
+  return false;
+}
+
+}  // namespace
+}  // namespace dgp
+
+extern "C" {
+
+int dgp_train_enable(dgp_handle* h) {
+  if (!h) return DGP_ERR_INVALID;
+  if (!h->finalized) return fail(h, DGP_ERR_STATE, "dgp_train_enable before dgp_finalize_weights");
+  if (h->train) return DGP_OK;
+  CU_OK(h, cudaSetDevice(h->device));
+  TrainState* ts = new TrainState();
+  h->train = ts;
+  CU_OK(h, cudaMalloc(&ts->grads, h->n_params * sizeof(float)));
+  CU_OK(h, cudaMalloc(&ts->accum, h->n_params * sizeof(float)));
+  CU_OK(h, cudaMemset(ts->grads, 0, h->n_params * sizeof(float)));
+  CU_OK(h, cudaMemset(ts->accum, 0, h->n_params * sizeof(float)));
+  CU_OK(h, cudaMalloc(&ts->norm_partial, sqnorm_partials() * sizeof(float)));
+  CU_OK(h, cudaMalloc(&ts->norm_clip, 2 * sizeof(float)));
+  CU_OK(h, cudaMemset(ts->norm_clip, 0, 2 * sizeof(float)));
+  ts->wd.assign(h->layers.size(), nullptr);
+  for (size_t i = 0; i < h->layers.size(); ++i) {
+    if ((int)i == h->conv1_layer || (int)i == h->head_layer) continue;
+    const ConvLayer& L = h->layers[i];
+    CU_OK(h, cudaMalloc(&ts->wd[i], (size_t)L.Cin * L.R * L.S * L.Cout * sizeof(W16)));
+  }
+  ts->head_Kd = ceil_div(std::max(9 * h->ctot, h->layers[h->head_layer].Npad), 64) * 64;
+  CU_OK(h, cudaMalloc(&ts->head_wd, (size_t)2048 * ts->head_Kd * sizeof(W16)));
+  return DGP_OK;
+}
+
+int dgp_train_forward_backward(dgp_handle* h, const uint8_t* frames_dev, int nt, int H, int W, const dgp_loss_cfg* cfg,
+                               const dgp_loss_batch* batch, int visible_only, float* losses_dev, void* stream) {
+  if (!h) return DGP_ERR_INVALID;
+  if (!h->train) return fail(h, DGP_ERR_STATE, "dgp_train_forward_backward before dgp_train_enable");
+  if (!frames_dev || !cfg || !batch || !losses_dev || nt < 1 || H < 32 || W < 32)
+    return fail(h, DGP_ERR_INVALID, "dgp_train_forward_backward: bad argument");
+  CU_OK(h, cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  TrainState* ts = h->train;
+  Plan* pl = nullptr;
+  int rc = build_plan(h, nt, H, W, true, &pl);
+  if (rc) return rc;
+  if (!pl->bwd && (rc = build_backward(h, pl))) return rc;
+  Backward* bw = static_cast<Backward*>(pl->bwd.get());
+  if (batch->nt != nt || batch->H != 2 * pl->hf || batch->W != 2 * pl->wf)
+    return fail(h, DGP_ERR_INVALID, "dgp_train_forward_backward: batch dims (%d,%d,%d) do not match the network output (%d,%d,%d)",
+                batch->nt, batch->H, batch->W, nt, 2 * pl->hf, 2 * pl->wf);
+  if (!ts->wd_fresh && (rc = refresh_dgrad_weights(h, s))) return rc;
+  if ((rc = run_forward_plan(h, pl, frames_dev, pl->logits, pl->locref, s))) return rc;
+  dgp_loss_batch b = *batch;
+  b.pred_dev = pl->logits;
+  b.locref_dev = pl->locref;
+  if ((rc = dgp_run_loss_impl(h, cfg, &b, losses_dev, nullptr, bw->g_logits, bw->g_locref, visible_only, stream))) return rc;
+  for (const BStep& st : bw->steps) {
+    ProfScope prof(h, st.kind, s);
+    CU_OK(h, st.run(s));
+    h->launches += st.launches;
+  }
+  return DGP_OK;
+}
+
+int dgp_optimizer_step(dgp_handle* h, float lr, float momentum, float clip_norm, float grad_scale, void* stream) {
+  if (!h) return DGP_ERR_INVALID;
+  if (!h->train) return fail(h, DGP_ERR_STATE, "dgp_optimizer_step before dgp_train_enable");
+  CU_OK(h, cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  TrainState* ts = h->train;
+  CU_OK(h, launch_global_norm(ts->grads, h->n_params, grad_scale, clip_norm, ts->norm_partial, ts->norm_clip, s));
+  CU_OK(h, launch_momentum_step(h->master, ts->accum, ts->grads, h->n_params, lr, momentum, grad_scale, ts->norm_clip, s));
+  h->launches += 3;
+  int rc = refresh_operands(h, s);
+  if (rc) return rc;
+  return refresh_dgrad_weights(h, s);
+}
+
+int dgp_get_grad_buffer(dgp_handle* h, void** dev_ptr, size_t* bytes) {
+  if (!h) return DGP_ERR_INVALID;
+  if (!h->train) return fail(h, DGP_ERR_STATE, "dgp_get_grad_buffer before dgp_train_enable");
+  if (dev_ptr) *dev_ptr = h->train->grads;
+  if (bytes) *bytes = h->n_params * sizeof(float);
+  return DGP_OK;
+}
+
+int dgp_get_grad_norm(dgp_handle* h, float* norm_host) {
+  if (!h || !norm_host) return DGP_ERR_INVALID;
+  if (!h->train) return fail(h, DGP_ERR_STATE, "dgp_get_grad_norm before dgp_train_enable");
+  CU_OK(h, cudaSetDevice(h->device));
+  CU_OK(h, cudaDeviceSynchronize());
+  CU_OK(h, cudaMemcpy(norm_host, h->train->norm_clip, sizeof(float), cudaMemcpyDeviceToHost));
+  return DGP_OK;
+}
+
+int dgp_train_outputs(dgp_handle* h, int nt, int H, int W, float** logits_dev, float** locref_dev) {
+  if (!h) return DGP_ERR_INVALID;
+  auto it = h->train_plans.find(std::make_tuple(nt, H, W));
+  if (it == h->train_plans.end()) return fail(h, DGP_ERR_STATE, "dgp_train_outputs: no training step has run at this shape");
+  if (logits_dev) *logits_dev = it->second->logits;
+  if (locref_dev) *locref_dev = it->second->locref;
+  return DGP_OK;
+}
+
+int dgp_get_variable(dgp_handle* h, const char* tf_var_name, int what, float* host_out, size_t max_elems, int64_t* shape4,
+                     int* ndim) {
+  if (!h || !tf_var_name) return DGP_ERR_INVALID;
+  if (!h->finalized) return fail(h, DGP_ERR_STATE, "dgp_get_variable before dgp_finalize_weights");
+  if (what < 0 || what > 2) return fail(h, DGP_ERR_INVALID, "dgp_get_variable: what must be 0 (value), 1 (gradient) or 2 (momentum)");
+  if (what > 0 && !h->train) return fail(h, DGP_ERR_STATE, "dgp_get_variable: gradients need dgp_train_enable");
+  VarRef r;
+  if (!find_variable(h, tf_var_name, &r)) return fail(h, DGP_ERR_INVALID, "unknown variable %s", tf_var_name);
+  const float* arena = what == 0 ? h->master : (what == 1 ? h->train->grads : h->train->accum);
+  const ConvLayer& L = *r.L;
+  const int nj = h->cfg.num_joints;
+  int64_t shp[4] = {0, 0, 0, 0};
+  int nd = 1;
+  switch (r.kind) {
+    case 0: shp[0] = L.R; shp[1] = L.S; shp[2] = L.Cin; shp[3] = L.Cout; nd = 4; break;
+    case 1: shp[0] = 7; shp[1] = 7; shp[2] = 3; shp[3] = 64; nd = 4; break;
+    case 2: case 3: shp[0] = L.Cout; nd = 1; break;
+    case 4: shp[0] = 3; shp[1] = 3; shp[2] = r.head_part ? 2 * nj : nj; shp[3] = 2048; nd = 4; break;
+    case 5: shp[0] = r.head_part ? 2 * nj : nj; nd = 1; break;
+  }
+  size_t n = 1;
+  for (int i = 0; i < nd; ++i) n *= (size_t)shp[i];
+  if (shape4) for (int i = 0; i < 4; ++i) shape4[i] = shp[i];
+  if (ndim) *ndim = nd;
+  if (!host_out) return DGP_OK;
+  if (n > max_elems) return fail(h, DGP_ERR_INVALID, "buffer too small for %s", tf_var_name);
+  CU_OK(h, cudaSetDevice(h->device));
+  CU_OK(h, cudaDeviceSynchronize());
+  if (r.kind == 2 || r.kind == 3) {
+    const size_t off = h->n_w + (r.kind == 3 ? h->n_ch : 0) + (size_t)L.ch_off;
+    CU_OK(h, cudaMemcpy(host_out, arena + off, n * 4, cudaMemcpyDeviceToHost));
+    return DGP_OK;
+  }
+  if (r.kind == 5) {
+    const size_t off = h->n_w + 2 * h->n_ch + (r.head_part ? nj : 0);
+    CU_OK(h, cudaMemcpy(host_out, arena + off, n * 4, cudaMemcpyDeviceToHost));
+    return DGP_OK;
+  }
+  std::vector<float> m((size_t)L.Npad * L.K);
+  CU_OK(h, cudaMemcpy(m.data(), arena + L.w_off, m.size() * 4, cudaMemcpyDeviceToHost));
+  if (r.kind == 0) {
+    const int T = L.R * L.S;
+    for (int t = 0; t < T; ++t)
+      for (int c = 0; c < L.Cin; ++c)
+        for (int o = 0; o < L.Cout; ++o) host_out[((size_t)t * L.Cin + c) * L.Cout + o] = m[(size_t)o * L.K + (size_t)t * L.Cin + c];
+  } else if (r.kind == 1) {
+    for (int kh = 0; kh < 7; ++kh)
+      for (int kw = 0; kw < 7; ++kw)
+        for (int c = 0; c < 3; ++c)
+          for (int o = 0; o < 64; ++o)
+            host_out[(((size_t)kh * 7 + kw) * 3 + c) * 64 + o] =
+                m[(size_t)o * 256 + (kh >> 1) * 64 + (kw >> 1) * 16 + ((kh & 1) * 2 + (kw & 1)) * 3 + c];
+  } else {
+    const int ctot = h->ctot, cn = r.head_part ? 2 * nj : nj, c0 = r.head_part ? nj : 0;
+    for (int t = 0; t < 9; ++t)
+      for (int cc = 0; cc < cn; ++cc)
+        memcpy(&host_out[((size_t)t * cn + cc) * 2048], &m[(size_t)(t * ctot + c0 + cc) * 2048], 2048 * sizeof(float));
+  }
+  return DGP_OK;
+}
+
+}  // extern "C"

@@ -135,7 +135,7 @@ typedef struct dgp_loss_batch {
 
 /* Replaces the loss part of sess.run([loss, ...]) in fit_dgp (fitdgp.py:817-818, graph :947-1128): soft-argmax of
  * the hidden markers, visible/hidden marker scatter, Gaussian-target sigmoid cross-entropies with the gm2/gm3
- * confidence scaling, locref Huber, skeleton (spatial) and temporal cliques.  FORWARD ONLY in this round.
+ * confidence scaling, locref Huber, skeleton (spatial) and temporal cliques (forward).
  * losses_dev[6] = {visible_loss_pred, hidden_loss_pred, visible_loss_locref, ws_loss, wt_loss, total_loss};
  * targets_all_dev (nt*nj,2) optionally receives targets_all_marker. */
 int dgp_loss_forward(dgp_handle* h, const dgp_loss_cfg* cfg, const dgp_loss_batch* batch, float* losses_dev,
@@ -145,8 +145,8 @@ int dgp_loss_forward(dgp_handle* h, const dgp_loss_cfg* cfg, const dgp_loss_batc
  * fit_dgp_labeledonly differentiates total_loss_visible, fitdgp.py:416 -> visible_only = 1): gradients of the loss
  * w.r.t. the head outputs, float32 (nt,H,W,nj) and (nt,H,W,2nj) (grad_locref_dev may be NULL).  They flow through the
  * cross-entropy labels (Gaussian targets -> soft-argmax), the confidence max and the (1 - c) weights exactly as in the
- * TF graph.  wt > 0 (temporal clique) is DGP_ERR_UNSUPPORTED here.  The network backward (dgrad / wgrad of the 53
- * convs) and the Momentum step are not implemented yet. */
+ * TF graph.  wt > 0 (temporal clique) is DGP_ERR_UNSUPPORTED here.  The network backward and the Momentum step are
+ * dgp_train_forward_backward / dgp_optimizer_step below. */
 int dgp_loss_backward(dgp_handle* h, const dgp_loss_cfg* cfg, const dgp_loss_batch* batch, float* losses_dev,
                       float* grad_pred_dev, float* grad_locref_dev, int visible_only, void* stream);
 
@@ -155,6 +155,35 @@ int dgp_loss_backward(dgp_handle* h, const dgp_loss_cfg* cfg, const dgp_loss_bat
  * gives asynchronous copies); mu_host float32 (T,nj,2); peak_host int32 (T,nj,2); lik_host float32 (T,nj). */
 int dgp_estimate_pose_host(dgp_handle* h, const uint8_t* frames_host, int T, int H, int W, int batch, float gamma,
                            float gauss_len, float* mu_host, int32_t* peak_host, float* lik_host);
+
+/* ---- training step (fit_dgp, src/deepgraphpose/models/fitdgp.py:706-713 and :817-818) ----
+ * Replaces sess.run([train_op, loss], feed_dict): dgp_train_forward_backward computes the loss and the gradients of
+ * total_loss (visible_only = 1: total_loss_visible, fit_dgp_labeledonly fitdgp.py:416) w.r.t. every trainable variable
+ * (conv weights, BatchNorm gamma/beta with frozen moving statistics, deconv weights + biases); dgp_optimizer_step applies
+ * tf.clip_by_global_norm(clip_norm) + MomentumOptimizer(lr, momentum).  Between the two calls a data-parallel caller
+ * all-reduces (sums) the flat gradient buffer of dgp_get_grad_buffer with NCCL and passes grad_scale = 1 / world_size
+ * (the tower averaging of src/deepgraphpose/helpers/utils_tf.py:4-39). */
+/* Allocates gradients, momentum accumulators and the transposed (dgrad) weight operands. Call after finalize. */
+int dgp_train_enable(dgp_handle* h);
+/* frames_dev uint8 (nt,H,W,3); batch->pred_dev / locref_dev are ignored (the handle's own head outputs are used), all other
+ * members as in dgp_loss_forward.  losses_dev[6] as in dgp_loss_forward.  wt > 0 is DGP_ERR_UNSUPPORTED (no backward of the
+ * temporal clique yet). */
+int dgp_train_forward_backward(dgp_handle* h, const uint8_t* frames_dev, int nt, int H, int W, const dgp_loss_cfg* cfg,
+                               const dgp_loss_batch* batch, int visible_only, float* losses_dev, void* stream);
+/* g' = g * grad_scale; g' *= clip_norm / max(||g'||, clip_norm) (clip_norm <= 0: no clipping);
+ * accum = momentum * accum + g'; var -= lr * accum; then refreshes the 16-bit operands and BN scale/shift. */
+int dgp_optimizer_step(dgp_handle* h, float lr, float momentum, float clip_norm, float grad_scale, void* stream);
+/* Flat float32 gradient buffer (kernel layouts: [weights | gamma | beta | head bias]) for ncclAllReduce. */
+int dgp_get_grad_buffer(dgp_handle* h, void** dev_ptr, size_t* bytes);
+/* Global gradient norm computed by the last dgp_optimizer_step (after grad_scale, before clipping). Synchronises. */
+int dgp_get_grad_norm(dgp_handle* h, float* norm_host);
+/* Device pointers of the head outputs (nt,2h,2w,nj) / (nt,2h,2w,2nj) written by the last training step at this shape. */
+int dgp_train_outputs(dgp_handle* h, int nt, int H, int W, float** logits_dev, float** locref_dev);
+/* Replaces sess.run(variable) / TF.train.Saver.save (fitdgp.py:830-839): copies a trainable variable back to the host under
+ * its TF name and TF layout.  what: 0 = value, 1 = gradient of the last step, 2 = momentum accumulator.
+ * host_out may be NULL to query shape4 / ndim only. */
+int dgp_get_variable(dgp_handle* h, const char* tf_var_name, int what, float* host_out, size_t max_elems, int64_t* shape4,
+                     int* ndim);
 
 /* ---- test / profiling hooks (not part of the reference surface) ---- */
 /* Keep every end_point (slim names, e.g. "resnet_v1_50/block1/unit_1/bottleneck_v1") of the next dgp_forward. */
@@ -175,7 +204,8 @@ int dgp_conv2d(dgp_handle* h, const void* x_dev, int N, int H, int W, int Cin, c
 int dgp_conv2d_wgrad(dgp_handle* h, const void* x_dev, int N, int H, int W, int Cin, const void* dy_dev, int R, int S,
                      int Cout, int stride, int dilation, int pad_mode, float* dw_dev, const int32_t* dbg3, void* stream);
 /* CUDA-event timing per kernel family, recorded on the launching stream around every launch while enabled.
- * kinds: 0 = u8->bf16 space-to-depth prep, 1 = tcgen05 conv GEMM, 2 = max-pool, 3 = deconv col2im, 4 = soft-argmax.
+ * kinds: 0 = u8->bf16 space-to-depth prep, 1 = tcgen05 conv GEMM, 2 = max-pool, 3 = deconv col2im, 4 = soft-argmax,
+ * 5 = dgrad GEMM, 6 = wgrad GEMM + reduce, 7 = bandwidth-class backward kernels.
  * dgp_get_profile synchronises the device, sums the elapsed ms and launch counts per kind and clears the records. */
 int dgp_set_profiling(dgp_handle* h, int enable);
 int dgp_get_profile(dgp_handle* h, double* ms_by_kind, int64_t* count_by_kind, int nkinds);
