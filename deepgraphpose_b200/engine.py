@@ -69,6 +69,18 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
+class _Raw:
+    """__cuda_array_interface__ carrier for memory owned by the handle."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"data": (int(ptr), False), "shape": tuple(shape), "typestr": typestr, "version": 2}
+
+
+def _device_view(ptr, shape, typestr, device):
+    with torch.cuda.device(device):
+        return torch.as_tensor(_Raw(ptr, shape, typestr), device=device)
+
+
 def _stream(device):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
@@ -226,6 +238,50 @@ class Engine:
                                                     _ptr(mu), _ptr(peak), _ptr(lik)))
         return mu, peak, lik
 
+    # ------------------------------------------------------------------ training (fit_dgp's train_op)
+    def train_enable(self):
+        if not getattr(self, "_train", False):
+            self._check(self.lib.dgp_train_enable(self.h))
+            self._train = True
+
+    def optimizer_step(self, lr=0.005, momentum=0.9, clip_norm=10.0, grad_scale=1.0):
+        """clip_by_global_norm(clip_norm) + MomentumOptimizer(lr, momentum) (fitdgp.py:706-713) on the gradient buffer."""
+        self._check(self.lib.dgp_optimizer_step(self.h, float(lr), float(momentum), float(clip_norm), float(grad_scale),
+                                                _stream(self.device)))
+
+    def grad_buffer(self):
+        """The flat float32 gradient buffer as a CUDA tensor VIEW (what a data-parallel caller all-reduces)."""
+        self.train_enable()
+        p, n = C.c_void_p(), C.c_size_t()
+        self._check(self.lib.dgp_get_grad_buffer(self.h, C.byref(p), C.byref(n)))
+        return _device_view(p.value, (n.value // 4,), "<f4", self.device)
+
+    def grad_norm(self):
+        v = C.c_float()
+        self._check(self.lib.dgp_get_grad_norm(self.h, C.byref(v)))
+        return float(v.value)
+
+    def train_outputs(self, nt, H, W):
+        """Views of the head outputs (logits, locref) the last training step at this input shape produced."""
+        a, b = C.c_void_p(), C.c_void_p()
+        self._check(self.lib.dgp_train_outputs(self.h, int(nt), int(H), int(W), C.byref(a), C.byref(b)))
+        _, (ho, wo) = output_dims(H, W)
+        logits = _device_view(a.value, (nt, ho, wo, self.nj), "<f4", self.device)
+        locref = _device_view(b.value, (nt, ho, wo, 2 * self.nj), "<f4", self.device) if b.value else None
+        return logits, locref
+
+    def get_variable(self, name, what="value"):
+        """A trainable variable (or its gradient / momentum accumulator) under its TF name, in TF layout (float32 ndarray)."""
+        code = {"value": 0, "grad": 1, "momentum": 2}[what]
+        shape = (C.c_int64 * 4)()
+        nd = C.c_int()
+        self._check(self.lib.dgp_get_variable(self.h, name.encode(), code, None, 0, shape, C.byref(nd)))
+        shp = tuple(int(shape[i]) for i in range(nd.value))
+        out = np.empty(shp, np.float32)
+        self._check(self.lib.dgp_get_variable(self.h, name.encode(), code, out.ctypes.data_as(C.c_void_p), out.size, shape,
+                                              C.byref(nd)))
+        return out
+
     # ------------------------------------------------------------------ test hooks
     def keep_activations(self, enable=True):
         self._check(self.lib.dgp_debug_keep_activations(self.h, int(enable)))
@@ -281,7 +337,8 @@ class Engine:
                                               _ptr(dw), d3, _stream(x.device)))
         return dw
 
-    PROFILE_KINDS = ("prep_s2d", "conv_gemm", "maxpool", "deconv_col2im", "softargmax")
+    PROFILE_KINDS = ("prep_s2d", "conv_gemm", "maxpool", "deconv_col2im", "softargmax", "dgrad_gemm", "wgrad_gemm",
+                     "bwd_bandwidth")
 
     def set_profiling(self, enable=True):
         self._check(self.lib.dgp_set_profiling(self.h, int(enable)))

@@ -62,24 +62,27 @@ def spatial_clique_params(joint_locs, S0, stride, ws, ws_max):
     return out_ws.astype(np.float32), out_max.astype(np.float32)
 
 
-def loss_forward(engine, pred, locref, feed, cfg, edges, ws, ws_max, n_frames_total, n_visible_frames_total,
-                 backward=False, visible_only=False):
-    """One call into dgp_loss_forward (or dgp_loss_backward).  pred/locref: CUDA tensors from Engine.forward; feed:
-    reference feed_dict values.  With backward=True returns (losses, (grad_pred, grad_locref))."""
-    dev = pred.device
-    nt, H, W, nj = pred.shape
+def _loss_args(dev, feed, cfg, edges, ws, ws_max, n_frames_total, n_visible_frames_total, nt, H, W, nj, pred=None,
+               locref=None, with_locref=None):
+    """(dgp_loss_cfg, dgp_loss_batch, keep-alive list) from the reference's feed_dict values (fitdgp.py:797-815)."""
     f32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32), device=dev)
     i32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32), device=dev)
     targets = f32(np.asarray(feed["targets"]).reshape(-1, nj, 2))
     vis, hid, vit = i32(feed["visible_marker_pl"]), i32(feed["hidden_marker_pl"]), i32(feed["visible_marker_in_targets_pl"])
     keep = [targets, vis, hid, vit]
     b = _lib.DgpLossBatch()
-    b.pred_dev, b.nt, b.H, b.W = pred.data_ptr(), nt, H, W
+    b.nt, b.H, b.W = nt, H, W
+    if pred is not None:
+        b.pred_dev = pred.data_ptr()
     b.targets_dev, b.nv = targets.data_ptr(), targets.shape[0]
-    if locref is not None:
+    if with_locref is None:
+        with_locref = locref is not None
+    if with_locref:
         lm, lk = f32(feed["locref_map"]), f32(feed["locref_mask"])
         keep += [lm, lk]
-        b.locref_dev, b.locref_map_dev, b.locref_mask_dev = locref.data_ptr(), lm.data_ptr(), lk.data_ptr()
+        b.locref_map_dev, b.locref_mask_dev = lm.data_ptr(), lk.data_ptr()
+        if locref is not None:
+            b.locref_dev = locref.data_ptr()
     b.visible_marker_dev, b.nbv = vis.data_ptr(), vis.numel()
     b.hidden_marker_dev, b.nbh = hid.data_ptr(), hid.numel()
     b.visible_marker_in_targets_dev = vit.data_ptr()
@@ -97,6 +100,17 @@ def loss_forward(engine, pred, locref, feed, cfg, edges, ws, ws_max, n_frames_to
                         wt, float(_get(cfg, "wt_max", 0)), float(_get(cfg, "wn_visible", 5)), float(_get(cfg, "wn_hidden", 3)),
                         float(_get(cfg, "locref_loss_weight", 0.05)), float(n_frames_total), float(n_visible_frames_total),
                         int(_get(cfg, "gm2", 1)), int(_get(cfg, "gm3", 3)))
+    return c, b, keep
+
+
+def loss_forward(engine, pred, locref, feed, cfg, edges, ws, ws_max, n_frames_total, n_visible_frames_total,
+                 backward=False, visible_only=False):
+    """One call into dgp_loss_forward (or dgp_loss_backward).  pred/locref: CUDA tensors from Engine.forward; feed:
+    reference feed_dict values.  With backward=True returns (losses, (grad_pred, grad_locref))."""
+    dev = pred.device
+    nt, H, W, nj = pred.shape
+    c, b, keep = _loss_args(dev, feed, cfg, edges, ws, ws_max, n_frames_total, n_visible_frames_total, nt, H, W, nj, pred,
+                            locref)
     out = torch.empty(6, dtype=torch.float32, device=dev)
     if backward:
         g_pred = torch.empty_like(pred)
@@ -111,6 +125,29 @@ def loss_forward(engine, pred, locref, feed, cfg, edges, ws, ws_max, n_frames_to
     vals = out.cpu().numpy()
     del keep
     return dict(zip(LOSS_KEYS, [np.float32(v) for v in vals])), all_markers
+
+
+def train_forward_backward(engine, frames, feed, cfg, edges, ws, ws_max, n_frames_total, n_visible_frames_total,
+                           visible_only=False, sync=True):
+    """Forward + loss + full backward of one fit_dgp batch (fitdgp.py:817-818 without the apply step): fills the
+    engine's gradient buffer.  frames: uint8 CUDA tensor (nt,H,W,3).  Returns the loss dict (or the device tensor of the 6
+    loss values when sync=False)."""
+    from .engine import output_dims
+    dev = frames.device
+    nt, Hin, Win, _ = frames.shape
+    _, (H, W) = output_dims(Hin, Win)
+    engine.train_enable()
+    c, b, keep = _loss_args(dev, feed, cfg, edges, ws, ws_max, n_frames_total, n_visible_frames_total, nt, H, W, engine.nj,
+                            with_locref=engine.location_refinement)
+    out = torch.empty(6, dtype=torch.float32, device=dev)
+    engine._check(engine.lib.dgp_train_forward_backward(engine.h, _ptr(frames.contiguous()), nt, Hin, Win, C.byref(c), C.byref(b),
+                                                        int(visible_only), _ptr(out), _stream(dev)))
+    if not sync:
+        engine._keep = keep  # device buffers must outlive the asynchronous launches
+        return out
+    vals = out.cpu().numpy()
+    del keep
+    return dict(zip(LOSS_KEYS, [np.float32(v) for v in vals]))
 
 
 def dgp_loss(data_batcher, dgp_cfg, variables="synthetic", device=None):
