@@ -2,8 +2,10 @@
 
 ``dgp_loss(data_batcher, dgp_cfg)`` keeps the reference's signature and 4-tuple return
 ``(loss, total_loss, total_loss_visible, placeholders)`` (:848-1144); the handles are evaluated by ``TrainSession.run``
-with the reference's feed_dict keys.  This round implements the FORWARD of the loss on the GPU (network forward +
-fused loss kernels); the backward pass / Momentum step (fitdgp.py:706-713) is the next row of SURVEY.md section 8.
+with the reference's feed_dict keys.  ``momentum_train_op`` stands in for fitdgp.py:706-713 (MomentumOptimizer + global-norm
+clipping); fetching it from ``TrainSession.run`` runs the whole training step on the GPU (network forward, fused loss
+kernels, dgrad/wgrad of every conv on tcgen05, optimizer) and, when ``torch.distributed`` is initialised, averages the
+gradients over the ranks with one NCCL all-reduce of the flat gradient buffer (``dp.allreduce_gradients``).
 """
 import ctypes as C
 from types import SimpleNamespace
@@ -178,13 +180,35 @@ def dgp_loss(data_batcher, dgp_cfg, variables="synthetic", device=None):
     return loss, loss["total_loss"], total_loss_visible, placeholders
 
 
+def momentum_train_op(total_loss, learning_rate=None, momentum=0.9, clip_norm=10.0, group=None):
+    """fitdgp.py:706-713: ``optimizer = MomentumOptimizer(learning_rate, 0.9); grads = compute_gradients(total_loss,
+    trainable_variables()); grads, _ = clip_by_global_norm(grads, 10.0); train_op = apply_gradients(...)``.
+    ``total_loss`` is the handle to differentiate (``total_loss`` or ``total_loss_visible``); ``learning_rate`` a float or
+    the placeholder handle returned by ``learning_rate_placeholder()``.  Returns the train_op handle."""
+    op = Handle("train_op", "train_op")
+    op.graph = total_loss.graph
+    op.visible_only = total_loss.kind == "total_loss_visible"
+    op.learning_rate, op.momentum, op.clip_norm, op.group = learning_rate, float(momentum), float(clip_norm), group
+    return op
+
+
+def learning_rate_placeholder():
+    """``learning_rate = TF.placeholder(tf.float32, shape=[])`` (fitdgp.py:686)."""
+    return Handle("learning_rate", "learning_rate")
+
+
 class TrainSession:
-    """``sess.run([loss, ...], feed_dict)`` for the handles of ``dgp_loss`` (forward only in this round)."""
+    """``sess.run([loss, train_op], feed_dict)`` for the handles of ``dgp_loss`` / ``momentum_train_op``."""
 
     def __init__(self, placeholders):
         self.ph = placeholders
 
+    def variables(self, graph, names):
+        """Current values of trainable variables by TF name (what ``saver.save`` would write, fitdgp.py:830-839)."""
+        return {n: graph.engine.get_variable(n) for n in names}
+
     def run(self, fetches, feed_dict):
+        from . import dp
         feed = {}
         for k, v in feed_dict.items():
             for name, hd in self.ph.items():
@@ -205,10 +229,26 @@ class TrainSession:
         frames = np.asarray(feed["inputs"])
         if frames.dtype != np.uint8:
             frames = np.clip(np.round(frames), 0, 255).astype(np.uint8)
-        pred, locref = g.engine.forward(torch.from_numpy(np.ascontiguousarray(frames)).to(g.engine.device))
-        vals, _ = loss_forward(g.engine, pred, locref, feed, g.cfg, g.edges, g.ws, g.ws_max, g.n_frames_total,
-                               g.n_visible_frames_total)
+        frames = torch.from_numpy(np.ascontiguousarray(frames)).to(g.engine.device)
+        train_ops = [f for f in flat if f.kind == "train_op"]
+        if train_ops:
+            op = train_ops[0]
+            lr = op.learning_rate
+            if isinstance(lr, Handle):
+                lr = [v for k, v in feed_dict.items() if k is lr]
+                if not lr:
+                    raise ValueError("feed_dict must provide the learning_rate placeholder")
+                lr = lr[0]
+            vals = train_forward_backward(g.engine, frames, feed, g.cfg, g.edges, g.ws, g.ws_max, g.n_frames_total,
+                                          g.n_visible_frames_total, visible_only=op.visible_only)
+            scale = dp.allreduce_gradients(g.engine, op.group)
+            g.engine.optimizer_step(float(lr), op.momentum, op.clip_norm, scale)
+        else:
+            pred, locref = g.engine.forward(frames)
+            vals, _ = loss_forward(g.engine, pred, locref, feed, g.cfg, g.edges, g.ws, g.ws_max, g.n_frames_total,
+                                   g.n_visible_frames_total)
         vals["total_loss_visible"] = np.float32(vals["visible_loss_pred"] + vals["visible_loss_locref"])
+        vals["train_op"] = None
         def build(f):
             if isinstance(f, dict):
                 return {k: build(v) for k, v in f.items()}

@@ -58,3 +58,71 @@ def test_two_gpu_shards_match_single_gpu(tmp_path):
     assert np.array_equal(got["temporal"][: T - 1], pot["temporal"].cpu().numpy())
     assert np.array_equal(got["skel"], pot["skel"].t().cpu().numpy())
     eng.close()
+
+
+CHECK_VARS = ("resnet_v1_50/conv1/weights", "resnet_v1_50/block2/unit_1/bottleneck_v1/conv2/weights",
+              "resnet_v1_50/block4/unit_3/bottleneck_v1/conv3/BatchNorm/gamma", "pose/part_pred/block4/weights",
+              "pose/locref_pred/block4/biases")
+
+
+def _train_setup(rank_seed):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import test_gpu_train as T
+    W, frames, batch, edges, S0, cfg, ws, ws_max = T._setup(seed=3)
+    from deepgraphpose_b200 import synthetic
+    frames, _ = synthetic.make_video(T.NT, T.HIN, T.WIN, T.NJ, seed=50 + rank_seed)   # each replica draws its own batch
+    return T, W, frames, batch, edges, cfg, ws, ws_max
+
+
+def _train_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from deepgraphpose_b200 import dp, fitdgp
+    from deepgraphpose_b200.engine import Engine
+    T, W, frames, batch, edges, cfg, ws, ws_max = _train_setup(rank)
+    eng = Engine(T.NJ, device=rank)
+    eng.load_weights(W)
+    fr = torch.from_numpy(frames).cuda(rank)
+    for _ in range(2):
+        fitdgp.train_forward_backward(eng, fr, batch, cfg, edges, ws, ws_max, 200, 20)
+        scale = dp.allreduce_gradients(eng)
+        eng.optimizer_step(0.005, 0.9, 10.0, scale)
+    same = dp.broadcast_check(eng, CHECK_VARS)
+    if rank == 0:
+        np.savez(os.path.join(out_dir, "dp.npz"), same=np.array(same), **{k.replace("/", "."): eng.get_variable(k) for k in CHECK_VARS})
+    dist.barrier()
+    dist.destroy_process_group()
+    eng.close()
+
+
+def test_two_gpu_data_parallel_training_matches_mean_gradient(tmp_path):
+    """2 NCCL replicas with different batches, all-reduced gradients, replicated clip + Momentum == one process that
+    averages the two batches' gradients itself (bit for bit: a two-rank sum is order independent)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from deepgraphpose_b200 import fitdgp
+    from deepgraphpose_b200.engine import Engine
+    mp.spawn(_train_worker, args=(2, 29541, str(tmp_path)), nprocs=2, join=True)
+    got = np.load(os.path.join(str(tmp_path), "dp.npz"))
+    assert bool(got["same"])
+    engs, frs = [], []
+    for r in range(2):
+        T, W, frames, batch, edges, cfg, ws, ws_max = _train_setup(r)
+        e = Engine(T.NJ, device=0)
+        e.load_weights(W)
+        engs.append(e)
+        frs.append(torch.from_numpy(frames).cuda(0))
+    for _ in range(2):
+        for e, fr in zip(engs, frs):
+            fitdgp.train_forward_backward(e, fr, batch, cfg, edges, ws, ws_max, 200, 20)
+        total = engs[0].grad_buffer() + engs[1].grad_buffer()
+        for e in engs:
+            e.grad_buffer().copy_(total)
+            e.optimizer_step(0.005, 0.9, 10.0, 0.5)
+    for k in CHECK_VARS:
+        assert np.array_equal(got[k.replace("/", ".")], engs[0].get_variable(k)), k
+    for e in engs:
+        e.close()

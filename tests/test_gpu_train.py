@@ -224,3 +224,41 @@ def test_training_step_is_bitwise_reproducible():
         bufs.append(eng.grad_buffer().clone())
         eng.close()
     assert torch.equal(bufs[0], bufs[1])
+
+
+def test_fit_dgp_shim_train_op():
+    """The reference's call surface: dgp_loss(...) -> handles; train_op = Momentum + clip (fitdgp.py:706-713);
+    [loss_eval, _] = sess.run([loss, train_op], feed_dict) (fitdgp.py:818)."""
+    from deepgraphpose_b200 import fitdgp
+    W, frames, batch, edges, S0, cfg, ws, ws_max = _setup(seed=9)
+
+    class DS:
+        pass
+    ds, db = DS(), DS()
+    ds.labels = np.asarray(batch["targets"])
+    db.S0, db.nj, db.n_frames_total, db.n_visible_frames_total, db.datasets = S0, NJ, 200, 20, [ds]
+    dgp_cfg = dict(stride=8.0, ws=1000.0, ws_max=1.2, wt=0.0, wt_max=0.0, wn_visible=5.0, wn_hidden=3.0, gamma=1, gm2=1, gm3=3,
+                   lengthscale=1, gauss_len=1, locref_loss_weight=0.05)
+    loss, total_loss, total_loss_visible, ph = fitdgp.dgp_loss(db, dgp_cfg, variables="synthetic:9")
+    learning_rate = fitdgp.learning_rate_placeholder()
+    train_op = fitdgp.momentum_train_op(total_loss, learning_rate, momentum=0.9, clip_norm=10.0)
+    sess = fitdgp.TrainSession(ph)
+    feed = {ph["inputs"]: frames, ph["targets"]: batch["targets"], ph["locref_map"]: batch["locref_map"],
+            ph["locref_mask"]: batch["locref_mask"], ph["visible_marker_pl"]: batch["visible_marker_pl"],
+            ph["hidden_marker_pl"]: batch["hidden_marker_pl"], ph["visible_marker_in_targets_pl"]: batch["visible_marker_in_targets_pl"],
+            ph["nt_batch_pl"]: NT, ph["alpha_tf"]: batch["alpha_tf"], learning_rate: 0.005}
+    hist = []
+    for _ in range(8):
+        loss_eval, _ = sess.run([loss, train_op], feed)
+        assert set(loss_eval) == set(loss)
+        hist.append(float(loss_eval["total_loss"]))
+    assert np.isfinite(hist).all() and hist[-1] < hist[0], hist
+    # step 1 of the reference (fit_dgp_labeledonly) optimises total_loss_visible
+    op_vis = fitdgp.momentum_train_op(total_loss_visible, 0.005)
+    v0 = float(sess.run(total_loss_visible, feed))
+    for _ in range(4):
+        sess.run([total_loss_visible, op_vis], feed)
+    assert float(sess.run(total_loss_visible, feed)) < v0
+    w = sess.variables(total_loss.graph, ["pose/part_pred/block4/biases"])
+    assert w["pose/part_pred/block4/biases"].shape == (NJ,) and np.abs(w["pose/part_pred/block4/biases"]).max() > 0
+    total_loss.graph.engine.close()

@@ -1,0 +1,129 @@
+#!/usr/bin/env python
+"""Training-step benchmark, BASELINE.json configs[3]: DGP semi-supervised step (visible + hidden frames, skeleton clique,
+fwd + bwd + clip/Momentum) in bf16, data-parallel over the ranks torchrun starts (one per GPU, NCCL all-reduce of the flat
+gradient buffer).  747x832 frames, nt frames per replica, nj = 4 with the locref head.  Prints one JSON line (rank 0).
+
+  python tools/bench_train.py --steps 10 --warmup 3 [--nt 10]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/bench_train.py
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import bench  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--nt", type=int, default=10)
+    ap.add_argument("--height", type=int, default=bench.H)
+    ap.add_argument("--width", type=int, default=bench.W)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    import torch.distributed as dist
+    from deepgraphpose_b200 import dp, fitdgp, synthetic
+    from deepgraphpose_b200.engine import Engine, output_dims
+    from oracle import dgp_loss as oracle_loss  # host-side batch construction only (feed_dict contract)
+    from oracle import dgp_ops
+    from test_gpu_loss import make_batch
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    H, W, NJ, nt = args.height, args.width, bench.NJ, args.nt
+    _, (hs, ws_) = output_dims(H, W)
+    rng = np.random.default_rng(100 + rank)
+    vis = [0, 3, 6][: max(1, nt // 3)]
+    labels, batch = make_batch(rng, nt, hs, ws_, NJ, vis, ((0, 1),))
+    edges = synthetic.chain_skeleton(NJ)
+    S0 = dgp_ops.skeleton_matrix(edges, NJ)
+    cfg = oracle_loss.default_dgp_cfg(gm2=1, gm3=3, wt=0.0)
+    ws, ws_max = oracle_loss.spatial_clique_params(labels, S0, cfg)
+    eng = Engine(NJ, location_refinement=True, device=local_rank)
+    eng.load_weights(synthetic.make_weights(NJ, seed=0))
+    frames_host = bench.make_frame_pool(nt, seed=1234 + rank) if (H, W) == (bench.H, bench.W) else \
+        synthetic.make_video(nt, H, W, NJ, seed=1234 + rank)[0]
+    frames = torch.from_numpy(frames_host).to(dev)
+    flops_fwd, _ = bench.conv_flops_per_frame(H, W, NJ, locref=True)
+
+    def step():
+        out = fitdgp.train_forward_backward(eng, frames, batch, cfg, edges, ws, ws_max, 1000, 100, sync=False)
+        scale = dp.allreduce_gradients(eng)
+        eng.optimizer_step(0.005, 0.9, 10.0, scale)
+        return out
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = bench.ClockSampler(local_rank)
+    sampler.start()
+    l0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = step()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    launches = eng.launch_count() - l0
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    eng.get_profile()
+    eng.set_profiling(True)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for _ in range(args.steps):
+        out = step()
+    p1.record()
+    torch.cuda.synchronize()
+    ms_prof = p0.elapsed_time(p1)
+    eng.set_profiling(False)
+    prof = eng.get_profile()
+    loss = float(out.cpu()[5])
+    if rank == 0:
+        peaks, src = bench.load_peaks()
+        peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
+        n = nt * args.steps
+        fam = {k: v[0] / args.steps for k, v in prof.items()}
+        tf = lambda gf, ms_: (gf * n / (ms_ / 1e3) / 1e12) if ms_ > 0 else None
+        line = {
+            "metric": "training frames/sec (DGP semi-supervised step: fwd + bwd + clip/Momentum)", "value": world * n / (ms / 1e3),
+            "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "configs[3]: DGP training step, %dx%d, nt=%d frames per replica (%d visible), nj=%d + locref, gm2=1 gm3=3 ws=1000 wt=0"
+                                   % (H, W, nt, len(vis), NJ), "parallelism": "dp%d, NCCL all-reduce of the 94 MB fp32 gradient buffer in %d buckets" % (world, dp.BUCKETS)},
+            "clocks": clocks, "gpu_launches": launches, "loss_after": loss, "finite": bool(np.isfinite(loss)),
+            "ms_per_step_by_family": fam, "ms_per_step_with_events": ms_prof / args.steps,
+            "tflops": {"forward_gemm": tf(flops_fwd, prof["conv_gemm"][0]), "dgrad_gemm": tf(flops_fwd, prof["dgrad_gemm"][0]),
+                       "wgrad_gemm": tf(flops_fwd, prof["wgrad_gemm"][0]),
+                       "step_total_3x_fwd": 3 * flops_fwd * n / (ms / 1e3) / 1e12, "peak": peak_tf, "peak_source": src,
+                       "note": "algorithmic FLOPs: dgrad ~ wgrad ~ forward (conv1 has no dgrad; the 2 stride-2 dgrads run 4x zero-inserted)"},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    eng.close()
+
+
+if __name__ == "__main__":
+    main()
