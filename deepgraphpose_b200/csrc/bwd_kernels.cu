@@ -108,23 +108,82 @@ __global__ void __launch_bounds__(256) relu_bn_bwd_kernel(uint4* __restrict__ g,
   }
 }
 
-// dbeta[c] (+)= S0;  dgamma[c] (+)= (S_which - beta * S0) / gamma   (sums over the blocks in index order)
-__global__ void bn_grad_finalize_kernel(const float* __restrict__ partial, int nblocks, int NS, int which, int C,
-                                        const float* __restrict__ gamma, const float* __restrict__ beta,
-                                        float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// dbeta[c] = S0;  dgamma[c] = (S_which - beta * S0) / gamma.  Block = 32 channels x 32 row groups: row group r sums the
+// partial rows r, r+32, ... (coalesced across the 32 channels), then a fixed-order tree over the row groups.
+__global__ void __launch_bounds__(1024) bn_grad_finalize_kernel(const float* __restrict__ partial, int nblocks, int NS,
+                                                                int which, int C, const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta,
+                                                                float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int cl = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
   float s0 = 0.0f, s1 = 0.0f;
-  for (int b = 0; b < nblocks; ++b) {
-    s0 += partial[((size_t)b * NS + 0) * C + c];
-    s1 += partial[((size_t)b * NS + which) * C + c];
+  if (c < C)
+    for (int b = rg; b < nblocks; b += 32) {
+      s0 += partial[((size_t)b * NS + 0) * C + c];
+      s1 += partial[((size_t)b * NS + which) * C + c];
+    }
+  __shared__ float sm0[32][33], sm1[32][33];
+  sm0[rg][cl] = s0;
+  sm1[rg][cl] = s1;
+  __syncthreads();
+  for (int st = 16; st > 0; st >>= 1) {
+    if (rg < st) {
+      sm0[rg][cl] += sm0[rg + st][cl];
+      sm1[rg][cl] += sm1[rg + st][cl];
+    }
+    __syncthreads();
   }
-  const float gm = gamma[c];
-  dbeta[c] = s0;
-  dgamma[c] = fabsf(gm) > 1e-20f ? (s1 - beta[c] * s0) / gm : 0.0f;
+  if (rg == 0 && c < C) {
+    const float gm = gamma[c];
+    dbeta[c] = sm0[0][cl];
+    dgamma[c] = fabsf(gm) > 1e-20f ? (sm1[0][cl] - beta[c] * sm0[0][cl]) / gm : 0.0f;
+  }
 }
 
-__global__ void maxpool_bwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ gout, int N, int H, int W, int C8,
+// First-maximum position (0..8, row-major in the 3x3 window) of every pooled element: one byte per channel.
+__global__ void maxpool_argmax_kernel(const uint4* __restrict__ x, int N, int H, int W, int C8, int Ho, int Wo, int pad_t,
+                                      int pad_l, uint2* __restrict__ arg, int fp16) {
+  const size_t total = (size_t)N * Ho * Wo * C8;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(t % C8);
+    size_t r = t / C8;
+    const int q = (int)(r % Wo);
+    r /= Wo;
+    const int p = (int)(r % Ho);
+    const int n = (int)(r / Ho);
+    float best[8];
+    uint32_t idx[8];
+    bool have = false;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int y = 2 * p - pad_t + dy;
+      if (y < 0 || y >= H) continue;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int xq = 2 * q - pad_l + dx;
+        if (xq < 0 || xq >= W) continue;
+        float v[8];
+        unpack8(__ldg(x + (((size_t)n * H + y) * W + xq) * C8 + c), v, fp16);
+        if (!have) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { best[j] = v[j]; idx[j] = dy * 3 + dx; }
+          have = true;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (v[j] > best[j]) { best[j] = v[j]; idx[j] = dy * 3 + dx; }
+        }
+      }
+    }
+    uint2 o;
+    o.x = idx[0] | (idx[1] << 8) | (idx[2] << 16) | (idx[3] << 24);
+    o.y = idx[4] | (idx[5] << 8) | (idx[6] << 16) | (idx[7] << 24);
+    arg[t] = o;
+  }
+}
+
+// gx[n,y,x,c] = sum over the <= 4 windows (p,q) containing (y,x) of gout[n,p,q,c] * [arg[n,p,q,c] == position of (y,x)]
+__global__ void maxpool_bwd_kernel(const uint2* __restrict__ arg, const uint4* __restrict__ gout, int N, int H, int W, int C8,
                                    int Ho, int Wo, int pad_t, int pad_l, uint4* __restrict__ gx, int fp16) {
   const size_t total = (size_t)N * H * W * C8;
   for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
@@ -146,36 +205,16 @@ __global__ void maxpool_bwd_kernel(const uint4* __restrict__ x, const uint4* __r
     if (q_hi > Wo - 1) q_hi = Wo - 1;
     for (int p = p_lo; p <= p_hi; ++p)
       for (int q = q_lo; q <= q_hi; ++q) {
-        float best[8];
-        int arg[8];
-        bool have = false;
-        int mine = -1;
-        for (int dy = 0; dy < 3; ++dy) {
-          const int y = 2 * p - pad_t + dy;
-          if (y < 0 || y >= H) continue;
-          for (int dx = 0; dx < 3; ++dx) {
-            const int xq = 2 * q - pad_l + dx;
-            if (xq < 0 || xq >= W) continue;
-            float v[8];
-            unpack8(__ldg(x + (((size_t)n * H + y) * W + xq) * C8 + c), v, fp16);
-            const int pos = dy * 3 + dx;
-            if (y == yy && xq == xx) mine = pos;
-            if (!have) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) { best[j] = v[j]; arg[j] = pos; }
-              have = true;
-            } else {
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                if (v[j] > best[j]) { best[j] = v[j]; arg[j] = pos; }
-            }
-          }
-        }
+        const uint32_t mine = (uint32_t)((yy - (2 * p - pad_t)) * 3 + (xx - (2 * q - pad_l)));
+        const size_t o = (((size_t)n * Ho + p) * Wo + q) * C8 + c;
+        const uint2 a = __ldg(arg + o);
         float gv[8];
-        unpack8(__ldg(gout + (((size_t)n * Ho + p) * Wo + q) * C8 + c), gv, fp16);
+        unpack8(__ldg(gout + o), gv, fp16);
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (arg[j] == mine) acc[j] += gv[j];
+        for (int j = 0; j < 4; ++j) {
+          if (((a.x >> (8 * j)) & 0xffu) == mine) acc[j] += gv[j];
+          if (((a.y >> (8 * j)) & 0xffu) == mine) acc[4 + j] += gv[4 + j];
+        }
       }
     gx[t] = pack8v(acc, fp16);
   }
@@ -248,23 +287,33 @@ __global__ void col2im_bwd_kernel(const float* __restrict__ g_logits, const floa
   }
 }
 
-// dbias[co] = sum over all pixels of the head gradient (one block per channel, fixed tree)
-__global__ void head_bias_grad_kernel(const float* __restrict__ g_logits, const float* __restrict__ g_locref, size_t npix,
-                                      int ctot, int nj, float* __restrict__ dbias) {
-  const int co = blockIdx.x;
-  const float* src = co < nj ? g_logits + co : (g_locref ? g_locref + (co - nj) : nullptr);
-  const int ld = co < nj ? nj : ctot - nj;
+// Head bias gradient, stage 1: block b sums a contiguous slice of the (npix, C) gradient per channel.  The thread
+// count is a multiple of C, so a thread's elements all belong to channel (global thread id) % C.
+__global__ void __launch_bounds__(256) head_bias_partial_kernel(const float* __restrict__ g, size_t n, int C, int nthreads,
+                                                                float* __restrict__ partial) {
+  const int gid = blockIdx.x * 256 + threadIdx.x;
   float acc = 0.0f;
-  if (src)
-    for (size_t i = threadIdx.x; i < npix; i += blockDim.x) acc += src[i * ld];
+  if (gid < nthreads)
+    for (size_t i = gid; i < n; i += (size_t)nthreads) acc += g[i];
   __shared__ float sm[256];
   sm[threadIdx.x] = acc;
   __syncthreads();
-  for (int s = 128; s > 0; s >>= 1) {
-    if ((int)threadIdx.x < s) sm[threadIdx.x] += sm[threadIdx.x + s];
-    __syncthreads();
+  if ((int)threadIdx.x < C) {
+    // threads t of this block with (blockIdx.x * 256 + t) % C == threadIdx.x
+    const int base = (blockIdx.x * 256) % C;
+    int t0 = (int)threadIdx.x - base;
+    if (t0 < 0) t0 += C;
+    float s = 0.0f;
+    for (int t = t0; t < 256; t += C) s += sm[t];
+    partial[(size_t)blockIdx.x * C + threadIdx.x] = s;
   }
-  if (threadIdx.x == 0) dbias[co] = sm[0];
+}
+__global__ void head_bias_final_kernel(const float* __restrict__ partial, int nblocks, int C, float* __restrict__ dbias) {
+  const int c = threadIdx.x;
+  if (c >= C) return;
+  float s = 0.0f;
+  for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * C + c];
+  dbias[c] = s;
 }
 
 int flat_grid(size_t n, int threads) {
@@ -298,14 +347,17 @@ cudaError_t launch_relu_bn_bwd(int mode, void* g, const void* act, const void* s
 
 cudaError_t launch_bn_grad_finalize(const float* partial, int nblocks, int ns, int which, int C, const float* gamma,
                                     const float* beta, float* dgamma, float* dbeta, cudaStream_t s) {
-  bn_grad_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(partial, nblocks, ns, which, C, gamma, beta, dgamma, dbeta);
+  bn_grad_finalize_kernel<<<(C + 31) / 32, 1024, 0, s>>>(partial, nblocks, ns, which, C, gamma, beta, dgamma, dbeta);
   return cudaGetLastError();
 }
 
 cudaError_t launch_maxpool_bwd(const void* x, const void* gout, int N, int H, int W, int C, int Ho, int Wo, int pad_t,
-                               int pad_l, void* gx, int fp16, cudaStream_t s) {
+                               int pad_l, void* arg_ws, void* gx, int fp16, cudaStream_t s) {
+  const size_t tout = (size_t)N * Ho * Wo * (C / 8);
+  maxpool_argmax_kernel<<<flat_grid(tout, 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(x), N, H, W, C / 8, Ho, Wo, pad_t,
+                                                             pad_l, reinterpret_cast<uint2*>(arg_ws), fp16);
   const size_t total = (size_t)N * H * W * (C / 8);
-  maxpool_bwd_kernel<<<flat_grid(total, 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(x),
+  maxpool_bwd_kernel<<<flat_grid(total, 256), 256, 0, s>>>(reinterpret_cast<const uint2*>(arg_ws),
                                                            reinterpret_cast<const uint4*>(gout), N, H, W, C / 8, Ho, Wo,
                                                            pad_t, pad_l, reinterpret_cast<uint4*>(gx), fp16);
   return cudaGetLastError();
@@ -334,9 +386,14 @@ cudaError_t launch_col2im_bwd(const float* g_logits, const float* g_locref, int 
   return cudaGetLastError();
 }
 
-cudaError_t launch_head_bias_grad(const float* g_logits, const float* g_locref, size_t npix, int ctot, int nj,
-                                  float* dbias, cudaStream_t s) {
-  head_bias_grad_kernel<<<ctot, 256, 0, s>>>(g_logits, g_locref, npix, ctot, nj, dbias);
+int head_bias_blocks() { return 148; }
+
+// g: (npix, C) fp32; partial: [head_bias_blocks()][C] workspace
+cudaError_t launch_head_bias_grad(const float* g, size_t npix, int C, float* partial, float* dbias, cudaStream_t s) {
+  if (C > 256) return cudaErrorInvalidValue;
+  const int nthreads = (148 * 256 / C) * C;
+  head_bias_partial_kernel<<<148, 256, 0, s>>>(g, npix * (size_t)C, C, nthreads, partial);
+  head_bias_final_kernel<<<1, 256, 0, s>>>(partial, 148, C, dbias);
   return cudaGetLastError();
 }
 

@@ -78,14 +78,16 @@ cudaError_t launch_relu_bn_bwd(int mode, void* g, const void* act, const void* s
                                int Wx, float* partial, int fp16, cudaStream_t s);
 cudaError_t launch_bn_grad_finalize(const float* partial, int nblocks, int ns, int which, int C, const float* gamma,
                                     const float* beta, float* dgamma, float* dbeta, cudaStream_t s);
+// arg_ws: N*Ho*Wo*C bytes (first-maximum position of every pooled element)
 cudaError_t launch_maxpool_bwd(const void* x, const void* gout, int N, int H, int W, int C, int Ho, int Wo, int pad_t,
-                               int pad_l, void* gx, int fp16, cudaStream_t s);
+                               int pad_l, void* arg_ws, void* gx, int fp16, cudaStream_t s);
 cudaError_t launch_upsample2(const void* in, int N, int P, int Q, int C, void* out, int H, int W, cudaStream_t s);
 cudaError_t launch_scatter_add2(const void* d, int N, int P, int Q, int C, void* gx, int H, int W, int fp16,
                                 cudaStream_t s);
 cudaError_t launch_col2im_bwd(const float* g_logits, const float* g_locref, int N, int h, int w, int ctot, int nj,
                               void* dG, int Kd, int fp16, cudaStream_t s);
-cudaError_t launch_head_bias_grad(const float* g_logits, const float* g_locref, size_t npix, int ctot, int nj,
-                                  float* dbias, cudaStream_t s);
+int head_bias_blocks();
+// g (npix, C) fp32 -> dbias[C]; partial: [head_bias_blocks()][C] floats of workspace
+cudaError_t launch_head_bias_grad(const float* g, size_t npix, int C, float* partial, float* dbias, cudaStream_t s);
 
 }  // namespace dgp

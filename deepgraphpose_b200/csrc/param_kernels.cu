@@ -47,29 +47,24 @@ __global__ void refresh_bn_kernel(const float* __restrict__ gamma, const float* 
 }
 
 // Data-gradient operand of one conv: wd[ci][T-1-tap][co] = round16(w[co][tap][ci] * scale[co])  (the BN scale of the
-// output channel is folded in, so the dgrad GEMM consumes dy = dL/d(BN output) directly).  One thread per 8 output
-// elements (consecutive co); reads are strided gathers over a matrix that lives in L2.
-__global__ void build_dgrad_w_kernel(const float* __restrict__ w, const float* __restrict__ scale, int Cout, int taps,
-                                     int Cin, int rows_w, uint16_t* __restrict__ wd, int Kd, int fp16) {
-  // w: [rows_w >= Cout][taps*Cin]; wd: [Cin][Kd], Kd >= taps*Cout (zero padded)
-  const size_t total = (size_t)Cin * (Kd >> 3);
-  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-    const int k8 = (int)(t % (size_t)(Kd >> 3)) * 8;
-    const int ci = (int)(t / (size_t)(Kd >> 3));
-    __align__(16) uint16_t v[8];
+// output channel is folded in, so the dgrad GEMM consumes dy = dL/d(BN output) directly).  Per tap this is a
+// Cout x Cin -> Cin x Cout transpose: 32 x 32 tiles through shared memory, coalesced on both sides.
+__global__ void __launch_bounds__(256) build_dgrad_w_kernel(const float* __restrict__ w, const float* __restrict__ scale,
+                                                            int Cout, int taps, int Cin, uint16_t* __restrict__ wd, int fp16) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int tap = blockIdx.z, ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
+  const size_t K = (size_t)taps * Cin, Kd = (size_t)taps * Cout;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int kk = k8 + j;
-      float f = 0.0f;
-      if (kk < taps * Cout) {
-        const int tapd = kk / Cout;
-        const int co = kk - tapd * Cout;
-        const int tap = taps - 1 - tapd;
-        f = w[(size_t)co * ((size_t)taps * Cin) + (size_t)tap * Cin + ci] * (scale ? scale[co] : 1.0f);
-      }
-      v[j] = cvt16(f, fp16);
-    }
-    *reinterpret_cast<uint4*>(wd + (size_t)ci * Kd + k8) = *reinterpret_cast<const uint4*>(v);
+  for (int j = 0; j < 4; ++j) {
+    const int co = co0 + ty + 8 * j;
+    tile[ty + 8 * j][tx] = w[(size_t)co * K + (size_t)tap * Cin + ci0 + tx] * (scale ? scale[co] : 1.0f);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int ci = ci0 + ty + 8 * j;
+    wd[(size_t)ci * Kd + (size_t)(taps - 1 - tap) * Cout + co0 + tx] = cvt16(tile[tx][ty + 8 * j], fp16);
   }
 }
 
@@ -162,8 +157,10 @@ cudaError_t launch_refresh_bn(const float* gamma, const float* beta, const float
 
 cudaError_t launch_build_dgrad_w(const float* w, const float* scale, int Cout, int taps, int Cin, int rows_w, void* wd,
                                  int Kd, int fp16, cudaStream_t s) {
-  build_dgrad_w_kernel<<<flat_grid((size_t)Cin * (Kd / 8), 256), 256, 0, s>>>(w, scale, Cout, taps, Cin, rows_w,
-                                                                               reinterpret_cast<uint16_t*>(wd), Kd, fp16);
+  if (Cout % 32 || Cin % 32 || Kd != taps * Cout) return cudaErrorInvalidValue;
+  (void)rows_w;
+  build_dgrad_w_kernel<<<dim3(Cin / 32, Cout / 32, taps), 256, 0, s>>>(w, scale, Cout, taps, Cin,
+                                                                       reinterpret_cast<uint16_t*>(wd), fp16);
   return cudaGetLastError();
 }
 

@@ -203,7 +203,13 @@ int build_backward(dgp_handle* h, Plan* pl) {
   {
     float* dbias = ts->grads + h->n_w + 2 * h->n_ch;
     const size_t npix = (size_t)B * 4 * hf * wf;
-    bw->steps.push_back({7, 1, [=](cudaStream_t s) { return launch_head_bias_grad(g_logits, g_locref, npix, ctot, nj, dbias, s); }});
+    bn_need = std::max(bn_need, (size_t)head_bias_blocks() * 256 * sizeof(float));
+    bw->steps.push_back({7, g_locref ? 4 : 2, [=](cudaStream_t s) {
+                           float* partial = (float*)ts->bn_partial.p;
+                           cudaError_t e = launch_head_bias_grad(g_logits, npix, nj, partial, dbias, s);
+                           if (e == cudaSuccess && g_locref) e = launch_head_bias_grad(g_locref, npix, 2 * nj, partial, dbias + nj, s);
+                           return e;
+                         }});
   }
   {
     const ConvLayer& Lh = h->layers[h->head_layer];
@@ -277,7 +283,9 @@ int build_backward(dgp_handle* h, Plan* pl) {
     void* Gp = gbuf[gi];
     const void* c1 = pl->c1;
     const int H1 = pl->H1, W1 = pl->W1, Hp = pl->Hp, Wp = pl->Wp, pt = pl->pool_pad_t, plft = pl->pool_pad_l;
-    bw->steps.push_back({7, 1, [=](cudaStream_t s) { return launch_maxpool_bwd(c1, Gp, B, H1, W1, 64, Hp, Wp, pt, plft, g_c1, fp16, s); }});
+    void* arg_ws = nullptr;
+    if ((rc = alloc_buf(h, pl, (size_t)B * Hp * Wp * 64 + 1024, &arg_ws))) return rc;
+    bw->steps.push_back({7, 2, [=](cudaStream_t s) { return launch_maxpool_bwd(c1, Gp, B, H1, W1, 64, Hp, Wp, pt, plft, arg_ws, g_c1, fp16, s); }});
     const ConvLayer& L = h->layers[h->conv1_layer];
     add_mask(h, bw.get(), 0, g_c1, c1, nullptr, B * H1 * W1, 64, 0, 0, 0, 0, &L, nullptr, &bn_need);
     WgradParams wp;

@@ -232,34 +232,53 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const __grid_
   }
 }
 
-// grad[co][kk] = rowscale[co] * mask[co][kk] * sum_s partial[(m_blk, n_blk, s)][co % 128][kk % 256]   (fixed order)
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partials, int Cout, int Kw, int nnb, int splits,
-                                    const float* __restrict__ rowscale, const float* __restrict__ mask,
-                                    float* __restrict__ grad, int accumulate) {
+// grad[co][kk] = rowscale[co] * mask[co][kk] * sum_s partial[(m_blk, n_blk, s)][co % 128][kk % 256].
+// SG threads share one float4 of the gradient: thread (e, sg) sums the splits sg, sg + SG, ...; the SG partial sums are
+// then added in index order by one thread (fixed order: bitwise reproducible, no atomics).
+template <int SG>
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partials, int Cout, int Kw, int nnb,
+                                                           int splits, const float* __restrict__ rowscale,
+                                                           const float* __restrict__ mask, float* __restrict__ grad,
+                                                           int accumulate) {
+  constexpr int EPB = 256 / SG;  // float4 elements per block
+  const int e = threadIdx.x % EPB, sg = threadIdx.x / EPB;
   const size_t total = (size_t)Cout * (Kw >> 2);
-  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-    const int kk = (int)(t % (size_t)(Kw >> 2)) * 4;
-    const int co = (int)(t / (size_t)(Kw >> 2));
+  const size_t t = (size_t)blockIdx.x * EPB + e;
+  __shared__ float4 sm[SG > 1 ? 256 : 1];
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  int co = 0, kk = 0;
+  if (t < total) {
+    kk = (int)(t % (size_t)(Kw >> 2)) * 4;
+    co = (int)(t / (size_t)(Kw >> 2));
     const int m_blk = co >> 7, n_blk = kk >> 8;
     const float* src = partials + ((size_t)(m_blk * nnb + n_blk) * splits * 128 + (size_t)(co & 127)) * 256 + (kk & 255);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int s = 0; s < splits; ++s) {
+    for (int s = sg; s < splits; s += SG) {
       const float4 v = *reinterpret_cast<const float4*>(src + (size_t)s * 128 * 256);
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
-    const float rs = rowscale ? rowscale[co] : 1.0f;
-    acc.x *= rs; acc.y *= rs; acc.z *= rs; acc.w *= rs;
-    float4* g = reinterpret_cast<float4*>(grad + (size_t)co * Kw + kk);
-    if (mask) {
-      const float4 m = *reinterpret_cast<const float4*>(mask + (size_t)co * Kw + kk);
-      acc.x *= m.x; acc.y *= m.y; acc.z *= m.z; acc.w *= m.w;
-    }
-    if (accumulate) {
-      const float4 o = *g;
-      acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
-    }
-    *g = acc;
   }
+  if (SG > 1) {
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    if (sg != 0) return;
+    for (int j = 1; j < SG; ++j) {
+      const float4 v = sm[j * EPB + e];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  if (t >= total) return;
+  const float rs = rowscale ? rowscale[co] : 1.0f;
+  acc.x *= rs; acc.y *= rs; acc.z *= rs; acc.w *= rs;
+  float4* g = reinterpret_cast<float4*>(grad + (size_t)co * Kw + kk);
+  if (mask) {
+    const float4 m = *reinterpret_cast<const float4*>(mask + (size_t)co * Kw + kk);
+    acc.x *= m.x; acc.y *= m.y; acc.z *= m.z; acc.w *= m.w;
+  }
+  if (accumulate) {
+    const float4 o = *g;
+    acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+  }
+  *g = acc;
 }
 
 }  // namespace
@@ -268,7 +287,7 @@ void wgrad_plan(WgradParams* p, int num_sms) {
   p->num_m_blocks = (p->Cout + 127) / 128;
   p->num_n_blocks = (p->Kw + 255) / 256;
   const int base = p->num_m_blocks * p->num_n_blocks;
-  int splits = (2 * num_sms) / base;
+  int splits = num_sms / base;  // one wave of work items
   if (splits < 1) splits = 1;
   const int max_splits = (p->num_pix_blocks + 3) / 4;  // at least 4 pixel blocks per split
   if (splits > max_splits) splits = max_splits;
@@ -301,10 +320,17 @@ cudaError_t launch_wgrad_gemm(const WgradParams& p, int num_sms, cudaStream_t st
 cudaError_t launch_wgrad_reduce(const WgradParams& p, const float* rowscale, const float* mask, float* grad,
                                 int accumulate, cudaStream_t stream) {
   const size_t total = (size_t)p.Cout * (p.Kw / 4);
-  size_t g = (total + 255) / 256;
-  if (g > 148 * 8) g = 148 * 8;
-  wgrad_reduce_kernel<<<(int)g, 256, 0, stream>>>(p.partials, p.Cout, p.Kw, p.num_n_blocks, p.splits, rowscale, mask,
-                                                  grad, accumulate);
+  // few elements and many splits (the narrow, pixel-rich layers of block 1/2): spread the split loop over threads
+  if (p.splits >= 32 && total <= 32768) {
+    wgrad_reduce_kernel<16><<<(unsigned)((total + 15) / 16), 256, 0, stream>>>(p.partials, p.Cout, p.Kw, p.num_n_blocks,
+                                                                             p.splits, rowscale, mask, grad, accumulate);
+  } else if (p.splits >= 8 && total <= 262144) {
+    wgrad_reduce_kernel<4><<<(unsigned)((total + 63) / 64), 256, 0, stream>>>(p.partials, p.Cout, p.Kw, p.num_n_blocks,
+                                                                            p.splits, rowscale, mask, grad, accumulate);
+  } else {
+    wgrad_reduce_kernel<1><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p.partials, p.Cout, p.Kw, p.num_n_blocks,
+                                                                              p.splits, rowscale, mask, grad, accumulate);
+  }
   return cudaGetLastError();
 }
 
