@@ -864,8 +864,6 @@ int dgp_run_loss_impl(dgp_handle* h, const dgp_loss_cfg* cfg, const dgp_loss_bat
                     float* targets_all_dev, float* grad_pred_dev, float* grad_locref_dev, int visible_only, void* stream) {
   if (!h) return DGP_ERR_INVALID;
   if (!cfg || !b || !losses_dev || !b->pred_dev) return fail(h, DGP_ERR_INVALID, "dgp_loss_forward: null argument");
-  if (grad_pred_dev && cfg->wt > 0.0f)
-    return fail(h, DGP_ERR_UNSUPPORTED, "dgp_loss_backward: the temporal clique (wt > 0) has no backward yet");
   const int nj = h->cfg.num_joints;
   if (b->nt < 1 || b->nbv < 0 || b->nbh < 0 || b->nbv + b->nbh > b->nt * nj)
     return fail(h, DGP_ERR_INVALID, "dgp_loss_forward: bad marker counts");
@@ -881,7 +879,7 @@ int dgp_run_loss_impl(dgp_handle* h, const dgp_loss_cfg* cfg, const dgp_loss_bat
     return fail(h, DGP_ERR_INVALID, "dgp_loss_forward: skeleton without ws/ws_max");
   CU_OK(h, cudaSetDevice(h->device));
   const int nm = b->nt * nj;
-  const size_t need = (size_t)nm * 2 * 4 * 3 + (size_t)(b->nbv + b->nbh + 1) * 16 + (size_t)nm * 4 + 256;
+  const size_t need = (size_t)nm * 2 * 4 * 3 + (size_t)(b->nbv + b->nbh + 1) * 16 + (size_t)nm * 4 + (size_t)nm * 16 + 512;
   int rc = ensure(h, &h->loss_ws, need);
   if (rc) return rc;
   char* w = (char*)h->loss_ws.p;
@@ -890,7 +888,9 @@ int dgp_run_loss_impl(dgp_handle* h, const dgp_loss_cfg* cfg, const dgp_loss_bat
   float* norm = (float*)w; w += (size_t)nm * 2 * 4;
   w = (char*)(((uintptr_t)w + 15) & ~(uintptr_t)15);
   float4* partials = (float4*)w; w += (size_t)(b->nbv + b->nbh + 1) * 16;
-  float* meanflow = (float*)w;
+  float* meanflow = (float*)w; w += (size_t)nm * 4;
+  w = (char*)(((uintptr_t)w + 15) & ~(uintptr_t)15);
+  float4* boxgrad = (float4*)w;
   if ((b->H & 1) || (b->W & 1) || cfg->gauss_len < 1.0f || cfg->gauss_len >= 5.0f || !(cfg->gamma > 0.0f))
     return fail(h, DGP_ERR_INVALID, "dgp_loss: scoremap dims must be even, gauss_len in [1,5), gamma > 0");
   {
@@ -921,6 +921,7 @@ int dgp_run_loss_impl(dgp_handle* h, const dgp_loss_cfg* cfg, const dgp_loss_bat
   a.n_vis_total = cfg->n_visible_frames_total; a.n_hid_total = cfg->n_frames_total - cfg->n_visible_frames_total;
   a.gm2 = cfg->gm2; a.gm3 = cfg->gm3;
   a.all_markers = all; a.partials = partials; a.meanflow = meanflow; a.out = losses_dev;
+  a.boxgrad = grad_pred_dev ? boxgrad : nullptr;
   if (a.wt > 0.0f && a.flow != nullptr && !a.wt_batch) return fail(h, DGP_ERR_INVALID, "dgp_loss_forward: wt > 0 needs wt_batch");
   CU_OK(h, launch_dgp_loss(a, (cudaStream_t)stream));
   h->launches += 4;

@@ -50,6 +50,7 @@ struct LossArgs {
   float* all_markers;   // scratch (nt*nj,2): targets_all_marker
   float4* partials;     // scratch (nbv+nbh)
   float* meanflow;      // scratch ((nt-1)*nj)
+  float4* boxgrad;      // scratch ((nt-1)*nj): d meanflow / d (y1, x1, y2, x2) of the crop box, or nullptr (forward only)
   float* out;           // [6]
 };
 cudaError_t launch_dgp_loss(const LossArgs& a, cudaStream_t stream);

@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(kLossThreads) marker_loss_kernel(
 // mean over tf.image.crop_and_resize(flow, box, [Hin, Win]) per (t, j) (fitdgp.py:1085-1110), bilinear, extrapolation 0.
 __global__ void __launch_bounds__(kLossThreads) flow_box_mean_kernel(const float* __restrict__ flow, const float* __restrict__ all,
                                                                    int nt, int nj, int Hin, int Win, float stride,
-                                                                   float* __restrict__ meanflow) {
+                                                                   float* __restrict__ meanflow, float4* __restrict__ boxgrad) {
   __shared__ float sh[kLossThreads / 32];
   const int t = blockIdx.x / nj, j = blockIdx.x - t * nj;
   const float* a0 = all + ((size_t)t * nj + j) * 2;
@@ -156,6 +156,7 @@ __global__ void __launch_bounds__(kLossThreads) flow_box_mean_kernel(const float
   const float sx = Win > 1 ? (x2 - x1) * (float)(Win - 1) / (float)(Win - 1) : 0.0f;
   const float* img = flow + (size_t)t * Hin * Win;
   float acc = 0.0f;
+  float gy1 = 0.0f, gx1 = 0.0f, gy2 = 0.0f, gx2 = 0.0f;  // d sum / d (y1, x1, y2, x2): tf CropAndResizeGradBoxes
   for (int p = threadIdx.x; p < Hin * Win; p += blockDim.x) {
     const int yy = p / Win, xx = p - yy * Win;
     const float ys = Hin > 1 ? y1 * (float)(Hin - 1) + (float)yy * sy : 0.5f * (y1 + y2) * (float)(Hin - 1);
@@ -167,8 +168,21 @@ __global__ void __launch_bounds__(kLossThreads) flow_box_mean_kernel(const float
     const float tl = img[yl * Win + xl], tr = img[yl * Win + xh], bl = img[yh * Win + xl], br = img[yh * Win + xh];
     const float top = tl + (tr - tl) * lx, bot = bl + (br - bl) * lx;
     acc += top + (bot - top) * ly;
+    if (boxgrad != nullptr) {
+      const float gy = (bl - tl) * (1.0f - lx) + (br - tr) * lx;   // d value / d in_y
+      const float gx = (tr - tl) * (1.0f - ly) + (br - bl) * ly;   // d value / d in_x
+      if (Hin > 1) { gy1 += gy * (float)(Hin - 1 - yy); gy2 += gy * (float)yy; }
+      else { gy1 += gy * 0.5f * (float)(Hin - 1); gy2 += gy * 0.5f * (float)(Hin - 1); }
+      if (Win > 1) { gx1 += gx * (float)(Win - 1 - xx); gx2 += gx * (float)xx; }
+      else { gx1 += gx * 0.5f * (float)(Win - 1); gx2 += gx * 0.5f * (float)(Win - 1); }
+    }
   }
   acc = block_sum(acc, sh);
+  if (boxgrad != nullptr) {
+    gy1 = block_sum(gy1, sh); gx1 = block_sum(gx1, sh); gy2 = block_sum(gy2, sh); gx2 = block_sum(gx2, sh);
+    const float k = 1.0f / (float)(Hin * Win);
+    if (threadIdx.x == 0) boxgrad[blockIdx.x] = make_float4(gy1 * k, gx1 * k, gy2 * k, gx2 * k);
+  }
   if (threadIdx.x == 0) meanflow[blockIdx.x] = acc / (float)(Hin * Win);
 }
 
@@ -255,7 +269,7 @@ __device__ __forceinline__ void blur_weights(int pos, int n, int radius, const f
   }
 }
 
-// d total_loss / d pred and d total_loss / d locref (wt == 0).  One CTA per listed marker, three passes over its plane:
+// d total_loss / d pred and d total_loss / d locref.  One CTA per listed marker, three passes over its plane:
 //   A  max of the Gaussian bump (value + pixel) and of sigmoid(x) (confidence c + its pixel)
 //   B  the marker-level sums that multiply dc and d mu
 //   C  per-pixel gradient = direct term + (pixel == argmax) * confidence term + soft-argmax backward of dL/dmu
@@ -268,7 +282,9 @@ __global__ void __launch_bounds__(kLossThreads) marker_loss_bwd_kernel(
     const float4* __restrict__ part, int nt, int H, int W, int nj, float inv2l2, int gm2, int gm3, float gamma, int radius,
     float sigma, const int* __restrict__ edges, int nl, const float* __restrict__ ws, const float* __restrict__ ws_max,
     float stride, float n_vis_total, float n_hid_total, float wn_visible, float wn_hidden, float locref_weight,
-    int visible_only, float* __restrict__ g_pred, float* __restrict__ g_locref) {
+    int visible_only, const float* __restrict__ meanflow, const float4* __restrict__ boxgrad,
+    const float* __restrict__ wt_batch, float wt_max, int Hin, int Win, const float* __restrict__ losses,
+    float* __restrict__ g_pred, float* __restrict__ g_locref) {
   __shared__ float shf[kLossThreads / 32];
   __shared__ int shi[kLossThreads / 32];
   __shared__ float s_cnt[3];
@@ -386,6 +402,48 @@ __global__ void __launch_bounds__(kLossThreads) marker_loss_bwd_kernel(
       }
     }
   }
+  // + temporal clique (fitdgp.py:1078-1124): wt_loss = c * || (relu(delta - wt_max) + wt_max) * inv ||_F.  delta and,
+  // through tf.image.crop_and_resize's box gradient, the flow weight inv both depend on mu of frames k and k+1.
+  if (meanflow != nullptr && losses[4] > 0.0f) {
+    const float cw = n_vis_total / fnbv / (n_vis_total + n_hid_total) / wn_visible;
+    const float nxi = (float)Hin, nyi = (float)Win;
+    for (int e = 0; e < 2; ++e) {
+      const int k = e == 0 ? t : t - 1;          // pair (k, k+1); e == 0: this marker is the first frame of the pair
+      if (k < 0 || k + 1 >= nt) continue;
+      const float* a0 = all + ((size_t)k * nj + j) * 2;
+      const float* a1 = all + ((size_t)(k + 1) * nj + j) * 2;
+      const float r0 = a0[0] * stride + 0.5f * stride, c0 = a0[1] * stride + 0.5f * stride;
+      const float r1 = a1[0] * stride + 0.5f * stride, c1 = a1[1] * stride + 0.5f * stride;
+      const float rme = e == 0 ? r0 : r1, cme = e == 0 ? c0 : c1, rot = e == 0 ? r1 : r0, cot = e == 0 ? c1 : c0;
+      const float dlt = sqrtf((r0 - r1) * (r0 - r1) + (c0 - c1) * (c0 - c1));
+      const float av = fmaxf(dlt - wt_max, 0.0f) + wt_max;
+      const float mf = meanflow[k * nj + j];
+      const float u = 1.0f / (mf + 1e-10f);
+      const float u1 = fminf(u, 1.0f);
+      const float wk = wt_batch[k] / (float)H / (float)W;
+      const float inv = fminf(expf(logf(u1) * 3.0f), 1.0f) * wk;
+      const float v = av * inv;
+      const float gv = cw * cw * v / losses[4];  // dL/dv = c * v / ||.||_F, ||.||_F = wt_loss / c
+      if (dlt > wt_max && dlt > 0.0f) {
+        Lr += gv * inv * (rme - rot) / dlt * stride;
+        Lc += gv * inv * (cme - cot) / dlt * stride;
+      }
+      if (u <= 1.0f) {
+        const float dinv = -3.0f * u1 * u1 * u * u * wk;   // d(u^3)/d mf = -3 u^4
+        const float4 bg = boxgrad[k * nj + j];
+        // which end of the pair owns the box edges (ties split the gradient, as reduce_min / reduce_max do)
+        const float wmin_r = rme < rot ? 1.0f : (rme == rot ? 0.5f : 0.0f), wmax_r = rme > rot ? 1.0f : (rme == rot ? 0.5f : 0.0f);
+        const float wmin_c = cme < cot ? 1.0f : (cme == cot ? 0.5f : 0.0f), wmax_c = cme > cot ? 1.0f : (cme == cot ? 0.5f : 0.0f);
+        float dr_ = 0.0f, dc_ = 0.0f;
+        if (fminf(r0, r1) - 10.0f > 0.0f) dr_ += wmin_r * bg.x / nxi;
+        if (fmaxf(r0, r1) + 10.0f < nxi) dr_ += wmax_r * bg.z / nxi;
+        if (fminf(c0, c1) - 10.0f > 0.0f) dc_ += wmin_c * bg.y / nyi;
+        if (fmaxf(c0, c1) + 10.0f < nyi) dc_ += wmax_c * bg.w / nyi;
+        Lr += gv * av * dinv * dr_ * stride;
+        Lc += gv * av * dinv * dc_ * stride;
+      }
+    }
+  }
   // pass C
   const float g2 = gamma * 1.4426950408889634f;
   const float m2 = norm[2 * m], s0 = norm[2 * m + 1];
@@ -443,7 +501,7 @@ cudaError_t launch_dgp_loss(const LossArgs& a, cudaStream_t stream) {
   const bool temporal = a.wt > 0.0f && a.flow != nullptr && a.nt > 1;
   if (temporal)
     flow_box_mean_kernel<<<(a.nt - 1) * a.nj, kLossThreads, 0, stream>>>(a.flow, a.all_markers, a.nt, a.nj, a.Hin, a.Win,
-                                                                        a.stride, a.meanflow);
+                                                                        a.stride, a.meanflow, a.boxgrad);
   loss_finalize_kernel<<<1, 32, 0, stream>>>(a.partials, a.nbv, a.nbh, a.all_markers, a.nt, a.nj, a.H, a.W, a.edges, a.nl,
                                              a.ws, a.ws_max, temporal ? a.meanflow : nullptr, a.wt_batch, a.wt, a.wt_max,
                                              a.stride, a.n_vis_total, a.n_hid_total, a.wn_visible, a.wn_hidden,
@@ -454,6 +512,7 @@ cudaError_t launch_dgp_loss(const LossArgs& a, cudaStream_t stream) {
 cudaError_t launch_dgp_loss_backward(const LossArgs& a, const float* norm, float gamma, float gauss_len, int visible_only,
                                      float* g_pred, float* g_locref, cudaStream_t stream) {
   const int nb = a.nbv + a.nbh;
+  const bool temporal = a.wt > 0.0f && a.flow != nullptr && a.nt > 1;
   cudaError_t e = cudaMemsetAsync(g_pred, 0, (size_t)a.nt * a.H * a.W * a.nj * sizeof(float), stream);
   if (e != cudaSuccess) return e;
   if (g_locref) {
@@ -465,7 +524,8 @@ cudaError_t launch_dgp_loss_backward(const LossArgs& a, const float* norm, float
         a.pred, a.locref, a.locref_map, a.locref_mask, a.all_markers, a.mu, norm, a.visible, a.nbv, a.hidden, a.nbh,
         a.partials, a.nt, a.H, a.W, a.nj, 1.0f / (2.0f * a.lengthscale * a.lengthscale), a.gm2, a.gm3, gamma,
         (int)gauss_len, gauss_len, a.edges, a.nl, a.ws, a.ws_max, a.stride, a.n_vis_total, a.n_hid_total, a.wn_visible,
-        a.wn_hidden, a.locref_weight, visible_only, g_pred, g_locref);
+        a.wn_hidden, a.locref_weight, visible_only, temporal ? a.meanflow : nullptr, a.boxgrad, a.wt_batch, a.wt_max, a.Hin,
+        a.Win, a.out, g_pred, g_locref);
   return cudaGetLastError();
 }
 

@@ -145,8 +145,8 @@ int dgp_loss_forward(dgp_handle* h, const dgp_loss_cfg* cfg, const dgp_loss_batc
  * fit_dgp_labeledonly differentiates total_loss_visible, fitdgp.py:416 -> visible_only = 1): gradients of the loss
  * w.r.t. the head outputs, float32 (nt,H,W,nj) and (nt,H,W,2nj) (grad_locref_dev may be NULL).  They flow through the
  * cross-entropy labels (Gaussian targets -> soft-argmax), the confidence max and the (1 - c) weights exactly as in the
- * TF graph.  wt > 0 (temporal clique) is DGP_ERR_UNSUPPORTED here.  The network backward and the Momentum step are
- * dgp_train_forward_backward / dgp_optimizer_step below. */
+ * TF graph, including the temporal clique's path through tf.image.crop_and_resize's box gradient (wt > 0).  The network
+ * backward and the Momentum step are dgp_train_forward_backward / dgp_optimizer_step below. */
 int dgp_loss_backward(dgp_handle* h, const dgp_loss_cfg* cfg, const dgp_loss_batch* batch, float* losses_dev,
                       float* grad_pred_dev, float* grad_locref_dev, int visible_only, void* stream);
 
@@ -166,8 +166,7 @@ int dgp_estimate_pose_host(dgp_handle* h, const uint8_t* frames_host, int T, int
 /* Allocates gradients, momentum accumulators and the transposed (dgrad) weight operands. Call after finalize. */
 int dgp_train_enable(dgp_handle* h);
 /* frames_dev uint8 (nt,H,W,3); batch->pred_dev / locref_dev are ignored (the handle's own head outputs are used), all other
- * members as in dgp_loss_forward.  losses_dev[6] as in dgp_loss_forward.  wt > 0 is DGP_ERR_UNSUPPORTED (no backward of the
- * temporal clique yet). */
+ * members as in dgp_loss_forward.  losses_dev[6] as in dgp_loss_forward. */
 int dgp_train_forward_backward(dgp_handle* h, const uint8_t* frames_dev, int nt, int H, int W, const dgp_loss_cfg* cfg,
                                const dgp_loss_batch* batch, int visible_only, float* losses_dev, void* stream);
 /* g' = g * grad_scale; g' *= clip_norm / max(||g'||, clip_norm) (clip_norm <= 0: no clipping);

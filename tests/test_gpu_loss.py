@@ -66,7 +66,8 @@ def test_loss_forward_matches_oracle(case):
 
 
 @pytest.mark.parametrize("case", [dict(gm2=1, gm3=3), dict(gm2=2, gm3=3), dict(gm2=0, gm3=0), dict(gm2=1, gm3=0),
-                                  dict(gm2=1, gm3=3, visible_only=True)])
+                                  dict(gm2=1, gm3=3, visible_only=True), dict(gm2=1, gm3=3, wt=20.0), dict(gm2=1, gm3=0, wt=60.0),
+                                  dict(gm2=1, gm3=3, wt=40.0, wt_max=30.0)])
 def test_loss_backward_matches_oracle_autograd(case):
     """d total_loss / d pred and d locref from dgp_loss_backward vs torch autograd through the oracle graph (gradients
     flow through the Gaussian targets into the soft-argmax, through the confidence max and the (1-c) weights)."""
@@ -79,7 +80,16 @@ def test_loss_backward_matches_oracle_autograd(case):
     loc = torch.from_numpy(rng.standard_normal((nt, H, W, 2 * nj)).astype(np.float32)).requires_grad_(True)
     edges = synthetic.chain_skeleton(nj)
     S0 = dgp_ops.skeleton_matrix(edges, nj)
-    cfg = oracle_loss.default_dgp_cfg(gm2=case["gm2"], gm3=case["gm3"], wt=0.0)
+    wt = case.get("wt", 0.0)
+    cfg = oracle_loss.default_dgp_cfg(gm2=case["gm2"], gm3=case["gm3"], wt=wt, wt_max=case.get("wt_max", 0.0))
+    if wt > 0:
+        # temporal clique: smooth flow magnitude around 1 so that both branches of min(1/m, 1) occur, and box edges that
+        # are clipped (markers near the border) as well as free ones
+        yy, xx = np.meshgrid(np.arange(8 * H), np.arange(8 * W), indexing="ij")
+        batch["vector_field_tf"] = np.stack([0.9 + 0.8 * np.sin(yy / (7.0 + t)) * np.cos(xx / (9.0 + 2 * t)) + 0.3 * rng.uniform(size=yy.shape)
+                                             for t in range(nt - 1)])
+        batch["wt_batch_pl"] = np.ones(nt - 1) * wt
+        batch["wt_batch_mask_pl"] = np.array([1.0, 0.0, 1.0])
     ws, ws_max = oracle_loss.spatial_clique_params(labels, S0, cfg)
     ws_max = ws_max * 0.3   # make the skeleton hinge active for some limbs so its gradient is exercised
     ref, ref_total, ref_vis = oracle_loss.dgp_loss_from_heads(pred, loc, batch, cfg, S0, ws, ws_max, 200, 20)
