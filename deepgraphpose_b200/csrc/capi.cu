@@ -946,6 +946,21 @@ int dgp_loss_backward(dgp_handle* h, const dgp_loss_cfg* cfg, const dgp_loss_bat
   return dgp_run_loss_impl(h, cfg, b, losses_dev, nullptr, grad_pred_dev, grad_locref_dev, visible_only, stream);
 }
 
+int dgp_locref_targets(dgp_handle* h, const double* joint_loc_dev, const int32_t* frame_idx_dev, int n_vis, int nt, int H,
+                       int W, double pos_dist_thresh, double locref_stdev, float* locref_map_dev, float* locref_mask_dev,
+                       void* stream) {
+  if (!h) return DGP_ERR_INVALID;
+  if (n_vis < 0 || nt < 1 || n_vis > nt || H < 1 || W < 1 || !locref_map_dev || !locref_mask_dev || !(pos_dist_thresh > 0) ||
+      (n_vis > 0 && (!joint_loc_dev || !frame_idx_dev)))
+    return fail(h, DGP_ERR_INVALID, "dgp_locref_targets: bad argument");
+  CU_OK(h, cudaSetDevice(h->device));
+  CU_OK(h, launch_locref_targets(joint_loc_dev, frame_idx_dev, n_vis, nt, h->cfg.num_joints, H, W, (double)h->cfg.stride,
+                                 pos_dist_thresh, locref_stdev > 0 ? locref_stdev : (double)h->cfg.locref_stdev, locref_map_dev, locref_mask_dev,
+                                 (cudaStream_t)stream));
+  h->launches += n_vis > 0 ? 1 : 0;
+  return DGP_OK;
+}
+
 int dgp_sigmoid(dgp_handle* h, const float* logits_dev, float* prob_dev, size_t n, void* stream) {
   if (!h) return DGP_ERR_INVALID;
   if (!logits_dev || !prob_dev || (n % 4)) return fail(h, DGP_ERR_INVALID, "dgp_sigmoid: bad argument");

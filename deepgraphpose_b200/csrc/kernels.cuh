@@ -91,4 +91,11 @@ int head_bias_blocks();
 // g (npix, C) fp32 -> dbias[C]; partial: [head_bias_blocks()][C] floats of workspace
 cudaError_t launch_head_bias_grad(const float* g, size_t npix, int C, float* partial, float* dbias, cudaStream_t s);
 
+// ---- host-feeder replacements (feeder_kernels.cu)
+// coord2map + scatter over the batch: joint_loc (n_vis,nj,2) double scoremap (row,col), NaN = missing; frame_idx (n_vis)
+// position of each visible frame in the batch; lmap / lmask (nt,H,W,2nj) float32 are fully overwritten.
+cudaError_t launch_locref_targets(const double* joint_loc, const int* frame_idx, int n_vis, int nt, int nj, int H, int W,
+                                  double stride, double pos_dist_thresh, double locref_stdev, float* lmap, float* lmask,
+                                  cudaStream_t s);
+
 }  // namespace dgp

@@ -282,6 +282,23 @@ class Engine:
                                               C.byref(nd)))
         return out
 
+    def locref_targets(self, joint_loc, visible_frame_within_batch, nt, H, W, pos_dist_thresh=17.0, locref_stdev=7.2801):
+        """Device-side coord2map + batch scatter (dataset.py:246-271, fitdgp.py:781-795): joint_loc (n_vis,nj,2) float64
+        scoremap (row,col) labels (NaN = missing).  Returns float32 CUDA tensors (locref_map, locref_mask) (nt,H,W,2nj)."""
+        jl = np.ascontiguousarray(np.asarray(joint_loc, dtype=np.float64).reshape(-1, self.nj, 2))
+        idx = np.ascontiguousarray(np.asarray(visible_frame_within_batch, dtype=np.int32).reshape(-1))
+        if jl.shape[0] != idx.shape[0]:
+            raise ValueError("one batch position per labelled frame is required")
+        dev = self.device
+        jl_d = torch.from_numpy(jl).to(dev) if jl.size else None
+        idx_d = torch.from_numpy(idx).to(dev) if idx.size else None
+        lmap = torch.empty((nt, H, W, 2 * self.nj), dtype=torch.float32, device=dev)
+        lmask = torch.empty_like(lmap)
+        self._check(self.lib.dgp_locref_targets(self.h, _ptr(jl_d), _ptr(idx_d), int(idx.shape[0]), int(nt), int(H), int(W),
+                                                float(pos_dist_thresh), float(locref_stdev), _ptr(lmap), _ptr(lmask),
+                                                _stream(dev)))
+        return lmap, lmask
+
     # ------------------------------------------------------------------ test hooks
     def keep_activations(self, enable=True):
         self._check(self.lib.dgp_debug_keep_activations(self.h, int(enable)))

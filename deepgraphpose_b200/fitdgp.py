@@ -65,8 +65,10 @@ def spatial_clique_params(joint_locs, S0, stride, ws, ws_max):
 
 
 def _loss_args(dev, feed, cfg, edges, ws, ws_max, n_frames_total, n_visible_frames_total, nt, H, W, nj, pred=None,
-               locref=None, with_locref=None):
-    """(dgp_loss_cfg, dgp_loss_batch, keep-alive list) from the reference's feed_dict values (fitdgp.py:797-815)."""
+               locref=None, with_locref=None, engine=None):
+    """(dgp_loss_cfg, dgp_loss_batch, keep-alive list) from the reference's feed_dict values (fitdgp.py:797-815).
+    When the feed carries ``visible_frame_within_batch`` instead of ``locref_map`` / ``locref_mask``, the two maps are
+    generated on the device (Engine.locref_targets, the coord2map feeder) instead of being copied from the host."""
     f32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32), device=dev)
     i32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32), device=dev)
     targets = f32(np.asarray(feed["targets"]).reshape(-1, nj, 2))
@@ -80,7 +82,11 @@ def _loss_args(dev, feed, cfg, edges, ws, ws_max, n_frames_total, n_visible_fram
     if with_locref is None:
         with_locref = locref is not None
     if with_locref:
-        lm, lk = f32(feed["locref_map"]), f32(feed["locref_mask"])
+        if "locref_map" in feed:
+            lm, lk = f32(feed["locref_map"]), f32(feed["locref_mask"])
+        else:
+            lm, lk = engine.locref_targets(feed["targets"], feed["visible_frame_within_batch"], nt, H, W,
+                                           float(_get(cfg, "pos_dist_thresh", 17.0)), float(_get(cfg, "locref_stdev", 7.2801)))
         keep += [lm, lk]
         b.locref_map_dev, b.locref_mask_dev = lm.data_ptr(), lk.data_ptr()
         if locref is not None:
@@ -140,7 +146,7 @@ def train_forward_backward(engine, frames, feed, cfg, edges, ws, ws_max, n_frame
     _, (H, W) = output_dims(Hin, Win)
     engine.train_enable()
     c, b, keep = _loss_args(dev, feed, cfg, edges, ws, ws_max, n_frames_total, n_visible_frames_total, nt, H, W, engine.nj,
-                            with_locref=engine.location_refinement)
+                            with_locref=engine.location_refinement, engine=engine)
     out = torch.empty(6, dtype=torch.float32, device=dev)
     engine._check(engine.lib.dgp_train_forward_backward(engine.h, _ptr(frames.contiguous()), nt, Hin, Win, C.byref(c), C.byref(b),
                                                         int(visible_only), _ptr(out), _stream(dev)))

@@ -92,6 +92,16 @@ int dgp_softargmax(dgp_handle* h, const float* logits_dev, const float* locref_d
 int dgp_softmax_map(dgp_handle* h, const float* logits_dev, int B, int H, int W, int nj, float gamma, float gauss_len,
                     float* map_dev, void* stream);
 
+/* Replaces the host feeder coord2map (src/deepgraphpose/dataset.py:246-271 -> PoseDataset.compute_target_part_scoremap,
+ * PTF/dataset/pose_defaultdataset.py:220-266) and the scatter of its output over the batch (fitdgp.py:781-795): the
+ * `locref_map` / `locref_mask` feeds are generated on the device.  joint_loc_dev: float64 (n_vis,nj,2) labels in scoremap
+ * (row, col) units, NaN = missing; frame_idx_dev: int32 (n_vis) = visible_frame_within_batch; outputs float32
+ * (nt,H,W,2nj), fully overwritten; locref_stdev as a double (0 = the handle's float config value).  Bit-identical to the
+ * reference's float64 arrays cast to the float32 placeholders. */
+int dgp_locref_targets(dgp_handle* h, const double* joint_loc_dev, const int32_t* frame_idx_dev, int n_vis, int nt, int H,
+                       int W, double pos_dist_thresh, double locref_stdev, float* locref_map_dev, float* locref_mask_dev,
+                       void* stream);
+
 /* Replaces PoseNet.test's tf.sigmoid(part_pred) (pose_net.py:84-90). n = number of floats (multiple of 4). */
 int dgp_sigmoid(dgp_handle* h, const float* logits_dev, float* prob_dev, size_t n, void* stream);
 

@@ -1,0 +1,57 @@
+"""tests/golden/feeders.npz: outputs of the REFERENCE'S OWN ``coord2map`` (src/deepgraphpose/dataset.py:246-271) and
+``PoseDataset.compute_target_part_scoremap`` (DeepLabCut .../dataset/pose_defaultdataset.py:220-266).  The two modules cannot
+be imported here (moviepy / skimage / tensorflow are absent), so the two function definitions are cut out of the reference
+files with ``ast`` and executed unmodified.  Run in the build container only:  python tests/golden/make_golden_feeders.py"""
+import ast
+import os
+import types
+
+import numpy as np
+
+REF = "/root/reference/src"
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def cut(path, name):
+    src = open(path).read()
+    for node in ast.walk(ast.parse(src)):
+        if isinstance(node, ast.FunctionDef) and node.name == name:
+            return ast.get_source_segment(src, node)
+    raise KeyError(name)
+
+
+if not hasattr(np, "asscalar"):
+    np.asscalar = lambda a: a.item()  # removed in numpy >= 1.23; the reference pins an older numpy
+ns = {"np": np, "arr": np.array, "cat": np.concatenate}
+exec(cut(REF + "/DeepLabCut/deeplabcut/pose_estimation_tensorflow/dataset/pose_defaultdataset.py", "compute_target_part_scoremap"), ns)
+exec(cut(REF + "/deepgraphpose/dataset.py", "coord2map"), ns)
+
+
+class PData:
+    """The attributes PoseDataset.__init__ sets (pose_defaultdataset.py:25-31) for the demo's pose_cfg.yaml."""
+
+    def __init__(self, nj):
+        self.cfg = types.SimpleNamespace(pos_dist_thresh=17, num_joints=nj)
+        self.locref_scale = 1.0 / 7.2801
+        self.stride = 8.0
+        self.half_stride = 4.0
+
+    def compute_scmap_weights(self, *a):
+        return None
+
+
+PData.compute_target_part_scoremap = ns["compute_target_part_scoremap"]
+
+rng = np.random.default_rng(5)
+out = {}
+for tag, (n_vis, nj, nx, ny) in {"a": (3, 4, 12, 16), "b": (1, 5, 30, 38), "c": (2, 3, 94, 104)}.items():
+    jl = np.stack([rng.uniform(-0.4, nx - 0.6, (n_vis, nj)), rng.uniform(-0.4, ny - 0.6, (n_vis, nj))], axis=2)
+    jl[0, 1] = np.nan                       # missing label
+    jl[-1, 0] = [0.0, 0.0]                  # corner
+    jl[-1, nj - 1] = [nx - 1.0, ny - 1.0]   # opposite corner
+    jl[0, 2] = [3.0, 5.0]                   # exactly on a cell centre: the 17 px circle passes through cell centres (8, 15)
+    t, m = ns["coord2map"](PData(nj), jl, nx, ny, nj)
+    out.update({tag + "_joint_loc": jl, tag + "_targets": t.astype(np.float32), tag + "_mask": m.astype(np.uint8),
+                tag + "_dims": np.array([nx, ny, nj])})
+np.savez_compressed(os.path.join(OUT, "feeders.npz"), **out)
+print({k: v.shape for k, v in out.items()})

@@ -1,0 +1,59 @@
+"""coord2map / compute_target_part_scoremap (host feeders of the training step): oracle vs the golden vectors produced by
+the reference's own functions (CPU), and the CUDA feeder kernel vs both (GPU, bit-exact)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import feeders
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "feeders.npz")
+
+
+def _cases():
+    with np.load(G) as z:
+        d = {k: z[k] for k in z.files}
+    return [(t, d[t + "_joint_loc"], d[t + "_targets"], d[t + "_mask"], [int(v) for v in d[t + "_dims"]]) for t in "abc"]
+
+
+@pytest.mark.parametrize("case", _cases(), ids=lambda c: c[0])
+def test_oracle_coord2map_matches_reference_golden(case):
+    _, jl, targets, mask, (nx, ny, nj) = case
+    t, m = feeders.coord2map(jl, nx, ny, nj)
+    assert np.array_equal(m.astype(np.uint8), mask)
+    assert np.array_equal(t.astype(np.float32), targets)
+
+
+def test_oracle_batch_scatter_and_empty():
+    t, m = feeders.coord2map(np.zeros((0, 3, 2)), 6, 7, 3)
+    assert t.shape[0] == 0 and m.shape[0] == 0
+    jl = np.array([[[2.0, 3.0], [np.nan, np.nan]]])
+    lt, lm = feeders.batch_locref_maps(jl, [2], 4, 6, 7, 2)
+    assert lt.shape == (4, 6, 7, 4) and lm[[0, 1, 3]].sum() == 0 and lm[2, :, :, :2].sum() > 0 and lm[2, :, :, 2:].sum() == 0
+    # centre cell: dx = dy = 0 -> target 0 with mask 1; its right neighbour: dx = -8 px
+    assert lm[2, 2, 3, 0] == 1 and lt[2, 2, 3, 0] == 0 and np.isclose(lt[2, 2, 4, 0], -8 / 7.2801)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", _cases(), ids=lambda c: c[0])
+def test_gpu_locref_targets_bit_exact(case):
+    from deepgraphpose_b200 import dataset
+    from deepgraphpose_b200.engine import Engine
+    _, jl, targets, mask, (nx, ny, nj) = case
+    eng = Engine(nj)
+    n_vis = jl.shape[0]
+    nt = n_vis + 2
+    pos = np.arange(n_vis) * 2 % nt if n_vis > 1 else np.array([1])
+    lmap, lmask = eng.locref_targets(jl, pos, nt, nx, ny)
+    lmap, lmask = lmap.cpu().numpy(), lmask.cpu().numpy()
+    ref_t, ref_m = feeders.batch_locref_maps(jl, pos, nt, nx, ny, nj)
+    assert np.array_equal(lmask, ref_m.astype(np.float32))
+    assert np.array_equal(lmap, ref_t.astype(np.float32))
+    for v, t in enumerate(pos):   # and against the reference's own output
+        assert np.array_equal(lmap[t], targets[v]) and np.array_equal(lmask[t].astype(np.uint8), mask[v])
+
+    class P:
+        cfg = dict(pos_dist_thresh=17, locref_stdev=7.2801)
+    t2, m2 = dataset.coord2map(P(), jl, nx, ny, nj, engine=eng)
+    assert t2.dtype == np.float64 and np.array_equal(t2.astype(np.float32), targets) and np.array_equal(m2.astype(np.uint8), mask)
+    eng.close()

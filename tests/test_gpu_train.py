@@ -262,3 +262,27 @@ def test_fit_dgp_shim_train_op():
     w = sess.variables(total_loss.graph, ["pose/part_pred/block4/biases"])
     assert w["pose/part_pred/block4/biases"].shape == (NJ,) and np.abs(w["pose/part_pred/block4/biases"]).max() > 0
     total_loss.graph.engine.close()
+
+
+def test_device_side_locref_feeder_gives_the_same_step():
+    """Feeding labels + visible_frame_within_batch (maps built by the coord2map CUDA feeder) == feeding the host maps the
+    oracle's coord2map builds: identical losses and gradient buffers."""
+    from deepgraphpose_b200 import fitdgp
+    from deepgraphpose_b200.engine import Engine
+    from oracle import feeders
+    W, frames, batch, edges, S0, cfg, ws, ws_max = _setup(seed=13)
+    H, Wd = 2 * -(-HIN // 16), 2 * -(-WIN // 16)
+    vis_pos = [0, 2]
+    lt, lm = feeders.batch_locref_maps(batch["targets"], vis_pos, NT, H, Wd, NJ)
+    host_feed = dict(batch, locref_map=lt, locref_mask=lm)
+    dev_feed = {k: v for k, v in batch.items() if k not in ("locref_map", "locref_mask")}
+    dev_feed["visible_frame_within_batch"] = vis_pos
+    res = []
+    for feed in (host_feed, dev_feed):
+        eng = Engine(NJ)
+        eng.load_weights(W)
+        loss = fitdgp.train_forward_backward(eng, torch.from_numpy(frames).cuda(), feed, cfg, edges, ws, ws_max, 200, 20)
+        res.append((loss, eng.grad_buffer().clone()))
+        eng.close()
+    assert res[0][0] == res[1][0] and torch.equal(res[0][1], res[1][1])
+    assert float(res[0][0]["visible_loss_locref"]) > 0
