@@ -99,39 +99,47 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const __grid_
       int kb1 = kb0 + p.kb_per_split;
       if (kb1 > p.num_pix_blocks) kb1 = p.num_pix_blocks;
       const uint32_t tx_bytes = (uint32_t)((2 + nchunks) * kBoxBytes);
+      // Lane-parallel issue: lanes 0..3 own the (up to 4) x boxes, lanes 4 and 5 the two dy boxes.  Everything that does not
+      // depend on the pixel block (channel block, tap offsets, smem slot) is computed once per item; the pixel coordinates
+      // advance incrementally (no divisions inside the k loop -- they sat on the single-warp critical path).
+      const bool x_lane = lane < nchunks, dy_lane = lane == 4 || lane == 5;
+      int my_c0 = 0, my_off_w = 0, my_off_h = 0, my_slot = 0;
+      if (x_lane) {
+        const int gc = n_blk * 4 + lane;
+        const int tap = gc / p.cblocks;
+        my_c0 = (gc - tap * p.cblocks) * 64;
+        const int tr = tap / p.S;
+        my_off_w = (tap - tr * p.S) * p.dil;
+        my_off_h = tr * p.dil;
+        my_slot = kWgABytes + lane * kBoxBytes;
+      } else if (dy_lane) {
+        my_c0 = m_blk * 128 + (lane - 4) * 64;
+        my_slot = (lane - 4) * kBoxBytes;
+      }
+      int pix0 = kb0 * 64;
+      int img = pix0 / PQ;
+      int pp = (pix0 - img * PQ) / Q;
+      int qq = pix0 - img * PQ - pp * Q;
       for (int kb = kb0; kb < kb1; ++kb) {
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-        if (ptx::elect_one()) {
-          uint8_t* sa = smem + stage * kWgStageBytes;
-          uint8_t* sb = sa + kWgABytes;
-          const int pix0 = kb * 64;
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-          ptx::tma_load_2d(sa, &p.tmap_dy, &full_bar[stage], m_blk * 128, pix0);
-          ptx::tma_load_2d(sa + kBoxBytes, &p.tmap_dy, &full_bar[stage], m_blk * 128 + 64, pix0);
-          int img = 0, cw = 0, ch = 0;
-          if (p.x_mode == 1) {
-            img = pix0 / PQ;
-            const int rem = pix0 - img * PQ;
-            const int pp = rem / Q;
-            const int qq = rem - pp * Q;
-            cw = qq * p.conv_stride + p.lower_w;
-            ch = pp * p.conv_stride + p.lower_h;
-          }
-          for (int c = 0; c < nchunks; ++c) {
-            const int gc = n_blk * 4 + c;
-            const int tap = gc / p.cblocks;
-            const int cb = gc - tap * p.cblocks;
-            if (p.x_mode == 0) {
-              ptx::tma_load_2d(sb + c * kBoxBytes, &p.tmap_x, &full_bar[stage], cb * 64, pix0);
-            } else {
-              const int tr = tap / p.S;
-              const int ts = tap - tr * p.S;
-              ptx::tma_load_im2col_4d(sb + c * kBoxBytes, &p.tmap_x, &full_bar[stage], cb * 64, cw, ch, img,
-                                      (uint16_t)(ts * p.dil), (uint16_t)(tr * p.dil));
-            }
+        uint8_t* st = smem + stage * kWgStageBytes;
+        if (lane == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+        __syncwarp();
+        if (dy_lane || (x_lane && p.x_mode == 0)) {
+          ptx::tma_load_2d(st + my_slot, dy_lane ? &p.tmap_dy : &p.tmap_x, &full_bar[stage], my_c0, pix0);
+        } else if (x_lane) {
+          ptx::tma_load_im2col_4d(st + my_slot, &p.tmap_x, &full_bar[stage], my_c0, qq * p.conv_stride + p.lower_w,
+                                  pp * p.conv_stride + p.lower_h, img, (uint16_t)my_off_w, (uint16_t)my_off_h);
+        }
+        pix0 += 64;
+        qq += 64;
+        while (qq >= Q) {
+          qq -= Q;
+          if (++pp == p.P) {
+            pp = 0;
+            ++img;
           }
         }
-        __syncwarp();
         if (++stage == kWgStages) {
           stage = 0;
           phase ^= 1;
