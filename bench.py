@@ -180,6 +180,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="frames per step per GPU (0 = engine.suggest_batch)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the auxiliary training-step measurement (configs[3])")
     ap.add_argument("--cpu-frames", type=int, default=12)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
@@ -281,6 +282,16 @@ def main():
         dt = float(t.item())
     e2e_value = world * e2e_steps * B / dt
 
+    # ---- configs[3] alongside: one data-parallel DGP training step per rank (fwd + bwd + all-reduce + clip/Momentum)
+    train_line = None
+    if not args.no_train:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import bench_train
+            train_line = bench_train.measure(rank, local_rank, world, 5, 3, 10, H, W, profile=False)
+        except Exception as ex:  # the headline line must survive a failure of the auxiliary measurement
+            train_line = {"error": repr(ex)}
     if rank == 0:
         peaks, peak_src = load_peaks()
         gemm_ms, gemm_n = prof["conv_gemm"]
@@ -324,6 +335,9 @@ def main():
                              "ms_by_kernel_family": {k: v[0] for k, v in prof.items()}},
             "finite": bool(np.isfinite(res["x"]).all()),
         }
+        if train_line is not None:
+            keep = ("metric", "value", "unit", "ms_per_step", "config", "gpu_launches", "loss_after", "finite", "error")
+            line["train_step"] = {k: train_line[k] for k in keep if k in train_line}
         if world == 1 and not args.no_cpu_baseline:
             fps, cores, cdt = cpu_reference_fps(args.cpu_frames, warmup=1)
             line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",

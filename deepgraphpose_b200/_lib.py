@@ -62,6 +62,7 @@ SIGNATURES = {
     "dgp_softmax_map": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _f, _vp, _vp]),
     "dgp_loss_forward": (_i, [_vp, C.POINTER(DgpLossCfg), C.POINTER(DgpLossBatch), _vp, _vp, _vp]),
     "dgp_loss_backward": (_i, [_vp, C.POINTER(DgpLossCfg), C.POINTER(DgpLossBatch), _vp, _vp, _vp, _i, _vp]),
+    "dgp_soft_pose": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _i, _vp, _vp, _vp]),
     "dgp_locref_targets": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, C.c_double, C.c_double, _vp, _vp, _vp]),
     "dgp_sigmoid": (_i, [_vp, _vp, _vp, _sz, _vp]),
     "dgp_potentials": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp]),

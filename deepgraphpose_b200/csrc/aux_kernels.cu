@@ -131,6 +131,46 @@ __global__ void deconv_col2im_kernel(const float* __restrict__ contrib, int N, i
   }
 }
 
+// evaluate_dgp's 'dgp' locref read-out (src/deepgraphpose/models/eval.py:751-785): with st the blurred spatial softmax,
+//   soft = sum st * (row, col) * stride + stride/2;  offset = sum st * (locref[..., 2j], locref[..., 2j+1]) * locref_stdev
+//   pose = (soft + offset)[::-1] -> (x, y, 1).  The reference adds locref's first component (DLC's dx) to the ROW
+//   coordinate (no [::-1] as in argmax_pose_predict); swap_offsets = 1 applies the offsets the DLC way instead.
+// One CTA per (frame, joint); fixed-order block reduction.
+__global__ void __launch_bounds__(256) soft_pose_kernel(const float* __restrict__ st, const float* __restrict__ locref, int H,
+                                                        int W, int nj, float stride, float locref_stdev, int swap_offsets,
+                                                        float* __restrict__ pose) {
+  const int b = blockIdx.x / nj, j = blockIdx.x - b * nj;
+  const float* s0 = st + (size_t)b * H * W * nj + j;
+  const float* l0 = locref + (size_t)b * H * W * 2 * nj + 2 * j;
+  float ar = 0.0f, ac = 0.0f, o0 = 0.0f, o1 = 0.0f;
+  for (int p = threadIdx.x; p < H * W; p += blockDim.x) {
+    const int r = p / W, c = p - r * W;
+    const float v = s0[(size_t)p * nj];
+    const float2 l = *reinterpret_cast<const float2*>(l0 + (size_t)p * 2 * nj);
+    ar += v * (float)r;
+    ac += v * (float)c;
+    o0 += v * (l.x * locref_stdev);
+    o1 += v * (l.y * locref_stdev);
+  }
+  __shared__ float sm[4][256];
+  sm[0][threadIdx.x] = ar; sm[1][threadIdx.x] = ac; sm[2][threadIdx.x] = o0; sm[3][threadIdx.x] = o1;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) sm[k][threadIdx.x] += sm[k][threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float row = sm[0][0] * stride + 0.5f * stride, col = sm[1][0] * stride + 0.5f * stride;
+    const float orow = swap_offsets ? sm[3][0] : sm[2][0], ocol = swap_offsets ? sm[2][0] : sm[3][0];
+    float* o = pose + (size_t)blockIdx.x * 3;
+    o[0] = col + ocol;
+    o[1] = row + orow;
+    o[2] = 1.0f;
+  }
+}
+
 int grid_for(size_t total, int threads) {
   size_t g = (total + threads - 1) / threads;
   if (g > 148 * 16) g = 148 * 16;
@@ -161,6 +201,12 @@ cudaError_t launch_deconv_col2im(const float* contrib, int N, int h, int w, int 
                                  const float* bias, float* logits, float* locref, cudaStream_t stream) {
   const size_t total = (size_t)N * 4 * h * w * ctot;
   deconv_col2im_kernel<<<grid_for(total, 256), 256, 0, stream>>>(contrib, N, h, w, ldn, ctot, nj, bias, logits, locref);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_soft_pose(const float* st, const float* locref, int B, int H, int W, int nj, float stride,
+                             float locref_stdev, int swap_offsets, float* pose, cudaStream_t stream) {
+  soft_pose_kernel<<<B * nj, 256, 0, stream>>>(st, locref, H, W, nj, stride, locref_stdev, swap_offsets, pose);
   return cudaGetLastError();
 }
 

@@ -946,6 +946,21 @@ int dgp_loss_backward(dgp_handle* h, const dgp_loss_cfg* cfg, const dgp_loss_bat
   return dgp_run_loss_impl(h, cfg, b, losses_dev, nullptr, grad_pred_dev, grad_locref_dev, visible_only, stream);
 }
 
+int dgp_soft_pose(dgp_handle* h, const float* logits_dev, const float* locref_dev, int B, int H, int W, int nj, float gamma,
+                  float gauss_len, int swap_offsets, float* map_ws_dev, float* pose_dev, void* stream) {
+  if (!h) return DGP_ERR_INVALID;
+  if (B == 0) return DGP_OK;
+  if (!logits_dev || !locref_dev || !map_ws_dev || !pose_dev || B < 0 || nj < 1)
+    return fail(h, DGP_ERR_INVALID, "dgp_soft_pose: bad argument");
+  if (((uintptr_t)locref_dev & 7) != 0) return fail(h, DGP_ERR_INVALID, "dgp_soft_pose: locref must be 8-byte aligned");
+  int rc = dgp_softmax_map(h, logits_dev, B, H, W, nj, gamma, gauss_len, map_ws_dev, stream);
+  if (rc) return rc;
+  CU_OK(h, launch_soft_pose(map_ws_dev, locref_dev, B, H, W, nj, h->cfg.stride, h->cfg.locref_stdev, swap_offsets, pose_dev,
+                            (cudaStream_t)stream));
+  h->launches++;
+  return DGP_OK;
+}
+
 int dgp_locref_targets(dgp_handle* h, const double* joint_loc_dev, const int32_t* frame_idx_dev, int n_vis, int nt, int H,
                        int W, double pos_dist_thresh, double locref_stdev, float* locref_map_dev, float* locref_mask_dev,
                        void* stream) {

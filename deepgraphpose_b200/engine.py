@@ -186,6 +186,18 @@ class Engine:
                                              _stream(logits.device)))
         return out
 
+    def soft_pose(self, logits, locref, gamma=1.0, gauss_len=1.0, swap_offsets=False):
+        """evaluate_dgp's 'dgp' locref branch (eval.py:751-785) on the device: (B,nj,3) = (x, y, 1)."""
+        logits, locref = logits.contiguous(), locref.contiguous()
+        B, H, W, nj = logits.shape
+        if locref.shape != (B, H, W, 2 * nj) or locref.dtype != torch.float32 or logits.dtype != torch.float32:
+            raise ValueError("logits (B,H,W,nj) and locref (B,H,W,2*nj) must be float32")
+        ws = torch.empty_like(logits)
+        pose = torch.empty((B, nj, 3), dtype=torch.float32, device=logits.device)
+        self._check(self.lib.dgp_soft_pose(self.h, _ptr(logits), _ptr(locref), B, H, W, nj, float(gamma), float(gauss_len),
+                                           int(swap_offsets), _ptr(ws), _ptr(pose), _stream(logits.device)))
+        return pose
+
     def sigmoid(self, logits):
         logits = logits.contiguous()
         out = torch.empty_like(logits)

@@ -136,3 +136,25 @@ def estimate_pose(proj_cfg_file, dgp_model_file, video_file, output_dir, shuffle
         table = np.stack([labels["x"], labels["y"], labels["likelihoods"]], axis=2).reshape(labels["x"].shape[0], -1)
         np.savetxt(save_file + ".csv", table, delimiter=",", header=header, comments="")
     return labels
+
+
+def evaluate_dgp_frames(engine, frames, loc_ref=True, loc_ref_calc="dlc", batch=16, gamma=1.0, gauss_len=1.0):
+    """The per-image pose read-out of ``evaluate_dgp`` (eval.py:744-790) for a uint8 (T,H,W,3) array: returns (T, nj*3)
+    rows of (x, y, likelihood) like ``PredicteData``.  Branches as in the reference: loc_ref with ``loc_ref_calc='dlc'`` ->
+    argmax_pose_predict (global peak + locref offset, likelihood = sigmoid at the peak); ``'dgp'`` -> soft-argmax + softmax
+    weighted locref offset (likelihood column 1); no loc_ref -> soft-argmax only."""
+    frames = np.asarray(frames)
+    T = frames.shape[0]
+    out = np.empty((T, engine.nj * 3), np.float64)
+    for t0 in range(0, T, batch):
+        fr = torch.from_numpy(np.ascontiguousarray(frames[t0:t0 + batch])).to(engine.device)
+        logits, locref = engine.forward(fr, want_locref=bool(loc_ref))
+        if loc_ref and loc_ref_calc.lower() == "dlc":
+            pose = engine.softargmax(logits, locref, gamma, gauss_len, want=("dlc_pose",))["dlc_pose"]
+        elif loc_ref:
+            pose = engine.soft_pose(logits, locref, gamma, gauss_len)
+        else:
+            mu = engine.softargmax(logits, None, gamma, gauss_len, want=("mu",))["mu"]
+            pose = torch.cat([mu.flip(2) * engine.stride + 0.5 * engine.stride, torch.ones_like(mu[:, :, :1])], dim=2)
+        out[t0:t0 + fr.shape[0]] = pose.reshape(fr.shape[0], -1).double().cpu().numpy()
+    return out

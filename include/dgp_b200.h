@@ -92,6 +92,13 @@ int dgp_softargmax(dgp_handle* h, const float* logits_dev, const float* locref_d
 int dgp_softmax_map(dgp_handle* h, const float* logits_dev, int B, int H, int W, int nj, float gamma, float gauss_len,
                     float* map_dev, void* stream);
 
+/* Replaces evaluate_dgp's 'dgp' locref read-out (src/deepgraphpose/models/eval.py:751-785): blurred spatial softmax of the
+ * logits, then pose = (sum st * (row, col) * stride + stride/2 + sum st * locref * locref_stdev)[::-1] -> float32 (B,nj,3) =
+ * (x, y, 1).  swap_offsets = 0 reproduces the reference (locref's first component is added to the row coordinate),
+ * 1 applies the offsets as DLC's argmax_pose_predict does.  map_ws_dev: float32 (B,H,W,nj) workspace (receives the map). */
+int dgp_soft_pose(dgp_handle* h, const float* logits_dev, const float* locref_dev, int B, int H, int W, int nj, float gamma,
+                  float gauss_len, int swap_offsets, float* map_ws_dev, float* pose_dev, void* stream);
+
 /* Replaces the host feeder coord2map (src/deepgraphpose/dataset.py:246-271 -> PoseDataset.compute_target_part_scoremap,
  * PTF/dataset/pose_defaultdataset.py:220-266) and the scatter of its output over the batch (fitdgp.py:781-795): the
  * `locref_map` / `locref_mask` feeds are generated on the device.  joint_loc_dev: float64 (n_vis,nj,2) labels in scoremap

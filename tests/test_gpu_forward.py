@@ -213,3 +213,31 @@ def test_forward_errors(setup):
     with pytest.raises(DgpError):
         e2.load_weights(bad)
     e2.close()
+
+
+def test_evaluate_dgp_frames_branches():
+    """The three pose read-outs of evaluate_dgp (eval.py:744-790) through the shim: shapes, likelihood column, consistency of
+    the no-locref branch with the soft-argmax and of the 'dlc' branch with argmax_pose_predict on the same maps."""
+    from deepgraphpose_b200 import synthetic
+    from deepgraphpose_b200.engine import Engine
+    from deepgraphpose_b200.eval import evaluate_dgp_frames
+    from oracle import dgp_ops, pose_net
+    nj = 4
+    eng = Engine(nj)
+    eng.load_weights(synthetic.make_weights(nj, seed=2))
+    frames, _ = synthetic.make_video(3, 96, 128, nj, seed=4)
+    dlc = evaluate_dgp_frames(eng, frames, True, "dlc", batch=2)
+    dgp = evaluate_dgp_frames(eng, frames, True, "dgp", batch=2)
+    nol = evaluate_dgp_frames(eng, frames, False, "dlc", batch=2)
+    assert dlc.shape == dgp.shape == nol.shape == (3, nj * 3)
+    assert np.isfinite(dlc).all() and np.isfinite(dgp).all() and (dgp.reshape(3, nj, 3)[:, :, 2] == 1).all()
+    logits, locref = eng.forward(torch.from_numpy(frames).cuda())
+    lg, lr = logits.cpu().numpy(), locref.cpu().numpy()
+    for t in range(3):
+        mu, st = dgp_ops.argmax_2d_from_cm(torch.from_numpy(lg[t:t + 1]), nj, 1.0, 1.0)
+        assert np.abs(nol[t].reshape(nj, 3) - dgp_ops.evaluate_dgp_pose_noloc(mu.numpy())).max() < 2e-3
+        assert np.abs(dgp[t].reshape(nj, 3) - dgp_ops.evaluate_dgp_pose_dgp_branch(st.numpy(), lr[t:t + 1])).max() < 2e-3
+        sc, off = pose_net.extract_cnn_output(1.0 / (1.0 + np.exp(-lg[t:t + 1])), lr[t:t + 1])
+        ref, _ = pose_net.argmax_pose_predict(sc, off)
+        assert np.abs(dlc[t].reshape(nj, 3) - ref).max() < 2e-3
+    eng.close()

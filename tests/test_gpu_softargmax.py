@@ -216,3 +216,26 @@ def test_potentials_and_halo(eng):
         b = eng.potentials(mu[400:].cuda(), edges)
         assert torch.equal(torch.cat([a["temporal"], b["temporal"]]), out["temporal"])
         assert torch.equal(torch.cat([a["skel"], b["skel"]], dim=1), out["skel"])
+
+
+@pytest.mark.parametrize("shape", [(2, 12, 16, 3), (1, 30, 38, 5), (3, 94, 104, 4)])
+def test_soft_pose_dgp_branch_matches_oracle(shape):
+    """evaluate_dgp 'dgp' locref read-out (eval.py:751-785) on the device vs the literal numpy restatement, including the
+    reference's quirk (locref's first component lands on the row coordinate) and the DLC-ordered variant."""
+    from deepgraphpose_b200.engine import Engine
+    from oracle import dgp_ops
+    B, H, W, nj = shape
+    rng = np.random.default_rng(B * 100 + nj)
+    logits = (rng.standard_normal(shape) * 3).astype(np.float32)
+    locref = rng.standard_normal((B, H, W, 2 * nj)).astype(np.float32)
+    eng = Engine(nj)
+    got = eng.soft_pose(torch.from_numpy(logits).cuda(), torch.from_numpy(locref).cuda()).cpu().numpy()
+    got_swapped = eng.soft_pose(torch.from_numpy(logits).cuda(), torch.from_numpy(locref).cuda(), swap_offsets=True).cpu().numpy()
+    for b in range(B):
+        _, st = dgp_ops.argmax_2d_from_cm(torch.from_numpy(logits[b:b + 1]), nj, 1.0, 1.0)
+        ref = dgp_ops.evaluate_dgp_pose_dgp_branch(st.numpy(), locref[b:b + 1])
+        assert np.abs(got[b] - ref).max() < 2e-3, np.abs(got[b] - ref).max()
+        lr2 = locref[b:b + 1].reshape(1, H, W, nj, 2)[..., ::-1].reshape(1, H, W, 2 * nj)
+        ref2 = dgp_ops.evaluate_dgp_pose_dgp_branch(st.numpy(), np.ascontiguousarray(lr2))
+        assert np.abs(got_swapped[b] - ref2).max() < 2e-3
+    eng.close()

@@ -20,17 +20,40 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import bench  # noqa: E402
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--nt", type=int, default=10)
-    ap.add_argument("--height", type=int, default=bench.H)
-    ap.add_argument("--width", type=int, default=bench.W)
-    args = ap.parse_args()
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
+def cpu_train_step_seconds(nt, H, W, NJ):
+    """The reference's training step on the host cores: torch-CPU autograd through the oracle network + dgp_loss (the CPU
+    restatement of sess.run([loss, train_op]); TF1.15 is not installable here).  Returns (seconds per step, cores)."""
+    import time
+    from deepgraphpose_b200 import synthetic
+    from deepgraphpose_b200.engine import output_dims
+    from oracle import dgp_loss as oracle_loss
+    from oracle import dgp_ops, pose_net
+    from test_gpu_loss import make_batch
+    torch.set_num_threads(os.cpu_count())
+    _, (hs, ws_) = output_dims(H, W)
+    rng = np.random.default_rng(7)
+    labels, batch = make_batch(rng, nt, hs, ws_, NJ, [0], ())
+    edges = synthetic.chain_skeleton(NJ)
+    S0 = dgp_ops.skeleton_matrix(edges, NJ)
+    cfg = oracle_loss.default_dgp_cfg(gm2=1, gm3=3, wt=0.0)
+    ws, ws_max = oracle_loss.spatial_clique_params(labels, S0, cfg)
+    Wn = synthetic.make_weights(NJ, seed=0)
+    Wt = {k: torch.from_numpy(v).requires_grad_(k.endswith(("/weights", "/gamma", "/beta", "/biases"))) for k, v in Wn.items()}
+    frames = synthetic.make_video(nt, H, W, NJ, seed=3)[0]
+    t0 = time.perf_counter()
+    heads = pose_net.get_net(torch.from_numpy(frames.astype(np.float32)), Wt, True)
+    _, total, _ = oracle_loss.dgp_loss_from_heads(heads["part_pred"], heads["locref"], batch, cfg, S0, ws, ws_max, 1000, 100)
+    total.backward()
+    params = [t for t in Wt.values() if t.requires_grad]
+    with torch.no_grad():
+        oracle_loss.momentum_step(params, [p.grad for p in params], [torch.zeros_like(p) for p in params])
+    return time.perf_counter() - t0, os.cpu_count()
+
+
+def measure(rank, local_rank, world, steps, warmup, nt, height, width, profile=True):
+    """One data-parallel training benchmark on the already-initialised process group; returns the JSON dict (rank 0) or None."""
+    import argparse as _a
+    args = _a.Namespace(steps=steps, warmup=warmup, nt=nt, height=height, width=width)
     import torch.distributed as dist
     from deepgraphpose_b200 import dp, fitdgp, synthetic
     from deepgraphpose_b200.engine import Engine, output_dims
@@ -39,9 +62,6 @@ def main():
     from test_gpu_loss import make_batch
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
     H, W, NJ, nt = args.height, args.width, bench.NJ, args.nt
     _, (hs, ws_) = output_dims(H, W)
     rng = np.random.default_rng(100 + rank)
@@ -87,24 +107,29 @@ def main():
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    eng.get_profile()
-    eng.set_profiling(True)
-    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    p0.record()
-    for _ in range(args.steps):
-        out = step()
-    p1.record()
-    torch.cuda.synchronize()
-    ms_prof = p0.elapsed_time(p1)
-    eng.set_profiling(False)
-    prof = eng.get_profile()
+    prof, ms_prof = None, 0.0
+    if profile:
+        eng.get_profile()
+        eng.set_profiling(True)
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for _ in range(args.steps):
+            out = step()
+        p1.record()
+        torch.cuda.synchronize()
+        ms_prof = p0.elapsed_time(p1)
+        eng.set_profiling(False)
+        prof = eng.get_profile()
     loss = float(out.cpu()[5])
+    line = None
     if rank == 0:
         peaks, src = bench.load_peaks()
         peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
         n = nt * args.steps
-        fam = {k: v[0] / args.steps for k, v in prof.items()}
+        fam = {k: v[0] / args.steps for k, v in prof.items()} if prof else None
         tf = lambda gf, ms_: (gf * n / (ms_ / 1e3) / 1e12) if ms_ > 0 else None
+        if prof is None:
+            prof = {k: (0.0, 0) for k in ("conv_gemm", "dgrad_gemm", "wgrad_gemm")}
         line = {
             "metric": "training frames/sec (DGP semi-supervised step: fwd + bwd + clip/Momentum)", "value": world * n / (ms / 1e3),
             "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -118,11 +143,38 @@ def main():
                        "step_total_3x_fwd": 3 * flops_fwd * n / (ms / 1e3) / 1e12, "peak": peak_tf, "peak_source": src,
                        "note": "algorithmic FLOPs: dgrad ~ wgrad ~ forward (conv1 has no dgrad; the 2 stride-2 dgrads run 4x zero-inserted)"},
         }
+    eng.close()
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--nt", type=int, default=10)
+    ap.add_argument("--height", type=int, default=bench.H)
+    ap.add_argument("--width", type=int, default=bench.W)
+    ap.add_argument("--cpu-frames", type=int, default=0, help="also time the CPU restatement of the step on this many frames")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    import torch.distributed as dist
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    line = measure(rank, local_rank, world, args.steps, args.warmup, args.nt, args.height, args.width)
+    if rank == 0:
+        if args.cpu_frames > 0 and world == 1:
+            sec, cores = cpu_train_step_seconds(args.cpu_frames, args.height, args.width, bench.NJ)
+            line["cpu_baseline"] = {"value": args.cpu_frames / sec, "unit": "frames/s", "cores": cores, "kind": "port",
+                                    "sample": "one step of %d frame(s): torch-CPU autograd through the oracle network + dgp_loss + "
+                                              "Momentum, %.1f s (TF1.15 not installable)" % (args.cpu_frames, sec)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    eng.close()
 
 
 if __name__ == "__main__":
