@@ -432,6 +432,15 @@ int build_plan(dgp_handle* h, int B, int H, int W, bool train, Plan** out) {
     *out = it->second.get();
     return DGP_OK;
   }
+  // Plans own gigabytes of activation buffers: keep at most a handful per kind (fit_dgp's last batch of an epoch and
+  // videos of different sizes create new shapes), dropping an arbitrary older one once the device is idle.
+  const size_t max_plans = train ? 3 : 6;
+  if (plans.size() >= max_plans) {
+    CU_OK(h, cudaDeviceSynchronize());
+    auto victim = plans.begin();
+    for (auto& b : victim->second->bufs) cudaFree(b.p);
+    plans.erase(victim);
+  }
   std::unique_ptr<Plan> pl(new Plan());
   pl->train = train;
   pl->B = B; pl->H = H; pl->W = W;

@@ -391,7 +391,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           ptx::mbar_wait(&rbar[buf], (uint32_t)((g >> nb_shift) & 1));
         } else {
           // the store that last used this buffer (chunk g - nb) must have finished reading it
-          if (leader && lane == 0) ptx::bulk_wait_group_read<1>();
+          if (leader && lane == 0) {
+            if (nb == 4) ptx::bulk_wait_group_read<3>();
+            else ptx::bulk_wait_group_read<1>();
+          }
           ptx::named_bar_sync(pair_bar, 64);
         }
         ptx::tmem_ld_wait();
