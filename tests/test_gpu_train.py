@@ -286,3 +286,58 @@ def test_device_side_locref_feeder_gives_the_same_step():
         eng.close()
     assert res[0][0] == res[1][0] and torch.equal(res[0][1], res[1][1])
     assert float(res[0][0]["visible_loss_locref"]) > 0
+
+
+@pytest.mark.parametrize("cfgcase", [dict(H=75, W=101, nj=5, locref=True, nt=2), dict(H=64, W=96, nj=4, locref=False, nt=3),
+                                     dict(H=97, W=70, nj=3, locref=True, nt=2, novis=True)],
+                         ids=["odd-sizes-nj5", "no-locref-head", "no-visible-frames"])
+def test_gradients_other_geometries(cfgcase):
+    """Odd input sizes (TF SAME pads of (1,1) in the max-pool, 2n-1 sized stride-2 units, scoremap of odd feature maps),
+    5 joints (head matrix padded to 48/144 rows), a network without the locref head, and a batch without visible frames:
+    gradients of every variable vs torch autograd through the fp32 oracle (bf16 thresholds as above)."""
+    from test_gpu_loss import make_batch
+    from deepgraphpose_b200 import fitdgp
+    from deepgraphpose_b200.engine import Engine
+    Hin, Win, nj, nt = cfgcase["H"], cfgcase["W"], cfgcase["nj"], cfgcase["nt"]
+    with_loc = cfgcase["locref"]
+    rng = np.random.default_rng(31)
+    W = synthetic.make_weights(nj, seed=4, location_refinement=with_loc)
+    frames, _ = synthetic.make_video(nt, Hin, Win, nj, seed=12)
+    c16 = lambda v: -(-(-(-(-(-(-(-v // 2)) // 2)) // 2)) // 2)
+    H, Wd = 2 * c16(Hin), 2 * c16(Win)
+    labels, batch = make_batch(rng, nt, H, Wd, nj, [] if cfgcase.get("novis") else [0], () if cfgcase.get("novis") else ((0, 1),))
+    edges = synthetic.chain_skeleton(nj)
+    S0 = dgp_ops.skeleton_matrix(edges, nj)
+    cfg = oracle_loss.default_dgp_cfg(gm2=1, gm3=3, wt=0.0)
+    lab_ws = labels if len(labels) else np.array([[[2.0 + j, 3.0 + 2 * j] for j in range(nj)]])
+    ws, ws_max = oracle_loss.spatial_clique_params(lab_ws, S0, cfg)
+    ws_max = ws_max * 0.3
+    Wt = {k: torch.from_numpy(v.copy()).requires_grad_(k.endswith(TRAINABLE)) for k, v in W.items()}
+    heads = pose_net.get_net(torch.from_numpy(frames.astype(np.float32)), Wt, with_loc)
+    if with_loc:
+        loc = heads["locref"]
+    else:   # the loss graph always has a locref term; without the head its inputs are constants (zero gradient)
+        loc = torch.zeros((nt, H, Wd, 2 * nj))
+    loss, total, _ = oracle_loss.dgp_loss_from_heads(heads["part_pred"], loc, batch, cfg, S0, ws, ws_max, 200, 20)
+    total.backward()
+    eng = Engine(nj, location_refinement=with_loc)
+    eng.load_weights(W)
+    got = fitdgp.train_forward_backward(eng, torch.from_numpy(frames).cuda(), batch, cfg, edges, ws, ws_max, 200, 20)
+    ref_total = float(total.detach()) - (float(loss["visible_loss_locref"].detach()) if not with_loc else 0.0)
+    assert abs(float(got["total_loss"]) - ref_total) <= 3e-2 * abs(ref_total), (got, ref_total)
+    worst = (1.0, None)
+    for name, t in sorted(Wt.items()):
+        if not t.requires_grad:
+            continue
+        g_ref = t.grad.numpy()
+        g = eng.get_variable(name, "grad")
+        assert g.shape == g_ref.shape, name
+        nr = float(np.linalg.norm(g_ref))
+        if nr < 1e-12:
+            assert float(np.abs(g).max()) < 1e-9, name
+            continue
+        cos = float((g * g_ref).sum() / (np.linalg.norm(g) * nr + 1e-30))
+        worst = min(worst, (cos, name))
+        assert cos > 0.97 and np.linalg.norm(g - g_ref) / nr < 0.3, (name, cos, np.linalg.norm(g - g_ref) / nr)
+    assert worst[0] > 0.97, worst
+    eng.close()
