@@ -28,6 +28,13 @@ METRIC = "frames/sec (ResNet-50 scoremap + DGP soft-argmax/potentials)"
 WORKLOAD = "configs[1]: synthetic 4-bodypart reaching video 747x832, estimate_pose inference (part_pred head, chain skeleton)"
 
 
+CONFIGS = {  # BASELINE.json configs -> (H, W, num_joints, skeleton, label)
+    "b": (747, 832, 4, "chain", WORKLOAD),
+    "c": (1024, 1280, 16, "chain", "configs[2]: synthetic 1280x1024 video, 16 bodyparts with chain skeleton, frame-sharded estimate_pose inference"),
+    "e": (480, 640, 20, "dense", "configs[4]: synthetic 640x480 videos x 20 bodyparts with dense skeleton (190 edges), estimate_pose inference"),
+}
+
+
 def conv_flops_per_frame(h, w, nj, locref=False):
     """Algorithmic forward FLOPs (2*MACs) of the conv + deconv layers (SURVEY.md 8d / Appendix B closed form)."""
     c2 = lambda v: -(-v // 2)
@@ -181,10 +188,16 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the auxiliary training-step measurement (configs[3])")
+    ap.add_argument("--config", default="b", choices=sorted(CONFIGS),
+                    help="BASELINE.json workload: b = configs[1] (the headline, default), c = configs[2], e = configs[4]")
     ap.add_argument("--cpu-frames", type=int, default=12)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
+    global H, W, NJ, WORKLOAD
+    H, W, NJ, skeleton_kind, WORKLOAD = CONFIGS[args.config]
+    if args.config != "b":
+        args.no_train = True
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -205,10 +218,10 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     from deepgraphpose_b200.engine import suggest_batch
-    B = args.batch if args.batch > 0 else suggest_batch(H, W)
+    B = args.batch if args.batch > 0 else suggest_batch(H, W, *((12, 24) if args.config == "c" else (24, 48)))
     eng = Engine(NJ, location_refinement=False, device=local_rank)
     eng.load_weights(synthetic.make_weights(NJ, seed=0, location_refinement=False))
-    edges = synthetic.chain_skeleton(NJ)
+    edges = synthetic.dense_skeleton(NJ) if skeleton_kind == "dense" else synthetic.chain_skeleton(NJ)
     flops_frame, (hs, ws) = conv_flops_per_frame(H, W, NJ, locref=False)
 
     # Distinct input batches, together larger than the 126 MB L2 (and every layer's activations are far larger still).
@@ -302,7 +315,7 @@ def main():
         sa_bytes = 4 * hs * ws * NJ * frames_timed
         traffic, traffic_note = None, "no ncu capture committed"
         tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(tpath):
+        if os.path.exists(tpath) and args.config == "b":
             with open(tpath) as f:
                 tj = json.load(f)
             traffic = tj["traffic_bytes_per_frame"] * B / 54
@@ -314,7 +327,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": B, "frame": [H, W, 3], "num_joints": NJ,
-                       "skeleton": "chain", "l2": "4 rotating input batches (%d MB) and per-layer activations (>600 MB/step) exceed the 126 MB L2" % (n_pool * B * H * W * 3 // 2 ** 20),
+                       "skeleton": skeleton_kind, "l2": "4 rotating input batches (%d MB) and per-layer activations (>600 MB/step) exceed the 126 MB L2" % (n_pool * B * H * W * 3 // 2 ** 20),
                        "batch_choice": "engine.suggest_batch: tile counts of the persistent GEMM grid land on multiples of the SM count",
                        "parallelism": "frame shards x%d, 1-frame halo all_gather" % world if world > 1 else "single GPU"},
             "clocks": clocks,
@@ -338,7 +351,7 @@ def main():
         if train_line is not None:
             keep = ("metric", "value", "unit", "ms_per_step", "config", "gpu_launches", "loss_after", "finite", "error")
             line["train_step"] = {k: train_line[k] for k in keep if k in train_line}
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.config == "b":
             fps, cores, cdt = cpu_reference_fps(args.cpu_frames, warmup=1)
             line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                                     "sample": "%d frames of the same workload, batch 1 (eval.py:328), %.1f s; CPU restatement of "
