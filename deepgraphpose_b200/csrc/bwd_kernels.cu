@@ -12,39 +12,15 @@
 //   scatter_add2  : gradient of resnet_utils.subsample (identity shortcut of a stride-2 unit): g_x[2p,2q] += d[p,q].
 //   col2im_bwd    : gradient of the deconv heads' col2im (gather of the head gradients per (pixel, tap, channel)).
 // Reductions are two-stage with a fixed order (bitwise reproducible).
+#include "half_utils.cuh"
 #include "kernels.cuh"
-
-#include <cuda_fp16.h>
 
 namespace dgp {
 
 namespace {
 
-__device__ __forceinline__ void unpack8(const uint4& v, float* f, int fp16) {
-  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    if (fp16) {
-      const float2 r = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
-      f[2 * i] = r.x;
-      f[2 * i + 1] = r.y;
-    } else {
-      f[2 * i] = __uint_as_float(w[i] << 16);
-      f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
-    }
-  }
-}
-__device__ __forceinline__ uint32_t pack2(float a, float b, int fp16) {
-  if (fp16) {
-    __half2 h = __floats2half2_rn(fminf(fmaxf(a, -65504.0f), 65504.0f), fminf(fmaxf(b, -65504.0f), 65504.0f));
-    return *reinterpret_cast<uint32_t*>(&h);
-  }
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
-__device__ __forceinline__ uint4 pack8v(const float* f, int fp16) {
-  return make_uint4(pack2(f[0], f[1], fp16), pack2(f[2], f[3], fp16), pack2(f[4], f[5], fp16), pack2(f[6], f[7], fp16));
-}
+using h16::unpack8;
+__device__ __forceinline__ uint4 pack8v(const float* f, int fp16) { return h16::pack8(f, fp16); }
 
 // MODE 0: plain ReLU layer.  MODE 1: junction, shortcut on the same pixel grid.  MODE 2: junction, identity shortcut
 // subsampled by 2 (sc is the unit input (N,Hx,Wx,C), read at (2p, 2q)).
@@ -280,10 +256,7 @@ __global__ void col2im_bwd_kernel(const float* __restrict__ g_logits, const floa
         else if (g_locref) v = g_locref[(((size_t)n * Ho + y) * Wo + x) * (size_t)(ctot - nj) + (co - nj)];
       }
     }
-    uint16_t o;
-    if (fp16) { __half hh = __float2half_rn(fminf(fmaxf(v, -65504.0f), 65504.0f)); o = *reinterpret_cast<uint16_t*>(&hh); }
-    else { __nv_bfloat16 bb = __float2bfloat16_rn(v); o = *reinterpret_cast<uint16_t*>(&bb); }
-    dG[t] = o;
+    dG[t] = h16::cvt1(v, fp16);
   }
 }
 

@@ -2,30 +2,15 @@
 // (dgrad) weight matrices, and the optimizer of fit_dgp (reference: src/deepgraphpose/models/fitdgp.py:706-713 --
 // MomentumOptimizer(lr, 0.9) on gradients clipped by global norm 10).  All of them are flat, HBM-bound passes over the
 // arena with 128-bit accesses; reductions use a fixed two-stage order (bitwise reproducible).
+#include "half_utils.cuh"
 #include "kernels.cuh"
-
-#include <cuda_fp16.h>
 
 namespace dgp {
 
 namespace {
 
-__device__ __forceinline__ uint32_t pack16(float a, float b, int fp16) {
-  if (fp16) {
-    __half2 h = __floats2half2_rn(fminf(fmaxf(a, -65504.0f), 65504.0f), fminf(fmaxf(b, -65504.0f), 65504.0f));
-    return *reinterpret_cast<uint32_t*>(&h);
-  }
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
-__device__ __forceinline__ uint16_t cvt16(float a, int fp16) {
-  if (fp16) {
-    __half h = __float2half_rn(fminf(fmaxf(a, -65504.0f), 65504.0f));
-    return *reinterpret_cast<uint16_t*>(&h);
-  }
-  __nv_bfloat16 h = __float2bfloat16_rn(a);
-  return *reinterpret_cast<uint16_t*>(&h);
-}
+__device__ __forceinline__ uint32_t pack16(float a, float b, int fp16) { return h16::pack2(a, b, fp16); }
+__device__ __forceinline__ uint16_t cvt16(float a, int fp16) { return h16::cvt1(a, fp16); }
 
 // w16[i] = round16(master[i]) over the weight part of the arena (n multiple of 8)
 __global__ void refresh_w16_kernel(const float4* __restrict__ master, uint4* __restrict__ w16, size_t n8, int fp16) {

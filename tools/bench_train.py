@@ -67,6 +67,9 @@ def measure(rank, local_rank, world, steps, warmup, nt, height, width, profile=T
     rng = np.random.default_rng(100 + rank)
     vis = [0, 3, 6][: max(1, nt // 3)]
     labels, batch = make_batch(rng, nt, hs, ws_, NJ, vis, ((0, 1),))
+    # the locref target / mask maps are generated on the device by the coord2map feeder kernel (no 6 MB feed per step)
+    batch = {k: v for k, v in batch.items() if k not in ("locref_map", "locref_mask")}
+    batch["visible_frame_within_batch"] = vis
     edges = synthetic.chain_skeleton(NJ)
     S0 = dgp_ops.skeleton_matrix(edges, NJ)
     cfg = oracle_loss.default_dgp_cfg(gm2=1, gm3=3, wt=0.0)
@@ -135,7 +138,8 @@ def measure(rank, local_rank, world, steps, warmup, nt, height, width, profile=T
             "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "configs[3]: DGP training step, %dx%d, nt=%d frames per replica (%d visible), nj=%d + locref, gm2=1 gm3=3 ws=1000 wt=0"
-                                   % (H, W, nt, len(vis), NJ), "parallelism": "dp%d, NCCL all-reduce of the 94 MB fp32 gradient buffer in %d buckets" % (world, dp.BUCKETS)},
+                                   % (H, W, nt, len(vis), NJ), "parallelism": "dp%d, NCCL all-reduce of the 94 MB fp32 gradient buffer in %d buckets" % (world, dp.BUCKETS),
+                       "feeds": "frames resident on the device; labels and marker index vectors fed from the host every step; locref maps built by dgp_locref_targets"},
             "clocks": clocks, "gpu_launches": launches, "loss_after": loss, "finite": bool(np.isfinite(loss)),
             "ms_per_step_by_family": fam, "ms_per_step_with_events": ms_prof / args.steps,
             "tflops": {"forward_gemm": tf(flops_fwd, prof["conv_gemm"][0]), "dgrad_gemm": tf(flops_fwd, prof["dgrad_gemm"][0]),
