@@ -76,6 +76,8 @@ SIGNATURES = {
     "dgp_train_forward_backward": (_i, [_vp, _vp, _i, _i, _i, C.POINTER(DgpLossCfg), C.POINTER(DgpLossBatch), _i, _vp, _vp]),
     "dgp_optimizer_step": (_i, [_vp, _f, _f, _f, _f, _vp]),
     "dgp_get_grad_buffer": (_i, [_vp, C.POINTER(_vp), C.POINTER(_sz)]),
+    "dgp_train_early_bucket": (_i, [_vp, C.POINTER(_sz), C.POINTER(_sz)]),
+    "dgp_train_wait_early_bucket": (_i, [_vp, _vp]),
     "dgp_get_grad_norm": (_i, [_vp, C.POINTER(_f)]),
     "dgp_train_outputs": (_i, [_vp, _i, _i, _i, C.POINTER(_vp), C.POINTER(_vp)]),
     "dgp_get_variable": (_i, [_vp, C.c_char_p, _i, _vp, _sz, _i64p, C.POINTER(_i)]),

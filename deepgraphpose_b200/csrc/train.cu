@@ -36,6 +36,7 @@ struct BStep {
 struct Backward {
   std::vector<BStep> steps;
   float *g_logits = nullptr, *g_locref = nullptr;
+  int early_step = -1;  // number of steps after which the gradients of block4 + heads (the arena's tail) are final
 };
 
 struct TrainState {
@@ -48,6 +49,11 @@ struct TrainState {
   W16* head_wd = nullptr;
   int head_Kd = 0;
   bool wd_fresh = false;
+  // Early all-reduce bucket: the weight gradients of block4 and the heads (two thirds of the arena, contiguous at the end of
+  // its weight part) are complete after a quarter of the backward pass; `ev_early` is recorded there so a data-parallel
+  // caller can start their all-reduce on a side stream while blocks 3..1 are still running.
+  cudaEvent_t ev_early = nullptr;
+  size_t early_off = 0, early_cnt = 0;
 };
 
 void train_destroy(dgp_handle* h) {
@@ -61,6 +67,7 @@ void train_destroy(dgp_handle* h) {
   cudaFree(ts->wgrad_ws.p);
   for (W16* p : ts->wd) cudaFree(p);
   cudaFree(ts->head_wd);
+  if (ts->ev_early) cudaEventDestroy(ts->ev_early);
   delete ts;
   h->train = nullptr;
 }
@@ -277,6 +284,7 @@ int build_backward(dgp_handle* h, Plan* pl) {
       bw->steps.push_back({7, 1, [=](cudaStream_t s) { return launch_scatter_add2(G, B, P, Q, C, Gx, H, W, fp16, s); }});
     }
     gi = (gi + 1) % 3;
+    if (ts->early_cnt > 0 && u.shortcut >= 0 && h->layers[u.shortcut].w_off == ts->early_off) bw->early_step = (int)bw->steps.size();
   }
   // ---- root: max-pool backward, conv1 ReLU/BN, conv1 wgrad (no dgrad: the input is the image)
   {
@@ -366,6 +374,13 @@ int dgp_train_enable(dgp_handle* h) {
     const ConvLayer& L = h->layers[i];
     CU_OK(h, cudaMalloc(&ts->wd[i], (size_t)L.Cin * L.R * L.S * L.Cout * sizeof(W16)));
   }
+  CU_OK(h, cudaEventCreateWithFlags(&ts->ev_early, cudaEventDisableTiming));
+  for (const UnitDesc& u : h->units)
+    if (u.scope.find("/block4/") != std::string::npos && u.shortcut >= 0) {
+      ts->early_off = h->layers[u.shortcut].w_off;
+      ts->early_cnt = h->n_w - ts->early_off;
+      break;
+    }
   ts->head_Kd = ceil_div(std::max(9 * h->ctot, h->layers[h->head_layer].Npad), 64) * 64;
   CU_OK(h, cudaMalloc(&ts->head_wd, (size_t)2048 * ts->head_Kd * sizeof(W16)));
   return DGP_OK;
@@ -394,11 +409,31 @@ int dgp_train_forward_backward(dgp_handle* h, const uint8_t* frames_dev, int nt,
   b.pred_dev = pl->logits;
   b.locref_dev = pl->locref;
   if ((rc = dgp_run_loss_impl(h, cfg, &b, losses_dev, nullptr, bw->g_logits, bw->g_locref, visible_only, stream))) return rc;
+  int k = 0;
   for (const BStep& st : bw->steps) {
-    ProfScope prof(h, st.kind, s);
-    CU_OK(h, st.run(s));
+    {
+      ProfScope prof(h, st.kind, s);
+      CU_OK(h, st.run(s));
+    }
     h->launches += st.launches;
+    if (++k == bw->early_step) CU_OK(h, cudaEventRecord(ts->ev_early, s));
   }
+  return DGP_OK;
+}
+
+int dgp_train_early_bucket(dgp_handle* h, size_t* offset_floats, size_t* count_floats) {
+  if (!h) return DGP_ERR_INVALID;
+  if (!h->train) return fail(h, DGP_ERR_STATE, "dgp_train_early_bucket before dgp_train_enable");
+  if (offset_floats) *offset_floats = h->train->early_off;
+  if (count_floats) *count_floats = h->train->early_cnt;
+  return DGP_OK;
+}
+
+int dgp_train_wait_early_bucket(dgp_handle* h, void* stream) {
+  if (!h) return DGP_ERR_INVALID;
+  if (!h->train) return fail(h, DGP_ERR_STATE, "dgp_train_wait_early_bucket before dgp_train_enable");
+  CU_OK(h, cudaSetDevice(h->device));
+  CU_OK(h, cudaStreamWaitEvent((cudaStream_t)stream, h->train->ev_early, 0));
   return DGP_OK;
 }
 

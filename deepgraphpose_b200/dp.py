@@ -27,13 +27,35 @@ def allreduce_flat_(flat, group=None, buckets=BUCKETS):
     return 1.0 / world
 
 
-def allreduce_gradients(engine, group=None):
-    """All-reduce the engine's gradient buffer across ranks; returns grad_scale for Engine.optimizer_step."""
+def allreduce_gradients(engine, group=None, overlap=True):
+    """All-reduce the engine's gradient buffer across ranks; returns grad_scale for Engine.optimizer_step.
+
+    With ``overlap`` the slice holding block4 + the heads (two thirds of the buffer, final after the first quarter of the
+    backward pass) is reduced on a side stream that waits on the handle's early-bucket event, i.e. while the GPU is still
+    differentiating blocks 3..1; the rest follows on the compute stream once the backward is done."""
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return 1.0
     buf = engine.grad_buffer()
-    # the training kernels ran on torch's current stream; NCCL orders its work after it
-    return allreduce_flat_(buf, group)
+    world = dist.get_world_size(group)
+    if not overlap:
+        # the training kernels ran on torch's current stream; NCCL orders its work after it
+        return allreduce_flat_(buf, group)
+    off, cnt = engine.early_bucket()
+    side = engine.__dict__.get("_dp_stream")
+    if side is None:
+        side = engine.__dict__["_dp_stream"] = torch.cuda.Stream(device=engine.device)
+    works = []
+    if cnt > 0:
+        with torch.cuda.stream(side):
+            engine.wait_early_bucket(side)
+            works.append(dist.all_reduce(buf[off:off + cnt], op=dist.ReduceOp.SUM, group=group, async_op=True))
+    if off > 0:
+        works.append(dist.all_reduce(buf[:off], op=dist.ReduceOp.SUM, group=group, async_op=True))
+    if off + cnt < buf.numel():
+        works.append(dist.all_reduce(buf[off + cnt:], op=dist.ReduceOp.SUM, group=group, async_op=True))
+    for w in works:
+        w.wait()   # the compute stream waits for the NCCL streams; the host does not block
+    return 1.0 / world
 
 
 def allreduce_mean_scalars(values, group=None):

@@ -268,6 +268,17 @@ class Engine:
         self._check(self.lib.dgp_get_grad_buffer(self.h, C.byref(p), C.byref(n)))
         return _device_view(p.value, (n.value // 4,), "<f4", self.device)
 
+    def early_bucket(self):
+        """(offset, count) in floats of the gradient-buffer slice that is final early in the backward pass (block4 + heads)."""
+        self.train_enable()
+        o, c = C.c_size_t(), C.c_size_t()
+        self._check(self.lib.dgp_train_early_bucket(self.h, C.byref(o), C.byref(c)))
+        return int(o.value), int(c.value)
+
+    def wait_early_bucket(self, stream):
+        """Make the torch.cuda.Stream `stream` wait until the early bucket of the last training step is final."""
+        self._check(self.lib.dgp_train_wait_early_bucket(self.h, C.c_void_p(stream.cuda_stream)))
+
     def grad_norm(self):
         v = C.c_float()
         self._check(self.lib.dgp_get_grad_norm(self.h, C.byref(v)))

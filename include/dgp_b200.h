@@ -191,6 +191,12 @@ int dgp_train_forward_backward(dgp_handle* h, const uint8_t* frames_dev, int nt,
 int dgp_optimizer_step(dgp_handle* h, float lr, float momentum, float clip_norm, float grad_scale, void* stream);
 /* Flat float32 gradient buffer (kernel layouts: [weights | gamma | beta | head bias]) for ncclAllReduce. */
 int dgp_get_grad_buffer(dgp_handle* h, void** dev_ptr, size_t* bytes);
+/* Overlap of the gradient all-reduce with the backward pass: the gradients of block4 and the heads -- floats
+ * [offset, offset + count) of the gradient buffer, about two thirds of it -- are final after the first quarter of the backward
+ * pass.  dgp_train_wait_early_bucket makes `stream` (a side stream) wait for that point of the LAST
+ * dgp_train_forward_backward, so their ncclAllReduce can run while blocks 3..1 are still being differentiated. */
+int dgp_train_early_bucket(dgp_handle* h, size_t* offset_floats, size_t* count_floats);
+int dgp_train_wait_early_bucket(dgp_handle* h, void* stream);
 /* Global gradient norm computed by the last dgp_optimizer_step (after grad_scale, before clipping). Synchronises. */
 int dgp_get_grad_norm(dgp_handle* h, float* norm_host);
 /* Device pointers of the head outputs (nt,2h,2w,nj) / (nt,2h,2w,2nj) written by the last training step at this shape. */

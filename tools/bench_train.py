@@ -83,7 +83,7 @@ def measure(rank, local_rank, world, steps, warmup, nt, height, width, profile=T
 
     def step():
         out = fitdgp.train_forward_backward(eng, frames, batch, cfg, edges, ws, ws_max, 1000, 100, sync=False)
-        scale = dp.allreduce_gradients(eng)
+        scale = dp.allreduce_gradients(eng, overlap=os.environ.get("DGP_DP_OVERLAP", "1") != "0")
         eng.optimizer_step(0.005, 0.9, 10.0, scale)
         return out
 
