@@ -77,6 +77,8 @@ class ClockSampler:
         self.index = index
         self.sm, self.bits = [], 0
         self.stop_flag = False
+        self.active = False     # samples are kept only while the timed region runs
+        self.ready = threading.Event()
         self.th = None
         self.max_mhz = None
 
@@ -86,14 +88,17 @@ class ClockSampler:
             pynvml.nvmlInit()
             h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
             self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.ready.set()
             while not self.stop_flag:
-                self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
-                try:
-                    self.bits |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
-                except Exception:
-                    self.bits |= int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
-                time.sleep(0.005)
+                if self.active:
+                    self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                    try:
+                        self.bits |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                    except Exception:
+                        self.bits |= int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                time.sleep(0.002)
         except Exception:
+            self.ready.set()
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm",
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
@@ -103,11 +108,17 @@ class ClockSampler:
             except Exception:
                 pass
 
+    def begin(self):
+        """Call right before the timed region (the thread was started earlier so that NVML is already initialised)."""
+        self.ready.wait(timeout=10)
+        self.active = True
+
     def start(self):
         self.th = threading.Thread(target=self._loop, daemon=True)
         self.th.start()
 
     def stop(self):
+        self.active = False
         self.stop_flag = True
         if self.th:
             self.th.join(timeout=5)
@@ -238,13 +249,14 @@ def main():
         pot = eng.potentials(out["mu"], edges, halo_next=halo, ws=ws_vec, ws_max=ws_max, wt_max=0.0)
         return out, pot
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for i in range(args.warmup):
         step(i)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.begin()
     launches0 = eng.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
@@ -300,7 +312,6 @@ def main():
     if not args.no_train:
         try:
             sys.path.insert(0, os.path.join(ROOT, "tools"))
-            sys.path.insert(0, os.path.join(ROOT, "tests"))
             import bench_train
             train_line = bench_train.measure(rank, local_rank, world, 5, 3, 10, H, W, profile=False)
         except Exception as ex:  # the headline line must survive a failure of the auxiliary measurement

@@ -107,3 +107,25 @@ def chain_skeleton(nj):
 
 def dense_skeleton(nj):
     return [(i, j) for i in range(nj) for j in range(i + 1, nj)]
+
+
+def make_training_batch(nt, H, W, nj, vis_frames, nan_joints=(), seed=0):
+    """Synthetic fit_dgp batch in the reference's feed_dict contract (fitdgp.py:797-815, dataset.py:187-239): labels of the
+    visible frames in scoremap (row, col) units with NaN for missing joints, marker index vectors
+    (marker = frame_in_batch * nj + joint; NaN-labelled joints of visible frames move to the hidden list), and the
+    positions of the visible frames in the batch (the locref maps are then built by the coord2map feeder).
+    Returns (labels (n_vis,nj,2) float64, feed dict)."""
+    rng = np.random.default_rng(seed)
+    vis = np.asarray(sorted(vis_frames), dtype=np.int64)
+    hid = np.array([t for t in range(nt) if t not in set(vis.tolist())], dtype=np.int64)
+    labels = np.stack([rng.uniform(1, H - 2, (len(vis), nj)), rng.uniform(1, W - 2, (len(vis), nj))], axis=2)
+    for (i, j) in nan_joints:
+        labels[i, j, :] = np.nan
+    nan_ind = sorted(int(nj * vis[i] + j) for (i, j) in nan_joints)
+    hidden = np.sort(np.concatenate([(hid[:, None] * nj + np.arange(nj)[None, :]).reshape(-1), np.asarray(nan_ind, dtype=np.int64)]))
+    vm0 = np.sort((vis[:, None] * nj + np.arange(nj)[None, :]).reshape(-1))
+    visible = np.setdiff1d(vm0, nan_ind)
+    feed = {"targets": labels, "visible_marker_pl": visible.astype(np.int64), "hidden_marker_pl": hidden.astype(np.int64),
+            "visible_marker_in_targets_pl": np.nonzero(np.isin(vm0, visible))[0], "nt_batch_pl": nt,
+            "visible_frame_within_batch": vis.tolist()}
+    return labels, feed

@@ -16,7 +16,6 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 import bench  # noqa: E402
 
 
@@ -28,11 +27,13 @@ def cpu_train_step_seconds(nt, H, W, NJ):
     from deepgraphpose_b200.engine import output_dims
     from oracle import dgp_loss as oracle_loss
     from oracle import dgp_ops, pose_net
-    from test_gpu_loss import make_batch
+    from oracle import feeders
     torch.set_num_threads(os.cpu_count())
     _, (hs, ws_) = output_dims(H, W)
-    rng = np.random.default_rng(7)
-    labels, batch = make_batch(rng, nt, hs, ws_, NJ, [0], ())
+    labels, batch = synthetic.make_training_batch(nt, hs, ws_, NJ, [0], (), seed=7)
+    batch["locref_map"], batch["locref_mask"] = feeders.batch_locref_maps(labels, [0], nt, hs, ws_, NJ)
+    xg, yg = np.meshgrid(np.linspace(0, hs - 1, hs), np.linspace(0, ws_ - 1, ws_))
+    batch["alpha_tf"] = np.array([xg, yg]).swapaxes(1, 2)
     edges = synthetic.chain_skeleton(NJ)
     S0 = dgp_ops.skeleton_matrix(edges, NJ)
     cfg = oracle_loss.default_dgp_cfg(gm2=1, gm3=3, wt=0.0)
@@ -57,23 +58,21 @@ def measure(rank, local_rank, world, steps, warmup, nt, height, width, profile=T
     import torch.distributed as dist
     from deepgraphpose_b200 import dp, fitdgp, synthetic
     from deepgraphpose_b200.engine import Engine, output_dims
-    from oracle import dgp_loss as oracle_loss  # host-side batch construction only (feed_dict contract)
-    from oracle import dgp_ops
-    from test_gpu_loss import make_batch
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     H, W, NJ, nt = args.height, args.width, bench.NJ, args.nt
     _, (hs, ws_) = output_dims(H, W)
-    rng = np.random.default_rng(100 + rank)
     vis = [0, 3, 6][: max(1, nt // 3)]
-    labels, batch = make_batch(rng, nt, hs, ws_, NJ, vis, ((0, 1),))
-    # the locref target / mask maps are generated on the device by the coord2map feeder kernel (no 6 MB feed per step)
-    batch = {k: v for k, v in batch.items() if k not in ("locref_map", "locref_mask")}
-    batch["visible_frame_within_batch"] = vis
+    # feed_dict contract of fit_dgp; the locref target / mask maps are generated on the device by the coord2map feeder
+    # kernel (no 6 MB feed per step)
+    labels, batch = synthetic.make_training_batch(nt, hs, ws_, NJ, vis, ((0, 1),), seed=100 + rank)
     edges = synthetic.chain_skeleton(NJ)
-    S0 = dgp_ops.skeleton_matrix(edges, NJ)
-    cfg = oracle_loss.default_dgp_cfg(gm2=1, gm3=3, wt=0.0)
-    ws, ws_max = oracle_loss.spatial_clique_params(labels, S0, cfg)
+    S0 = np.zeros((len(edges), NJ))
+    for l, (a, b) in enumerate(edges):
+        S0[l, a], S0[l, b] = 1.0, -1.0
+    cfg = dict(gm2=1, gm3=3, wt=0.0, wt_max=0.0, wn_visible=5.0, wn_hidden=3.0, gamma=1.0, gauss_len=1.0, lengthscale=1.0,
+               locref_loss_weight=0.05, stride=8.0)
+    ws, ws_max = fitdgp.spatial_clique_params([labels], S0, 8.0, 1000.0, 1.2)
     eng = Engine(NJ, location_refinement=True, device=local_rank)
     eng.load_weights(synthetic.make_weights(NJ, seed=0))
     frames_host = bench.make_frame_pool(nt, seed=1234 + rank) if (H, W) == (bench.H, bench.W) else \
@@ -87,13 +86,14 @@ def measure(rank, local_rank, world, steps, warmup, nt, height, width, profile=T
         eng.optimizer_step(0.005, 0.9, 10.0, scale)
         return out
 
+    sampler = bench.ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = bench.ClockSampler(local_rank)
-    sampler.start()
+    sampler.begin()
     l0 = eng.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
