@@ -84,25 +84,26 @@ __global__ void __launch_bounds__(256) relu_bn_bwd_kernel(uint4* __restrict__ g,
   }
 }
 
-// dbeta[c] = S0;  dgamma[c] = (S_which - beta * S0) / gamma.  Block = 32 channels x 32 row groups: row group r sums the
-// partial rows r, r+32, ... (coalesced across the 32 channels), then a fixed-order tree over the row groups.
+// dbeta[c] = S0;  dgamma[c] = (S_which - beta * S0) / gamma.  Block = 8 channels x 128 row groups: row group r sums the
+// partial rows r, r+128, ... (at most 5 dependent loads per thread -- this kernel is pure latency), then a fixed-order tree
+// over the row groups.
 __global__ void __launch_bounds__(1024) bn_grad_finalize_kernel(const float* __restrict__ partial, int nblocks, int NS,
                                                                 int which, int C, const float* __restrict__ gamma,
                                                                 const float* __restrict__ beta,
                                                                 float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  const int cl = threadIdx.x & 31, rg = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cl;
+  const int cl = threadIdx.x & 7, rg = threadIdx.x >> 3;
+  const int c = blockIdx.x * 8 + cl;
   float s0 = 0.0f, s1 = 0.0f;
   if (c < C)
-    for (int b = rg; b < nblocks; b += 32) {
+    for (int b = rg; b < nblocks; b += 128) {
       s0 += partial[((size_t)b * NS + 0) * C + c];
       s1 += partial[((size_t)b * NS + which) * C + c];
     }
-  __shared__ float sm0[32][33], sm1[32][33];
+  __shared__ float sm0[128][9], sm1[128][9];
   sm0[rg][cl] = s0;
   sm1[rg][cl] = s1;
   __syncthreads();
-  for (int st = 16; st > 0; st >>= 1) {
+  for (int st = 64; st > 0; st >>= 1) {
     if (rg < st) {
       sm0[rg][cl] += sm0[rg + st][cl];
       sm1[rg][cl] += sm1[rg + st][cl];
@@ -320,7 +321,7 @@ cudaError_t launch_relu_bn_bwd(int mode, void* g, const void* act, const void* s
 
 cudaError_t launch_bn_grad_finalize(const float* partial, int nblocks, int ns, int which, int C, const float* gamma,
                                     const float* beta, float* dgamma, float* dbeta, cudaStream_t s) {
-  bn_grad_finalize_kernel<<<(C + 31) / 32, 1024, 0, s>>>(partial, nblocks, ns, which, C, gamma, beta, dgamma, dbeta);
+  bn_grad_finalize_kernel<<<(C + 7) / 8, 1024, 0, s>>>(partial, nblocks, ns, which, C, gamma, beta, dgamma, dbeta);
   return cudaGetLastError();
 }
 

@@ -62,9 +62,17 @@ cudaError_t launch_dgp_loss_backward(const LossArgs& a, const float* norm, float
 cudaError_t launch_refresh_w16(const float* master, void* w16, size_t n, int fp16, cudaStream_t s);
 cudaError_t launch_refresh_bn(const float* gamma, const float* beta, const float* mean, const float* var, float eps, int n,
                               float* scale, float* shift, cudaStream_t s);
-// wd[ci][T-1-tap][co] = round16(w[co][tap][ci] * scale[co]); Kd = row length of wd (>= taps * Cout, zero padded)
-cudaError_t launch_build_dgrad_w(const float* w, const float* scale, int Cout, int taps, int Cin, int rows_w, void* wd,
-                                 int Kd, int fp16, cudaStream_t s);
+// wd[ci][T-1-tap][co] = round16(w[co][tap][ci] * scale[co]) for every conv layer in one launch: one job per layer,
+// tile_start = prefix sum of (Cin/32)*(Cout/32)*taps over the jobs (Cin, Cout multiples of 32).
+struct DgradWJob {
+  size_t w_off;     // offset of w [Cout][taps*Cin] in the master arena
+  uint16_t* wd;     // [Cin][taps*Cout]
+  int ch_off;       // offset of the layer's channels in the BN scale arena
+  int Cout, taps, Cin;
+  int tile_start;
+};
+cudaError_t launch_build_dgrad_w(const DgradWJob* jobs_dev, int njobs, int total_tiles, const float* master,
+                                 const float* scale_arena, int fp16, cudaStream_t s);
 cudaError_t launch_build_head_dgrad_w(const float* wh, int rows, int C, void* whT, int Kd, int fp16, cudaStream_t s);
 int sqnorm_partials();
 // norm_clip[0] = |grad_scale| * ||g||_2, norm_clip[1] = clip / max(norm, clip) (1 if clip <= 0)

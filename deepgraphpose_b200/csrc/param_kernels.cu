@@ -34,22 +34,38 @@ __global__ void refresh_bn_kernel(const float* __restrict__ gamma, const float* 
 // Data-gradient operand of one conv: wd[ci][T-1-tap][co] = round16(w[co][tap][ci] * scale[co])  (the BN scale of the
 // output channel is folded in, so the dgrad GEMM consumes dy = dL/d(BN output) directly).  Per tap this is a
 // Cout x Cin -> Cin x Cout transpose: 32 x 32 tiles through shared memory, coalesced on both sides.
-__global__ void __launch_bounds__(256) build_dgrad_w_kernel(const float* __restrict__ w, const float* __restrict__ scale,
-                                                            int Cout, int taps, int Cin, uint16_t* __restrict__ wd, int fp16) {
+__global__ void __launch_bounds__(256) build_dgrad_w_kernel(const DgradWJob* __restrict__ jobs, int njobs,
+                                                            const float* __restrict__ master,
+                                                            const float* __restrict__ scale_arena, int fp16) {
   __shared__ float tile[32][33];
+  __shared__ int s_job;
+  // all layers in ONE launch: a block finds its layer from the prefix of 32x32-tile counts (<= 52 entries)
+  if (threadIdx.x == 0) {
+    int j = 0;
+    while (j + 1 < njobs && (int)blockIdx.x >= jobs[j + 1].tile_start) ++j;
+    s_job = j;
+  }
+  __syncthreads();
+  const DgradWJob jb = jobs[s_job];
+  const int local = (int)blockIdx.x - jb.tile_start;
+  const int tx_n = jb.Cin / 32, ty_n = jb.Cout / 32;
+  const int tap = local / (tx_n * ty_n);
+  const int rem = local - tap * (tx_n * ty_n);
+  const int co0 = (rem / tx_n) * 32, ci0 = (rem - (rem / tx_n) * tx_n) * 32;
+  const float* w = master + jb.w_off;
+  const float* scale = scale_arena + jb.ch_off;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int tap = blockIdx.z, ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
-  const size_t K = (size_t)taps * Cin, Kd = (size_t)taps * Cout;
+  const size_t K = (size_t)jb.taps * jb.Cin, Kd = (size_t)jb.taps * jb.Cout;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int co = co0 + ty + 8 * j;
-    tile[ty + 8 * j][tx] = w[(size_t)co * K + (size_t)tap * Cin + ci0 + tx] * (scale ? scale[co] : 1.0f);
+    tile[ty + 8 * j][tx] = w[(size_t)co * K + (size_t)tap * jb.Cin + ci0 + tx] * scale[co];
   }
   __syncthreads();
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int ci = ci0 + ty + 8 * j;
-    wd[(size_t)ci * Kd + (size_t)(taps - 1 - tap) * Cout + co0 + tx] = cvt16(tile[tx][ty + 8 * j], fp16);
+    jb.wd[(size_t)ci * Kd + (size_t)(jb.taps - 1 - tap) * jb.Cout + co0 + tx] = cvt16(tile[tx][ty + 8 * j], fp16);
   }
 }
 
@@ -140,12 +156,10 @@ cudaError_t launch_refresh_bn(const float* gamma, const float* beta, const float
   return cudaGetLastError();
 }
 
-cudaError_t launch_build_dgrad_w(const float* w, const float* scale, int Cout, int taps, int Cin, int rows_w, void* wd,
-                                 int Kd, int fp16, cudaStream_t s) {
-  if (Cout % 32 || Cin % 32 || Kd != taps * Cout) return cudaErrorInvalidValue;
-  (void)rows_w;
-  build_dgrad_w_kernel<<<dim3(Cin / 32, Cout / 32, taps), 256, 0, s>>>(w, scale, Cout, taps, Cin,
-                                                                       reinterpret_cast<uint16_t*>(wd), fp16);
+cudaError_t launch_build_dgrad_w(const DgradWJob* jobs_dev, int njobs, int total_tiles, const float* master,
+                                 const float* scale_arena, int fp16, cudaStream_t s) {
+  if (njobs < 1 || total_tiles < 1) return cudaSuccess;
+  build_dgrad_w_kernel<<<total_tiles, 256, 0, s>>>(jobs_dev, njobs, master, scale_arena, fp16);
   return cudaGetLastError();
 }
 

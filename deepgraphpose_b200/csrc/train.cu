@@ -49,6 +49,8 @@ struct TrainState {
   W16* head_wd = nullptr;
   int head_Kd = 0;
   bool wd_fresh = false;
+  DgradWJob* wd_jobs = nullptr;  // device table for the one-launch rebuild of every dgrad operand
+  int n_wd_jobs = 0, wd_tiles = 0;
   // Early all-reduce bucket: the weight gradients of block4 and the heads (two thirds of the arena, contiguous at the end of
   // its weight part) are complete after a quarter of the backward pass; `ev_early` is recorded there so a data-parallel
   // caller can start their all-reduce on a side stream while blocks 3..1 are still running.
@@ -67,6 +69,7 @@ void train_destroy(dgp_handle* h) {
   cudaFree(ts->wgrad_ws.p);
   for (W16* p : ts->wd) cudaFree(p);
   cudaFree(ts->head_wd);
+  cudaFree(ts->wd_jobs);
   if (ts->ev_early) cudaEventDestroy(ts->ev_early);
   delete ts;
   h->train = nullptr;
@@ -76,16 +79,10 @@ namespace {
 
 int refresh_dgrad_weights(dgp_handle* h, cudaStream_t s) {
   TrainState* ts = h->train;
-  for (size_t i = 0; i < h->layers.size(); ++i) {
-    if (!ts->wd[i]) continue;
-    const ConvLayer& L = h->layers[i];
-    CU_OK(h, launch_build_dgrad_w(h->master + L.w_off, L.scale, L.Cout, L.R * L.S, L.Cin, L.Npad, ts->wd[i],
-                                  L.R * L.S * L.Cout, h->fp16, s));
-    h->launches++;
-  }
+  CU_OK(h, launch_build_dgrad_w(ts->wd_jobs, ts->n_wd_jobs, ts->wd_tiles, h->master, h->bn_ss, h->fp16, s));
   const ConvLayer& Lh = h->layers[h->head_layer];
   CU_OK(h, launch_build_head_dgrad_w(h->master + Lh.w_off, 9 * h->ctot, 2048, ts->head_wd, ts->head_Kd, h->fp16, s));
-  h->launches++;
+  h->launches += 2;
   ts->wd_fresh = true;
   return DGP_OK;
 }
@@ -369,11 +366,21 @@ int dgp_train_enable(dgp_handle* h) {
   CU_OK(h, cudaMalloc(&ts->norm_clip, 2 * sizeof(float)));
   CU_OK(h, cudaMemset(ts->norm_clip, 0, 2 * sizeof(float)));
   ts->wd.assign(h->layers.size(), nullptr);
+  std::vector<DgradWJob> jobs;
   for (size_t i = 0; i < h->layers.size(); ++i) {
     if ((int)i == h->conv1_layer || (int)i == h->head_layer) continue;
     const ConvLayer& L = h->layers[i];
+    if (L.Cin % 32 || L.Cout % 32 || L.ch_off < 0) return fail(h, DGP_ERR_UNSUPPORTED, "%s: dgrad operand needs 32-aligned channels", L.scope.c_str());
     CU_OK(h, cudaMalloc(&ts->wd[i], (size_t)L.Cin * L.R * L.S * L.Cout * sizeof(W16)));
+    DgradWJob jb;
+    jb.w_off = L.w_off; jb.wd = reinterpret_cast<uint16_t*>(ts->wd[i]); jb.ch_off = L.ch_off;
+    jb.Cout = L.Cout; jb.taps = L.R * L.S; jb.Cin = L.Cin; jb.tile_start = ts->wd_tiles;
+    ts->wd_tiles += (L.Cin / 32) * (L.Cout / 32) * L.R * L.S;
+    jobs.push_back(jb);
   }
+  ts->n_wd_jobs = (int)jobs.size();
+  CU_OK(h, cudaMalloc(&ts->wd_jobs, jobs.size() * sizeof(DgradWJob)));
+  CU_OK(h, cudaMemcpy(ts->wd_jobs, jobs.data(), jobs.size() * sizeof(DgradWJob), cudaMemcpyHostToDevice));
   CU_OK(h, cudaEventCreateWithFlags(&ts->ev_early, cudaEventDisableTiming));
   for (const UnitDesc& u : h->units)
     if (u.scope.find("/block4/") != std::string::npos && u.shortcut >= 0) {
