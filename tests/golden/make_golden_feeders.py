@@ -53,5 +53,24 @@ for tag, (n_vis, nj, nx, ny) in {"a": (3, 4, 12, 16), "b": (1, 5, 30, 38), "c": 
     t, m = ns["coord2map"](PData(nj), jl, nx, ny, nj)
     out.update({tag + "_joint_loc": jl, tag + "_targets": t.astype(np.float32), tag + "_mask": m.astype(np.uint8),
                 tag + "_dims": np.array([nx, ny, nj])})
+# ---- marker index vectors: the reference's gen_idx_chunk (dataset.py:187-239) on the batches synthetic.make_training_batch draws
+import sys
+from itertools import chain
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+from deepgraphpose_b200 import synthetic  # noqa: E402
+
+ns["chain"] = chain
+exec(cut(REF + "/deepgraphpose/dataset.py", "gen_idx_chunk"), ns)
+for tag, (nt, H, W, nj, vis, nan_joints, seed) in {"m0": (10, 94, 104, 4, [0, 3, 6], ((0, 1),), 100),
+                                                  "m1": (5, 20, 24, 5, [1, 3], ((0, 0), (1, 4), (1, 2)), 3),
+                                                  "m2": (4, 12, 16, 3, [], (), 9), "m3": (3, 12, 16, 3, [0, 1, 2], (), 2)}.items():
+    labels, feed = synthetic.make_training_batch(nt, H, W, nj, vis, nan_joints, seed=seed)
+    hid = np.array([t for t in range(nt) if t not in vis], dtype=np.int64)
+    v, h, vit = ns["gen_idx_chunk"](np.array(vis, dtype=np.int64), hid, labels)
+    out.update({tag + "_args": np.array([nt, H, W, nj, seed]), tag + "_vis": np.array(vis, dtype=np.int64),
+                tag + "_nan": np.array(nan_joints, dtype=np.int64).reshape(-1, 2), tag + "_labels": labels,
+                tag + "_visible_marker": np.asarray(v, dtype=np.int64), tag + "_hidden_marker": np.asarray(h, dtype=np.int64),
+                tag + "_vit": np.asarray(vit, dtype=np.int64)})
 np.savez_compressed(os.path.join(OUT, "feeders.npz"), **out)
 print({k: v.shape for k, v in out.items()})

@@ -57,3 +57,20 @@ def test_gpu_locref_targets_bit_exact(case):
     t2, m2 = dataset.coord2map(P(), jl, nx, ny, nj, engine=eng)
     assert t2.dtype == np.float64 and np.array_equal(t2.astype(np.float32), targets) and np.array_equal(m2.astype(np.uint8), mask)
     eng.close()
+
+
+@pytest.mark.parametrize("tag", ["m0", "m1", "m2", "m3"])
+def test_synthetic_training_batch_matches_reference_gen_idx_chunk(tag):
+    """The marker index vectors of synthetic.make_training_batch (what bench / tests feed) == the reference's own
+    gen_idx_chunk (dataset.py:187-239) on the same labels: NaN joints of visible frames move to the hidden list,
+    visible_marker_in_targets indexes targets.reshape(-1, 2)."""
+    from deepgraphpose_b200 import synthetic
+    with np.load(G) as z:
+        g = {k[len(tag) + 1:]: z[k] for k in z.files if k.startswith(tag + "_")}
+    nt, H, W, nj, seed = [int(v) for v in g["args"]]
+    labels, feed = synthetic.make_training_batch(nt, H, W, nj, g["vis"].tolist(), [tuple(r) for r in g["nan"].tolist()], seed=seed)
+    assert np.array_equal(np.isnan(labels), np.isnan(g["labels"])) and np.allclose(np.nan_to_num(labels), np.nan_to_num(g["labels"]))
+    assert np.array_equal(feed["visible_marker_pl"], g["visible_marker"])
+    assert np.array_equal(feed["hidden_marker_pl"], g["hidden_marker"])
+    assert np.array_equal(feed["visible_marker_in_targets_pl"], g["vit"])
+    assert feed["visible_frame_within_batch"] == g["vis"].tolist() and feed["nt_batch_pl"] == nt
