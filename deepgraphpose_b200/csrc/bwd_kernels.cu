@@ -290,6 +290,10 @@ __global__ void head_bias_final_kernel(const float* __restrict__ partial, int nb
   dbias[c] = s;
 }
 
+__global__ void scale_inplace_kernel(float* __restrict__ x, size_t n, float s) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) x[i] *= s;
+}
+
 int flat_grid(size_t n, int threads) {
   size_t g = (n + threads - 1) / threads;
   if (g > 148 * 16) g = 148 * 16;
@@ -368,6 +372,12 @@ cudaError_t launch_head_bias_grad(const float* g, size_t npix, int C, float* par
   const int nthreads = (148 * 256 / C) * C;
   head_bias_partial_kernel<<<148, 256, 0, s>>>(g, npix * (size_t)C, C, nthreads, partial);
   head_bias_final_kernel<<<1, 256, 0, s>>>(partial, 148, C, dbias);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_scale_inplace(float* x, size_t n, float scale, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  scale_inplace_kernel<<<flat_grid(n, 256), 256, 0, s>>>(x, n, scale);
   return cudaGetLastError();
 }
 

@@ -99,6 +99,8 @@ int head_bias_blocks();
 // g (npix, C) fp32 -> dbias[C]; partial: [head_bias_blocks()][C] floats of workspace
 cudaError_t launch_head_bias_grad(const float* g, size_t npix, int C, float* partial, float* dbias, cudaStream_t s);
 
+cudaError_t launch_scale_inplace(float* x, size_t n, float scale, cudaStream_t s);
+
 // evaluate_dgp 'dgp' locref read-out: st (B,H,W,nj) blurred softmax, locref (B,H,W,2nj) raw -> pose (B,nj,3) = (x,y,1)
 cudaError_t launch_soft_pose(const float* st, const float* locref, int B, int H, int W, int nj, float stride,
                              float locref_stdev, int swap_offsets, float* pose, cudaStream_t stream);

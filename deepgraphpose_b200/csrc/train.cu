@@ -14,6 +14,7 @@
 //   shortcut  : identity: + d (GEMM residual; stride 2: scatter-add)   projection: wgrad(x, d), g_x += dgrad(d)
 // The BN scale of a layer is folded into its dgrad operand (build_dgrad_w_kernel) and applied per output row in the
 // wgrad reduction, so every GEMM consumes the same dy tensor.
+#include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -49,6 +50,7 @@ struct TrainState {
   W16* head_wd = nullptr;
   int head_Kd = 0;
   bool wd_fresh = false;
+  float loss_scale = 1.0f;       // head gradients are multiplied by this before the network backward (fp16 storage)
   DgradWJob* wd_jobs = nullptr;  // device table for the one-launch rebuild of every dgrad operand
   int n_wd_jobs = 0, wd_tiles = 0;
   // Early all-reduce bucket: the weight gradients of block4 and the heads (two thirds of the arena, contiguous at the end of
@@ -417,6 +419,12 @@ int dgp_train_forward_backward(dgp_handle* h, const uint8_t* frames_dev, int nt,
   b.locref_dev = pl->locref;
   if ((rc = dgp_run_loss_impl(h, cfg, &b, losses_dev, nullptr, bw->g_logits, bw->g_locref, visible_only, stream))) return rc;
   int k = 0;
+  if (ts->loss_scale != 1.0f) {
+    const size_t n = (size_t)nt * 4 * pl->hf * pl->wf * h->cfg.num_joints;
+    CU_OK(h, launch_scale_inplace(bw->g_logits, n, ts->loss_scale, s));
+    if (bw->g_locref) CU_OK(h, launch_scale_inplace(bw->g_locref, 2 * n, ts->loss_scale, s));
+    h->launches += bw->g_locref ? 2 : 1;
+  }
   for (const BStep& st : bw->steps) {
     {
       ProfScope prof(h, st.kind, s);
@@ -450,12 +458,21 @@ int dgp_optimizer_step(dgp_handle* h, float lr, float momentum, float clip_norm,
   CU_OK(h, cudaSetDevice(h->device));
   cudaStream_t s = (cudaStream_t)stream;
   TrainState* ts = h->train;
+  grad_scale /= ts->loss_scale;  // the buffer holds loss_scale * gradient
   CU_OK(h, launch_global_norm(ts->grads, h->n_params, grad_scale, clip_norm, ts->norm_partial, ts->norm_clip, s));
   CU_OK(h, launch_momentum_step(h->master, ts->accum, ts->grads, h->n_params, lr, momentum, grad_scale, ts->norm_clip, s));
   h->launches += 3;
   int rc = refresh_operands(h, s);
   if (rc) return rc;
   return refresh_dgrad_weights(h, s);
+}
+
+int dgp_train_set_loss_scale(dgp_handle* h, float loss_scale) {
+  if (!h) return DGP_ERR_INVALID;
+  if (!h->train) return fail(h, DGP_ERR_STATE, "dgp_train_set_loss_scale before dgp_train_enable");
+  if (!(loss_scale > 0.0f) || !isfinite(loss_scale)) return fail(h, DGP_ERR_INVALID, "dgp_train_set_loss_scale: scale must be positive and finite");
+  h->train->loss_scale = loss_scale;
+  return DGP_OK;
 }
 
 int dgp_get_grad_buffer(dgp_handle* h, void** dev_ptr, size_t* bytes) {
@@ -510,6 +527,10 @@ int dgp_get_variable(dgp_handle* h, const char* tf_var_name, int what, float* ho
   if (ndim) *ndim = nd;
   if (!host_out) return DGP_OK;
   if (n > max_elems) return fail(h, DGP_ERR_INVALID, "buffer too small for %s", tf_var_name);
+  struct Unscale {  // gradients are stored multiplied by the loss scale; hand back the true gradient
+    float* p; size_t n; float f;
+    ~Unscale() { if (f != 1.0f) for (size_t i = 0; i < n; ++i) p[i] *= f; }
+  } unscale{host_out, n, what == 1 ? 1.0f / h->train->loss_scale : 1.0f};
   CU_OK(h, cudaSetDevice(h->device));
   CU_OK(h, cudaDeviceSynchronize());
   if (r.kind == 2 || r.kind == 3) {

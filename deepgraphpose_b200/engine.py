@@ -268,6 +268,11 @@ class Engine:
         self._check(self.lib.dgp_get_grad_buffer(self.h, C.byref(p), C.byref(n)))
         return _device_view(p.value, (n.value // 4,), "<f4", self.device)
 
+    def set_loss_scale(self, loss_scale):
+        """Loss scaling for fp16-storage training (no effect on the update; see dgp_train_set_loss_scale)."""
+        self.train_enable()
+        self._check(self.lib.dgp_train_set_loss_scale(self.h, float(loss_scale)))
+
     def early_bucket(self):
         """(offset, count) in floats of the gradient-buffer slice that is final early in the backward pass (block4 + heads)."""
         self.train_enable()

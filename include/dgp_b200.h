@@ -189,6 +189,11 @@ int dgp_train_forward_backward(dgp_handle* h, const uint8_t* frames_dev, int nt,
 /* g' = g * grad_scale; g' *= clip_norm / max(||g'||, clip_norm) (clip_norm <= 0: no clipping);
  * accum = momentum * accum + g'; var -= lr * accum; then refreshes the 16-bit operands and BN scale/shift. */
 int dgp_optimizer_step(dgp_handle* h, float lr, float momentum, float clip_norm, float grad_scale, void* stream);
+/* Loss scaling for fp16 storage (precision = 1): the head gradients are multiplied by loss_scale before the network
+ * backward so that small activation gradients stay above fp16's subnormal range; dgp_optimizer_step divides it out again and
+ * dgp_get_variable(what = 1) returns unscaled gradients (the raw buffer of dgp_get_grad_buffer holds loss_scale * gradient).
+ * Default 1 (bf16 storage has fp32's exponent range and needs none). */
+int dgp_train_set_loss_scale(dgp_handle* h, float loss_scale);
 /* Flat float32 gradient buffer (kernel layouts: [weights | gamma | beta | head bias]) for ncclAllReduce. */
 int dgp_get_grad_buffer(dgp_handle* h, void** dev_ptr, size_t* bytes);
 /* Overlap of the gradient all-reduce with the backward pass: the gradients of block4 and the heads -- floats

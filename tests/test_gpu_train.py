@@ -151,8 +151,9 @@ def _report(tag, rows):
 
 def test_gradient_error_scales_with_storage_precision():
     """The gap to the fp32 oracle is storage rounding, not logic: the same kernels with fp16 storage (8x finer mantissa)
-    give ~3x smaller gradient errors (measured: median rel-L2 0.029 / max 0.054 vs 0.081 / 0.153 in bf16; what remains
-    is fp16 underflow of the small activation gradients).  tools/diag_emulation.py shows why a bf16-rounding emulation of
+    give ~3x smaller gradient errors (measured: median rel-L2 0.029 / max 0.054 vs 0.081 / 0.153 in bf16; loss scales of
+    1, 1024 and 65536 give the same figures, so the remainder is forward rounding -- ReLU masks and pool winners taken from
+    rounded activations -- not underflow of the activation gradients).  tools/diag_emulation.py shows why a bf16-rounding emulation of
     the oracle cannot be used instead: rounding-boundary flips decorrelate the two forwards after ~10 layers."""
     from deepgraphpose_b200 import fitdgp
     from deepgraphpose_b200.engine import Engine
@@ -160,6 +161,7 @@ def test_gradient_error_scales_with_storage_precision():
     loss, ref, _ = _oracle_grads(W, frames, batch, S0, cfg, ws, ws_max)
     eng = Engine(NJ, precision="fp16")
     eng.load_weights(W)
+    eng.set_loss_scale(float(os.environ.get("DGP_TEST_LOSS_SCALE", "1024")))   # keeps small gradients out of fp16's subnormals
     got = fitdgp.train_forward_backward(eng, torch.from_numpy(frames).cuda(), batch, cfg, edges, ws, ws_max, 200, 20)
     assert abs(float(got["total_loss"]) - loss["total_loss"]) <= 1e-3 * abs(loss["total_loss"])  # BASELINE: loss <= 1e-3 rel
     rows = []
@@ -341,3 +343,24 @@ def test_gradients_other_geometries(cfgcase):
         assert cos > 0.97 and np.linalg.norm(g - g_ref) / nr < 0.3, (name, cos, np.linalg.norm(g - g_ref) / nr)
     assert worst[0] > 0.97, worst
     eng.close()
+
+
+def test_loss_scale_is_transparent():
+    """A power-of-two loss scale only shifts exponents (bf16 storage, no overflow): unscaled gradients, the clipped Momentum
+    update and therefore the weights are bitwise identical to the unscaled run."""
+    from deepgraphpose_b200 import fitdgp
+    from deepgraphpose_b200.engine import Engine
+    W, frames, batch, edges, S0, cfg, ws, ws_max = _setup(seed=21)
+    res = []
+    for scale in (1.0, 256.0):
+        eng = Engine(NJ)
+        eng.load_weights(W)
+        eng.set_loss_scale(scale)
+        fitdgp.train_forward_backward(eng, torch.from_numpy(frames).cuda(), batch, cfg, edges, ws, ws_max, 200, 20)
+        g = eng.get_variable("resnet_v1_50/block2/unit_1/bottleneck_v1/conv2/weights", "grad")
+        eng.optimizer_step(0.005, 0.9, 10.0, 1.0)
+        res.append((g, eng.get_variable("resnet_v1_50/block2/unit_1/bottleneck_v1/conv2/weights"), eng.grad_norm(),
+                    eng.get_variable("pose/part_pred/block4/biases")))
+        eng.close()
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][3], res[1][3])
+    assert res[0][2] == res[1][2]
