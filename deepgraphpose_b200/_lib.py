@@ -82,6 +82,7 @@ SIGNATURES = {
     "dgp_get_grad_norm": (_i, [_vp, C.POINTER(_f)]),
     "dgp_train_outputs": (_i, [_vp, _i, _i, _i, C.POINTER(_vp), C.POINTER(_vp)]),
     "dgp_get_variable": (_i, [_vp, C.c_char_p, _i, _vp, _sz, _i64p, C.POINTER(_i)]),
+    "dgp_set_variable": (_i, [_vp, C.c_char_p, _i, _vp, _sz]),
     "dgp_set_profiling": (_i, [_vp, _i]),
     "dgp_get_profile": (_i, [_vp, C.POINTER(C.c_double), _i64p, _i]),
     "dgp_launch_count": (C.c_int64, [_vp]),

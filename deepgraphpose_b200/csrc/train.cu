@@ -566,4 +566,65 @@ int dgp_get_variable(dgp_handle* h, const char* tf_var_name, int what, float* ho
   return DGP_OK;
 }
 
+int dgp_set_variable(dgp_handle* h, const char* tf_var_name, int what, const float* host_in, size_t n_elems) {
+  if (!h || !tf_var_name || !host_in) return DGP_ERR_INVALID;
+  if (!h->finalized) return fail(h, DGP_ERR_STATE, "dgp_set_variable before dgp_finalize_weights");
+  if (what != 0 && what != 2) return fail(h, DGP_ERR_INVALID, "dgp_set_variable: what must be 0 (value) or 2 (momentum)");
+  if (what == 2 && !h->train) return fail(h, DGP_ERR_STATE, "dgp_set_variable: momentum needs dgp_train_enable");
+  VarRef r;
+  if (!find_variable(h, tf_var_name, &r)) return fail(h, DGP_ERR_INVALID, "unknown variable %s", tf_var_name);
+  float* arena = what == 0 ? h->master : h->train->accum;
+  const ConvLayer& L = *r.L;
+  const int nj = h->cfg.num_joints;
+  CU_OK(h, cudaSetDevice(h->device));
+  CU_OK(h, cudaDeviceSynchronize());
+  size_t want = 0;
+  if (r.kind == 2 || r.kind == 3) {
+    want = (size_t)L.Cout;
+    if (n_elems != want) return fail(h, DGP_ERR_INVALID, "%s: expected %zu elements", tf_var_name, want);
+    const size_t off = h->n_w + (r.kind == 3 ? h->n_ch : 0) + (size_t)L.ch_off;
+    CU_OK(h, cudaMemcpy(arena + off, host_in, want * 4, cudaMemcpyHostToDevice));
+  } else if (r.kind == 5) {
+    want = (size_t)(r.head_part ? 2 * nj : nj);
+    if (n_elems != want) return fail(h, DGP_ERR_INVALID, "%s: expected %zu elements", tf_var_name, want);
+    const size_t off = h->n_w + 2 * h->n_ch + (r.head_part ? nj : 0);
+    CU_OK(h, cudaMemcpy(arena + off, host_in, want * 4, cudaMemcpyHostToDevice));
+  } else {
+    std::vector<float> m((size_t)L.Npad * L.K);
+    CU_OK(h, cudaMemcpy(m.data(), arena + L.w_off, m.size() * 4, cudaMemcpyDeviceToHost));
+    if (r.kind == 0) {
+      const int T = L.R * L.S;
+      want = (size_t)T * L.Cin * L.Cout;
+      if (n_elems != want) return fail(h, DGP_ERR_INVALID, "%s: expected %zu elements", tf_var_name, want);
+      for (int t = 0; t < T; ++t)
+        for (int c = 0; c < L.Cin; ++c)
+          for (int o = 0; o < L.Cout; ++o) m[(size_t)o * L.K + (size_t)t * L.Cin + c] = host_in[((size_t)t * L.Cin + c) * L.Cout + o];
+    } else if (r.kind == 1) {
+      want = (size_t)7 * 7 * 3 * 64;
+      if (n_elems != want) return fail(h, DGP_ERR_INVALID, "%s: expected %zu elements", tf_var_name, want);
+      for (int kh = 0; kh < 7; ++kh)
+        for (int kw = 0; kw < 7; ++kw)
+          for (int c = 0; c < 3; ++c)
+            for (int o = 0; o < 64; ++o)
+              m[(size_t)o * 256 + (kh >> 1) * 64 + (kw >> 1) * 16 + ((kh & 1) * 2 + (kw & 1)) * 3 + c] =
+                  host_in[(((size_t)kh * 7 + kw) * 3 + c) * 64 + o];
+    } else {
+      const int ctot = h->ctot, cn = r.head_part ? 2 * nj : nj, c0 = r.head_part ? nj : 0;
+      want = (size_t)9 * cn * 2048;
+      if (n_elems != want) return fail(h, DGP_ERR_INVALID, "%s: expected %zu elements", tf_var_name, want);
+      for (int t = 0; t < 9; ++t)
+        for (int cc = 0; cc < cn; ++cc)
+          memcpy(&m[(size_t)(t * ctot + c0 + cc) * 2048], &host_in[((size_t)t * cn + cc) * 2048], 2048 * sizeof(float));
+    }
+    CU_OK(h, cudaMemcpy(arena + L.w_off, m.data(), m.size() * 4, cudaMemcpyHostToDevice));
+  }
+  if (what == 0) {  // the tensor-core operands are derived from the master copy
+    int rc = refresh_operands(h, nullptr);
+    if (rc) return rc;
+    if (h->train) h->train->wd_fresh = false;
+    CU_OK(h, cudaDeviceSynchronize());
+  }
+  return DGP_OK;
+}
+
 }  // extern "C"

@@ -327,6 +327,42 @@ class Engine:
                                                 _stream(dev)))
         return lmap, lmask
 
+    def set_variable(self, name, array, what="value"):
+        """Overwrite a trainable variable ("value") or its Momentum accumulator ("momentum") from a TF-layout array."""
+        code = {"value": 0, "momentum": 2}[what]
+        if code == 2:
+            self.train_enable()
+        a = np.ascontiguousarray(array, dtype=np.float32)
+        self._check(self.lib.dgp_set_variable(self.h, name.encode(), code, a.ctypes.data_as(C.c_void_p), a.size))
+
+    def variable_names(self):
+        """TF names of every trainable variable of the graph (slim resnet_v1_50 + the deconv heads)."""
+        from .synthetic import resnet50_conv_specs
+        names = []
+        for scope, *_ in resnet50_conv_specs():
+            names += [scope + "/weights", scope + "/BatchNorm/gamma", scope + "/BatchNorm/beta"]
+        for head in ["part_pred"] + (["locref_pred"] if self.location_refinement else []):
+            names += ["pose/%s/block4/weights" % head, "pose/%s/block4/biases" % head]
+        return names
+
+    def save_checkpoint(self, path):
+        """All trainable variables and their Momentum accumulators under TF names -> .npz (Saver.save, fitdgp.py:830-839)."""
+        out = {}
+        for n in self.variable_names():
+            out[n] = self.get_variable(n)
+            if getattr(self, "_train", False):
+                out["momentum::" + n] = self.get_variable(n, "momentum")
+        np.savez(path, **out)
+
+    def load_checkpoint(self, path):
+        """Resume from save_checkpoint (the frozen moving statistics stay as loaded by load_weights)."""
+        with np.load(path) as z:
+            for k in z.files:
+                if k.startswith("momentum::"):
+                    self.set_variable(k[len("momentum::"):], z[k], "momentum")
+                else:
+                    self.set_variable(k, z[k], "value")
+
     # ------------------------------------------------------------------ test hooks
     def keep_activations(self, enable=True):
         self._check(self.lib.dgp_debug_keep_activations(self.h, int(enable)))

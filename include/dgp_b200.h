@@ -212,6 +212,11 @@ int dgp_train_outputs(dgp_handle* h, int nt, int H, int W, float** logits_dev, f
 int dgp_get_variable(dgp_handle* h, const char* tf_var_name, int what, float* host_out, size_t max_elems, int64_t* shape4,
                      int* ndim);
 
+/* Replaces TF.train.Saver.restore on a live session (resuming fit_dgp from a snapshot, fitdgp.py:689-720): overwrite a
+ * trainable variable (what = 0; the 16-bit operands and BN scale/shift are refreshed) or its Momentum accumulator
+ * (what = 2) from a host array in TF layout.  Together with dgp_get_variable this is checkpoint / resume. */
+int dgp_set_variable(dgp_handle* h, const char* tf_var_name, int what, const float* host_in, size_t n_elems);
+
 /* ---- test / profiling hooks (not part of the reference surface) ---- */
 /* Keep every end_point (slim names, e.g. "resnet_v1_50/block1/unit_1/bottleneck_v1") of the next dgp_forward. */
 int dgp_debug_keep_activations(dgp_handle* h, int enable);

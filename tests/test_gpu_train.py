@@ -364,3 +364,41 @@ def test_loss_scale_is_transparent():
         eng.close()
     assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][3], res[1][3])
     assert res[0][2] == res[1][2]
+
+
+def test_checkpoint_resume_is_exact(tmp_path):
+    """Train 2 steps, save (values + Momentum accumulators under TF names), restore into a FRESH handle, train 1 more step on
+    both: bitwise identical weights (Saver.save / Saver.restore replacement, fitdgp.py:689-720, 830-839)."""
+    from deepgraphpose_b200 import fitdgp
+    from deepgraphpose_b200.engine import Engine
+    W, frames, batch, edges, S0, cfg, ws, ws_max = _setup(seed=17)
+    fr = torch.from_numpy(frames).cuda()
+
+    def step(e):
+        fitdgp.train_forward_backward(e, fr, batch, cfg, edges, ws, ws_max, 200, 20)
+        e.optimizer_step(0.005, 0.9, 10.0, 1.0)
+
+    a = Engine(NJ)
+    a.load_weights(W)
+    step(a)
+    step(a)
+    path = str(tmp_path / "snapshot.npz")
+    a.save_checkpoint(path)
+    b = Engine(NJ)
+    b.load_weights(W)          # moving statistics (not trainable) + graph; everything trainable is overwritten next
+    b.train_enable()
+    b.load_checkpoint(path)
+    names = a.variable_names()
+    assert len(names) == 53 * 3 + 4
+    for n in names[:6] + names[-4:]:
+        assert np.array_equal(a.get_variable(n), b.get_variable(n)), n
+        assert np.array_equal(a.get_variable(n, "momentum"), b.get_variable(n, "momentum")), n
+    step(a)
+    step(b)
+    for n in names:
+        assert np.array_equal(a.get_variable(n), b.get_variable(n)), n
+    la, _ = a.forward(fr)
+    lb, _ = b.forward(fr)
+    assert torch.equal(la, lb)
+    a.close()
+    b.close()
