@@ -402,3 +402,35 @@ def test_checkpoint_resume_is_exact(tmp_path):
     assert torch.equal(la, lb)
     a.close()
     b.close()
+
+
+def test_training_step_with_temporal_clique():
+    """wt > 0 through the whole training step: the temporal clique (optical-flow weighted, gradient through delta and through
+    crop_and_resize's boxes) reaches every variable; gradients vs oracle autograd with the bf16 thresholds."""
+    from deepgraphpose_b200 import fitdgp
+    from deepgraphpose_b200.engine import Engine
+    W, frames, batch, edges, S0, cfg0, ws, ws_max = _setup(seed=3)
+    cfg = oracle_loss.default_dgp_cfg(gm2=1, gm3=3, wt=60.0, wt_max=0.0)
+    rng = np.random.default_rng(8)
+    yy, xx = np.meshgrid(np.arange(HIN), np.arange(WIN), indexing="ij")
+    batch = dict(batch)
+    batch["vector_field_tf"] = np.stack([0.9 + 0.8 * np.sin(yy / (7.0 + t)) * np.cos(xx / (9.0 + 2 * t)) + 0.3 * rng.uniform(size=yy.shape)
+                                         for t in range(NT - 1)])
+    batch["wt_batch_pl"] = np.ones(NT - 1) * 60.0
+    batch["wt_batch_mask_pl"] = np.ones(NT - 1)
+    Wt = {k: torch.from_numpy(v.copy()).requires_grad_(k.endswith(TRAINABLE)) for k, v in W.items()}
+    heads = pose_net.get_net(torch.from_numpy(frames.astype(np.float32)), Wt, True)
+    loss, total, _ = oracle_loss.dgp_loss_from_heads(heads["part_pred"], heads["locref"], batch, cfg, S0, ws, ws_max, 200, 20)
+    total.backward()
+    assert float(loss["wt_loss"].detach()) > 0.02 * float(total.detach())   # the clique matters in this batch
+    eng = Engine(NJ)
+    eng.load_weights(W)
+    got = fitdgp.train_forward_backward(eng, torch.from_numpy(frames).cuda(), batch, cfg, edges, ws, ws_max, 200, 20)
+    assert abs(float(got["wt_loss"]) - float(loss["wt_loss"].detach())) <= 0.1 * float(loss["wt_loss"].detach()), (got, loss)
+    assert abs(float(got["total_loss"]) - float(total.detach())) <= 3e-2 * float(total.detach())
+    for name in ("pose/part_pred/block4/weights", "resnet_v1_50/block4/unit_3/bottleneck_v1/conv3/weights",
+                 "resnet_v1_50/block3/unit_1/bottleneck_v1/conv2/weights", "resnet_v1_50/conv1/weights"):
+        g, g_ref = eng.get_variable(name, "grad"), Wt[name].grad.numpy()
+        cos = float((g * g_ref).sum() / (np.linalg.norm(g) * np.linalg.norm(g_ref) + 1e-30))
+        assert cos > 0.97, (name, cos)
+    eng.close()
