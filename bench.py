@@ -360,7 +360,7 @@ def main():
             "finite": bool(np.isfinite(res["x"]).all()),
         }
         if train_line is not None:
-            keep = ("metric", "value", "unit", "ms_per_step", "config", "gpu_launches", "loss_after", "finite", "error")
+            keep = ("metric", "value", "unit", "ms_per_step", "config", "gpu_launches", "loss_after", "finite", "e2e", "error")
             line["train_step"] = {k: train_line[k] for k in keep if k in train_line}
         if world == 1 and not args.no_cpu_baseline and args.config == "b":
             fps, cores, cdt = cpu_reference_fps(args.cpu_frames, warmup=1)

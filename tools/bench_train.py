@@ -110,6 +110,31 @@ def measure(rank, local_rank, world, steps, warmup, nt, height, width, profile=T
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    # ---- end to end as fit_dgp runs it: frames from (pinned) host memory every step, loss values read back every step
+    frames_pinned = torch.from_numpy(frames_host).pin_memory()
+    e2e_steps = max(3, min(args.steps, 10))
+
+    def e2e_step():
+        fr = frames_pinned.to(dev, non_blocking=True)
+        out = fitdgp.train_forward_backward(eng, fr, batch, cfg, edges, ws, ws_max, 1000, 100, sync=False)
+        scale = dp.allreduce_gradients(eng, overlap=os.environ.get("DGP_DP_OVERLAP", "1") != "0")
+        eng.optimizer_step(0.005, 0.9, 10.0, scale)
+        return out.cpu()      # [loss_eval, _] = sess.run([loss, train_op]) hands the losses to the host
+
+    e2e_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    import time
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_dt], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_dt = float(t.item())
     prof, ms_prof = None, 0.0
     if profile:
         eng.get_profile()
@@ -141,6 +166,9 @@ def measure(rank, local_rank, world, steps, warmup, nt, height, width, profile=T
                                    % (H, W, nt, len(vis), NJ), "parallelism": "dp%d, NCCL all-reduce of the 94 MB fp32 gradient buffer in %d buckets" % (world, dp.BUCKETS),
                        "feeds": "frames resident on the device; labels and marker index vectors fed from the host every step; locref maps built by dgp_locref_targets"},
             "clocks": clocks, "gpu_launches": launches, "loss_after": loss, "finite": bool(np.isfinite(loss)),
+            "e2e": {"value": world * nt * e2e_steps / e2e_dt, "unit": "frames/s", "ms_per_step": 1e3 * e2e_dt / e2e_steps,
+                    "h2d_bytes_per_step": int(frames_pinned.numel()) + int(sum(np.asarray(v).nbytes for v in batch.values() if not isinstance(v, (int, list)))),
+                    "d2h_bytes_per_step": 24, "timing": "wall clock, frames copied from pinned host memory and the 6 loss values read back every step, max over ranks"},
             "ms_per_step_by_family": fam, "ms_per_step_with_events": ms_prof / args.steps,
             "tflops": {"forward_gemm": tf(flops_fwd, prof["conv_gemm"][0]), "dgrad_gemm": tf(flops_fwd, prof["dgrad_gemm"][0]),
                        "wgrad_gemm": tf(flops_fwd, prof["wgrad_gemm"][0]),
