@@ -78,6 +78,7 @@ SIGNATURES = {
     "dgp_get_grad_buffer": (_i, [_vp, C.POINTER(_vp), C.POINTER(_sz)]),
     "dgp_train_early_bucket": (_i, [_vp, C.POINTER(_sz), C.POINTER(_sz)]),
     "dgp_train_wait_early_bucket": (_i, [_vp, _vp]),
+    "dgp_train_use_graphs": (_i, [_vp, _i]),
     "dgp_train_set_loss_scale": (_i, [_vp, _f]),
     "dgp_get_grad_norm": (_i, [_vp, C.POINTER(_f)]),
     "dgp_train_outputs": (_i, [_vp, _i, _i, _i, C.POINTER(_vp), C.POINTER(_vp)]),

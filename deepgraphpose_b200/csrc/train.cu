@@ -38,6 +38,15 @@ struct Backward {
   std::vector<BStep> steps;
   float *g_logits = nullptr, *g_locref = nullptr;
   int early_step = -1;  // number of steps after which the gradients of block4 + heads (the arena's tail) are final
+  // The ~280 launches of the network backward have fixed arguments per plan: after the first (eager) step they are
+  // replayed as one CUDA graph, which removes the launch gaps between the many small bandwidth-class kernels.
+  int runs = 0;
+  int launches = 0;
+  uint64_t graph_gen = 0;
+  cudaGraphExec_t graph_exec = nullptr;
+  ~Backward() {
+    if (graph_exec) cudaGraphExecDestroy(graph_exec);
+  }
 };
 
 struct TrainState {
@@ -50,6 +59,8 @@ struct TrainState {
   W16* head_wd = nullptr;
   int head_Kd = 0;
   bool wd_fresh = false;
+  uint64_t ws_gen = 1;           // bumped whenever a shared workspace is reallocated (captured graphs hold its address)
+  bool use_graphs = true;
   float loss_scale = 1.0f;       // head gradients are multiplied by this before the network backward (fp16 storage)
   DgradWJob* wd_jobs = nullptr;  // device table for the one-launch rebuild of every dgrad operand
   int n_wd_jobs = 0, wd_tiles = 0;
@@ -310,8 +321,11 @@ int build_backward(dgp_handle* h, Plan* pl) {
     wgrad_plan(&wp, h->num_sms);
     if ((rc = add_wgrad_params(h, bw.get(), wp, L.scale, h->conv1_mask, ts->grads + L.w_off, &ws_need))) return rc;
   }
+  const void *p0 = ts->wgrad_ws.p, *p1 = ts->bn_partial.p;
   if ((rc = ensure(h, &ts->wgrad_ws, ws_need))) return rc;
   if ((rc = ensure(h, &ts->bn_partial, bn_need))) return rc;
+  if (p0 != ts->wgrad_ws.p || p1 != ts->bn_partial.p) ++ts->ws_gen;
+  for (const BStep& st : bw->steps) bw->launches += st.launches;
   pl->bwd = bw;
   return DGP_OK;
 }
@@ -418,21 +432,61 @@ int dgp_train_forward_backward(dgp_handle* h, const uint8_t* frames_dev, int nt,
   b.pred_dev = pl->logits;
   b.locref_dev = pl->locref;
   if ((rc = dgp_run_loss_impl(h, cfg, &b, losses_dev, nullptr, bw->g_logits, bw->g_locref, visible_only, stream))) return rc;
-  int k = 0;
   if (ts->loss_scale != 1.0f) {
     const size_t n = (size_t)nt * 4 * pl->hf * pl->wf * h->cfg.num_joints;
     CU_OK(h, launch_scale_inplace(bw->g_logits, n, ts->loss_scale, s));
     if (bw->g_locref) CU_OK(h, launch_scale_inplace(bw->g_locref, 2 * n, ts->loss_scale, s));
     h->launches += bw->g_locref ? 2 : 1;
   }
-  for (const BStep& st : bw->steps) {
-    {
-      ProfScope prof(h, st.kind, s);
-      CU_OK(h, st.run(s));
+  const bool graphs = ts->use_graphs && !h->profiling && bw->runs > 0;
+  if (graphs && (!bw->graph_exec || bw->graph_gen != ts->ws_gen)) {
+    // (re)capture on the handle's private stream; the first step ran eagerly, so every lazy cudaFuncSetAttribute is done
+    if (bw->graph_exec) { cudaGraphExecDestroy(bw->graph_exec); bw->graph_exec = nullptr; }
+    cudaGraph_t graph = nullptr;
+    CU_OK(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    cudaError_t ce = cudaSuccess;
+    int k = 0;
+    for (const BStep& st : bw->steps) {
+      ce = st.run(h->stream);
+      if (ce != cudaSuccess) break;
+      if (++k == bw->early_step) {
+        ce = cudaEventRecordWithFlags(ts->ev_early, h->stream, cudaEventRecordExternal);
+        if (ce != cudaSuccess) break;
+      }
     }
-    h->launches += st.launches;
-    if (++k == bw->early_step) CU_OK(h, cudaEventRecord(ts->ev_early, s));
+    cudaError_t ee = cudaStreamEndCapture(h->stream, &graph);
+    if (ce == cudaSuccess) ce = ee;
+    if (ce == cudaSuccess) ce = cudaGraphInstantiate(&bw->graph_exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) {
+      bw->graph_exec = nullptr;
+      cudaGetLastError();
+      return fail(h, DGP_ERR_CUDA, "capturing the backward graph failed: %s", cudaGetErrorString(ce));
+    }
+    bw->graph_gen = ts->ws_gen;
   }
+  if (graphs) {
+    CU_OK(h, cudaGraphLaunch(bw->graph_exec, s));
+    h->launches += bw->launches;
+  } else {
+    int k = 0;
+    for (const BStep& st : bw->steps) {
+      {
+        ProfScope prof(h, st.kind, s);
+        CU_OK(h, st.run(s));
+      }
+      h->launches += st.launches;
+      if (++k == bw->early_step) CU_OK(h, cudaEventRecord(ts->ev_early, s));
+    }
+  }
+  bw->runs++;
+  return DGP_OK;
+}
+
+int dgp_train_use_graphs(dgp_handle* h, int enable) {
+  if (!h) return DGP_ERR_INVALID;
+  if (!h->train) return fail(h, DGP_ERR_STATE, "dgp_train_use_graphs before dgp_train_enable");
+  h->train->use_graphs = enable != 0;
   return DGP_OK;
 }
 

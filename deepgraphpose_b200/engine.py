@@ -268,6 +268,11 @@ class Engine:
         self._check(self.lib.dgp_get_grad_buffer(self.h, C.byref(p), C.byref(n)))
         return _device_view(p.value, (n.value // 4,), "<f4", self.device)
 
+    def use_graphs(self, enable=True):
+        """Replay the network backward as a CUDA graph from the second step on (default) or launch it eagerly."""
+        self.train_enable()
+        self._check(self.lib.dgp_train_use_graphs(self.h, int(enable)))
+
     def set_loss_scale(self, loss_scale):
         """Loss scaling for fp16-storage training (no effect on the update; see dgp_train_set_loss_scale)."""
         self.train_enable()

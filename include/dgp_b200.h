@@ -189,6 +189,9 @@ int dgp_train_forward_backward(dgp_handle* h, const uint8_t* frames_dev, int nt,
 /* g' = g * grad_scale; g' *= clip_norm / max(||g'||, clip_norm) (clip_norm <= 0: no clipping);
  * accum = momentum * accum + g'; var -= lr * accum; then refreshes the 16-bit operands and BN scale/shift. */
 int dgp_optimizer_step(dgp_handle* h, float lr, float momentum, float clip_norm, float grad_scale, void* stream);
+/* From its second run at a given input shape the network backward (about 280 launches with fixed arguments) is replayed as
+ * one CUDA graph; enable = 0 goes back to eager launches (always used while dgp_set_profiling is on). Default 1. */
+int dgp_train_use_graphs(dgp_handle* h, int enable);
 /* Loss scaling for fp16 storage (precision = 1): the head gradients are multiplied by loss_scale before the network
  * backward so that small activation gradients stay above fp16's subnormal range; dgp_optimizer_step divides it out again and
  * dgp_get_variable(what = 1) returns unscaled gradients (the raw buffer of dgp_get_grad_buffer holds loss_scale * gradient).

@@ -75,6 +75,7 @@ def measure(rank, local_rank, world, steps, warmup, nt, height, width, profile=T
     ws, ws_max = fitdgp.spatial_clique_params([labels], S0, 8.0, 1000.0, 1.2)
     eng = Engine(NJ, location_refinement=True, device=local_rank)
     eng.load_weights(synthetic.make_weights(NJ, seed=0))
+    eng.use_graphs(os.environ.get("DGP_TRAIN_GRAPHS", "1") != "0")
     frames_host = bench.make_frame_pool(nt, seed=1234 + rank) if (H, W) == (bench.H, bench.W) else \
         synthetic.make_video(nt, H, W, NJ, seed=1234 + rank)[0]
     frames = torch.from_numpy(frames_host).to(dev)
