@@ -46,7 +46,8 @@ def layer_list(H=747, W=832, nt=10, nj=4):
 def main(path):
     L = load(path)
     starts = [i for i, (n, _, _) in enumerate(L) if n == "prep_s2d_kernel"]
-    step = L[starts[-1]:]
+    # the capture may end in the middle of a step: take the last COMPLETE one (between two consecutive prep launches)
+    step = L[starts[-2]:starts[-1]] if len(starts) >= 2 else L[starts[-1]:]
     # the profiled pass is the last one; cut at its end (everything after the last build_head_dgrad_w_kernel belongs to teardown)
     fam = collections.OrderedDict()
     for n, us, by in step:
