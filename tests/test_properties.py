@@ -13,7 +13,7 @@ from oracle import dgp_ops, feeders, resnet_v1, tf_ops
 
 @settings(max_examples=200, deadline=None)
 @given(st.integers(32, 2000), st.integers(32, 2000))
-def test_output_dims_closed_form_equals_the_layer_chain(H, W):
+def test_output_dims_closed_form_equals_the_layer_chain(lib_built, H, W):
     """dgp_output_dims (C ABI, replaces Dataset._compute_pred_dims) == oracle closed form == the SAME-padding chain of
     conv1 (s2) -> pool (s2) -> block1 (s2) -> block2 (s2) -> deconv (x2)."""
     lib = _lib.load()
