@@ -400,13 +400,65 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int s2 = 0; s2 < 2; ++s2) {
+          const int u = 4 * half + 2 * s2;  // 16-byte unit inside the 128 B staging row (SWIZZLE_128B: u ^ (row & 7))
+          uint4* s0 = reinterpret_cast<uint4*>(my_row + ((u ^ (lane & 7)) << 4));
+          uint4* s1 = reinterpret_cast<uint4*>(my_row + (((u + 1) ^ (lane & 7)) << 4));
+#ifndef DGP_EPI_SCALAR
+          // Packed fp32x2 epilogue (FFMA2 / FADD2, ReLU as one bf16x2 max after rounding): same values bit for bit
+          // (fma / add are IEEE per lane; rounding is monotonic and 0 is exact), two thirds of the issue slots.
+          const float* scp = ss + c * 32 + s2 * 16;
+          const float* shp = ss + 128 + c * 32 + s2 * 16;
+          uint32_t rr[8];
+          if (has_res) {
+            const uint4 r0 = *s0;
+            const uint4 r1 = *s1;
+            rr[0] = r0.x; rr[1] = r0.y; rr[2] = r0.z; rr[3] = r0.w; rr[4] = r1.x; rr[5] = r1.y; rr[6] = r1.z; rr[7] = r1.w;
+          }
+          uint32_t o[8];
+#pragma unroll
+          for (int i = 0; i < 8; i += 2) {
+            const float4 sc = *reinterpret_cast<const float4*>(scp + 2 * i);
+            const float4 sh = *reinterpret_cast<const float4*>(shp + 2 * i);
+            ptx::f32x2 q0 = ptx::fma2(ptx::pk2(__uint_as_float(v[s2][2 * i]), __uint_as_float(v[s2][2 * i + 1])),
+                                      ptx::pk2(sc.x, sc.y), ptx::pk2(sh.x, sh.y));
+            ptx::f32x2 q1 = ptx::fma2(ptx::pk2(__uint_as_float(v[s2][2 * i + 2]), __uint_as_float(v[s2][2 * i + 3])),
+                                      ptx::pk2(sc.z, sc.w), ptx::pk2(sh.z, sh.w));
+            if (has_res) {
+              if (kFp16) {
+                const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&rr[i]));
+                const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&rr[i + 1]));
+                q0 = ptx::add2(q0, ptx::pk2(a.x, a.y));
+                q1 = ptx::add2(q1, ptx::pk2(b.x, b.y));
+              } else {
+                q0 = ptx::add2(q0, ptx::pk2(bf16lo(rr[i]), bf16hi(rr[i])));
+                q1 = ptx::add2(q1, ptx::pk2(bf16lo(rr[i + 1]), bf16hi(rr[i + 1])));
+              }
+            }
+            float a0, a1, b0, b1;
+            ptx::upk2(q0, a0, a1);
+            ptx::upk2(q1, b0, b1);
+            o[i] = kFp16 ? pack_fp16(a0, a1) : pack_bf16(a0, a1);
+            o[i + 1] = kFp16 ? pack_fp16(b0, b1) : pack_bf16(b0, b1);
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (kFp16) {
+                const __half2 z = __hmax2(*reinterpret_cast<const __half2*>(&o[i]), __float2half2_rn(0.0f));
+                o[i] = *reinterpret_cast<const uint32_t*>(&z);
+              } else {
+                const __nv_bfloat162 z = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&o[i]), __float2bfloat162_rn(0.0f));
+                o[i] = *reinterpret_cast<const uint32_t*>(&z);
+              }
+            }
+          }
+          *s0 = make_uint4(o[0], o[1], o[2], o[3]);
+          *s1 = make_uint4(o[4], o[5], o[6], o[7]);
+#else
           float f[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[s2][i]);
           apply_scale_shift(f, ss, ss + 128, c * 32 + s2 * 16);
-          const int u = 4 * half + 2 * s2;  // 16-byte unit inside the 128 B staging row (SWIZZLE_128B: u ^ (row & 7))
-          uint4* s0 = reinterpret_cast<uint4*>(my_row + ((u ^ (lane & 7)) << 4));
-          uint4* s1 = reinterpret_cast<uint4*>(my_row + (((u + 1) ^ (lane & 7)) << 4));
           if (has_res) {
             const uint4 r0 = *s0;
             const uint4 r1 = *s1;
@@ -422,6 +474,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           }
           *s0 = pack8(f, kFp16);
           *s1 = pack8(f + 8, kFp16);
+#endif
         }
         ptx::fence_proxy_async_smem();  // my generic-proxy smem writes -> visible to the TMA store (async proxy)
         ptx::named_bar_sync(pair_bar, 64);
