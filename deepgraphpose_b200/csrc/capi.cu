@@ -1170,6 +1170,24 @@ int dgp_get_profile(dgp_handle* h, double* ms_by_kind, int64_t* count_by_kind, i
   return DGP_OK;
 }
 
+uint32_t dgp_crc32c(const void* data, size_t n) {
+  // CRC-32C (Castagnoli, reflected polynomial 0x82F63B78), host only: the per-tensor checksums of TensorFlow checkpoint bundles
+  static uint32_t table[256];
+  static bool init = false;
+  if (!init) {
+    for (uint32_t i = 0; i < 256; ++i) {
+      uint32_t c = i;
+      for (int k = 0; k < 8; ++k) c = (c & 1) ? (c >> 1) ^ 0x82F63B78u : c >> 1;
+      table[i] = c;
+    }
+    init = true;
+  }
+  const unsigned char* p = static_cast<const unsigned char*>(data);
+  uint32_t crc = 0xFFFFFFFFu;
+  for (size_t i = 0; i < n; ++i) crc = table[(crc ^ p[i]) & 0xFF] ^ (crc >> 8);
+  return crc ^ 0xFFFFFFFFu;
+}
+
 int64_t dgp_launch_count(const dgp_handle* h) { return h ? h->launches : 0; }
 int dgp_num_sms(const dgp_handle* h) { return h ? h->num_sms : 0; }
 

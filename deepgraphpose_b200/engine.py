@@ -139,6 +139,9 @@ class Engine:
             self._check(self.lib.dgp_load_weights(self.h, name.encode(), a.ctypes.data_as(C.c_void_p), shape, a.ndim, 0))
         self._check(self.lib.dgp_finalize_weights(self.h))
         self.weights_loaded = True
+        # the frozen moving statistics are not trainable state of the handle; keep them for checkpoint export
+        self._frozen = {k: np.array(v, dtype=np.float32) for k, v in variables.items()
+                        if k.endswith("/moving_mean") or k.endswith("/moving_variance")}
 
     # ------------------------------------------------------------------ forward
     def forward(self, frames, want_locref=None):
@@ -358,6 +361,19 @@ class Engine:
             if getattr(self, "_train", False):
                 out["momentum::" + n] = self.get_variable(n, "momentum")
         np.savez(path, **out)
+
+    def save_tf_checkpoint(self, prefix, with_momentum=True, global_step=None):
+        """``saver.save(sess, prefix)`` (fitdgp.py:830-839) as a TensorFlow checkpoint bundle: every trainable variable, the
+        frozen moving statistics and (like the reference's full Saver) the MomentumOptimizer slots ``<var>/Momentum``."""
+        from . import tf_checkpoint
+        out = dict(getattr(self, "_frozen", {}))
+        for n in self.variable_names():
+            out[n] = self.get_variable(n)
+            if with_momentum and getattr(self, "_train", False):
+                out[n + "/Momentum"] = self.get_variable(n, "momentum")
+        if global_step is not None:
+            out["global_step"] = np.array(int(global_step), dtype=np.int64)
+        tf_checkpoint.write_checkpoint(prefix, out)
 
     def load_checkpoint(self, path):
         """Resume from save_checkpoint (the frozen moving statistics stay as loaded by load_weights)."""

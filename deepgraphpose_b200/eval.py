@@ -23,8 +23,8 @@ def _cfg_get(cfg, key, default=None):
 
 def load_variables(dgp_model_file, num_joints, location_refinement):
     """Weights for the graph.  Accepts a ``{tf_var_name: ndarray}`` dict, a ``.npz`` of such arrays, or
-    ``"synthetic"`` / ``"synthetic:<seed>"`` (random-init weights, BASELINE.json configs).  Reading TF checkpoint
-    bundles (``snapshot-*.index/.data``) is a "next" row of SURVEY.md 8(f) and raises here."""
+    ``"synthetic"`` / ``"synthetic:<seed>"`` (random-init weights, BASELINE.json configs), or the prefix of a TensorFlow
+    checkpoint bundle (``snapshot-step2-final--0`` -> ``.index`` + ``.data-0000N-of-0000M``, read by tf_checkpoint.py)."""
     if isinstance(dgp_model_file, dict):
         return dgp_model_file
     name = str(dgp_model_file)
@@ -34,8 +34,13 @@ def load_variables(dgp_model_file, num_joints, location_refinement):
     if name.endswith(".npz") and os.path.exists(name):
         with np.load(name) as z:
             return {k: z[k] for k in z.files}
-    raise NotImplementedError(
-        "TF checkpoint bundles are not readable yet (SURVEY.md 8f rank 3); pass a .npz / dict of TF-named variables")
+    prefix = name[:-6] if name.endswith(".index") else name
+    if os.path.exists(prefix + ".index"):
+        # a TensorFlow checkpoint bundle (DLC / DGP snapshot, resnet_v1_50.ckpt): restorer.restore without TensorFlow
+        from . import tf_checkpoint
+        return tf_checkpoint.model_variables(tf_checkpoint.read_checkpoint(prefix))
+    raise FileNotFoundError("no weights at %r: pass a {tf_var_name: ndarray} dict, an .npz of it, 'synthetic[:seed]', or the "
+                            "prefix of a TensorFlow checkpoint (<prefix>.index + <prefix>.data-*)" % (name,))
 
 
 def setup_dgp_eval_graph(dlc_cfg, dgp_model_file, loc_ref=False, gauss_len=1, gamma=1, device=None):

@@ -434,3 +434,32 @@ def test_training_step_with_temporal_clique():
         cos = float((g * g_ref).sum() / (np.linalg.norm(g) * np.linalg.norm(g_ref) + 1e-30))
         assert cos > 0.97, (name, cos)
     eng.close()
+
+
+def test_tf_checkpoint_export_and_restore(tmp_path):
+    """Train a step, export a TensorFlow checkpoint bundle (variables + moving statistics + Momentum slots), read it back
+    with the bundle reader and restore a fresh engine from the prefix: identical scoremaps."""
+    from deepgraphpose_b200 import fitdgp, tf_checkpoint
+    from deepgraphpose_b200.engine import Engine
+    from deepgraphpose_b200.eval import load_variables
+    W, frames, batch, edges, S0, cfg, ws, ws_max = _setup(seed=19)
+    fr = torch.from_numpy(frames).cuda()
+    a = Engine(NJ)
+    a.load_weights(W)
+    fitdgp.train_forward_backward(a, fr, batch, cfg, edges, ws, ws_max, 200, 20)
+    a.optimizer_step(0.005, 0.9, 10.0, 1.0)
+    prefix = str(tmp_path / "snapshot-step2-final--0")
+    a.save_tf_checkpoint(prefix, global_step=1)
+    full = tf_checkpoint.read_checkpoint(prefix, verify=True)
+    assert int(full["global_step"]) == 1 and "resnet_v1_50/conv1/weights/Momentum" in full
+    assert np.array_equal(full["resnet_v1_50/conv1/BatchNorm/moving_variance"], W["resnet_v1_50/conv1/BatchNorm/moving_variance"])
+    assert np.abs(full["pose/part_pred/block4/weights/Momentum"]).max() > 0
+    restored = load_variables(prefix, NJ, True)          # what restorer.restore would load: model variables only
+    assert sorted(restored) == sorted(W)
+    b = Engine(NJ)
+    b.load_weights(restored)
+    la, ra = a.forward(fr)
+    lb, rb = b.forward(fr)
+    assert torch.equal(la, lb) and torch.equal(ra, rb)
+    a.close()
+    b.close()
