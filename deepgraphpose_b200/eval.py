@@ -137,10 +137,33 @@ def estimate_pose(proj_cfg_file, dgp_model_file, video_file, output_dir, shuffle
     if save_pose and save_file is not None:
         os.makedirs(os.path.dirname(save_file) or ".", exist_ok=True)
         names = _cfg_get(dlc_cfg, "all_joints_names", ["joint%d" % i for i in range(labels["x"].shape[1])])
-        header = ",".join("%s_%s" % (n, c) for n in names for c in ("x", "y", "likelihood"))
-        table = np.stack([labels["x"], labels["y"], labels["likelihoods"]], axis=2).reshape(labels["x"].shape[0], -1)
-        np.savetxt(save_file + ".csv", table, delimiter=",", header=header, comments="")
+        scorer = os.path.basename(str(dgp_model_file)) if isinstance(dgp_model_file, (str, os.PathLike)) else "dgp_b200"
+        export_pose_like_dlc(labels, scorer, list(names), save_file)
     return labels
+
+
+def export_pose_like_dlc(labels, scorer, joints_names, save_file):
+    """eval.py:621-645: the DeepLabCut table layout -- columns (scorer, bodypart, x | y | likelihood), one row per frame --
+    written as ``save_file + '.csv'`` (three header rows + frame index column, what DLC / ``plot_dgp`` /
+    ``load_pose_from_dlc_to_dict`` read) and, when pytables is installed, as ``save_file + '.h5'`` (key df_with_missing)."""
+    import pandas as pd
+    x = np.asarray(labels["x"])
+    table = np.empty((x.shape[0], 3 * x.shape[1]), dtype=x.dtype)
+    table[:, 0::3], table[:, 1::3], table[:, 2::3] = x, labels["y"], labels["likelihoods"]
+    columns = pd.MultiIndex.from_product([[scorer], list(joints_names), ["x", "y", "likelihood"]],
+                                         names=["scorer", "bodyparts", "coords"])
+    frame = pd.DataFrame(table, columns=columns, index=np.arange(x.shape[0]))
+    try:
+        frame.to_hdf(save_file + ".h5", key="df_with_missing", format="table", mode="w")
+    except ImportError:   # pytables is optional here; the csv carries the same table
+        pass
+    frame.to_csv(save_file + ".csv")
+
+
+def load_pose_from_dlc_to_dict(filename):
+    """eval.py:648-653: read a DLC csv back into {'x', 'y', 'likelihoods'} (T, nj) arrays."""
+    body = np.genfromtxt(filename, delimiter=",", skip_header=3)[:, 1:]   # missing values (empty cells) become NaN
+    return {"x": body[:, 0::3], "y": body[:, 1::3], "likelihoods": body[:, 2::3]}
 
 
 def evaluate_dgp_frames(engine, frames, loc_ref=True, loc_ref_calc="dlc", batch=16, gamma=1.0, gauss_len=1.0):

@@ -72,5 +72,21 @@ for tag, (nt, H, W, nj, vis, nan_joints, seed) in {"m0": (10, 94, 104, 4, [0, 3,
                 tag + "_nan": np.array(nan_joints, dtype=np.int64).reshape(-1, 2), tag + "_labels": labels,
                 tag + "_visible_marker": np.asarray(v, dtype=np.int64), tag + "_hidden_marker": np.asarray(h, dtype=np.int64),
                 tag + "_vit": np.asarray(vit, dtype=np.int64)})
+# ---- DLC csv export: the reference's export_pose_like_dlc (models/eval.py:621-645); to_hdf needs pytables (absent) -> no-op
+import tempfile
+
+import pandas as pd
+
+ns2 = {"np": np}
+exec(cut(REF + "/deepgraphpose/models/eval.py", "export_pose_like_dlc"), ns2)
+_to_hdf = pd.DataFrame.to_hdf
+pd.DataFrame.to_hdf = lambda self, *a, **k: None
+lab = {"x": rng.uniform(0, 800, (4, 3)), "y": rng.uniform(0, 700, (4, 3)), "likelihoods": rng.uniform(0, 1, (4, 3))}
+lab["x"][1, 2] = np.nan
+with tempfile.TemporaryDirectory() as d:
+    ns2["export_pose_like_dlc"](lab, "snapshot-step2-final--0", ["hand", "finger", "elbow"], os.path.join(d, "vid_labeled"))
+    csv_text = open(os.path.join(d, "vid_labeled.csv")).read()
+pd.DataFrame.to_hdf = _to_hdf
+out.update({"csv_x": lab["x"], "csv_y": lab["y"], "csv_l": lab["likelihoods"], "csv_text": np.array(csv_text)})
 np.savez_compressed(os.path.join(OUT, "feeders.npz"), **out)
 print({k: v.shape for k, v in out.items()})

@@ -74,3 +74,18 @@ def test_synthetic_training_batch_matches_reference_gen_idx_chunk(tag):
     assert np.array_equal(feed["hidden_marker_pl"], g["hidden_marker"])
     assert np.array_equal(feed["visible_marker_in_targets_pl"], g["vit"])
     assert feed["visible_frame_within_batch"] == g["vis"].tolist() and feed["nt_batch_pl"] == nt
+
+
+def test_dlc_csv_export_matches_reference_bytes(tmp_path):
+    """export_pose_like_dlc (eval.py:621-645): the csv our shim writes == the bytes the reference's own function wrote for
+    the same labels (golden), and load_pose_from_dlc_to_dict reads it back."""
+    from deepgraphpose_b200.eval import export_pose_like_dlc, load_pose_from_dlc_to_dict
+    with np.load(G) as z:
+        lab = {"x": z["csv_x"], "y": z["csv_y"], "likelihoods": z["csv_l"]}
+        ref_text = str(z["csv_text"])
+    save = str(tmp_path / "vid_labeled")
+    export_pose_like_dlc(lab, "snapshot-step2-final--0", ["hand", "finger", "elbow"], save)
+    assert open(save + ".csv").read() == ref_text
+    back = load_pose_from_dlc_to_dict(save + ".csv")
+    for k in lab:
+        assert np.allclose(back[k], lab[k], equal_nan=True)
