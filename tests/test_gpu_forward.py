@@ -241,3 +241,29 @@ def test_evaluate_dgp_frames_branches():
         ref, _ = pose_net.argmax_pose_predict(sc, off)
         assert np.abs(dlc[t].reshape(nj, 3) - ref).max() < 2e-3
     eng.close()
+
+
+def test_estimate_pose_from_video_file_writes_dlc_csv(tmp_path):
+    """estimate_pose on a video FILE (OpenCV decode) with save_pose=True: DLC-format csv next to the expected name,
+    read back by load_pose_from_dlc_to_dict; a second call skips the already-labelled video like the reference."""
+    cv2 = pytest.importorskip("cv2")
+    from deepgraphpose_b200 import eval as dgp_eval
+    from deepgraphpose_b200 import synthetic
+    nj, T, H, W = 4, 6, 96, 128
+    frames, _ = synthetic.make_video(T, H, W, nj, seed=6)
+    path = str(tmp_path / "reach.avi")
+    vw = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"MJPG"), 10.0, (W, H))
+    if not vw.isOpened():
+        pytest.skip("no MJPG encoder in this OpenCV build")
+    for f in frames:
+        vw.write(f[:, :, ::-1])
+    vw.release()
+    cfg = {"num_joints": nj, "all_joints_names": ["a", "b", "c", "d"], "stride": 8.0}
+    labels = dgp_eval.estimate_pose(cfg, "synthetic:3", path, str(tmp_path), save_pose=True, batch=4)
+    assert labels["x"].shape == (T, nj) and np.isfinite(labels["x"]).all()
+    csv = str(tmp_path / "reach_labeled.csv")
+    back = dgp_eval.load_pose_from_dlc_to_dict(csv)
+    assert np.allclose(back["x"], labels["x"]) and np.allclose(back["likelihoods"], labels["likelihoods"])
+    head = open(csv).read().splitlines()[:3]
+    assert head[0].startswith("scorer,synthetic:3") and head[1].startswith("bodyparts,a,a,a,b") and head[2].startswith("coords,x,y,likelihood")
+    assert dgp_eval.estimate_pose(cfg, "synthetic:3", path, str(tmp_path), save_pose=True) == csv
