@@ -44,3 +44,15 @@ def make_2Dgrids(H, W, device="cuda"):
     r = torch.arange(H, dtype=torch.float32, device=device).view(H, 1).expand(H, W)
     c = torch.arange(W, dtype=torch.float32, device=device).view(1, W).expand(H, W)
     return torch.stack([r, c], dim=2).unsqueeze(2)
+
+
+def learn_wt(all_data_batch):
+    """fitdgp_util.py:454-467: optical-flow magnitude per consecutive frame pair, the ``vector_field_tf`` feed of the
+    temporal clique (nt-1, H, W): OpenCV Farneback flow (pyr_scale 0.5, 3 levels, window 15, 3 iterations, poly_n 5,
+    poly_sigma 1.2) on the BGR2GRAY-converted frames, |u| + |v|.  Host-side (cv2), exactly the reference's feeder; moving it
+    to the GPU is SURVEY.md 8(f) rank 4."""
+    import cv2
+    frames = np.asarray(all_data_batch)
+    gray = [cv2.cvtColor(f.astype(np.uint8), cv2.COLOR_BGR2GRAY) for f in frames]
+    fields = [np.abs(cv2.calcOpticalFlowFarneback(a, b, None, 0.5, 3, 15, 3, 5, 1.2, 0)).sum(2) for a, b in zip(gray[:-1], gray[1:])]
+    return np.array(fields)

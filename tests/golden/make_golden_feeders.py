@@ -88,5 +88,13 @@ with tempfile.TemporaryDirectory() as d:
     csv_text = open(os.path.join(d, "vid_labeled.csv")).read()
 pd.DataFrame.to_hdf = _to_hdf
 out.update({"csv_x": lab["x"], "csv_y": lab["y"], "csv_l": lab["likelihoods"], "csv_text": np.array(csv_text)})
+# ---- learn_wt (models/fitdgp_util.py:454-467): Farneback flow magnitude, the reference's own function on 3 synthetic frames
+import cv2
+
+ns3 = {"np": np, "cv2": cv2}
+exec(cut(REF + "/deepgraphpose/models/fitdgp_util.py", "learn_wt"), ns3)
+vid, _ = synthetic.make_video(3, 64, 96, 3, seed=77)
+vf = ns3["learn_wt"](vid.astype(np.float64))
+out.update({"flow_seed": np.array(77), "flow_field": vf.astype(np.float32)})
 np.savez_compressed(os.path.join(OUT, "feeders.npz"), **out)
 print({k: v.shape for k, v in out.items()})

@@ -89,3 +89,16 @@ def test_dlc_csv_export_matches_reference_bytes(tmp_path):
     back = load_pose_from_dlc_to_dict(save + ".csv")
     for k in lab:
         assert np.allclose(back[k], lab[k], equal_nan=True)
+
+
+def test_learn_wt_matches_reference_flow():
+    """learn_wt (fitdgp_util.py:454-467) == the reference's own function (same OpenCV build) on the same frames."""
+    pytest.importorskip("cv2")
+    from deepgraphpose_b200 import synthetic
+    from deepgraphpose_b200.fitdgp_util import learn_wt
+    with np.load(G) as z:
+        ref = z["flow_field"]
+    vid, _ = synthetic.make_video(3, 64, 96, 3, seed=77)
+    got = learn_wt(vid.astype(np.float64))
+    assert got.shape == ref.shape == (2, 64, 96) and float(ref.max()) > 0
+    assert np.allclose(got, ref, rtol=1e-5, atol=1e-5)
