@@ -37,7 +37,7 @@ def allreduce_gradients(engine, group=None, overlap=True):
         return 1.0
     buf = engine.grad_buffer()
     world = dist.get_world_size(group)
-    if not overlap:
+    if not overlap or not buf.is_cuda:
         # the training kernels ran on torch's current stream; NCCL orders its work after it
         return allreduce_flat_(buf, group)
     off, cnt = engine.early_bucket()
