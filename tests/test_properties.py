@@ -3,7 +3,7 @@ feeder restatement and the skeleton-clique host precompute.  CPU only."""
 import ctypes as C
 
 import numpy as np
-from hypothesis import given, settings
+from hypothesis import assume, given, settings
 from hypothesis import strategies as st
 
 from deepgraphpose_b200 import _lib, fitdgp, sharding, synthetic
@@ -59,7 +59,10 @@ def test_training_batch_marker_vectors(nt, nj, data):
 @settings(max_examples=40, deadline=None)
 @given(st.integers(6, 40), st.integers(6, 40), st.floats(-3.0, 45.0), st.floats(-3.0, 45.0))
 def test_locref_feeder_geometry(nx, ny, r, c):
-    """coord2map: exactly the cells whose centre lies within 17 px get mask 1 and the target (dx, dy) / locref_stdev."""
+    """coord2map: exactly the cells whose centre lies within 17 px get mask 1 and the target (dx, dy) / locref_stdev.
+    A joint whose image coordinates sum to exactly 0 is dropped by the reference's `nan_to_num(...).sum != 0` filter
+    (dataset.py:255) -- pinned separately in test_locref_feeder_drops_joint_whose_coordinates_sum_to_zero."""
+    assume((c * 8 + 4) + (r * 8 + 4) != 0)
     t, m = feeders.coord2map(np.array([[[r, c]]]), nx, ny, 1)
     jj, ii = np.meshgrid(np.arange(nx), np.arange(ny), indexing="ij")
     dx, dy = (c * 8 + 4) - (ii * 8.0 + 4), (r * 8 + 4) - (jj * 8.0 + 4)
@@ -67,6 +70,15 @@ def test_locref_feeder_geometry(nx, ny, r, c):
     assert np.array_equal(m[0, :, :, 0] == 1, inside) and np.array_equal(m[0, :, :, 1] == 1, inside)
     assert np.allclose(t[0, :, :, 0][inside], dx[inside] / 7.2801) and np.allclose(t[0, :, :, 1][inside], dy[inside] / 7.2801)
     assert (t[0][~inside] == 0).all() and np.abs(t).max() <= 17.0 / 7.2801 + 1e-12
+
+
+def test_locref_feeder_drops_joint_whose_coordinates_sum_to_zero():
+    """Reference quirk (dataset.py:255): joints are kept iff nan_to_num(x, y).sum() != 0, so a finite label with
+    x + y == 0 (e.g. scoremap (-0.5, -0.5) -> image (0, 0)) is treated like a missing one: no mask, no target."""
+    for r, c in ((-0.5, -0.5), (-1.0, 0.0), (0.25, -1.25)):
+        t, m = feeders.coord2map(np.array([[[r, c], [1.0, 1.0]]]), 8, 8, 2)
+        assert not m[0, :, :, :2].any() and not t[0, :, :, :2].any()
+        assert m[0, :, :, 2:].any()
 
 
 @settings(max_examples=40, deadline=None)
