@@ -36,7 +36,7 @@ class DgpLossCfg(C.Structure):
     _fields_ = [("gamma", C.c_float), ("gauss_len", C.c_float), ("lengthscale", C.c_float), ("wt", C.c_float),
                 ("wt_max", C.c_float), ("wn_visible", C.c_float), ("wn_hidden", C.c_float),
                 ("locref_loss_weight", C.c_float), ("n_frames_total", C.c_float), ("n_visible_frames_total", C.c_float),
-                ("gm2", C.c_int32), ("gm3", C.c_int32)]
+                ("gm2", C.c_int32), ("gm3", C.c_int32), ("locref_mse", C.c_int32)]
 
 
 class DgpLossBatch(C.Structure):
@@ -58,7 +58,11 @@ SIGNATURES = {
     "dgp_finalize_weights": (_i, [_vp]),
     "dgp_output_dims": (_i, [_i, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "dgp_forward": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "dgp_extract_features": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    "dgp_prediction_layers": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "dgp_deconv2d": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "dgp_softargmax": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "dgp_softmax_threshold": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp]),
     "dgp_softmax_map": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _f, _vp, _vp]),
     "dgp_loss_forward": (_i, [_vp, C.POINTER(DgpLossCfg), C.POINTER(DgpLossBatch), _vp, _vp, _vp]),
     "dgp_loss_backward": (_i, [_vp, C.POINTER(DgpLossCfg), C.POINTER(DgpLossBatch), _vp, _vp, _vp, _i, _vp]),

@@ -204,6 +204,86 @@ cudaError_t launch_deconv_col2im(const float* contrib, int N, int h, int w, int 
   return cudaGetLastError();
 }
 
+// argmax_2d_from_cm(th=...) (src/deepgraphpose/models/fitdgp_util.py:379-399): on the blurred, renormalised softmax map
+// zero every entry below th * max, renormalise by the new sum, and take E[(row, col)].  One CTA per (frame, joint), three
+// fixed-order passes over the joint's H*W entries (stride nj in the NHWC map); the map is rewritten in place.
+__global__ void __launch_bounds__(256) softmax_threshold_kernel(float* __restrict__ map, int H, int W, int nj, float th,
+                                                                float* __restrict__ mu) {
+  __shared__ float red[3][8];
+  __shared__ float bc[2];
+  const int b = blockIdx.x / nj, j = blockIdx.x - b * nj;
+  float* p = map + (size_t)b * H * W * nj + j;
+  const int n = H * W, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float mx = 0.0f;   // entries are >= 0 (or NaN, which the reference's reduce_max also skips only by accident)
+  for (int i = threadIdx.x; i < n; i += 256) mx = fmaxf(mx, p[(size_t)i * nj]);
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) red[0][warp] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = red[0][0];
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, red[0][w]);
+    bc[0] = m * th;
+  }
+  __syncthreads();
+  const float cut = bc[0];
+  float s0 = 0.0f, sr = 0.0f, sc = 0.0f;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    float v = p[(size_t)i * nj];
+    if (v < cut) v = 0.0f;
+    const int r = i / W, c = i - r * W;
+    s0 += v; sr += v * (float)r; sc += v * (float)c;
+  }
+  for (int o = 16; o; o >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    sr += __shfl_xor_sync(0xffffffffu, sr, o);
+    sc += __shfl_xor_sync(0xffffffffu, sc, o);
+  }
+  if (lane == 0) { red[0][warp] = s0; red[1][warp] = sr; red[2][warp] = sc; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.0f, r = 0.0f, c = 0.0f;
+    for (int w = 0; w < 8; ++w) { a += red[0][w]; r += red[1][w]; c += red[2][w]; }
+    bc[1] = a;
+    if (mu) { mu[((size_t)b * nj + j) * 2] = r / a; mu[((size_t)b * nj + j) * 2 + 1] = c / a; }
+  }
+  __syncthreads();
+  const float inv = 1.0f / bc[1];
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const float v = p[(size_t)i * nj];
+    p[(size_t)i * nj] = v < cut ? 0.0f : v * inv;
+  }
+}
+
+cudaError_t launch_softmax_threshold(float* map, int B, int H, int W, int nj, float th, float* mu, cudaStream_t stream) {
+  softmax_threshold_kernel<<<B * nj, 256, 0, stream>>>(map, H, W, nj, th, mu);
+  return cudaGetLastError();
+}
+
+__global__ void cvt16_to_f32_kernel(const uint16_t* __restrict__ in, float* __restrict__ out, size_t n, int fp16) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const uint16_t v = in[i];
+    out[i] = fp16 ? __half2float(*reinterpret_cast<const __half*>(&v)) : __uint_as_float((uint32_t)v << 16);
+  }
+}
+
+__global__ void f32_to_cvt16_kernel(const float* __restrict__ in, uint16_t* __restrict__ out, size_t n, int fp16) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float f = in[i];
+    if (fp16) f = fminf(fmaxf(f, -65504.0f), 65504.0f);
+    out[i] = to_half_bits(f, fp16);
+  }
+}
+
+cudaError_t launch_cvt16_to_f32(const void* in, float* out, size_t n, int fp16, cudaStream_t stream) {
+  cvt16_to_f32_kernel<<<grid_for(n, 256), 256, 0, stream>>>((const uint16_t*)in, out, n, fp16);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_f32_to_cvt16(const float* in, void* out, size_t n, int fp16, cudaStream_t stream) {
+  f32_to_cvt16_kernel<<<grid_for(n, 256), 256, 0, stream>>>(in, (uint16_t*)out, n, fp16);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_soft_pose(const float* st, const float* locref, int B, int H, int W, int nj, float stride,
                              float locref_stdev, int swap_offsets, float* pose, cudaStream_t stream) {
   soft_pose_kernel<<<B * nj, 256, 0, stream>>>(st, locref, H, W, nj, stride, locref_stdev, swap_offsets, pose);

@@ -8,6 +8,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -424,24 +425,47 @@ int make_wgrad_params(dgp_handle* h, const char* scope, int R, int S, int Cin, i
 
 int keep_activation(dgp_handle* h, const Step& st, cudaStream_t s);
 
+// Experiment knob (off by default): with DGP_CONV1_CHUNK_MB=<n> conv1 + pool1 run over chunks of frames that share ONE
+// conv1-output buffer of at most n MB, hoping that conv1's output (20 MB per 747x832 frame, the largest tensor of the net)
+// is consumed by the pool out of the L2 and overwritten by the next chunk before it is evicted.  Measured on B200
+// (profiles/r02_conv1_chunk_ab.md): no gain at 40 / 64 / 100 / 128 MB -- the L2 writes dirty lines back regardless, and the
+// extra launches cost 50 us -- so the default is one launch over the whole batch.  Outputs are bit-identical either way.
+int conv1_chunk_frames(int B, size_t frame_bytes) {
+  static long budget_mb = -1;
+  if (budget_mb < 0) {
+    const char* e = getenv("DGP_CONV1_CHUNK_MB");
+    budget_mb = e ? atol(e) : 0;
+  }
+  if (budget_mb == 0) return B;
+  long n = (long)((size_t)budget_mb * 1024 * 1024 / frame_bytes);
+  if (n < 1) n = 1;
+  return n < B ? (int)n : B;
+}
+
 int build_plan(dgp_handle* h, int B, int H, int W, bool train, Plan** out) {
-  auto key = std::make_tuple(B, H, W);
+  // debug runs (dgp_debug_keep_activations) need conv1's whole output: they get their own unchunked plan (key -B)
+  const bool unchunked = train || h->debug_keep;
+  auto key = std::make_tuple((!train && h->debug_keep) ? -B : B, H, W);
   auto& plans = train ? h->train_plans : h->plans;
   auto it = plans.find(key);
   if (it != plans.end()) {
+    it->second->last_use = ++h->plan_clock;
     *out = it->second.get();
     return DGP_OK;
   }
   // Plans own gigabytes of activation buffers: keep at most a handful per kind (fit_dgp's last batch of an epoch and
-  // videos of different sizes create new shapes), dropping an arbitrary older one once the device is idle.
+  // videos of different sizes create new shapes), dropping the least recently used one once the device is idle.
   const size_t max_plans = train ? 3 : 6;
   if (plans.size() >= max_plans) {
     CU_OK(h, cudaDeviceSynchronize());
     auto victim = plans.begin();
+    for (auto jt = plans.begin(); jt != plans.end(); ++jt)
+      if (jt->second->last_use < victim->second->last_use) victim = jt;
     for (auto& b : victim->second->bufs) cudaFree(b.p);
     plans.erase(victim);
   }
   std::unique_ptr<Plan> pl(new Plan());
+  pl->last_use = ++h->plan_clock;
   pl->train = train;
   pl->B = B; pl->H = H; pl->W = W;
   pl->H1 = ceil_div(H, 2); pl->W1 = ceil_div(W, 2);
@@ -472,36 +496,13 @@ int build_plan(dgp_handle* h, int B, int H, int W, bool train, Plan** out) {
       hh = ho; ww = wo; cin = u.depth;
     }
   }
-  const size_t big = (size_t)B * pl->H1 * pl->W1 * 64 * 2;
+  const size_t c1_frame_bytes = (size_t)pl->H1 * pl->W1 * 64 * 2;
+  const int chunk = unchunked ? B : conv1_chunk_frames(B, c1_frame_bytes);
+  const size_t big = (size_t)chunk * c1_frame_bytes;
   const size_t x_bytes = (size_t)B * max_x * 2 + 1024, t_bytes = (size_t)B * max_t * 2 + 1024,
                sc_bytes = (size_t)B * max_sc * 2 + 1024;
   void *c1 = nullptr, *xa = nullptr, *xb = nullptr, *t1 = nullptr, *t2 = nullptr, *sc = nullptr;
   if ((rc = alloc_buf(h, pl.get(), big, &c1))) return rc;
-  {
-    const ConvLayer& L = h->layers[h->conv1_layer];
-    Step st;
-    memset(&st.gp, 0, sizeof(st.gp));
-    ConvGemmParams& g = st.gp;
-    g.fp16 = h->fp16;
-    tmap_set_fp16(h->fp16);
-    g.M = B * pl->H1 * pl->W1; g.N = 64; g.block_n = 64; g.num_k_blocks = 4; g.a_mode = 1;
-    g.P = pl->H1; g.Q = pl->W1; g.conv_stride = 1; g.lower_h = 0; g.lower_w = 0; g.S = 1; g.dil = 1; g.cblocks = 1;
-    g.scale = L.scale; g.shift = L.shift; g.residual = nullptr; g.res_sub = 1; g.relu = 1;
-    g.out = c1; g.out_f32 = 0; g.ldc = 64;
-    g.num_m_blocks = ceil_div(g.M, kBlockM); g.num_n_blocks = 1;
-    g.tmem_cols = tmem_cols_for(64);
-    if ((rc = setup_epilogue(h, g, "conv1", B))) return rc;
-    const char* e = make_tmap_im2col(&g.tmap_a, pl->s2d, 64, (uint64_t)pl->W1, (uint64_t)pl->Hs, (uint64_t)B, 32,
-                                     (uint64_t)pl->Ws * 32, (uint64_t)pl->Hs * pl->Ws * 32, 0, 0, 0, -3, 1,
-                                     (uint64_t)B * pl->Hs * pl->Ws * 32, kBlockM * g.msub);
-    if (e) return fail(h, DGP_ERR_CUDA, "conv1: %s", e);
-    e = make_tmap_2d(&g.tmap_b, L.w, 64, 256, 512, 64);
-    if (e) return fail(h, DGP_ERR_CUDA, "conv1: %s", e);
-    st.kind = STEP_GEMM; st.end_point = "resnet_v1_50/conv1"; st.out_ptr = c1;
-    st.oN = B; st.oH = pl->H1; st.oW = pl->W1; st.oC = 64;
-    pl->steps.push_back(st);
-  }
-  // ---- pool1
   int Hc, Wc, pad_t, pad_l;
   same_pad(pl->H1, 3, 2, 1, &pad_t, &Hc);
   same_pad(pl->W1, 3, 2, 1, &pad_l, &Wc);
@@ -516,11 +517,42 @@ int build_plan(dgp_handle* h, int B, int H, int W, bool train, Plan** out) {
     if ((rc = alloc_buf(h, pl.get(), (size_t)B * Hc * Wc * 64 * 2 + 1024, &xa))) return rc;
   }
   pl->c1 = c1; pl->pool = xa; pl->Hp = Hc; pl->Wp = Wc; pl->pool_pad_t = pad_t; pl->pool_pad_l = pad_l;
-  {
-    Step st; st.kind = STEP_POOL;
-    st.pin = (const __nv_bfloat16*)c1; st.pH = pl->H1; st.pW = pl->W1; st.pC = 64; st.pad_t = pad_t; st.pad_l = pad_l;
-    st.end_point = "resnet_v1_50/pool1"; st.out_ptr = xa; st.oN = B; st.oH = Hc; st.oW = Wc; st.oC = 64;
-    pl->steps.push_back(st);
+  for (int f0 = 0; f0 < B; f0 += chunk) {
+    const int nf = (B - f0) < chunk ? (B - f0) : chunk;
+    {
+      const ConvLayer& L = h->layers[h->conv1_layer];
+      Step st;
+      memset(&st.gp, 0, sizeof(st.gp));
+      ConvGemmParams& g = st.gp;
+      g.fp16 = h->fp16;
+      tmap_set_fp16(h->fp16);
+      g.M = nf * pl->H1 * pl->W1; g.N = 64; g.block_n = 64; g.num_k_blocks = 4; g.a_mode = 1;
+      g.P = pl->H1; g.Q = pl->W1; g.conv_stride = 1; g.lower_h = 0; g.lower_w = 0; g.S = 1; g.dil = 1; g.cblocks = 1;
+      g.scale = L.scale; g.shift = L.shift; g.residual = nullptr; g.res_sub = 1; g.relu = 1;
+      g.out = c1; g.out_f32 = 0; g.ldc = 64;
+      g.num_m_blocks = ceil_div(g.M, kBlockM); g.num_n_blocks = 1;
+      g.tmem_cols = tmem_cols_for(64);
+      if ((rc = setup_epilogue(h, g, "conv1", nf))) return rc;
+      const __nv_bfloat16* s2d_chunk = pl->s2d + (size_t)f0 * pl->Hs * pl->Ws * 16;
+      const char* e = make_tmap_im2col(&g.tmap_a, s2d_chunk, 64, (uint64_t)pl->W1, (uint64_t)pl->Hs, (uint64_t)nf, 32,
+                                       (uint64_t)pl->Ws * 32, (uint64_t)pl->Hs * pl->Ws * 32, 0, 0, 0, -3, 1,
+                                       (uint64_t)nf * pl->Hs * pl->Ws * 32, kBlockM * g.msub);
+      if (e) return fail(h, DGP_ERR_CUDA, "conv1: %s", e);
+      e = make_tmap_2d(&g.tmap_b, L.w, 64, 256, 512, 64);
+      if (e) return fail(h, DGP_ERR_CUDA, "conv1: %s", e);
+      st.kind = STEP_GEMM; st.out_ptr = c1;
+      if (chunk == B) st.end_point = "resnet_v1_50/conv1";
+      st.oN = nf; st.oH = pl->H1; st.oW = pl->W1; st.oC = 64;
+      pl->steps.push_back(st);
+    }
+    {
+      Step st; st.kind = STEP_POOL;
+      st.pin = (const __nv_bfloat16*)c1; st.pN = nf; st.pH = pl->H1; st.pW = pl->W1; st.pC = 64; st.pad_t = pad_t; st.pad_l = pad_l;
+      st.out_ptr = (__nv_bfloat16*)xa + (size_t)f0 * Hc * Wc * 64;
+      if (chunk == B) st.end_point = "resnet_v1_50/pool1";
+      st.oN = nf; st.oH = Hc; st.oW = Wc; st.oC = 64;
+      pl->steps.push_back(st);
+    }
   }
   // ---- bottleneck units
   void* x = xa;
@@ -590,6 +622,7 @@ int build_plan(dgp_handle* h, int B, int H, int W, bool train, Plan** out) {
     int dh, dw;
     rc = make_gemm_step(h, L, x, B, Hc, Wc, 0, pl->contrib, true, nullptr, 1, 0, 0, 0, &st, &dh, &dw);
     if (rc) return rc;
+    pl->head_step = (int)pl->steps.size();
     pl->steps.push_back(st);
     Step c; c.kind = STEP_COL2IM;
     pl->steps.push_back(c);
@@ -608,10 +641,14 @@ int build_plan(dgp_handle* h, int B, int H, int W, bool train, Plan** out) {
   return DGP_OK;
 }
 
+// first_step / last_step select a slice of the plan: [0, head_step) is PoseNet.extract_features, [head_step, end) the
+// prediction layers (dgp_extract_features / dgp_prediction_layers); the default runs everything.
 int run_forward_plan(dgp_handle* h, Plan* pl, const uint8_t* frames_dev, float* logits_dev, float* locref_dev,
-                     cudaStream_t s) {
+                     cudaStream_t s, int first_step, int last_step) {
   int rc;
-  for (const Step& st : pl->steps) {
+  if (last_step < 0) last_step = (int)pl->steps.size();
+  for (int si = first_step; si < last_step; ++si) {
+    const Step& st = pl->steps[si];
     ProfScope prof(h, (int)st.kind, s);
     switch (st.kind) {
       case STEP_PREP:
@@ -621,7 +658,7 @@ int run_forward_plan(dgp_handle* h, Plan* pl, const uint8_t* frames_dev, float* 
         CU_OK(h, launch_conv_gemm(st.gp, h->num_sms, s));
         break;
       case STEP_POOL:
-        CU_OK(h, launch_maxpool3x3s2(st.pin, pl->B, st.pH, st.pW, st.pC, (__nv_bfloat16*)st.out_ptr, st.oH, st.oW, st.pad_t,
+        CU_OK(h, launch_maxpool3x3s2(st.pin, st.pN, st.pH, st.pW, st.pC, (__nv_bfloat16*)st.out_ptr, st.oH, st.oW, st.pad_t,
                                      st.pad_l, h->fp16, s));
         break;
       case STEP_COL2IM:
@@ -928,7 +965,7 @@ int dgp_run_loss_impl(dgp_handle* h, const dgp_loss_cfg* cfg, const dgp_loss_bat
   a.stride = h->cfg.stride; a.lengthscale = cfg->lengthscale; a.wt = cfg->wt; a.wt_max = cfg->wt_max;
   a.wn_visible = cfg->wn_visible; a.wn_hidden = cfg->wn_hidden; a.locref_weight = cfg->locref_loss_weight;
   a.n_vis_total = cfg->n_visible_frames_total; a.n_hid_total = cfg->n_frames_total - cfg->n_visible_frames_total;
-  a.gm2 = cfg->gm2; a.gm3 = cfg->gm3;
+  a.gm2 = cfg->gm2; a.gm3 = cfg->gm3; a.locref_mse = cfg->locref_mse ? 1 : 0;
   a.all_markers = all; a.partials = partials; a.meanflow = meanflow; a.out = losses_dev;
   a.boxgrad = grad_pred_dev ? boxgrad : nullptr;
   if (a.wt > 0.0f && a.flow != nullptr && !a.wt_batch) return fail(h, DGP_ERR_INVALID, "dgp_loss_forward: wt > 0 needs wt_batch");

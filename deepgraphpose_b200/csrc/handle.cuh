@@ -63,11 +63,12 @@ struct Step {
   int oN = 0, oH = 0, oW = 0, oC = 0;  // output shape (bf16 NHWC) for debug dumps
   // pool
   const __nv_bfloat16* pin = nullptr;
-  int pH = 0, pW = 0, pC = 0, pad_t = 0, pad_l = 0;
+  int pN = 0, pH = 0, pW = 0, pC = 0, pad_t = 0, pad_l = 0;
 };
 
 struct Plan {
   int B = 0, H = 0, W = 0;
+  uint64_t last_use = 0;               // plan-cache LRU clock
   int H1 = 0, W1 = 0, Hs = 0, Ws = 0;  // conv1 output / s2d dims
   int hf = 0, wf = 0;                  // feature map (stride 16)
   std::vector<DevBuf> bufs;
@@ -75,6 +76,7 @@ struct Plan {
   float* contrib = nullptr;
   int contrib_ld = 0;
   std::vector<Step> steps;
+  int head_step = 0;                   // index of the head GEMM in `steps` (everything before it is extract_features)
   // training plans keep every activation (no buffer rotation) and own the fp32 head outputs
   bool train = false;
   struct UnitBufs {
@@ -115,7 +117,8 @@ struct dgp_handle {
   float* conv1_mask = nullptr;   // [64][256] 1 = real 7x7x3 tap of the space-to-depth conv1 matrix
   size_t n_w = 0, n_ch = 0, n_bias = 0, n_params = 0;
   std::vector<float> host_master, host_gamma, host_beta, host_mean, host_var, host_bias, host_conv1_mask;
-  std::map<std::tuple<int, int, int>, std::unique_ptr<Plan>> plans, train_plans;
+  std::map<std::tuple<int, int, int>, std::unique_ptr<Plan>> plans, train_plans;  // inference key (-B,..) = unchunked debug plan
+  uint64_t plan_clock = 0;
   bool debug_keep = false;
   struct Kept {
     void* p;
@@ -175,7 +178,7 @@ int make_wgrad_params(dgp_handle* h, const char* scope, int R, int S, int Cin, i
 int alloc_buf(dgp_handle* h, Plan* pl, size_t bytes, void** out);
 int build_plan(dgp_handle* h, int B, int H, int W, bool train, Plan** out);
 int run_forward_plan(dgp_handle* h, Plan* pl, const uint8_t* frames_dev, float* logits_dev, float* locref_dev,
-                     cudaStream_t s);
+                     cudaStream_t s, int first_step = 0, int last_step = -1);
 int ensure(dgp_handle* h, DevBuf* b, size_t bytes);
 int refresh_operands(dgp_handle* h, cudaStream_t s);
 void train_destroy(dgp_handle* h);  // train.cu

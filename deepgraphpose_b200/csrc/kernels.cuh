@@ -36,6 +36,13 @@ cudaError_t launch_maxpool3x3s2(const __nv_bfloat16* in, int N, int H, int W, in
 cudaError_t launch_deconv_col2im(const float* contrib, int N, int h, int w, int ldn, int ctot, int nj,
                                  const float* bias, float* logits, float* locref, cudaStream_t stream);
 
+// argmax_2d_from_cm(th=...): threshold + renormalise the blurred softmax map in place and return E[(row, col)] (B,nj,2).
+cudaError_t launch_softmax_threshold(float* map, int B, int H, int W, int nj, float th, float* mu, cudaStream_t stream);
+
+// 16-bit storage (bf16 / fp16) <-> float32, elementwise (boundary entry points that hand activations to the caller).
+cudaError_t launch_cvt16_to_f32(const void* in, float* out, size_t n, int fp16, cudaStream_t stream);
+cudaError_t launch_f32_to_cvt16(const float* in, void* out, size_t n, int fp16, cudaStream_t stream);
+
 // Forward DGP loss on the head outputs (loss_kernels.cu).  All pointers are device pointers.
 struct LossArgs {
   const float* pred; const float* locref; const float* mu;  // (nt,H,W,nj), (nt,H,W,2nj) or null, (nt,nj,2)
@@ -47,6 +54,7 @@ struct LossArgs {
   const float* flow; int Hin, Win; const float* wt_batch;   // (nt-1,Hin,Win), (nt-1) = wt * mask
   float stride, lengthscale, wt, wt_max, wn_visible, wn_hidden, locref_weight, n_vis_total, n_hid_total;
   int gm2, gm3;
+  int locref_mse;       // 0 = Huber (k = 1) locref loss, 1 = mean squared error (dgp_cfg.locref_huber_loss False)
   float* all_markers;   // scratch (nt*nj,2): targets_all_marker
   float4* partials;     // scratch (nbv+nbh)
   float* meanflow;      // scratch ((nt-1)*nj)

@@ -73,7 +73,8 @@ __global__ void combine_markers_kernel(const float* __restrict__ mu, const float
 __global__ void __launch_bounds__(kLossThreads) marker_loss_kernel(
     const float* __restrict__ pred, const float* __restrict__ locref, const float* __restrict__ locref_map,
     const float* __restrict__ locref_mask, const float* __restrict__ all, const int* __restrict__ visible, int nbv,
-    const int* __restrict__ hidden, int H, int W, int nj, float inv2l2, int gm2, int gm3, float4* __restrict__ part) {
+    const int* __restrict__ hidden, int H, int W, int nj, float inv2l2, int gm2, int gm3, int locref_mse,
+    float4* __restrict__ part) {
   __shared__ float sh[kLossThreads / 32];
   const bool is_vis = (int)blockIdx.x < nbv;
   const int m = is_vis ? visible[blockIdx.x] : hidden[blockIdx.x - nbv];
@@ -128,7 +129,8 @@ __global__ void __launch_bounds__(kLossThreads) marker_loss_kernel(
       const float w = locref_mask[o];
       const float d = locref[o] - locref_map[o];
       const float a = fabsf(d);
-      const float l = a < 1.0f ? 0.5f * d * d : a - 0.5f;
+      // huber_loss (k = 1), or tf.losses.mean_squared_error when dgp_cfg.locref_huber_loss is False (fitdgp.py:1053)
+      const float l = locref_mse ? d * d : (a < 1.0f ? 0.5f * d * d : a - 0.5f);
       hub += l * w;
       mcount += (w != 0.0f) ? 1.0f : 0.0f;
     }
@@ -279,7 +281,8 @@ __global__ void __launch_bounds__(kLossThreads) marker_loss_bwd_kernel(
     const float* __restrict__ pred, const float* __restrict__ locref, const float* __restrict__ locref_map,
     const float* __restrict__ locref_mask, const float* __restrict__ all, const float* __restrict__ mu,
     const float* __restrict__ norm, const int* __restrict__ visible, int nbv, const int* __restrict__ hidden, int nbh,
-    const float4* __restrict__ part, int nt, int H, int W, int nj, float inv2l2, int gm2, int gm3, float gamma, int radius,
+    const float4* __restrict__ part, int nt, int H, int W, int nj, float inv2l2, int gm2, int gm3, int locref_mse, float gamma,
+    int radius,
     float sigma, const int* __restrict__ edges, int nl, const float* __restrict__ ws, const float* __restrict__ ws_max,
     float stride, float n_vis_total, float n_hid_total, float wn_visible, float wn_hidden, float locref_weight,
     int visible_only, const float* __restrict__ meanflow, const float4* __restrict__ boxgrad,
@@ -340,7 +343,7 @@ __global__ void __launch_bounds__(kLossThreads) marker_loss_bwd_kernel(
       for (int p = threadIdx.x; p < 2 * HW; p += blockDim.x) {
         const size_t o = base + (size_t)(p >> 1) * 2 * nj + (p & 1);
         const float d = locref[o] - locref_map[o];
-        g_locref[o] = kl * locref_mask[o] * (fabsf(d) < 1.0f ? d : (d > 0.0f ? 1.0f : -1.0f));
+        g_locref[o] = kl * locref_mask[o] * (locref_mse ? 2.0f * d : (fabsf(d) < 1.0f ? d : (d > 0.0f ? 1.0f : -1.0f)));
       }
     }
     return;
@@ -496,7 +499,7 @@ cudaError_t launch_dgp_loss(const LossArgs& a, cudaStream_t stream) {
     marker_loss_kernel<<<nb, kLossThreads, 0, stream>>>(a.pred, a.locref, a.locref_map, a.locref_mask, a.all_markers,
                                                         a.visible, a.nbv, a.hidden, a.H, a.W, a.nj,
                                                         1.0f / (2.0f * a.lengthscale * a.lengthscale), a.gm2, a.gm3,
-                                                        a.partials);
+                                                        a.locref_mse, a.partials);
   }
   const bool temporal = a.wt > 0.0f && a.flow != nullptr && a.nt > 1;
   if (temporal)
@@ -522,7 +525,7 @@ cudaError_t launch_dgp_loss_backward(const LossArgs& a, const float* norm, float
   if (nb > 0)
     marker_loss_bwd_kernel<<<nb, kLossThreads, 0, stream>>>(
         a.pred, a.locref, a.locref_map, a.locref_mask, a.all_markers, a.mu, norm, a.visible, a.nbv, a.hidden, a.nbh,
-        a.partials, a.nt, a.H, a.W, a.nj, 1.0f / (2.0f * a.lengthscale * a.lengthscale), a.gm2, a.gm3, gamma,
+        a.partials, a.nt, a.H, a.W, a.nj, 1.0f / (2.0f * a.lengthscale * a.lengthscale), a.gm2, a.gm3, a.locref_mse, gamma,
         (int)gauss_len, gauss_len, a.edges, a.nl, a.ws, a.ws_max, a.stride, a.n_vis_total, a.n_hid_total, a.wn_visible,
         a.wn_hidden, a.locref_weight, visible_only, temporal ? a.meanflow : nullptr, a.boxgrad, a.wt_batch, a.wt_max, a.Hin,
         a.Win, a.out, g_pred, g_locref);

@@ -87,7 +87,7 @@ def _stream(device):
 
 class Engine:
     def __init__(self, num_joints, location_refinement=True, device=None, stride=STRIDE, locref_stdev=LOCREF_STDEV,
-                 mean_pixel=MEAN_PIXEL, precision="bf16"):
+                 mean_pixel=MEAN_PIXEL, precision="fp16"):
         if not torch.cuda.is_available():
             raise DgpError(-2, "no CUDA device: deepgraphpose_b200 has no CPU fallback")
         self.lib = _lib.load()
@@ -157,6 +157,50 @@ class Engine:
         locref = torch.empty((B, ho, wo, 2 * self.nj), dtype=torch.float32, device=frames.device) if want_locref else None
         self._check(self.lib.dgp_forward(self.h, _ptr(frames), B, H, W, _ptr(logits), _ptr(locref), _stream(frames.device)))
         return logits, locref
+
+    def extract_features(self, frames):
+        """PoseNet.extract_features (pose_net.py:36-54): uint8 cuda frames (B,H,W,3) -> net (B,hf,wf,2048) float32."""
+        if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[-1] != 3 or not frames.is_cuda:
+            raise ValueError("frames must be a uint8 CUDA tensor of shape (B,H,W,3)")
+        frames = frames.contiguous()
+        B, H, W, _ = frames.shape
+        (hf, wf), _ = output_dims(H, W)
+        net = torch.empty((B, hf, wf, 2048), dtype=torch.float32, device=frames.device)
+        self._check(self.lib.dgp_extract_features(self.h, _ptr(frames), B, H, W, _ptr(net), _stream(frames.device)))
+        return net
+
+    def prediction_layers(self, net, want_locref=None):
+        """PoseNet.prediction_layers (pose_net.py:56-78) on a float32 cuda ``net`` (B,hf,wf,2048) -> (logits, locref | None)."""
+        if net.dtype != torch.float32 or net.dim() != 4 or net.shape[-1] != 2048 or not net.is_cuda:
+            raise ValueError("net must be a float32 CUDA tensor (B,hf,wf,2048)")
+        net = net.contiguous()
+        B, hf, wf, _ = net.shape
+        if want_locref is None:
+            want_locref = self.location_refinement
+        logits = torch.empty((B, 2 * hf, 2 * wf, self.nj), dtype=torch.float32, device=net.device)
+        locref = torch.empty((B, 2 * hf, 2 * wf, 2 * self.nj), dtype=torch.float32, device=net.device) if want_locref else None
+        self._check(self.lib.dgp_prediction_layers(self.h, _ptr(net), B, hf, wf, _ptr(logits), _ptr(locref), _stream(net.device)))
+        return logits, locref
+
+    def deconv2d(self, x, w, bias=None):
+        """slim.conv2d_transpose(x, Cout, [3,3], stride=2, 'SAME') + bias: x float32 cuda (N,H,W,Cin), Cin % 64 == 0;
+        w float32 ndarray in the TF layout [3,3,Cout,Cin]; returns float32 (N,2H,2W,Cout)."""
+        if x.dtype != torch.float32 or x.dim() != 4 or not x.is_cuda:
+            raise ValueError("x must be a float32 CUDA tensor (N,H,W,Cin)")
+        x = x.contiguous()
+        w = np.ascontiguousarray(w, dtype=np.float32)
+        if w.ndim != 4 or w.shape[0] != 3 or w.shape[1] != 3 or w.shape[3] != x.shape[3]:
+            raise ValueError("w must be [3,3,Cout,Cin] with Cin = %d" % x.shape[3])
+        N, H, W, Cin = x.shape
+        Cout = w.shape[2]
+        b = np.ascontiguousarray(bias, dtype=np.float32).reshape(-1) if bias is not None else None
+        if b is not None and b.size != Cout:
+            raise ValueError("bias must have %d entries" % Cout)
+        out = torch.empty((N, 2 * H, 2 * W, Cout), dtype=torch.float32, device=x.device)
+        self._check(self.lib.dgp_deconv2d(self.h, _ptr(x), N, H, W, Cin, w.ctypes.data_as(C.c_void_p),
+                                          b.ctypes.data_as(C.c_void_p) if b is not None else None, Cout, _ptr(out),
+                                          _stream(x.device)))
+        return out
 
     def softargmax(self, logits, locref=None, gamma=1.0, gauss_len=1.0, want=("mu", "peak", "lik", "dlc_peak", "dlc_pose")):
         """Fused argmax_2d_from_cm + estimate_pose read-out + DLC argmax pose. Returns a dict of cuda tensors."""
@@ -258,6 +302,10 @@ class Engine:
         if not getattr(self, "_train", False):
             self._check(self.lib.dgp_train_enable(self.h))
             self._train = True
+            if self.precision == "fp16":
+                # keeps the smallest activation gradients out of fp16's subnormal range; a power of two, divided out again by
+                # dgp_optimizer_step, so the update is unchanged wherever nothing underflowed
+                self._check(self.lib.dgp_train_set_loss_scale(self.h, 1024.0))
 
     def optimizer_step(self, lr=0.005, momentum=0.9, clip_norm=10.0, grad_scale=1.0):
         """clip_by_global_norm(clip_norm) + MomentumOptimizer(lr, momentum) (fitdgp.py:706-713) on the gradient buffer."""

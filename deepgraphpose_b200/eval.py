@@ -53,7 +53,7 @@ def setup_dgp_eval_graph(dlc_cfg, dgp_model_file, loc_ref=False, gauss_len=1, ga
                  stride=float(_cfg_get(dlc_cfg, "stride", 8.0)),
                  locref_stdev=float(_cfg_get(dlc_cfg, "locref_stdev", 7.2801)),
                  mean_pixel=tuple(_cfg_get(dlc_cfg, "mean_pixel", (123.68, 116.779, 103.939))),
-                 precision=_cfg_get(dlc_cfg, "precision", "bf16"))
+                 precision=_cfg_get(dlc_cfg, "precision", "fp16"))
     eng.load_weights(load_variables(dgp_model_file, nj, bool(loc_ref)))
     handles = {
         "inputs": Handle("Placeholder:0", "inputs"),

@@ -42,26 +42,25 @@ def skeleton_edges(S0):
 
 
 def spatial_clique_params(joint_locs, S0, stride, ws, ws_max):
-    """Host precompute of dgp_loss (fitdgp.py:874-892, float64 numpy): per-limb weight ws_l and upper bound ws_max_l,
-    including the reference's quirk that a missing limb contributes stride/2 to the mean length."""
-    S0 = np.asarray(S0, dtype=np.float64)
-    nj = S0.shape[1]
-    full = np.empty((0, nj, 2))
-    for j in joint_locs:
-        if len(j) > 0:
-            full = np.vstack((j, full))
-    f1 = np.copy(full).swapaxes(1, 2).reshape(-1, nj)
-    f1[np.isnan(f1)] = 1e10
-    limb = np.matmul(f1, S0.T)
-    limb[np.abs(limb) > 1e5] = 0
-    limb = np.reshape(limb, [full.shape[0], 2, -1])
-    limb = np.sqrt(np.sum(np.square(limb), 1))
-    limb = limb.T * stride + stride / 2
-    out_max = np.max(np.nan_to_num(limb), 1) * ws_max
-    with np.errstate(invalid="ignore", divide="ignore"):
-        mean = np.true_divide(limb.sum(1), (limb != 0).sum(1))
-    out_ws = 1 / (np.nan_to_num(mean) + 1e-20) * ws
-    return out_ws.astype(np.float32), out_max.astype(np.float32)
+    """Host precompute of dgp_loss (fitdgp.py:874-892): per limb l = (a, b) of the skeleton and over every labelled frame t,
+    ``L[t, l] = |label[t, a] - label[t, b]| * stride + stride / 2`` in image pixels, then the clique's upper bound
+    ``ws_max_l = ws_max * max_t L`` and weight ``ws_l = ws / mean_t L``.  A coordinate difference with an unlabelled (NaN) end
+    counts as 0, so a limb missing from a frame enters the mean with length stride/2 -- the reference's behaviour (its
+    ``!= 0`` mask never excludes anything because stride/2 was already added), kept for parity.
+    joint_locs: one (n_vis_i, nj, 2) array of scoremap (row, col) labels per dataset."""
+    edges = skeleton_edges(S0)
+    labelled = [np.asarray(j, dtype=np.float64) for j in joint_locs if len(j) > 0]
+    if not labelled:
+        raise ValueError("spatial_clique_params needs at least one labelled frame (the reference takes max over frames)")
+    lab = np.concatenate(labelled, axis=0)
+    head = np.array([e[0] for e in edges], dtype=np.int64)
+    tail = np.array([e[1] for e in edges], dtype=np.int64)
+    diff = lab[:, head, :] - lab[:, tail, :]                 # (T, nl, 2); NaN wherever an end point is unlabelled
+    diff = np.where(np.isnan(diff), 0.0, diff)
+    length_px = np.hypot(diff[..., 0], diff[..., 1]) * stride + 0.5 * stride
+    upper = ws_max * length_px.max(axis=0) if len(edges) else np.zeros(0)
+    weight = ws / (length_px.mean(axis=0) + 1e-20) if len(edges) else np.zeros(0)
+    return weight.astype(np.float32), upper.astype(np.float32)
 
 
 def _loss_args(dev, feed, cfg, edges, ws, ws_max, n_frames_total, n_visible_frames_total, nt, H, W, nj, pred=None,
@@ -107,7 +106,8 @@ def _loss_args(dev, feed, cfg, edges, ws, ws_max, n_frames_total, n_visible_fram
     c = _lib.DgpLossCfg(float(_get(cfg, "gamma", 1)), float(_get(cfg, "gauss_len", 1)), float(_get(cfg, "lengthscale", 1)),
                         wt, float(_get(cfg, "wt_max", 0)), float(_get(cfg, "wn_visible", 5)), float(_get(cfg, "wn_hidden", 3)),
                         float(_get(cfg, "locref_loss_weight", 0.05)), float(n_frames_total), float(n_visible_frames_total),
-                        int(_get(cfg, "gm2", 1)), int(_get(cfg, "gm3", 3)))
+                        int(_get(cfg, "gm2", 1)), int(_get(cfg, "gm3", 3)),
+                        0 if bool(_get(cfg, "locref_huber_loss", True)) else 1)
     return c, b, keep
 
 
@@ -158,20 +158,36 @@ def train_forward_backward(engine, frames, feed, cfg, edges, ws, ws_max, n_frame
     return dict(zip(LOSS_KEYS, [np.float32(v) for v in vals]))
 
 
-def dgp_loss(data_batcher, dgp_cfg, variables="synthetic", device=None):
+def dgp_loss(data_batcher, dgp_cfg, variables=None, device=None):
     """fitdgp.py:848-1144.  Returns (loss, total_loss, total_loss_visible, placeholders) of handles; evaluate them with
-    ``TrainSession(...)``.run(fetches, feed_dict) using the reference's placeholder keys."""
+    ``TrainSession(...)``.run(fetches, feed_dict) using the reference's placeholder keys.
+
+    The reference builds the graph here and restores ``init_weights`` into it afterwards (``restorer.restore``,
+    fitdgp.py:689-720).  The engine needs its variables at construction, so they come from ``variables`` (a
+    ``{tf_var_name: ndarray}`` dict, an ``.npz``, a TensorFlow checkpoint prefix, or ``'synthetic[:seed]'`` spelled out) or,
+    when that is None, from ``dgp_cfg.init_weights`` -- the snapshot the reference would restore.  There is no default: a
+    drop-in call never trains from random weights silently."""
     from .eval import load_variables
     S0 = np.asarray(data_batcher.S0)
     nj = int(data_batcher.nj)
     gm2, gm3 = int(_get(dgp_cfg, "gm2", 1)), int(_get(dgp_cfg, "gm3", 3))
     if gm2 not in (0, 1, 2) or gm3 not in (0, 3):
         raise Exception("Not implemented")  # fitdgp.py:1021, 1037
+    if gm3 == 3 and gm2 == 0:
+        # the reference dies here with NameError: pred_h_scaled1 is only defined for gm2 in {1, 2} (fitdgp.py:994-1033)
+        raise NameError("name 'pred_h_scaled1' is not defined (gm3=3 needs gm2 in {1, 2}, fitdgp.py:1027)")
+    if variables is None:
+        variables = _get(dgp_cfg, "init_weights", None)
+        if variables is None:
+            raise ValueError("dgp_loss needs the network variables: pass variables=... or set dgp_cfg.init_weights to the "
+                             "snapshot fit_dgp would restore (fitdgp.py:592, 720)")
     stride = float(_get(dgp_cfg, "stride", 8.0))
     ws, ws_max = spatial_clique_params([d.labels for d in data_batcher.datasets], S0, stride,
                                        float(_get(dgp_cfg, "ws", 1000.0)), float(_get(dgp_cfg, "ws_max", 1.2)))
     eng = Engine(nj, location_refinement=True, device=device, stride=stride,
-                 locref_stdev=float(_get(dgp_cfg, "locref_stdev", 7.2801)))
+                 locref_stdev=float(_get(dgp_cfg, "locref_stdev", 7.2801)),
+                 mean_pixel=tuple(_get(dgp_cfg, "mean_pixel", (123.68, 116.779, 103.939))),
+                 precision=_get(dgp_cfg, "precision", "fp16"))
     eng.load_weights(load_variables(variables, nj, True))
     graph = SimpleNamespace(engine=eng, cfg=dgp_cfg, edges=skeleton_edges(S0) if S0.shape[0] else [], ws=ws, ws_max=ws_max,
                             n_frames_total=float(data_batcher.n_frames_total),

@@ -28,7 +28,7 @@ def resnet50_conv_specs():
     return specs
 
 
-def make_weights(nj, seed=0, location_refinement=True, bn_random=True, head_gain=1.0):
+def make_weights(nj, seed=0, location_refinement=True, bn_random=True, head_gain=1.0, trained_like=False):
     """Random-init weights of the DLC ResNet-50 pose net, TF names -> float32 ndarrays.
 
     conv: He-normal (fan-in) HWIO; BN: gamma~U(.5,1.5), beta~N(0,.1), mean~N(0,.1), var~U(.5,1.5)
@@ -36,6 +36,12 @@ def make_weights(nj, seed=0, location_refinement=True, bn_random=True, head_gain
     The last BN of every bottleneck gets gamma scaled by 0.25 so the residual stream of the
     16 units stays O(1) (otherwise logits saturate the sigmoid and every parity test degenerates
     to ties).  Heads: xavier-uniform ``[3,3,cout,2048]`` scaled so logits have std ~3, zero bias.
+
+    ``trained_like=True`` gives the second weight set of the parity tests, shaped like a fine-tuned DLC snapshot rather than
+    a fresh initialisation: (i) an ImageNet-style BatchNorm spectrum -- in every bottleneck's last BN 15 % of the channels
+    carry a near-zero gamma (10^U(-5,-2)) and 2 % exactly 0 (resnet_v1_50.ckpt, the reference's starting point, README.md:52,
+    has many such channels; they are what a division by gamma cannot differentiate), (ii) peaked scoremaps -- part_pred
+    gain x2 with bias -4, so the sigmoid map is ~0 background with a few confident peaks instead of a flat 0.5 field.
     """
     rng = np.random.default_rng(seed)
     W = {}
@@ -54,6 +60,11 @@ def make_weights(nj, seed=0, location_refinement=True, bn_random=True, head_gain
             g, b, m, v = np.ones(cout), np.zeros(cout), np.zeros(cout), np.ones(cout)
         if scope.endswith("/conv3"):
             g = g * 0.25
+            if trained_like:
+                u = rng.uniform(size=cout)
+                tiny = 10.0 ** rng.uniform(-5.0, -2.0, cout)
+                g = np.where(u < 0.15, tiny, g)
+                g = np.where(u < 0.02, 0.0, g)
         W[scope + "/BatchNorm/gamma"] = g.astype(np.float32)
         W[scope + "/BatchNorm/beta"] = b.astype(np.float32)
         W[scope + "/BatchNorm/moving_mean"] = m.astype(np.float32)
@@ -65,8 +76,11 @@ def make_weights(nj, seed=0, location_refinement=True, bn_random=True, head_gain
         fan_in, fan_out = 9 * 2048, 9 * cout
         lim = np.sqrt(6.0 / (fan_in + fan_out))
         w = rng.uniform(-lim, lim, (3, 3, cout, 2048)) * head_gain
+        b = np.zeros(cout)
+        if trained_like and name == "part_pred":
+            w, b = w * 2.0, b - 4.0
         W["pose/%s/block4/weights" % name] = w.astype(np.float32)
-        W["pose/%s/block4/biases" % name] = np.zeros(cout, np.float32)
+        W["pose/%s/block4/biases" % name] = b.astype(np.float32)
     return W
 
 

@@ -46,8 +46,11 @@ typedef struct dgp_config {
   float locref_stdev;          /* default_config.py:29  (7.2801) */
   float mean_pixel[3];         /* default_config.py:23  (123.68, 116.779, 103.939), RGB */
   float bn_epsilon;            /* slim resnet_arg_scope batch_norm_epsilon (1e-5) */
-  int32_t precision;           /* storage type of activations/weights fed to the tensor cores: 0 = bf16 (default; range-safe),
-                                  1 = fp16 (same tcgen05 kind::f16 path and speed, 8x tighter parity, saturates at 65504) */
+  int32_t precision;           /* 16-bit storage type of the activations / weights fed to the tensor cores (fp32 accumulate,
+                                  fp32 BN epilogue, fp32 logits either way; same tcgen05 kind::f16 kernels, same speed):
+                                  1 = fp16 -- what the Python shims and bench.py select: 11-bit mantissa, meets BASELINE.json's
+                                      parity tolerances (sigmoid 1e-2, soft-argmax 0.5 px, loss 1e-3); values saturate at 65504;
+                                  0 = bf16 -- fp32's exponent range, 8-bit mantissa: sigmoid scoremaps differ by up to ~4e-2 */
 } dgp_config;
 
 /* Replaces the graph construction in setup_dgp_eval_graph (src/deepgraphpose/models/eval.py:147-214) and in
@@ -75,6 +78,24 @@ int dgp_output_dims(int H, int W, int* h_feat, int* w_feat, int* h_out, int* w_o
 int dgp_forward(dgp_handle* h, const uint8_t* frames_dev, int B, int H, int W, float* logits_dev, float* locref_dev,
                 void* stream);
 
+/* The two halves of dgp_forward under the reference's method names.
+ * dgp_extract_features replaces PoseNet.extract_features (PTF/nnet/pose_net.py:36-54): net_dev float32 (B,hf,wf,2048) =
+ * the block4 output `net` (hf, wf from dgp_output_dims).
+ * dgp_prediction_layers replaces PoseNet.prediction_layers / prediction_layer (pose_net.py:18-26, 56-78) with the
+ * handle's own pose/part_pred and pose/locref_pred variables: net_dev float32 (B,hf,wf,2048) -> logits_dev (B,2hf,2wf,nj)
+ * and locref_dev (B,2hf,2wf,2nj) or NULL.  Both round `net` to the handle's 16-bit storage type exactly as dgp_forward
+ * does, so extract_features followed by prediction_layers is bit-identical to dgp_forward.  Synchronous. */
+int dgp_extract_features(dgp_handle* h, const uint8_t* frames_dev, int B, int H, int W, float* net_dev, void* stream);
+int dgp_prediction_layers(dgp_handle* h, const float* net_dev, int B, int hf, int wf, float* logits_dev, float* locref_dev,
+                          void* stream);
+/* Replaces slim.conv2d_transpose(inputs, num_outputs, kernel_size=[3,3], stride=2, padding='SAME') + bias as built by
+ * prediction_layer (pose_net.py:18-26) and dgp_prediction_layer (src/deepgraphpose/models/fitdgp_util.py:18-74, whose
+ * init_flag hands the kernel in as constants): x_dev float32 (N,H,W,Cin), Cin a multiple of 64; w_host float32 in the TF
+ * layout [3,3,Cout,Cin]; bias_host [Cout] or NULL; out_dev float32 (N,2H,2W,Cout).  One tcgen05 GEMM over the input
+ * pixels + col2im (out[2i+k] += x[i] w[k], cropped to 2H x 2W).  Synchronous. */
+int dgp_deconv2d(dgp_handle* h, const float* x_dev, int N, int H, int W, int Cin, const float* w_host, const float* bias_host,
+                 int Cout, float* out_dev, void* stream);
+
 /* Replaces argmax_2d_from_cm (src/deepgraphpose/models/fitdgp_util.py:342-402) fused with the per-frame read-outs
  * that consume it: estimate_pose's windowed peak + likelihood (eval.py:331-343) and DLC's global-argmax pose
  * (PTF/nnet/predict.py:62-77, pose_net.py:92-163).  Any output pointer may be NULL.
@@ -91,6 +112,11 @@ int dgp_softargmax(dgp_handle* h, const float* logits_dev, const float* locref_d
  * Gaussian-blurred, renormalised spatial softmax, float32 (B,H,W,nj). */
 int dgp_softmax_map(dgp_handle* h, const float* logits_dev, int B, int H, int W, int nj, float gamma, float gauss_len,
                     float* map_dev, void* stream);
+
+/* The `th` branch of argmax_2d_from_cm (fitdgp_util.py:379-399; no reference caller passes it): on the map written by
+ * dgp_softmax_map, zero every entry below th * (the joint's maximum), renormalise, and return the soft-argmax of the
+ * thresholded map.  map_dev float32 (B,H,W,nj) is rewritten in place; mu_dev float32 (B,nj,2) (row, col) or NULL. */
+int dgp_softmax_threshold(dgp_handle* h, float* map_dev, int B, int H, int W, int nj, float th, float* mu_dev, void* stream);
 
 /* Replaces evaluate_dgp's 'dgp' locref read-out (src/deepgraphpose/models/eval.py:751-785): blurred spatial softmax of the
  * logits, then pose = (sum st * (row, col) * stride + stride/2 + sum st * locref * locref_stdev)[::-1] -> float32 (B,nj,3) =
@@ -130,6 +156,8 @@ typedef struct dgp_loss_cfg {
   float locref_loss_weight;                  /* 0.05 */
   float n_frames_total, n_visible_frames_total;
   int32_t gm2, gm3;                          /* {0,1,2}, {0,3} */
+  int32_t locref_mse;                        /* 0 = losses.huber_loss (dlc_cfg.locref_huber_loss True, the DLC default),
+                                                1 = tf.losses.mean_squared_error (fitdgp.py:1053) */
 } dgp_loss_cfg;
 
 /* The feeds of dgp_loss's placeholders (fitdgp.py:1130-1142), as device pointers.  Index vectors are int32. */

@@ -389,9 +389,22 @@ def _scoped(name):
     return "/".join(_SCOPE + [name])
 
 
-def slim_conv2d_transpose(inputs, num_outputs, kernel_size, stride=1, scope=None, **kw):
+class _ConstInit:
+    """tf.constant_initializer(value): the variable starts as `value` (reshaped to the variable's shape)."""
+    def __init__(self, value):
+        self.value = np.asarray(value, dtype=np.float32)
+
+
+def slim_conv2d_transpose(inputs, num_outputs, kernel_size, stride=1, scope=None, weights_initializer=None,
+                          biases_initializer=None, **kw):
     full = _scoped(scope)
     assert list(kernel_size) == [3, 3] and stride == 2
+    if isinstance(weights_initializer, _ConstInit):
+        # dgp_prediction_layer(init_flag=True) (fitdgp_util.py:57-66): the variables are created from constants, nothing is restored
+        w = torch.from_numpy(np.ascontiguousarray(weights_initializer.value))
+        b = torch.from_numpy(np.ascontiguousarray(biases_initializer.value.reshape(-1)))
+        assert tuple(w.shape[:3]) == (3, 3, num_outputs) and b.numel() == num_outputs
+        return _op(lambda a: _tfops.conv2d_transpose_same_s2(a, w, b), inputs, static_shape=(None, None, None, num_outputs))
     return _op(lambda a: _tfops.conv2d_transpose_same_s2(a, VARIABLES[full + "/weights"], VARIABLES[full + "/biases"]), inputs,
                static_shape=(None, None, None, num_outputs))
 
@@ -471,7 +484,7 @@ def _build_tf():
         norm=norm, argmax=argmax, unravel_index=unravel_index, variable_scope=variable_scope, Session=Session,
         AUTO_REUSE=True, reset_default_graph=lambda: None,
         global_variables_initializer=lambda: None, local_variables_initializer=lambda: None,
-        constant_initializer=lambda *a, **k: None,
+        constant_initializer=lambda value=0, *a, **k: _ConstInit(value),
     )
     nn = _ns("tensorflow.nn", softmax=softmax, separable_conv2d=separable_conv2d, relu=relu, sigmoid=sigmoid)
     math = _ns("tensorflow.math", multiply=multiply, maximum=maximum, minimum=minimum)

@@ -165,11 +165,55 @@ def golden_dgp_loss():
     np.savez_compressed(os.path.join(OUT, "dgp_loss.npz"), **out)
 
 
+def golden_boundary():
+    """The reference-named pieces of the boundary: PoseNet.extract_features, prediction_layer,
+    dgp_prediction_layer (graph variables and init_flag constants), the batched branch of PoseNet.inference
+    (pose_net.py:129-163) and argmax_2d_from_cm(th=...).  Synthetic weights seed 3, video seed 7, 64x96 frames."""
+    nj = 3
+    W = synthetic.make_weights(nj, seed=3)
+    tf1_shim.set_variables(W)
+    frames, _ = synthetic.make_video(2, 64, 96, nj, seed=7)
+    cfg = base_cfg(nj)
+    out = {"meta": np.array([nj, 3, 7, 64, 96])}
+    inputs = TF.placeholder(tf.float32, shape=[None, None, None, 3])
+    pn = ref_pose_net.PoseNet(cfg)
+    net, end_points = pn.extract_features(inputs)
+    with tf.variable_scope("pose", reuse=None):
+        part = ref_pose_net.prediction_layer(cfg, net, "part_pred", nj)
+        loc = ref_pose_net.prediction_layer(cfg, net, "locref_pred", 2 * nj)
+        part_dgp = ref_util.dgp_prediction_layer(None, None, cfg, net, name="part_pred", num_outputs=nj, init_flag=False,
+                                                 nc=None, train_flag=True, stride=cfg.deconvolutionstride)
+    rng = np.random.default_rng(5)
+    w_const = (rng.standard_normal((3, 3, nj, 2048)) * 0.01).astype(np.float32)
+    b_const = rng.standard_normal((1, nj)).astype(np.float32)
+    part_const = ref_util.dgp_prediction_layer(w_const, b_const, cfg, net, "confidencemap", nj, True, 2048, True)
+    sess = TF.Session()
+    net_v, part_v, loc_v, part_dgp_v, part_const_v = sess.run([net, part, loc, part_dgp, part_const], {inputs: frames[:1]})
+    out.update(net=net_v, part_pred=part_v, locref_pred=loc_v, part_pred_dgp=part_dgp_v, w_const=w_const, b_const=b_const,
+               part_pred_const=part_const_v)
+    # batched PoseNet.inference: batch_size = 2 takes the else-branch (pose_net.py:129-163)
+    cfg2 = base_cfg(nj, batch_size=2)
+    inputs2 = TF.placeholder(tf.float32, shape=[2, None, None, 3])
+    pose_b = ref_pose_net.PoseNet(cfg2).inference(inputs2)
+    out["pose_tf_batched"] = TF.Session().run(pose_b["pose"], {inputs2: frames})
+    # argmax_2d_from_cm with the threshold branch (fitdgp_util.py:379-389)
+    x = (rng.standard_normal((2, 12, 16, nj)) * 3.0).astype(np.float32)
+    ph = TF.placeholder(TF.float32, shape=[None, None, None, nj])
+    mu, sm = ref_util.argmax_2d_from_cm(ph, nj, 1.0, 1, th=0.3)
+    mu_v, sm_v = TF.Session().run([mu, sm], {ph: x})
+    out.update(th_x=x, th_mu=mu_v, th_sm=sm_v, th=np.float32(0.3))
+    np.savez_compressed(os.path.join(OUT, "boundary.npz"), **out)
+
+
 if __name__ == "__main__":
+    if "--boundary-only" in sys.argv:
+        golden_boundary()
+        sys.exit(0)
     golden_softargmax()
     golden_posenet()
     golden_estimate_pose()
     golden_dgp_loss()
+    golden_boundary()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -8,13 +8,18 @@ from oracle import dgp_ops, pose_net
 
 pytestmark = pytest.mark.gpu
 
-# bf16 tensor-core inputs (north_star) carry 8 mantissa bits through 53 conv layers.  On the random-init net whose
-# logits have std ~4 the measured worst cases are: activations 1.3% of the layer max, logits 1.1%, sigmoid 3.1e-2,
-# soft-argmax 0.07 scoremap px.  See DESIGN.md "Numerics" for the decomposition (bf16 weights alone give 1.9e-2).
-ACT_REL_TOL = 2.5e-2
-LOGIT_REL_TOL = 2.5e-2
-SIGMOID_TOL = 5e-2
-MU_TOL_SCOREMAP_PX = 0.15
+# BASELINE.json north_star tolerances, asserted as such for the storage mode the shims and bench.py run (fp16 operands on
+# tcgen05 kind::f16, fp32 accumulate): sigmoid scoremaps <= 1e-2 max-abs, soft-argmax <= 0.5 image px (0.0625 scoremap px).
+# Measured worst cases over the BASELINE shapes (tools/diag_precision.py, profiles/r02_precision.md): logits 1.8e-3 of
+# their max, sigmoid 5.4e-3 (flat random-init set) / 9.2e-3 (trained-like set), soft-argmax 0.27 image px.
+ACT_REL_TOL = 4e-3
+LOGIT_REL_TOL = 4e-3
+SIGMOID_TOL = 1e-2
+MU_TOL_SCOREMAP_PX = 0.0625
+# The bf16 storage mode (precision="bf16", not what bench.py reports) carries 8 mantissa bits through 53 conv layers and
+# cannot meet those tolerances on this net (bf16 weights alone give 1.9e-2, DESIGN.md "Numerics"); its own, wider bounds:
+BF16_ACT_REL_TOL = 2.5e-2
+BF16_SIGMOID_TOL = 5e-2
 
 
 @pytest.fixture(scope="module")
@@ -57,12 +62,12 @@ def test_forward_layerwise(setup, shape):
     assert (out["mu"].cpu() - mu_ref).abs().max().item() < MU_TOL_SCOREMAP_PX
 
 
-def test_forward_fp16_storage_meets_baseline_tolerances(setup):
-    """precision='fp16' (same tcgen05 kind::f16 kernels, fp16 instead of bf16 storage): BASELINE.json's tolerances hold --
-    sigmoid scoremaps <= 1e-2 max-abs, soft-argmax <= 0.5 image px (0.0625 scoremap px)."""
+def test_forward_bf16_storage_mode(setup):
+    """precision='bf16' (same kernels, bf16 instead of fp16 storage) stays within ITS documented bounds: an optional mode for
+    weights whose activations would overflow fp16; it does not meet BASELINE's 1e-2 and is not the benchmarked mode."""
     from deepgraphpose_b200.engine import Engine
     _, W, Wt, nj = setup
-    eng = Engine(nj, location_refinement=True, precision="fp16")
+    eng = Engine(nj, location_refinement=True, precision="bf16")
     eng.load_weights(W)
     for (T, H, Wd) in [(2, 235, 301), (1, 470, 640)]:
         frames, _ = synthetic.make_video(T, H, Wd, nj, seed=H)
@@ -71,24 +76,29 @@ def test_forward_fp16_storage_meets_baseline_tolerances(setup):
             pred = pose_net.prediction_layer(net, Wt, "part_pred")
             loc = pose_net.prediction_layer(net, Wt, "locref_pred")
         logits, locref = eng.forward(torch.from_numpy(frames).cuda())
-        assert (logits.cpu() - pred).abs().max().item() / pred.abs().max().item() < 4e-3
-        assert (locref.cpu() - loc).abs().max().item() / loc.abs().max().item() < 4e-3
-        assert (torch.sigmoid(logits.cpu()) - torch.sigmoid(pred)).abs().max().item() < 1e-2
-        mu_ref, _ = dgp_ops.argmax_2d_from_cm(pred, nj, 1.0, 1.0)
-        assert (eng.softargmax(logits)["mu"].cpu() - mu_ref).abs().max().item() < 0.0625
+        assert (logits.cpu() - pred).abs().max().item() / pred.abs().max().item() < BF16_ACT_REL_TOL
+        assert (locref.cpu() - loc).abs().max().item() / loc.abs().max().item() < BF16_ACT_REL_TOL
+        assert (torch.sigmoid(logits.cpu()) - torch.sigmoid(pred)).abs().max().item() < BF16_SIGMOID_TOL
     eng.close()
 
 
-@pytest.mark.parametrize("cfg", [dict(nj=16, H=1024, W=1280, locref=False, skel="chain"),   # BASELINE configs[2] shape
-                                 dict(nj=20, H=480, W=640, locref=True, skel="dense"),      # BASELINE configs[4] shape
-                                 dict(nj=5, H=747, W=832, locref=True, skel="demo")])       # BASELINE configs[0] shape
-def test_baseline_config_shapes(cfg):
-    """One frame of each BASELINE.json configuration through the whole path (head widths 16 / 60 / 15 channels)."""
+BASELINE_SHAPES = [dict(nj=5, H=747, W=832, locref=True, skel="demo"),      # configs[0]: the bundled demo project
+                   dict(nj=4, H=747, W=832, locref=False, skel="chain"),    # configs[1]: the benchmarked workload
+                   dict(nj=16, H=1024, W=1280, locref=False, skel="chain"),  # configs[2]
+                   dict(nj=20, H=480, W=640, locref=True, skel="dense")]    # configs[4]
+
+
+@pytest.mark.parametrize("cfg", BASELINE_SHAPES, ids=["a-demo", "b-reaching", "c-1280x1024", "e-640x480"])
+def test_baseline_config_shapes_meet_baseline_tolerances(cfg):
+    """One frame of every BASELINE.json inference configuration through the whole path vs the fp32 oracle, at the north_star
+    tolerances: sigmoid scoremaps <= 1e-2 max-abs, soft-argmax <= 0.5 image px; integer peaks bit-exact and coordinates
+    <= 1e-3 px when computed from the same fp32 maps; potentials vs the oracle."""
     from deepgraphpose_b200.engine import Engine
     nj = cfg["nj"]
     W = synthetic.make_weights(nj, seed=2, location_refinement=cfg["locref"])
     Wt = {k: torch.from_numpy(v) for k, v in W.items()}
     eng = Engine(nj, location_refinement=cfg["locref"])
+    assert eng.precision == "fp16"
     eng.load_weights(W)
     frames, _ = synthetic.make_video(1, cfg["H"], cfg["W"], nj, seed=11)
     with torch.no_grad():
@@ -98,15 +108,46 @@ def test_baseline_config_shapes(cfg):
     logits, locref = eng.forward(torch.from_numpy(frames).cuda())
     assert logits.shape == pred.shape
     assert (logits.cpu() - pred).abs().max().item() / pred.abs().max().item() < LOGIT_REL_TOL
+    assert (torch.sigmoid(logits.cpu()) - torch.sigmoid(pred)).abs().max().item() < SIGMOID_TOL
     if cfg["locref"]:
         assert (locref.cpu() - loc).abs().max().item() / loc.abs().max().item() < LOGIT_REL_TOL
     out = eng.softargmax(logits, locref)
-    mu_ref, _ = dgp_ops.argmax_2d_from_cm(logits.cpu(), nj, 1.0, 1.0)    # same fp32 maps -> tight
+    mu_oracle, _ = dgp_ops.argmax_2d_from_cm(pred, nj, 1.0, 1.0)             # oracle network -> oracle soft-argmax
+    assert (out["mu"].cpu() - mu_oracle).abs().max().item() * 8.0 < 0.5
+    mu_ref, _ = dgp_ops.argmax_2d_from_cm(logits.cpu(), nj, 1.0, 1.0)        # same fp32 maps -> tight
     assert (out["mu"].cpu() - mu_ref).abs().max().item() < 1e-3
+    _, pk, _ = dgp_ops.estimate_pose_readout(out["mu"].cpu().numpy(), logits.cpu().numpy())
+    assert (pk == out["peak"][0].cpu().numpy()).all()
     edges = {"chain": synthetic.chain_skeleton(nj), "dense": synthetic.dense_skeleton(nj), "demo": [(0, 1), (3, 4)]}[cfg["skel"]]
     pot = eng.potentials(out["mu"], edges)
     d_ref = dgp_ops.skeleton_distances(out["mu"].cpu(), dgp_ops.skeleton_matrix(edges, nj))
     assert (pot["skel"].cpu() - d_ref).abs().max().item() < 1e-3
+    eng.close()
+
+
+def test_trained_like_weights_meet_the_scoremap_tolerance():
+    """The second synthetic weight set (synthetic.make_weights(trained_like=True): near-zero / zero BatchNorm gammas as in an
+    ImageNet checkpoint, part_pred gain x2 with bias -4 -> sparse, confident scoremaps): sigmoid <= 1e-2 at the benchmarked
+    shape.  Its random multi-peaked maps make the soft-argmax ill-conditioned (two far-apart pixels of equal weight), so
+    the coordinate check is made where the reference's tolerance is meaningful: from the same fp32 maps."""
+    from deepgraphpose_b200.engine import Engine
+    nj = 4
+    W = synthetic.make_weights(nj, seed=0, location_refinement=False, trained_like=True)
+    Wt = {k: torch.from_numpy(v) for k, v in W.items()}
+    eng = Engine(nj, location_refinement=False)
+    eng.load_weights(W)
+    frames, _ = synthetic.make_video(1, 747, 832, nj, seed=7)
+    with torch.no_grad():
+        pred = pose_net.prediction_layer(pose_net.extract_features(torch.from_numpy(frames.astype(np.float32)), Wt), Wt, "part_pred")
+    logits, _ = eng.forward(torch.from_numpy(frames).cuda())
+    prob, ref = torch.sigmoid(logits.cpu()), torch.sigmoid(pred)
+    assert (prob - ref).abs().max().item() < SIGMOID_TOL
+    assert float((ref > 0.5).float().mean()) < 0.35          # sparse map, not the flat 0.5 field of the random-init set
+    out = eng.softargmax(logits)
+    mu_ref, _ = dgp_ops.argmax_2d_from_cm(logits.cpu(), nj, 1.0, 1.0)
+    assert (out["mu"].cpu() - mu_ref).abs().max().item() < 1e-3
+    _, pk, _ = dgp_ops.estimate_pose_readout(out["mu"].cpu().numpy(), logits.cpu().numpy())
+    assert (pk == out["peak"][0].cpu().numpy()).all()
     eng.close()
 
 
@@ -195,8 +236,8 @@ def test_posenet_shim(setup):
     loc = out["locref"].cpu().numpy()
     for b in range(2):
         scm, off = pose_net.extract_cnn_output(prob[b:b + 1], loc[b:b + 1])
-        ref_pose, _ = pose_net.argmax_pose_predict(scm, off, 8.0)
-        assert np.abs(ref_pose - pose[b * nj:(b + 1) * nj]).max() < 1e-3
+        ref_pose, _ = pose_net.argmax_pose_predict(scm, off, 8.0)           # (x, y, lik); PoseNet.inference emits (y, x, lik)
+        assert np.abs(ref_pose - pose[b * nj:(b + 1) * nj][:, [1, 0, 2]]).max() < 1e-3
 
 
 def test_forward_errors(setup):

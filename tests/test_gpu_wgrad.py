@@ -12,10 +12,11 @@ from oracle import tf_ops
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def eng():
+@pytest.fixture(scope="module", params=["fp16", "bf16"])
+def eng(request):
+    """Both 16-bit storage modes of the same kernels: fp16 (the default of the shims / bench.py) and bf16."""
     from deepgraphpose_b200.engine import Engine
-    e = Engine(4)
+    e = Engine(4, precision=request.param)
     yield e
     e.close()
 
@@ -47,21 +48,21 @@ CASES = [
 def test_wgrad_matches_autograd(eng, case):
     N, H, W, Cin, Cout, R, stride, dil, pm = case
     rng = np.random.default_rng(abs(hash(case)) % (2 ** 31))
-    x = torch.from_numpy(rng.standard_normal((N, H, W, Cin)).astype(np.float32)).to(torch.bfloat16)
+    x = torch.from_numpy(rng.standard_normal((N, H, W, Cin)).astype(np.float32)).to(eng.act_dtype)
     w = torch.zeros((R, R, Cin, Cout), requires_grad=True)
     y = ref_conv(x.float(), w, stride, dil, pm)
-    dy = torch.from_numpy(rng.standard_normal(tuple(y.shape)).astype(np.float32)).to(torch.bfloat16)
+    dy = torch.from_numpy(rng.standard_normal(tuple(y.shape)).astype(np.float32)).to(eng.act_dtype)
     (y * dy.float()).sum().backward()
     ref = w.grad.permute(3, 0, 1, 2).reshape(Cout, R * R * Cin)  # kernel layout [Cout][tap][Cin]
     got = eng.conv2d_wgrad(x.cuda(), dy.cuda(), R, stride, dil, pm).cpu()
-    # bf16 products are exact in fp32; only the fp32 accumulation order differs
+    # 16-bit x 16-bit products are exact in fp32; only the fp32 accumulation order differs
     assert (got - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
 
 
 def test_wgrad_is_bitwise_reproducible(eng):
     rng = np.random.default_rng(1)
-    x = torch.from_numpy(rng.standard_normal((3, 47, 52, 256)).astype(np.float32)).to(torch.bfloat16).cuda()
-    dy = torch.from_numpy(rng.standard_normal((3, 47, 52, 256)).astype(np.float32)).to(torch.bfloat16).cuda()
+    x = torch.from_numpy(rng.standard_normal((3, 47, 52, 256)).astype(np.float32)).to(eng.act_dtype).cuda()
+    dy = torch.from_numpy(rng.standard_normal((3, 47, 52, 256)).astype(np.float32)).to(eng.act_dtype).cuda()
     a = eng.conv2d_wgrad(x, dy, 3, 1, 1, 1)
     b = eng.conv2d_wgrad(x, dy, 3, 1, 1, 1)
     assert torch.equal(a, b)
@@ -73,15 +74,15 @@ def test_dgrad_as_flipped_conv_matches_autograd(eng, case):
     rng = np.random.default_rng(abs(hash(case)) % (2 ** 31) + 1)
     x = torch.zeros((N, H, W, Cin), requires_grad=True)
     w = (rng.standard_normal((R, R, Cin, Cout)) * np.sqrt(1.0 / (R * R * Cin))).astype(np.float32)
-    wq = torch.from_numpy(w).to(torch.bfloat16).float()
+    wq = torch.from_numpy(w).to(eng.act_dtype).float()
     y = ref_conv(x, wq, stride, dil, pm)
-    dy = torch.from_numpy(rng.standard_normal(tuple(y.shape)).astype(np.float32)).to(torch.bfloat16)
+    dy = torch.from_numpy(rng.standard_normal(tuple(y.shape)).astype(np.float32)).to(eng.act_dtype)
     (y * dy.float()).sum().backward()
     wd = np.ascontiguousarray(w[::-1, ::-1].transpose(0, 1, 3, 2))
     if stride == 1:
         dyu = dy
     else:
-        dyu = torch.zeros((N, H, W, Cout), dtype=torch.bfloat16)
+        dyu = torch.zeros((N, H, W, Cout), dtype=eng.act_dtype)
         dyu[:, ::stride, ::stride, :][:, :dy.shape[1], :dy.shape[2]] = dy
     got = eng.conv2d(dyu.cuda(), wd, 1, dil, 1 if R > 1 else 0, None, None, None, 1, False, True, 0).cpu()
     assert (got - x.grad).abs().max().item() <= 2e-5 * x.grad.abs().max().item()
