@@ -4,12 +4,19 @@
   python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU under torchrun)
   python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port) on the host cores
 
-A "step" is one pass of the hot path over one batch of synthetic frames of BASELINE.json configs[1]
-(747x832 RGB, 4 bodyparts, chain skeleton): ResNet-50 OS16 scoremap net + part_pred deconv head + fused
-soft-argmax / peak / likelihood + skeleton & temporal potentials (+ the one-frame halo exchange when N > 1).
+Headline (`value`, every N): BASELINE.json configs[1] -- synthetic 4-bodypart reaching video, 747x832, estimate_pose
+inference.  A "step" is one pass of the hot path over one batch of frames: ResNet-50 OS16 scoremap net + part_pred deconv
+head + fused soft-argmax / peak / likelihood + skeleton & temporal potentials (+ the one-frame halo exchange when N > 1),
+inputs resident in HBM.  `e2e` is the same workload through the public API with HOST buffers: a 10 000-frame (per GPU)
+video streamed from pinned host memory through eval.estimate_pose_sharded -- H2D of every batch, D2H of the read-outs, and at
+N > 1 the halo exchange, the potentials and the all-gather of the per-frame results inside the timed region.
+Extra objects on the same line: `configs2` (configs[2]: 1280x1024, 16 bodyparts, frame-sharded across the N GPUs, with an
+in-run bit-exactness check of the sharded result against a single-GPU recomputation), `train_step` (configs[3]),
+`aux_bf16` (the same step in the bf16 storage mode), `roofline`, `roofline_aux`, `cpu_baseline`.
 Prints ONE JSON line (rank 0).
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -26,7 +33,7 @@ sys.path.insert(0, ROOT)
 H, W, NJ = 747, 832, 4
 METRIC = "frames/sec (ResNet-50 scoremap + DGP soft-argmax/potentials)"
 WORKLOAD = "configs[1]: synthetic 4-bodypart reaching video 747x832, estimate_pose inference (part_pred head, chain skeleton)"
-
+PRECISION = "fp16"   # the storage mode whose GPU tests assert BASELINE.json's tolerances (tests/test_gpu_forward.py)
 
 CONFIGS = {  # BASELINE.json configs -> (H, W, num_joints, skeleton, label)
     "b": (747, 832, 4, "chain", WORKLOAD),
@@ -69,8 +76,18 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
 
 
+def csrc_sha():
+    """Hash of the kernel sources: ncu-derived numbers under profiles/ are only quoted while they describe THIS code."""
+    d = os.path.join(ROOT, "deepgraphpose_b200", "csrc")
+    hsh = hashlib.sha256()
+    for fn in sorted(os.listdir(d)):
+        with open(os.path.join(d, fn), "rb") as f:
+            hsh.update(fn.encode() + b"\0" + f.read())
+    return hsh.hexdigest()[:16]
+
+
 class ClockSampler:
-    """SM clocks / throttle reasons sampled DURING the timed region (NVML every 5 ms; nvidia-smi as fallback)."""
+    """SM clocks / throttle reasons sampled DURING the timed region (NVML every 2 ms; nvidia-smi as fallback)."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
@@ -127,12 +144,13 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.sm)}
 
 
-def make_frame_pool(n_frames, seed=1234):
+def make_frame_pool(n_frames, seed=1234, h=None, w=None, nj=None):
     """n_frames distinct synthetic frames (uint8, T,H,W,3): a short seeded clip, extended by cyclic shifts."""
     from deepgraphpose_b200 import synthetic
+    h, w, nj = h or H, w or W, nj or NJ
     base_n = min(n_frames, 16)
-    base, _ = synthetic.make_video(base_n, H, W, NJ, seed=seed)
-    out = np.empty((n_frames, H, W, 3), np.uint8)
+    base, _ = synthetic.make_video(base_n, h, w, nj, seed=seed)
+    out = np.empty((n_frames, h, w, 3), np.uint8)
     for i in range(n_frames):
         out[i] = np.roll(base[i % base_n], shift=(3 * (i // base_n), 5 * (i // base_n)), axis=(0, 1))
     return out
@@ -190,6 +208,204 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+class Workload:
+    """One inference configuration on this rank: engine, device-resident input batches, pinned host pool, skeleton."""
+
+    def __init__(self, key, local_rank, rank, precision, batch=0):
+        from deepgraphpose_b200 import synthetic
+        from deepgraphpose_b200.engine import Engine, suggest_batch
+        self.key = key
+        self.H, self.W, self.nj, self.skeleton_kind, self.label = CONFIGS[key]
+        self.dev = torch.device("cuda", local_rank)
+        self.B = batch if batch > 0 else suggest_batch(self.H, self.W, *((12, 24) if key == "c" else (24, 48)))
+        self.eng = Engine(self.nj, location_refinement=False, device=local_rank, precision=precision)
+        self.eng.load_weights(synthetic.make_weights(self.nj, seed=0, location_refinement=False))
+        self.edges = synthetic.dense_skeleton(self.nj) if self.skeleton_kind == "dense" else synthetic.chain_skeleton(self.nj)
+        self.flops_frame, (self.hs, self.ws) = conv_flops_per_frame(self.H, self.W, self.nj, locref=False)
+        self.n_pool = 4
+        # ONE video for all ranks (frame t = pool[t % P]): every rank reads its own contiguous range of it
+        self.pool_host = torch.from_numpy(make_frame_pool(self.n_pool * self.B, seed=1234, h=self.H, w=self.W, nj=self.nj)).pin_memory()
+        # device-resident batches for the kernel-level number: distinct per rank, together larger than the 126 MB L2
+        self.pool = [torch.roll(self.pool_host[i * self.B:(i + 1) * self.B], shifts=7 * rank, dims=2).to(self.dev)
+                     for i in range(self.n_pool)]
+        self.ws_vec = np.full(len(self.edges), 1000.0 / 60.0, np.float32)
+        self.ws_max = np.full(len(self.edges), 1.2 * 80.0, np.float32)
+
+    def step(self, i, world):
+        from deepgraphpose_b200 import sharding
+        logits, _ = self.eng.forward(self.pool[i % self.n_pool], want_locref=False)
+        out = self.eng.softargmax(logits, None, 1.0, 1.0, want=("mu", "peak", "lik"))
+        halo = sharding.exchange_halo(out["mu"][0]) if world > 1 else None
+        pot = self.eng.potentials(out["mu"], self.edges, halo_next=halo, ws=self.ws_vec, ws_max=self.ws_max, wt_max=0.0)
+        return out, pot
+
+    def close(self):
+        self.eng.close()
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+
+
+def max_over_ranks(x, world, dev):
+    if world == 1:
+        return x
+    import torch.distributed as dist
+    t = torch.tensor([x], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def measure_device(wl, steps, warmup, world, local_rank, profile=True):
+    """K device-timed steps with inputs resident in HBM (+ a second pass with per-launch CUDA events for the rooflines)."""
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for i in range(warmup):
+        wl.step(i, world)
+    torch.cuda.synchronize()
+    barrier(world)
+    sampler.begin()
+    launches0 = wl.eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(steps):
+        wl.step(i, world)
+    e1.record()
+    torch.cuda.synchronize()
+    barrier(world)
+    ms = max_over_ranks(e0.elapsed_time(e1), world, wl.dev)
+    launches = wl.eng.launch_count() - launches0
+    clocks = sampler.stop()
+    prof, ms_prof = None, None
+    if profile:
+        # Second pass over the SAME K steps with a CUDA-event pair around every kernel launch (recorded by the handle on the
+        # launching stream).  Kept out of the headline pass: an event record between two layers defeats their
+        # programmatic-dependent-launch overlap.
+        wl.eng.get_profile()
+        wl.eng.set_profiling(True)
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for i in range(steps):
+            wl.step(i, world)
+        p1.record()
+        torch.cuda.synchronize()
+        ms_prof = p0.elapsed_time(p1)
+        wl.eng.set_profiling(False)
+        prof = wl.eng.get_profile()
+    return {"ms": ms, "launches": launches, "clocks": clocks, "prof": prof, "ms_prof": ms_prof,
+            "value": world * wl.B * steps / (ms / 1e3)}
+
+
+def measure_e2e(wl, frames_per_gpu, world):
+    """The public API with HOST buffers: eval.estimate_pose_sharded streams a (world * frames_per_gpu)-frame video from
+    pinned host memory (frame t = pool[t % P]) -- every rank its contiguous shard -- H2D per batch, D2H of the read-outs,
+    halo exchange + potentials + all-gather of the per-frame results.  Wall clock between barriers, max over ranks."""
+    from deepgraphpose_b200.eval import estimate_pose_sharded
+    T = world * frames_per_gpu
+    run = lambda n: estimate_pose_sharded(wl.eng, wl.pool_host, n, wl.H, wl.W, wl.edges, wl.ws_vec, wl.ws_max, 0.0, batch=wl.B)
+    run(world * 2 * wl.B)     # warm-up: plans, pinned ring, NCCL
+    torch.cuda.synchronize()
+    barrier(world)
+    t0 = time.perf_counter()
+    res = run(T)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    barrier(world)
+    dt = max_over_ranks(dt, world, wl.dev)
+    return res, {"value": T / dt, "unit": "frames/s", "frames": T, "seconds": dt,
+                 "h2d_bytes_per_step": wl.B * wl.H * wl.W * 3, "d2h_bytes_per_step": wl.B * wl.nj * (8 + 8 + 4),
+                 "timing": "wall clock around eval.estimate_pose_sharded (synchronous public API: pinned host frames -> "
+                           "streamed H2D per %d-frame batch -> forward + soft-argmax -> D2H of mu / peak / likelihood%s), "
+                           "max over ranks" % (wl.B, "; halo all_gather + potentials + all_gather of the per-frame results" if world > 1 else "; potentials")}
+
+
+def check_sharded_equals_single(wl, res, world, rank, k=8):
+    """Bit-exactness of the sharded run IN the run: rank 0 recomputes the k frames around the first shard boundary on its
+    own GPU in ONE batch (different batch composition, no halo needed) and compares mu / peak / likelihood / skeleton and
+    temporal potentials with the gathered result bit for bit."""
+    if world == 1:
+        return None
+    from deepgraphpose_b200 import sharding
+    T = res["markers"].shape[0]
+    b0 = sharding.shard_range(T, 0, world)[1]
+    lo, hi = max(0, b0 - k // 2), min(T, b0 + k // 2)
+    ok = True
+    if rank == 0:
+        P = wl.pool_host.shape[0]
+        idx = torch.tensor([t % P for t in range(lo, hi)])
+        frames = wl.pool_host[idx].to(wl.dev)
+        logits, _ = wl.eng.forward(frames, want_locref=False)
+        out = wl.eng.softargmax(logits, None, 1.0, 1.0, want=("mu", "peak", "lik"))
+        pot = wl.eng.potentials(out["mu"], wl.edges, ws=wl.ws_vec, ws_max=wl.ws_max, wt_max=0.0)
+        ok = (np.array_equal(out["mu"].cpu().numpy().astype(np.float64), res["markers"][lo:hi])
+              and np.array_equal(out["peak"].cpu().numpy(), res["mu_likelihoods"][lo:hi])
+              and np.array_equal(out["lik"].cpu().numpy().astype(np.float64), res["likelihoods"][lo:hi])
+              and np.array_equal(pot["temporal"].cpu().numpy(), res["temporal"][lo:hi - 1])
+              and np.array_equal(pot["skel"].t().cpu().numpy(), res["skel"][lo:hi]))
+    return {"equal": bool(ok), "frames_checked": [lo, hi], "shard_boundary": b0,
+            "what": "mu, integer peaks, likelihoods, skeleton distances, temporal potentials across the shard edge; bit for bit"}
+
+
+def roofline_of(wl, m, steps, peaks, peak_src):
+    prof = m["prof"]
+    gemm_ms, gemm_n = prof["conv_gemm"]
+    frames_timed = wl.B * steps
+    achieved_tf = wl.flops_frame * frames_timed / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
+    peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
+    traffic, traffic_note = None, "no ncu --set full capture of the current kernel sources under profiles/"
+    tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if os.path.exists(tpath) and wl.key == "b":
+        with open(tpath) as f:
+            tj = json.load(f)
+        if tj.get("csrc_sha") == csrc_sha():
+            traffic = tj["traffic_bytes_per_frame"] * wl.B / tj["gemm_launches_per_step"]
+            traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum per conv_gemm launch (mean over the %d GEMM launches of a step) "
+                            "from the ncu capture %s of these kernel sources (csrc sha %s, B=%d there); algorithmic minimum %.0f MB/launch"
+                            % (tj["gemm_launches_per_step"], tj.get("source", "profiles/r02_launches_dram.csv"), tj["csrc_sha"], tj["batch"],
+                               tj["minimum_bytes_per_frame_16bit"] * wl.B / tj["gemm_launches_per_step"] / 1e6))
+        else:
+            traffic_note = "profiles/r02_traffic.json describes other kernel sources (csrc sha %s != %s): not quoted" % (tj.get("csrc_sha"), csrc_sha())
+    return {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM, %d launches)" % gemm_n,
+            "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+            "frac": (achieved_tf / peak_tf) if achieved_tf else None, "traffic": traffic, "traffic_note": traffic_note,
+            "peak_source": peak_src + ", 16-bit dense sustained (cuBLAS bf16; fp16 runs at the same tensor rate)",
+            "share_of_step": gemm_ms / m["ms_prof"],
+            "timing": "CUDA events around each of the %d launches in a second pass over the same steps (%.3f ms/step with events, %.3f without)"
+                      % (gemm_n, m["ms_prof"] / steps, m["ms"] / steps),
+            "algorithmic_gflop_per_frame": wl.flops_frame / 1e9}
+
+
+def softargmax_roofline(local_rank, peaks):
+    """GPU-filling soft-argmax measurement (the in-step launch moves 5 MB and is latency bound): 4096 maps of each BASELINE
+    shape, far larger than the L2, CUDA events around the stream + finalize pair, best of 5 after warm-up."""
+    from deepgraphpose_b200.engine import Engine
+    out = {}
+    for tag, (hs, ws, nj) in {"nj4_94x104": (94, 104, 4), "nj16_128x160": (128, 160, 16), "nj20_60x80": (60, 80, 20)}.items():
+        nmaps = 4096 if nj <= 4 else (1024 if nj == 16 else 2048)
+        eng = Engine(nj, location_refinement=False, device=local_rank)
+        x = torch.randn((nmaps, hs, ws, nj), device="cuda:%d" % local_rank) * 3.0
+        for _ in range(3):
+            eng.softargmax(x, None, 1.0, 1.0, want=("mu", "peak", "lik"))
+        best = None
+        for _ in range(5):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            eng.softargmax(x, None, 1.0, 1.0, want=("mu", "peak", "lik"))
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b)
+            best = ms if best is None else min(best, ms)
+        gbs = x.numel() * 4 / (best / 1e3) / 1e9
+        out[tag] = {"maps": nmaps, "bytes": x.numel() * 4, "ms": best, "achieved": gbs, "unit": "GB/s",
+                    "frac": gbs / peaks.get("hbm_gbs")}
+        eng.close()
+        del x
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -199,8 +415,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the auxiliary training-step measurement (configs[3])")
+    ap.add_argument("--no-aux", action="store_true", help="skip configs[2], the bf16 line and the soft-argmax microbenchmark")
     ap.add_argument("--config", default="b", choices=sorted(CONFIGS),
-                    help="BASELINE.json workload: b = configs[1] (the headline, default), c = configs[2], e = configs[4]")
+                    help="BASELINE.json workload of the headline: b = configs[1] (default), c = configs[2], e = configs[4]")
+    ap.add_argument("--precision", default=PRECISION, choices=["fp16", "bf16"])
+    ap.add_argument("--e2e-frames", type=int, default=10000, help="frames per GPU of the end-to-end video (configs[1]: 10 k)")
     ap.add_argument("--cpu-frames", type=int, default=12)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
@@ -218,94 +437,56 @@ def main():
         return
 
     import torch.distributed as dist
-    from deepgraphpose_b200 import sharding, synthetic
-    from deepgraphpose_b200.engine import Engine
-    from deepgraphpose_b200.eval import estimate_pose_frames
-
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    from deepgraphpose_b200.engine import suggest_batch
-    B = args.batch if args.batch > 0 else suggest_batch(H, W, *((12, 24) if args.config == "c" else (24, 48)))
-    eng = Engine(NJ, location_refinement=False, device=local_rank)
-    eng.load_weights(synthetic.make_weights(NJ, seed=0, location_refinement=False))
-    edges = synthetic.dense_skeleton(NJ) if skeleton_kind == "dense" else synthetic.chain_skeleton(NJ)
-    flops_frame, (hs, ws) = conv_flops_per_frame(H, W, NJ, locref=False)
+    peaks, peak_src = load_peaks()
+    wl = Workload(args.config, local_rank, rank, args.precision, args.batch)
+    m = measure_device(wl, args.steps, args.warmup, world, local_rank)
+    res, e2e = measure_e2e(wl, args.e2e_frames, world)
+    finite = bool(np.isfinite(res["x"]).all())
+    roof = roofline_of(wl, m, args.steps, peaks, peak_src) if rank == 0 else None
+    sa_ms, sa_n = m["prof"]["softargmax"]
+    fam = {k: v[0] for k, v in m["prof"].items()}
+    B = wl.B
+    wl.close()
+    del wl
+    torch.cuda.empty_cache()
 
-    # Distinct input batches, together larger than the 126 MB L2 (and every layer's activations are far larger still).
-    n_pool = 4
-    pool_host = make_frame_pool(n_pool * B, seed=1234 + rank)
-    pool = [torch.from_numpy(pool_host[i * B:(i + 1) * B]).to(dev) for i in range(n_pool)]
-    ws_vec = np.full(len(edges), 1000.0 / 60.0, np.float32)
-    ws_max = np.full(len(edges), 1.2 * 80.0, np.float32)
-
-    def step(i):
-        logits, _ = eng.forward(pool[i % n_pool], want_locref=False)
-        out = eng.softargmax(logits, None, 1.0, 1.0, want=("mu", "peak", "lik"))
-        halo = sharding.exchange_halo(out["mu"][0]) if world > 1 else None
-        pot = eng.potentials(out["mu"], edges, halo_next=halo, ws=ws_vec, ws_max=ws_max, wt_max=0.0)
-        return out, pot
-
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    for i in range(args.warmup):
-        step(i)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    sampler.begin()
-    launches0 = eng.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    for i in range(args.steps):
-        step(i)
-    e1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    ms = e0.elapsed_time(e1)
-    launches = eng.launch_count() - launches0
-    clocks = sampler.stop()
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    # Second pass over the SAME K steps with a CUDA-event pair around every kernel launch (recorded by the handle on the
-    # launching stream) for the per-kernel-family roofline numbers.  It is kept out of the headline pass because an
-    # event record between two layers defeats their programmatic-dependent-launch overlap.
-    eng.get_profile()
-    eng.set_profiling(True)
-    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    p0.record()
-    for i in range(args.steps):
-        step(i)
-    p1.record()
-    torch.cuda.synchronize()
-    ms_prof = p0.elapsed_time(p1)
-    eng.set_profiling(False)
-    prof = eng.get_profile()
-    value = world * B * args.steps / (ms / 1e3)
-
-    # ---- end to end through the public API with HOST buffers (H2D of every batch + D2H of its results inside)
-    e2e_steps = max(2, min(args.steps, 10))
-    host = torch.from_numpy(np.concatenate([pool_host] * ((e2e_steps * B + len(pool_host) - 1) // len(pool_host)))[: e2e_steps * B]).pin_memory()
-    estimate_pose_frames(eng, host[: 2 * B], batch=B)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    res = estimate_pose_frames(eng, host, batch=B)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([dt], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
-    e2e_value = world * e2e_steps * B / dt
+    aux = {}
+    if not args.no_aux:
+        # ---- configs[2] (the multi-GPU workload north_star names): device-timed step + sharded e2e + in-run exactness
+        if args.config != "c":
+            wc = Workload("c", local_rank, rank, args.precision)
+            mc = measure_device(wc, max(5, args.steps // 2), 3, world, local_rank)
+            resc, e2ec = measure_e2e(wc, 2000, world)
+            chk = check_sharded_equals_single(wc, resc, world, rank)
+            if rank == 0:
+                rc = roofline_of(wc, mc, max(5, args.steps // 2), peaks, peak_src)
+                aux["configs2"] = {"workload": wc.label, "value": mc["value"], "unit": "frames/s", "ms_per_step": mc["ms"] / max(5, args.steps // 2),
+                                   "frames_per_step_per_gpu": wc.B, "frame": [wc.H, wc.W, 3], "num_joints": wc.nj, "n_gpus": world,
+                                   "parallelism": ("contiguous frame shards x%d, 1-frame halo" % world) if world > 1 else "single GPU",
+                                   "e2e": e2ec, "sharded_equals_single": chk, "roofline_frac": rc["frac"],
+                                   "finite": bool(np.isfinite(resc["x"]).all())}
+            wc.close()
+            del wc
+            torch.cuda.empty_cache()
+        # ---- the other storage mode, same step
+        other = "bf16" if args.precision == "fp16" else "fp16"
+        wo = Workload(args.config, local_rank, rank, other, B)
+        mo = measure_device(wo, max(5, args.steps // 2), 3, world, local_rank)
+        if rank == 0:
+            ro = roofline_of(wo, mo, max(5, args.steps // 2), peaks, peak_src)
+            aux["aux_" + other] = {"value": mo["value"], "unit": "frames/s", "ms_per_step": mo["ms"] / max(5, args.steps // 2), "roofline_frac": ro["frac"],
+                                   "note": "same kernels and step with %s storage; its GPU tests assert %s" % (
+                                       other, "wider, documented bounds (sigmoid <= 5e-2), not BASELINE's" if other == "bf16" else "BASELINE's tolerances")}
+        wo.close()
+        del wo
+        torch.cuda.empty_cache()
+    sa_fill = softargmax_roofline(local_rank, peaks) if (rank == 0 and not args.no_aux) else None
 
     # ---- configs[3] alongside: one data-parallel DGP training step per rank (fwd + bwd + all-reduce + clip/Momentum)
     train_line = None
@@ -313,54 +494,37 @@ def main():
         try:
             sys.path.insert(0, os.path.join(ROOT, "tools"))
             import bench_train
-            train_line = bench_train.measure(rank, local_rank, world, 5, 3, 10, H, W, profile=False)
+            train_line = bench_train.measure(rank, local_rank, world, 20, 3, 10, H, W, profile=False, precision=args.precision)
         except Exception as ex:  # the headline line must survive a failure of the auxiliary measurement
             train_line = {"error": repr(ex)}
     if rank == 0:
-        peaks, peak_src = load_peaks()
-        gemm_ms, gemm_n = prof["conv_gemm"]
-        sa_ms, sa_n = prof["softargmax"]
-        frames_timed = B * args.steps
-        achieved_tf = flops_frame * frames_timed / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
-        peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
-        sa_bytes = 4 * hs * ws * NJ * frames_timed
-        traffic, traffic_note = None, "no ncu capture committed"
-        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(tpath) and args.config == "b":
-            with open(tpath) as f:
-                tj = json.load(f)
-            traffic = tj["traffic_bytes_per_frame"] * B / 54
-            traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum per conv_gemm launch (mean of the 54 layers) scaled from the "
-                            "committed ncu capture profiles/r01_launches.csv (B=%d there); algorithmic minimum %.0f MB/launch" %
-                            (tj["batch"], tj["minimum_bytes_per_frame_bf16"] * B / 54 / 1e6))
+        sa_bytes = 4 * (2 * -(-H // 16)) * (2 * -(-W // 16)) * NJ * B * args.steps
         line = {
-            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "metric": METRIC, "value": m["value"], "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": m["ms"] / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": B, "frame": [H, W, 3], "num_joints": NJ,
-                       "skeleton": skeleton_kind, "l2": "4 rotating input batches (%d MB) and per-layer activations (>600 MB/step) exceed the 126 MB L2" % (n_pool * B * H * W * 3 // 2 ** 20),
+                       "skeleton": skeleton_kind,
+                       "precision": "%s operands on tcgen05 kind::f16, fp32 accumulate / BN epilogue / logits: the mode whose GPU tests assert BASELINE.json's tolerances "
+                                    "(sigmoid 1e-2, soft-argmax 0.5 px, loss 1e-3) on all four inference shapes and the training step" % args.precision,
+                       "l2": "4 rotating input batches (%d MB) and per-layer activations (>600 MB/step) exceed the 126 MB L2" % (4 * B * H * W * 3 // 2 ** 20),
                        "batch_choice": "engine.suggest_batch: tile counts of the persistent GEMM grid land on multiples of the SM count",
                        "parallelism": "frame shards x%d, 1-frame halo all_gather" % world if world > 1 else "single GPU"},
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": B * H * W * 3,
-                    "d2h_bytes_per_step": B * NJ * (8 + 8 + 4), "timing": "wall clock around estimate_pose_frames (synchronous API), max over ranks",
-                    "frames": e2e_steps * B * world},
-            "gpu_launches": launches,
-            "roofline": {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM, %d launches)" % gemm_n,
-                         "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": (achieved_tf / peak_tf) if achieved_tf else None, "traffic": traffic,
-                         "traffic_note": traffic_note,
-                         "peak_source": peak_src + ", bf16 sustained", "share_of_step": gemm_ms / ms_prof,
-                         "timing": "CUDA events around each of the %d launches in a second pass over the same steps (%.3f ms/step with events, %.3f without)" % (gemm_n, ms_prof / args.steps, ms / args.steps),
-                         "algorithmic_gflop_per_frame": flops_frame / 1e9},
-            "roofline_aux": {"softargmax": {"bound": "hbm", "achieved": sa_bytes / (sa_ms / 1e3) / 1e9 if sa_ms > 0 else None,
-                                            "peak": peaks.get("hbm_gbs"), "unit": "GB/s", "launches": sa_n,
-                                            "note": "partial+finalize pair timed together inside the step"},
-                             "ms_by_kernel_family": {k: v[0] for k, v in prof.items()}},
-            "finite": bool(np.isfinite(res["x"]).all()),
+            "clocks": m["clocks"],
+            "e2e": e2e,
+            "gpu_launches": m["launches"],
+            "roofline": roof,
+            "roofline_aux": {"softargmax_in_step": {"bound": "hbm", "achieved": sa_bytes / (sa_ms / 1e3) / 1e9 if sa_ms > 0 else None,
+                                                    "peak": peaks.get("hbm_gbs"), "unit": "GB/s", "launches": sa_n,
+                                                    "note": "stream + finalize pair inside the step: 4.9 MB per batch, latency bound"},
+                             "softargmax": sa_fill,
+                             "ms_by_kernel_family": fam},
+            "finite": finite,
         }
+        line.update(aux)
         if train_line is not None:
-            keep = ("metric", "value", "unit", "ms_per_step", "config", "gpu_launches", "loss_after", "finite", "e2e", "error")
+            keep = ("metric", "value", "unit", "ms_per_step", "config", "gpu_launches", "loss_after", "finite", "e2e", "error", "dtype",
+                    "allreduce")
             line["train_step"] = {k: train_line[k] for k in keep if k in train_line}
         if world == 1 and not args.no_cpu_baseline and args.config == "b":
             fps, cores, cdt = cpu_reference_fps(args.cpu_frames, warmup=1)

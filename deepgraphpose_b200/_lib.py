@@ -48,6 +48,15 @@ class DgpLossBatch(C.Structure):
                 ("vector_field_dev", C.c_void_p), ("Hin", C.c_int32), ("Win", C.c_int32), ("wt_batch_dev", C.c_void_p)]
 
 
+class DgpCyclicSource(C.Structure):
+    _fields_ = [("pool", C.c_void_p), ("pool_frames", C.c_int64), ("total_frames", C.c_int64), ("position", C.c_int64),
+                ("frame_bytes", C.c_size_t)]
+
+
+# reader(user, slot, max_frames, &direct) -> frames delivered (0 = end of video, < 0 = error)
+FRAME_READER = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p))
+
+
 # name -> (restype, argtypes); kept in one table so the CPU test-suite can check every exported symbol.
 _vp, _i, _f, _sz, _i64p = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.POINTER(C.c_int64)
 SIGNATURES = {
@@ -71,6 +80,8 @@ SIGNATURES = {
     "dgp_sigmoid": (_i, [_vp, _vp, _vp, _sz, _vp]),
     "dgp_potentials": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp]),
     "dgp_estimate_pose_host": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp]),
+    "dgp_estimate_pose_stream": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _f, C.c_int64, _vp, _vp, _vp, _i64p]),
+    "dgp_cyclic_reader": (_i, [_vp, _vp, _i, C.POINTER(_vp)]),
     "dgp_debug_keep_activations": (_i, [_vp, _i]),
     "dgp_debug_get_activation": (_i, [_vp, C.c_char_p, _vp, _sz, _i64p]),
     "dgp_conv2d": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp,
@@ -84,6 +95,12 @@ SIGNATURES = {
     "dgp_train_wait_early_bucket": (_i, [_vp, _vp]),
     "dgp_train_use_graphs": (_i, [_vp, _i]),
     "dgp_train_set_loss_scale": (_i, [_vp, _f]),
+    "dgp_comm_unique_id": (_i, [C.c_char_p]),
+    "dgp_comm_init_rank": (_i, [_vp, C.c_char_p, _i, _i]),
+    "dgp_attach_comm": (_i, [_vp, _vp]),
+    "dgp_comm_world_size": (_i, [_vp]),
+    "dgp_allreduce_gradients": (_i, [_vp, _vp, C.POINTER(_f)]),
+    "dgp_allreduce_exposed_ms": (_i, [_vp, C.POINTER(_f)]),
     "dgp_get_grad_norm": (_i, [_vp, C.POINTER(_f)]),
     "dgp_train_outputs": (_i, [_vp, _i, _i, _i, C.POINTER(_vp), C.POINTER(_vp)]),
     "dgp_get_variable": (_i, [_vp, C.c_char_p, _i, _vp, _sz, _i64p, C.POINTER(_i)]),

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libdgp_b200.so")
-SOURCES = ["capi.cu", "conv_gemm_sm100.cu", "wgrad_gemm_sm100.cu", "softargmax.cu", "aux_kernels.cu", "loss_kernels.cu", "param_kernels.cu", "bwd_kernels.cu", "train.cu", "feeder_kernels.cu", "boundary.cu"]
+SOURCES = ["capi.cu", "conv_gemm_sm100.cu", "wgrad_gemm_sm100.cu", "softargmax.cu", "aux_kernels.cu", "loss_kernels.cu", "param_kernels.cu", "bwd_kernels.cu", "train.cu", "feeder_kernels.cu", "boundary.cu", "stream.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xcompiler", "-Wno-unused-function",
@@ -53,7 +53,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    link = [_nvcc(), "-shared", "-o", LIB] + objs + ["-lcudart"]
+    link = [_nvcc(), "-shared", "-o", LIB] + objs + ["-lcudart", "-lpthread", "-ldl"]
     subprocess.check_call(link)
     return LIB
 

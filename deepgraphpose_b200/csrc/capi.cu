@@ -756,6 +756,8 @@ void dgp_destroy(dgp_handle* h) {
   cudaFree(h->loss_ws.p);
   cudaFree(h->st_frames2[0].p);
   cudaFree(h->st_frames2[1].p);
+  for (int i = 0; i < 3; ++i)
+    if (h->ring_slot[i]) cudaFreeHost(h->ring_slot[i]);
   for (int i = 0; i < 2; ++i) {
     if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
     if (h->ev_consumed[i]) cudaEventDestroy(h->ev_consumed[i]);

@@ -143,6 +143,9 @@ struct dgp_handle {
   cudaStream_t copy_stream = nullptr;  // H2D of the next batch overlaps the current batch's kernels
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
   DevBuf st_frames2[2], st_logits, st_mu, st_peak, st_lik;
+  // dgp_estimate_pose_stream: pinned host ring the reader thread decodes into (stream.cu)
+  void* ring_slot[3] = {nullptr, nullptr, nullptr};
+  size_t ring_bytes = 0;
 };
 
 // loss forward (+ optional loss-side backward) shared by dgp_loss_forward / dgp_loss_backward / the training step

@@ -19,6 +19,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <functional>
 
@@ -37,6 +39,7 @@ struct BStep {
 struct Backward {
   std::vector<BStep> steps;
   float *g_logits = nullptr, *g_locref = nullptr;
+  int bucket_step[3] = {-1, -1, -1};  // steps after which buckets 0 (block4 + heads), 1 (block3), 2 (block2) are final
   int early_step = -1;  // number of steps after which the gradients of block4 + heads (the arena's tail) are final
   // The ~280 launches of the network backward have fixed arguments per plan: after the first (eager) step they are
   // replayed as one CUDA graph, which removes the launch gaps between the many small bandwidth-class kernels.
@@ -69,7 +72,22 @@ struct TrainState {
   // caller can start their all-reduce on a side stream while blocks 3..1 are still running.
   cudaEvent_t ev_early = nullptr;
   size_t early_off = 0, early_cnt = 0;
+  // Data-parallel all-reduce owned by the library (dgp_attach_comm / dgp_comm_init_rank + dgp_allreduce_gradients): the
+  // weight gradients of a block are final once the backward has passed its first unit, so the arena is reduced in four
+  // buckets in backward order -- [block4 + heads], [block3], [block2], [conv1 + block1 + gamma/beta/bias] -- each on the
+  // communication stream behind an event recorded at that point of the backward (ev_bucket[0] == ev_early's position).
+  static constexpr int kBuckets = 4;
+  size_t bucket_off[kBuckets + 1] = {0, 0, 0, 0, 0};   // weight-part offsets: bucket k = [bucket_off[k+1], bucket_off[k])
+  cudaEvent_t ev_bucket[kBuckets - 1] = {nullptr, nullptr, nullptr};
+  void* comm = nullptr;           // ncclComm_t
+  bool comm_owned = false;
+  int comm_world = 1;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_bwd_done = nullptr, ev_comm_done = nullptr;   // timing enabled: exposed all-reduce time
+  bool bwd_ran = false;           // a backward has recorded the bucket events on some stream
 };
+
+void comm_release(dgp_handle* h);
 
 void train_destroy(dgp_handle* h) {
   TrainState* ts = h->train;
@@ -84,8 +102,67 @@ void train_destroy(dgp_handle* h) {
   cudaFree(ts->head_wd);
   cudaFree(ts->wd_jobs);
   if (ts->ev_early) cudaEventDestroy(ts->ev_early);
+  for (cudaEvent_t e : ts->ev_bucket) if (e) cudaEventDestroy(e);
+  if (ts->ev_bwd_done) cudaEventDestroy(ts->ev_bwd_done);
+  if (ts->ev_comm_done) cudaEventDestroy(ts->ev_comm_done);
+  comm_release(h);
+  if (ts->comm_stream) cudaStreamDestroy(ts->comm_stream);
   delete ts;
   h->train = nullptr;
+}
+
+// ---- NCCL, resolved at run time from the process (the copy PyTorch loaded, if any) or the system library: the .so has no
+// link-time NCCL dependency, and a host that never calls dgp_attach_comm / dgp_comm_init_rank never needs it.
+namespace nccl {
+typedef struct { char internal[128]; } UniqueId;     // ncclUniqueId (NCCL_UNIQUE_ID_BYTES = 128)
+typedef int (*GetUniqueIdFn)(UniqueId*);
+typedef int (*CommInitRankFn)(void**, int, UniqueId, int);
+typedef int (*CommDestroyFn)(void*);
+typedef int (*CommCountFn)(void*, int*);
+typedef int (*AllReduceFn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*GroupFn)();
+typedef const char* (*ErrStrFn)(int);
+constexpr int kFloat = 7, kSum = 0;                  // ncclFloat32, ncclSum
+struct Api {
+  GetUniqueIdFn get_unique_id = nullptr;
+  CommInitRankFn comm_init_rank = nullptr;
+  CommDestroyFn comm_destroy = nullptr;
+  CommCountFn comm_count = nullptr;
+  AllReduceFn all_reduce = nullptr;
+  GroupFn group_start = nullptr, group_end = nullptr;
+  ErrStrFn err_str = nullptr;
+  bool ok = false;
+};
+const Api& api() {
+  static Api a;
+  static bool tried = false;
+  if (tried) return a;
+  tried = true;
+  void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);   // already in the process (torch's bundled NCCL)
+  if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) return a;
+  a.get_unique_id = (GetUniqueIdFn)dlsym(lib, "ncclGetUniqueId");
+  a.comm_init_rank = (CommInitRankFn)dlsym(lib, "ncclCommInitRank");
+  a.comm_destroy = (CommDestroyFn)dlsym(lib, "ncclCommDestroy");
+  a.comm_count = (CommCountFn)dlsym(lib, "ncclCommCount");
+  a.all_reduce = (AllReduceFn)dlsym(lib, "ncclAllReduce");
+  a.group_start = (GroupFn)dlsym(lib, "ncclGroupStart");
+  a.group_end = (GroupFn)dlsym(lib, "ncclGroupEnd");
+  a.err_str = (ErrStrFn)dlsym(lib, "ncclGetErrorString");
+  a.ok = a.get_unique_id && a.comm_init_rank && a.comm_destroy && a.comm_count && a.all_reduce && a.group_start &&
+         a.group_end && a.err_str;
+  return a;
+}
+}  // namespace nccl
+
+void comm_release(dgp_handle* h) {
+  TrainState* ts = h->train;
+  if (!ts || !ts->comm) return;
+  if (ts->comm_owned && nccl::api().ok) nccl::api().comm_destroy(ts->comm);
+  ts->comm = nullptr;
+  ts->comm_owned = false;
+  ts->comm_world = 1;
 }
 
 namespace {
@@ -295,6 +372,9 @@ int build_backward(dgp_handle* h, Plan* pl) {
     }
     gi = (gi + 1) % 3;
     if (ts->early_cnt > 0 && u.shortcut >= 0 && h->layers[u.shortcut].w_off == ts->early_off) bw->early_step = (int)bw->steps.size();
+    if (u.shortcut >= 0)
+      for (int k = 0; k < 3; ++k)
+        if (h->layers[u.shortcut].w_off == ts->bucket_off[k + 1]) bw->bucket_step[k] = (int)bw->steps.size();
   }
   // ---- root: max-pool backward, conv1 ReLU/BN, conv1 wgrad (no dgrad: the input is the image)
   {
@@ -404,6 +484,19 @@ int dgp_train_enable(dgp_handle* h) {
       ts->early_cnt = h->n_w - ts->early_off;
       break;
     }
+  {
+    // bucket k = the weight gradients of one block (k = 0: block4 + heads ... k = 3: conv1 + block1 + the BN / bias tail)
+    const char* first[3] = {"/block4/unit_1/", "/block3/unit_1/", "/block2/unit_1/"};
+    ts->bucket_off[0] = h->n_w;
+    for (int k = 0; k < 3; ++k)
+      for (const UnitDesc& u : h->units)
+        if (u.scope.find(first[k]) != std::string::npos && u.shortcut >= 0) ts->bucket_off[k + 1] = h->layers[u.shortcut].w_off;
+    ts->bucket_off[4] = 0;
+    for (int k = 0; k < 3; ++k) CU_OK(h, cudaEventCreateWithFlags(&ts->ev_bucket[k], cudaEventDisableTiming));
+    CU_OK(h, cudaEventCreate(&ts->ev_bwd_done));
+    CU_OK(h, cudaEventCreate(&ts->ev_comm_done));
+    CU_OK(h, cudaStreamCreateWithFlags(&ts->comm_stream, cudaStreamNonBlocking));
+  }
   ts->head_Kd = ceil_div(std::max(9 * h->ctot, h->layers[h->head_layer].Npad), 64) * 64;
   CU_OK(h, cudaMalloc(&ts->head_wd, (size_t)2048 * ts->head_Kd * sizeof(W16)));
   return DGP_OK;
@@ -449,10 +542,14 @@ int dgp_train_forward_backward(dgp_handle* h, const uint8_t* frames_dev, int nt,
     for (const BStep& st : bw->steps) {
       ce = st.run(h->stream);
       if (ce != cudaSuccess) break;
-      if (++k == bw->early_step) {
+      ++k;
+      if (k == bw->early_step) {
         ce = cudaEventRecordWithFlags(ts->ev_early, h->stream, cudaEventRecordExternal);
         if (ce != cudaSuccess) break;
       }
+      for (int b = 0; b < 3 && ce == cudaSuccess; ++b)
+        if (k == bw->bucket_step[b]) ce = cudaEventRecordWithFlags(ts->ev_bucket[b], h->stream, cudaEventRecordExternal);
+      if (ce != cudaSuccess) break;
     }
     cudaError_t ee = cudaStreamEndCapture(h->stream, &graph);
     if (ce == cudaSuccess) ce = ee;
@@ -476,9 +573,13 @@ int dgp_train_forward_backward(dgp_handle* h, const uint8_t* frames_dev, int nt,
         CU_OK(h, st.run(s));
       }
       h->launches += st.launches;
-      if (++k == bw->early_step) CU_OK(h, cudaEventRecord(ts->ev_early, s));
+      ++k;
+      if (k == bw->early_step) CU_OK(h, cudaEventRecord(ts->ev_early, s));
+      for (int b = 0; b < 3; ++b)
+        if (k == bw->bucket_step[b]) CU_OK(h, cudaEventRecord(ts->ev_bucket[b], s));
     }
   }
+  ts->bwd_ran = bw->early_step > 0;
   bw->runs++;
   return DGP_OK;
 }
@@ -501,6 +602,9 @@ int dgp_train_early_bucket(dgp_handle* h, size_t* offset_floats, size_t* count_f
 int dgp_train_wait_early_bucket(dgp_handle* h, void* stream) {
   if (!h) return DGP_ERR_INVALID;
   if (!h->train) return fail(h, DGP_ERR_STATE, "dgp_train_wait_early_bucket before dgp_train_enable");
+  if (!h->train->bwd_ran)
+    return fail(h, DGP_ERR_STATE, "dgp_train_wait_early_bucket: no backward pass has recorded the early-bucket event (waiting on a "
+                                  "never-recorded event would not order anything)");
   CU_OK(h, cudaSetDevice(h->device));
   CU_OK(h, cudaStreamWaitEvent((cudaStream_t)stream, h->train->ev_early, 0));
   return DGP_OK;
@@ -678,6 +782,95 @@ int dgp_set_variable(dgp_handle* h, const char* tf_var_name, int what, const flo
     if (h->train) h->train->wd_fresh = false;
     CU_OK(h, cudaDeviceSynchronize());
   }
+  return DGP_OK;
+}
+
+// ---------------------------------------------------------------- data-parallel all-reduce inside the C ABI
+#define NCCL_OK(h, expr)                                                                                       \
+  do {                                                                                                         \
+    int _r = (expr);                                                                                           \
+    if (_r != 0) return fail(h, DGP_ERR_CUDA, "%s failed: %s", #expr, nccl::api().err_str(_r));                \
+  } while (0)
+
+int dgp_comm_unique_id(char* id128) {
+  if (!id128) return DGP_ERR_INVALID;
+  if (!nccl::api().ok) return fail(nullptr, DGP_ERR_UNSUPPORTED, "dgp_comm_unique_id: libnccl.so.2 could not be loaded");
+  nccl::UniqueId id;
+  const int r = nccl::api().get_unique_id(&id);
+  if (r != 0) return fail(nullptr, DGP_ERR_CUDA, "ncclGetUniqueId failed: %s", nccl::api().err_str(r));
+  memcpy(id128, id.internal, 128);
+  return DGP_OK;
+}
+
+int dgp_comm_init_rank(dgp_handle* h, const char* id128, int nranks, int rank) {
+  if (!h) return DGP_ERR_INVALID;
+  if (!h->train) return fail(h, DGP_ERR_STATE, "dgp_comm_init_rank before dgp_train_enable");
+  if (!id128 || nranks < 1 || rank < 0 || rank >= nranks) return fail(h, DGP_ERR_INVALID, "dgp_comm_init_rank: bad argument");
+  if (!nccl::api().ok) return fail(h, DGP_ERR_UNSUPPORTED, "dgp_comm_init_rank: libnccl.so.2 could not be loaded");
+  CU_OK(h, cudaSetDevice(h->device));
+  comm_release(h);
+  nccl::UniqueId id;
+  memcpy(id.internal, id128, 128);
+  void* comm = nullptr;
+  NCCL_OK(h, nccl::api().comm_init_rank(&comm, nranks, id, rank));
+  h->train->comm = comm;
+  h->train->comm_owned = true;
+  h->train->comm_world = nranks;
+  return DGP_OK;
+}
+
+int dgp_attach_comm(dgp_handle* h, void* nccl_comm) {
+  if (!h) return DGP_ERR_INVALID;
+  if (!h->train) return fail(h, DGP_ERR_STATE, "dgp_attach_comm before dgp_train_enable");
+  comm_release(h);
+  if (!nccl_comm) return DGP_OK;   // detach
+  if (!nccl::api().ok) return fail(h, DGP_ERR_UNSUPPORTED, "dgp_attach_comm: libnccl.so.2 could not be loaded");
+  int n = 0;
+  NCCL_OK(h, nccl::api().comm_count(nccl_comm, &n));
+  h->train->comm = nccl_comm;
+  h->train->comm_owned = false;
+  h->train->comm_world = n;
+  return DGP_OK;
+}
+
+int dgp_comm_world_size(dgp_handle* h) { return (h && h->train && h->train->comm) ? h->train->comm_world : 1; }
+
+int dgp_allreduce_gradients(dgp_handle* h, void* stream, float* grad_scale) {
+  if (!h) return DGP_ERR_INVALID;
+  if (!h->train) return fail(h, DGP_ERR_STATE, "dgp_allreduce_gradients before dgp_train_enable");
+  TrainState* ts = h->train;
+  if (grad_scale) *grad_scale = 1.0f / (float)ts->comm_world;
+  if (!ts->comm || ts->comm_world == 1) return DGP_OK;
+  if (!ts->bwd_ran) return fail(h, DGP_ERR_STATE, "dgp_allreduce_gradients: no backward pass has run");
+  CU_OK(h, cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream, cs = ts->comm_stream;
+  const nccl::Api& nc = nccl::api();
+  CU_OK(h, cudaEventRecord(ts->ev_bwd_done, s));                    // the end of the backward on the caller's stream
+  for (int k = 0; k < 3; ++k) {                                      // buckets that were final before the backward ended
+    const size_t lo = ts->bucket_off[k + 1], hi = ts->bucket_off[k];
+    if (hi <= lo) continue;
+    CU_OK(h, cudaStreamWaitEvent(cs, ts->ev_bucket[k], 0));
+    NCCL_OK(h, nc.all_reduce(ts->grads + lo, ts->grads + lo, hi - lo, nccl::kFloat, nccl::kSum, ts->comm, cs));
+  }
+  CU_OK(h, cudaStreamWaitEvent(cs, ts->ev_bwd_done, 0));             // conv1 + block1 weights, then gamma / beta / head bias
+  NCCL_OK(h, nc.group_start());
+  if (ts->bucket_off[3] > 0)
+    NCCL_OK(h, nc.all_reduce(ts->grads, ts->grads, ts->bucket_off[3], nccl::kFloat, nccl::kSum, ts->comm, cs));
+  NCCL_OK(h, nc.all_reduce(ts->grads + h->n_w, ts->grads + h->n_w, h->n_params - h->n_w, nccl::kFloat, nccl::kSum, ts->comm, cs));
+  NCCL_OK(h, nc.group_end());
+  CU_OK(h, cudaEventRecord(ts->ev_comm_done, cs));
+  CU_OK(h, cudaStreamWaitEvent(s, ts->ev_comm_done, 0));             // the optimizer step on `s` follows the reduced gradients
+  return DGP_OK;
+}
+
+int dgp_allreduce_exposed_ms(dgp_handle* h, float* ms) {
+  if (!h || !ms) return DGP_ERR_INVALID;
+  if (!h->train) return fail(h, DGP_ERR_STATE, "dgp_allreduce_exposed_ms before dgp_train_enable");
+  *ms = 0.0f;
+  if (!h->train->comm || h->train->comm_world == 1) return DGP_OK;
+  CU_OK(h, cudaSetDevice(h->device));
+  CU_OK(h, cudaEventSynchronize(h->train->ev_comm_done));
+  CU_OK(h, cudaEventElapsedTime(ms, h->train->ev_bwd_done, h->train->ev_comm_done));
   return DGP_OK;
 }
 

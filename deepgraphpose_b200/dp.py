@@ -27,12 +27,54 @@ def allreduce_flat_(flat, group=None, buckets=BUCKETS):
     return 1.0 / world
 
 
+def attach_comm(engine, group=None):
+    """Give the engine's C handle its own NCCL communicator over the ranks of ``group`` (dgp_comm_unique_id on rank 0, the
+    128-byte id broadcast through torch.distributed -- plumbing only --, dgp_comm_init_rank everywhere).  From then on
+    ``allreduce_gradients`` is one C call (dgp_allreduce_gradients): four buckets in backward order on the handle's
+    communication stream, overlapped with the backward pass; torch.distributed is no longer on the data path.
+    Returns the world size.  A no-op (returns 1) without an initialised process group or on CPU-only groups."""
+    import ctypes as C
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return 1
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    engine.train_enable()
+    ident = C.create_string_buffer(128)
+    if rank == 0:
+        from ._lib import check
+        check(engine.lib.dgp_comm_unique_id(ident))
+    box = [bytes(ident.raw)]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    engine._check(engine.lib.dgp_comm_init_rank(engine.h, box[0], world, rank))
+    engine._c_comm = True
+    return world
+
+
+def ensure_comm(engine, group=None):
+    """attach_comm once per engine, when the process group runs on NCCL (CUDA ranks); gloo / CPU groups keep the
+    torch.distributed path."""
+    if getattr(engine, "_c_comm", None) is not None:
+        return
+    engine._c_comm = False
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1 and \
+            "nccl" in str(dist.get_backend(group)).lower():
+        attach_comm(engine, group)
+
+
 def allreduce_gradients(engine, group=None, overlap=True):
     """All-reduce the engine's gradient buffer across ranks; returns grad_scale for Engine.optimizer_step.
+
+    With a communicator attached to the C handle (``attach_comm``) this is ``dgp_allreduce_gradients``; otherwise the
+    torch.distributed path below (NCCL or, for the CPU tests, gloo).
 
     With ``overlap`` the slice holding block4 + the heads (two thirds of the buffer, final after the first quarter of the
     backward pass) is reduced on a side stream that waits on the handle's early-bucket event, i.e. while the GPU is still
     differentiating blocks 3..1; the rest follows on the compute stream once the backward is done."""
+    if getattr(engine, "_c_comm", False):
+        import ctypes as C
+        from .engine import _stream
+        scale = C.c_float(1.0)
+        engine._check(engine.lib.dgp_allreduce_gradients(engine.h, _stream(engine.device), C.byref(scale)))
+        return float(scale.value)
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return 1.0
     buf = engine.grad_buffer()

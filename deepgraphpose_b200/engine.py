@@ -297,6 +297,64 @@ class Engine:
                                                     _ptr(mu), _ptr(peak), _ptr(lik)))
         return mu, peak, lik
 
+    def estimate_pose_stream(self, source, H, W, max_frames, batch=16, gamma=1.0, gauss_len=1.0, start=0):
+        """Streaming estimate_pose (dgp_estimate_pose_stream): host memory is bounded by a ring of 3 pinned slots of `batch`
+        frames, whatever the length of the video.  ``source`` is either
+
+        * an iterator / generator yielding uint8 (H,W,3) RGB frames (a video decoder): frames are written into the pinned
+          slot by a reader thread while the GPU works on the previous slots, or
+        * a uint8 CPU tensor (P,H,W,3) (pinned for asynchronous copies): a video of ``max_frames`` frames that cycles over
+          these P frames, served zero-copy by the library's own ``dgp_cyclic_reader`` (synthetic videos, bench.py);
+          ``start`` is the index of the first frame to serve (frame t of the video is ``source[t % P]``), which lets every
+          rank of a sharded run read its own contiguous range of the same video.
+
+        Returns (mu (T,nj,2) f32, peak (T,nj,2) i32, lik (T,nj) f32) as CPU tensors, T = frames actually delivered."""
+        T = int(max_frames)
+        mu = torch.empty((T, self.nj, 2), dtype=torch.float32).pin_memory()
+        peak = torch.empty((T, self.nj, 2), dtype=torch.int32).pin_memory()
+        lik = torch.empty((T, self.nj), dtype=torch.float32).pin_memory()
+        done = C.c_int64(0)
+        frame_bytes = int(H) * int(W) * 3
+        if isinstance(source, torch.Tensor):
+            if source.is_cuda or source.dtype != torch.uint8 or source.dim() != 4 or tuple(source.shape[1:]) != (H, W, 3):
+                raise ValueError("a tensor source must be a uint8 CPU tensor (P,%d,%d,3)" % (H, W))
+            pool = source.contiguous()
+            src = _lib.DgpCyclicSource(pool.data_ptr(), pool.shape[0], int(start) + T, int(start), frame_bytes)
+            reader, user, keep = C.cast(self.lib.dgp_cyclic_reader, C.c_void_p), C.cast(C.pointer(src), C.c_void_p), (pool, src)
+        else:
+            it = iter(source)
+            state = {"error": None}
+
+            def _read(user_, slot, want, direct):
+                try:
+                    dst = np.ctypeslib.as_array(C.cast(slot, C.POINTER(C.c_uint8)), shape=(want, H, W, 3))
+                    n = 0
+                    for n in range(1, want + 1):
+                        try:
+                            fr = next(it)
+                        except StopIteration:
+                            n -= 1
+                            break
+                        fr = np.asarray(fr)
+                        if fr.shape != (H, W, 3) or fr.dtype != np.uint8:
+                            raise ValueError("the source must yield uint8 frames of shape (%d, %d, 3), got %s %s"
+                                             % (H, W, fr.dtype, fr.shape))
+                        dst[n - 1] = fr
+                    return n
+                except Exception as ex:  # never unwind through the C frame
+                    state["error"] = ex
+                    return -1
+
+            cb = _lib.FRAME_READER(_read)
+            reader, user, keep = C.cast(cb, C.c_void_p), C.c_void_p(0), (cb, state)
+        status = self.lib.dgp_estimate_pose_stream(self.h, reader, user, int(H), int(W), int(batch), float(gamma),
+                                                   float(gauss_len), T, _ptr(mu), _ptr(peak), _ptr(lik), C.byref(done))
+        if not isinstance(source, torch.Tensor) and keep[1]["error"] is not None:
+            raise keep[1]["error"]
+        self._check(status)
+        n = int(done.value)
+        return mu[:n], peak[:n], lik[:n]
+
     # ------------------------------------------------------------------ training (fit_dgp's train_op)
     def train_enable(self):
         if not getattr(self, "_train", False):
@@ -339,6 +397,12 @@ class Engine:
     def wait_early_bucket(self, stream):
         """Make the torch.cuda.Stream `stream` wait until the early bucket of the last training step is final."""
         self._check(self.lib.dgp_train_wait_early_bucket(self.h, C.c_void_p(stream.cuda_stream)))
+
+    def allreduce_exposed_ms(self):
+        """Milliseconds between the end of the last backward pass and the end of its C-side gradient all-reduce."""
+        v = C.c_float()
+        self._check(self.lib.dgp_allreduce_exposed_ms(self.h, C.byref(v)))
+        return float(v.value)
 
     def grad_norm(self):
         v = C.c_float()

@@ -95,10 +95,125 @@ def estimate_pose_frames(engine, frames, batch=16, gamma=1.0, gauss_len=1.0, str
             "mu_likelihoods": peak.numpy().astype("int"), "markers": markers}
 
 
+def _readout_dict(mu, peak, lik, stride):
+    markers = mu.numpy().astype(np.float64)
+    return {"x": markers[:, :, 1] * stride + 0.5 * stride, "y": markers[:, :, 0] * stride + 0.5 * stride,
+            "likelihoods": lik.numpy().astype(np.float64), "mu_likelihoods": peak.numpy().astype("int"), "markers": markers}
+
+
+def estimate_pose_stream(engine, source, H, W, n_frames=None, batch=16, gamma=1.0, gauss_len=1.0, chunk=65536):
+    """The estimate_pose frame loop (eval.py:306-357) over a frame SOURCE instead of an in-memory array: an iterator of uint8
+    (H,W,3) RGB frames (video decoder) or a pinned uint8 tensor (P,H,W,3) cycled for ``n_frames`` frames.  Frames stream
+    through a pinned ring of 3 x ``batch`` frames (Engine.estimate_pose_stream): host memory does not grow with the video.
+    ``n_frames`` may be None for iterators of unknown length (results are collected ``chunk`` frames at a time)."""
+    parts = []
+    if isinstance(source, torch.Tensor):
+        if n_frames is None:
+            n_frames = source.shape[0]
+        parts.append(engine.estimate_pose_stream(source, H, W, n_frames, batch, gamma, gauss_len))
+    else:
+        it = iter(source)
+        left = None if n_frames is None else int(n_frames)
+        while left is None or left > 0:
+            want = chunk if left is None else min(chunk, left)
+            mu, peak, lik = engine.estimate_pose_stream(it, H, W, want, batch, gamma, gauss_len)
+            parts.append((mu, peak, lik))
+            if left is not None:
+                left -= mu.shape[0]
+            if mu.shape[0] < want:
+                break
+    mu, peak, lik = (torch.cat([p[i] for p in parts]) for i in range(3))
+    return _readout_dict(mu, peak, lik, engine.stride)
+
+
+def estimate_pose_sharded(engine, source, T, H, W, edges=(), ws=None, ws_max=None, wt_max=0.0, batch=16, gamma=1.0,
+                          gauss_len=1.0, group=None, gather=True):
+    """estimate_pose over a T-frame video sharded contiguously by frame over the ranks of ``group`` (one process
+    per GPU): rank r streams frames [a_r, b_r) (``sharding.shard_range``) through its own engine, the ranks exchange the
+    soft-argmax of their first frame (one all_gather of nj*8 bytes per rank) so that the temporal potential at every shard
+    edge uses the exact neighbour, the skeleton / temporal potentials of the shard are evaluated on the device, and the
+    per-frame results are all-gathered back into video order.  The reference has no multi-GPU inference; the per-frame
+    arithmetic is that of estimate_pose (eval.py:306-357) and of the clique terms of dgp_loss (fitdgp.py:1063-1083).
+
+    ``source``: a pinned uint8 tensor (P,H,W,3) cycled as the video (frame t = source[t % P]), or a callable
+    ``(start, stop) -> iterator of frames`` that opens the rank's own range of a real video.
+    Returns the estimate_pose dict plus 'skel' (T,nl), 'temporal' (T,nj; last row 0), 'e_skel', 'e_temp' (T) -- for the
+    whole video on every rank when ``gather`` (else for the rank's shard) -- and 'shard' = (a_r, b_r)."""
+    import torch.distributed as dist
+    from . import sharding
+    on = dist.is_available() and dist.is_initialized()
+    world = dist.get_world_size(group) if on else 1
+    rank = dist.get_rank(group) if on else 0
+    if T < world:
+        raise ValueError("a %d-frame video cannot be sharded over %d ranks" % (T, world))
+    a, b = sharding.shard_range(T, rank, world)
+    if isinstance(source, torch.Tensor):
+        mu, peak, lik = engine.estimate_pose_stream(source, H, W, b - a, batch, gamma, gauss_len, start=a)
+    else:
+        mu, peak, lik = engine.estimate_pose_stream(source(a, b), H, W, b - a, batch, gamma, gauss_len)
+    if mu.shape[0] != b - a:
+        raise RuntimeError("rank %d: the source delivered %d of its %d frames" % (rank, mu.shape[0], b - a))
+    dev = engine.device
+    mu_d = mu.to(dev, non_blocking=True)
+    halo = sharding.exchange_halo(mu_d[0].contiguous(), group) if world > 1 else None
+    edges = [tuple(e) for e in edges]
+    pot = engine.potentials(mu_d, edges, halo_next=halo, ws=ws, ws_max=ws_max, wt_max=wt_max)
+    temporal = pot["temporal"]
+    if temporal.shape[0] < b - a:       # the video's last frame has no successor
+        temporal = torch.cat([temporal, torch.zeros((1, engine.nj), dtype=temporal.dtype, device=dev)])
+    local = {"mu": mu_d, "peak": peak.to(dev, non_blocking=True), "lik": lik.to(dev, non_blocking=True),
+             "temporal": temporal, "skel": pot["skel"].t().contiguous(), "e_temp": pot["e_temp"]}
+    if pot["e_skel"] is not None:
+        local["e_skel"] = pot["e_skel"]
+    full = {k: (sharding.gather_frames(v, T, group) if gather else v) for k, v in local.items()}
+    out = _readout_dict(full["mu"].cpu(), full["peak"].cpu(), full["lik"].cpu(), engine.stride)
+    for k in ("temporal", "skel", "e_temp", "e_skel"):
+        if k in full:
+            out[k] = full[k].cpu().numpy()
+    out["shard"] = (a, b)
+    return out
+
+
+def _video_source(video_file, new_size=None, crop_size=None):
+    """(frame iterator, H, W, frame count or None, scale_x, scale_y) for a video file: frames are decoded one at a time
+    (OpenCV), resized / cropped the way the reference does per frame (eval.py:309-326), and never held beyond the ring."""
+    import cv2
+    cap = cv2.VideoCapture(str(video_file))
+    if not cap.isOpened():
+        raise IOError("cannot open video %s" % video_file)
+    w0, h0 = int(cap.get(cv2.CAP_PROP_FRAME_WIDTH)), int(cap.get(cv2.CAP_PROP_FRAME_HEIGHT))
+    count = int(cap.get(cv2.CAP_PROP_FRAME_COUNT))
+    cap.release()
+    scale_x = scale_y = 1.0
+    H, W = h0, w0
+    if new_size is not None:
+        scale_x, scale_y = w0 / new_size[1], h0 / new_size[0]
+        H, W = int(new_size[0]), int(new_size[1])
+    if crop_size is not None:
+        W, H = int(crop_size[2] - crop_size[0]), int(crop_size[3] - crop_size[1])
+
+    def frames():
+        if new_size is None and crop_size is None:
+            yield from _iter_video(video_file)
+            return
+        from PIL import Image
+        for fr in _iter_video(video_file):
+            im = Image.fromarray(np.ascontiguousarray(fr))
+            if new_size is not None:
+                im = im.resize(size=(new_size[1], new_size[0]))
+            if crop_size is not None:
+                im = im.crop(crop_size)
+            yield np.asarray(im)
+
+    return frames(), H, W, (count if count > 0 else None), scale_x, scale_y
+
+
 def estimate_pose(proj_cfg_file, dgp_model_file, video_file, output_dir, shuffle=1, save_pose=True, save_str="",
                   new_size=None, crop_size=None, batch=16):
     """eval.py:217-372.  ``proj_cfg_file`` may be a dict-like dlc_cfg (num_joints, stride, ...) or a DLC project yaml with
-    ``bodyparts``; ``video_file`` a path or a uint8 array (T,H,W,3).  Returns {'x','y','likelihoods'} (T,nj) each."""
+    ``bodyparts``; ``video_file`` a path or a uint8 array (T,H,W,3).  Returns {'x','y','likelihoods'} (T,nj) each.
+    A video file is STREAMED: decoded frame by frame (as the reference's ``clip.iter_frames()``, eval.py:306) into a pinned
+    ring that the GPU drains batch by batch, so a 100 k-frame clip needs no more host memory than a 100-frame one."""
     if isinstance(proj_cfg_file, (dict,)) or hasattr(proj_cfg_file, "num_joints"):
         dlc_cfg = proj_cfg_file
     else:
@@ -107,31 +222,34 @@ def estimate_pose(proj_cfg_file, dgp_model_file, video_file, output_dir, shuffle
             proj = yaml.safe_load(stream)
         dlc_cfg = {"num_joints": len(proj["bodyparts"]), "all_joints_names": list(proj["bodyparts"]), "stride": 8.0}
     save_file = None
+    scale_x = scale_y = 1.0
     if isinstance(video_file, (str, os.PathLike)):
         f = os.path.basename(str(video_file)).rsplit(".", 1)
         save_file = os.path.join(str(output_dir), f[0] + "_labeled%s" % save_str)
         if os.path.exists(save_file + ".csv"):
             print("labels already exist! video at %s will not be processed" % video_file)
             return save_file + ".csv"
-        frames = np.stack(list(_iter_video(video_file)))
+        source, H, W, n_frames, scale_x, scale_y = _video_source(video_file, new_size, crop_size)
+        sess, mu_n, _, scmap, _, inputs = setup_dgp_eval_graph(dlc_cfg, dgp_model_file)
+        # the container's frame count is a hint only (it can be off by a few frames): read until the decoder runs dry
+        res = estimate_pose_stream(sess.engine, source, H, W, None, batch=batch)
     else:
         frames = np.asarray(video_file)
-    scale_x = scale_y = 1.0
-    if new_size is not None or crop_size is not None:
-        from PIL import Image
-        out = []
-        for fr in frames:
-            im = Image.fromarray(fr)
-            if new_size is not None:
-                scale_x = im.width / new_size[1]
-                scale_y = im.height / new_size[0]
-                im = im.resize(size=(new_size[1], new_size[0]))
-            if crop_size is not None:
-                im = im.crop(crop_size)
-            out.append(np.asarray(im))
-        frames = np.stack(out)
-    sess, mu_n, _, scmap, _, inputs = setup_dgp_eval_graph(dlc_cfg, dgp_model_file)
-    res = estimate_pose_frames(sess.engine, frames, batch=batch)
+        if new_size is not None or crop_size is not None:
+            from PIL import Image
+            out = []
+            for fr in frames:
+                im = Image.fromarray(fr)
+                if new_size is not None:
+                    scale_x = im.width / new_size[1]
+                    scale_y = im.height / new_size[0]
+                    im = im.resize(size=(new_size[1], new_size[0]))
+                if crop_size is not None:
+                    im = im.crop(crop_size)
+                out.append(np.asarray(im))
+            frames = np.stack(out)
+        sess, mu_n, _, scmap, _, inputs = setup_dgp_eval_graph(dlc_cfg, dgp_model_file)
+        res = estimate_pose_frames(sess.engine, frames, batch=batch)
     sess.close()
     labels = {"x": res["x"] * scale_x, "y": res["y"] * scale_y, "likelihoods": res["likelihoods"]}
     if save_pose and save_file is not None:

@@ -21,6 +21,10 @@ LOSS_KEYS = ("visible_loss_pred", "hidden_loss_pred", "visible_loss_locref", "ws
 PLACEHOLDER_KEYS = ("inputs", "targets", "locref_map", "locref_mask", "visible_marker_pl", "hidden_marker_pl",
                     "visible_marker_in_targets_pl", "wt_batch_mask_pl", "vector_field_tf", "nt_batch_pl", "wt_batch_pl",
                     "alpha_tf")
+# One placeholder beyond the reference's twelve: feeding the batch positions of the visible frames (fit_dgp's own
+# `visible_frame_within_batch`, fitdgp.py:763) INSTEAD of locref_map / locref_mask makes the device build the two maps
+# (coord2map feeder kernel) rather than copying 2 x (nt,H,W,2nj) float64 arrays from the host every step.
+EXTRA_PLACEHOLDER_KEYS = ("visible_frame_within_batch",)
 
 
 def _get(cfg, key, default=None):
@@ -68,8 +72,15 @@ def _loss_args(dev, feed, cfg, edges, ws, ws_max, n_frames_total, n_visible_fram
     """(dgp_loss_cfg, dgp_loss_batch, keep-alive list) from the reference's feed_dict values (fitdgp.py:797-815).
     When the feed carries ``visible_frame_within_batch`` instead of ``locref_map`` / ``locref_mask``, the two maps are
     generated on the device (Engine.locref_targets, the coord2map feeder) instead of being copied from the host."""
-    f32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32), device=dev)
-    i32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32), device=dev)
+    def f32(a):   # host arrays are uploaded; CUDA tensors (feeds produced on the device) are used in place
+        if isinstance(a, torch.Tensor):
+            return a.to(device=dev, dtype=torch.float32).contiguous()
+        return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32), device=dev)
+
+    def i32(a):
+        if isinstance(a, torch.Tensor):
+            return a.to(device=dev, dtype=torch.int32).contiguous()
+        return torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32), device=dev)
     targets = f32(np.asarray(feed["targets"]).reshape(-1, nj, 2))
     vis, hid, vit = i32(feed["visible_marker_pl"]), i32(feed["hidden_marker_pl"]), i32(feed["visible_marker_in_targets_pl"])
     keep = [targets, vis, hid, vit]
@@ -100,6 +111,8 @@ def _loss_args(dev, feed, cfg, edges, ws, ws_max, n_frames_total, n_visible_fram
     wt = float(_get(cfg, "wt", 0.0))
     if wt > 0:
         vf = f32(feed["vector_field_tf"])
+        if vf.dim() != 3 or vf.shape[0] != nt - 1:
+            raise ValueError("vector_field_tf must be (nt-1, Hin, Win) = (%d, ., .), got %s" % (nt - 1, tuple(vf.shape)))
         wb = f32(np.asarray(feed["wt_batch_pl"], dtype=np.float32) * np.asarray(feed["wt_batch_mask_pl"], dtype=np.float32))
         keep += [vf, wb]
         b.vector_field_dev, b.Hin, b.Win, b.wt_batch_dev = vf.data_ptr(), vf.shape[1], vf.shape[2], wb.data_ptr()
@@ -198,7 +211,7 @@ def dgp_loss(data_batcher, dgp_cfg, variables=None, device=None):
         hd.graph = graph
     total_loss_visible = Handle("total_loss_visible", "total_loss_visible")
     total_loss_visible.graph = graph
-    placeholders = {k: Handle(k, k) for k in PLACEHOLDER_KEYS}
+    placeholders = {k: Handle(k, k) for k in PLACEHOLDER_KEYS + EXTRA_PLACEHOLDER_KEYS}
     return loss, loss["total_loss"], total_loss_visible, placeholders
 
 
@@ -233,6 +246,9 @@ class TrainSession:
         from . import dp
         feed = {}
         for k, v in feed_dict.items():
+            if isinstance(k, str) and k in self.ph:     # plain placeholder names are accepted as keys too
+                feed[k] = v
+                continue
             for name, hd in self.ph.items():
                 if k is hd:
                     feed[name] = v
@@ -261,10 +277,14 @@ class TrainSession:
                 if not lr:
                     raise ValueError("feed_dict must provide the learning_rate placeholder")
                 lr = lr[0]
-            vals = train_forward_backward(g.engine, frames, feed, g.cfg, g.edges, g.ws, g.ws_max, g.n_frames_total,
-                                          g.n_visible_frames_total, visible_only=op.visible_only)
+            # nothing blocks the host between the backward, the gradient all-reduce (whose first bucket overlaps the rest of
+            # the backward on a side stream) and the optimizer: the six loss values are read only after all three are enqueued
+            out = train_forward_backward(g.engine, frames, feed, g.cfg, g.edges, g.ws, g.ws_max, g.n_frames_total,
+                                         g.n_visible_frames_total, visible_only=op.visible_only, sync=False)
+            dp.ensure_comm(g.engine, op.group)      # NCCL process group: the C handle owns the all-reduce from here on
             scale = dp.allreduce_gradients(g.engine, op.group)
             g.engine.optimizer_step(float(lr), op.momentum, op.clip_norm, scale)
+            vals = dict(zip(LOSS_KEYS, [np.float32(v) for v in out.cpu().numpy()]))
         else:
             pred, locref = g.engine.forward(frames)
             vals, _ = loss_forward(g.engine, pred, locref, feed, g.cfg, g.edges, g.ws, g.ws_max, g.n_frames_total,

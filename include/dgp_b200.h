@@ -201,6 +201,30 @@ int dgp_loss_backward(dgp_handle* h, const dgp_loss_cfg* cfg, const dgp_loss_bat
 int dgp_estimate_pose_host(dgp_handle* h, const uint8_t* frames_host, int T, int H, int W, int batch, float gamma,
                            float gauss_len, float* mu_host, int32_t* peak_host, float* lik_host);
 
+/* Streaming form of the estimate_pose frame loop (eval.py:256, 306-345: `for frame in clip.iter_frames()`), for videos that
+ * do not fit in host memory.  A reader thread owned by the call asks `reader` for up to `max_frames` frames at a time and
+ * stages them in a ring of 3 pinned host slots of `batch` frames; the calling thread copies filled slots to the device and
+ * runs dgp_forward + dgp_softargmax on them, so decode, H2D and compute overlap and host memory is bounded by the ring.
+ *  reader(user, slot, max_frames, &direct): write n <= max_frames uint8 (H,W,3) RGB frames into `slot` (pinned) and return n,
+ *    or leave `slot` alone, point *direct at n frames the source already holds in (ideally pinned) host memory, and return n;
+ *    return 0 at the end of the video, < 0 on error.  It is called from the reader thread, never concurrently.
+ *  max_frames: capacity of the output arrays (frames beyond it are not read); *frames_done receives the number processed.
+ *  Outputs as in dgp_estimate_pose_host.  Synchronous: returns when every result is in the host arrays. */
+typedef int (*dgp_frame_reader)(void* user, uint8_t* slot, int max_frames, const uint8_t** direct);
+int dgp_estimate_pose_stream(dgp_handle* h, dgp_frame_reader reader, void* user, int H, int W, int batch, float gamma,
+                             float gauss_len, int64_t max_frames, float* mu_host, int32_t* peak_host, float* lik_host,
+                             int64_t* frames_done);
+/* A ready-made reader for frames already resident in (pinned) host memory, e.g. a decoded clip kept in RAM or bench.py's
+ * synthetic video: serves `total_frames` frames by cycling over pool[0 .. pool_frames) in direct (zero-copy) mode. */
+typedef struct dgp_cyclic_source {
+  const uint8_t* pool;     /* pool_frames frames of frame_bytes each */
+  int64_t pool_frames;
+  int64_t total_frames;    /* length of the video to serve */
+  int64_t position;        /* next frame to serve (start at 0) */
+  size_t frame_bytes;      /* H * W * 3 */
+} dgp_cyclic_source;
+int dgp_cyclic_reader(void* user, uint8_t* slot, int max_frames, const uint8_t** direct);
+
 /* ---- training step (fit_dgp, src/deepgraphpose/models/fitdgp.py:706-713 and :817-818) ----
  * Replaces sess.run([train_op, loss], feed_dict): dgp_train_forward_backward computes the loss and the gradients of
  * total_loss (visible_only = 1: total_loss_visible, fit_dgp_labeledonly fitdgp.py:416) w.r.t. every trainable variable
@@ -233,6 +257,28 @@ int dgp_get_grad_buffer(dgp_handle* h, void** dev_ptr, size_t* bytes);
  * dgp_train_forward_backward, so their ncclAllReduce can run while blocks 3..1 are still being differentiated. */
 int dgp_train_early_bucket(dgp_handle* h, size_t* offset_floats, size_t* count_floats);
 int dgp_train_wait_early_bucket(dgp_handle* h, void* stream);
+/* ---- data-parallel training inside the C ABI (dgp_attach_comm).  The reference's only multi-GPU design averages
+ * tower gradients (src/deepgraphpose/helpers/utils_tf.py:4-39, average_gradients); here one process per GPU owns a handle and
+ * an NCCL communicator, and the library itself all-reduces the flat gradient arena -- no Python, no torch.distributed on the
+ * data path.  NCCL is resolved at run time (dlopen of libnccl.so.2, the copy already in the process if there is one).
+ *  dgp_comm_unique_id: rank 0 creates the 128-byte ncclUniqueId and the host distributes it (MPI, a file, a torch store ...).
+ *  dgp_comm_init_rank: every rank creates the communicator (owned and destroyed by the handle).
+ *  dgp_attach_comm:    alternatively hand over an existing ncclComm_t (not owned; NULL detaches).
+ *  dgp_allreduce_gradients: SUM all-reduce of the gradient arena of the LAST dgp_train_forward_backward in four buckets in
+ *    backward order -- [block4 + heads], [block3], [block2], [conv1 + block1 + gamma / beta / bias] -- on the handle's
+ *    communication stream, each bucket behind an event recorded at the point of the backward pass where it became final, so
+ *    the first three overlap the rest of the backward; `stream` (the stream of the training calls) is made to wait for the
+ *    last one.  *grad_scale receives 1 / world_size for dgp_optimizer_step (mean semantics of average_gradients; replicas stay
+ *    bit-identical because every rank applies the same reduced gradient).  Without a communicator it is a no-op with
+ *    *grad_scale = 1.
+ *  dgp_allreduce_exposed_ms: time between the end of the last backward pass and the end of its all-reduce (the part of the
+ *    communication that was NOT hidden behind compute).  Synchronises with the communication stream. */
+int dgp_comm_unique_id(char* id128);
+int dgp_comm_init_rank(dgp_handle* h, const char* id128, int nranks, int rank);
+int dgp_attach_comm(dgp_handle* h, void* nccl_comm);
+int dgp_comm_world_size(dgp_handle* h);
+int dgp_allreduce_gradients(dgp_handle* h, void* stream, float* grad_scale);
+int dgp_allreduce_exposed_ms(dgp_handle* h, float* ms);
 /* Global gradient norm computed by the last dgp_optimizer_step (after grad_scale, before clipping). Synchronises. */
 int dgp_get_grad_norm(dgp_handle* h, float* norm_host);
 /* Device pointers of the head outputs (nt,2h,2w,nj) / (nt,2h,2w,2nj) written by the last training step at this shape. */

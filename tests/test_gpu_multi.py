@@ -60,6 +60,46 @@ def test_two_gpu_shards_match_single_gpu(tmp_path):
     eng.close()
 
 
+def _sharded_worker(rank, world, port, T, H, W, nj, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from deepgraphpose_b200 import eval as dgp_eval
+    from deepgraphpose_b200 import synthetic
+    from deepgraphpose_b200.engine import Engine
+    frames, _ = synthetic.make_video(T, H, W, nj, seed=22)
+    eng = Engine(nj, location_refinement=False, device=rank)
+    eng.load_weights(synthetic.make_weights(nj, seed=0, location_refinement=False))
+    res = dgp_eval.estimate_pose_sharded(eng, torch.from_numpy(frames).pin_memory(), T, H, W, synthetic.chain_skeleton(nj),
+                                         np.full(nj - 1, 9.0, np.float32), np.full(nj - 1, 70.0, np.float32), 0.0, batch=3)
+    if rank == 0:
+        np.savez(os.path.join(out_dir, "sharded_entry.npz"), **{k: v for k, v in res.items() if k != "shard"})
+    dist.barrier()
+    dist.destroy_process_group()
+    eng.close()
+
+
+def test_estimate_pose_sharded_entry_matches_single_gpu(tmp_path):
+    """eval.estimate_pose_sharded on 2 ranks (streamed host frames -> halo -> potentials -> gather) == the same call on one."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from deepgraphpose_b200 import eval as dgp_eval
+    from deepgraphpose_b200 import synthetic
+    from deepgraphpose_b200.engine import Engine
+    T, H, W, nj = 11, 96, 128, 4
+    mp.spawn(_sharded_worker, args=(2, 29551, T, H, W, nj, str(tmp_path)), nprocs=2, join=True)
+    got = np.load(os.path.join(str(tmp_path), "sharded_entry.npz"))
+    frames, _ = synthetic.make_video(T, H, W, nj, seed=22)
+    eng = Engine(nj, location_refinement=False, device=0)
+    eng.load_weights(synthetic.make_weights(nj, seed=0, location_refinement=False))
+    ref = dgp_eval.estimate_pose_sharded(eng, torch.from_numpy(frames).pin_memory(), T, H, W, synthetic.chain_skeleton(nj),
+                                         np.full(nj - 1, 9.0, np.float32), np.full(nj - 1, 70.0, np.float32), 0.0, batch=4)
+    for k in ("x", "y", "likelihoods", "mu_likelihoods", "markers", "temporal", "skel", "e_skel", "e_temp"):
+        assert np.array_equal(got[k], ref[k]), k
+    eng.close()
+
+
 CHECK_VARS = ("resnet_v1_50/conv1/weights", "resnet_v1_50/block2/unit_1/bottleneck_v1/conv2/weights",
               "resnet_v1_50/block4/unit_3/bottleneck_v1/conv3/BatchNorm/gamma", "pose/part_pred/block4/weights",
               "pose/locref_pred/block4/biases")
@@ -75,7 +115,7 @@ def _train_setup(rank_seed):
     return T, W, frames, batch, edges, cfg, ws, ws_max
 
 
-def _train_worker(rank, world, port, out_dir):
+def _train_worker(rank, world, port, out_dir, c_comm=True):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
@@ -85,6 +125,8 @@ def _train_worker(rank, world, port, out_dir):
     T, W, frames, batch, edges, cfg, ws, ws_max = _train_setup(rank)
     eng = Engine(T.NJ, device=rank)
     eng.load_weights(W)
+    if c_comm:
+        assert dp.attach_comm(eng) == world      # the C handle owns the communicator and the bucketed all-reduce
     fr = torch.from_numpy(frames).cuda(rank)
     for _ in range(2):
         fitdgp.train_forward_backward(eng, fr, batch, cfg, edges, ws, ws_max, 200, 20)
@@ -98,14 +140,16 @@ def _train_worker(rank, world, port, out_dir):
     eng.close()
 
 
-def test_two_gpu_data_parallel_training_matches_mean_gradient(tmp_path):
-    """2 NCCL replicas with different batches, all-reduced gradients, replicated clip + Momentum == one process that
-    averages the two batches' gradients itself (bit for bit: a two-rank sum is order independent)."""
+@pytest.mark.parametrize("c_comm", [True, False], ids=["c-abi-comm", "torch-distributed"])
+def test_two_gpu_data_parallel_training_matches_mean_gradient(tmp_path, c_comm):
+    """2 NCCL replicas with different batches, all-reduced gradients (dgp_allreduce_gradients inside the C ABI, or the
+    torch.distributed path), replicated clip + Momentum == one process that averages the two batches' gradients itself
+    (bit for bit: a two-rank sum is order independent)."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     from deepgraphpose_b200 import fitdgp
     from deepgraphpose_b200.engine import Engine
-    mp.spawn(_train_worker, args=(2, 29541, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_train_worker, args=(2, 29541 + int(c_comm), str(tmp_path), c_comm), nprocs=2, join=True)
     got = np.load(os.path.join(str(tmp_path), "dp.npz"))
     assert bool(got["same"])
     engs, frs = [], []

@@ -14,6 +14,7 @@ from oracle import dgp_ops, pose_net
 pytestmark = pytest.mark.gpu
 
 NJ, NT, HIN, WIN = 4, 3, 64, 96
+LOSS_REL_TOL = 1e-3   # BASELINE.json: DGP loss <= 1e-3 relative
 TRAINABLE = ("/weights", "/BatchNorm/gamma", "/BatchNorm/beta", "/biases")
 
 
@@ -107,19 +108,21 @@ def test_train_forward_matches_inference_forward(trained):
     l2, r2 = eng.forward(trained["frames"])
     assert torch.equal(logits, l2) and torch.equal(locref, r2)
     ref = trained["heads"]["part_pred"].detach()
-    assert (logits.cpu() - ref).abs().max().item() <= 3e-2 * ref.abs().max().item()
+    assert (logits.cpu() - ref).abs().max().item() <= 4e-3 * ref.abs().max().item()
 
 
 def test_loss_of_training_step(trained):
     got, ref = trained["got"], trained["ref_loss"]
-    # heads come from the bf16 network (about 1 % logit noise): total loss within 3 % of the fp32 oracle
-    assert abs(float(got["total_loss"]) - ref["total_loss"]) <= 3e-2 * abs(ref["total_loss"]), (got, ref)
+    # BASELINE.json north_star: DGP loss <= 1e-3 relative (the network runs in the default fp16 storage mode)
+    assert trained["eng"].precision == "fp16"
+    assert abs(float(got["total_loss"]) - ref["total_loss"]) <= LOSS_REL_TOL * abs(ref["total_loss"]), (got, ref)
 
 
 def test_gradients_match_oracle_autograd(trained):
     """Every trainable variable's gradient vs torch autograd through the fp32 oracle (network + dgp_loss).  The GPU path
-    stores activations and activation gradients in bf16, so the comparison is statistical: cosine similarity and relative
-    L2 error per variable.  A wrong tap flip / transpose / mask gives cosine ~ 0."""
+    stores activations and activation gradients in 16 bits (fp16 here, the default), so the comparison is statistical:
+    cosine similarity and relative L2 error per variable (measured: median rel-L2 0.03, max 0.054; what is left is ReLU masks
+    and pool winners taken from rounded activations).  A wrong tap flip / transpose / mask gives cosine ~ 0."""
     eng, ref = trained["eng"], trained["ref_grads"]
     rows, bad = [], []
     for name, g_ref in sorted(ref.items()):
@@ -132,14 +135,13 @@ def test_gradients_match_oracle_autograd(trained):
         cos = float((g * g_ref).sum() / (np.linalg.norm(g) * nr + 1e-30))
         rel = float(np.linalg.norm(g - g_ref) / nr)
         rows.append((name, cos, rel, nr))
-        if not (cos > 0.97 and rel < 0.25):
+        if not (cos > 0.995 and rel < 0.1):
             bad.append((name, cos, rel, nr))
     _report("fp32_oracle", rows)
     worst = sorted(rows, key=lambda r: r[1])[:5]
     assert not bad, "gradient mismatch: %s (worst cosine: %s)" % (bad[:8], worst)
-    # the bulk must be much better than the per-variable floor (measured: median cosine 0.9967, median rel-L2 0.081;
-    # ReLU masks taken from bf16 activations differ from the fp32 oracle's near zero, which compounds over 50 layers)
-    assert np.median([r[1] for r in rows]) > 0.99 and np.median([r[2] for r in rows]) < 0.12, worst
+    # the bulk must be much better than the per-variable bound
+    assert np.median([r[1] for r in rows]) > 0.998 and np.median([r[2] for r in rows]) < 0.05, worst
 
 
 def _report(tag, rows):
@@ -149,29 +151,27 @@ def _report(tag, rows):
             json.dump([dict(name=n, cos=c, rel_l2=r, ref_norm=v) for n, c, r, v in rows], f, indent=1)
 
 
-def test_gradient_error_scales_with_storage_precision():
-    """The gap to the fp32 oracle is storage rounding, not logic: the same kernels with fp16 storage (8x finer mantissa)
-    give ~3x smaller gradient errors (measured: median rel-L2 0.029 / max 0.054 vs 0.081 / 0.153 in bf16; loss scales of
-    1, 1024 and 65536 give the same figures, so the remainder is forward rounding -- ReLU masks and pool winners taken from
-    rounded activations -- not underflow of the activation gradients).  tools/diag_emulation.py shows why a bf16-rounding emulation of
-    the oracle cannot be used instead: rounding-boundary flips decorrelate the two forwards after ~10 layers."""
+def test_bf16_storage_mode_gradients():
+    """The optional bf16 storage mode (not the benchmarked one) through the same kernels: its gap to the fp32 oracle is
+    storage rounding, not logic -- ~3x the fp16 figures (measured: median rel-L2 0.081 / max 0.153 vs 0.029 / 0.054 in fp16;
+    loss 3e-4 .. 7e-3 relative).  tools/diag_emulation.py shows why a bf16-rounding emulation of the oracle cannot be used
+    instead: rounding-boundary flips decorrelate the two forwards after ~10 layers."""
     from deepgraphpose_b200 import fitdgp
     from deepgraphpose_b200.engine import Engine
     W, frames, batch, edges, S0, cfg, ws, ws_max = _setup()
     loss, ref, _ = _oracle_grads(W, frames, batch, S0, cfg, ws, ws_max)
-    eng = Engine(NJ, precision="fp16")
+    eng = Engine(NJ, precision="bf16")
     eng.load_weights(W)
-    eng.set_loss_scale(float(os.environ.get("DGP_TEST_LOSS_SCALE", "1024")))   # keeps small gradients out of fp16's subnormals
     got = fitdgp.train_forward_backward(eng, torch.from_numpy(frames).cuda(), batch, cfg, edges, ws, ws_max, 200, 20)
-    assert abs(float(got["total_loss"]) - loss["total_loss"]) <= 1e-3 * abs(loss["total_loss"])  # BASELINE: loss <= 1e-3 rel
+    assert abs(float(got["total_loss"]) - loss["total_loss"]) <= 3e-2 * abs(loss["total_loss"])
     rows = []
     for name, g_ref in sorted(ref.items()):
         g = eng.get_variable(name, "grad")
         nr = float(np.linalg.norm(g_ref))
         rows.append((name, float((g * g_ref).sum() / (np.linalg.norm(g) * nr + 1e-30)), float(np.linalg.norm(g - g_ref) / nr), nr))
-    _report("fp16_mode", rows)
+    _report("bf16_mode", rows)
     worst = sorted(rows, key=lambda r: -r[2])[:5]
-    assert max(r[2] for r in rows) < 0.1 and np.median([r[2] for r in rows]) < 0.05 and min(r[1] for r in rows) > 0.995, worst
+    assert max(r[2] for r in rows) < 0.25 and np.median([r[2] for r in rows]) < 0.12 and min(r[1] for r in rows) > 0.97, worst
     eng.close()
 
 
@@ -296,7 +296,7 @@ def test_device_side_locref_feeder_gives_the_same_step():
 def test_gradients_other_geometries(cfgcase):
     """Odd input sizes (TF SAME pads of (1,1) in the max-pool, 2n-1 sized stride-2 units, scoremap of odd feature maps),
     5 joints (head matrix padded to 48/144 rows), a network without the locref head, and a batch without visible frames:
-    gradients of every variable vs torch autograd through the fp32 oracle (bf16 thresholds as above)."""
+    gradients of every variable vs torch autograd through the fp32 oracle; loss at the north_star tolerance."""
     from test_gpu_loss import make_batch
     from deepgraphpose_b200 import fitdgp
     from deepgraphpose_b200.engine import Engine
@@ -326,7 +326,7 @@ def test_gradients_other_geometries(cfgcase):
     eng.load_weights(W)
     got = fitdgp.train_forward_backward(eng, torch.from_numpy(frames).cuda(), batch, cfg, edges, ws, ws_max, 200, 20)
     ref_total = float(total.detach()) - (float(loss["visible_loss_locref"].detach()) if not with_loc else 0.0)
-    assert abs(float(got["total_loss"]) - ref_total) <= 3e-2 * abs(ref_total), (got, ref_total)
+    assert abs(float(got["total_loss"]) - ref_total) <= LOSS_REL_TOL * abs(ref_total), (got, ref_total)
     worst = (1.0, None)
     for name, t in sorted(Wt.items()):
         if not t.requires_grad:
@@ -340,20 +340,20 @@ def test_gradients_other_geometries(cfgcase):
             continue
         cos = float((g * g_ref).sum() / (np.linalg.norm(g) * nr + 1e-30))
         worst = min(worst, (cos, name))
-        assert cos > 0.97 and np.linalg.norm(g - g_ref) / nr < 0.3, (name, cos, np.linalg.norm(g - g_ref) / nr)
-    assert worst[0] > 0.97, worst
+        assert cos > 0.99 and np.linalg.norm(g - g_ref) / nr < 0.15, (name, cos, np.linalg.norm(g - g_ref) / nr)
+    assert worst[0] > 0.99, worst
     eng.close()
 
 
 def test_loss_scale_is_transparent():
-    """A power-of-two loss scale only shifts exponents (bf16 storage, no overflow): unscaled gradients, the clipped Momentum
-    update and therefore the weights are bitwise identical to the unscaled run."""
+    """A power-of-two loss scale only shifts exponents: in bf16 storage (fp32's exponent range, nothing under- or overflows)
+    unscaled gradients, the clipped Momentum update and therefore the weights are bitwise identical to the unscaled run."""
     from deepgraphpose_b200 import fitdgp
     from deepgraphpose_b200.engine import Engine
     W, frames, batch, edges, S0, cfg, ws, ws_max = _setup(seed=21)
     res = []
     for scale in (1.0, 256.0):
-        eng = Engine(NJ)
+        eng = Engine(NJ, precision="bf16")
         eng.load_weights(W)
         eng.set_loss_scale(scale)
         fitdgp.train_forward_backward(eng, torch.from_numpy(frames).cuda(), batch, cfg, edges, ws, ws_max, 200, 20)
@@ -406,7 +406,7 @@ def test_checkpoint_resume_is_exact(tmp_path):
 
 def test_training_step_with_temporal_clique():
     """wt > 0 through the whole training step: the temporal clique (optical-flow weighted, gradient through delta and through
-    crop_and_resize's boxes) reaches every variable; gradients vs oracle autograd with the bf16 thresholds."""
+    crop_and_resize's boxes) reaches every variable; loss at the north_star tolerance, gradients vs oracle autograd."""
     from deepgraphpose_b200 import fitdgp
     from deepgraphpose_b200.engine import Engine
     W, frames, batch, edges, S0, cfg0, ws, ws_max = _setup(seed=3)
@@ -426,13 +426,13 @@ def test_training_step_with_temporal_clique():
     eng = Engine(NJ)
     eng.load_weights(W)
     got = fitdgp.train_forward_backward(eng, torch.from_numpy(frames).cuda(), batch, cfg, edges, ws, ws_max, 200, 20)
-    assert abs(float(got["wt_loss"]) - float(loss["wt_loss"].detach())) <= 0.1 * float(loss["wt_loss"].detach()), (got, loss)
-    assert abs(float(got["total_loss"]) - float(total.detach())) <= 3e-2 * float(total.detach())
+    assert abs(float(got["wt_loss"]) - float(loss["wt_loss"].detach())) <= 1e-2 * float(loss["wt_loss"].detach()), (got, loss)
+    assert abs(float(got["total_loss"]) - float(total.detach())) <= LOSS_REL_TOL * float(total.detach()), (got, loss)
     for name in ("pose/part_pred/block4/weights", "resnet_v1_50/block4/unit_3/bottleneck_v1/conv3/weights",
                  "resnet_v1_50/block3/unit_1/bottleneck_v1/conv2/weights", "resnet_v1_50/conv1/weights"):
         g, g_ref = eng.get_variable(name, "grad"), Wt[name].grad.numpy()
         cos = float((g * g_ref).sum() / (np.linalg.norm(g) * np.linalg.norm(g_ref) + 1e-30))
-        assert cos > 0.97, (name, cos)
+        assert cos > 0.99, (name, cos)
     eng.close()
 
 

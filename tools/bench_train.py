@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Training-step benchmark, BASELINE.json configs[3]: DGP semi-supervised step (visible + hidden frames, skeleton clique,
-fwd + bwd + clip/Momentum) in bf16, data-parallel over the ranks torchrun starts (one per GPU, NCCL all-reduce of the flat
+fwd + bwd + clip/Momentum) in the default 16-bit storage mode (fp16), data-parallel over the ranks torchrun starts (one per GPU, NCCL all-reduce of the flat
 gradient buffer).  747x832 frames, nt frames per replica, nj = 4 with the locref head.  Prints one JSON line (rank 0).
 
   python tools/bench_train.py --steps 10 --warmup 3 [--nt 10]
@@ -51,7 +51,7 @@ def cpu_train_step_seconds(nt, H, W, NJ):
     return time.perf_counter() - t0, os.cpu_count()
 
 
-def measure(rank, local_rank, world, steps, warmup, nt, height, width, profile=True):
+def measure(rank, local_rank, world, steps, warmup, nt, height, width, profile=True, precision="fp16", wt=1.0):
     """One data-parallel training benchmark on the already-initialised process group; returns the JSON dict (rank 0) or None."""
     import argparse as _a
     args = _a.Namespace(steps=steps, warmup=warmup, nt=nt, height=height, width=width)
@@ -70,16 +70,30 @@ def measure(rank, local_rank, world, steps, warmup, nt, height, width, profile=T
     S0 = np.zeros((len(edges), NJ))
     for l, (a, b) in enumerate(edges):
         S0[l, a], S0[l, b] = 1.0, -1.0
-    cfg = dict(gm2=1, gm3=3, wt=0.0, wt_max=0.0, wn_visible=5.0, wn_hidden=3.0, gamma=1.0, gauss_len=1.0, lengthscale=1.0,
+    cfg = dict(gm2=1, gm3=3, wt=float(wt), wt_max=0.0, wn_visible=5.0, wn_hidden=3.0, gamma=1.0, gauss_len=1.0, lengthscale=1.0,
                locref_loss_weight=0.05, stride=8.0)
     ws, ws_max = fitdgp.spatial_clique_params([labels], S0, 8.0, 1000.0, 1.2)
-    eng = Engine(NJ, location_refinement=True, device=local_rank)
+    eng = Engine(NJ, location_refinement=True, device=local_rank, precision=precision)
     eng.load_weights(synthetic.make_weights(NJ, seed=0))
     eng.use_graphs(os.environ.get("DGP_TRAIN_GRAPHS", "1") != "0")
+    c_comm = world > 1 and os.environ.get("DGP_DP_TORCH", "0") != "1"
+    if c_comm:
+        dp.attach_comm(eng)     # the C handle owns its NCCL communicator: dgp_allreduce_gradients, 4 buckets in backward order
     frames_host = bench.make_frame_pool(nt, seed=1234 + rank) if (H, W) == (bench.H, bench.W) else \
         synthetic.make_video(nt, H, W, NJ, seed=1234 + rank)[0]
     frames = torch.from_numpy(frames_host).to(dev)
     flops_fwd, _ = bench.conv_flops_per_frame(H, W, NJ, locref=True)
+    flow_pinned = None
+    if wt > 0:
+        # temporal clique (fitdgp.py:1079-1124): vector_field_tf = optical-flow magnitude per consecutive frame pair
+        # (nt-1, Hin, Win).  A synthetic smooth field of the right shape and range stands in for learn_wt's Farneback output;
+        # it is resident on the device for the kernel-level number and copied from pinned host memory every e2e step.
+        yy, xx = np.meshgrid(np.arange(H, dtype=np.float32), np.arange(W, dtype=np.float32), indexing="ij")
+        flow = np.stack([0.9 + 0.8 * np.sin(yy / (37.0 + 3 * t)) * np.cos(xx / (41.0 + 5 * t)) for t in range(nt - 1)]).astype(np.float32)
+        flow_pinned = torch.from_numpy(flow).pin_memory()
+        batch["vector_field_tf"] = flow_pinned.to(dev)
+        batch["wt_batch_pl"] = np.ones(nt - 1, np.float32) * wt
+        batch["wt_batch_mask_pl"] = np.ones(nt - 1, np.float32)
 
     def step():
         out = fitdgp.train_forward_backward(eng, frames, batch, cfg, edges, ws, ws_max, 1000, 100, sync=False)
@@ -117,7 +131,8 @@ def measure(rank, local_rank, world, steps, warmup, nt, height, width, profile=T
 
     def e2e_step():
         fr = frames_pinned.to(dev, non_blocking=True)
-        out = fitdgp.train_forward_backward(eng, fr, batch, cfg, edges, ws, ws_max, 1000, 100, sync=False)
+        b2 = batch if flow_pinned is None else dict(batch, vector_field_tf=flow_pinned.to(dev, non_blocking=True))
+        out = fitdgp.train_forward_backward(eng, fr, b2, cfg, edges, ws, ws_max, 1000, 100, sync=False)
         scale = dp.allreduce_gradients(eng, overlap=os.environ.get("DGP_DP_OVERLAP", "1") != "0")
         eng.optimizer_step(0.005, 0.9, 10.0, scale)
         return out.cpu()      # [loss_eval, _] = sess.run([loss, train_op]) hands the losses to the host
@@ -150,6 +165,7 @@ def measure(rank, local_rank, world, steps, warmup, nt, height, width, profile=T
         eng.set_profiling(False)
         prof = eng.get_profile()
     loss = float(out.cpu()[5])
+    exposed_ms = eng.allreduce_exposed_ms() if c_comm else None
     line = None
     if rank == 0:
         peaks, src = bench.load_peaks()
@@ -162,14 +178,19 @@ def measure(rank, local_rank, world, steps, warmup, nt, height, width, profile=T
         line = {
             "metric": "training frames/sec (DGP semi-supervised step: fwd + bwd + clip/Momentum)", "value": world * n / (ms / 1e3),
             "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "configs[3]: DGP training step, %dx%d, nt=%d frames per replica (%d visible), nj=%d + locref, gm2=1 gm3=3 ws=1000 wt=0"
-                                   % (H, W, nt, len(vis), NJ), "parallelism": "dp%d, NCCL all-reduce of the 94 MB fp32 gradient buffer in %d buckets" % (world, dp.BUCKETS),
-                       "feeds": "frames resident on the device; labels and marker index vectors fed from the host every step; locref maps built by dgp_locref_targets"},
+            "higher_is_better": True, "scaling": "weak", "dtype": precision, "data": "synthetic",
+            "config": {"workload": "configs[3]: DGP training step, %dx%d, nt=%d frames per replica (%d visible), nj=%d + locref, gm2=1 gm3=3 ws=1000 wt=%g (temporal + skeleton cliques)"
+                                   % (H, W, nt, len(vis), NJ, wt), "parallelism": ("dp%d, dgp_allreduce_gradients: NCCL SUM all-reduce of the 94 MB fp32 gradient arena inside the C ABI, 4 buckets in backward order "
+                                       "(block4+heads, block3, block2, rest) overlapped with the backward pass" % world) if c_comm else
+                                      "dp%d, torch.distributed NCCL all-reduce of the 94 MB fp32 gradient buffer" % world,
+                       "feeds": "frames and the (nt-1,H,W) flow-magnitude field resident on the device; labels and marker index vectors fed from the host every step; locref maps built by dgp_locref_targets"},
+            "allreduce": {"exposed_ms_last_step": exposed_ms, "path": "C ABI (dgp_allreduce_gradients)" if c_comm else ("torch.distributed" if world > 1 else "none"),
+                          "note": "time between the end of the backward pass and the end of the gradient all-reduce on rank 0"},
             "clocks": clocks, "gpu_launches": launches, "loss_after": loss, "finite": bool(np.isfinite(loss)),
             "e2e": {"value": world * nt * e2e_steps / e2e_dt, "unit": "frames/s", "ms_per_step": 1e3 * e2e_dt / e2e_steps,
-                    "h2d_bytes_per_step": int(frames_pinned.numel()) + int(sum(np.asarray(v).nbytes for v in batch.values() if not isinstance(v, (int, list)))),
-                    "d2h_bytes_per_step": 24, "timing": "wall clock, frames copied from pinned host memory and the 6 loss values read back every step, max over ranks"},
+                    "h2d_bytes_per_step": int(frames_pinned.numel()) + (int(flow_pinned.numel()) * 4 if flow_pinned is not None else 0)
+                                          + int(sum(np.asarray(v).nbytes for v in batch.values() if not isinstance(v, (int, list, torch.Tensor)))),
+                    "d2h_bytes_per_step": 24, "timing": "wall clock, frames (and the flow field) copied from pinned host memory and the 6 loss values read back every step, max over ranks"},
             "ms_per_step_by_family": fam, "ms_per_step_with_events": ms_prof / args.steps,
             "tflops": {"forward_gemm": tf(flops_fwd, prof["conv_gemm"][0]), "dgrad_gemm": tf(flops_fwd, prof["dgrad_gemm"][0]),
                        "wgrad_gemm": tf(flops_fwd, prof["wgrad_gemm"][0]),
@@ -182,9 +203,11 @@ def measure(rank, local_rank, world, steps, warmup, nt, height, width, profile=T
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--nt", type=int, default=10)
+    ap.add_argument("--wt", type=float, default=1.0, help="temporal clique weight (0 = off)")
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--height", type=int, default=bench.H)
     ap.add_argument("--width", type=int, default=bench.W)
     ap.add_argument("--cpu-frames", type=int, default=0, help="also time the CPU restatement of the step on this many frames")
@@ -197,7 +220,8 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    line = measure(rank, local_rank, world, args.steps, args.warmup, args.nt, args.height, args.width)
+    line = measure(rank, local_rank, world, args.steps, args.warmup, args.nt, args.height, args.width, precision=args.precision,
+                   wt=args.wt)
     if rank == 0:
         if args.cpu_frames > 0 and world == 1:
             sec, cores = cpu_train_step_seconds(args.cpu_frames, args.height, args.width, bench.NJ)
