@@ -107,6 +107,7 @@ SIGNATURES = {
     "dgp_set_variable": (_i, [_vp, C.c_char_p, _i, _vp, _sz]),
     "dgp_set_profiling": (_i, [_vp, _i]),
     "dgp_get_profile": (_i, [_vp, C.POINTER(C.c_double), _i64p, _i]),
+    "dgp_get_profile_records": (_i, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_int32), _i, C.POINTER(C.c_int)]),
     "dgp_crc32c": (C.c_uint32, [_vp, _sz]),
     "dgp_launch_count": (C.c_int64, [_vp]),
     "dgp_num_sms": (_i, [_vp]),

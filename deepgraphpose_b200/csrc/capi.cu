@@ -278,27 +278,37 @@ int alloc_buf(dgp_handle* h, Plan* pl, size_t bytes, void** out) {
   return DGP_OK;
 }
 
+// Staging buffers per epilogue warp (2 KB each, 16 warps): the residual prefetch runs epi_bufs-1 units ahead.
+// DGP_EPI_BUFS_RES / DGP_EPI_BUFS override the defaults (A/B experiments).
+int epi_bufs_for(bool residual, int block_n) {
+  const char* e = getenv(residual ? "DGP_EPI_BUFS_RES" : "DGP_EPI_BUFS");
+  // 64-wide layers (256-row tiles, one unit per warp and tile): a single buffer leaves room for a fourth smem stage
+  int v = e ? atoi(e) : ((!residual && block_n == 64) ? 1 : 2);
+  const int lo = residual ? 2 : 1;
+  return v < lo ? lo : (v > 4 ? 4 : v);
+}
+
 // Epilogue configuration: bf16 outputs whose tile width is a multiple of 64 go through the TMA-staged epilogue
 // (TMA store of the output, TMA load of the residual); everything else uses direct register->global stores.
 int setup_epilogue(dgp_handle* h, ConvGemmParams& g, const char* scope, int n_img) {
-  const bool staged = !g.out_f32 && (g.block_n % kEpiChunkCols == 0);
+  const bool staged = !g.out_f32 && (g.block_n == 64 || g.block_n == 128 || g.block_n == 256);
   if (!staged) {
-    if (g.residual) return fail(h, DGP_ERR_UNSUPPORTED, "%s: residual needs a bf16 output with block_n %% 64 == 0", scope);
+    if (g.residual) return fail(h, DGP_ERR_UNSUPPORTED, "%s: residual needs a 16-bit output with block_n 64, 128 or 256", scope);
     g.epi_mode = 0;
     g.epi_bufs = 0;
   } else {
     g.epi_mode = 1;
-    g.epi_bufs = g.residual ? 4 : 2;
-    const char* e = make_tmap_2d(&g.tmap_out, g.out, (uint64_t)g.M, (uint64_t)g.N, (uint64_t)g.ldc * 2, 32);
+    g.epi_bufs = epi_bufs_for(g.residual != nullptr, g.block_n);
+    const char* e = make_tmap_2d(&g.tmap_out, g.out, (uint64_t)g.M, (uint64_t)g.N, (uint64_t)g.ldc * 2, 32, kEpiUnitCols);
     if (e) return fail(h, DGP_ERR_CUDA, "%s (out map): %s", scope, e);
     if (g.residual) {
       if (g.res_sub == 1) {
-        e = make_tmap_2d(&g.tmap_res, g.residual, (uint64_t)g.M, (uint64_t)g.N, (uint64_t)g.ldres * 2, 32);
+        e = make_tmap_2d(&g.tmap_res, g.residual, (uint64_t)g.M, (uint64_t)g.N, (uint64_t)g.ldres * 2, 32, kEpiUnitCols);
       } else {
         e = make_tmap_im2col(&g.tmap_res, g.residual, (uint64_t)g.N, (uint64_t)g.res_W, (uint64_t)g.res_H, (uint64_t)n_img,
                              (uint64_t)g.ldres * 2, (uint64_t)g.res_W * g.ldres * 2,
                              (uint64_t)g.res_H * g.res_W * g.ldres * 2, 0, 0, 0, 0, g.res_sub,
-                             (uint64_t)n_img * g.res_H * g.res_W * g.ldres * 2, 32);
+                             (uint64_t)n_img * g.res_H * g.res_W * g.ldres * 2, 32, kEpiUnitCols);
       }
       if (e) return fail(h, DGP_ERR_CUDA, "%s (residual map): %s", scope, e);
     }
@@ -1206,6 +1216,26 @@ int dgp_get_profile(dgp_handle* h, double* ms_by_kind, int64_t* count_by_kind, i
     h->ev_pool.push_back(r.b);
   }
   h->prof.clear();
+  return DGP_OK;
+}
+
+int dgp_get_profile_records(dgp_handle* h, float* ms, int32_t* kind, int max_records, int* n_records) {
+  if (!h || !ms || !kind || !n_records || max_records < 0) return DGP_ERR_INVALID;
+  CU_OK(h, cudaSetDevice(h->device));
+  CU_OK(h, cudaDeviceSynchronize());
+  int n = 0;
+  for (auto& r : h->prof) {
+    float t = 0.0f;
+    if (n < max_records && cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) {
+      ms[n] = t;
+      kind[n] = r.kind;
+      ++n;
+    }
+    h->ev_pool.push_back(r.a);
+    h->ev_pool.push_back(r.b);
+  }
+  h->prof.clear();
+  *n_records = n;
   return DGP_OK;
 }
 

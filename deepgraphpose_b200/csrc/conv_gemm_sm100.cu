@@ -1,13 +1,14 @@
 // Implicit-GEMM convolution on tcgen05 / TMEM / TMA (sm_100a).  See conv_gemm_sm100.cuh.
 //
-// CTA = 192 threads, persistent over (m_blk, n_blk) tiles:
-//   warp 0      TMA producer   (one lane): A tile 128 x 64 (tiled or im2col) + B tile block_n x 64 per stage
-//   warp 1      MMA issuer     (one lane): 4 x tcgen05.mma (K=16) per stage into a double-buffered TMEM accumulator
-//   warps 2..9  epilogue: tcgen05.ld -> fp32 BN scale/shift (+residual)(+ReLU) -> bf16 (two warps per TMEM quadrant)
+// CTA = 576 threads, persistent over (m_blk, n_blk) tiles:
+//   warp 0       TMA producer   (one lane): A tile 128 x 64 (tiled or im2col) + B tile block_n x 64 per stage
+//   warp 1       MMA issuer     (one lane): 4 x tcgen05.mma (K=16) per stage into a double-buffered TMEM accumulator
+//   warps 2..17  epilogue: tcgen05.ld -> fp32 BN scale/shift (+residual)(+ReLU) -> 16 bit (four warps per TMEM quadrant)
 // Pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty pair (MMA <-> epilogue), and per epilogue warp a
-// ring of 4 KB staging buffers (32 rows x 64 channels, SWIZZLE_128B): the residual tile is TMA-loaded into a buffer
+// ring of 2 KB staging buffers (32 rows x 32 channels, SWIZZLE_64B): the residual tile is TMA-loaded into a buffer
 // ahead of time, the warp adds it to the accumulator in place and the buffer is TMA-stored to the output, so that
-// every byte of residual / output traffic moves as full 128 B lines issued by the copy engine, not by the LSU.
+// every byte of residual / output traffic is moved by the copy engine, not by the LSU, and no epilogue warp ever
+// waits for another one (round 1 ran 8 warps in pairs around named barriers: latency-bound at 35 % issue activity).
 #include "conv_gemm_sm100.cuh"
 
 #include <stdio.h>
@@ -20,10 +21,12 @@ namespace dgp {
 
 namespace {
 
-constexpr int kThreads = 320;  // TMA warp + MMA warp + 8 epilogue warps
+constexpr int kEpiWarps = 16;
+constexpr int kThreads = 64 + 32 * kEpiWarps;  // TMA warp + MMA warp + 16 epilogue warps
 constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KiB
 constexpr int kMaxStages = 8;
 constexpr int kMaxEpiBufs = 4;
+constexpr int kEpiUnitBytes = 32 * kEpiUnitCols * 2;  // one warp's 32 rows x 32 columns
 
 __device__ __forceinline__ float bf16lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
@@ -40,44 +43,56 @@ __device__ __forceinline__ uint4 pack8(const float* f, int fp16) {
   if (fp16) return make_uint4(pack_fp16(f[0], f[1]), pack_fp16(f[2], f[3]), pack_fp16(f[4], f[5]), pack_fp16(f[6], f[7]));
   return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
 }
-__device__ __forceinline__ void add_residual2(float& a, float& b, uint32_t v, int fp16) {
-  if (fp16) {
-    const float2 r = __half22float2(*reinterpret_cast<const __half2*>(&v));
-    a += r.x;
-    b += r.y;
-  } else {
-    a += bf16lo(v);
-    b += bf16hi(v);
-  }
-}
-
-// BN scale/shift of 16 consecutive channels from this warp's shared-memory copy (broadcast LDS.128).
-__device__ __forceinline__ void apply_scale_shift(float (&f)[16], const float* ss_scale, const float* ss_shift, int c) {
+// One epilogue unit = this warp's 32 accumulator rows x 32 columns: BN scale/shift (fp32, packed FFMA2) (+ residual)
+// (+ ReLU, folded into the float -> 16-bit conversion) written in place into the warp's 2 KB staging buffer
+// (32 rows x 64 B, SWIZZLE_64B: 16-byte unit u of row r lives at u ^ ((r >> 1) & 3), conflict-free for LDS/STS.128).
+template <bool kFp16, bool kRelu, bool kRes>
+__device__ __forceinline__ void epi_unit_math(const uint32_t (&v)[2][16], uint8_t* my_row, int lane, const float* ss) {
+  const int sw = (lane >> 1) & 3;
 #pragma unroll
-  for (int i = 0; i < 16; i += 4) {
-    const float4 sc = *reinterpret_cast<const float4*>(ss_scale + c + i);
-    const float4 sh = *reinterpret_cast<const float4*>(ss_shift + c + i);
-    f[i] = fmaf(f[i], sc.x, sh.x);
-    f[i + 1] = fmaf(f[i + 1], sc.y, sh.y);
-    f[i + 2] = fmaf(f[i + 2], sc.z, sh.z);
-    f[i + 3] = fmaf(f[i + 3], sc.w, sh.w);
+  for (int s2 = 0; s2 < 2; ++s2) {
+    uint4* s0 = reinterpret_cast<uint4*>(my_row + (((2 * s2) ^ sw) << 4));
+    uint4* s1 = reinterpret_cast<uint4*>(my_row + (((2 * s2 + 1) ^ sw) << 4));
+    const float* scp = ss + s2 * 16;
+    const float* shp = ss + 32 + s2 * 16;
+    uint32_t rr[8];
+    if (kRes) {
+      const uint4 r0 = *s0;
+      const uint4 r1 = *s1;
+      rr[0] = r0.x; rr[1] = r0.y; rr[2] = r0.z; rr[3] = r0.w; rr[4] = r1.x; rr[5] = r1.y; rr[6] = r1.z; rr[7] = r1.w;
+    }
+    uint32_t o[8];
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+      const float4 sc = *reinterpret_cast<const float4*>(scp + 2 * i);
+      const float4 sh = *reinterpret_cast<const float4*>(shp + 2 * i);
+      ptx::f32x2 q0 = ptx::fma2(ptx::pk2(__uint_as_float(v[s2][2 * i]), __uint_as_float(v[s2][2 * i + 1])),
+                                ptx::pk2(sc.x, sc.y), ptx::pk2(sh.x, sh.y));
+      ptx::f32x2 q1 = ptx::fma2(ptx::pk2(__uint_as_float(v[s2][2 * i + 2]), __uint_as_float(v[s2][2 * i + 3])),
+                                ptx::pk2(sc.z, sc.w), ptx::pk2(sh.z, sh.w));
+      if (kRes) {
+        if (kFp16) {
+          const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&rr[i]));
+          const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&rr[i + 1]));
+          q0 = ptx::add2(q0, ptx::pk2(a.x, a.y));
+          q1 = ptx::add2(q1, ptx::pk2(b.x, b.y));
+        } else {
+          q0 = ptx::add2(q0, ptx::pk2(bf16lo(rr[i]), bf16hi(rr[i])));
+          q1 = ptx::add2(q1, ptx::pk2(bf16lo(rr[i + 1]), bf16hi(rr[i + 1])));
+        }
+      }
+      float a0, a1, b0, b1;
+      ptx::upk2(q0, a0, a1);
+      ptx::upk2(q1, b0, b1);
+      o[i] = ptx::cvt_pack16<kFp16, kRelu>(a0, a1);
+      o[i + 1] = ptx::cvt_pack16<kFp16, kRelu>(b0, b1);
+    }
+    *s0 = make_uint4(o[0], o[1], o[2], o[3]);
+    *s1 = make_uint4(o[4], o[5], o[6], o[7]);
   }
 }
 
-// Each epilogue warp keeps its own copy of the tile's scale/shift ([2][256] floats): with 227 KB of shared memory
-// carved out there is no L1 left, so a per-use __ldg would put an L2 round trip on the epilogue's critical path.
-__device__ __forceinline__ void load_scale_shift(float* ss, const float* __restrict__ scale,
-                                                 const float* __restrict__ shift, int n0, int block_n, int lane) {
-  for (int i = lane * 4; i < block_n; i += 128) {
-    const float4 sc = scale ? __ldg(reinterpret_cast<const float4*>(scale + n0 + i)) : make_float4(1.f, 1.f, 1.f, 1.f);
-    const float4 sh = shift ? __ldg(reinterpret_cast<const float4*>(shift + n0 + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    *reinterpret_cast<float4*>(ss + i) = sc;
-    *reinterpret_cast<float4*>(ss + 256 + i) = sh;
-  }
-  __syncwarp();
-}
-
-// kFp16 selects the 16-bit storage type at compile time (bf16 default / fp16): no dtype branches in the epilogue.
+// kFp16 selects the 16-bit storage type at compile time (bf16 / fp16): no dtype branches in the epilogue.
 template <bool kFp16>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -88,15 +103,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   const int b_bytes = p.block_n * kBlockK * 2;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + stages * a_bytes;
-  uint8_t* smem_epi = smem_b + stages * b_bytes;  // [4 warps][epi_bufs][4 KiB], 1024 B aligned
+  uint8_t* smem_epi = smem_b + stages * b_bytes;  // [16 warps][epi_bufs][2 KiB], 1024 B aligned
   const int epi_bufs = p.epi_mode == 1 ? p.epi_bufs : 0;
-  float* smem_ss = reinterpret_cast<float*>(smem_epi + 4 * epi_bufs * kEpiChunkBytes);  // [4 warps][2][256]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_ss + 4 * 512);
+  float* smem_ss = reinterpret_cast<float*>(smem_epi + kEpiWarps * epi_bufs * kEpiUnitBytes);  // [16 warps][2 sets][scale 32 | shift 32]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_ss + kEpiWarps * 128);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tmem_full_bar = empty_bar + kMaxStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-  uint64_t* res_bar = tmem_empty_bar + 2;  // [4 warps][kMaxEpiBufs]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 4 * kMaxEpiBufs);
+  uint64_t* res_bar = tmem_empty_bar + 2;  // [16 warps][kMaxEpiBufs]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + kEpiWarps * kMaxEpiBufs);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -116,9 +131,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full_bar[a], 1);
-      ptx::mbar_init(&tmem_empty_bar[a], 8);
+      ptx::mbar_init(&tmem_empty_bar[a], kEpiWarps);
     }
-    for (int i = 0; i < 4 * kMaxEpiBufs; ++i) ptx::mbar_init(&res_bar[i], 1);
+    for (int i = 0; i < kEpiWarps * kMaxEpiBufs; ++i) ptx::mbar_init(&res_bar[i], 1);
     ptx::fence_mbar_init();
   }
   if (warp == 2) {
@@ -239,9 +254,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     else run(std::integral_constant<int, 1>{});
   } else if (p.epi_mode == 0) {
     // -------------------------------------------------------------- epilogue, direct stores (fp32 head GEMM)
-    // 8 epilogue warps: two per TMEM lane quadrant, taking alternate 16-column groups.
+    // 16 epilogue warps: four per TMEM lane quadrant, taking every fourth 16-column group.
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
-    const int half = (warp - 2) >> 2;
+    const int cg = (warp - 2) >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -253,7 +268,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.block_n);
-      for (int c0 = half * 16; c0 < p.block_n; c0 += 32) {
+      for (int c0 = cg * 16; c0 < p.block_n; c0 += 64) {
         uint32_t v[16];
         ptx::tmem_ld_x16(taddr + (uint32_t)c0, v);
         ptx::tmem_ld_wait();
@@ -292,211 +307,140 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       if (acc == 0) acc_phase ^= 1;
     }
   } else {
-    // -------------------------------------------------------------- epilogue, TMA-staged bf16 (+ TMA residual)
-    // 8 epilogue warps = 4 pairs, one pair per TMEM lane quadrant (32 rows).  The pair shares a ring of 4 KB staging
-    // buffers (32 rows x 64 channels): the leader warp (half 0) handles channels 0..31 of each chunk and issues all
-    // TMA traffic, the follower handles channels 32..63; they meet on a 64-thread named barrier before the store.
+    // -------------------------------------------------------------- epilogue, TMA-staged 16-bit (+ TMA residual)
+    // 16 INDEPENDENT epilogue warps, four per TMEM lane quadrant.  A tile is cut into units of 32 rows x 32 columns
+    // (one warp's TMEM rows x two tcgen05.ld.x16); the warp with column-group index cg takes units cg, cg+4, ... of
+    // the (sub-tile, column group) sequence.  Each warp owns a small ring of 2 KB staging buffers (32 rows x 64 B,
+    // SWIZZLE_64B), TMA-loads the residual tile into a buffer ahead of time, combines in place and TMA-stores the
+    // buffer: no barrier between warps anywhere in the epilogue, 16 units in flight per SM.
     const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;
-    const bool leader = half == 0;
+    const int ew = warp - 2;
+    const int cg = ew >> 2;
     const int nb = p.epi_bufs;
-    uint8_t* ebuf = smem_epi + (size_t)quad * nb * kEpiChunkBytes;
-    uint64_t* rbar = res_bar + quad * kMaxEpiBufs;
-    const uint32_t pair_bar = 1u + (uint32_t)quad;
+    uint8_t* ebuf = smem_epi + (size_t)ew * nb * kEpiUnitBytes;
+    uint64_t* rbar = res_bar + ew * kMaxEpiBufs;
     const bool has_res = p.residual != nullptr;
-    const int chunks_per_tile = p.block_n / kEpiChunkCols;
+    const int block_n = p.block_n, nnb = p.num_n_blocks;
+    const int ncg = block_n >> 5;                                   // 32-column groups per tile row: 2, 4 or 8
+    const int ncg_shift = ncg == 8 ? 3 : (ncg == 4 ? 2 : 1);
+    const int units = msub * ncg;
+    const int nsets = ncg == 8 ? 2 : 1;                             // distinct column groups this warp ever touches
     const int PQ = p.P * p.Q;
-    float* ss = smem_ss + (warp - 2) * 256;  // this warp's [2][128] scale/shift (its 32 channels of every chunk)
+    float* ss = smem_ss + ew * 128;
     int ss_n0 = -1;
-    const int nb_mask = nb - 1;              // nb is 2 or 4
-    const int nb_shift = nb == 4 ? 2 : 1;
 
-    // Residual prefetch cursor (leader warp only): walks this CTA's (tile, chunk) sequence nb-1 chunks ahead of the
-    // consumer.  All leader lanes keep the (uniform) cursor; lane 0 issues.  Divisions happen once per tile.
-    int pf_g = 0, pf_tile = blockIdx.x, pf_c = 0, pf_sub = 0, pf_row0 = 0, pf_col0 = 0, pf_img = 0, pf_w = 0, pf_h = 0;
+    // Residual prefetch cursor: walks this warp's (tile, unit) sequence nb-1 units ahead of the consumer.  All lanes
+    // keep the (uniform) cursor; lane 0 issues.
+    int pf_tile = blockIdx.x, pf_u = cg, pf_buf = 0, pf_mblk = 0, pf_n0 = 0;
     auto pf_setup_tile = [&]() {
-      const int m_blk = pf_tile / p.num_n_blocks;
-      const int n_blk = pf_tile - m_blk * p.num_n_blocks;
-      pf_row0 = (m_blk * msub + pf_sub) * kBlockM + quad * 32;
-      pf_col0 = n_blk * p.block_n;
-      if (p.res_sub != 1) {
-        pf_img = pf_row0 / PQ;
-        const int rem = pf_row0 - pf_img * PQ;
-        const int pp = rem / p.Q;
-        pf_h = pp * p.res_sub;
-        pf_w = (rem - pp * p.Q) * p.res_sub;
-      }
+      pf_mblk = pf_tile / nnb;
+      pf_n0 = (pf_tile - pf_mblk * nnb) * block_n;
     };
     auto issue_residual = [&]() {
       if (pf_tile >= num_tiles) return;
+      const int sub = pf_u >> ncg_shift;
+      const int row0 = (pf_mblk * msub + sub) * kBlockM + quad * 32;
+      const int col0 = pf_n0 + ((pf_u & (ncg - 1)) << 5);
       if (lane == 0) {
-        const int buf = pf_g & nb_mask;
-        ptx::mbar_arrive_expect_tx(&rbar[buf], (uint32_t)kEpiChunkBytes);
+        ptx::mbar_arrive_expect_tx(&rbar[pf_buf], (uint32_t)kEpiUnitBytes);
         if (p.res_sub == 1) {
-          ptx::tma_load_2d(ebuf + buf * kEpiChunkBytes, &p.tmap_res, &rbar[buf], pf_col0 + pf_c * kEpiChunkCols, pf_row0);
+          ptx::tma_load_2d(ebuf + pf_buf * kEpiUnitBytes, &p.tmap_res, &rbar[pf_buf], col0, row0);
         } else {
-          ptx::tma_load_im2col_4d(ebuf + buf * kEpiChunkBytes, &p.tmap_res, &rbar[buf], pf_col0 + pf_c * kEpiChunkCols,
-                                  pf_w, pf_h, pf_img, 0, 0);
+          const int img = row0 / PQ;
+          const int rem = row0 - img * PQ;
+          const int pp = rem / p.Q;
+          ptx::tma_load_im2col_4d(ebuf + pf_buf * kEpiUnitBytes, &p.tmap_res, &rbar[pf_buf], col0,
+                                  (rem - pp * p.Q) * p.res_sub, pp * p.res_sub, img, 0, 0);
         }
       }
-      ++pf_g;
-      if (++pf_c == chunks_per_tile) {
-        pf_c = 0;
-        if (++pf_sub == msub) {
-          pf_sub = 0;
-          pf_tile += gridDim.x;
-        }
+      if (++pf_buf == nb) pf_buf = 0;
+      pf_u += 4;
+      if (pf_u >= units) {
+        pf_u = cg;
+        pf_tile += gridDim.x;
         if (pf_tile < num_tiles) pf_setup_tile();
       }
     };
 
-    if (has_res && leader) {
+    const bool active = cg < units;  // 128-row tiles of a 64-wide layer have only two units
+    if (has_res && active) {
       if (pf_tile < num_tiles) pf_setup_tile();
       for (int i = 0; i < nb - 1; ++i) issue_residual();
       __syncwarp();
     }
-    int g = 0;  // chunk sequence number
+    int buf = 0;
+    uint32_t buf_phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / p.num_n_blocks;
-      const int n_blk = tile - m_blk * p.num_n_blocks;
-      const int n0 = n_blk * p.block_n;
-      if (n0 != ss_n0) {
-        // my 32 channels of chunk cc live at ss[cc*32 ..] (scale) and ss[128 + cc*32 ..] (shift)
-        for (int i = lane * 4; i < (p.block_n >> 1); i += 128) {
-          const int col = n0 + (i >> 5) * kEpiChunkCols + half * 32 + (i & 31);
-          const float4 sc = p.scale ? __ldg(reinterpret_cast<const float4*>(p.scale + col)) : make_float4(1.f, 1.f, 1.f, 1.f);
-          const float4 sh = p.shift ? __ldg(reinterpret_cast<const float4*>(p.shift + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          *reinterpret_cast<float4*>(ss + i) = sc;
-          *reinterpret_cast<float4*>(ss + 128 + i) = sh;
+      const int m_blk = tile / nnb;
+      const int n0 = (tile - m_blk * nnb) * block_n;
+      if (n0 != ss_n0 && active) {
+        if (lane < 16 * nsets) {
+          const int set = lane >> 4, is_shift = (lane >> 3) & 1, i = (lane & 7) * 4;
+          const int col = n0 + (((cg & (ncg - 1)) + 4 * set) << 5) + i;
+          const float* src = is_shift ? p.shift : p.scale;
+          const float fill = is_shift ? 0.f : 1.f;
+          const float4 val = src ? __ldg(reinterpret_cast<const float4*>(src + col)) : make_float4(fill, fill, fill, fill);
+          *reinterpret_cast<float4*>(ss + set * 64 + is_shift * 32 + i) = val;
         }
         __syncwarp();
         ss_n0 = n0;
       }
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after();
-      for (int sub = 0; sub < msub; ++sub) {
-      const int row0 = (m_blk * msub + sub) * kBlockM + quad * 32;
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) +
-                             (uint32_t)((acc * msub + sub) * p.block_n + half * 32);
-      for (int c = 0; c < chunks_per_tile; ++c, ++g) {
-        const int buf = g & nb_mask;
-        uint8_t* my_row = ebuf + buf * kEpiChunkBytes + lane * 128;
-        // both TMEM loads of my half-chunk are in flight before the single wait
+      for (int u = cg; u < units; u += 4) {
+        const int sub = u >> ncg_shift;
+        const int colg = u & (ncg - 1);
+        const int row0 = (m_blk * msub + sub) * kBlockM + quad * 32;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((acc * msub + sub) * block_n + (colg << 5));
+        uint8_t* my_buf = ebuf + buf * kEpiUnitBytes;
         uint32_t v[2][16];
-        ptx::tmem_ld_x16(taddr + (uint32_t)(c * kEpiChunkCols), v[0]);
-        ptx::tmem_ld_x16(taddr + (uint32_t)(c * kEpiChunkCols + 16), v[1]);
+        ptx::tmem_ld_x16(taddr, v[0]);
+        ptx::tmem_ld_x16(taddr + 16, v[1]);
         if (has_res) {
-          ptx::mbar_wait(&rbar[buf], (uint32_t)((g >> nb_shift) & 1));
+          // the buffer the next prefetch lands in was last used by the unit before this one: its store must have
+          // finished reading shared memory (it was committed a whole unit ago)
+          if (lane == 0) ptx::bulk_wait_group_read<0>();
+          issue_residual();
+          ptx::mbar_wait(&rbar[buf], buf_phase);
         } else {
-          // the store that last used this buffer (chunk g - nb) must have finished reading it
-          if (leader && lane == 0) {
-            if (nb == 4) ptx::bulk_wait_group_read<3>();
-            else ptx::bulk_wait_group_read<1>();
-          }
-          ptx::named_bar_sync(pair_bar, 64);
-        }
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int s2 = 0; s2 < 2; ++s2) {
-          const int u = 4 * half + 2 * s2;  // 16-byte unit inside the 128 B staging row (SWIZZLE_128B: u ^ (row & 7))
-          uint4* s0 = reinterpret_cast<uint4*>(my_row + ((u ^ (lane & 7)) << 4));
-          uint4* s1 = reinterpret_cast<uint4*>(my_row + (((u + 1) ^ (lane & 7)) << 4));
-#ifndef DGP_EPI_SCALAR
-          // Packed fp32x2 epilogue (FFMA2 / FADD2, ReLU as one bf16x2 max after rounding): same values bit for bit
-          // (fma / add are IEEE per lane; rounding is monotonic and 0 is exact), two thirds of the issue slots.
-          const float* scp = ss + c * 32 + s2 * 16;
-          const float* shp = ss + 128 + c * 32 + s2 * 16;
-          uint32_t rr[8];
-          if (has_res) {
-            const uint4 r0 = *s0;
-            const uint4 r1 = *s1;
-            rr[0] = r0.x; rr[1] = r0.y; rr[2] = r0.z; rr[3] = r0.w; rr[4] = r1.x; rr[5] = r1.y; rr[6] = r1.z; rr[7] = r1.w;
-          }
-          uint32_t o[8];
-#pragma unroll
-          for (int i = 0; i < 8; i += 2) {
-            const float4 sc = *reinterpret_cast<const float4*>(scp + 2 * i);
-            const float4 sh = *reinterpret_cast<const float4*>(shp + 2 * i);
-            ptx::f32x2 q0 = ptx::fma2(ptx::pk2(__uint_as_float(v[s2][2 * i]), __uint_as_float(v[s2][2 * i + 1])),
-                                      ptx::pk2(sc.x, sc.y), ptx::pk2(sh.x, sh.y));
-            ptx::f32x2 q1 = ptx::fma2(ptx::pk2(__uint_as_float(v[s2][2 * i + 2]), __uint_as_float(v[s2][2 * i + 3])),
-                                      ptx::pk2(sc.z, sc.w), ptx::pk2(sh.z, sh.w));
-            if (has_res) {
-              if (kFp16) {
-                const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&rr[i]));
-                const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&rr[i + 1]));
-                q0 = ptx::add2(q0, ptx::pk2(a.x, a.y));
-                q1 = ptx::add2(q1, ptx::pk2(b.x, b.y));
-              } else {
-                q0 = ptx::add2(q0, ptx::pk2(bf16lo(rr[i]), bf16hi(rr[i])));
-                q1 = ptx::add2(q1, ptx::pk2(bf16lo(rr[i + 1]), bf16hi(rr[i + 1])));
-              }
-            }
-            float a0, a1, b0, b1;
-            ptx::upk2(q0, a0, a1);
-            ptx::upk2(q1, b0, b1);
-            o[i] = kFp16 ? pack_fp16(a0, a1) : pack_bf16(a0, a1);
-            o[i + 1] = kFp16 ? pack_fp16(b0, b1) : pack_bf16(b0, b1);
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              if (kFp16) {
-                const __half2 z = __hmax2(*reinterpret_cast<const __half2*>(&o[i]), __float2half2_rn(0.0f));
-                o[i] = *reinterpret_cast<const uint32_t*>(&z);
-              } else {
-                const __nv_bfloat162 z = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&o[i]), __float2bfloat162_rn(0.0f));
-                o[i] = *reinterpret_cast<const uint32_t*>(&z);
-              }
-            }
-          }
-          *s0 = make_uint4(o[0], o[1], o[2], o[3]);
-          *s1 = make_uint4(o[4], o[5], o[6], o[7]);
-#else
-          float f[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[s2][i]);
-          apply_scale_shift(f, ss, ss + 128, c * 32 + s2 * 16);
-          if (has_res) {
-            const uint4 r0 = *s0;
-            const uint4 r1 = *s1;
-            const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              add_residual2(f[2 * i], f[2 * i + 1], rr[i], kFp16);
-            }
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.0f);
-          }
-          *s0 = pack8(f, kFp16);
-          *s1 = pack8(f + 8, kFp16);
-#endif
-        }
-        ptx::fence_proxy_async_smem();  // my generic-proxy smem writes -> visible to the TMA store (async proxy)
-        ptx::named_bar_sync(pair_bar, 64);
-        if (leader) {
+          // the store that last used this buffer (nb units ago) must have finished reading it
           if (lane == 0) {
-            ptx::tma_store_2d(&p.tmap_out, ebuf + buf * kEpiChunkBytes, n0 + c * kEpiChunkCols, row0);
-            ptx::bulk_commit_group();
-            // chunk g+nb-1 reuses the buffer of chunk g-1: its store may be the only one still pending besides mine
-            if (has_res && g >= 1) ptx::bulk_wait_group_read<1>();
+            if (nb >= 3) ptx::bulk_wait_group_read<2>();
+            else if (nb == 2) ptx::bulk_wait_group_read<1>();
+            else ptx::bulk_wait_group_read<0>();
           }
-          if (has_res) issue_residual();
           __syncwarp();
         }
+        ptx::tmem_ld_wait();
+        const float* ssu = ss + (colg >> 2) * 64;
+        uint8_t* my_row = my_buf + lane * 64;
+        if (has_res) {
+          if (p.relu) epi_unit_math<kFp16, true, true>(v, my_row, lane, ssu);
+          else epi_unit_math<kFp16, false, true>(v, my_row, lane, ssu);
+        } else {
+          if (p.relu) epi_unit_math<kFp16, true, false>(v, my_row, lane, ssu);
+          else epi_unit_math<kFp16, false, false>(v, my_row, lane, ssu);
+        }
+        ptx::fence_proxy_async_smem();  // my generic-proxy smem writes -> visible to the TMA store (async proxy)
+        __syncwarp();
+        if (lane == 0) {
+          ptx::tma_store_2d(&p.tmap_out, my_buf, n0 + (colg << 5), row0);
+          ptx::bulk_commit_group();
+        }
+        if (++buf == nb) {
+          buf = 0;
+          buf_phase ^= 1;
+        }
       }
-      }  // sub
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-    if (leader && lane == 0) ptx::bulk_wait_group_read<0>();
+    if (lane == 0) ptx::bulk_wait_group_read<0>();
     __syncwarp();
   }
 
@@ -540,14 +484,16 @@ namespace { int g_tmap_fp16 = 0; }
 void tmap_set_fp16(int fp16) { g_tmap_fp16 = fp16; }
 
 const char* make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t k, uint64_t row_stride_bytes,
-                         uint32_t box_rows) {
+                         uint32_t box_rows, uint32_t box_cols) {
   if (const char* e = tma_init()) return e;
   cuuint64_t dims[2] = {k, rows};
   cuuint64_t strides[1] = {row_stride_bytes};
-  cuuint32_t box[2] = {(cuuint32_t)kBlockK, box_rows};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  const CUtensorMapSwizzle swz = box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;  // 128 B / 64 B rows
+  if (box_cols != 64 && box_cols != 32) return "make_tmap_2d: box_cols must be 64 or 32";
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode_tiled(out, g_tmap_fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
-                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     snprintf(g_err, sizeof(g_err), "cuTensorMapEncodeTiled failed: %d (rows=%llu k=%llu stride=%llu box_rows=%u)", (int)r,
@@ -560,16 +506,18 @@ const char* make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint
 const char* make_tmap_im2col(CUtensorMap* out, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t N,
                              uint64_t stride_w_bytes, uint64_t stride_h_bytes, uint64_t stride_n_bytes, int lower_w,
                              int lower_h, int upper_w, int upper_h, int conv_stride, uint64_t total_bytes,
-                             uint32_t pixels_per_column) {
+                             uint32_t pixels_per_column, uint32_t channels_per_pixel) {
   if (const char* e = tma_init()) return e;
+  if (channels_per_pixel != 64 && channels_per_pixel != 32) return "make_tmap_im2col: channels_per_pixel must be 64 or 32";
+  const CUtensorMapSwizzle swz = channels_per_pixel == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   cuuint64_t dims[4] = {C, W, H, N};
   cuuint64_t strides[3] = {stride_w_bytes, stride_h_bytes, stride_n_bytes};
   int lower[2] = {lower_w, lower_h};
   int upper[2] = {upper_w, upper_h};
   cuuint32_t estr[4] = {1, (cuuint32_t)conv_stride, (cuuint32_t)conv_stride, 1};
   CUresult r = g_encode_im2col(out, g_tmap_fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, lower,
-                               upper, (cuuint32_t)kBlockK, (cuuint32_t)pixels_per_column, estr,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               upper, (cuuint32_t)channels_per_pixel, (cuuint32_t)pixels_per_column, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     snprintf(g_err, sizeof(g_err),
@@ -588,8 +536,9 @@ const char* make_tmap_im2col(CUtensorMap* out, const void* base, uint64_t C, uin
 }
 
 size_t conv_gemm_smem_bytes(int block_n, int num_stages, int epi_bufs, int msub) {
-  return 1024 + (size_t)num_stages * ((size_t)msub * kABytes + (size_t)block_n * kBlockK * 2) + (size_t)4 * epi_bufs * kEpiChunkBytes +
-         4 * 512 * sizeof(float) + (2 * kMaxStages + 4 + 4 * kMaxEpiBufs) * 8 + 16;
+  return 1024 + (size_t)num_stages * ((size_t)msub * kABytes + (size_t)block_n * kBlockK * 2) +
+         (size_t)kEpiWarps * epi_bufs * kEpiUnitBytes + kEpiWarps * 128 * sizeof(float) +
+         (2 * kMaxStages + 4 + kEpiWarps * kMaxEpiBufs) * 8 + 16;
 }
 
 int conv_gemm_pick_stages(int block_n, int epi_bufs, int msub) {

@@ -22,13 +22,12 @@ namespace dgp {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
 
-constexpr int kEpiChunkCols = 64;   // bf16 columns per epilogue staging chunk (128 B swizzle row)
-constexpr int kEpiChunkBytes = 32 * kEpiChunkCols * 2;  // one warp's 32 rows x 64 cols
+constexpr int kEpiUnitCols = 32;    // 16-bit columns per epilogue staging unit (64 B rows, SWIZZLE_64B)
 
 struct ConvGemmParams {
   CUtensorMap tmap_a;
   CUtensorMap tmap_b;
-  CUtensorMap tmap_out;  // epi_mode 1: [M, N] bf16, box 64 x 32, SWIZZLE_128B
+  CUtensorMap tmap_out;  // epi_mode 1: [M, N] 16-bit, box 32 columns x 32 rows, SWIZZLE_64B
   CUtensorMap tmap_res;  // epi_mode 1 with residual: same box over the residual tensor (tiled or im2col stride 2)
   int M;             // output pixels
   int N;             // output channels (multiple of block_n)
@@ -48,7 +47,7 @@ struct ConvGemmParams {
   const float* scale;  // [N] or nullptr (=1)
   const float* shift;  // [N] or nullptr (=0)
   int epi_mode;      // 0 = direct register->global stores (fp32 head GEMM), 1 = TMA-staged bf16 (+ TMA residual)
-  int epi_bufs;      // staging buffers per epilogue warp (epi_mode 1): 2 without residual, 4 with
+  int epi_bufs;      // 2 KB staging buffers per epilogue warp (epi_mode 1): 2..4; the residual prefetch runs epi_bufs-1 units ahead
   const __nv_bfloat16* residual;  // nullptr = none
   int res_sub;       // 1 = same pixel grid as the output, 2 = residual grid is (res_H, res_W), read at (2p, 2q)
   int res_H, res_W;
@@ -85,14 +84,14 @@ cudaError_t launch_wgrad_reduce(const WgradParams& p, const float* rowscale, con
 // Host helpers (conv_gemm_sm100.cu)
 void tmap_set_fp16(int fp16);  // element type of subsequently encoded tensor maps
 const char* tma_init();  // resolves the driver's tensor-map encoders; returns nullptr on success, else an error string
-// [rows, k] row-major bf16 matrix, box = [box_rows, 64], SWIZZLE_128B.
+// [rows, k] row-major 16-bit matrix, box = [box_rows, box_cols]: 64 columns -> SWIZZLE_128B, 32 columns -> SWIZZLE_64B.
 const char* make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t k, uint64_t row_stride_bytes,
-                         uint32_t box_rows);
+                         uint32_t box_rows, uint32_t box_cols = kBlockK);
 // NHWC-like activation tensor for im2col loads: dims (C, W, H, N) with explicit byte strides for W, H, N.
 const char* make_tmap_im2col(CUtensorMap* out, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t N,
                              uint64_t stride_w_bytes, uint64_t stride_h_bytes, uint64_t stride_n_bytes, int lower_w,
                              int lower_h, int upper_w, int upper_h, int conv_stride, uint64_t total_bytes,
-                             uint32_t pixels_per_column = kBlockM);
+                             uint32_t pixels_per_column = kBlockM, uint32_t channels_per_pixel = kBlockK);
 size_t conv_gemm_smem_bytes(int block_n, int num_stages, int epi_bufs, int msub);
 int conv_gemm_pick_stages(int block_n, int epi_bufs, int msub);
 cudaError_t launch_conv_gemm(const ConvGemmParams& p, int num_sms, cudaStream_t stream);

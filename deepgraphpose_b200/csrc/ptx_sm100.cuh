@@ -107,6 +107,22 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
   return d;
 }
 
+// Two floats -> packed 16-bit pair (lo in the low half) in ONE F2FP: fp16 saturates to +-65504 instead of overflowing
+// to inf (.satfinite), ReLU rides in the conversion (.relu: negative -> +0; rounding is monotonic, so relu(round(x)) ==
+// round(relu(x))).
+template <bool kFp16, bool kRelu>
+__device__ __forceinline__ uint32_t cvt_pack16(float lo, float hi) {
+  uint32_t r;
+  if (kFp16) {
+    if (kRelu) asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    else asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  } else {
+    if (kRelu) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  }
+  return r;
+}
+
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

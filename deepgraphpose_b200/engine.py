@@ -565,6 +565,14 @@ class Engine:
         self._check(self.lib.dgp_get_profile(self.h, ms, cnt, n))
         return {k: (ms[i], int(cnt[i])) for i, k in enumerate(self.PROFILE_KINDS)}
 
+    def get_profile_records(self, max_records=65536):
+        """[(kind, ms)] per launch, in launch order, since the last call (synchronises the device)."""
+        ms = (C.c_float * max_records)()
+        kind = (C.c_int32 * max_records)()
+        n = C.c_int(0)
+        self._check(self.lib.dgp_get_profile_records(self.h, ms, kind, max_records, C.byref(n)))
+        return [(self.PROFILE_KINDS[kind[i]] if 0 <= kind[i] < len(self.PROFILE_KINDS) else str(kind[i]), ms[i]) for i in range(n.value)]
+
     def launch_count(self):
         return int(self.lib.dgp_launch_count(self.h))
 

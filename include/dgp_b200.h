@@ -318,6 +318,9 @@ int dgp_conv2d_wgrad(dgp_handle* h, const void* x_dev, int N, int H, int W, int 
  * dgp_get_profile synchronises the device, sums the elapsed ms and launch counts per kind and clears the records. */
 int dgp_set_profiling(dgp_handle* h, int enable);
 int dgp_get_profile(dgp_handle* h, double* ms_by_kind, int64_t* count_by_kind, int nkinds);
+/* The same records one by one, in launch order (elapsed ms and kind of up to max_records launches; clears the records):
+ * the in-step duration of every layer, at the clocks and power state of the real step (tools/instep_layers.py). */
+int dgp_get_profile_records(dgp_handle* h, float* ms, int32_t* kind, int max_records, int* n_records);
 /* Host helper: CRC-32C of a byte range (the tensor checksums of TensorFlow checkpoint bundles, tf_checkpoint.py). */
 uint32_t dgp_crc32c(const void* data, size_t n);
 /* Number of kernels this handle has launched since creation. */
