@@ -318,7 +318,7 @@ int setup_epilogue(dgp_handle* h, ConvGemmParams& g, const char* scope, int n_im
   g.msub = (g.epi_mode == 1 && g.block_n <= 128 && g.M > kBlockM) ? 2 : 1;
   g.num_m_blocks = ceil_div(g.M, kBlockM * g.msub);
   g.tmem_cols = tmem_cols_for(g.block_n * g.msub);
-  g.num_stages = conv_gemm_pick_stages(g.block_n, g.epi_bufs, g.msub);
+  g.num_stages = conv_gemm_pick_stages(g);
   return DGP_OK;
 }
 
@@ -381,8 +381,37 @@ int make_gemm_step(dgp_handle* h, const ConvLayer& L, const void* x, int N, int 
   g.num_m_blocks = ceil_div(g.M, kBlockM);
   g.num_n_blocks = L.Npad / bn;
   g.tmem_cols = tmem_cols_for(bn);
-  if (int rc = setup_epilogue(h, g, L.scope.c_str(), N)) return rc;
   const char* e = nullptr;
+  // 3x3 stride-1 convs over 64 channels (block 1 conv2 and its dgrad) run from a shared-memory resident input patch: the
+  // im2col form re-reads every activation nine times from the L2 and is bound by the L2 -> SM fabric (~11 TB/s of
+  // distinct lines), not by the tensor pipe.  DGP_NO_PATCH_CONV=1 restores the im2col path (A/B, tests).
+  const bool patch = L.R == 3 && L.S == 3 && L.stride == 1 && L.Cin == 64 && bn == 64 && L.Npad == 64 && !out_f32 && !residual &&
+                     lower_h == L.dil && lower_w == L.dil && getenv("DGP_NO_PATCH_CONV") == nullptr;
+  if (patch) {
+    g.a_mode = 3; g.epi_mode = 3; g.epi_bufs = 0; g.msub = 2;
+    g.pt_rows = 14; g.pt_cols = 16;
+    if (L.dil > 1) { g.pt_rows = 12; g.pt_cols = 16; }
+    g.pt_wp = g.pt_cols + 2 * L.dil;
+    while (g.pt_rows * g.pt_wp > 256) --g.pt_rows;
+    g.pt_stage_bytes = conv_patch_stage_bytes(g.pt_wp, L.dil);
+    g.pt_base_offset_mode = 0;  // measured: the UMMA swizzle is a function of the absolute smem address; base_offset stays 0
+    g.pool_tiles_i = ceil_div(P, g.pt_rows); g.pool_tiles_j = ceil_div(Q, g.pt_cols);
+    g.num_m_blocks = N * g.pool_tiles_i * g.pool_tiles_j;
+    g.num_n_blocks = 1;
+    g.tmem_cols = tmem_cols_for(bn * 2);
+    g.num_stages = 2;
+    if (conv_gemm_smem_bytes(g) > 227 * 1024) return fail(h, DGP_ERR_UNSUPPORTED, "%s: patch conv does not fit shared memory", L.scope.c_str());
+    e = make_tmap_tiled4d(&g.tmap_a, x, 64, (uint64_t)W, (uint64_t)H, (uint64_t)N, 128, (uint64_t)W * 128, (uint64_t)H * W * 128,
+                          (uint32_t)g.pt_wp, (uint32_t)(g.pt_rows + 2 * L.dil));
+    if (e) return fail(h, DGP_ERR_CUDA, "%s: %s", L.scope.c_str(), e);
+    e = make_tmap_2d(&g.tmap_b, L.w, (uint64_t)L.Npad, (uint64_t)L.K, (uint64_t)L.K * 2, (uint32_t)bn);
+    if (e) return fail(h, DGP_ERR_CUDA, "%s: %s", L.scope.c_str(), e);
+    st->kind = STEP_GEMM;
+    st->out_ptr = out;
+    st->oN = N; st->oH = P; st->oW = Q; st->oC = L.Npad;
+    return DGP_OK;
+  }
+  if (int rc = setup_epilogue(h, g, L.scope.c_str(), N)) return rc;
   const bool pointwise = (L.R == 1 && L.S == 1 && L.stride == 1);
   if (pointwise) {
     g.a_mode = 0;
@@ -435,26 +464,11 @@ int make_wgrad_params(dgp_handle* h, const char* scope, int R, int S, int Cin, i
 
 int keep_activation(dgp_handle* h, const Step& st, cudaStream_t s);
 
-// Experiment knob (off by default): with DGP_CONV1_CHUNK_MB=<n> conv1 + pool1 run over chunks of frames that share ONE
-// conv1-output buffer of at most n MB, hoping that conv1's output (20 MB per 747x832 frame, the largest tensor of the net)
-// is consumed by the pool out of the L2 and overwritten by the next chunk before it is evicted.  Measured on B200
-// (profiles/r02_conv1_chunk_ab.md): no gain at 40 / 64 / 100 / 128 MB -- the L2 writes dirty lines back regardless, and the
-// extra launches cost 50 us -- so the default is one launch over the whole batch.  Outputs are bit-identical either way.
-int conv1_chunk_frames(int B, size_t frame_bytes) {
-  static long budget_mb = -1;
-  if (budget_mb < 0) {
-    const char* e = getenv("DGP_CONV1_CHUNK_MB");
-    budget_mb = e ? atol(e) : 0;
-  }
-  if (budget_mb == 0) return B;
-  long n = (long)((size_t)budget_mb * 1024 * 1024 / frame_bytes);
-  if (n < 1) n = 1;
-  return n < B ? (int)n : B;
-}
-
 int build_plan(dgp_handle* h, int B, int H, int W, bool train, Plan** out) {
-  // debug runs (dgp_debug_keep_activations) need conv1's whole output: they get their own unchunked plan (key -B)
-  const bool unchunked = train || h->debug_keep;
+  // Inference plans run conv1 fused with pool1 (conv_gemm_kernel a_mode / epi_mode 2): conv1's output -- 20 MB per 747x832
+  // frame, the largest tensor of the net -- never reaches HBM.  Training keeps it for the backward pass and debug runs
+  // (dgp_debug_keep_activations) dump it: those plans (key -B for the debug one) run conv1 and the pool as two launches.
+  const bool unfused = train || h->debug_keep || getenv("DGP_NO_POOL_FUSION") != nullptr;
   auto key = std::make_tuple((!train && h->debug_keep) ? -B : B, H, W);
   auto& plans = train ? h->train_plans : h->plans;
   auto it = plans.find(key);
@@ -506,13 +520,11 @@ int build_plan(dgp_handle* h, int B, int H, int W, bool train, Plan** out) {
       hh = ho; ww = wo; cin = u.depth;
     }
   }
-  const size_t c1_frame_bytes = (size_t)pl->H1 * pl->W1 * 64 * 2;
-  const int chunk = unchunked ? B : conv1_chunk_frames(B, c1_frame_bytes);
-  const size_t big = (size_t)chunk * c1_frame_bytes;
+  const size_t big = (size_t)B * pl->H1 * pl->W1 * 64 * 2;
   const size_t x_bytes = (size_t)B * max_x * 2 + 1024, t_bytes = (size_t)B * max_t * 2 + 1024,
                sc_bytes = (size_t)B * max_sc * 2 + 1024;
   void *c1 = nullptr, *xa = nullptr, *xb = nullptr, *t1 = nullptr, *t2 = nullptr, *sc = nullptr;
-  if ((rc = alloc_buf(h, pl.get(), big, &c1))) return rc;
+  if (unfused && (rc = alloc_buf(h, pl.get(), big, &c1))) return rc;
   int Hc, Wc, pad_t, pad_l;
   same_pad(pl->H1, 3, 2, 1, &pad_t, &Hc);
   same_pad(pl->W1, 3, 2, 1, &pad_l, &Wc);
@@ -527,42 +539,62 @@ int build_plan(dgp_handle* h, int B, int H, int W, bool train, Plan** out) {
     if ((rc = alloc_buf(h, pl.get(), (size_t)B * Hc * Wc * 64 * 2 + 1024, &xa))) return rc;
   }
   pl->c1 = c1; pl->pool = xa; pl->Hp = Hc; pl->Wp = Wc; pl->pool_pad_t = pad_t; pl->pool_pad_l = pad_l;
-  for (int f0 = 0; f0 < B; f0 += chunk) {
-    const int nf = (B - f0) < chunk ? (B - f0) : chunk;
-    {
-      const ConvLayer& L = h->layers[h->conv1_layer];
-      Step st;
-      memset(&st.gp, 0, sizeof(st.gp));
-      ConvGemmParams& g = st.gp;
-      g.fp16 = h->fp16;
-      tmap_set_fp16(h->fp16);
-      g.M = nf * pl->H1 * pl->W1; g.N = 64; g.block_n = 64; g.num_k_blocks = 4; g.a_mode = 1;
-      g.P = pl->H1; g.Q = pl->W1; g.conv_stride = 1; g.lower_h = 0; g.lower_w = 0; g.S = 1; g.dil = 1; g.cblocks = 1;
-      g.scale = L.scale; g.shift = L.shift; g.residual = nullptr; g.res_sub = 1; g.relu = 1;
-      g.out = c1; g.out_f32 = 0; g.ldc = 64;
-      g.num_m_blocks = ceil_div(g.M, kBlockM); g.num_n_blocks = 1;
+  {
+    const ConvLayer& L = h->layers[h->conv1_layer];
+    Step st;
+    memset(&st.gp, 0, sizeof(st.gp));
+    ConvGemmParams& g = st.gp;
+    g.fp16 = h->fp16;
+    tmap_set_fp16(h->fp16);
+    g.M = B * pl->H1 * pl->W1; g.N = 64; g.block_n = 64; g.num_k_blocks = 4;
+    g.P = pl->H1; g.Q = pl->W1; g.conv_stride = 1; g.lower_h = 0; g.lower_w = 0; g.S = 1; g.dil = 1; g.cblocks = 1;
+    g.scale = L.scale; g.shift = L.shift; g.residual = nullptr; g.res_sub = 1; g.relu = 1;
+    g.out_f32 = 0; g.ldc = 64; g.num_n_blocks = 1;
+    uint32_t pixels_per_load;
+    if (unfused) {
+      g.a_mode = 1;
+      g.out = c1;
+      g.num_m_blocks = ceil_div(g.M, kBlockM);
       g.tmem_cols = tmem_cols_for(64);
-      if ((rc = setup_epilogue(h, g, "conv1", nf))) return rc;
-      const __nv_bfloat16* s2d_chunk = pl->s2d + (size_t)f0 * pl->Hs * pl->Ws * 16;
-      const char* e = make_tmap_im2col(&g.tmap_a, s2d_chunk, 64, (uint64_t)pl->W1, (uint64_t)pl->Hs, (uint64_t)nf, 32,
-                                       (uint64_t)pl->Ws * 32, (uint64_t)pl->Hs * pl->Ws * 32, 0, 0, 0, -3, 1,
-                                       (uint64_t)nf * pl->Hs * pl->Ws * 32, kBlockM * g.msub);
-      if (e) return fail(h, DGP_ERR_CUDA, "conv1: %s", e);
-      e = make_tmap_2d(&g.tmap_b, L.w, 64, 256, 512, 64);
-      if (e) return fail(h, DGP_ERR_CUDA, "conv1: %s", e);
-      st.kind = STEP_GEMM; st.out_ptr = c1;
-      if (chunk == B) st.end_point = "resnet_v1_50/conv1";
-      st.oN = nf; st.oH = pl->H1; st.oW = pl->W1; st.oC = 64;
-      pl->steps.push_back(st);
+      if ((rc = setup_epilogue(h, g, "conv1", B))) return rc;
+      pixels_per_load = kBlockM * g.msub;
+    } else {
+      // a tile = the 15 x 17 patch of conv1 outputs (255 of the 256 accumulator rows) under 7 x 8 pooled pixels
+      g.a_mode = 2; g.epi_mode = 2; g.epi_bufs = 0; g.msub = 2;
+      g.out = xa;
+      g.pool_R = 7; g.pool_C = 8; g.pool_H = Hc; g.pool_W = Wc; g.pool_pad_t = pad_t; g.pool_pad_l = pad_l;
+      g.pool_tiles_i = ceil_div(Hc, g.pool_R); g.pool_tiles_j = ceil_div(Wc, g.pool_C);
+      g.num_m_blocks = B * g.pool_tiles_i * g.pool_tiles_j;
+      g.tmem_cols = tmem_cols_for(64 * g.msub);
+      g.num_stages = conv_gemm_pick_stages(g);
+      pixels_per_load = 0;
     }
-    {
-      Step st; st.kind = STEP_POOL;
-      st.pin = (const __nv_bfloat16*)c1; st.pN = nf; st.pH = pl->H1; st.pW = pl->W1; st.pC = 64; st.pad_t = pad_t; st.pad_l = pad_l;
-      st.out_ptr = (__nv_bfloat16*)xa + (size_t)f0 * Hc * Wc * 64;
-      if (chunk == B) st.end_point = "resnet_v1_50/pool1";
-      st.oN = nf; st.oH = Hc; st.oW = Wc; st.oC = 64;
-      pl->steps.push_back(st);
+    const char* e = unfused
+        ? make_tmap_im2col(&g.tmap_a, pl->s2d, 64, (uint64_t)pl->W1, (uint64_t)pl->Hs, (uint64_t)B, 32, (uint64_t)pl->Ws * 32,
+                           (uint64_t)pl->Hs * pl->Ws * 32, 0, 0, 0, -3, 1, (uint64_t)B * pl->Hs * pl->Ws * 32, pixels_per_load)
+        : make_tmap_tiled4d(&g.tmap_a, pl->s2d, 64, (uint64_t)pl->W1, (uint64_t)pl->Hs, (uint64_t)B, 32, (uint64_t)pl->Ws * 32,
+                            (uint64_t)pl->Hs * pl->Ws * 32, (uint32_t)(2 * g.pool_C + 1), (uint32_t)(2 * g.pool_R + 1));
+    if (e) return fail(h, DGP_ERR_CUDA, "conv1: %s", e);
+    e = make_tmap_2d(&g.tmap_b, L.w, 64, 256, 512, 64);
+    if (e) return fail(h, DGP_ERR_CUDA, "conv1: %s", e);
+    st.kind = STEP_GEMM;
+    if (unfused) {
+      st.out_ptr = c1;
+      st.end_point = "resnet_v1_50/conv1";
+      st.oN = B; st.oH = pl->H1; st.oW = pl->W1; st.oC = 64;
+    } else {
+      st.out_ptr = xa;
+      st.oN = B; st.oH = Hc; st.oW = Wc; st.oC = 64;
     }
+    pl->steps.push_back(st);
+  }
+  if (unfused) {
+    Step st; st.kind = STEP_POOL;
+    st.pin = (const __nv_bfloat16*)c1; st.pN = B; st.pH = pl->H1; st.pW = pl->W1; st.pC = 64; st.pad_t = pad_t; st.pad_l = pad_l;
+    st.out_ptr = xa;
+    st.end_point = "resnet_v1_50/pool1";
+    st.oN = B; st.oH = Hc; st.oW = Wc; st.oC = 64;
+    pl->steps.push_back(st);
   }
   // ---- bottleneck units
   void* x = xa;

@@ -27,6 +27,7 @@ constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KiB
 constexpr int kMaxStages = 8;
 constexpr int kMaxEpiBufs = 4;
 constexpr int kEpiUnitBytes = 32 * kEpiUnitCols * 2;  // one warp's 32 rows x 32 columns
+constexpr int kPatchBytes = 256 * 128;                 // epi_mode 2: one 256-pixel x 64-channel patch of conv1 outputs
 
 __device__ __forceinline__ float bf16lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
@@ -99,19 +100,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stages = p.num_stages;
   const int msub = p.msub;                     // 128-row sub-tiles per CTA tile (BLOCK_M = 128 * msub)
-  const int a_bytes = msub * kABytes;
+  const int a_bytes = p.a_mode == 3 ? p.pt_stage_bytes : msub * kABytes;
   const int b_bytes = p.block_n * kBlockK * 2;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + stages * a_bytes;
-  uint8_t* smem_epi = smem_b + stages * b_bytes;  // [16 warps][epi_bufs][2 KiB], 1024 B aligned
+  uint8_t* smem_epi = smem_b + (p.a_mode == 3 ? p.num_k_blocks : stages) * b_bytes;  // [16 warps][epi_bufs][2 KiB], 1024 B aligned
   const int epi_bufs = p.epi_mode == 1 ? p.epi_bufs : 0;
-  float* smem_ss = reinterpret_cast<float*>(smem_epi + kEpiWarps * epi_bufs * kEpiUnitBytes);  // [16 warps][2 sets][scale 32 | shift 32]
+  float* smem_ss = reinterpret_cast<float*>(smem_epi + (p.epi_mode == 2 ? 2 * kPatchBytes : kEpiWarps * epi_bufs * kEpiUnitBytes));  // [16 warps][2 sets][scale 32 | shift 32]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_ss + kEpiWarps * 128);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tmem_full_bar = empty_bar + kMaxStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
   uint64_t* res_bar = tmem_empty_bar + 2;  // [16 warps][kMaxEpiBufs]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + kEpiWarps * kMaxEpiBufs);
+  uint64_t* b_bar = res_bar + kEpiWarps * kMaxEpiBufs;  // a_mode 3: the resident weight matrix has landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -134,6 +136,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       ptx::mbar_init(&tmem_empty_bar[a], kEpiWarps);
     }
     for (int i = 0; i < kEpiWarps * kMaxEpiBufs; ++i) ptx::mbar_init(&res_bar[i], 1);
+    ptx::mbar_init(b_bar, 1);
     ptx::fence_mbar_init();
   }
   if (warp == 2) {
@@ -161,6 +164,58 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     const int PQ = p.P * p.Q, Q = p.Q, nnb = p.num_n_blocks, nkb = p.num_k_blocks, block_n = p.block_n;
     const int a_mode = p.a_mode, cblocks = p.cblocks, S = p.S, dil = p.dil, cstride = p.conv_stride;
     const int lower_w = p.lower_w, lower_h = p.lower_h, block_m = kBlockM * msub;
+    if (a_mode == 3) {
+      // shared-memory resident input patch: the whole weight matrix once, then ONE tiled box (patch + halo, zero filled
+      // outside the image) per tile
+      const int tiles_j = p.pool_tiles_j, tiles_ij = p.pool_tiles_i * tiles_j;
+      const uint32_t box_bytes = (uint32_t)(p.pt_wp * (p.pt_rows + 2 * dil) * 128);
+      if (lane == 0) {
+        ptx::mbar_arrive_expect_tx(b_bar, (uint32_t)(nkb * b_bytes));
+        for (int kb = 0; kb < nkb; ++kb) ptx::tma_load_2d(smem_b + kb * b_bytes, &p.tmap_b, b_bar, kb * kBlockK, 0);
+      }
+      __syncwarp();
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int img = tile / tiles_ij;
+        const int rem = tile - img * tiles_ij;
+        const int ti = rem / tiles_j;
+        const int tj = rem - ti * tiles_j;
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (lane == 0) {
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], box_bytes);
+          ptx::tma_load_4d(smem_a + stage * a_bytes, &p.tmap_a, &full_bar[stage], 0, tj * p.pt_cols - dil, ti * p.pt_rows - dil, img);
+        }
+        __syncwarp();
+        if (++stage == stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    } else if (a_mode == 2) {
+      // conv1 + pool1: the A tile is a 2-D patch of conv outputs = ONE tiled box per filter-row tap (the tensor map's
+      // "pixels" are overlapping 4-pixel windows of the space-to-depth input; rows / columns past the end read as zero)
+      const int tiles_j = p.pool_tiles_j, tiles_ij = p.pool_tiles_i * tiles_j;
+      const uint32_t tx = (uint32_t)((2 * p.pool_R + 1) * (2 * p.pool_C + 1) * 128 + b_bytes);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int img = tile / tiles_ij;
+        const int rem = tile - img * tiles_ij;
+        const int ti = rem / tiles_j;
+        const int tj = rem - ti * tiles_j;
+        const int ra = max(0, 2 * ti * p.pool_R - p.pool_pad_t), ca = max(0, 2 * tj * p.pool_C - p.pool_pad_l);
+        for (int kb = 0; kb < nkb; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (lane == 0) {
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], tx);
+            ptx::tma_load_4d(smem_a + stage * a_bytes, &p.tmap_a, &full_bar[stage], 0, ca, ra + kb, img);
+            ptx::tma_load_2d(smem_b + stage * b_bytes, &p.tmap_b, &full_bar[stage], kb * kBlockK, 0);
+          }
+          __syncwarp();
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    } else
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / nnb;
       const int n_blk = tile - m_blk * nnb;
@@ -250,7 +305,46 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         if (acc == 0) acc_phase ^= 1;
       }
     };
-    if (msub == 2) run(std::integral_constant<int, 2>{});
+    if (p.a_mode == 3) {
+      // 3x3 taps as row-shifted views of the resident patch: accumulator row m reads patch row m + (kr*Wp + ks)*dil
+      const int Wp = p.pt_wp, dil = p.dil, bo_mode = p.pt_base_offset_mode;
+      const uint32_t a0 = ptx::smem_u32(smem_a);
+      ptx::mbar_wait(b_bar, 0);
+      ptx::tc_fence_after();
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        ptx::mbar_wait(&full_bar[stage], phase);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint32_t tmem_d = tmem_base + (uint32_t)acc * acc_cols;
+          const uint32_t abase = a0 + (uint32_t)(stage * a_bytes);
+#pragma unroll 1
+          for (int tap = 0; tap < 9; ++tap) {
+            const int kr = tap / 3, ks = tap - kr * 3;
+            const uint32_t shift = (uint32_t)((kr * Wp + ks) * dil) * 128u;
+            const uint64_t bdesc = bdesc0 + (uint64_t)(tap * b_step);
+#pragma unroll
+            for (int sub = 0; sub < 2; ++sub) {
+              const uint32_t start = abase + shift + (uint32_t)sub * (uint32_t)kABytes;
+              const uint64_t adesc = ptx::make_desc_k_sw128(start, bo_mode ? (start >> 7) : 0u);
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k)
+                ptx::umma_bf16(tmem_d + (uint32_t)(sub * block_n), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                               (tap | k) != 0);
+            }
+          }
+          ptx::umma_commit(&empty_bar[stage]);
+          ptx::umma_commit(&tmem_full_bar[acc]);
+        }
+        __syncwarp();
+        if (++stage == stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    } else if (msub == 2) run(std::integral_constant<int, 2>{});
     else run(std::integral_constant<int, 1>{});
   } else if (p.epi_mode == 0) {
     // -------------------------------------------------------------- epilogue, direct stores (fp32 head GEMM)
@@ -303,6 +397,183 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else if (p.epi_mode == 3) {
+    // -------------------------------------------------------------- epilogue of a patch tile (a_mode 3): direct stores
+    // accumulator row m = pr * Wp + pc lies on the input-patch grid; rows with pc >= pt_cols or pr >= pt_rows are halo
+    // positions (junk) and are not stored.  Every lane owns one pixel x 32 channels = 64 contiguous bytes of the output.
+    const int quad = warp & 3;
+    const int ew = warp - 2;
+    const int cg = ew >> 2;
+    const int sub = cg >> 1, colg = cg & 1;
+    float* ss = smem_ss + ew * 128;
+    if (lane < 16) {
+      const int is_shift = lane >> 3, i = (lane & 7) * 4;
+      const float* src = is_shift ? p.shift : p.scale;
+      const float fill = is_shift ? 0.f : 1.f;
+      const float4 val = src ? __ldg(reinterpret_cast<const float4*>(src + colg * 32 + i)) : make_float4(fill, fill, fill, fill);
+      *reinterpret_cast<float4*>(ss + is_shift * 32 + i) = val;
+    }
+    __syncwarp();
+    const int tiles_j = p.pool_tiles_j, tiles_ij = p.pool_tiles_i * tiles_j;
+    const int m = sub * 128 + quad * 32 + lane;
+    const int pr = m / p.pt_wp, pc = m - pr * p.pt_wp;
+    const bool in_tile = pr < p.pt_rows && pc < p.pt_cols;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int img = tile / tiles_ij;
+      const int rem = tile - img * tiles_ij;
+      const int ti = rem / tiles_j;
+      const int tj = rem - ti * tiles_j;
+      ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((acc * 2 + sub) * 64 + colg * 32);
+      uint32_t v[2][16];
+      ptx::tmem_ld_x16(taddr, v[0]);
+      ptx::tmem_ld_x16(taddr + 16, v[1]);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+      const int r = ti * p.pt_rows + pr, c = tj * p.pt_cols + pc;
+      if (in_tile && r < p.P && c < p.Q) {
+        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.out) +
+                                              ((((size_t)img * p.P + r) * p.Q + c) * p.ldc + colg * 32) * 2);
+#pragma unroll
+        for (int s2 = 0; s2 < 2; ++s2) {
+          uint32_t o[8];
+#pragma unroll
+          for (int i = 0; i < 8; i += 2) {
+            const float4 sc = *reinterpret_cast<const float4*>(ss + s2 * 16 + 2 * i);
+            const float4 sh = *reinterpret_cast<const float4*>(ss + 32 + s2 * 16 + 2 * i);
+            const ptx::f32x2 q0 = ptx::fma2(ptx::pk2(__uint_as_float(v[s2][2 * i]), __uint_as_float(v[s2][2 * i + 1])),
+                                            ptx::pk2(sc.x, sc.y), ptx::pk2(sh.x, sh.y));
+            const ptx::f32x2 q1 = ptx::fma2(ptx::pk2(__uint_as_float(v[s2][2 * i + 2]), __uint_as_float(v[s2][2 * i + 3])),
+                                            ptx::pk2(sc.z, sc.w), ptx::pk2(sh.z, sh.w));
+            float a0, a1, b0, b1;
+            ptx::upk2(q0, a0, a1);
+            ptx::upk2(q1, b0, b1);
+            if (p.relu) {
+              o[i] = ptx::cvt_pack16<kFp16, true>(a0, a1);
+              o[i + 1] = ptx::cvt_pack16<kFp16, true>(b0, b1);
+            } else {
+              o[i] = ptx::cvt_pack16<kFp16, false>(a0, a1);
+              o[i + 1] = ptx::cvt_pack16<kFp16, false>(b0, b1);
+            }
+          }
+          dst[2 * s2] = make_uint4(o[0], o[1], o[2], o[3]);
+          dst[2 * s2 + 1] = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else if (p.epi_mode == 2) {
+    // -------------------------------------------------------------- epilogue, conv1 + BN + ReLU + 3x3/2 max-pool
+    // The 256 accumulator rows are the pixels of a (2R+1) x (2C+1) patch of conv1 outputs (row-major).  Every warp turns
+    // its 32 rows x 32 channels into 16-bit activations in a shared-memory copy of the patch (128 B per pixel, 16-byte
+    // units XOR-swizzled by the pixel index), the 16 warps meet on one named barrier, and 512 threads reduce the R x C
+    // pooled pixels (one 16-byte channel group each, nine LDS.128 + packed max) straight to global memory.  conv1's
+    // 20 MB-per-frame output never reaches HBM.  The patch is double buffered: one barrier per tile suffices.
+    const int quad = warp & 3;
+    const int ew = warp - 2;
+    const int cg = ew >> 2;
+    const int sub = cg >> 1, colg = cg & 1;
+    float* ss = smem_ss + ew * 128;
+    if (lane < 16) {
+      const int is_shift = lane >> 3, i = (lane & 7) * 4;
+      const float* src = is_shift ? p.shift : p.scale;
+      const float fill = is_shift ? 0.f : 1.f;
+      const float4 val = src ? __ldg(reinterpret_cast<const float4*>(src + colg * 32 + i)) : make_float4(fill, fill, fill, fill);
+      *reinterpret_cast<float4*>(ss + is_shift * 32 + i) = val;
+    }
+    __syncwarp();
+    const int R = p.pool_R, Cp = p.pool_C, Cw = 2 * p.pool_C + 1, H1 = p.P, W1 = p.Q;
+    const int tiles_j = p.pool_tiles_j, tiles_ij = p.pool_tiles_i * tiles_j;
+    const int px = sub * 128 + quad * 32 + lane;
+    const int item = (int)threadIdx.x - 64;          // pooling work item: (pooled pixel, 16-byte channel group)
+    const int pv = item & 7, pp = item >> 3;
+    const int pi = pp / Cp, pj = pp - pi * Cp;
+    const bool pool_thread = pp < R * Cp;
+    int acc = 0, pb = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int img = tile / tiles_ij;
+      const int rem = tile - img * tiles_ij;
+      const int ti = rem / tiles_j;
+      const int tj = rem - ti * tiles_j;
+      ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((acc * 2 + sub) * 64 + colg * 32);
+      uint32_t v[2][16];
+      ptx::tmem_ld_x16(taddr, v[0]);
+      ptx::tmem_ld_x16(taddr + 16, v[1]);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);   // the accumulator is in registers: the MMA may reuse it
+      uint8_t* patch = smem_epi + pb * kPatchBytes;
+      uint8_t* my_row = patch + px * 128;
+#pragma unroll
+      for (int s2 = 0; s2 < 2; ++s2) {
+        uint32_t o[8];
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+          const float4 sc = *reinterpret_cast<const float4*>(ss + s2 * 16 + 2 * i);
+          const float4 sh = *reinterpret_cast<const float4*>(ss + 32 + s2 * 16 + 2 * i);
+          const ptx::f32x2 q0 = ptx::fma2(ptx::pk2(__uint_as_float(v[s2][2 * i]), __uint_as_float(v[s2][2 * i + 1])),
+                                          ptx::pk2(sc.x, sc.y), ptx::pk2(sh.x, sh.y));
+          const ptx::f32x2 q1 = ptx::fma2(ptx::pk2(__uint_as_float(v[s2][2 * i + 2]), __uint_as_float(v[s2][2 * i + 3])),
+                                          ptx::pk2(sc.z, sc.w), ptx::pk2(sh.z, sh.w));
+          float a0, a1, b0, b1;
+          ptx::upk2(q0, a0, a1);
+          ptx::upk2(q1, b0, b1);
+          o[i] = ptx::cvt_pack16<kFp16, true>(a0, a1);
+          o[i + 1] = ptx::cvt_pack16<kFp16, true>(b0, b1);
+        }
+        const int u = colg * 4 + 2 * s2;
+        *reinterpret_cast<uint4*>(my_row + ((u ^ (px & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<uint4*>(my_row + (((u + 1) ^ (px & 7)) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
+      }
+      ptx::named_bar_sync(1, kEpiWarps * 32);
+      if (pool_thread) {
+        const int i = ti * R + pi, j = tj * Cp + pj;
+        if (i < p.pool_H && j < p.pool_W) {
+          const int ra = max(0, 2 * ti * R - p.pool_pad_t), ca = max(0, 2 * tj * Cp - p.pool_pad_l);
+          uint32_t m[4] = {0u, 0u, 0u, 0u};          // post-ReLU values are >= 0 and every window holds a valid pixel
+#pragma unroll
+          for (int dr = 0; dr < 3; ++dr) {
+            const int rr = 2 * i - p.pool_pad_t + dr;
+            if (rr < 0 || rr >= H1) continue;
+#pragma unroll
+            for (int dc = 0; dc < 3; ++dc) {
+              const int cc = 2 * j - p.pool_pad_l + dc;
+              if (cc < 0 || cc >= W1) continue;
+              const int q = (rr - ra) * Cw + (cc - ca);
+              const uint4 x = *reinterpret_cast<const uint4*>(patch + q * 128 + ((pv ^ (q & 7)) << 4));
+              const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (kFp16) {
+                  const __half2 z = __hmax2(*reinterpret_cast<const __half2*>(&m[k]), *reinterpret_cast<const __half2*>(&xs[k]));
+                  m[k] = *reinterpret_cast<const uint32_t*>(&z);
+                } else {
+                  const __nv_bfloat162 z = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&m[k]),
+                                                   *reinterpret_cast<const __nv_bfloat162*>(&xs[k]));
+                  m[k] = *reinterpret_cast<const uint32_t*>(&z);
+                }
+              }
+            }
+          }
+          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.out) +
+                                                ((((size_t)img * p.pool_H + i) * p.pool_W + j) * 64 + pv * 8) * 2);
+          *dst = make_uint4(m[0], m[1], m[2], m[3]);
+        }
+      }
+      pb ^= 1;
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -535,17 +806,45 @@ const char* make_tmap_im2col(CUtensorMap* out, const void* base, uint64_t C, uin
   return nullptr;
 }
 
-size_t conv_gemm_smem_bytes(int block_n, int num_stages, int epi_bufs, int msub) {
-  return 1024 + (size_t)num_stages * ((size_t)msub * kABytes + (size_t)block_n * kBlockK * 2) +
-         (size_t)kEpiWarps * epi_bufs * kEpiUnitBytes + kEpiWarps * 128 * sizeof(float) +
-         (2 * kMaxStages + 4 + kEpiWarps * kMaxEpiBufs) * 8 + 16;
+size_t conv_gemm_smem_bytes(const ConvGemmParams& p) {
+  const size_t a_bytes = p.a_mode == 3 ? (size_t)p.pt_stage_bytes : (size_t)p.msub * kABytes;
+  const size_t b_bytes = (size_t)p.block_n * kBlockK * 2;
+  const size_t epi = p.epi_mode == 2 ? (size_t)2 * kPatchBytes : (p.epi_mode == 1 ? (size_t)kEpiWarps * p.epi_bufs * kEpiUnitBytes : 0);
+  return 1024 + (size_t)p.num_stages * a_bytes + (size_t)(p.a_mode == 3 ? p.num_k_blocks : p.num_stages) * b_bytes + epi +
+         kEpiWarps * 128 * sizeof(float) + (2 * kMaxStages + 4 + kEpiWarps * kMaxEpiBufs + 1) * 8 + 16;
 }
 
-int conv_gemm_pick_stages(int block_n, int epi_bufs, int msub) {
+int conv_gemm_pick_stages(ConvGemmParams p) {
   const size_t budget = 227 * 1024;
-  int s = kMaxStages;
-  while (s > 2 && conv_gemm_smem_bytes(block_n, s, epi_bufs, msub) > budget) --s;
-  return s;
+  p.num_stages = kMaxStages;
+  while (p.num_stages > 2 && conv_gemm_smem_bytes(p) > budget) --p.num_stages;
+  return p.num_stages;
+}
+
+int conv_patch_stage_bytes(int pt_wp, int dil) {
+  // 256 accumulator rows + the largest tap shift, 128 B per row, rounded up to the 1024 B swizzle period
+  const int rows = 256 + (2 * pt_wp + 2) * dil;
+  return (rows * 128 + 1023) / 1024 * 1024;
+}
+
+const char* make_tmap_tiled4d(CUtensorMap* out, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t N,
+                              uint64_t stride_w_bytes, uint64_t stride_h_bytes, uint64_t stride_n_bytes, uint32_t box_w,
+                              uint32_t box_h) {
+  if (const char* e = tma_init()) return e;
+  if (C != 64) return "make_tmap_tiled4d: 64 channels expected";
+  cuuint64_t dims[4] = {C, W, H, N};
+  cuuint64_t strides[3] = {stride_w_bytes, stride_h_bytes, stride_n_bytes};
+  cuuint32_t box[4] = {64, box_w, box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  if (box_w > 256 || box_h > 256) return "make_tmap_tiled4d: box too large";
+  CUresult r = g_encode_tiled(out, g_tmap_fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims,
+                              strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_err, sizeof(g_err), "cuTensorMapEncodeTiled (4-D) failed: %d", (int)r);
+    return g_err;
+  }
+  return nullptr;
 }
 
 cudaError_t launch_conv_gemm(const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
@@ -559,7 +858,8 @@ cudaError_t launch_conv_gemm(const ConvGemmParams& p, int num_sms, cudaStream_t 
   }
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   const int grid = tiles < num_sms ? tiles : num_sms;
-  const size_t smem = conv_gemm_smem_bytes(p.block_n, p.num_stages, p.epi_mode == 1 ? p.epi_bufs : 0, p.msub);
+  const size_t smem = conv_gemm_smem_bytes(p);
+  if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kThreads);

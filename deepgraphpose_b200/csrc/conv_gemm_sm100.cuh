@@ -34,7 +34,9 @@ struct ConvGemmParams {
   int block_n;       // UMMA N (multiple of 16, 16..256)
   int msub;          // 128-row sub-tiles per CTA tile: 1, or 2 (BLOCK_M = 256) for narrow layers (block_n <= 128)
   int num_k_blocks;  // K / 64
-  int a_mode;        // 0 = tiled [M,K], 1 = im2col
+  int a_mode;        // 0 = tiled [M,K], 1 = im2col, 2 = im2col by 2-D patches (conv1 fused with the 3x3/2 max-pool),
+                     // 3 = shared-memory resident input patch (3x3 stride-1 convs with 64 input channels): ONE tiled TMA box
+                     //     per tile, the nine taps are row-shifted UMMA descriptors over it, all weights stay resident
   int fp16;          // 0 = bf16 activations/weights (default), 1 = fp16 storage (same kind::f16 MMA, fp32 accumulate)
   // im2col geometry (a_mode == 1)
   int P, Q;          // output height / width
@@ -46,7 +48,9 @@ struct ConvGemmParams {
   // epilogue
   const float* scale;  // [N] or nullptr (=1)
   const float* shift;  // [N] or nullptr (=0)
-  int epi_mode;      // 0 = direct register->global stores (fp32 head GEMM), 1 = TMA-staged bf16 (+ TMA residual)
+  int epi_mode;      // 0 = direct register->global stores (fp32 head GEMM), 1 = TMA-staged 16-bit (+ TMA residual),
+                     // 2 = BN + ReLU + 3x3 stride-2 max-pool of a 2-D patch (a_mode 2), pooled pixels stored directly,
+                     // 3 = direct masked 16-bit stores of a patch tile (a_mode 3)
   int epi_bufs;      // 2 KB staging buffers per epilogue warp (epi_mode 1): 2..4; the residual prefetch runs epi_bufs-1 units ahead
   const __nv_bfloat16* residual;  // nullptr = none
   int res_sub;       // 1 = same pixel grid as the output, 2 = residual grid is (res_H, res_W), read at (2p, 2q)
@@ -59,6 +63,13 @@ struct ConvGemmParams {
   int num_m_blocks, num_n_blocks;
   int num_stages;
   int tmem_cols;     // power of two >= 2 * block_n
+  // a_mode / epi_mode 2 (conv1 + pool1): a tile is the (2R+1) x (2C+1) patch of conv outputs under R x C pooled pixels;
+  // P, Q are the conv output dims, pool_H / pool_W the pooled dims, pool_pad_* the TF SAME padding of the pool (0 or 1)
+  int pool_R, pool_C, pool_H, pool_W, pool_pad_t, pool_pad_l, pool_tiles_i, pool_tiles_j;
+  // a_mode 3: output tile = pt_rows x pt_cols pixels (tile grid pool_tiles_i x pool_tiles_j per image); accumulator row
+  // m = r * pt_wp + c over the INPUT patch grid (pt_wp = pt_cols + 2 * dil columns), so tap (kr, ks) reads smem rows
+  // m + (kr * pt_wp + ks) * dil: a constant shift of the descriptor start address
+  int pt_rows, pt_cols, pt_wp, pt_stage_bytes, pt_base_offset_mode;
 };
 
 // Weight-gradient GEMM (wgrad_gemm_sm100.cu): dW[co, kk] = sum_p dy[p, co] * xcol[p, kk], kk = (tap, ci).
@@ -92,8 +103,13 @@ const char* make_tmap_im2col(CUtensorMap* out, const void* base, uint64_t C, uin
                              uint64_t stride_w_bytes, uint64_t stride_h_bytes, uint64_t stride_n_bytes, int lower_w,
                              int lower_h, int upper_w, int upper_h, int conv_stride, uint64_t total_bytes,
                              uint32_t pixels_per_column = kBlockM, uint32_t channels_per_pixel = kBlockK);
-size_t conv_gemm_smem_bytes(int block_n, int num_stages, int epi_bufs, int msub);
-int conv_gemm_pick_stages(int block_n, int epi_bufs, int msub);
+// a_mode 3: patch stage bytes (1024-aligned) for a tile geometry, and the tiled 4-D activation map (box = whole input patch)
+int conv_patch_stage_bytes(int pt_wp, int dil);
+const char* make_tmap_tiled4d(CUtensorMap* out, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t N,
+                              uint64_t stride_w_bytes, uint64_t stride_h_bytes, uint64_t stride_n_bytes, uint32_t box_w,
+                              uint32_t box_h);
+size_t conv_gemm_smem_bytes(const ConvGemmParams& p);   // uses block_n, num_stages, epi_*, msub, a_mode, pt_stage_bytes, num_k_blocks
+int conv_gemm_pick_stages(ConvGemmParams p);            // largest num_stages (<= 8) that fits 227 KB
 cudaError_t launch_conv_gemm(const ConvGemmParams& p, int num_sms, cudaStream_t stream);
 
 }  // namespace dgp

@@ -149,6 +149,14 @@ __device__ __forceinline__ void tma_load_im2col_4d(void* smem_dst, const void* t
       : "memory");
 }
 
+// tiled-mode load of a 4-D box (dims C,W,H,N): coordinates may be negative / past the end, those elements read as zero
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* tmap, uint64_t* bar, int c, int w, int h, int n) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n)
+      : "memory");
+}
+
 // 2-D tile store smem -> global (bulk async group; out-of-bounds rows/cols are clipped by the hardware).
 // 1-D bulk async copy global -> shared (bytes % 16 == 0, both addresses 16 B aligned), completion on an mbarrier
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
@@ -211,8 +219,10 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (rows of 128 B, 8-row atoms 1024 B apart).
 // Bit layout: cute::UMMA::SmemDescriptor (start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
 // version=1 [46,48), layout_type=2 (SWIZZLE_128B) [61,64)).
-__device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t smem_addr) {
+// base_offset [49,52): phase of the 8-row swizzle pattern at the start address when it is not 1024 B aligned.
+__device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t smem_addr, uint32_t base_offset = 0) {
   uint64_t d = 0;
+  d |= (uint64_t)(base_offset & 7) << 49;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
   d |= (uint64_t)1 << 16;            // LBO (unused for swizzled K-major), canonical value 1
   d |= (uint64_t)(1024 >> 4) << 32;  // SBO = 1024 B between 8-row groups

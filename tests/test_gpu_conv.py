@@ -39,6 +39,9 @@ CASES = [
     (3, 47, 52, 256, 1024, 1, 1, 1, 0, True, True, 1, True, 0, False),    # block3 shapes, > 148 tiles (persistent loop)
     (3, 47, 52, 256, 256, 3, 1, 1, 1, True, False, 1, True, 0, False),
     (1, 5, 5, 64, 64, 3, 1, 1, 2, False, False, 1, False, 0, True),       # VALID
+    (3, 47, 52, 64, 64, 3, 1, 1, 1, True, False, 1, True, 0, False),      # shared-memory resident patch path: many tiles,
+    (2, 101, 75, 64, 64, 3, 1, 1, 0, True, False, 1, False, 0, False),    # ragged tile edges, no ReLU
+    (1, 33, 40, 64, 64, 3, 1, 2, 1, True, False, 1, True, 0, False),      # ... and dilation 2
 ]
 
 
