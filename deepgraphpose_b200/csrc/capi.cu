@@ -316,7 +316,10 @@ int setup_epilogue(dgp_handle* h, ConvGemmParams& g, const char* scope, int n_im
   // narrow layers (N tile <= 128) run 256-row CTA tiles: one TMA + two UMMAs per k-step halves the per-k-block
   // issue overhead of the single-warp producer / MMA loops (see DESIGN.md "BLOCK_M = 256")
   g.msub = (g.epi_mode == 1 && g.block_n <= 128 && g.M > kBlockM) ? 2 : 1;
-  g.num_m_blocks = ceil_div(g.M, kBlockM * g.msub);
+  // 256-wide tiles of big layers run as CTA pairs (cta_group::2): a single-CTA M=128 x N=256 MMA reads 12 KB of operands
+  // from shared memory per K=16 step and is bound by that, the pair reads 8 KB per CTA.  DGP_NO_CTA2=1 disables (A/B).
+  g.cta2 = (g.epi_mode == 1 && g.block_n == 256 && g.M >= 4 * kBlockM && getenv("DGP_NO_CTA2") == nullptr) ? 1 : 0;
+  g.num_m_blocks = ceil_div(g.M, g.cta2 ? 2 * kBlockM : kBlockM * g.msub);
   g.tmem_cols = tmem_cols_for(g.block_n * g.msub);
   g.num_stages = conv_gemm_pick_stages(g);
   return DGP_OK;
@@ -424,7 +427,7 @@ int make_gemm_step(dgp_handle* h, const ConvLayer& L, const void* x, int N, int 
                          (uint64_t)N * H * W * L.Cin * 2, kBlockM * g.msub);
   }
   if (e) return fail(h, DGP_ERR_CUDA, "%s: %s", L.scope.c_str(), e);
-  e = make_tmap_2d(&g.tmap_b, L.w, (uint64_t)L.Npad, (uint64_t)L.K, (uint64_t)L.K * 2, (uint32_t)bn);
+  e = make_tmap_2d(&g.tmap_b, L.w, (uint64_t)L.Npad, (uint64_t)L.K, (uint64_t)L.K * 2, (uint32_t)(g.cta2 ? bn / 2 : bn));
   if (e) return fail(h, DGP_ERR_CUDA, "%s: %s", L.scope.c_str(), e);
   st->kind = STEP_GEMM;
   st->out_ptr = out;
@@ -551,6 +554,7 @@ int build_plan(dgp_handle* h, int B, int H, int W, bool train, Plan** out) {
     g.scale = L.scale; g.shift = L.shift; g.residual = nullptr; g.res_sub = 1; g.relu = 1;
     g.out_f32 = 0; g.ldc = 64; g.num_n_blocks = 1;
     uint32_t pixels_per_load;
+    bool resident = false;
     if (unfused) {
       g.a_mode = 1;
       g.out = c1;
@@ -559,17 +563,35 @@ int build_plan(dgp_handle* h, int B, int H, int W, bool train, Plan** out) {
       if ((rc = setup_epilogue(h, g, "conv1", B))) return rc;
       pixels_per_load = kBlockM * g.msub;
     } else {
-      // a tile = the 15 x 17 patch of conv1 outputs (255 of the 256 accumulator rows) under 7 x 8 pooled pixels
-      g.a_mode = 2; g.epi_mode = 2; g.epi_bufs = 0; g.msub = 2;
+      g.epi_mode = 2; g.epi_bufs = 0; g.msub = 2;
       g.out = xa;
-      g.pool_R = 7; g.pool_C = 8; g.pool_H = Hc; g.pool_W = Wc; g.pool_pad_t = pad_t; g.pool_pad_l = pad_l;
+      g.pool_H = Hc; g.pool_W = Wc; g.pool_pad_t = pad_t; g.pool_pad_l = pad_l;
+      // Measured (profiles/r02_conv1_variants.md): both variants are bound by the SM's shared-memory port (UMMA operand reads
+      // of the 64-wide tile + the pooling epilogue's patch traffic), the resident one needs 20 % more tiles (48 instead of
+      // 56 pooled pixels per 256 accumulator rows) and is the slower of the two; it stays as DGP_CONV1_RESIDENT=1.
+      resident = getenv("DGP_CONV1_RESIDENT") != nullptr;
+      if (resident) {
+        // a tile = 4 x 12 pooled pixels <- 9 x 25 conv1 outputs <- a 12 x 28 patch of space-to-depth pixels that stays in
+        // shared memory: the accumulator rows run over the patch grid (9 x 28 = 252 of 256), every tap is a shifted view
+        g.a_mode = 4; g.pool_R = 4; g.pool_C = 12;
+        g.pt_wp = 2 * g.pool_C + 4;
+        g.pt_stage_bytes = ((256 + 3 * g.pt_wp + 3) * 32 + 1023) / 1024 * 1024;
+        g.num_stages = 3;
+      } else {
+        // a tile = the 15 x 17 patch of conv1 outputs (255 of the 256 accumulator rows) under 7 x 8 pooled pixels, loaded
+        // per filter row as one tiled box of overlapping 4-pixel windows (10x read amplification out of the L2)
+        g.a_mode = 2; g.pool_R = 7; g.pool_C = 8;
+      }
       g.pool_tiles_i = ceil_div(Hc, g.pool_R); g.pool_tiles_j = ceil_div(Wc, g.pool_C);
       g.num_m_blocks = B * g.pool_tiles_i * g.pool_tiles_j;
       g.tmem_cols = tmem_cols_for(64 * g.msub);
-      g.num_stages = conv_gemm_pick_stages(g);
+      if (!resident) g.num_stages = conv_gemm_pick_stages(g);
       pixels_per_load = 0;
     }
-    const char* e = unfused
+    const char* e = resident
+        ? make_tmap_tiled4d(&g.tmap_a, pl->s2d, 16, (uint64_t)pl->Ws, (uint64_t)pl->Hs, (uint64_t)B, 32, (uint64_t)pl->Ws * 32,
+                            (uint64_t)pl->Hs * pl->Ws * 32, (uint32_t)g.pt_wp, (uint32_t)(2 * g.pool_R + 4))
+        : unfused
         ? make_tmap_im2col(&g.tmap_a, pl->s2d, 64, (uint64_t)pl->W1, (uint64_t)pl->Hs, (uint64_t)B, 32, (uint64_t)pl->Ws * 32,
                            (uint64_t)pl->Hs * pl->Ws * 32, 0, 0, 0, -3, 1, (uint64_t)B * pl->Hs * pl->Ws * 32, pixels_per_load)
         : make_tmap_tiled4d(&g.tmap_a, pl->s2d, 64, (uint64_t)pl->W1, (uint64_t)pl->Hs, (uint64_t)B, 32, (uint64_t)pl->Ws * 32,
@@ -676,6 +698,16 @@ int build_plan(dgp_handle* h, int B, int H, int W, bool train, Plan** out) {
     if (h->cfg.location_refinement) {
       if ((rc = alloc_buf(h, pl.get(), (size_t)B * 4 * Hc * Wc * 2 * nj * 4, &p))) return rc;
       pl->locref = (float*)p;
+    }
+  }
+  if (getenv("DGP_DEBUG_PLAN")) {
+    for (size_t i = 0; i < pl->steps.size(); ++i) {
+      const Step& st = pl->steps[i];
+      if (st.kind != STEP_GEMM) continue;
+      const ConvGemmParams& g = st.gp;
+      fprintf(stderr, "dgp plan B=%d %dx%d step %2zu %-50s M=%d N=%d K=%d block_n=%d a_mode=%d epi=%d msub=%d cta2=%d stages=%d epi_bufs=%d smem=%zu\n",
+              B, H, W, i, st.end_point.c_str(), g.M, g.N, g.num_k_blocks * 64, g.block_n, g.a_mode, g.epi_mode, g.msub, g.cta2,
+              g.num_stages, g.epi_bufs, conv_gemm_smem_bytes(g));
     }
   }
   *out = pl.get();

@@ -44,6 +44,17 @@ __device__ __forceinline__ uint4 pack8(const float* f, int fp16) {
   if (fp16) return make_uint4(pack_fp16(f[0], f[1]), pack_fp16(f[2], f[3]), pack_fp16(f[4], f[5]), pack_fp16(f[6], f[7]));
   return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
 }
+// packed maximum of two 16-bit pairs (fp16 / bf16)
+template <bool kFp16>
+__device__ __forceinline__ uint32_t max16x2(uint32_t a, uint32_t b) {
+  if (kFp16) {
+    const __half2 z = __hmax2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&z);
+  }
+  const __nv_bfloat162 z = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&z);
+}
+
 // One epilogue unit = this warp's 32 accumulator rows x 32 columns: BN scale/shift (fp32, packed FFMA2) (+ residual)
 // (+ ReLU, folded into the float -> 16-bit conversion) written in place into the warp's 2 KB staging buffer
 // (32 rows x 64 B, SWIZZLE_64B: 16-byte unit u of row r lives at u ^ ((r >> 1) & 3), conflict-free for LDS/STS.128).
@@ -94,17 +105,22 @@ __device__ __forceinline__ void epi_unit_math(const uint32_t (&v)[2][16], uint8_
 }
 
 // kFp16 selects the 16-bit storage type at compile time (bf16 / fp16): no dtype branches in the epilogue.
-template <bool kFp16>
+// kCta2: CTA-pair variant (cluster of 2, tcgen05 cta_group::2): one 256-row x 256-column tile per pair, each CTA stages its
+// own 128 rows of A and half of the weight tile (half the shared-memory operand traffic per MMA), the leader issues the MMA.
+template <bool kFp16, bool kCta2>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
+  const uint32_t cta_rank = kCta2 ? ptx::cluster_ctarank() : 0u;
+  const int tile0 = kCta2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;     // first tile / tile stride of this CTA (pair)
+  const int tstep = kCta2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stages = p.num_stages;
   const int msub = p.msub;                     // 128-row sub-tiles per CTA tile (BLOCK_M = 128 * msub)
-  const int a_bytes = p.a_mode == 3 ? p.pt_stage_bytes : msub * kABytes;
-  const int b_bytes = p.block_n * kBlockK * 2;
+  const int a_bytes = p.a_mode >= 3 ? p.pt_stage_bytes : msub * kABytes;
+  const int b_bytes = (kCta2 ? p.block_n / 2 : p.block_n) * kBlockK * 2;   // a CTA pair splits the weight tile
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + stages * a_bytes;
-  uint8_t* smem_epi = smem_b + (p.a_mode == 3 ? p.num_k_blocks : stages) * b_bytes;  // [16 warps][epi_bufs][2 KiB], 1024 B aligned
+  uint8_t* smem_epi = smem_b + (p.a_mode >= 3 ? p.num_k_blocks : stages) * b_bytes;  // [16 warps][epi_bufs][2 KiB], 1024 B aligned
   const int epi_bufs = p.epi_mode == 1 ? p.epi_bufs : 0;
   float* smem_ss = reinterpret_cast<float*>(smem_epi + (p.epi_mode == 2 ? 2 * kPatchBytes : kEpiWarps * epi_bufs * kEpiUnitBytes));  // [16 warps][2 sets][scale 32 | shift 32]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_ss + kEpiWarps * 128);
@@ -128,23 +144,31 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < stages; ++s) {
-      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&full_bar[s], kCta2 ? 2 : 1);   // pair: the leader's expect_tx arrive + the peer's remote arrive
       ptx::mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full_bar[a], 1);
-      ptx::mbar_init(&tmem_empty_bar[a], kEpiWarps);
+      // arrivals per accumulator buffer: every epilogue warp (both CTAs' in a pair); the pooling epilogue splits the warps
+      // into two groups, one per buffer
+      ptx::mbar_init(&tmem_empty_bar[a], kCta2 ? 2 * kEpiWarps : (p.epi_mode == 2 ? kEpiWarps / 2 : kEpiWarps));
     }
     for (int i = 0; i < kEpiWarps * kMaxEpiBufs; ++i) ptx::mbar_init(&res_bar[i], 1);
     ptx::mbar_init(b_bar, 1);
     ptx::fence_mbar_init();
   }
   if (warp == 2) {
-    ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
-    ptx::tmem_relinquish();
+    if (kCta2) {
+      ptx::tmem_alloc_2sm(tmem_slot, (uint32_t)p.tmem_cols);
+      ptx::tmem_relinquish_2sm();
+    } else {
+      ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (kCta2) ptx::cluster_sync_all();   // the peer's barriers must be initialised before anything signals them
+  else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // Programmatic dependent launch: everything above (smem carve-up, barrier init, TMEM alloc, descriptor prefetch)
@@ -163,8 +187,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     const uint32_t tx_bytes = (uint32_t)(a_bytes + b_bytes);
     const int PQ = p.P * p.Q, Q = p.Q, nnb = p.num_n_blocks, nkb = p.num_k_blocks, block_n = p.block_n;
     const int a_mode = p.a_mode, cblocks = p.cblocks, S = p.S, dil = p.dil, cstride = p.conv_stride;
-    const int lower_w = p.lower_w, lower_h = p.lower_h, block_m = kBlockM * msub;
-    if (a_mode == 3) {
+    const int lower_w = p.lower_w, lower_h = p.lower_h, block_m = kCta2 ? 2 * kBlockM : kBlockM * msub;
+    if (!kCta2 && a_mode == 3) {
       // shared-memory resident input patch: the whole weight matrix once, then ONE tiled box (patch + halo, zero filled
       // outside the image) per tile
       const int tiles_j = p.pool_tiles_j, tiles_ij = p.pool_tiles_i * tiles_j;
@@ -174,7 +198,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         for (int kb = 0; kb < nkb; ++kb) ptx::tma_load_2d(smem_b + kb * b_bytes, &p.tmap_b, b_bar, kb * kBlockK, 0);
       }
       __syncwarp();
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tstep) {
         const int img = tile / tiles_ij;
         const int rem = tile - img * tiles_ij;
         const int ti = rem / tiles_j;
@@ -190,12 +214,38 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           phase ^= 1;
         }
       }
-    } else if (a_mode == 2) {
+    } else if (!kCta2 && a_mode == 4) {
+      // conv1 + pool1 from a resident space-to-depth patch: all weights once, then one tiled box per tile
+      const int tiles_j = p.pool_tiles_j, tiles_ij = p.pool_tiles_i * tiles_j;
+      const uint32_t box_bytes = (uint32_t)(p.pt_wp * (2 * p.pool_R + 4) * 32);
+      if (lane == 0) {
+        ptx::mbar_arrive_expect_tx(b_bar, (uint32_t)(nkb * b_bytes));
+        for (int kb = 0; kb < nkb; ++kb) ptx::tma_load_2d(smem_b + kb * b_bytes, &p.tmap_b, b_bar, kb * kBlockK, 0);
+      }
+      __syncwarp();
+      for (int tile = tile0; tile < num_tiles; tile += tstep) {
+        const int img = tile / tiles_ij;
+        const int rem = tile - img * tiles_ij;
+        const int ti = rem / tiles_j;
+        const int tj = rem - ti * tiles_j;
+        const int ra = max(0, 2 * ti * p.pool_R - p.pool_pad_t), ca = max(0, 2 * tj * p.pool_C - p.pool_pad_l);
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (lane == 0) {
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], box_bytes);
+          ptx::tma_load_4d(smem_a + stage * a_bytes, &p.tmap_a, &full_bar[stage], 0, ca, ra, img);
+        }
+        __syncwarp();
+        if (++stage == stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    } else if (!kCta2 && a_mode == 2) {
       // conv1 + pool1: the A tile is a 2-D patch of conv outputs = ONE tiled box per filter-row tap (the tensor map's
       // "pixels" are overlapping 4-pixel windows of the space-to-depth input; rows / columns past the end read as zero)
       const int tiles_j = p.pool_tiles_j, tiles_ij = p.pool_tiles_i * tiles_j;
       const uint32_t tx = (uint32_t)((2 * p.pool_R + 1) * (2 * p.pool_C + 1) * 128 + b_bytes);
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tstep) {
         const int img = tile / tiles_ij;
         const int rem = tile - img * tiles_ij;
         const int ti = rem / tiles_j;
@@ -216,11 +266,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         }
       }
     } else
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < num_tiles; tile += tstep) {
       const int m_blk = tile / nnb;
       const int n_blk = tile - m_blk * nnb;
-      const int m0 = m_blk * block_m;
-      const int n0 = n_blk * block_n;
+      const int m0 = m_blk * block_m + (int)cta_rank * kBlockM;              // pair: this CTA's 128 rows
+      const int n0 = n_blk * block_n + (int)cta_rank * (block_n >> 1) * (kCta2 ? 1 : 0);   // ... and its half of the weights
       int img = 0, cw = 0, ch = 0;
       if (a_mode == 1) {
         img = m0 / PQ;
@@ -234,14 +284,28 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       for (int kb = 0; kb < nkb; ++kb) {
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
         if (ptx::elect_one()) {
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-          if (a_mode == 0) {
-            ptx::tma_load_2d(smem_a + stage * a_bytes, &p.tmap_a, &full_bar[stage], kb * kBlockK, m0);
+          if (kCta2) {
+            // both CTAs count their bytes on the LEADER's barrier (it alone feeds the MMA issuer)
+            const uint32_t lbar = ptx::mapa_u32(&full_bar[stage], 0);
+            if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * tx_bytes);
+            if (a_mode == 0) {
+              ptx::tma_load_2d_2sm(smem_a + stage * a_bytes, &p.tmap_a, lbar, kb * kBlockK, m0);
+            } else {
+              ptx::tma_load_im2col_4d_2sm(smem_a + stage * a_bytes, &p.tmap_a, lbar, cb * kBlockK, cw, ch, img, (uint16_t)off_w,
+                                          (uint16_t)off_h);
+            }
+            ptx::tma_load_2d_2sm(smem_b + stage * b_bytes, &p.tmap_b, lbar, kb * kBlockK, n0);
+            if (cta_rank != 0) ptx::mbar_arrive_cluster(lbar);
           } else {
-            ptx::tma_load_im2col_4d(smem_a + stage * a_bytes, &p.tmap_a, &full_bar[stage], cb * kBlockK, cw, ch, img,
-                                    (uint16_t)off_w, (uint16_t)off_h);
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+            if (a_mode == 0) {
+              ptx::tma_load_2d(smem_a + stage * a_bytes, &p.tmap_a, &full_bar[stage], kb * kBlockK, m0);
+            } else {
+              ptx::tma_load_im2col_4d(smem_a + stage * a_bytes, &p.tmap_a, &full_bar[stage], cb * kBlockK, cw, ch, img,
+                                      (uint16_t)off_w, (uint16_t)off_h);
+            }
+            ptx::tma_load_2d(smem_b + stage * b_bytes, &p.tmap_b, &full_bar[stage], kb * kBlockK, n0);
           }
-          ptx::tma_load_2d(smem_b + stage * b_bytes, &p.tmap_b, &full_bar[stage], kb * kBlockK, n0);
         }
         __syncwarp();
         if (++cb == cblocks) {
@@ -260,9 +324,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       }
     }
   } else if (warp == 1) {
+    if (!kCta2 || cta_rank == 0) {
     // ------------------------------------------------------------ MMA issuer (whole warp loops, one lane issues)
     const int block_n = p.block_n, nkb = p.num_k_blocks;
-    const uint32_t idesc = ptx::make_idesc_bf16_f32(kBlockM, block_n, kFp16 ? 1 : 0);
+    const uint32_t idesc = ptx::make_idesc_bf16_f32(kCta2 ? 2 * kBlockM : kBlockM, block_n, kFp16 ? 1 : 0);
     const uint64_t adesc0 = ptx::make_desc_k_sw128(ptx::smem_u32(smem_a));
     const uint64_t bdesc0 = ptx::make_desc_k_sw128(ptx::smem_u32(smem_b));
     const uint32_t a_step = (uint32_t)a_bytes >> 4, b_step = (uint32_t)b_bytes >> 4;
@@ -274,7 +339,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     // The two tile heights get separate, branch-free issue loops (a predicate between UTCHMMAs costs issue slots).
     auto run = [&](auto msub_tag) {
       constexpr int kMsub = decltype(msub_tag)::value;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tstep) {
         ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)acc * acc_cols;
@@ -287,13 +352,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k) {
               // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
-              ptx::umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-              if (kMsub == 2)  // rows 128..255 of a 256-row tile: A 16 KiB further, D block_n columns further
-                ptx::umma_bf16(tmem_d + (uint32_t)block_n, adesc + (uint64_t)((kABytes >> 4) + k * 2),
-                               bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+              if (kCta2) {
+                ptx::umma_bf16_2sm(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+              } else {
+                ptx::umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                if (kMsub == 2)  // rows 128..255 of a 256-row tile: A 16 KiB further, D block_n columns further
+                  ptx::umma_bf16(tmem_d + (uint32_t)block_n, adesc + (uint64_t)((kABytes >> 4) + k * 2),
+                                 bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+              }
             }
-            ptx::umma_commit(&empty_bar[stage]);
-            if (kb == nkb - 1) ptx::umma_commit(&tmem_full_bar[acc]);
+            if (kCta2) {
+              ptx::umma_commit_2sm(&empty_bar[stage]);                           // frees the stage in BOTH CTAs
+              if (kb == nkb - 1) ptx::umma_commit_2sm(&tmem_full_bar[acc]);      // ... and wakes both epilogues
+            } else {
+              ptx::umma_commit(&empty_bar[stage]);
+              if (kb == nkb - 1) ptx::umma_commit(&tmem_full_bar[acc]);
+            }
           }
           __syncwarp();
           if (++stage == stages) {
@@ -305,13 +379,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         if (acc == 0) acc_phase ^= 1;
       }
     };
-    if (p.a_mode == 3) {
+    if (!kCta2 && p.a_mode == 3) {
       // 3x3 taps as row-shifted views of the resident patch: accumulator row m reads patch row m + (kr*Wp + ks)*dil
       const int Wp = p.pt_wp, dil = p.dil, bo_mode = p.pt_base_offset_mode;
       const uint32_t a0 = ptx::smem_u32(smem_a);
       ptx::mbar_wait(b_bar, 0);
       ptx::tc_fence_after();
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tstep) {
         ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after();
@@ -344,16 +418,54 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
-    } else if (msub == 2) run(std::integral_constant<int, 2>{});
+    } else if (!kCta2 && p.a_mode == 4) {
+      // conv1: 4 x 4 taps of 16 (space-to-depth) channels = sixteen K=16 MMAs per 128-row sub-tile; tap (kr, ks) reads
+      // patch rows m + kr*Wp + ks (32 B each, SWIZZLE_32B) and the weight slab at k-block kr, +ks*32 B
+      const int Wp = p.pt_wp;
+      const uint32_t a0 = ptx::smem_u32(smem_a);
+      ptx::mbar_wait(b_bar, 0);
+      ptx::tc_fence_after();
+      for (int tile = tile0; tile < num_tiles; tile += tstep) {
+        ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        ptx::mbar_wait(&full_bar[stage], phase);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint32_t tmem_d = tmem_base + (uint32_t)acc * acc_cols;
+          const uint32_t abase = a0 + (uint32_t)(stage * a_bytes);
+#pragma unroll
+          for (int kr = 0; kr < 4; ++kr) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t bdesc = bdesc0 + (uint64_t)(kr * b_step + ks * 2);
+#pragma unroll
+              for (int sub = 0; sub < 2; ++sub) {
+                const uint64_t adesc = ptx::make_desc_k_sw32(abase + (uint32_t)((kr * Wp + ks + sub * 128) * 32));
+                ptx::umma_bf16(tmem_d + (uint32_t)(sub * block_n), adesc, bdesc, idesc, (kr | ks) != 0);
+              }
+            }
+          }
+          ptx::umma_commit(&empty_bar[stage]);
+          ptx::umma_commit(&tmem_full_bar[acc]);
+        }
+        __syncwarp();
+        if (++stage == stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    } else if (!kCta2 && msub == 2) run(std::integral_constant<int, 2>{});
     else run(std::integral_constant<int, 1>{});
-  } else if (p.epi_mode == 0) {
+    }  // leader CTA (or single-CTA kernel)
+  } else if (!kCta2 && p.epi_mode == 0) {
     // -------------------------------------------------------------- epilogue, direct stores (fp32 head GEMM)
     // 16 epilogue warps: four per TMEM lane quadrant, taking every fourth 16-column group.
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     const int cg = (warp - 2) >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < num_tiles; tile += tstep) {
       const int m_blk = tile / p.num_n_blocks;
       const int n_blk = tile - m_blk * p.num_n_blocks;
       const int row = m_blk * kBlockM + quad * 32 + lane;
@@ -400,7 +512,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-  } else if (p.epi_mode == 3) {
+  } else if (!kCta2 && p.epi_mode == 3) {
     // -------------------------------------------------------------- epilogue of a patch tile (a_mode 3): direct stores
     // accumulator row m = pr * Wp + pc lies on the input-patch grid; rows with pc >= pt_cols or pr >= pt_rows are halo
     // positions (junk) and are not stored.  Every lane owns one pixel x 32 channels = 64 contiguous bytes of the output.
@@ -423,7 +535,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     const bool in_tile = pr < p.pt_rows && pc < p.pt_cols;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < num_tiles; tile += tstep) {
       const int img = tile / tiles_ij;
       const int rem = tile - img * tiles_ij;
       const int ti = rem / tiles_j;
@@ -471,17 +583,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-  } else if (p.epi_mode == 2) {
+  } else if (!kCta2 && p.epi_mode == 2) {
     // -------------------------------------------------------------- epilogue, conv1 + BN + ReLU + 3x3/2 max-pool
-    // The 256 accumulator rows are the pixels of a (2R+1) x (2C+1) patch of conv1 outputs (row-major).  Every warp turns
-    // its 32 rows x 32 channels into 16-bit activations in a shared-memory copy of the patch (128 B per pixel, 16-byte
-    // units XOR-swizzled by the pixel index), the 16 warps meet on one named barrier, and 512 threads reduce the R x C
-    // pooled pixels (one 16-byte channel group each, nine LDS.128 + packed max) straight to global memory.  conv1's
-    // 20 MB-per-frame output never reaches HBM.  The patch is double buffered: one barrier per tile suffices.
+    // The 256 accumulator rows are the pixels of a 2-D patch of conv1 outputs (row-major, `Cw` accumulator rows per patch
+    // row).  The 16 epilogue warps form TWO groups of 8 that take alternate tiles (group g owns accumulator buffer g and
+    // patch buffer g), so two tiles are in flight per SM and one group's barrier / load latencies hide under the other's
+    // arithmetic.  Per tile a group turns the accumulator (each warp: 32 rows x 32 channels of both 128-row halves) into
+    // 16-bit activations in its shared-memory patch (128 B per pixel, 16-byte units XOR-swizzled by the pixel index), meets
+    // on its own named barrier, and its 256 threads reduce the R x C pooled pixels (one 16-byte channel group each, nine
+    // LDS.128 + packed max) straight to global memory.  conv1's 20 MB-per-frame output never reaches HBM.
     const int quad = warp & 3;
     const int ew = warp - 2;
-    const int cg = ew >> 2;
-    const int sub = cg >> 1, colg = cg & 1;
+    const int grp = ew >> 3;
+    const int colg = (ew >> 2) & 1;
     float* ss = smem_ss + ew * 128;
     if (lane < 16) {
       const int is_shift = lane >> 3, i = (lane & 7) * 4;
@@ -491,59 +605,95 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       *reinterpret_cast<float4*>(ss + is_shift * 32 + i) = val;
     }
     __syncwarp();
-    const int R = p.pool_R, Cp = p.pool_C, Cw = 2 * p.pool_C + 1, H1 = p.P, W1 = p.Q;
-    const int tiles_j = p.pool_tiles_j, tiles_ij = p.pool_tiles_i * tiles_j;
-    const int px = sub * 128 + quad * 32 + lane;
-    const int item = (int)threadIdx.x - 64;          // pooling work item: (pooled pixel, 16-byte channel group)
-    const int pv = item & 7, pp = item >> 3;
-    const int pi = pp / Cp, pj = pp - pi * Cp;
-    const bool pool_thread = pp < R * Cp;
-    int acc = 0, pb = 0;
+    const int R = p.pool_R, Cp = p.pool_C, H1 = p.P, W1 = p.Q;
+    const int Cw = p.a_mode == 4 ? p.pt_wp : 2 * p.pool_C + 1;   // accumulator rows per patch row
+    const int tiles_i = p.pool_tiles_i, tiles_j = p.pool_tiles_j;
+    uint8_t* patch = smem_epi + grp * kPatchBytes;
+    const uint32_t bar_id = 1u + (uint32_t)grp;
+    // pooling work items of this thread: (pooled pixel, 16-byte channel group), items t and t + 256 of R * C * 8
+    const int t = (int)threadIdx.x - 64 - grp * 256;
+    const int pv = t & 7;
+    int pi[2], pj[2], q0[2];
+    bool pool_item[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int pp = (t >> 3) + 32 * k;
+      pi[k] = pp / Cp;
+      pj[k] = pp - pi[k] * Cp;
+      pool_item[k] = pp < R * Cp;
+      q0[k] = 2 * pi[k] * Cw + 2 * pj[k];       // first patch pixel of the window in an interior tile
+    }
+    // this group's tile sequence: tile0 + grp * tstep, then every 2 * tstep; (img, ti, tj) advance without divisions
+    int tile = tile0 + grp * tstep;
+    int img = tile / (tiles_i * tiles_j);
+    int ti = (tile - img * tiles_i * tiles_j) / tiles_j;
+    int tj = tile - (img * tiles_i + ti) * tiles_j;
+    const int step = 2 * tstep;
+    const int d_img = step / (tiles_i * tiles_j);
+    const int d_ti = (step - d_img * tiles_i * tiles_j) / tiles_j;
+    const int d_tj = step - (d_img * tiles_i + d_ti) * tiles_j;
+    const int acc = grp;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int img = tile / tiles_ij;
-      const int rem = tile - img * tiles_ij;
-      const int ti = rem / tiles_j;
-      const int tj = rem - ti * tiles_j;
+    for (; tile < num_tiles; tile += step) {
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((acc * 2 + sub) * 64 + colg * 32);
-      uint32_t v[2][16];
-      ptx::tmem_ld_x16(taddr, v[0]);
-      ptx::tmem_ld_x16(taddr + 16, v[1]);
-      ptx::tmem_ld_wait();
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);   // the accumulator is in registers: the MMA may reuse it
-      uint8_t* patch = smem_epi + pb * kPatchBytes;
-      uint8_t* my_row = patch + px * 128;
 #pragma unroll
-      for (int s2 = 0; s2 < 2; ++s2) {
-        uint32_t o[8];
-#pragma unroll
-        for (int i = 0; i < 8; i += 2) {
-          const float4 sc = *reinterpret_cast<const float4*>(ss + s2 * 16 + 2 * i);
-          const float4 sh = *reinterpret_cast<const float4*>(ss + 32 + s2 * 16 + 2 * i);
-          const ptx::f32x2 q0 = ptx::fma2(ptx::pk2(__uint_as_float(v[s2][2 * i]), __uint_as_float(v[s2][2 * i + 1])),
-                                          ptx::pk2(sc.x, sc.y), ptx::pk2(sh.x, sh.y));
-          const ptx::f32x2 q1 = ptx::fma2(ptx::pk2(__uint_as_float(v[s2][2 * i + 2]), __uint_as_float(v[s2][2 * i + 3])),
-                                          ptx::pk2(sc.z, sc.w), ptx::pk2(sh.z, sh.w));
-          float a0, a1, b0, b1;
-          ptx::upk2(q0, a0, a1);
-          ptx::upk2(q1, b0, b1);
-          o[i] = ptx::cvt_pack16<kFp16, true>(a0, a1);
-          o[i + 1] = ptx::cvt_pack16<kFp16, true>(b0, b1);
+      for (int sub = 0; sub < 2; ++sub) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((acc * 2 + sub) * 64 + colg * 32);
+        uint32_t v[2][16];
+        ptx::tmem_ld_x16(taddr, v[0]);
+        ptx::tmem_ld_x16(taddr + 16, v[1]);
+        ptx::tmem_ld_wait();
+        if (sub == 1) {
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);   // the accumulator is in registers: the MMA may reuse it
         }
-        const int u = colg * 4 + 2 * s2;
-        *reinterpret_cast<uint4*>(my_row + ((u ^ (px & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
-        *reinterpret_cast<uint4*>(my_row + (((u + 1) ^ (px & 7)) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
+        const int px = sub * 128 + quad * 32 + lane;
+        uint8_t* my_row = patch + px * 128;
+#pragma unroll
+        for (int s2 = 0; s2 < 2; ++s2) {
+          uint32_t o[8];
+#pragma unroll
+          for (int i = 0; i < 8; i += 2) {
+            const float4 sc = *reinterpret_cast<const float4*>(ss + s2 * 16 + 2 * i);
+            const float4 sh = *reinterpret_cast<const float4*>(ss + 32 + s2 * 16 + 2 * i);
+            const ptx::f32x2 r0 = ptx::fma2(ptx::pk2(__uint_as_float(v[s2][2 * i]), __uint_as_float(v[s2][2 * i + 1])),
+                                            ptx::pk2(sc.x, sc.y), ptx::pk2(sh.x, sh.y));
+            const ptx::f32x2 r1 = ptx::fma2(ptx::pk2(__uint_as_float(v[s2][2 * i + 2]), __uint_as_float(v[s2][2 * i + 3])),
+                                            ptx::pk2(sc.z, sc.w), ptx::pk2(sh.z, sh.w));
+            float a0, a1, b0, b1;
+            ptx::upk2(r0, a0, a1);
+            ptx::upk2(r1, b0, b1);
+            o[i] = ptx::cvt_pack16<kFp16, true>(a0, a1);
+            o[i + 1] = ptx::cvt_pack16<kFp16, true>(b0, b1);
+          }
+          const int u = colg * 4 + 2 * s2;
+          *reinterpret_cast<uint4*>(my_row + ((u ^ (px & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<uint4*>(my_row + (((u + 1) ^ (px & 7)) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
+        }
       }
-      ptx::named_bar_sync(1, kEpiWarps * 32);
-      if (pool_thread) {
-        const int i = ti * R + pi, j = tj * Cp + pj;
-        if (i < p.pool_H && j < p.pool_W) {
+      ptx::named_bar_sync(bar_id, 256);
+      // interior tiles (patch origin not clamped, no window row / column outside the image): constant patch offsets
+      const bool interior = 2 * ti * R >= p.pool_pad_t && 2 * tj * Cp >= p.pool_pad_l &&
+                            2 * (ti * R + R - 1) - p.pool_pad_t + 2 < H1 && 2 * (tj * Cp + Cp - 1) - p.pool_pad_l + 2 < W1;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        if (!pool_item[k]) continue;
+        const int i = ti * R + pi[k], j = tj * Cp + pj[k];
+        uint32_t m[4] = {0u, 0u, 0u, 0u};          // post-ReLU values are >= 0 and every window holds a valid pixel
+        if (interior) {
+#pragma unroll
+          for (int w = 0; w < 9; ++w) {
+            const int q = q0[k] + (w / 3) * Cw + w % 3;
+            const uint4 x = *reinterpret_cast<const uint4*>(patch + q * 128 + ((pv ^ (q & 7)) << 4));
+            const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) m[c] = max16x2<kFp16>(m[c], xs[c]);
+          }
+        } else {
+          if (i >= p.pool_H || j >= p.pool_W) continue;
           const int ra = max(0, 2 * ti * R - p.pool_pad_t), ca = max(0, 2 * tj * Cp - p.pool_pad_l);
-          uint32_t m[4] = {0u, 0u, 0u, 0u};          // post-ReLU values are >= 0 and every window holds a valid pixel
 #pragma unroll
           for (int dr = 0; dr < 3; ++dr) {
             const int rr = 2 * i - p.pool_pad_t + dr;
@@ -556,26 +706,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
               const uint4 x = *reinterpret_cast<const uint4*>(patch + q * 128 + ((pv ^ (q & 7)) << 4));
               const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                if (kFp16) {
-                  const __half2 z = __hmax2(*reinterpret_cast<const __half2*>(&m[k]), *reinterpret_cast<const __half2*>(&xs[k]));
-                  m[k] = *reinterpret_cast<const uint32_t*>(&z);
-                } else {
-                  const __nv_bfloat162 z = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&m[k]),
-                                                   *reinterpret_cast<const __nv_bfloat162*>(&xs[k]));
-                  m[k] = *reinterpret_cast<const uint32_t*>(&z);
-                }
-              }
+              for (int c = 0; c < 4; ++c) m[c] = max16x2<kFp16>(m[c], xs[c]);
             }
           }
-          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.out) +
-                                                ((((size_t)img * p.pool_H + i) * p.pool_W + j) * 64 + pv * 8) * 2);
-          *dst = make_uint4(m[0], m[1], m[2], m[3]);
         }
+        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.out) +
+                                              ((((size_t)img * p.pool_H + i) * p.pool_W + j) * 64 + pv * 8) * 2);
+        *dst = make_uint4(m[0], m[1], m[2], m[3]);
       }
-      pb ^= 1;
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+      // the group's next write into this patch buffer happens after its next barrier-free phase; the barrier below keeps
+      // a fast warp from overwriting pixels a slow one is still pooling
+      ptx::named_bar_sync(bar_id, 256);
+      acc_phase ^= 1;
+      tj += d_tj;
+      if (tj >= tiles_j) { tj -= tiles_j; ++ti; }
+      ti += d_ti;
+      if (ti >= tiles_i) { ti -= tiles_i; ++img; }
+      img += d_img;
     }
   } else {
     // -------------------------------------------------------------- epilogue, TMA-staged 16-bit (+ TMA residual)
@@ -602,7 +749,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 
     // Residual prefetch cursor: walks this warp's (tile, unit) sequence nb-1 units ahead of the consumer.  All lanes
     // keep the (uniform) cursor; lane 0 issues.
-    int pf_tile = blockIdx.x, pf_u = cg, pf_buf = 0, pf_mblk = 0, pf_n0 = 0;
+    int pf_tile = tile0, pf_u = cg, pf_buf = 0, pf_mblk = 0, pf_n0 = 0;
     auto pf_setup_tile = [&]() {
       pf_mblk = pf_tile / nnb;
       pf_n0 = (pf_tile - pf_mblk * nnb) * block_n;
@@ -610,7 +757,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     auto issue_residual = [&]() {
       if (pf_tile >= num_tiles) return;
       const int sub = pf_u >> ncg_shift;
-      const int row0 = (pf_mblk * msub + sub) * kBlockM + quad * 32;
+      const int row0 = (kCta2 ? pf_mblk * 2 + (int)cta_rank : pf_mblk * msub + sub) * kBlockM + quad * 32;
       const int col0 = pf_n0 + ((pf_u & (ncg - 1)) << 5);
       if (lane == 0) {
         ptx::mbar_arrive_expect_tx(&rbar[pf_buf], (uint32_t)kEpiUnitBytes);
@@ -628,7 +775,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       pf_u += 4;
       if (pf_u >= units) {
         pf_u = cg;
-        pf_tile += gridDim.x;
+        pf_tile += tstep;
         if (pf_tile < num_tiles) pf_setup_tile();
       }
     };
@@ -643,7 +790,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     uint32_t buf_phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < num_tiles; tile += tstep) {
       const int m_blk = tile / nnb;
       const int n0 = (tile - m_blk * nnb) * block_n;
       if (n0 != ss_n0 && active) {
@@ -663,7 +810,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       for (int u = cg; u < units; u += 4) {
         const int sub = u >> ncg_shift;
         const int colg = u & (ncg - 1);
-        const int row0 = (m_blk * msub + sub) * kBlockM + quad * 32;
+        const int row0 = (kCta2 ? m_blk * 2 + (int)cta_rank : m_blk * msub + sub) * kBlockM + quad * 32;
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((acc * msub + sub) * block_n + (colg << 5));
         uint8_t* my_buf = ebuf + buf * kEpiUnitBytes;
         uint32_t v[2][16];
@@ -707,7 +854,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+      if (lane == 0) {
+        if (kCta2) ptx::mbar_arrive_cluster(ptx::mapa_u32(&tmem_empty_bar[acc], 0));   // the leader's MMA issuer waits on it
+        else ptx::mbar_arrive(&tmem_empty_bar[acc]);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -716,10 +866,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  if (kCta2) ptx::cluster_sync_all();   // the leader's MMAs read the peer's shared memory: nobody leaves early
+  else __syncthreads();
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    if (kCta2) ptx::tmem_dealloc_2sm(tmem_base, (uint32_t)p.tmem_cols);
+    else ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
 }
 
@@ -807,10 +959,10 @@ const char* make_tmap_im2col(CUtensorMap* out, const void* base, uint64_t C, uin
 }
 
 size_t conv_gemm_smem_bytes(const ConvGemmParams& p) {
-  const size_t a_bytes = p.a_mode == 3 ? (size_t)p.pt_stage_bytes : (size_t)p.msub * kABytes;
-  const size_t b_bytes = (size_t)p.block_n * kBlockK * 2;
+  const size_t a_bytes = p.a_mode >= 3 ? (size_t)p.pt_stage_bytes : (size_t)p.msub * kABytes;
+  const size_t b_bytes = (size_t)(p.cta2 ? p.block_n / 2 : p.block_n) * kBlockK * 2;
   const size_t epi = p.epi_mode == 2 ? (size_t)2 * kPatchBytes : (p.epi_mode == 1 ? (size_t)kEpiWarps * p.epi_bufs * kEpiUnitBytes : 0);
-  return 1024 + (size_t)p.num_stages * a_bytes + (size_t)(p.a_mode == 3 ? p.num_k_blocks : p.num_stages) * b_bytes + epi +
+  return 1024 + (size_t)p.num_stages * a_bytes + (size_t)(p.a_mode >= 3 ? p.num_k_blocks : p.num_stages) * b_bytes + epi +
          kEpiWarps * 128 * sizeof(float) + (2 * kMaxStages + 4 + kEpiWarps * kMaxEpiBufs + 1) * 8 + 16;
 }
 
@@ -831,14 +983,15 @@ const char* make_tmap_tiled4d(CUtensorMap* out, const void* base, uint64_t C, ui
                               uint64_t stride_w_bytes, uint64_t stride_h_bytes, uint64_t stride_n_bytes, uint32_t box_w,
                               uint32_t box_h) {
   if (const char* e = tma_init()) return e;
-  if (C != 64) return "make_tmap_tiled4d: 64 channels expected";
+  if (C != 64 && C != 16) return "make_tmap_tiled4d: 64 or 16 channels expected";
   cuuint64_t dims[4] = {C, W, H, N};
   cuuint64_t strides[3] = {stride_w_bytes, stride_h_bytes, stride_n_bytes};
-  cuuint32_t box[4] = {64, box_w, box_h, 1};
+  cuuint32_t box[4] = {(cuuint32_t)C, box_w, box_h, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   if (box_w > 256 || box_h > 256) return "make_tmap_tiled4d: box too large";
   CUresult r = g_encode_tiled(out, g_tmap_fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims,
-                              strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              C == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     snprintf(g_err, sizeof(g_err), "cuTensorMapEncodeTiled (4-D) failed: %d", (int)r);
@@ -850,14 +1003,19 @@ const char* make_tmap_tiled4d(CUtensorMap* out, const void* base, uint64_t C, ui
 cudaError_t launch_conv_gemm(const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return e;
+    const void* fns[4] = {(const void*)conv_gemm_kernel<false, false>, (const void*)conv_gemm_kernel<true, false>,
+                          (const void*)conv_gemm_kernel<false, true>, (const void*)conv_gemm_kernel<true, true>};
+    for (const void* f : fns) {
+      cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) return e;
+    }
     attr_set = true;
   }
   const int tiles = p.num_m_blocks * p.num_n_blocks;
-  const int grid = tiles < num_sms ? tiles : num_sms;
+  int grid = tiles < num_sms ? tiles : num_sms;
+  if (p.cta2) {   // one tile per CTA pair
+    grid = 2 * tiles < num_sms ? 2 * tiles : (num_sms & ~1);
+  }
   const size_t smem = conv_gemm_smem_bytes(p);
   if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
   cudaLaunchConfig_t cfg = {};
@@ -865,13 +1023,22 @@ cudaError_t launch_conv_gemm(const ConvGemmParams& p, int num_sms, cudaStream_t 
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (p.fp16) return cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true>, p);
-  return cudaLaunchKernelEx(&cfg, conv_gemm_kernel<false>, p);
+  if (p.cta2) {
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = 2;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
+    cfg.numAttrs = 2;
+    if (p.fp16) return cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true, true>, p);
+    return cudaLaunchKernelEx(&cfg, conv_gemm_kernel<false, true>, p);
+  }
+  if (p.fp16) return cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true, false>, p);
+  return cudaLaunchKernelEx(&cfg, conv_gemm_kernel<false, false>, p);
 }
 
 }  // namespace dgp

@@ -36,7 +36,9 @@ struct ConvGemmParams {
   int num_k_blocks;  // K / 64
   int a_mode;        // 0 = tiled [M,K], 1 = im2col, 2 = im2col by 2-D patches (conv1 fused with the 3x3/2 max-pool),
                      // 3 = shared-memory resident input patch (3x3 stride-1 convs with 64 input channels): ONE tiled TMA box
-                     //     per tile, the nine taps are row-shifted UMMA descriptors over it, all weights stay resident
+                     //     per tile, the nine taps are row-shifted UMMA descriptors over it, all weights stay resident,
+                     // 4 = the same for conv1 fused with pool1: the space-to-depth input patch (32 B per pixel, SWIZZLE_32B)
+                     //     is resident, the 4x4 taps are K=16 MMAs over 32 B-shifted descriptors
   int fp16;          // 0 = bf16 activations/weights (default), 1 = fp16 storage (same kind::f16 MMA, fp32 accumulate)
   // im2col geometry (a_mode == 1)
   int P, Q;          // output height / width
@@ -62,6 +64,8 @@ struct ConvGemmParams {
   int ldc;
   int num_m_blocks, num_n_blocks;
   int num_stages;
+  int cta2;          // 1 = CTA-pair kernel (cluster of 2, tcgen05 cta_group::2): tiles of 256 rows x 256 columns, each CTA stages
+                     // its 128 rows of A and 128 of the 256 weight rows; num_m_blocks counts 256-row tiles
   int tmem_cols;     // power of two >= 2 * block_n
   // a_mode / epi_mode 2 (conv1 + pool1): a tile is the (2R+1) x (2C+1) patch of conv outputs under R x C pooled pixels;
   // P, Q are the conv output dims, pool_H / pool_W the pooled dims, pool_pad_* the TF SAME padding of the pool (0 or 1)
@@ -105,6 +109,7 @@ const char* make_tmap_im2col(CUtensorMap* out, const void* base, uint64_t C, uin
                              uint32_t pixels_per_column = kBlockM, uint32_t channels_per_pixel = kBlockK);
 // a_mode 3: patch stage bytes (1024-aligned) for a tile geometry, and the tiled 4-D activation map (box = whole input patch)
 int conv_patch_stage_bytes(int pt_wp, int dil);
+// C = 64 channels per pixel (128 B rows, SWIZZLE_128B) or 16 (32 B rows, SWIZZLE_32B)
 const char* make_tmap_tiled4d(CUtensorMap* out, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t N,
                               uint64_t stride_w_bytes, uint64_t stride_h_bytes, uint64_t stride_n_bytes, uint32_t box_w,
                               uint32_t box_h);
