@@ -281,11 +281,12 @@ def measure_device(wl, steps, warmup, world, local_rank, profile=True):
     clocks = sampler.stop()
     prof, ms_prof = None, None
     if profile:
-        # Second pass over the SAME K steps with a CUDA-event pair around every kernel launch (recorded by the handle on the
-        # launching stream).  Kept out of the headline pass: an event record between two layers defeats their
-        # programmatic-dependent-launch overlap.
+        # Second pass over the SAME K steps with CUDA events recorded by the handle on the launching stream: one pair around
+        # every run of same-kind launches -- the 54 conv_gemm layers of a step are one run (the pool is fused into conv1), so
+        # their total is measured with the programmatic-dependent-launch chaining of the real step intact (an event record
+        # between two layers would serialise them; tools/instep_layers.py does that on purpose for the per-layer table).
         wl.eng.get_profile()
-        wl.eng.set_profiling(True)
+        wl.eng.set_profiling(2)
         p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         p0.record()
         for i in range(steps):
@@ -373,8 +374,9 @@ def roofline_of(wl, m, steps, peaks, peak_src):
             "frac": (achieved_tf / peak_tf) if achieved_tf else None, "traffic": traffic, "traffic_note": traffic_note,
             "peak_source": peak_src + ", 16-bit dense sustained (cuBLAS bf16; fp16 runs at the same tensor rate)",
             "share_of_step": gemm_ms / m["ms_prof"],
-            "timing": "CUDA events around each of the %d launches in a second pass over the same steps (%.3f ms/step with events, %.3f without)"
-                      % (gemm_n, m["ms_prof"] / steps, m["ms"] / steps),
+            "timing": "CUDA events on the launching stream around each step's run of %d consecutive conv_gemm launches, in a second "
+                      "pass over the same steps (%.3f ms/step with events, %.3f without); achieved = algorithmic FLOPs of the "
+                      "timed launches / their summed duration" % (gemm_n // steps, m["ms_prof"] / steps, m["ms"] / steps),
             "algorithmic_gflop_per_frame": wl.flops_frame / 1e9}
 
 

@@ -53,7 +53,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    link = [_nvcc(), "-shared", "-o", LIB] + objs + ["-lcudart", "-lpthread", "-ldl"]
+    link = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs + ["-lcudart", "-lpthread", "-ldl"]
     subprocess.check_call(link)
     return LIB
 

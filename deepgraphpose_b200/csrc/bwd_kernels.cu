@@ -3,10 +3,10 @@
 // optimizer.compute_gradients(total_loss, TF.trainable_variables()) (src/deepgraphpose/models/fitdgp.py:706-713) through
 // slim resnet_v1_50 with is_training=False (frozen moving statistics; gamma, beta and conv weights trainable).
 //
-//   relu_bn_bwd   : dy = g * [a > 0] in place, plus the per-channel sums the frozen-BN parameter gradients need
-//                   (dbeta = sum dy, dgamma = sum dy * (y - beta) / gamma with y the BN output, recovered from the
-//                   stored post-ReLU activation where the mask is open).  At a bottleneck junction
-//                   out = relu(shortcut + bn3(conv3)) the same pass yields conv3's and the projection shortcut's sums.
+//   relu_bn_bwd   : dy = g * [a > 0] in place, plus the per-channel sum of dy (dbeta of the frozen BN; at a bottleneck junction
+//                   out = relu(shortcut + bn3(conv3)) conv3 and the projection shortcut share it).  dgamma is taken from the
+//                   weight gradient: sum_p dy*z = <W[c,:], dW_raw[c,:]> with z the conv output, so
+//                   dgamma = (<W, dW_raw> - mean * dbeta) / sigma -- exact for gamma = 0 too (wgrad_gemm_sm100.cu).
 //   maxpool_bwd   : gradient of slim.max_pool2d(3x3, stride 2, SAME), routed to the first maximum of each window.
 //   upsample2     : zero insertion that turns the stride-2 3x3 dgrad into a stride-1 conv.
 //   scatter_add2  : gradient of resnet_utils.subsample (identity shortcut of a stride-2 unit): g_x[2p,2q] += d[p,q].
@@ -22,98 +22,65 @@ namespace {
 using h16::unpack8;
 __device__ __forceinline__ uint4 pack8v(const float* f, int fp16) { return h16::pack8(f, fp16); }
 
-// MODE 0: plain ReLU layer.  MODE 1: junction, shortcut on the same pixel grid.  MODE 2: junction, identity shortcut
-// subsampled by 2 (sc is the unit input (N,Hx,Wx,C), read at (2p, 2q)).
-template <int MODE>
-__global__ void __launch_bounds__(256) relu_bn_bwd_kernel(uint4* __restrict__ g, const uint4* __restrict__ act,
-                                                          const uint4* __restrict__ sc, int M, int C8, int P, int Q,
-                                                          int Hx, int Wx, float* __restrict__ partial, int fp16) {
-  constexpr int NS = MODE == 0 ? 2 : 3;
+// dy = g * [act > 0] in place + per-channel partial sums of dy (-> dbeta).  The same kernel serves plain ReLU layers and the
+// bottleneck junctions out = relu(shortcut + bn3(conv3)): dgamma no longer needs the BN output (see bn_gamma_grad_kernel in
+// wgrad_gemm_sm100.cu), so neither the shortcut tensor nor a division by gamma is involved.
+__global__ void __launch_bounds__(256) relu_bn_bwd_kernel(uint4* __restrict__ g, const uint4* __restrict__ act, int M, int C8,
+                                                          float* __restrict__ partial, int fp16) {
   const int my_cg = threadIdx.x % C8;
   const int my_r = threadIdx.x / C8;
   const int rpb = 256 / C8;
-  float S[NS][8];
+  float S[8];
 #pragma unroll
-  for (int s = 0; s < NS; ++s)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) S[s][j] = 0.0f;
+  for (int j = 0; j < 8; ++j) S[j] = 0.0f;
   for (int r = blockIdx.x * rpb + my_r; r < M; r += gridDim.x * rpb) {
     const size_t idx = (size_t)r * C8 + my_cg;
-    float gv[8], av[8], sv[8];
+    float gv[8], av[8];
     unpack8(g[idx], gv, fp16);
     unpack8(__ldg(act + idx), av, fp16);
-    if (MODE == 1) {
-      unpack8(__ldg(sc + idx), sv, fp16);
-    } else if (MODE == 2) {
-      const int n = r / (P * Q);
-      const int rem = r - n * (P * Q);
-      const int pp = rem / Q;
-      const int qq = rem - pp * Q;
-      unpack8(__ldg(sc + (((size_t)n * Hx + 2 * pp) * Wx + 2 * qq) * C8 + my_cg), sv, fp16);
-    }
     float d[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       d[j] = av[j] > 0.0f ? gv[j] : 0.0f;
-      S[0][j] += d[j];
-      if (MODE == 0) {
-        S[1][j] += d[j] * av[j];
-      } else {
-        S[1][j] += d[j] * (av[j] - sv[j]);
-        S[2][j] += d[j] * sv[j];
-      }
+      S[j] += d[j];
     }
     g[idx] = pack8v(d, fp16);
   }
-  __shared__ float sm[256][NS * 8 + 1];
+  __shared__ float sm[256][9];
 #pragma unroll
-  for (int s = 0; s < NS; ++s)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) sm[threadIdx.x][s * 8 + j] = S[s][j];
+  for (int j = 0; j < 8; ++j) sm[threadIdx.x][j] = S[j];
   __syncthreads();
   if (my_r == 0) {
     const int C = C8 * 8;
 #pragma unroll
-    for (int s = 0; s < NS; ++s)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float acc = 0.0f;
-        for (int rr = 0; rr < rpb; ++rr) acc += sm[rr * C8 + my_cg][s * 8 + j];
-        partial[((size_t)blockIdx.x * NS + s) * C + my_cg * 8 + j] = acc;
-      }
+    for (int j = 0; j < 8; ++j) {
+      float acc = 0.0f;
+      for (int rr = 0; rr < rpb; ++rr) acc += sm[rr * C8 + my_cg][j];
+      partial[(size_t)blockIdx.x * C + my_cg * 8 + j] = acc;
+    }
   }
 }
 
-// dbeta[c] = S0;  dgamma[c] = (S_which - beta * S0) / gamma.  Block = 8 channels x 128 row groups: row group r sums the
-// partial rows r, r+128, ... (at most 5 dependent loads per thread -- this kernel is pure latency), then a fixed-order tree
-// over the row groups.
-__global__ void __launch_bounds__(1024) bn_grad_finalize_kernel(const float* __restrict__ partial, int nblocks, int NS,
-                                                                int which, int C, const float* __restrict__ gamma,
-                                                                const float* __restrict__ beta,
-                                                                float* __restrict__ dgamma, float* __restrict__ dbeta) {
+// dbeta[c] = sum of the partial rows (written to one or two layers: conv3 and the projection shortcut share dy at a junction).
+// Block = 8 channels x 128 row groups: row group r sums the partial rows r, r+128, ... (at most 5 dependent loads per thread --
+// this kernel is pure latency), then a fixed-order tree over the row groups.
+__global__ void __launch_bounds__(1024) bn_grad_finalize_kernel(const float* __restrict__ partial, int nblocks, int C,
+                                                                float* __restrict__ dbeta_a, float* __restrict__ dbeta_b) {
   const int cl = threadIdx.x & 7, rg = threadIdx.x >> 3;
   const int c = blockIdx.x * 8 + cl;
-  float s0 = 0.0f, s1 = 0.0f;
+  float s0 = 0.0f;
   if (c < C)
-    for (int b = rg; b < nblocks; b += 128) {
-      s0 += partial[((size_t)b * NS + 0) * C + c];
-      s1 += partial[((size_t)b * NS + which) * C + c];
-    }
-  __shared__ float sm0[128][9], sm1[128][9];
+    for (int b = rg; b < nblocks; b += 128) s0 += partial[(size_t)b * C + c];
+  __shared__ float sm0[128][9];
   sm0[rg][cl] = s0;
-  sm1[rg][cl] = s1;
   __syncthreads();
   for (int st = 64; st > 0; st >>= 1) {
-    if (rg < st) {
-      sm0[rg][cl] += sm0[rg + st][cl];
-      sm1[rg][cl] += sm1[rg + st][cl];
-    }
+    if (rg < st) sm0[rg][cl] += sm0[rg + st][cl];
     __syncthreads();
   }
   if (rg == 0 && c < C) {
-    const float gm = gamma[c];
-    dbeta[c] = sm0[0][cl];
-    dgamma[c] = fabsf(gm) > 1e-20f ? (sm1[0][cl] - beta[c] * sm0[0][cl]) / gm : 0.0f;
+    dbeta_a[c] = sm0[0][cl];
+    if (dbeta_b != nullptr) dbeta_b[c] = sm0[0][cl];
   }
 }
 
@@ -310,22 +277,15 @@ int relu_bn_bwd_blocks(int M, int C) {
   return blocks < 1 ? 1 : blocks;
 }
 
-cudaError_t launch_relu_bn_bwd(int mode, void* g, const void* act, const void* sc, int M, int C, int P, int Q, int Hx,
-                               int Wx, float* partial, int fp16, cudaStream_t s) {
+cudaError_t launch_relu_bn_bwd(void* g, const void* act, int M, int C, float* partial, int fp16, cudaStream_t s) {
   if (C % 8 || 256 % (C / 8) || C / 8 > 256) return cudaErrorInvalidValue;
   const int blocks = relu_bn_bwd_blocks(M, C);
-  uint4* gg = reinterpret_cast<uint4*>(g);
-  const uint4* aa = reinterpret_cast<const uint4*>(act);
-  const uint4* ss = reinterpret_cast<const uint4*>(sc);
-  if (mode == 0) relu_bn_bwd_kernel<0><<<blocks, 256, 0, s>>>(gg, aa, ss, M, C / 8, P, Q, Hx, Wx, partial, fp16);
-  else if (mode == 1) relu_bn_bwd_kernel<1><<<blocks, 256, 0, s>>>(gg, aa, ss, M, C / 8, P, Q, Hx, Wx, partial, fp16);
-  else relu_bn_bwd_kernel<2><<<blocks, 256, 0, s>>>(gg, aa, ss, M, C / 8, P, Q, Hx, Wx, partial, fp16);
+  relu_bn_bwd_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<uint4*>(g), reinterpret_cast<const uint4*>(act), M, C / 8, partial, fp16);
   return cudaGetLastError();
 }
 
-cudaError_t launch_bn_grad_finalize(const float* partial, int nblocks, int ns, int which, int C, const float* gamma,
-                                    const float* beta, float* dgamma, float* dbeta, cudaStream_t s) {
-  bn_grad_finalize_kernel<<<(C + 7) / 8, 1024, 0, s>>>(partial, nblocks, ns, which, C, gamma, beta, dgamma, dbeta);
+cudaError_t launch_bn_grad_finalize(const float* partial, int nblocks, int C, float* dbeta_a, float* dbeta_b, cudaStream_t s) {
+  bn_grad_finalize_kernel<<<(C + 7) / 8, 1024, 0, s>>>(partial, nblocks, C, dbeta_a, dbeta_b);
   return cudaGetLastError();
 }
 

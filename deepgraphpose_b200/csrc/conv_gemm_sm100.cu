@@ -58,9 +58,43 @@ __device__ __forceinline__ uint32_t max16x2(uint32_t a, uint32_t b) {
 // One epilogue unit = this warp's 32 accumulator rows x 32 columns: BN scale/shift (fp32, packed FFMA2) (+ residual)
 // (+ ReLU, folded into the float -> 16-bit conversion) written in place into the warp's 2 KB staging buffer
 // (32 rows x 64 B, SWIZZLE_64B: 16-byte unit u of row r lives at u ^ ((r >> 1) & 3), conflict-free for LDS/STS.128).
-template <bool kFp16, bool kRelu, bool kRes>
-__device__ __forceinline__ void epi_unit_math(const uint32_t (&v)[2][16], uint8_t* my_row, int lane, const float* ss) {
+// per-pair mask 0xFFFF where the 16-bit activation is > 0 (post-ReLU tensors: > 0 <=> != 0)
+template <bool kFp16>
+__device__ __forceinline__ uint32_t gt0_mask16x2(uint32_t a) {
+  if (kFp16) return __hgt2_mask(*reinterpret_cast<const __half2*>(&a), __float2half2_rn(0.0f));
+  return __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&a), __float2bfloat162_rn(0.0f));
+}
+template <bool kFp16>
+__device__ __forceinline__ float2 unpack16x2(uint32_t v) {
+  if (kFp16) return __half22float2(*reinterpret_cast<const __half2*>(&v));
+  return make_float2(bf16lo(v), bf16hi(v));
+}
+
+// Sum over the 32 lanes (rows) of 32 per-lane values (channels): lane l ends up with the total of channel l.  Halving
+// butterfly: at distance d the lane keeps the half of its values its bit d selects and receives the partner's copy of that
+// half (31 shuffles, fixed order -> bitwise reproducible).
+__device__ __forceinline__ float colsum32(float (&f)[32], int lane) {
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) {
+    const bool up = (lane & d) != 0;
+#pragma unroll
+    for (int i = 0; i < d; ++i) {
+      const float send = up ? f[i] : f[i + d];
+      const float keep = up ? f[i + d] : f[i];
+      f[i] = keep + __shfl_xor_sync(0xffffffffu, send, d);
+    }
+  }
+  return f[0];
+}
+
+// kMask: the unit is a dgrad tile whose consumer would apply dy = g * [act > 0] and sum dy per channel (frozen-BN dbeta):
+// done here -- `act` holds this lane's 32 activations (64 B), the masked 16-bit values go to the staging row and their
+// per-channel sums over the 32 rows come back in lane order (lane l = channel l of the unit).
+template <bool kFp16, bool kRelu, bool kRes, bool kMask>
+__device__ __forceinline__ float epi_unit_math(const uint32_t (&v)[2][16], uint8_t* my_row, int lane, const float* ss,
+                                               const uint4* act = nullptr) {
   const int sw = (lane >> 1) & 3;
+  float f[kMask ? 32 : 1];
 #pragma unroll
   for (int s2 = 0; s2 < 2; ++s2) {
     uint4* s0 = reinterpret_cast<uint4*>(my_row + (((2 * s2) ^ sw) << 4));
@@ -99,15 +133,33 @@ __device__ __forceinline__ void epi_unit_math(const uint32_t (&v)[2][16], uint8_
       o[i] = ptx::cvt_pack16<kFp16, kRelu>(a0, a1);
       o[i + 1] = ptx::cvt_pack16<kFp16, kRelu>(b0, b1);
     }
+    if (kMask) {
+      const uint4 m0 = act[2 * s2], m1 = act[2 * s2 + 1];
+      const uint32_t mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        o[i] &= gt0_mask16x2<kFp16>(mm[i]);
+        const float2 d = unpack16x2<kFp16>(o[i]);
+        f[s2 * 16 + 2 * i] = d.x;
+        f[s2 * 16 + 2 * i + 1] = d.y;
+      }
+    }
     *s0 = make_uint4(o[0], o[1], o[2], o[3]);
     *s1 = make_uint4(o[4], o[5], o[6], o[7]);
   }
+  if (kMask) {
+    float (&f32)[32] = reinterpret_cast<float (&)[32]>(f);
+    return colsum32(f32, lane);
+  }
+  return 0.0f;
 }
 
 // kFp16 selects the 16-bit storage type at compile time (bf16 / fp16): no dtype branches in the epilogue.
 // kCta2: CTA-pair variant (cluster of 2, tcgen05 cta_group::2): one 256-row x 256-column tile per pair, each CTA stages its
 // own 128 rows of A and half of the weight tile (half the shared-memory operand traffic per MMA), the leader issues the MMA.
-template <bool kFp16, bool kCta2>
+// kMask: backward-pass variant whose epilogue applies the consumer's ReLU mask and writes dbeta partial sums (own
+// instantiation so that the forward kernels keep their register allocation).
+template <bool kFp16, bool kCta2, bool kMask>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t cta_rank = kCta2 ? ptx::cluster_ctarank() : 0u;
@@ -816,6 +868,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         uint32_t v[2][16];
         ptx::tmem_ld_x16(taddr, v[0]);
         ptx::tmem_ld_x16(taddr + 16, v[1]);
+        uint4 act[kMask ? 4 : 1];
+        if (kMask) {
+          const int row = row0 + lane;
+          if (row < p.M) {
+            const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.mask_act) +
+                                                             ((size_t)row * p.ldc + n0 + (colg << 5)) * 2);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) act[i] = __ldg(ap + i);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) act[i] = make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
         if (has_res) {
           // the buffer the next prefetch lands in was last used by the unit before this one: its store must have
           // finished reading shared memory (it was committed a whole unit ago)
@@ -834,12 +899,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         ptx::tmem_ld_wait();
         const float* ssu = ss + (colg >> 2) * 64;
         uint8_t* my_row = my_buf + lane * 64;
-        if (has_res) {
-          if (p.relu) epi_unit_math<kFp16, true, true>(v, my_row, lane, ssu);
-          else epi_unit_math<kFp16, false, true>(v, my_row, lane, ssu);
+        if (kMask) {
+          // dgrad tile with the consumer's ReLU mask and dbeta sums fused (the activation row was requested before the waits)
+          const float cs = has_res ? epi_unit_math<kFp16, false, true, true>(v, my_row, lane, ssu, act)
+                                   : epi_unit_math<kFp16, false, false, true>(v, my_row, lane, ssu, act);
+          if (row0 < p.M) p.colsum_part[(size_t)(row0 >> 5) * p.N + n0 + (colg << 5) + lane] = cs;
+        } else if (has_res) {
+          if (p.relu) epi_unit_math<kFp16, true, true, false>(v, my_row, lane, ssu);
+          else epi_unit_math<kFp16, false, true, false>(v, my_row, lane, ssu);
         } else {
-          if (p.relu) epi_unit_math<kFp16, true, false>(v, my_row, lane, ssu);
-          else epi_unit_math<kFp16, false, false>(v, my_row, lane, ssu);
+          if (p.relu) epi_unit_math<kFp16, true, false, false>(v, my_row, lane, ssu);
+          else epi_unit_math<kFp16, false, false, false>(v, my_row, lane, ssu);
         }
         ptx::fence_proxy_async_smem();  // my generic-proxy smem writes -> visible to the TMA store (async proxy)
         __syncwarp();
@@ -1002,15 +1072,18 @@ const char* make_tmap_tiled4d(CUtensorMap* out, const void* base, uint64_t C, ui
 
 cudaError_t launch_conv_gemm(const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
   static bool attr_set = false;
+  const void* fns[8] = {(const void*)conv_gemm_kernel<false, false, false>, (const void*)conv_gemm_kernel<true, false, false>,
+                        (const void*)conv_gemm_kernel<false, true, false>,  (const void*)conv_gemm_kernel<true, true, false>,
+                        (const void*)conv_gemm_kernel<false, false, true>,  (const void*)conv_gemm_kernel<true, false, true>,
+                        (const void*)conv_gemm_kernel<false, true, true>,   (const void*)conv_gemm_kernel<true, true, true>};
   if (!attr_set) {
-    const void* fns[4] = {(const void*)conv_gemm_kernel<false, false>, (const void*)conv_gemm_kernel<true, false>,
-                          (const void*)conv_gemm_kernel<false, true>, (const void*)conv_gemm_kernel<true, true>};
     for (const void* f : fns) {
       cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       if (e != cudaSuccess) return e;
     }
     attr_set = true;
   }
+  if (p.mask_act != nullptr && (p.epi_mode != 1 || p.colsum_part == nullptr)) return cudaErrorInvalidValue;
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   int grid = tiles < num_sms ? tiles : num_sms;
   if (p.cta2) {   // one tile per CTA pair
@@ -1034,11 +1107,10 @@ cudaError_t launch_conv_gemm(const ConvGemmParams& p, int num_sms, cudaStream_t 
     attr[1].val.clusterDim.y = 1;
     attr[1].val.clusterDim.z = 1;
     cfg.numAttrs = 2;
-    if (p.fp16) return cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true, true>, p);
-    return cudaLaunchKernelEx(&cfg, conv_gemm_kernel<false, true>, p);
   }
-  if (p.fp16) return cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true, false>, p);
-  return cudaLaunchKernelEx(&cfg, conv_gemm_kernel<false, false>, p);
+  const void* fn = fns[(p.fp16 ? 1 : 0) + (p.cta2 ? 2 : 0) + (p.mask_act != nullptr ? 4 : 0)];
+  void* args[1] = {const_cast<ConvGemmParams*>(&p)};
+  return cudaLaunchKernelExC(&cfg, fn, args);
 }
 
 }  // namespace dgp

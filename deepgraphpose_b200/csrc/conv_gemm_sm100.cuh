@@ -59,6 +59,10 @@ struct ConvGemmParams {
   int res_H, res_W;
   int ldres;         // residual row stride (elements)
   int relu;
+  // epi_mode 1, backward pass: the consumer's ReLU mask and dbeta sums fused into this (dgrad) GEMM's epilogue --
+  // out = value * [mask_act > 0] and colsum_part[row / 32][n] = sum over the 32 rows of a unit of the stored 16-bit values
+  const void* mask_act;   // 16-bit [M, ldc] post-ReLU activation of the tensor whose gradient this GEMM produces, or nullptr
+  float* colsum_part;     // fp32 [ceil(M / 32), N]
   void* out;         // bf16 or fp32, row-major [M, ldc]
   int out_f32;
   int ldc;
@@ -93,8 +97,13 @@ void wgrad_plan(WgradParams* p, int num_sms);
 size_t wgrad_workspace_bytes(const WgradParams& p);
 cudaError_t launch_wgrad_gemm(const WgradParams& p, int num_sms, cudaStream_t stream);
 // grad[co][kk] (=|+=) rowscale[co] * mask[co][kk] * sum over splits (fixed order); rowscale / mask may be null.
+// wmaster / rowdot_part (optional): also write <W[co, 4 kk], dW_raw[co, 4 kk]> per float4 of the row (Cout * Kw / 4 floats)
 cudaError_t launch_wgrad_reduce(const WgradParams& p, const float* rowscale, const float* mask, float* grad,
-                                int accumulate, cudaStream_t stream);
+                                int accumulate, cudaStream_t stream, const float* wmaster = nullptr,
+                                float* rowdot_part = nullptr);
+// dgamma = (row sums of rowdot_part - mean * dbeta) / sqrt(var + eps)  (frozen BN; exact, no division by gamma)
+cudaError_t launch_bn_gamma_grad(const float* rowdot_part, int Cout, int Kw, const float* mean, const float* var, float eps,
+                                 const float* dbeta, float* dgamma, cudaStream_t stream);
 
 // Host helpers (conv_gemm_sm100.cu)
 void tmap_set_fp16(int fp16);  // element type of subsequently encoded tensor maps

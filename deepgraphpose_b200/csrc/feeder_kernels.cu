@@ -41,7 +41,66 @@ __global__ void locref_targets_kernel(const double* __restrict__ joint_loc, cons
   }
 }
 
+// calculate_motion_energy (src/deepgraphpose/dataset.py:29-43): mean over the bytes of a frame of |frame - previous|, where
+// the reference subtracts uint8 arrays -- the difference wraps modulo 256 and np.abs is the identity on uint8.  Integer work:
+// the kernel returns the exact sum of (cur - prev) & 0xFF per frame (uint64); the host divides by the byte count in double,
+// which reproduces numpy's mean bit for bit.  Grid (frame, slice): every CTA streams 16 B per thread and iteration from the two
+// frames (coalesced uint4 loads), sums the 16 byte differences with packed byte arithmetic, reduces with warp shuffles and
+// adds one atomic per CTA (integer atomics: order-independent, exact).
+__global__ void __launch_bounds__(256) motion_energy_kernel(const uint8_t* __restrict__ frames, size_t frame_bytes,
+                                                            unsigned long long* __restrict__ sums) {
+  const int t = blockIdx.x + 1;                       // frame 0 has no predecessor: its energy is 0
+  const uint8_t* cur = frames + (size_t)t * frame_bytes;
+  const uint8_t* prev = cur - frame_bytes;
+  const size_t n16 = frame_bytes >> 4;
+  unsigned long long acc = 0;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(cur) | reinterpret_cast<uintptr_t>(prev)) & 15) == 0;
+  if (aligned) {
+    const uint4* c4 = reinterpret_cast<const uint4*>(cur);
+    const uint4* p4 = reinterpret_cast<const uint4*>(prev);
+    for (size_t i = (size_t)blockIdx.y * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.y * blockDim.x) {
+      const uint4 a = __ldg(c4 + i), b = __ldg(p4 + i);
+      const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+      uint32_t s = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t d = __vsub4(aw[k], bw[k]);     // per-byte wrapping difference
+        s += __vsadu4(d, 0u);                         // sum of the four bytes
+      }
+      acc += s;
+    }
+    if (blockIdx.y == 0)
+      for (size_t i = (n16 << 4) + threadIdx.x; i < frame_bytes; i += blockDim.x) acc += (uint8_t)(cur[i] - prev[i]);
+  } else {
+    for (size_t i = (size_t)blockIdx.y * blockDim.x + threadIdx.x; i < frame_bytes; i += (size_t)gridDim.y * blockDim.x)
+      acc += (uint8_t)(cur[i] - prev[i]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ unsigned long long sh[8];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long tot = 0;
+    for (int w = 0; w < 8; ++w) tot += sh[w];
+    atomicAdd(sums + t, tot);
+  }
+}
+
 }  // namespace
+
+cudaError_t launch_motion_energy(const uint8_t* frames, int T, size_t frame_bytes, unsigned long long* sums, int num_sms,
+                                 cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(sums, 0, (size_t)T * sizeof(unsigned long long), s);
+  if (e != cudaSuccess || T < 2) return e;
+  // enough slices per frame to fill the GPU a few times over, at least 64 KB per CTA
+  int slices = (int)((frame_bytes + 65535) / 65536);
+  const int want = (8 * num_sms + (T - 2)) / (T - 1);
+  if (slices > want) slices = want;
+  if (slices < 1) slices = 1;
+  motion_energy_kernel<<<dim3(T - 1, slices), 256, 0, s>>>(frames, frame_bytes, sums);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_locref_targets(const double* joint_loc, const int* frame_idx, int n_vis, int nt, int nj, int H, int W,
                                   double stride, double pos_dist_thresh, double locref_stdev, float* lmap, float* lmask,

@@ -130,8 +130,10 @@ struct dgp_handle {
   bool profiling = false;
   struct ProfRec {
     int kind;
+    int count = 1;   // launches bracketed by the event pair (> 1 in bracket mode)
     cudaEvent_t a, b;
   };
+  bool profile_brackets = false;  // dgp_set_profiling(h, 2): one event pair around every RUN of same-kind launches
   std::vector<ProfRec> prof;
   std::vector<cudaEvent_t> ev_pool;
   // softargmax workspace
@@ -201,10 +203,11 @@ struct ProfScope {
   dgp_handle* h;
   cudaStream_t s;
   int idx = -1;
-  ProfScope(dgp_handle* h_, int kind, cudaStream_t s_) : h(h_), s(s_) {
+  ProfScope(dgp_handle* h_, int kind, cudaStream_t s_, int count = 1) : h(h_), s(s_) {
     if (!h->profiling) return;
     dgp_handle::ProfRec r;
     r.kind = kind;
+    r.count = count;
     r.a = prof_event(h);
     r.b = prof_event(h);
     cudaEventRecord(r.a, s);

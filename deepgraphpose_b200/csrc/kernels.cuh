@@ -58,6 +58,7 @@ struct LossArgs {
   float* all_markers;   // scratch (nt*nj,2): targets_all_marker
   float4* partials;     // scratch (nbv+nbh)
   float* meanflow;      // scratch ((nt-1)*nj)
+  float* flow_part;     // scratch ((nt-1)*nj * ceil(Hin/16) * 8): per row-chunk partial sums of the flow box means
   float4* boxgrad;      // scratch ((nt-1)*nj): d meanflow / d (y1, x1, y2, x2) of the crop box, or nullptr (forward only)
   float* out;           // [6]
 };
@@ -90,11 +91,9 @@ cudaError_t launch_momentum_step(float* w, float* accum, const float* g, size_t 
                                  float grad_scale, const float* norm_clip, cudaStream_t s);
 
 // ---- network backward, bandwidth-class parts (bwd_kernels.cu)
-int relu_bn_bwd_blocks(int M, int C);  // rows of `partial` ([blocks][ns][C], ns = 2 for mode 0 else 3)
-cudaError_t launch_relu_bn_bwd(int mode, void* g, const void* act, const void* sc, int M, int C, int P, int Q, int Hx,
-                               int Wx, float* partial, int fp16, cudaStream_t s);
-cudaError_t launch_bn_grad_finalize(const float* partial, int nblocks, int ns, int which, int C, const float* gamma,
-                                    const float* beta, float* dgamma, float* dbeta, cudaStream_t s);
+int relu_bn_bwd_blocks(int M, int C);  // rows of `partial` ([blocks][C])
+cudaError_t launch_relu_bn_bwd(void* g, const void* act, int M, int C, float* partial, int fp16, cudaStream_t s);
+cudaError_t launch_bn_grad_finalize(const float* partial, int nblocks, int C, float* dbeta_a, float* dbeta_b, cudaStream_t s);
 // arg_ws: N*Ho*Wo*C bytes (first-maximum position of every pooled element)
 cudaError_t launch_maxpool_bwd(const void* x, const void* gout, int N, int H, int W, int C, int Ho, int Wo, int pad_t,
                                int pad_l, void* arg_ws, void* gx, int fp16, cudaStream_t s);
@@ -116,6 +115,9 @@ cudaError_t launch_soft_pose(const float* st, const float* locref, int B, int H,
 // ---- host-feeder replacements (feeder_kernels.cu)
 // coord2map + scatter over the batch: joint_loc (n_vis,nj,2) double scoremap (row,col), NaN = missing; frame_idx (n_vis)
 // position of each visible frame in the batch; lmap / lmask (nt,H,W,2nj) float32 are fully overwritten.
+// sums[t] = sum over the bytes of (frames[t] - frames[t-1]) & 0xFF (sums[0] = 0): calculate_motion_energy, dataset.py:29-43
+cudaError_t launch_motion_energy(const uint8_t* frames, int T, size_t frame_bytes, unsigned long long* sums, int num_sms,
+                                 cudaStream_t s);
 cudaError_t launch_locref_targets(const double* joint_loc, const int* frame_idx, int n_vis, int nt, int nj, int H, int W,
                                   double stride, double pos_dist_thresh, double locref_stdev, float* lmap, float* lmask,
                                   cudaStream_t s);

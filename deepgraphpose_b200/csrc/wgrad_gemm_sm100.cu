@@ -247,7 +247,8 @@ template <int SG>
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partials, int Cout, int Kw, int nnb,
                                                            int splits, const float* __restrict__ rowscale,
                                                            const float* __restrict__ mask, float* __restrict__ grad,
-                                                           int accumulate) {
+                                                           int accumulate, const float* __restrict__ wmaster,
+                                                           float* __restrict__ rowdot_part) {
   constexpr int EPB = 256 / SG;  // float4 elements per block
   const int e = threadIdx.x % EPB, sg = threadIdx.x / EPB;
   const size_t total = (size_t)Cout * (Kw >> 2);
@@ -275,6 +276,11 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
     }
   }
   if (t >= total) return;
+  if (rowdot_part != nullptr) {
+    // <W[co, kk..kk+3], dW_raw[co, kk..kk+3]>: summed over the row this is sum_p dy[p,co] * z[p,co] (z = conv output)
+    const float4 w = *reinterpret_cast<const float4*>(wmaster + (size_t)co * Kw + kk);
+    rowdot_part[t] = (acc.x * w.x + acc.y * w.y) + (acc.z * w.z + acc.w * w.w);
+  }
   const float rs = rowscale ? rowscale[co] : 1.0f;
   acc.x *= rs; acc.y *= rs; acc.z *= rs; acc.w *= rs;
   float4* g = reinterpret_cast<float4*>(grad + (size_t)co * Kw + kk);
@@ -287,6 +293,23 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
     acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
   }
   *g = acc;
+}
+
+// dgamma[c] = (sum_kk rowdot_part[c][kk] - mean[c] * dbeta[c]) / sqrt(var[c] + eps): one warp per channel, lane-strided sums
+// then a fixed shuffle tree (bitwise reproducible).  No division by gamma: channels with gamma = 0 get their true gradient.
+__global__ void __launch_bounds__(256) bn_gamma_grad_kernel(const float* __restrict__ rowdot_part, int Cout, int K4,
+                                                            const float* __restrict__ mean, const float* __restrict__ var,
+                                                            float eps, const float* __restrict__ dbeta,
+                                                            float* __restrict__ dgamma) {
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (c >= Cout) return;
+  const float* row = rowdot_part + (size_t)c * K4;
+  float a = 0.0f;
+  for (int i = lane; i < K4; i += 32) a += row[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (lane == 0) dgamma[c] = (a - mean[c] * dbeta[c]) * rsqrtf(var[c] + eps);
 }
 
 }  // namespace
@@ -326,19 +349,25 @@ cudaError_t launch_wgrad_gemm(const WgradParams& p, int num_sms, cudaStream_t st
 }
 
 cudaError_t launch_wgrad_reduce(const WgradParams& p, const float* rowscale, const float* mask, float* grad,
-                                int accumulate, cudaStream_t stream) {
+                                int accumulate, cudaStream_t stream, const float* wmaster, float* rowdot_part) {
   const size_t total = (size_t)p.Cout * (p.Kw / 4);
   // few elements and many splits (the narrow, pixel-rich layers of block 1/2): spread the split loop over threads
   if (p.splits >= 32 && total <= 32768) {
     wgrad_reduce_kernel<16><<<(unsigned)((total + 15) / 16), 256, 0, stream>>>(p.partials, p.Cout, p.Kw, p.num_n_blocks,
-                                                                             p.splits, rowscale, mask, grad, accumulate);
+                                                                             p.splits, rowscale, mask, grad, accumulate, wmaster, rowdot_part);
   } else if (p.splits >= 8 && total <= 262144) {
     wgrad_reduce_kernel<4><<<(unsigned)((total + 63) / 64), 256, 0, stream>>>(p.partials, p.Cout, p.Kw, p.num_n_blocks,
-                                                                            p.splits, rowscale, mask, grad, accumulate);
+                                                                            p.splits, rowscale, mask, grad, accumulate, wmaster, rowdot_part);
   } else {
     wgrad_reduce_kernel<1><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p.partials, p.Cout, p.Kw, p.num_n_blocks,
-                                                                              p.splits, rowscale, mask, grad, accumulate);
+                                                                              p.splits, rowscale, mask, grad, accumulate, wmaster, rowdot_part);
   }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bn_gamma_grad(const float* rowdot_part, int Cout, int Kw, const float* mean, const float* var, float eps,
+                                 const float* dbeta, float* dgamma, cudaStream_t stream) {
+  bn_gamma_grad_kernel<<<(Cout + 7) / 8, 256, 0, stream>>>(rowdot_part, Cout, Kw / 4, mean, var, eps, dbeta, dgamma);
   return cudaGetLastError();
 }
 

@@ -1,7 +1,8 @@
-"""Drop-ins for the host feeders of deepgraphpose.dataset that sit on the training hot loop (reference:
-src/deepgraphpose/dataset.py).  Only the per-step feeders are here; video decoding, batching and the label files stay with
-the reference's Dataset class."""
+"""Drop-ins for the host feeders of deepgraphpose.dataset that sit on the training hot loop or scan whole videos (reference:
+src/deepgraphpose/dataset.py): coord2map (per step), calculate_motion_energy + select_hidden_frames (hidden-frame selection).
+Video decoding, batching and the label files stay with the reference's Dataset class."""
 import numpy as np
+import torch
 
 
 def coord2map(pdata, joint_loc, nx_out, ny_out, nj, engine=None):
@@ -19,3 +20,88 @@ def coord2map(pdata, joint_loc, nx_out, ny_out, nj, engine=None):
     lmap, lmask = engine.locref_targets(joint_loc, np.arange(n_vis), n_vis, nx_out, ny_out,
                                         float(get("pos_dist_thresh", 17)), float(get("locref_stdev", 7.2801)))
     return lmap.cpu().numpy().astype(np.float64), lmask.cpu().numpy().astype(np.float64)
+
+
+def calculate_motion_energy(video, engine=None, chunk=256):
+    """dataset.py:29-43: ``motion_energy[t] = np.mean(np.abs(frame[t] - frame[t-1]))`` with the frames as the decoder delivers
+    them (uint8: the difference wraps modulo 256 and ``abs`` is the identity -- reproduced, it is what ranks the hidden
+    frames), ``motion_energy[0] = 0``.  ``video`` is a path (decoded frame by frame with OpenCV, RGB) or an iterable / array of
+    uint8 (H,W,3) frames; the byte sums are computed on the GPU of ``engine`` (dgp_motion_energy, exact integers) chunk by
+    chunk, so host memory stays bounded and the result equals the reference's float64 means bit for bit."""
+    if engine is None:
+        raise ValueError("calculate_motion_energy needs the Engine whose GPU computes the sums (no CPU fallback)")
+    if isinstance(video, (str, bytes)) or hasattr(video, "__fspath__"):
+        from .eval import _iter_video
+        frames = _iter_video(video)
+    else:
+        frames = iter(video)
+    out = []
+    carry = None            # last frame of the previous chunk, on the device
+    buf = []
+    nbytes = None
+
+    def flush():
+        nonlocal carry, buf
+        if not buf:
+            return
+        x = torch.from_numpy(np.ascontiguousarray(np.stack(buf))).to(engine.device)
+        if carry is not None:
+            x = torch.cat([carry[None], x])
+        sums = engine.motion_energy_sums(x).cpu().numpy()
+        out.append(sums if carry is None else sums[1:])
+        carry = x[-1].clone()
+        buf = []
+
+    for fr in frames:
+        fr = np.asarray(fr)
+        if fr.dtype != np.uint8:
+            raise ValueError("calculate_motion_energy expects uint8 frames (as clip.iter_frames() yields them)")
+        nbytes = fr.size
+        buf.append(fr)
+        if len(buf) == chunk:
+            flush()
+    flush()
+    if not out:
+        return np.zeros((0,))
+    return np.concatenate(out).astype(np.float64) / float(nbytes)
+
+
+def make_neighboring_window(window_size=5):
+    """dataset.py:104-110: the offsets -n..n."""
+    return np.arange(-int(window_size), int(window_size) + 1)
+
+
+def get_neighboring_window(pv_all, ns, nt_max, nt_min=0):
+    """dataset.py:113-119: sorted union of the +-ns windows around the frames ``pv_all``, clipped to [nt_min, nt_max)."""
+    pv_all = np.asarray(pv_all)
+    idx = np.unique(pv_all[:, None] + make_neighboring_window(ns)[None, :])
+    return idx[(idx >= nt_min) & (idx < nt_max)]
+
+
+def select_hidden_frames(ns, pv_all, pvh_sorted, n_frames, n_max_frames, ns_jump=None, verbose=False):
+    """dataset.py:46-101: walk the frames in decreasing motion energy (``pvh_sorted``), skip those inside the +-ns window of a
+    visible frame or closer than ``max(ns - ns_jump, 1)`` to an already chosen frame, and stop when the windows of all chosen
+    frames would exceed ``n_max_frames``.  Returns the selected hidden-frame indices in selection order."""
+    if ns_jump is None:
+        ns_jump = ns
+    min_gap = max(ns - ns_jump, 1)
+    pv_all = np.asarray(pv_all)
+    chosen = np.empty(0, dtype="int")
+    visible_window = get_neighboring_window(pv_all, ns, n_frames)
+    if len(visible_window) >= n_max_frames:
+        return chosen
+    anchors = pv_all.copy()
+    pvh_sorted = np.asarray(pvh_sorted)
+    skipped = 0
+    for cand in pvh_sorted[~np.isin(pvh_sorted, visible_window)]:
+        if len(anchors) > 0 and np.min(np.abs(cand - anchors)) < min_gap:
+            skipped += 1
+            continue
+        if len(get_neighboring_window(np.append(anchors, cand), ns, n_frames)) > n_max_frames:
+            break
+        chosen = np.append(chosen, cand)
+        anchors = np.append(anchors, cand)
+    if verbose:
+        print("Selected additional {} hidden frames".format(len(chosen)))
+        print("Skipped {} high motion energy (me) frames".format(skipped))
+    return chosen

@@ -551,10 +551,22 @@ class Engine:
                                               _ptr(dw), d3, _stream(x.device)))
         return dw
 
+    def motion_energy_sums(self, frames):
+        """Exact byte sums of (frames[t] - frames[t-1]) mod 256 per frame (dgp_motion_energy): frames uint8 cuda (T,...)."""
+        if frames.dtype != torch.uint8 or not frames.is_cuda:
+            raise ValueError("frames must be a uint8 CUDA tensor")
+        frames = frames.contiguous()
+        T = frames.shape[0]
+        sums = torch.zeros((T,), dtype=torch.int64, device=frames.device)
+        if T:
+            self._check(self.lib.dgp_motion_energy(self.h, _ptr(frames), T, frames[0].numel(), _ptr(sums), _stream(frames.device)))
+        return sums
+
     PROFILE_KINDS = ("prep_s2d", "conv_gemm", "maxpool", "deconv_col2im", "softargmax", "dgrad_gemm", "wgrad_gemm",
                      "bwd_bandwidth")
 
     def set_profiling(self, enable=True):
+        """True / 1: CUDA events around every launch; 2: one event pair around every run of same-kind launches."""
         self._check(self.lib.dgp_set_profiling(self.h, int(enable)))
 
     def get_profile(self):

@@ -304,3 +304,93 @@ def evaluate_dgp_frames(engine, frames, loc_ref=True, loc_ref_calc="dlc", batch=
             pose = torch.cat([mu.flip(2) * engine.stride + 0.5 * engine.stride, torch.ones_like(mu[:, :, :1])], dim=2)
         out[t0:t0 + fr.shape[0]] = pose.reshape(fr.shape[0], -1).double().cpu().numpy()
     return out
+
+
+def pairwisedistances(DataCombined, scorer1, scorer2, pcutoff=-1, bodyparts=None):
+    """DeepLabCut's evaluate.pairwisedistances (called at eval.py:803-804) on the (scorer, bodypart, coord) column index:
+    per frame and bodypart the Euclidean distance between the two scorers' (x, y), and the same masked to predictions of
+    ``scorer2`` with likelihood >= pcutoff.  Returns (RMSE, RMSEpcutoff) DataFrames."""
+    import pandas as pd
+    mask = DataCombined[scorer2].xs("likelihood", level=1, axis=1) >= pcutoff
+    if bodyparts is None:
+        pointwise = (DataCombined[scorer1] - DataCombined[scorer2]) ** 2
+    else:
+        pointwise = (DataCombined[scorer1][bodyparts] - DataCombined[scorer2][bodyparts]) ** 2
+        mask = mask[bodyparts]
+    rmse = np.sqrt(pointwise.xs("x", level=1, axis=1) + pointwise.xs("y", level=1, axis=1))
+    return rmse, rmse[mask]
+
+
+def _read_collected_data(project_path, trainingset_folder, scorer):
+    """Human labels of a DLC project: ``CollectedData_<scorer>.h5`` (key df_with_missing) as the reference reads it
+    (eval.py:724-725), or the ``.csv`` DLC writes next to it when pytables is not installed."""
+    import pandas as pd
+    base = os.path.join(project_path, trainingset_folder, "CollectedData_" + scorer)
+    try:
+        return pd.read_hdf(base + ".h5", "df_with_missing")
+    except (ImportError, FileNotFoundError, OSError):
+        return pd.read_csv(base + ".csv", header=[0, 1, 2], index_col=0)
+
+
+def evaluate_dgp(proj_cfg_file, dgp_model_file, shuffle=1, loc_ref=None, loc_ref_calc="dlc", *, dlc_cfg=None, batch=8,
+                 device=None):
+    """eval.py:656-813: RMSE per labelled frame / joint of a DLC project, train and test errors printed, the RMSE DataFrame
+    returned.  ``proj_cfg_file`` is the project's config.yaml; the training-set folder, the train / test split
+    (Documentation_data-*.pickle) and the pose config follow DeepLabCut's layout (auxiliaryfunctions.GetTrainingSetFolder /
+    GetDataandMetaDataFilenames / LoadMetadata, restated here because deeplabcut is not a dependency).  ``dlc_cfg`` may supply
+    the pose config (num_joints, all_joints_names, stride, location_refinement, locref_stdev) instead of the project's
+    train/pose_cfg.yaml.  Frames are read with PIL and evaluated in batches of equal size through ``evaluate_dgp_frames``."""
+    import pickle
+    import pandas as pd
+    import yaml
+    from PIL import Image
+    with open(proj_cfg_file, "r") as stream:
+        proj_config = yaml.safe_load(stream)
+    project_path = proj_config.get("project_path") or os.path.dirname(os.path.abspath(str(proj_cfg_file)))
+    task, date = proj_config["Task"], proj_config["date"]
+    iteration = proj_config.get("iteration", 0)
+    trainingset_folder = os.path.join("training-datasets", "iteration-" + str(iteration), "UnaugmentedDataSet_" + task + date)
+    train_fraction = proj_config["TrainingFraction"][0]
+    if dlc_cfg is None:
+        model_folder = os.path.join("dlc-models", "iteration-" + str(iteration),
+                                    task + date + "-trainset" + str(int(train_fraction * 100)) + "shuffle" + str(shuffle))
+        with open(os.path.join(project_path, model_folder, "train", "pose_cfg.yaml"), "r") as stream:
+            dlc_cfg = yaml.safe_load(stream)
+    dlc_cfg = dict(dlc_cfg) if isinstance(dlc_cfg, dict) else dict(vars(dlc_cfg))
+    loc_ref = bool(dlc_cfg.get("location_refinement", True)) if loc_ref is None else bool(loc_ref)
+    dlc_cfg["location_refinement"] = loc_ref
+    dlc_cfg.setdefault("stride", 8.0)
+    sess, mu_n, softmax_tensor, scmap_tf, locref_tf, inputs = setup_dgp_eval_graph(dlc_cfg, dgp_model_file, loc_ref=loc_ref,
+                                                                                   device=device)
+    Data = _read_collected_data(project_path, trainingset_folder, proj_config["scorer"])
+    comparisonbodyparts = list(proj_config["bodyparts"])
+    meta = os.path.join(project_path, trainingset_folder,
+                        "Documentation_data-" + task + "_" + str(int(train_fraction * 100)) + "shuffle" + str(shuffle) + ".pickle")
+    with open(meta, "rb") as f:
+        _, trainIndices, testIndices, _ = pickle.load(f)
+    names = dlc_cfg.get("all_joints_names") or comparisonbodyparts
+    nj = len(names)
+    PredicteData = np.ones((len(Data.index), 3 * nj))
+    print("Analyzing data...")
+    # images of one size go through the engine together (the reference runs them one by one, eval.py:741-742)
+    by_shape = {}
+    for imageindex, imagename in enumerate(Data.index):
+        name = imagename if isinstance(imagename, str) else os.path.join(*imagename)
+        image = np.asarray(Image.open(os.path.join(project_path, name)).convert("RGB"))
+        by_shape.setdefault(image.shape, []).append((imageindex, image))
+    for shape, items in by_shape.items():
+        frames = np.stack([im for _, im in items])
+        pose = evaluate_dgp_frames(sess.engine, frames, loc_ref, loc_ref_calc, batch=batch)
+        for (imageindex, _), row in zip(items, pose):
+            PredicteData[imageindex, :] = row
+    sess.close()
+    DLCscorer = "DGP"
+    index = pd.MultiIndex.from_product([[DLCscorer], list(names), ["x", "y", "likelihood"]], names=["scorer", "bodyparts", "coords"])
+    DataMachine = pd.DataFrame(PredicteData, columns=index, index=Data.index.values)
+    DataCombined = pd.concat([Data.T, DataMachine.T], axis=0).T
+    RMSE, _ = pairwisedistances(DataCombined, proj_config["scorer"], DLCscorer, proj_config.get("pcutoff", 0.1), comparisonbodyparts)
+    testerror = np.nanmean(RMSE.iloc[testIndices].values.flatten())
+    trainerror = np.nanmean(RMSE.iloc[trainIndices].values.flatten())
+    print("Train error:", np.round(trainerror, 2), " pixels")
+    print("Test error:", np.round(testerror, 2), " pixels")
+    return RMSE

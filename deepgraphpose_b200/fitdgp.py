@@ -298,3 +298,168 @@ class TrainSession:
                 return type(f)(build(v) for v in f)
             return vals[f.kind]
         return build(fetches)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# fit_dgp / fit_dgp_labeledonly step loops (fitdgp.py:549-845, 257-546)
+# ----------------------------------------------------------------------------------------------------------------------
+def gen_batch(visible_frame_total, hidden_frame_total, all_frame_total, dgp_cfg, maxiters):
+    """Pre-computed batch list of fit_dgp (fitdgp_util.py:146-202): per dataset, windows of ``batch_size`` consecutive entries
+    of its sorted frame pool starting at random offsets (single frames when the pool is smaller than a batch), each tagged
+    with the dataset index as its last element; all windows shuffled.  Draws from ``np.random`` / ``random`` in the
+    reference's order, so the same seeds give the same list (pinned by tests/golden/feeders.npz)."""
+    import random
+    batch_size = int(_get(dgp_cfg, "batch_size"))
+    n_frames_total = int(np.sum([len(v) for v in all_frame_total]))
+    nepoch = int(min(int(n_frames_total * _get(dgp_cfg, "n_times_all_frames") / batch_size), maxiters))
+    windows = []
+    for i in range(len(all_frame_total)):
+        pool = np.unique(list(visible_frame_total[i]) + list(all_frame_total[i]) + list(hidden_frame_total[i]))
+        n_win = max(1, int(nepoch / n_frames_total * len(pool)))
+        if len(pool) < batch_size:
+            width = 1
+            starts = np.random.randint(0, len(pool), size=n_win)
+        else:
+            width = batch_size
+            starts = np.random.randint(0, len(pool) - batch_size, size=n_win)
+        picks = pool[(starts[:, None] + np.arange(width)[None, :]).astype(np.int64)]
+        tagged = np.hstack([picks, np.full((n_win, 1), i)])
+        windows += [w.astype(np.int32) for w in tagged]
+    return random.sample(windows, len(windows))
+
+
+def _fit_loop(data_batcher, dgp_cfg, variables, visible_frame_total, hidden_frame_total, all_frame_total, maxiters, step,
+              saveiters, displayiters, debug, labeled_only, device, batch_ind_all=None, snapshot_fn=None, verbose=True):
+    """The training loop both drivers share (fitdgp.py:727-845 / 431-546): batch schedule, per-batch feeds (learn_wt flow field
+    when wt > 0, coord2map locref targets -- built on the device --, 2-D grids), ``sess.run([loss, train_op])`` and snapshots.
+    Returns the list of per-iteration loss dicts (the reference only prints them)."""
+    import time
+    from random import randint
+    from .fitdgp_util import learn_wt
+    loss, total_loss, total_loss_visible, placeholders = dgp_loss(data_batcher, dgp_cfg, variables=variables, device=device)
+    learning_rate = learning_rate_placeholder()
+    train_op = momentum_train_op(total_loss_visible if labeled_only else total_loss, learning_rate)   # fitdgp.py:706-713
+    sess = TrainSession(placeholders)
+    engine = total_loss.graph.engine
+    if batch_ind_all is None:
+        if labeled_only:
+            # fitdgp.py:431-439: one labelled frame per iteration, drawn uniformly over the (dataset, frame) pairs
+            pairs = np.array([(v, i) for i, vis in enumerate(visible_frame_total) for v in vis]).reshape(-1, 2)
+            n_vis = float(_get(dgp_cfg, "n_visible_frames_total", None) or data_batcher.n_visible_frames_total)
+            nepoch = int(min(int(n_vis * _get(dgp_cfg, "n_times_all_frames")), maxiters))
+            batch_ind_all = [pairs[k] for k in np.random.randint(0, pairs.shape[0], size=nepoch)]
+        else:
+            batch_ind_all = gen_batch(visible_frame_total, hidden_frame_total, all_frame_total, dgp_cfg, maxiters)
+    save_iters = max(1, int(saveiters) if labeled_only else int(saveiters / int(_get(dgp_cfg, "batch_size"))))
+    maxiters = len(batch_ind_all)
+    data_batcher.reset()
+    wt = float(_get(dgp_cfg, "wt", 0))
+    prefix = str(_get(dgp_cfg, "snapshot_prefix", "snapshot"))
+    history = []
+    t_start = time.time()
+    for it in range(maxiters):
+        batch_ind = batch_ind_all[it]
+        dataset_i = int(batch_ind[-1])
+        all_frame_batch = batch_ind[:-1]
+        visible_frame_i = visible_frame_total[dataset_i]
+        all_frame_i = list(all_frame_total[dataset_i]) + list(hidden_frame_total[dataset_i])
+        visible_frame_batch_i = np.sort(np.array([i for i in all_frame_batch if i in visible_frame_i]))
+        if len(visible_frame_batch_i) == 0 and len(visible_frame_i) > 0:
+            visible_frame_batch_i = np.array([visible_frame_i[randint(0, len(visible_frame_i) - 1)]])
+        if labeled_only:
+            hidden_frame_batch_i = np.array([], dtype=np.int64)
+        else:
+            hidden_frame_batch_i = np.sort(np.array([i for i in all_frame_batch if (i in all_frame_i) and (i not in visible_frame_i)]))
+        (visible_frame, hidden_frame, _, all_data_batch, joint_loc, wt_batch_mask, all_marker_batch, addn_batch_info), d = \
+            data_batcher.next_batch(0, dataset_i, visible_frame_batch_i, hidden_frame_batch_i)
+        nt_batch = len(visible_frame) + len(hidden_frame)
+        visible_marker, hidden_marker, visible_marker_in_targets = addn_batch_info
+        all_frame = np.sort(list(visible_frame) + list(hidden_frame))
+        visible_frame_within_batch = [int(np.where(all_frame == i)[0][0]) for i in visible_frame]
+        vector_field = learn_wt(all_data_batch) if wt > 0 else np.zeros((1, 1, 1))
+        feed = {
+            placeholders["inputs"]: all_data_batch,
+            placeholders["targets"]: joint_loc,
+            # coord2map (dataset.py:242-331) runs on the device from `targets` + the batch positions of the visible frames
+            placeholders["visible_frame_within_batch"]: visible_frame_within_batch,
+            placeholders["visible_marker_pl"]: visible_marker,
+            placeholders["hidden_marker_pl"]: hidden_marker,
+            placeholders["visible_marker_in_targets_pl"]: visible_marker_in_targets,
+            placeholders["wt_batch_mask_pl"]: wt_batch_mask,
+            placeholders["vector_field_tf"]: vector_field,
+            placeholders["nt_batch_pl"]: nt_batch,
+            placeholders["wt_batch_pl"]: np.ones(nt_batch - 1) * wt,
+            learning_rate: float(_get(dgp_cfg, "lr", 0.005)),
+        }
+        t0 = time.time()
+        loss_eval, _ = sess.run([loss, train_op], feed)
+        history.append(loss_eval)
+        if verbose and it % displayiters == 0 and it > 0:
+            print("\nIteration {}/{}".format(it, maxiters))
+            print("dataset_i: ", dataset_i, flush=True)
+            print("\n running time: ", time.time() - t0, flush=True)
+            print("\n loss: ", loss_eval, flush=True)
+        if (it % save_iters == 0) or (it + 1) == maxiters:
+            names = [prefix + "-step" + str(step) + "{}".format(debug) + "-"]
+            if (it + 1) == maxiters:
+                names.append(prefix + "-step" + str(step) + "{}".format(debug) + "-final-")
+            for model_name in names:
+                if snapshot_fn is not None:
+                    snapshot_fn(engine, model_name, it)
+                else:   # saver.save(sess, model_name, global_step=...): TensorFlow checkpoint bundles
+                    engine.save_tf_checkpoint(model_name + "-0")
+                    if model_name.endswith("-") and not model_name.endswith("-final-"):
+                        engine.save_tf_checkpoint(model_name + "-%d" % it)
+    if verbose:
+        print("Finished {} iterations\n".format(maxiters), flush=True)
+        print("\n\n TOTAL TIME ELAPSED: ", time.time() - t_start)
+    engine.close()
+    return history
+
+
+_PROJECT_READER_MSG = (
+    "%s(snapshot, dlcpath, ...): reading the DLC project (config.yaml, labelled frames, videos_dgp/*) into a MultiDataset is the "
+    "reference's host-side data pipeline (dataset.py, moviepy decode) and is outside this library's scope (SURVEY.md 8: the "
+    "path starts at the feed_dict).  Pass data_batcher= (any object with the MultiDataset interface: .datasets[i].nx_out / "
+    ".ny_out / .labels, .S0, .nj, .n_frames_total, .n_visible_frames_total, .reset(), .next_batch(...)), dgp_cfg= and the frame "
+    "index lists; the step loop, feeders, loss, backward and optimizer then run here.")
+
+
+def fit_dgp(snapshot, dlcpath, batch_size=10, shuffle=1, step=2, saveiters=1000, displayiters=5, maxiters=200000, ns=10,
+            nc=2048, n_max_frames=2000, gm2=0, gm3=0, nepoch=100, wt=0, aug=True, debug="", trainingsetindex=0, *,
+            data_batcher=None, dgp_cfg=None, frame_lists=None, variables=None, device=None, batch_ind_all=None,
+            snapshot_fn=None, verbose=True):
+    """fitdgp.py:549-845 with the reference's argument list.  The keyword-only arguments carry what the reference derives from
+    the DLC project on the host: ``data_batcher`` (MultiDataset interface), ``dgp_cfg`` (the merged training config; gm2 / gm3 /
+    wt / batch_size given here override it like fitdgp.py:640-660), ``frame_lists`` = (visible_frame_total, hidden_frame_total,
+    all_frame_total) and ``variables`` (what ``restorer.restore(sess, init_weights)`` would load; defaults to
+    dgp_cfg.init_weights or ``snapshot``)."""
+    if data_batcher is None or dgp_cfg is None or frame_lists is None:
+        raise NotImplementedError(_PROJECT_READER_MSG % "fit_dgp")
+    cfg = SimpleNamespace(**(dict(dgp_cfg) if isinstance(dgp_cfg, dict) else vars(dgp_cfg)))
+    cfg.batch_size, cfg.gm2, cfg.gm3, cfg.wt = batch_size, gm2, gm3, wt
+    if aug and wt == 0 and verbose:
+        print("note: imgaug augmentation of visible frames (fitdgp.py:773-775) is a host feeder outside this library")
+    if variables is None:
+        variables = _get(cfg, "init_weights", None) or snapshot
+    vis, hid, allf = frame_lists
+    return _fit_loop(data_batcher, cfg, variables, vis, hid, allf, maxiters, step, saveiters, displayiters, debug, False, device,
+                     batch_ind_all, snapshot_fn, verbose)
+
+
+def fit_dgp_labeledonly(snapshot, dlcpath, shuffle=1, step=1, saveiters=1000, displayiters=5, maxiters=50000, ns=10, nc=2048,
+                        n_max_frames=2000, aug=True, trainingsetindex=0, *, data_batcher=None, dgp_cfg=None,
+                        frame_lists=None, variables=None, device=None, batch_ind_all=None, snapshot_fn=None, verbose=True):
+    """fitdgp.py:257-546: the same loop on the labelled frames only -- no hidden frames in a batch, and the optimizer follows
+    ``total_loss_visible`` (visible cross-entropy + locref Huber), fitdgp.py:406-414."""
+    if data_batcher is None or dgp_cfg is None or frame_lists is None:
+        raise NotImplementedError(_PROJECT_READER_MSG % "fit_dgp_labeledonly")
+    cfg = SimpleNamespace(**(dict(dgp_cfg) if isinstance(dgp_cfg, dict) else vars(dgp_cfg)))
+    cfg.wt = 0
+    cfg.batch_size = int(_get(cfg, "batch_size", 1))
+    cfg.gm2, cfg.gm3 = int(_get(cfg, "gm2", 1)) or 1, int(_get(cfg, "gm3", 3))
+    if variables is None:
+        variables = _get(cfg, "init_weights", None) or snapshot
+    vis, hid, allf = frame_lists
+    return _fit_loop(data_batcher, cfg, variables, vis, hid, allf, maxiters, step, saveiters, displayiters, "", True, device,
+                     batch_ind_all, snapshot_fn, verbose)

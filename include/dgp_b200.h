@@ -135,6 +135,13 @@ int dgp_locref_targets(dgp_handle* h, const double* joint_loc_dev, const int32_t
                        int W, double pos_dist_thresh, double locref_stdev, float* locref_map_dev, float* locref_mask_dev,
                        void* stream);
 
+/* Replaces the per-frame arithmetic of calculate_motion_energy (src/deepgraphpose/dataset.py:29-43), the score that ranks
+ * hidden frames for training: motion_energy[t] = np.mean(np.abs(frame[t] - frame[t-1])) on uint8 frames, i.e. the mean of the
+ * byte differences MODULO 256 (uint8 subtraction wraps, abs is the identity).  frames_dev: uint8 (T, frame_bytes), T consecutive
+ * frames; sums_dev: uint64 (T) <- exact byte sums (sums[0] = 0 -- pass the last frame of the previous chunk first to continue a
+ * video).  The caller divides by frame_bytes in double: bit-identical to the reference's float64 mean. */
+int dgp_motion_energy(dgp_handle* h, const uint8_t* frames_dev, int T, size_t frame_bytes, uint64_t* sums_dev, void* stream);
+
 /* Replaces PoseNet.test's tf.sigmoid(part_pred) (pose_net.py:84-90). n = number of floats (multiple of 4). */
 int dgp_sigmoid(dgp_handle* h, const float* logits_dev, float* prob_dev, size_t n, void* stream);
 
@@ -315,7 +322,10 @@ int dgp_conv2d_wgrad(dgp_handle* h, const void* x_dev, int N, int H, int W, int 
 /* CUDA-event timing per kernel family, recorded on the launching stream around every launch while enabled.
  * kinds: 0 = u8->bf16 space-to-depth prep, 1 = tcgen05 conv GEMM, 2 = max-pool, 3 = deconv col2im, 4 = soft-argmax,
  * 5 = dgrad GEMM, 6 = wgrad GEMM + reduce, 7 = bandwidth-class backward kernels.
- * dgp_get_profile synchronises the device, sums the elapsed ms and launch counts per kind and clears the records. */
+ * dgp_get_profile synchronises the device, sums the elapsed ms and launch counts per kind and clears the records.
+ * enable = 2 ("bracket" mode): ONE event pair around every run of consecutive same-kind launches (the 54 GEMM layers of a
+ * forward pass are one run) -- the launches inside keep their programmatic-dependent-launch overlap, which an event record
+ * between two of them would break. */
 int dgp_set_profiling(dgp_handle* h, int enable);
 int dgp_get_profile(dgp_handle* h, double* ms_by_kind, int64_t* count_by_kind, int nkinds);
 /* The same records one by one, in launch order (elapsed ms and kind of up to max_records launches; clears the records):

@@ -1,7 +1,9 @@
 """tests/golden/feeders.npz: outputs of the REFERENCE'S OWN ``coord2map`` (src/deepgraphpose/dataset.py:246-271) and
 ``PoseDataset.compute_target_part_scoremap`` (DeepLabCut .../dataset/pose_defaultdataset.py:220-266).  The two modules cannot
 be imported here (moviepy / skimage / tensorflow are absent), so the two function definitions are cut out of the reference
-files with ``ast`` and executed unmodified.  Run in the build container only:  python tests/golden/make_golden_feeders.py"""
+files with ``ast`` and executed unmodified.  Also: gen_idx_chunk, export_pose_like_dlc, learn_wt, calculate_motion_energy /
+select_hidden_frames / get_neighboring_window and gen_batch, the same way.
+Run in the build container only:  python tests/golden/make_golden_feeders.py"""
 import ast
 import os
 import types
@@ -96,5 +98,48 @@ exec(cut(REF + "/deepgraphpose/models/fitdgp_util.py", "learn_wt"), ns3)
 vid, _ = synthetic.make_video(3, 64, 96, 3, seed=77)
 vf = ns3["learn_wt"](vid.astype(np.float64))
 out.update({"flow_seed": np.array(77), "flow_field": vf.astype(np.float32)})
+# ---- hidden-frame selection: the reference's calculate_motion_energy / select_hidden_frames / get_neighboring_window
+# (dataset.py:29-119) on a synthetic clip (a stand-in for moviepy's VideoFileClip yields the frames) -- note the uint8 wrap
+class _Clip:
+    def __init__(self, frames):
+        self._f = frames
+        self.fps, self.duration = 10.0, len(frames) / 10.0
+
+    def iter_frames(self):
+        return iter(self._f)
+
+    def close(self):
+        pass
+
+
+me_vid, _ = synthetic.make_video(24, 48, 64, 3, seed=21)
+ns4 = {"np": np, "VideoFileClip": lambda path: _Clip(me_vid)}
+for fn in ("calculate_motion_energy", "make_neighboring_window", "get_neighboring_window", "select_hidden_frames"):
+    exec(cut(REF + "/deepgraphpose/dataset.py", fn), ns4)
+me = ns4["calculate_motion_energy"]("clip.mp4")
+order = np.argsort(me)[::-1]
+pv = np.array([3, 15])
+import contextlib, io
+with contextlib.redirect_stdout(io.StringIO()):
+    sel = [ns4["select_hidden_frames"](2, pv, order, len(me), nmax, jump) for nmax, jump in ((14, None), (20, 0), (8, None), (24, 1))]
+out.update({"me_seed": np.array(21), "me_values": me, "me_pv": pv, "me_order": order, "me_windowed": ns4["get_neighboring_window"](pv, 2, len(me))})
+for k, v in enumerate(sel):
+    out["me_sel%d" % k] = np.asarray(v, dtype=np.int64)
+# ---- gen_batch (models/fitdgp_util.py:146-202) with both RNGs seeded
+import random
+
+np.int = int    # removed from numpy; the reference pins an older one
+ns5 = {"np": np, "random": random}
+exec(cut(REF + "/deepgraphpose/models/fitdgp_util.py", "gen_batch"), ns5)
+gb_cfg = types.SimpleNamespace(batch_size=4, n_times_all_frames=3)
+gb_vis = [np.array([2, 9, 17]), np.array([1])]
+gb_hid = [np.array([5, 6, 30, 31]), np.array([], dtype=np.int64)]
+gb_all = [np.array([0, 1, 2, 3, 4, 7, 8, 9, 10, 11, 15, 16, 17, 18, 19]), np.array([0, 1, 2])]
+np.random.seed(11)
+random.seed(12)
+with contextlib.redirect_stdout(io.StringIO()):
+    gb = ns5["gen_batch"](gb_vis, gb_hid, gb_all, gb_cfg, 500)
+out["gen_batch_lens"] = np.array([len(b) for b in gb])
+out["gen_batch_flat"] = np.concatenate(gb)
 np.savez_compressed(os.path.join(OUT, "feeders.npz"), **out)
 print({k: v.shape for k, v in out.items()})

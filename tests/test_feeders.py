@@ -102,3 +102,61 @@ def test_learn_wt_matches_reference_flow():
     got = learn_wt(vid.astype(np.float64))
     assert got.shape == ref.shape == (2, 64, 96) and float(ref.max()) > 0
     assert np.allclose(got, ref, rtol=1e-5, atol=1e-5)
+
+
+def _golden():
+    with np.load(G) as z:
+        return {k: z[k] for k in z.files}
+
+
+def test_gen_batch_matches_reference_golden():
+    """fitdgp.gen_batch draws from np.random / random in the reference's order: same seeds -> the same batch list as the
+    reference's own gen_batch (fitdgp_util.py:146-202, run by tests/golden/make_golden_feeders.py)."""
+    import random
+    from types import SimpleNamespace
+    from deepgraphpose_b200 import fitdgp
+    g = _golden()
+    cfg = SimpleNamespace(batch_size=4, n_times_all_frames=3)
+    vis = [np.array([2, 9, 17]), np.array([1])]
+    hid = [np.array([5, 6, 30, 31]), np.array([], dtype=np.int64)]
+    allf = [np.array([0, 1, 2, 3, 4, 7, 8, 9, 10, 11, 15, 16, 17, 18, 19]), np.array([0, 1, 2])]
+    np.random.seed(11)
+    random.seed(12)
+    got = fitdgp.gen_batch(vis, hid, allf, cfg, 500)
+    assert [len(b) for b in got] == g["gen_batch_lens"].tolist()
+    assert np.array_equal(np.concatenate(got), g["gen_batch_flat"])
+    assert all(b.dtype == np.int32 for b in got)
+
+
+def test_hidden_frame_selection_matches_reference_golden():
+    """dataset.get_neighboring_window / select_hidden_frames vs the reference's own functions (dataset.py:46-119)."""
+    from deepgraphpose_b200 import dataset
+    g = _golden()
+    me, pv, order = g["me_values"], g["me_pv"], g["me_order"]
+    assert np.array_equal(dataset.get_neighboring_window(pv, 2, len(me)), g["me_windowed"])
+    for k, (nmax, jump) in enumerate(((14, None), (20, 0), (8, None), (24, 1))):
+        assert np.array_equal(dataset.select_hidden_frames(2, pv, order, len(me), nmax, jump), g["me_sel%d" % k]), k
+
+
+@pytest.mark.gpu
+def test_gpu_motion_energy_bit_exact_vs_reference_golden():
+    """dataset.calculate_motion_energy (dgp_motion_energy kernel: exact byte sums of the uint8-wrapped frame difference) ==
+    the reference's calculate_motion_energy on the same clip, bit for bit, whatever the chunking; odd byte counts and
+    unaligned frames take the scalar path."""
+    import torch
+    from deepgraphpose_b200 import dataset, synthetic
+    from deepgraphpose_b200.engine import Engine
+    g = _golden()
+    vid, _ = synthetic.make_video(24, 48, 64, 3, seed=int(g["me_seed"]))
+    eng = Engine(3, location_refinement=False)
+    for chunk in (256, 5, 1):
+        me = dataset.calculate_motion_energy(vid, engine=eng, chunk=chunk)
+        assert me.dtype == np.float64 and np.array_equal(me, g["me_values"]), chunk
+    rng = np.random.default_rng(0)
+    odd = rng.integers(0, 256, (7, 37, 29, 3), dtype=np.uint8)          # 3219 bytes per frame: not a multiple of 16
+    ref = np.array([0.0] + [np.mean(np.abs(odd[t] - odd[t - 1])) for t in range(1, 7)])
+    assert np.array_equal(dataset.calculate_motion_energy(odd, engine=eng), ref)
+    big = rng.integers(0, 256, (3, 747, 832, 3), dtype=np.uint8)
+    sums = eng.motion_energy_sums(torch.from_numpy(big).cuda()).cpu().numpy()
+    assert sums[0] == 0 and sums[1] == int((big[1] - big[0]).astype(np.uint64).sum()) and sums[2] == int((big[2] - big[1]).astype(np.uint64).sum())
+    eng.close()

@@ -175,6 +175,49 @@ def test_bf16_storage_mode_gradients():
     eng.close()
 
 
+def test_gamma_gradients_of_zero_and_tiny_gamma_channels():
+    """The second weight set (synthetic.make_weights(trained_like=True)): in every bottleneck's last BN 15 % of the channels
+    carry gamma = 10^U(-5,-2) and 2 % exactly 0, as in an ImageNet resnet_v1_50.ckpt.  dgamma is computed as
+    (<W[c,:], dW_raw[c,:]> - mean * dbeta) / sigma (wgrad_gemm_sm100.cu: bn_gamma_grad_kernel) -- no division by gamma -- so
+    those channels get their true gradient: checked against oracle autograd per BN vector AND restricted to the zero / tiny
+    channels (round 1 returned 0 for gamma = 0 and cancelled for small gamma)."""
+    from deepgraphpose_b200 import fitdgp
+    from deepgraphpose_b200.engine import Engine
+    rng = np.random.default_rng(5)
+    W = synthetic.make_weights(NJ, seed=5, trained_like=True)
+    frames, _ = synthetic.make_video(NT, HIN, WIN, NJ, seed=11)
+    H, Wd = 2 * -(-HIN // 16), 2 * -(-WIN // 16)
+    labels, batch = _batch(rng, NT, H, Wd, NJ)
+    edges = synthetic.chain_skeleton(NJ)
+    S0 = dgp_ops.skeleton_matrix(edges, NJ)
+    cfg = oracle_loss.default_dgp_cfg(gm2=1, gm3=3, wt=0.0)
+    ws, ws_max = oracle_loss.spatial_clique_params(labels, S0, cfg)
+    _, ref, _ = _oracle_grads(W, frames, batch, S0, cfg, ws, ws_max)
+    eng = Engine(NJ)
+    eng.load_weights(W)
+    fitdgp.train_forward_backward(eng, torch.from_numpy(frames).cuda(), batch, cfg, edges, ws, ws_max, 200, 20)
+    n_small = 0
+    for name, g_ref in sorted(ref.items()):
+        if not name.endswith("/conv3/BatchNorm/gamma"):
+            continue
+        g = eng.get_variable(name, "grad")
+        nr = float(np.linalg.norm(g_ref))
+        cos = float((g * g_ref).sum() / (np.linalg.norm(g) * nr + 1e-30))
+        assert cos > 0.99 and np.linalg.norm(g - g_ref) / nr < 0.12, (name, cos, np.linalg.norm(g - g_ref) / nr)
+        small = np.abs(W[name]) < 1e-2          # the zero and near-zero gamma channels of this BN
+        if small.sum() >= 8:
+            n_small += int(small.sum())
+            ns = float(np.linalg.norm(g_ref[small]))
+            assert ns > 0
+            cs = float((g[small] * g_ref[small]).sum() / (np.linalg.norm(g[small]) * ns + 1e-30))
+            assert cs > 0.99 and np.linalg.norm(g[small] - g_ref[small]) / ns < 0.12, (name, cs)
+            zero = W[name] == 0
+            if zero.any():
+                assert np.abs(g[zero]).max() > 0, name      # not the silent 0 a division by gamma would give
+    assert n_small > 100
+    eng.close()
+
+
 def test_optimizer_step_matches_oracle_momentum(trained):
     """clip_by_global_norm(10) + Momentum(0.9) on the GPU's own gradients == oracle.momentum_step, two steps in a row."""
     from deepgraphpose_b200 import fitdgp
