@@ -84,6 +84,39 @@ __global__ void __launch_bounds__(1024) bn_grad_finalize_kernel(const float* __r
   }
 }
 
+// All frozen-BN parameter gradients of the network in one launch (one block per 8 channels, 128 row groups x 8 channels):
+// dbeta = sum over the row blocks of the dy sums its mask site left, dgamma = (sum_kk <W, dW_raw> - mean * dbeta) / sigma.
+// Fixed summation order (strided partial sums, then a tree over the row groups): bitwise reproducible.
+__global__ void __launch_bounds__(1024) bn_finalize_all_kernel(const BnGroup* __restrict__ table, const float* __restrict__ part,
+                                                               const float* __restrict__ rowdot, const float* __restrict__ mean,
+                                                               const float* __restrict__ var, float eps,
+                                                               float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const BnGroup g = table[blockIdx.x];
+  const int cl = threadIdx.x & 7, rg = threadIdx.x >> 3;
+  const float* pp = part + g.part_off + g.col + cl;
+  float s0 = 0.0f, s1 = 0.0f;
+  for (int b = rg; b < g.rows; b += 128) s0 += pp[(size_t)b * g.C];
+  const float* rd = rowdot + g.rd_off + (size_t)cl * g.K4;
+  for (int i = rg; i < g.K4; i += 128) s1 += rd[i];
+  __shared__ float sm0[128][9], sm1[128][9];
+  sm0[rg][cl] = s0;
+  sm1[rg][cl] = s1;
+  __syncthreads();
+  for (int st = 64; st > 0; st >>= 1) {
+    if (rg < st) {
+      sm0[rg][cl] += sm0[rg + st][cl];
+      sm1[rg][cl] += sm1[rg + st][cl];
+    }
+    __syncthreads();
+  }
+  if (rg == 0) {
+    const int c = blockIdx.x * 8 + cl;
+    const float db = sm0[0][cl];
+    dbeta[c] = db;
+    dgamma[c] = (sm1[0][cl] - mean[c] * db) * rsqrtf(var[c] + eps);
+  }
+}
+
 // First-maximum position (0..8, row-major in the 3x3 window) of every pooled element: one byte per channel.
 __global__ void maxpool_argmax_kernel(const uint4* __restrict__ x, int N, int H, int W, int C8, int Ho, int Wo, int pad_t,
                                       int pad_l, uint2* __restrict__ arg, int fp16) {
@@ -281,6 +314,12 @@ cudaError_t launch_relu_bn_bwd(void* g, const void* act, int M, int C, float* pa
   if (C % 8 || 256 % (C / 8) || C / 8 > 256) return cudaErrorInvalidValue;
   const int blocks = relu_bn_bwd_blocks(M, C);
   relu_bn_bwd_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<uint4*>(g), reinterpret_cast<const uint4*>(act), M, C / 8, partial, fp16);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bn_finalize_all(const BnGroup* table, int ngroups, const float* part, const float* rowdot, const float* mean,
+                                   const float* var, float eps, float* dgamma, float* dbeta, cudaStream_t s) {
+  bn_finalize_all_kernel<<<ngroups, 1024, 0, s>>>(table, part, rowdot, mean, var, eps, dgamma, dbeta);
   return cudaGetLastError();
 }
 

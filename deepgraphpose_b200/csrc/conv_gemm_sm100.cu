@@ -70,31 +70,33 @@ __device__ __forceinline__ float2 unpack16x2(uint32_t v) {
   return make_float2(bf16lo(v), bf16hi(v));
 }
 
-// Sum over the 32 lanes (rows) of 32 per-lane values (channels): lane l ends up with the total of channel l.  Halving
-// butterfly: at distance d the lane keeps the half of its values its bit d selects and receives the partner's copy of that
-// half (31 shuffles, fixed order -> bitwise reproducible).
-__device__ __forceinline__ float colsum32(float (&f)[32], int lane) {
+// Per-channel sums over the 32 rows of a unit that sits in its staging buffer (32 rows x 64 B, SWIZZLE_64B): lane (j = lane & 15,
+// h = lane >> 4) walks the 16 rows h*16.. of channel pair j -- per step the warp reads two whole rows (128 B, conflict free) --
+// then the two halves meet in one shuffle.  Fixed order: bitwise reproducible.  Lanes 0..15 return the sums of channels 2j, 2j+1.
+template <bool kFp16>
+__device__ __forceinline__ float2 unit_colsum(const uint8_t* buf, int lane) {
+  const int j = lane & 15, h = lane >> 4;
+  const int u = j >> 2, w = j & 3;
+  float sx = 0.0f, sy = 0.0f;
 #pragma unroll
-  for (int d = 16; d >= 1; d >>= 1) {
-    const bool up = (lane & d) != 0;
-#pragma unroll
-    for (int i = 0; i < d; ++i) {
-      const float send = up ? f[i] : f[i + d];
-      const float keep = up ? f[i + d] : f[i];
-      f[i] = keep + __shfl_xor_sync(0xffffffffu, send, d);
-    }
+  for (int it = 0; it < 16; ++it) {
+    const int r = h * 16 + it;
+    const uint32_t v = *reinterpret_cast<const uint32_t*>(buf + r * 64 + ((u ^ ((r >> 1) & 3)) << 4) + w * 4);
+    const float2 d = unpack16x2<kFp16>(v);
+    sx += d.x;
+    sy += d.y;
   }
-  return f[0];
+  sx += __shfl_xor_sync(0xffffffffu, sx, 16);
+  sy += __shfl_xor_sync(0xffffffffu, sy, 16);
+  return make_float2(sx, sy);
 }
 
-// kMask: the unit is a dgrad tile whose consumer would apply dy = g * [act > 0] and sum dy per channel (frozen-BN dbeta):
-// done here -- `act` holds this lane's 32 activations (64 B), the masked 16-bit values go to the staging row and their
-// per-channel sums over the 32 rows come back in lane order (lane l = channel l of the unit).
+// kMask: the unit is a dgrad tile whose consumer would apply dy = g * [act > 0] (and sum dy per channel, unit_colsum above):
+// `act` holds this lane's 32 activations (64 B), the masked 16-bit values go to the staging row.
 template <bool kFp16, bool kRelu, bool kRes, bool kMask>
-__device__ __forceinline__ float epi_unit_math(const uint32_t (&v)[2][16], uint8_t* my_row, int lane, const float* ss,
-                                               const uint4* act = nullptr) {
+__device__ __forceinline__ void epi_unit_math(const uint32_t (&v)[2][16], uint8_t* my_row, int lane, const float* ss,
+                                              const uint4* act = nullptr) {
   const int sw = (lane >> 1) & 3;
-  float f[kMask ? 32 : 1];
 #pragma unroll
   for (int s2 = 0; s2 < 2; ++s2) {
     uint4* s0 = reinterpret_cast<uint4*>(my_row + (((2 * s2) ^ sw) << 4));
@@ -137,21 +139,11 @@ __device__ __forceinline__ float epi_unit_math(const uint32_t (&v)[2][16], uint8
       const uint4 m0 = act[2 * s2], m1 = act[2 * s2 + 1];
       const uint32_t mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        o[i] &= gt0_mask16x2<kFp16>(mm[i]);
-        const float2 d = unpack16x2<kFp16>(o[i]);
-        f[s2 * 16 + 2 * i] = d.x;
-        f[s2 * 16 + 2 * i + 1] = d.y;
-      }
+      for (int i = 0; i < 8; ++i) o[i] &= gt0_mask16x2<kFp16>(mm[i]);
     }
     *s0 = make_uint4(o[0], o[1], o[2], o[3]);
     *s1 = make_uint4(o[4], o[5], o[6], o[7]);
   }
-  if (kMask) {
-    float (&f32)[32] = reinterpret_cast<float (&)[32]>(f);
-    return colsum32(f32, lane);
-  }
-  return 0.0f;
 }
 
 // kFp16 selects the 16-bit storage type at compile time (bf16 / fp16): no dtype branches in the epilogue.
@@ -901,9 +893,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         uint8_t* my_row = my_buf + lane * 64;
         if (kMask) {
           // dgrad tile with the consumer's ReLU mask and dbeta sums fused (the activation row was requested before the waits)
-          const float cs = has_res ? epi_unit_math<kFp16, false, true, true>(v, my_row, lane, ssu, act)
-                                   : epi_unit_math<kFp16, false, false, true>(v, my_row, lane, ssu, act);
-          if (row0 < p.M) p.colsum_part[(size_t)(row0 >> 5) * p.N + n0 + (colg << 5) + lane] = cs;
+          if (has_res) epi_unit_math<kFp16, false, true, true>(v, my_row, lane, ssu, act);
+          else epi_unit_math<kFp16, false, false, true>(v, my_row, lane, ssu, act);
+          __syncwarp();
+          const float2 cs = unit_colsum<kFp16>(my_buf, lane);
+          if (lane < 16 && row0 < p.M)
+            *reinterpret_cast<float2*>(p.colsum_part + (size_t)(row0 >> 5) * p.N + n0 + (colg << 5) + 2 * lane) = cs;
         } else if (has_res) {
           if (p.relu) epi_unit_math<kFp16, true, true, false>(v, my_row, lane, ssu);
           else epi_unit_math<kFp16, false, true, false>(v, my_row, lane, ssu);

@@ -91,6 +91,15 @@ cudaError_t launch_momentum_step(float* w, float* accum, const float* g, size_t 
                                  float grad_scale, const float* norm_clip, cudaStream_t s);
 
 // ---- network backward, bandwidth-class parts (bwd_kernels.cu)
+// One entry per 8 consecutive BatchNorm channels (always one layer): where their dy sums ([rows][C] floats, this group at column
+// `col`) and their <W, dW_raw> products ([8][K4] floats) were left by the backward pass.
+struct BnGroup {
+  unsigned long long part_off = 0, rd_off = 0;
+  int rows = 0, C = 0, col = 0, K4 = 0;
+};
+// dbeta[c] = sum of the dy sums, dgamma[c] = (sum of the row-dot products - mean * dbeta) / sqrt(var + eps), all channels at once
+cudaError_t launch_bn_finalize_all(const BnGroup* table, int ngroups, const float* part, const float* rowdot, const float* mean,
+                                   const float* var, float eps, float* dgamma, float* dbeta, cudaStream_t s);
 int relu_bn_bwd_blocks(int M, int C);  // rows of `partial` ([blocks][C])
 cudaError_t launch_relu_bn_bwd(void* g, const void* act, int M, int C, float* partial, int fp16, cudaStream_t s);
 cudaError_t launch_bn_grad_finalize(const float* partial, int nblocks, int C, float* dbeta_a, float* dbeta_b, cudaStream_t s);

@@ -39,6 +39,14 @@ struct BStep {
 struct Backward {
   std::vector<BStep> steps;
   float *g_logits = nullptr, *g_locref = nullptr;
+  // Deferred frozen-BN gradients: every mask site leaves its per-row-block sums of dy in its own region of `bn_part`, every
+  // wgrad its <W, dW_raw> products in its slice of `rowdot`; ONE kernel at the end of the backward turns both into dbeta / dgamma
+  // for all 26 k channels (instead of ~100 latency-bound launches of 3-7 us each inside the pass).
+  float* bn_part = nullptr;
+  float* rowdot = nullptr;
+  BnGroup* bn_table = nullptr;
+  size_t bn_part_floats = 0;
+  std::vector<BnGroup> bn_groups;   // host copy, one entry per 8 channels
   int bucket_step[3] = {-1, -1, -1};  // steps after which buckets 0 (block4 + heads), 1 (block3), 2 (block2) are final
   int early_step = -1;  // number of steps after which the gradients of block4 + heads (the arena's tail) are final
   // The ~280 launches of the network backward have fixed arguments per plan: after the first (eager) step they are
@@ -57,8 +65,7 @@ struct TrainState {
   float* accum = nullptr;
   float* norm_partial = nullptr;
   float* norm_clip = nullptr;  // [0] = global norm of the last step, [1] = clip factor
-  DevBuf bn_partial, wgrad_ws, rowdot_ws, colsum_ws;   // colsum_ws: [ceil(M/32)][C] dbeta partials of a mask fused into a dgrad epilogue
-  //   // rowdot_ws: per-float4 <W, dW_raw> products of one layer (-> dgamma)
+  DevBuf bn_partial, wgrad_ws;
   std::vector<W16*> wd;  // per layer: dgrad operand [Cin][taps*Cout] (nullptr for conv1 / head)
   W16* head_wd = nullptr;
   int head_Kd = 0;
@@ -99,8 +106,6 @@ void train_destroy(dgp_handle* h) {
   cudaFree(ts->norm_clip);
   cudaFree(ts->bn_partial.p);
   cudaFree(ts->wgrad_ws.p);
-  cudaFree(ts->rowdot_ws.p);
-  cudaFree(ts->colsum_ws.p);
   for (W16* p : ts->wd) cudaFree(p);
   cudaFree(ts->head_wd);
   cudaFree(ts->wd_jobs);
@@ -185,8 +190,7 @@ int refresh_dgrad_weights(dgp_handle* h, cudaStream_t s) {
 // dy = g * [act > 0] and the per-channel sums of dy are produced by this GEMM's epilogue (conv_gemm_kernel kMask) when the layer
 // runs the staged epilogue.  Returns through *fused whether that happened (else the caller adds the stand-alone mask pass).
 int add_dgrad(dgp_handle* h, Backward* bw, const ConvLayer& L, W16* wd, const void* dy, int N, int H, int W, void* out,
-              const void* residual, const void* mask_act = nullptr, size_t* colsum_need = nullptr, bool* fused = nullptr) {
-  TrainState* ts = h->train;
+              const void* residual, const void* mask_act = nullptr, long long* site = nullptr) {
   ConvLayer D;
   D.scope = L.scope + "/dgrad";
   D.R = L.R; D.S = L.S; D.Cin = L.Cout; D.Cout = L.Cin; D.stride = 1; D.dil = L.dil; D.relu = false;
@@ -200,92 +204,82 @@ int add_dgrad(dgp_handle* h, Backward* bw, const ConvLayer& L, W16* wd, const vo
                           W, 0, &st, &Ho, &Wo);
   if (rc) return rc;
   const bool fuse = mask_act != nullptr && st.gp.epi_mode == 1 && getenv("DGP_NO_MASK_FUSION") == nullptr;
-  if (fused) *fused = fuse;
+  long long off = -1;
   if (fuse) {
-    const size_t need = (size_t)ceil_div(st.gp.M, 32) * st.gp.N * sizeof(float);
-    if (colsum_need && need > *colsum_need) *colsum_need = need;
+    off = (long long)bw->bn_part_floats;                                   // this site's [ceil(M/32)][N] region
+    bw->bn_part_floats += (size_t)ceil_div(st.gp.M, 32) * st.gp.N;
     st.gp.mask_act = mask_act;
   }
+  if (site) *site = off;
   const ConvGemmParams gp = st.gp;
   const int sms = h->num_sms;
-  bw->steps.push_back({5, 1, [gp, sms, ts, fuse](cudaStream_t s) {
+  bw->steps.push_back({5, 1, [gp, sms, bw, off](cudaStream_t s) {
                          ConvGemmParams g = gp;
-                         if (fuse) g.colsum_part = (float*)ts->colsum_ws.p;
+                         if (off >= 0) g.colsum_part = bw->bn_part + off;
                          return launch_conv_gemm(g, sms, s);
                        }});
   return DGP_OK;
 }
 
-// bn_layer: the conv's frozen BN (gamma gradient from the row dot <W, dW_raw>; needs dbeta of the layer, written by the mask
-// step that precedes every wgrad), or nullptr (heads)
+// bn_layer: the conv's frozen BN -- the reduce also leaves <W[co, 4 kk], dW_raw[co, 4 kk]> in the layer's slice of bw->rowdot
+// (-> dgamma in the final bn_finalize_all pass), or nullptr (heads)
 int add_wgrad_params(dgp_handle* h, Backward* bw, const WgradParams& wp0, const float* rowscale, const float* mask,
-                     float* grad, size_t* ws_need, const ConvLayer* bn_layer = nullptr, size_t* rowdot_need = nullptr) {
+                     float* grad, size_t* ws_need, const ConvLayer* bn_layer = nullptr) {
   TrainState* ts = h->train;
   const size_t need = wgrad_workspace_bytes(wp0);
   if (need > *ws_need) *ws_need = need;
   const int sms = h->num_sms;
-  const float* wmaster = nullptr;
-  const float *mean = nullptr, *var = nullptr, *dbeta = nullptr;
-  float* dgamma = nullptr;
-  const float eps = h->cfg.bn_epsilon;
+  const float* wmaster = bn_layer ? h->master + bn_layer->w_off : nullptr;
+  const size_t rd_off = bn_layer ? bn_layer->w_off / 4 : 0;
   if (bn_layer) {
-    wmaster = h->master + bn_layer->w_off;
-    mean = h->bn_mean + bn_layer->ch_off;
-    var = h->bn_var + bn_layer->ch_off;
-    dgamma = ts->grads + h->n_w + bn_layer->ch_off;
-    dbeta = ts->grads + h->n_w + h->n_ch + bn_layer->ch_off;
-    const size_t rd = (size_t)wp0.Cout * (wp0.Kw / 4) * sizeof(float);
-    if (rowdot_need && rd > *rowdot_need) *rowdot_need = rd;
+    for (int c = 0; c < wp0.Cout; c += 8) {
+      BnGroup& g = bw->bn_groups[(bn_layer->ch_off + c) / 8];
+      g.rd_off = rd_off + (unsigned long long)c * (wp0.Kw / 4);
+      g.K4 = wp0.Kw / 4;
+    }
   }
-  bw->steps.push_back({6, bn_layer ? 3 : 2, [=](cudaStream_t s) {
+  bw->steps.push_back({6, 2, [=](cudaStream_t s) {
                          WgradParams wp = wp0;
                          wp.partials = (float*)ts->wgrad_ws.p;
                          cudaError_t e = launch_wgrad_gemm(wp, sms, s);
                          if (e != cudaSuccess) return e;
-                         float* rowdot = wmaster ? (float*)ts->rowdot_ws.p : nullptr;
-                         e = launch_wgrad_reduce(wp, rowscale, mask, grad, 0, s, wmaster, rowdot);
-                         if (e != cudaSuccess || !wmaster) return e;
-                         return launch_bn_gamma_grad(rowdot, wp.Cout, wp.Kw, mean, var, eps, dbeta, dgamma, s);
+                         return launch_wgrad_reduce(wp, rowscale, mask, grad, 0, s, wmaster, wmaster ? bw->rowdot + rd_off : nullptr);
                        }});
   return DGP_OK;
 }
 
 int add_wgrad(dgp_handle* h, Backward* bw, const ConvLayer& L, const void* x, int N, int H, int W, int pad_mode,
-              const void* dy, size_t* ws_need, size_t* rowdot_need) {
+              const void* dy, size_t* ws_need) {
   WgradParams wp;
   int rc = make_wgrad_params(h, L.scope.c_str(), L.R, L.S, L.Cin, L.Cout, L.stride, L.dil, x, N, H, W, pad_mode, dy, &wp);
   if (rc) return rc;
-  return add_wgrad_params(h, bw, wp, L.scale, nullptr, h->train->grads + L.w_off, ws_need, &L, rowdot_need);
+  return add_wgrad_params(h, bw, wp, L.scale, nullptr, h->train->grads + L.w_off, ws_need, &L);
 }
 
-// dy = g * [act > 0] in place + dbeta of up to two layers (conv3 and the projection shortcut share dy at a junction).
-// fused: the dgrad GEMM that produced g already applied the mask and left [ceil(M/32)][C] partial sums in colsum_ws.
+// dy = g * [act > 0] in place and the dy sums of up to two layers (conv3 and the projection shortcut share dy at a junction).
+// site >= 0: the dgrad GEMM that produced g already applied the mask and writes the [ceil(M/32)][C] sums into that region of
+// bw->bn_part; otherwise a stand-alone relu_bn_bwd pass does both into a region of its own.
 void add_mask(dgp_handle* h, Backward* bw, void* g, const void* act, int M, int C, const ConvLayer* la, const ConvLayer* lb,
-              size_t* bn_need, bool fused = false) {
-  TrainState* ts = h->train;
-  if (fused) {
-    float* dbet0 = ts->grads + h->n_w + h->n_ch;
-    float* dba0 = dbet0 + la->ch_off;
-    float* dbb0 = lb ? dbet0 + lb->ch_off : nullptr;
-    const int rows = ceil_div(M, 32);
-    bw->steps.push_back({7, 1, [=](cudaStream_t s) {
-                           return launch_bn_grad_finalize((const float*)ts->colsum_ws.p, rows, C, dba0, dbb0, s);
-                         }});
-    return;
+              long long site = -1) {
+  int rows;
+  if (site >= 0) {
+    rows = ceil_div(M, 32);
+  } else {
+    rows = relu_bn_bwd_blocks(M, C);
+    site = (long long)bw->bn_part_floats;
+    bw->bn_part_floats += (size_t)rows * C;
+    const int fp16 = h->fp16;
+    const long long off = site;
+    bw->steps.push_back({7, 1, [=](cudaStream_t s) { return launch_relu_bn_bwd(g, act, M, C, bw->bn_part + off, fp16, s); }});
   }
-  const int blocks = relu_bn_bwd_blocks(M, C);
-  const size_t need = (size_t)blocks * C * sizeof(float);
-  if (need > *bn_need) *bn_need = need;
-  const int fp16 = h->fp16;
-  float* dbet = ts->grads + h->n_w + h->n_ch;
-  float* dba = dbet + la->ch_off;
-  float* dbb = lb ? dbet + lb->ch_off : nullptr;
-  bw->steps.push_back({7, 2, [=](cudaStream_t s) {
-                         float* partial = (float*)ts->bn_partial.p;
-                         cudaError_t e = launch_relu_bn_bwd(g, act, M, C, partial, fp16, s);
-                         if (e != cudaSuccess) return e;
-                         return launch_bn_grad_finalize(partial, blocks, C, dba, dbb, s);
-                       }});
+  for (const ConvLayer* L : {la, lb}) {
+    if (!L) continue;
+    for (int c = 0; c < C; c += 8) {
+      BnGroup& grp = bw->bn_groups[(L->ch_off + c) / 8];
+      grp.part_off = (unsigned long long)site;
+      grp.rows = rows; grp.C = C; grp.col = c;
+    }
+  }
 }
 
 int build_backward(dgp_handle* h, Plan* pl) {
@@ -295,8 +289,9 @@ int build_backward(dgp_handle* h, Plan* pl) {
   const int hf = pl->hf, wf = pl->wf;
   int rc;
   void* p = nullptr;
-  size_t ws_need = 0, bn_need = 0, rowdot_need = 0, colsum_need = 0;
-  bool g_masked = false;   // the gradient w.r.t. the current unit's output already carries its junction mask (+ colsum partials)
+  size_t ws_need = 0, bn_need = 0;
+  long long g_site = -1;   // >= 0: the gradient w.r.t. the current unit's output already carries its junction mask; its dy sums live there
+  bw->bn_groups.assign((h->n_ch + 7) / 8, BnGroup());
   // ---- gradient buffers
   size_t max_unit = (size_t)pl->Hp * pl->Wp * 64, max_t1 = 0, max_t2 = 0, max_up = 0;
   for (size_t i = 0; i < h->units.size(); ++i) {
@@ -358,17 +353,18 @@ int build_backward(dgp_handle* h, Plan* pl) {
     rc = make_gemm_step(h, D, dG, B, hf, wf, 0, gbuf[0], false, nullptr, 1, 0, 0, 0, &st, &Ho, &Wo);
     if (rc) return rc;
     // gbuf[0] is the gradient w.r.t. block4's output: the last unit's junction mask rides in this GEMM's epilogue
-    g_masked = st.gp.epi_mode == 1 && getenv("DGP_NO_MASK_FUSION") == nullptr;
-    if (g_masked) {
+    if (st.gp.epi_mode == 1 && getenv("DGP_NO_MASK_FUSION") == nullptr) {
       st.gp.mask_act = pl->feat;
-      colsum_need = std::max(colsum_need, (size_t)ceil_div(st.gp.M, 32) * st.gp.N * sizeof(float));
+      g_site = (long long)bw->bn_part_floats;
+      bw->bn_part_floats += (size_t)ceil_div(st.gp.M, 32) * st.gp.N;
     }
     const ConvGemmParams gp = st.gp;
     const int sms = h->num_sms;
-    const bool fuse = g_masked;
-    bw->steps.push_back({5, 1, [gp, sms, ts, fuse](cudaStream_t s) {
+    const long long off = g_site;
+    Backward* bwp = bw.get();
+    bw->steps.push_back({5, 1, [gp, sms, bwp, off](cudaStream_t s) {
                            ConvGemmParams g = gp;
-                           if (fuse) g.colsum_part = (float*)ts->colsum_ws.p;
+                           if (off >= 0) g.colsum_part = bwp->bn_part + off;
                            return launch_conv_gemm(g, sms, s);
                          }});
   }
@@ -387,35 +383,35 @@ int build_backward(dgp_handle* h, Plan* pl) {
     void* Gy = gbuf[(gi + 2) % 3];
     const int Mo = B * ub.Ho * ub.Wo, Mi = B * ub.H * ub.W;
     // junction
-    add_mask(h, bw.get(), G, ub.out, Mo, u.depth, &L3, Ls, &bn_need, g_masked);
-    // conv3 (its dgrad's epilogue applies conv2's ReLU mask and leaves the dbeta partials)
-    bool fused = false;
-    if ((rc = add_wgrad(h, bw.get(), L3, ub.t2, B, ub.Ho, ub.Wo, 0, G, &ws_need, &rowdot_need))) return rc;
-    if ((rc = add_dgrad(h, bw.get(), L3, ts->wd[u.conv3], G, B, ub.Ho, ub.Wo, gt2, nullptr, ub.t2, &colsum_need, &fused))) return rc;
+    add_mask(h, bw.get(), G, ub.out, Mo, u.depth, &L3, Ls, g_site);
+    // conv3 (its dgrad's epilogue applies conv2's ReLU mask and leaves the dy sums)
+    long long site = -1;
+    if ((rc = add_wgrad(h, bw.get(), L3, ub.t2, B, ub.Ho, ub.Wo, 0, G, &ws_need))) return rc;
+    if ((rc = add_dgrad(h, bw.get(), L3, ts->wd[u.conv3], G, B, ub.Ho, ub.Wo, gt2, nullptr, ub.t2, &site))) return rc;
     // conv2
-    add_mask(h, bw.get(), gt2, ub.t2, Mo, u.base, &L2, nullptr, &bn_need, fused);
-    if ((rc = add_wgrad(h, bw.get(), L2, ub.t1, B, ub.H, ub.W, 1, gt2, &ws_need, &rowdot_need))) return rc;
+    add_mask(h, bw.get(), gt2, ub.t2, Mo, u.base, &L2, nullptr, site);
+    if ((rc = add_wgrad(h, bw.get(), L2, ub.t1, B, ub.H, ub.W, 1, gt2, &ws_need))) return rc;
     if (u.stride == 1) {
-      if ((rc = add_dgrad(h, bw.get(), L2, ts->wd[u.conv2], gt2, B, ub.H, ub.W, gt1, nullptr, ub.t1, &colsum_need, &fused))) return rc;
+      if ((rc = add_dgrad(h, bw.get(), L2, ts->wd[u.conv2], gt2, B, ub.H, ub.W, gt1, nullptr, ub.t1, &site))) return rc;
     } else {
       const int P = ub.Ho, Q = ub.Wo, H = ub.H, W = ub.W, C = u.base;
       bw->steps.push_back({7, 1, [=](cudaStream_t s) { return launch_upsample2(gt2, B, P, Q, C, gup, H, W, s); }});
-      if ((rc = add_dgrad(h, bw.get(), L2, ts->wd[u.conv2], gup, B, ub.H, ub.W, gt1, nullptr, ub.t1, &colsum_need, &fused))) return rc;
+      if ((rc = add_dgrad(h, bw.get(), L2, ts->wd[u.conv2], gup, B, ub.H, ub.W, gt1, nullptr, ub.t1, &site))) return rc;
     }
     // conv1
-    add_mask(h, bw.get(), gt1, ub.t1, Mi, u.base, &L1, nullptr, &bn_need, fused);
-    if ((rc = add_wgrad(h, bw.get(), L1, ub.x, B, ub.H, ub.W, 0, gt1, &ws_need, &rowdot_need))) return rc;
+    add_mask(h, bw.get(), gt1, ub.t1, Mi, u.base, &L1, nullptr, site);
+    if ((rc = add_wgrad(h, bw.get(), L1, ub.x, B, ub.H, ub.W, 0, gt1, &ws_need))) return rc;
     // the GEMM that completes Gx (gradient w.r.t. this unit's input = the previous unit's post-ReLU output) also applies that
     // unit's junction mask -- except for the first unit (its input is the max-pool output) and the stride-2 identity shortcuts
     // (scatter_add2 still adds into Gx afterwards)
     const void* junction_act = i > 0 ? ub.x : nullptr;
-    g_masked = false;
+    g_site = -1;
     if (Ls) {
       if ((rc = add_dgrad(h, bw.get(), L1, ts->wd[u.conv1], gt1, B, ub.H, ub.W, Gy, nullptr))) return rc;
-      if ((rc = add_wgrad(h, bw.get(), *Ls, ub.x, B, ub.H, ub.W, 0, G, &ws_need, &rowdot_need))) return rc;
-      if ((rc = add_dgrad(h, bw.get(), *Ls, ts->wd[u.shortcut], G, B, ub.H, ub.W, Gx, Gy, junction_act, &colsum_need, &g_masked))) return rc;
+      if ((rc = add_wgrad(h, bw.get(), *Ls, ub.x, B, ub.H, ub.W, 0, G, &ws_need))) return rc;
+      if ((rc = add_dgrad(h, bw.get(), *Ls, ts->wd[u.shortcut], G, B, ub.H, ub.W, Gx, Gy, junction_act, &g_site))) return rc;
     } else if (u.stride == 1) {
-      if ((rc = add_dgrad(h, bw.get(), L1, ts->wd[u.conv1], gt1, B, ub.H, ub.W, Gx, G, junction_act, &colsum_need, &g_masked))) return rc;
+      if ((rc = add_dgrad(h, bw.get(), L1, ts->wd[u.conv1], gt1, B, ub.H, ub.W, Gx, G, junction_act, &g_site))) return rc;
     } else {
       if ((rc = add_dgrad(h, bw.get(), L1, ts->wd[u.conv1], gt1, B, ub.H, ub.W, Gx, nullptr))) return rc;
       const int P = ub.Ho, Q = ub.Wo, H = ub.H, W = ub.W, C = u.depth;
@@ -436,7 +432,7 @@ int build_backward(dgp_handle* h, Plan* pl) {
     if ((rc = alloc_buf(h, pl, (size_t)B * Hp * Wp * 64 + 1024, &arg_ws))) return rc;
     bw->steps.push_back({7, 2, [=](cudaStream_t s) { return launch_maxpool_bwd(c1, Gp, B, H1, W1, 64, Hp, Wp, pt, plft, arg_ws, g_c1, fp16, s); }});
     const ConvLayer& L = h->layers[h->conv1_layer];
-    add_mask(h, bw.get(), g_c1, c1, B * H1 * W1, 64, &L, nullptr, &bn_need);
+    add_mask(h, bw.get(), g_c1, c1, B * H1 * W1, 64, &L, nullptr);
     WgradParams wp;
     memset(&wp, 0, sizeof(wp));
     tmap_set_fp16(h->fp16);
@@ -450,14 +446,33 @@ int build_backward(dgp_handle* h, Plan* pl) {
                          (uint64_t)pl->Hs * pl->Ws * 32, 0, 0, 0, -3, 1, (uint64_t)B * pl->Hs * pl->Ws * 32, 64);
     if (e) return fail(h, DGP_ERR_CUDA, "conv1 wgrad (x map): %s", e);
     wgrad_plan(&wp, h->num_sms);
-    if ((rc = add_wgrad_params(h, bw.get(), wp, L.scale, h->conv1_mask, ts->grads + L.w_off, &ws_need, &L, &rowdot_need))) return rc;
+    if ((rc = add_wgrad_params(h, bw.get(), wp, L.scale, h->conv1_mask, ts->grads + L.w_off, &ws_need, &L))) return rc;
   }
-  const void *p0 = ts->wgrad_ws.p, *p1 = ts->bn_partial.p, *p2 = ts->rowdot_ws.p, *p3 = ts->colsum_ws.p;
+  // ---- every channel's dbeta / dgamma in one pass at the end
+  {
+    if ((rc = alloc_buf(h, pl, bw->bn_part_floats * sizeof(float) + 1024, &p))) return rc;
+    bw->bn_part = (float*)p;
+    if ((rc = alloc_buf(h, pl, (h->n_w / 4 + 64) * sizeof(float), &p))) return rc;
+    bw->rowdot = (float*)p;
+    if ((rc = alloc_buf(h, pl, bw->bn_groups.size() * sizeof(BnGroup), &p))) return rc;
+    bw->bn_table = (BnGroup*)p;
+    for (const BnGroup& g : bw->bn_groups)
+      if (g.rows <= 0 || g.K4 <= 0) return fail(h, DGP_ERR_STATE, "backward plan: a BatchNorm channel group has no gradient source");
+    CU_OK(h, cudaMemcpy(bw->bn_table, bw->bn_groups.data(), bw->bn_groups.size() * sizeof(BnGroup), cudaMemcpyHostToDevice));
+    const int ngroups = (int)bw->bn_groups.size();
+    Backward* bwp = bw.get();
+    const float *mean = h->bn_mean, *var = h->bn_var;
+    const float eps = h->cfg.bn_epsilon;
+    float* dgam = ts->grads + h->n_w;
+    float* dbet = ts->grads + h->n_w + h->n_ch;
+    bw->steps.push_back({7, 1, [=](cudaStream_t s) {
+                           return launch_bn_finalize_all(bwp->bn_table, ngroups, bwp->bn_part, bwp->rowdot, mean, var, eps, dgam, dbet, s);
+                         }});
+  }
+  const void *p0 = ts->wgrad_ws.p, *p1 = ts->bn_partial.p;
   if ((rc = ensure(h, &ts->wgrad_ws, ws_need))) return rc;
   if ((rc = ensure(h, &ts->bn_partial, bn_need))) return rc;
-  if ((rc = ensure(h, &ts->rowdot_ws, rowdot_need))) return rc;
-  if ((rc = ensure(h, &ts->colsum_ws, colsum_need))) return rc;
-  if (p0 != ts->wgrad_ws.p || p1 != ts->bn_partial.p || p2 != ts->rowdot_ws.p || p3 != ts->colsum_ws.p) ++ts->ws_gen;
+  if (p0 != ts->wgrad_ws.p || p1 != ts->bn_partial.p) ++ts->ws_gen;
   for (const BStep& st : bw->steps) bw->launches += st.launches;
   pl->bwd = bw;
   return DGP_OK;
