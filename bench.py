@@ -11,7 +11,8 @@ inputs resident in HBM.  `e2e` is the same workload through the public API with 
 video streamed from pinned host memory through eval.estimate_pose_sharded -- H2D of every batch, D2H of the read-outs, and at
 N > 1 the halo exchange, the potentials and the all-gather of the per-frame results inside the timed region.
 Extra objects on the same line: `configs2` (configs[2]: 1280x1024, 16 bodyparts, frame-sharded across the N GPUs, with an
-in-run bit-exactness check of the sharded result against a single-GPU recomputation), `train_step` (configs[3]),
+in-run bit-exactness check of the sharded result against a single-GPU recomputation), `configs4` (configs[4]: 640x480 x 20
+bodyparts, dense skeleton, batch sweep 1..256), `train_step` (configs[3]),
 `aux_bf16` (the same step in the bf16 storage mode), `roofline`, `roofline_aux`, `cpu_baseline`.
 Prints ONE JSON line (rank 0).
 """
@@ -488,6 +489,22 @@ def main():
         wo.close()
         del wo
         torch.cuda.empty_cache()
+    # ---- configs[4]: 640x480 videos x 20 bodyparts with a dense (190-edge) skeleton, throughput sweep over the batch size
+    if not args.no_aux and args.config == "b":
+        sweep = []
+        for bsz in (1, 8, 32, 64, 128, 256):
+            we = Workload("e", local_rank, rank, args.precision, bsz)
+            n_steps = max(4, min(40, 512 // bsz))
+            me = measure_device(we, n_steps, 3, world, local_rank, profile=False)
+            sweep.append({"batch": bsz, "value": me["value"], "ms_per_step": me["ms"] / n_steps})
+            finite_e = bool(torch.isfinite(we.step(0, world)[0]["mu"]).all().item())
+            we.close()
+            del we
+            torch.cuda.empty_cache()
+        if rank == 0:
+            aux["configs4"] = {"workload": CONFIGS["e"][4], "unit": "frames/s", "n_gpus": world, "frame": [480, 640, 3], "num_joints": 20,
+                               "skeleton_edges": 190, "sweep": sweep, "finite": finite_e,
+                               "note": "device-resident inputs, the same step as the headline (forward + soft-argmax + potentials), frames per step per GPU = batch"}
     sa_fill = softargmax_roofline(local_rank, peaks) if (rank == 0 and not args.no_aux) else None
 
     # ---- configs[3] alongside: one data-parallel DGP training step per rank (fwd + bwd + all-reduce + clip/Momentum)

@@ -835,6 +835,7 @@ void dgp_destroy(dgp_handle* h) {
     for (auto& b : kv.second->bufs) cudaFree(b.p);
   for (auto& kv : h->kept) cudaFree(kv.second.p);
   cudaFree(h->sa_ws);
+  cudaFree(h->flow_ws.p);
   cudaFree(h->loss_ws.p);
   cudaFree(h->st_frames2[0].p);
   cudaFree(h->st_frames2[1].p);
@@ -1106,6 +1107,18 @@ int dgp_locref_targets(dgp_handle* h, const double* joint_loc_dev, const int32_t
                                  pos_dist_thresh, locref_stdev > 0 ? locref_stdev : (double)h->cfg.locref_stdev, locref_map_dev, locref_mask_dev,
                                  (cudaStream_t)stream));
   h->launches += n_vis > 0 ? 1 : 0;
+  return DGP_OK;
+}
+
+int dgp_learn_wt(dgp_handle* h, const uint8_t* frames_dev, int T, int H, int W, float* field_dev, void* stream) {
+  if (!h) return DGP_ERR_INVALID;
+  if (T < 0 || H < 1 || W < 1 || (T > 1 && (!frames_dev || !field_dev))) return fail(h, DGP_ERR_INVALID, "dgp_learn_wt: bad argument");
+  if (T < 2) return DGP_OK;
+  CU_OK(h, cudaSetDevice(h->device));
+  if (int rc = ensure(h, &h->flow_ws, learn_wt_workspace_bytes(T, H, W))) return rc;
+  int nl = 0;
+  CU_OK(h, launch_learn_wt(frames_dev, T, H, W, field_dev, h->flow_ws.p, &nl, (cudaStream_t)stream));
+  h->launches += nl;
   return DGP_OK;
 }
 

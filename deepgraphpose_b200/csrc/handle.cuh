@@ -137,6 +137,7 @@ struct dgp_handle {
   std::vector<ProfRec> prof;
   std::vector<cudaEvent_t> ev_pool;
   // softargmax workspace
+  DevBuf flow_ws;   // dgp_learn_wt workspace
   SaPartial* sa_ws = nullptr;
   size_t sa_ws_bytes = 0;
   DevBuf loss_ws;

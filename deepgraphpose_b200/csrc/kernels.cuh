@@ -124,6 +124,10 @@ cudaError_t launch_soft_pose(const float* st, const float* locref, int B, int H,
 // ---- host-feeder replacements (feeder_kernels.cu)
 // coord2map + scatter over the batch: joint_loc (n_vis,nj,2) double scoremap (row,col), NaN = missing; frame_idx (n_vis)
 // position of each visible frame in the batch; lmap / lmask (nt,H,W,2nj) float32 are fully overwritten.
+// learn_wt (fitdgp_util.py:454-467): |u| + |v| of OpenCV's dense Farneback flow (0.5, 3, 15, 3, 5, 1.2, 0) between consecutive
+// BGR2GRAY-converted frames, all T-1 pairs per launch sequence (flow_kernels.cu).  out: float32 (T-1, H, W).
+size_t learn_wt_workspace_bytes(int T, int H, int W);
+cudaError_t launch_learn_wt(const uint8_t* frames, int T, int H, int W, float* out, void* workspace, int* launches, cudaStream_t s);
 // sums[t] = sum over the bytes of (frames[t] - frames[t-1]) & 0xFF (sums[0] = 0): calculate_motion_energy, dataset.py:29-43
 cudaError_t launch_motion_energy(const uint8_t* frames, int T, size_t frame_bytes, unsigned long long* sums, int num_sms,
                                  cudaStream_t s);

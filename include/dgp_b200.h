@@ -135,6 +135,13 @@ int dgp_locref_targets(dgp_handle* h, const double* joint_loc_dev, const int32_t
                        int W, double pos_dist_thresh, double locref_stdev, float* locref_map_dev, float* locref_mask_dev,
                        void* stream);
 
+/* Replaces learn_wt (src/deepgraphpose/models/fitdgp_util.py:454-467), the host feeder of the temporal clique's
+ * `vector_field_tf`: for every consecutive pair of the T frames (uint8 (T,H,W,3) on the device, as fed to the network),
+ * cv2.cvtColor(BGR2GRAY) -> cv2.calcOpticalFlowFarneback(prev, next, None, 0.5, 3, 15, 3, 5, 1.2, 0) -> |u| + |v|.
+ * field_dev: float32 (T-1, H, W).  OpenCV is an un-vendored dependency of the reference; the algorithm is restated from the
+ * published method / OpenCV 4.x semantics and agrees with cv2 4.13 to ~1e-5 px (tests/test_flow.py). */
+int dgp_learn_wt(dgp_handle* h, const uint8_t* frames_dev, int T, int H, int W, float* field_dev, void* stream);
+
 /* Replaces the per-frame arithmetic of calculate_motion_energy (src/deepgraphpose/dataset.py:29-43), the score that ranks
  * hidden frames for training: motion_energy[t] = np.mean(np.abs(frame[t] - frame[t-1])) on uint8 frames, i.e. the mean of the
  * byte differences MODULO 256 (uint8 subtraction wraps, abs is the identity).  frames_dev: uint8 (T, frame_bytes), T consecutive

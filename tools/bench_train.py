@@ -131,7 +131,9 @@ def measure(rank, local_rank, world, steps, warmup, nt, height, width, profile=T
 
     def e2e_step():
         fr = frames_pinned.to(dev, non_blocking=True)
-        b2 = batch if flow_pinned is None else dict(batch, vector_field_tf=flow_pinned.to(dev, non_blocking=True))
+        # wt > 0: the flow-magnitude field of THIS batch, computed on the device from the frames just copied (dgp_learn_wt: the
+        # reference's learn_wt = cv2 Farneback on the host, 175 ms per frame pair)
+        b2 = batch if flow_pinned is None else dict(batch, vector_field_tf=eng.learn_wt(fr))
         out = fitdgp.train_forward_backward(eng, fr, b2, cfg, edges, ws, ws_max, 1000, 100, sync=False)
         scale = dp.allreduce_gradients(eng, overlap=os.environ.get("DGP_DP_OVERLAP", "1") != "0")
         eng.optimizer_step(0.005, 0.9, 10.0, scale)
@@ -183,14 +185,14 @@ def measure(rank, local_rank, world, steps, warmup, nt, height, width, profile=T
                                    % (H, W, nt, len(vis), NJ, wt), "parallelism": ("dp%d, dgp_allreduce_gradients: NCCL SUM all-reduce of the 94 MB fp32 gradient arena inside the C ABI, 4 buckets in backward order "
                                        "(block4+heads, block3, block2, rest) overlapped with the backward pass" % world) if c_comm else
                                       "dp%d, torch.distributed NCCL all-reduce of the 94 MB fp32 gradient buffer" % world,
-                       "feeds": "frames and the (nt-1,H,W) flow-magnitude field resident on the device; labels and marker index vectors fed from the host every step; locref maps built by dgp_locref_targets"},
+                       "feeds": "device-timed value: frames and a (nt-1,H,W) flow-magnitude field resident on the device; e2e: frames from the host, the field from dgp_learn_wt (Farneback on the GPU); labels and marker index vectors fed from the host every step; locref maps built by dgp_locref_targets"},
             "allreduce": {"exposed_ms_last_step": exposed_ms, "path": "C ABI (dgp_allreduce_gradients)" if c_comm else ("torch.distributed" if world > 1 else "none"),
                           "note": "time between the end of the backward pass and the end of the gradient all-reduce on rank 0"},
             "clocks": clocks, "gpu_launches": launches, "loss_after": loss, "finite": bool(np.isfinite(loss)),
             "e2e": {"value": world * nt * e2e_steps / e2e_dt, "unit": "frames/s", "ms_per_step": 1e3 * e2e_dt / e2e_steps,
-                    "h2d_bytes_per_step": int(frames_pinned.numel()) + (int(flow_pinned.numel()) * 4 if flow_pinned is not None else 0)
+                    "h2d_bytes_per_step": int(frames_pinned.numel())
                                           + int(sum(np.asarray(v).nbytes for v in batch.values() if not isinstance(v, (int, list, torch.Tensor)))),
-                    "d2h_bytes_per_step": 24, "timing": "wall clock, frames (and the flow field) copied from pinned host memory and the 6 loss values read back every step, max over ranks"},
+                    "d2h_bytes_per_step": 24, "timing": "wall clock, frames copied from pinned host memory, the Farneback flow-magnitude field of the batch computed on the device (dgp_learn_wt) and the 6 loss values read back every step, max over ranks"},
             "ms_per_step_by_family": fam, "ms_per_step_with_events": ms_prof / args.steps,
             "tflops": {"forward_gemm": tf(flops_fwd, prof["conv_gemm"][0]), "dgrad_gemm": tf(flops_fwd, prof["dgrad_gemm"][0]),
                        "wgrad_gemm": tf(flops_fwd, prof["wgrad_gemm"][0]),
