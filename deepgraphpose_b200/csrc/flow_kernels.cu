@@ -207,41 +207,68 @@ __global__ void update_matrices_kernel(const float* __restrict__ R, const float*
   }
 }
 
-// 15-row box sum of the 5 matrix entries, rows clamped to the image (double, as the library's running sums)
+// 15-row box sum of the 5 matrix entries, rows clamped to the image (double, as the library's running sums).  One thread owns
+// one (x, c) column of a kBoxRows-row band and slides the window down: 2 loads per output instead of 15.
+constexpr int kBoxRows = 32;
 __global__ void box_v_kernel(const float* __restrict__ M, double* __restrict__ V, int np, int H, int W) {
-  const size_t total = (size_t)np * H * W * 5;
   const int m = kWin / 2;
+  const size_t rowlen = (size_t)W * 5;
+  const int bands = (H + kBoxRows - 1) / kBoxRows;
+  const size_t total = (size_t)np * bands * rowlen;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t rowlen = (size_t)W * 5;
-    const int y = (int)((i / rowlen) % H);
-    const size_t base = i - (size_t)y * rowlen;   // (pair, 0, x, c)
+    const size_t col = i % rowlen;
+    const int band = (int)((i / rowlen) % bands);
+    const size_t p = i / (rowlen * bands);
+    const float* src = M + p * (size_t)H * rowlen + col;
+    double* dst = V + p * (size_t)H * rowlen + col;
+    const int y0 = band * kBoxRows, y1 = min(y0 + kBoxRows, H);
     double s = 0.0;
-    for (int k = -m; k <= m; ++k) s += (double)M[base + (size_t)clampi(y + k, 0, H - 1) * rowlen];
-    V[i] = s;
+    for (int k = -m; k <= m; ++k) s += (double)src[(size_t)clampi(y0 + k, 0, H - 1) * rowlen];
+    dst[(size_t)y0 * rowlen] = s;
+    for (int y = y0 + 1; y < y1; ++y) {
+      s += (double)src[(size_t)min(y + m, H - 1) * rowlen] - (double)src[(size_t)max(y - m - 1, 0) * rowlen];
+      dst[(size_t)y * rowlen] = s;
+    }
   }
 }
 
-// 15-column box sum (columns clamped) + the 2x2 solve; `mag` != nullptr on the last iteration of the finest level: |u| + |v|
-__global__ void box_h_solve_kernel(const double* __restrict__ V, float* __restrict__ flow, float* __restrict__ mag, int np, int H,
-                                   int W) {
-  const size_t total = (size_t)np * H * W;
+// 15-column box sum (columns clamped) + the 2x2 solve; `mag` != nullptr on the last iteration of the finest level: |u| + |v|.
+// A block stages a 128-pixel row segment plus its 7-pixel aprons in shared memory.
+constexpr int kBoxSeg = 128;
+__global__ void __launch_bounds__(kBoxSeg) box_h_solve_kernel(const double* __restrict__ V, float* __restrict__ flow,
+                                                              float* __restrict__ mag, int np, int H, int W) {
   const int m = kWin / 2;
+  __shared__ double sh[(kBoxSeg + kWin - 1) * 5];
+  const int segs = (W + kBoxSeg - 1) / kBoxSeg;
+  const size_t nblocks = (size_t)np * H * segs;
   const double scale = 1.0 / (kWin * kWin);
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int x = (int)(i % W);
-    const double* row = V + (i - x) * 5;
-    double s[5] = {0, 0, 0, 0, 0};
-    for (int k = -m; k <= m; ++k) {
-      const double* q = row + 5 * clampi(x + k, 0, W - 1);
-#pragma unroll
-      for (int c = 0; c < 5; ++c) s[c] += q[c];
+  for (size_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+    const int seg = (int)(blk % segs);
+    const size_t rowi = blk / segs;                // (pair, y)
+    const double* row = V + rowi * (size_t)W * 5;
+    const int x0 = seg * kBoxSeg;
+    __syncthreads();
+    for (int t = threadIdx.x; t < (kBoxSeg + kWin - 1) * 5; t += kBoxSeg) {
+      const int px = t / 5, c = t - px * 5;
+      sh[t] = row[(size_t)clampi(x0 - m + px, 0, W - 1) * 5 + c];
     }
-    const double g11 = s[0] * scale, g12 = s[1] * scale, g22 = s[2] * scale, h1 = s[3] * scale, h2 = s[4] * scale;
-    const double idet = 1.0 / (g11 * g22 - g12 * g12 + 1e-3);
-    const float u = (float)((g11 * h2 - g12 * h1) * idet), v = (float)((g22 * h1 - g12 * h2) * idet);
-    flow[2 * i] = u;
-    flow[2 * i + 1] = v;
-    if (mag) mag[i] = fabsf(u) + fabsf(v);
+    __syncthreads();
+    const int x = x0 + threadIdx.x;
+    if (x < W) {
+      double s[5] = {0, 0, 0, 0, 0};
+      for (int k = 0; k < kWin; ++k) {
+        const double* q = sh + (threadIdx.x + k) * 5;
+#pragma unroll
+        for (int c = 0; c < 5; ++c) s[c] += q[c];
+      }
+      const double g11 = s[0] * scale, g12 = s[1] * scale, g22 = s[2] * scale, h1 = s[3] * scale, h2 = s[4] * scale;
+      const double idet = 1.0 / (g11 * g22 - g12 * g12 + 1e-3);
+      const float u = (float)((g11 * h2 - g12 * h1) * idet), v = (float)((g22 * h1 - g12 * h2) * idet);
+      const size_t i = rowi * (size_t)W + x;
+      flow[2 * i] = u;
+      flow[2 * i + 1] = v;
+      if (mag) mag[i] = fabsf(u) + fabsf(v);
+    }
   }
 }
 
@@ -369,8 +396,11 @@ cudaError_t launch_learn_wt(const uint8_t* frames, int T, int H, int W, float* o
     update_matrices_kernel<<<grid_for((size_t)(T - 1) * pl), 256, 0, s>>>(R, flow, M, T - 1, hl, wl);
     ++nl;
     for (int it = 0; it < kIters; ++it) {
-      box_v_kernel<<<grid_for((size_t)(T - 1) * pl * 5), 256, 0, s>>>(M, V, T - 1, hl, wl);
-      box_h_solve_kernel<<<grid_for((size_t)(T - 1) * pl), 256, 0, s>>>(V, flow, (k == 0 && it == kIters - 1) ? out : nullptr, T - 1, hl, wl);
+      box_v_kernel<<<grid_for((size_t)(T - 1) * ((hl + kBoxRows - 1) / kBoxRows) * wl * 5), 256, 0, s>>>(M, V, T - 1, hl, wl);
+      {
+        const size_t nb = (size_t)(T - 1) * hl * ((wl + kBoxSeg - 1) / kBoxSeg);
+        box_h_solve_kernel<<<(unsigned)(nb < 148 * 64 ? nb : 148 * 64), kBoxSeg, 0, s>>>(V, flow, (k == 0 && it == kIters - 1) ? out : nullptr, T - 1, hl, wl);
+      }
       nl += 2;
       if (it < kIters - 1) {
         update_matrices_kernel<<<grid_for((size_t)(T - 1) * pl), 256, 0, s>>>(R, flow, M, T - 1, hl, wl);
