@@ -106,6 +106,7 @@ SIGNATURES = {
     "dgp_get_variable": (_i, [_vp, C.c_char_p, _i, _vp, _sz, _i64p, C.POINTER(_i)]),
     "dgp_set_variable": (_i, [_vp, C.c_char_p, _i, _vp, _sz]),
     "dgp_set_profiling": (_i, [_vp, _i]),
+    "dgp_marker_indices": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "dgp_learn_wt": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "dgp_motion_energy": (_i, [_vp, _vp, _i, C.c_size_t, _vp, _vp]),
     "dgp_get_profile": (_i, [_vp, C.POINTER(C.c_double), _i64p, _i]),

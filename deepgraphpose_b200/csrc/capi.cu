@@ -1110,6 +1110,20 @@ int dgp_locref_targets(dgp_handle* h, const double* joint_loc_dev, const int32_t
   return DGP_OK;
 }
 
+int dgp_marker_indices(dgp_handle* h, const int32_t* visible_frames_dev, int n_vis, const int32_t* hidden_frames_dev, int n_hid,
+                       const double* joint_loc_dev, int nt, int32_t* visible_marker_dev, int32_t* hidden_marker_dev,
+                       int32_t* visible_in_targets_dev, int32_t* counts_dev, void* stream) {
+  if (!h) return DGP_ERR_INVALID;
+  if (n_vis < 0 || n_hid < 0 || nt < 1 || n_vis + n_hid > nt || !visible_marker_dev || !hidden_marker_dev || !visible_in_targets_dev ||
+      !counts_dev || (n_vis > 0 && (!visible_frames_dev || !joint_loc_dev)) || (n_hid > 0 && !hidden_frames_dev))
+    return fail(h, DGP_ERR_INVALID, "dgp_marker_indices: bad argument");
+  CU_OK(h, cudaSetDevice(h->device));
+  CU_OK(h, launch_marker_indices(visible_frames_dev, n_vis, hidden_frames_dev, n_hid, joint_loc_dev, h->cfg.num_joints, nt,
+                                 visible_marker_dev, hidden_marker_dev, visible_in_targets_dev, counts_dev, (cudaStream_t)stream));
+  h->launches++;
+  return DGP_OK;
+}
+
 int dgp_learn_wt(dgp_handle* h, const uint8_t* frames_dev, int T, int H, int W, float* field_dev, void* stream) {
   if (!h) return DGP_ERR_INVALID;
   if (T < 0 || H < 1 || W < 1 || (T > 1 && (!frames_dev || !field_dev))) return fail(h, DGP_ERR_INVALID, "dgp_learn_wt: bad argument");

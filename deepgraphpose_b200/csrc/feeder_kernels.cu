@@ -41,6 +41,66 @@ __global__ void locref_targets_kernel(const double* __restrict__ joint_loc, cons
   }
 }
 
+// gen_idx_chunk / find_marker_index (src/deepgraphpose/dataset.py:157-239): the marker index vectors of a batch.  Marker id =
+// frame_position * nj + joint; a marker of a visible frame whose label is NaN counts as hidden.  One CTA: every thread classifies
+// markers id, id + blockDim, ... in increasing order, an in-block exclusive scan of the per-thread counts gives each thread its
+// output offsets, so the three lists come out sorted (what np.sort / np.setdiff1d / np.nonzero produce) -- integer work, bit-exact.
+// counts[0] = number of visible markers, counts[1] = number of hidden markers.
+__global__ void __launch_bounds__(256) marker_indices_kernel(const int* __restrict__ vis_frames, int n_vis, const int* __restrict__ hid_frames,
+                                                             int n_hid, const double* __restrict__ joint_loc, int nj, int nt,
+                                                             int* __restrict__ visible_marker, int* __restrict__ hidden_marker,
+                                                             int* __restrict__ visible_in_targets, int* __restrict__ counts) {
+  extern __shared__ int sh[];          // [nt] frame -> row of joint_loc (visible), -1 (hidden), -2 (not in the batch); then scan scratch
+  int* kind = sh;
+  int* scan_v = sh + nt;
+  int* scan_h = scan_v + blockDim.x;
+  for (int t = threadIdx.x; t < nt; t += blockDim.x) kind[t] = -2;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_vis; i += blockDim.x) kind[vis_frames[i]] = i;
+  for (int i = threadIdx.x; i < n_hid; i += blockDim.x) kind[hid_frames[i]] = -1;
+  __syncthreads();
+  const int total = nt * nj;
+  // contiguous range of marker ids per thread keeps the outputs sorted after the scan
+  const int per = (total + blockDim.x - 1) / blockDim.x;
+  const int m0 = threadIdx.x * per, m1 = min(m0 + per, total);
+  int cv = 0, ch = 0;
+  for (int m = m0; m < m1; ++m) {
+    const int k = kind[m / nj];
+    if (k == -2) continue;
+    const bool vis = k >= 0 && !isnan(joint_loc[((size_t)k * nj + (m % nj)) * 2]);
+    cv += vis ? 1 : 0;
+    ch += vis ? 0 : 1;
+  }
+  scan_v[threadIdx.x] = cv;
+  scan_h[threadIdx.x] = ch;
+  __syncthreads();
+  if (threadIdx.x == 0) {              // <= 256 entries: a serial exclusive scan is the simplest exact thing
+    int av = 0, ah = 0;
+    for (int i = 0; i < (int)blockDim.x; ++i) {
+      const int tv = scan_v[i], th = scan_h[i];
+      scan_v[i] = av; scan_h[i] = ah;
+      av += tv; ah += th;
+    }
+    counts[0] = av;
+    counts[1] = ah;
+  }
+  __syncthreads();
+  int ov = scan_v[threadIdx.x], oh = scan_h[threadIdx.x];
+  for (int m = m0; m < m1; ++m) {
+    const int t = m / nj, j = m - t * nj;
+    const int k = kind[t];
+    if (k == -2) continue;
+    if (k >= 0 && !isnan(joint_loc[((size_t)k * nj + j) * 2])) {
+      visible_marker[ov] = m;
+      // position in the (n_vis, nj) targets array: rows follow the SORTED visible frame positions = joint_loc's row order
+      visible_in_targets[ov] = k * nj + j;
+      ++ov;
+    } else {
+      hidden_marker[oh++] = m;
+    }
+  }
+}
+
 // calculate_motion_energy (src/deepgraphpose/dataset.py:29-43): mean over the bytes of a frame of |frame - previous|, where
 // the reference subtracts uint8 arrays -- the difference wraps modulo 256 and np.abs is the identity on uint8.  Integer work:
 // the kernel returns the exact sum of (cur - prev) & 0xFF per frame (uint64); the host divides by the byte count in double,
@@ -88,6 +148,16 @@ __global__ void __launch_bounds__(256) motion_energy_kernel(const uint8_t* __res
 }
 
 }  // namespace
+
+cudaError_t launch_marker_indices(const int* vis_frames, int n_vis, const int* hid_frames, int n_hid, const double* joint_loc, int nj,
+                                  int nt, int* visible_marker, int* hidden_marker, int* visible_in_targets, int* counts,
+                                  cudaStream_t s) {
+  const size_t smem = ((size_t)nt + 2 * 256) * sizeof(int);
+  if (smem > 48 * 1024) return cudaErrorInvalidValue;
+  marker_indices_kernel<<<1, 256, smem, s>>>(vis_frames, n_vis, hid_frames, n_hid, joint_loc, nj, nt, visible_marker, hidden_marker,
+                                              visible_in_targets, counts);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_motion_energy(const uint8_t* frames, int T, size_t frame_bytes, unsigned long long* sums, int num_sms,
                                  cudaStream_t s) {

@@ -128,6 +128,11 @@ cudaError_t launch_soft_pose(const float* st, const float* locref, int B, int H,
 // BGR2GRAY-converted frames, all T-1 pairs per launch sequence (flow_kernels.cu).  out: float32 (T-1, H, W).
 size_t learn_wt_workspace_bytes(int T, int H, int W);
 cudaError_t launch_learn_wt(const uint8_t* frames, int T, int H, int W, float* out, void* workspace, int* launches, cudaStream_t s);
+// gen_idx_chunk (dataset.py:187-239): sorted marker index vectors of a batch (visible_marker, hidden_marker,
+// visible_marker_in_targets) + counts[2]; vis_frames sorted ascending (joint_loc rows follow that order), nt <= ~11 k frames
+cudaError_t launch_marker_indices(const int* vis_frames, int n_vis, const int* hid_frames, int n_hid, const double* joint_loc, int nj,
+                                  int nt, int* visible_marker, int* hidden_marker, int* visible_in_targets, int* counts,
+                                  cudaStream_t s);
 // sums[t] = sum over the bytes of (frames[t] - frames[t-1]) & 0xFF (sums[0] = 0): calculate_motion_energy, dataset.py:29-43
 cudaError_t launch_motion_energy(const uint8_t* frames, int T, size_t frame_bytes, unsigned long long* sums, int num_sms,
                                  cudaStream_t s);

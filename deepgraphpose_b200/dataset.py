@@ -22,6 +22,20 @@ def coord2map(pdata, joint_loc, nx_out, ny_out, nj, engine=None):
     return lmap.cpu().numpy().astype(np.float64), lmask.cpu().numpy().astype(np.float64)
 
 
+def gen_idx_chunk(visible_frame_indices, hidden_frame_indices, joint_loc, engine=None):
+    """dataset.py:187-239 with the reference's arguments and return values (three sorted int arrays: visible_marker,
+    hidden_marker, visible_marker_in_targets); computed by the marker-index kernel of ``engine`` (required).  The frame indices are
+    positions within the batch (as ``next_batch`` passes them), ``joint_loc`` the (n_vis, nj, 2) labels of the visible frames in
+    ascending frame order, NaN = unlabelled (such markers count as hidden)."""
+    if engine is None:
+        raise ValueError("gen_idx_chunk needs the Engine whose GPU computes the index vectors (no CPU fallback)")
+    vis = np.asarray(visible_frame_indices, dtype=np.int64).reshape(-1)
+    hid = np.asarray(hidden_frame_indices, dtype=np.int64).reshape(-1)
+    nt = int(max(vis.max(initial=-1), hid.max(initial=-1)) + 1)
+    vm, hm, vit = engine.marker_indices(vis, hid, joint_loc, max(nt, 1))
+    return vm.cpu().numpy().astype("int"), hm.cpu().numpy().astype("int"), vit.cpu().numpy().astype("int")
+
+
 def calculate_motion_energy(video, engine=None, chunk=256):
     """dataset.py:29-43: ``motion_energy[t] = np.mean(np.abs(frame[t] - frame[t-1]))`` with the frames as the decoder delivers
     them (uint8: the difference wraps modulo 256 and ``abs`` is the identity -- reproduced, it is what ranks the hidden

@@ -551,6 +551,24 @@ class Engine:
                                               _ptr(dw), d3, _stream(x.device)))
         return dw
 
+    def marker_indices(self, visible_frames, hidden_frames, joint_loc, nt):
+        """gen_idx_chunk on the device (dgp_marker_indices).  Returns int32 CUDA tensors (visible_marker, hidden_marker,
+        visible_marker_in_targets), already cut to their lengths (one 8-byte read-back of the two counts)."""
+        dev = self.device
+        vf = torch.as_tensor(np.asarray(visible_frames, dtype=np.int32)).to(dev)
+        hf = torch.as_tensor(np.asarray(hidden_frames, dtype=np.int32)).to(dev)
+        jl = torch.as_tensor(np.ascontiguousarray(np.asarray(joint_loc, dtype=np.float64).reshape(-1, self.nj, 2))).to(dev)
+        cap = max(int(nt) * self.nj, 1)
+        vm = torch.empty(cap, dtype=torch.int32, device=dev)
+        hm = torch.empty(cap, dtype=torch.int32, device=dev)
+        vit = torch.empty(cap, dtype=torch.int32, device=dev)
+        cnt = torch.zeros(2, dtype=torch.int32, device=dev)
+        self._check(self.lib.dgp_marker_indices(self.h, _ptr(vf) if vf.numel() else None, vf.numel(), _ptr(hf) if hf.numel() else None,
+                                                hf.numel(), _ptr(jl) if jl.numel() else None, int(nt), _ptr(vm), _ptr(hm), _ptr(vit),
+                                                _ptr(cnt), _stream(dev)))
+        nv, nh = [int(x) for x in cnt.cpu().tolist()]
+        return vm[:nv], hm[:nh], vit[:nv]
+
     def learn_wt(self, frames):
         """Farneback flow magnitude |u| + |v| per consecutive frame pair (dgp_learn_wt): frames uint8 cuda (T,H,W,3) ->
         float32 cuda (T-1,H,W), the `vector_field_tf` feed of the temporal clique."""

@@ -135,6 +135,16 @@ int dgp_locref_targets(dgp_handle* h, const double* joint_loc_dev, const int32_t
                        int W, double pos_dist_thresh, double locref_stdev, float* locref_map_dev, float* locref_mask_dev,
                        void* stream);
 
+/* Replaces gen_idx_chunk / find_marker_index (src/deepgraphpose/dataset.py:157-239), the marker bookkeeping of every training
+ * batch: marker id = frame_position * nj + joint; visible_frames_dev (ascending; joint_loc_dev float64 (n_vis,nj,2) rows in that
+ * order, NaN = unlabelled) and hidden_frames_dev are positions within the nt-frame batch.  Outputs (capacity nt * nj each),
+ * sorted ascending as the reference's np.sort / np.setdiff1d produce them: visible_marker, hidden_marker (hidden frames' markers
+ * + the NaN-labelled markers of visible frames), visible_marker_in_targets (row * nj + joint of each visible marker in the
+ * targets array); counts_dev[0..1] = their lengths.  Integer work, bit-exact. */
+int dgp_marker_indices(dgp_handle* h, const int32_t* visible_frames_dev, int n_vis, const int32_t* hidden_frames_dev, int n_hid,
+                       const double* joint_loc_dev, int nt, int32_t* visible_marker_dev, int32_t* hidden_marker_dev,
+                       int32_t* visible_in_targets_dev, int32_t* counts_dev, void* stream);
+
 /* Replaces learn_wt (src/deepgraphpose/models/fitdgp_util.py:454-467), the host feeder of the temporal clique's
  * `vector_field_tf`: for every consecutive pair of the T frames (uint8 (T,H,W,3) on the device, as fed to the network),
  * cv2.cvtColor(BGR2GRAY) -> cv2.calcOpticalFlowFarneback(prev, next, None, 0.5, 3, 15, 3, 5, 1.2, 0) -> |u| + |v|.

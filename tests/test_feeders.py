@@ -160,3 +160,22 @@ def test_gpu_motion_energy_bit_exact_vs_reference_golden():
     sums = eng.motion_energy_sums(torch.from_numpy(big).cuda()).cpu().numpy()
     assert sums[0] == 0 and sums[1] == int((big[1] - big[0]).astype(np.uint64).sum()) and sums[2] == int((big[2] - big[1]).astype(np.uint64).sum())
     eng.close()
+
+
+@pytest.mark.gpu
+def test_gpu_marker_indices_bit_exact_vs_reference_golden():
+    """dataset.gen_idx_chunk (dgp_marker_indices) == the reference's own gen_idx_chunk on the batches of the golden file
+    (NaN labels in visible frames, no visible frame at all, no hidden frame at all)."""
+    from deepgraphpose_b200 import dataset
+    from deepgraphpose_b200.engine import Engine
+    g = _golden()
+    for tag in ("m0", "m1", "m2", "m3"):
+        nt, H, W, nj, seed = [int(v) for v in g[tag + "_args"]]
+        vis = g[tag + "_vis"]
+        hid = np.array([t for t in range(nt) if t not in set(vis.tolist())], dtype=np.int64)
+        eng = Engine(nj, location_refinement=False)
+        v, h, vit = dataset.gen_idx_chunk(vis, hid, g[tag + "_labels"], engine=eng)
+        assert np.array_equal(v, g[tag + "_visible_marker"]), tag
+        assert np.array_equal(h, g[tag + "_hidden_marker"]), tag
+        assert np.array_equal(vit, g[tag + "_vit"]), tag
+        eng.close()
