@@ -308,7 +308,9 @@ def measure_e2e(wl, frames_per_gpu, world):
     from deepgraphpose_b200.eval import estimate_pose_sharded
     T = world * frames_per_gpu
     run = lambda n: estimate_pose_sharded(wl.eng, wl.pool_host, n, wl.H, wl.W, wl.edges, wl.ws_vec, wl.ws_max, 0.0, batch=wl.B)
-    run(world * 2 * wl.B)     # warm-up: plans, pinned ring, NCCL
+    run(world * 2 * wl.B)     # warm-up: plans, pinned ring, NCCL communicator
+    if world > 1:
+        run(T)                # ... and NCCL's first all_gather at the full result size (70 ms once, tools/e2e_phases.py)
     torch.cuda.synchronize()
     barrier(world)
     t0 = time.perf_counter()

@@ -1207,9 +1207,12 @@ int dgp_estimate_pose_host(dgp_handle* h, const uint8_t* frames_host, int T, int
                              cudaMemcpyHostToDevice, cs));
     CU_OK(h, cudaEventRecord(h->ev_copied[slot], cs));
     CU_OK(h, cudaStreamWaitEvent(s, h->ev_copied[slot], 0));
-    if ((rc = dgp_forward(h, (const uint8_t*)h->st_frames2[slot].p, b, H, W, (float*)h->st_logits.p, nullptr, s))) return rc;
+    // the tail batch of a multi-batch video reuses the full-batch plan (see dgp_estimate_pose_stream): surplus rows hold an
+    // earlier batch's frames and their read-outs are not copied back
+    const int run_b = (b < batch && it > 0 && getenv("DGP_STREAM_NO_PAD") == nullptr) ? batch : b;
+    if ((rc = dgp_forward(h, (const uint8_t*)h->st_frames2[slot].p, run_b, H, W, (float*)h->st_logits.p, nullptr, s))) return rc;
     CU_OK(h, cudaEventRecord(h->ev_consumed[slot], s));
-    if ((rc = dgp_softargmax(h, (const float*)h->st_logits.p, nullptr, b, ho, wo, nj, gamma, gauss_len,
+    if ((rc = dgp_softargmax(h, (const float*)h->st_logits.p, nullptr, run_b, ho, wo, nj, gamma, gauss_len,
                              (float*)h->st_mu.p, (int32_t*)h->st_peak.p, (float*)h->st_lik.p, nullptr, nullptr, s)))
       return rc;
     CU_OK(h, cudaMemcpyAsync(mu_host + (size_t)t0 * nj * 2, h->st_mu.p, (size_t)b * nj * 2 * 4, cudaMemcpyDeviceToHost, s));

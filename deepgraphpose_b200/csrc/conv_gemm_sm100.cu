@@ -112,12 +112,14 @@ __device__ __forceinline__ void epi_unit_math(const uint32_t (&v)[2][16], uint8_
     uint32_t o[8];
 #pragma unroll
     for (int i = 0; i < 8; i += 2) {
-      const float4 sc = *reinterpret_cast<const float4*>(scp + 2 * i);
-      const float4 sh = *reinterpret_cast<const float4*>(shp + 2 * i);
-      ptx::f32x2 q0 = ptx::fma2(ptx::pk2(__uint_as_float(v[s2][2 * i]), __uint_as_float(v[s2][2 * i + 1])),
-                                ptx::pk2(sc.x, sc.y), ptx::pk2(sh.x, sh.y));
-      ptx::f32x2 q1 = ptx::fma2(ptx::pk2(__uint_as_float(v[s2][2 * i + 2]), __uint_as_float(v[s2][2 * i + 3])),
-                                ptx::pk2(sc.z, sc.w), ptx::pk2(sh.z, sh.w));
+      ptx::f32x2 q0 = ptx::pk2(__uint_as_float(v[s2][2 * i]), __uint_as_float(v[s2][2 * i + 1]));
+      ptx::f32x2 q1 = ptx::pk2(__uint_as_float(v[s2][2 * i + 2]), __uint_as_float(v[s2][2 * i + 3]));
+      if (!kMask) {   // the backward GEMMs (kMask) carry no BatchNorm: the scale is folded into their weights
+        const float4 sc = *reinterpret_cast<const float4*>(scp + 2 * i);
+        const float4 sh = *reinterpret_cast<const float4*>(shp + 2 * i);
+        q0 = ptx::fma2(q0, ptx::pk2(sc.x, sc.y), ptx::pk2(sh.x, sh.y));
+        q1 = ptx::fma2(q1, ptx::pk2(sc.z, sc.w), ptx::pk2(sh.z, sh.w));
+      }
       if (kRes) {
         if (kFp16) {
           const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&rr[i]));
@@ -1078,7 +1080,8 @@ cudaError_t launch_conv_gemm(const ConvGemmParams& p, int num_sms, cudaStream_t 
     }
     attr_set = true;
   }
-  if (p.mask_act != nullptr && (p.epi_mode != 1 || p.colsum_part == nullptr)) return cudaErrorInvalidValue;
+  if (p.mask_act != nullptr && (p.epi_mode != 1 || p.colsum_part == nullptr || p.scale != nullptr || p.shift != nullptr))
+    return cudaErrorInvalidValue;
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   int grid = tiles < num_sms ? tiles : num_sms;
   if (p.cta2) {   // one tile per CTA pair

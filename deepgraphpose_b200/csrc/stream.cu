@@ -6,6 +6,7 @@
 #include "../../include/dgp_b200.h"
 
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include <condition_variable>
 #include <deque>
@@ -149,6 +150,8 @@ int dgp_estimate_pose_stream(dgp_handle* h, dgp_frame_reader reader, void* user,
   // ---- consumer: H2D (copy stream) -> forward + soft-argmax (compute stream) -> D2H of the read-outs
   int64_t t0 = 0;
   int it = 0;
+  bool full_batch_seen = false;
+  const bool no_pad = getenv("DGP_STREAM_NO_PAD") != nullptr;   // A/B switch for the short-batch rule below
   int status = DGP_OK;
   cudaError_t ce = cudaSuccess;
   for (;;) {
@@ -168,9 +171,15 @@ int dgp_estimate_pose_stream(dgp_handle* h, dgp_frame_reader reader, void* user,
     if (ce == cudaSuccess) ce = cudaEventRecord(h->ev_copied[dslot], cs);
     if (ce == cudaSuccess) ce = cudaStreamWaitEvent(s, h->ev_copied[dslot], 0);
     if (ce != cudaSuccess) break;
-    if ((status = dgp_forward(h, (const uint8_t*)h->st_frames2[dslot].p, f.n, H, W, (float*)h->st_logits.p, nullptr, s))) break;
+    // A short batch (the tail of the video, or the wrap of a cyclic source) reuses the full-batch plan once one exists:
+    // every frame's arithmetic is independent of its batch, the surplus rows of the device slot hold an earlier batch's
+    // frames, and only the first f.n read-outs are copied back.  Building a second plan for it would cost far more than the
+    // surplus frames (allocation of every activation, tensor maps, first-use kernel loads).
+    const int run_n = (f.n < batch && full_batch_seen && !no_pad) ? batch : f.n;
+    if (f.n == batch) full_batch_seen = true;
+    if ((status = dgp_forward(h, (const uint8_t*)h->st_frames2[dslot].p, run_n, H, W, (float*)h->st_logits.p, nullptr, s))) break;
     if ((ce = cudaEventRecord(h->ev_consumed[dslot], s)) != cudaSuccess) break;
-    if ((status = dgp_softargmax(h, (const float*)h->st_logits.p, nullptr, f.n, ho, wo, nj, gamma, gauss_len, (float*)h->st_mu.p,
+    if ((status = dgp_softargmax(h, (const float*)h->st_logits.p, nullptr, run_n, ho, wo, nj, gamma, gauss_len, (float*)h->st_mu.p,
                                  (int32_t*)h->st_peak.p, (float*)h->st_lik.p, nullptr, nullptr, s)))
       break;
     ce = cudaMemcpyAsync(mu_host + (size_t)t0 * nj * 2, h->st_mu.p, (size_t)f.n * nj * 2 * 4, cudaMemcpyDeviceToHost, s);

@@ -127,7 +127,7 @@ def estimate_pose_stream(engine, source, H, W, n_frames=None, batch=16, gamma=1.
 
 
 def estimate_pose_sharded(engine, source, T, H, W, edges=(), ws=None, ws_max=None, wt_max=0.0, batch=16, gamma=1.0,
-                          gauss_len=1.0, group=None, gather=True):
+                          gauss_len=1.0, group=None, gather=True, timings=None):
     """estimate_pose over a T-frame video sharded contiguously by frame over the ranks of ``group`` (one process
     per GPU): rank r streams frames [a_r, b_r) (``sharding.shard_range``) through its own engine, the ranks exchange the
     soft-argmax of their first frame (one all_gather of nj*8 bytes per rank) so that the temporal potential at every shard
@@ -138,7 +138,9 @@ def estimate_pose_sharded(engine, source, T, H, W, edges=(), ws=None, ws_max=Non
     ``source``: a pinned uint8 tensor (P,H,W,3) cycled as the video (frame t = source[t % P]), or a callable
     ``(start, stop) -> iterator of frames`` that opens the rank's own range of a real video.
     Returns the estimate_pose dict plus 'skel' (T,nl), 'temporal' (T,nj; last row 0), 'e_skel', 'e_temp' (T) -- for the
-    whole video on every rank when ``gather`` (else for the rank's shard) -- and 'shard' = (a_r, b_r)."""
+    whole video on every rank when ``gather`` (else for the rank's shard) -- and 'shard' = (a_r, b_r).
+    ``timings``: an optional dict that receives the wall-clock seconds of the phases ('stream', 'potentials', 'gather')."""
+    import time
     import torch.distributed as dist
     from . import sharding
     on = dist.is_available() and dist.is_initialized()
@@ -147,6 +149,7 @@ def estimate_pose_sharded(engine, source, T, H, W, edges=(), ws=None, ws_max=Non
     if T < world:
         raise ValueError("a %d-frame video cannot be sharded over %d ranks" % (T, world))
     a, b = sharding.shard_range(T, rank, world)
+    t_start = time.perf_counter()
     if isinstance(source, torch.Tensor):
         mu, peak, lik = engine.estimate_pose_stream(source, H, W, b - a, batch, gamma, gauss_len, start=a)
     else:
@@ -154,6 +157,7 @@ def estimate_pose_sharded(engine, source, T, H, W, edges=(), ws=None, ws_max=Non
     if mu.shape[0] != b - a:
         raise RuntimeError("rank %d: the source delivered %d of its %d frames" % (rank, mu.shape[0], b - a))
     dev = engine.device
+    t_stream = time.perf_counter()
     mu_d = mu.to(dev, non_blocking=True)
     halo = sharding.exchange_halo(mu_d[0].contiguous(), group) if world > 1 else None
     edges = [tuple(e) for e in edges]
@@ -165,12 +169,17 @@ def estimate_pose_sharded(engine, source, T, H, W, edges=(), ws=None, ws_max=Non
              "temporal": temporal, "skel": pot["skel"].t().contiguous(), "e_temp": pot["e_temp"]}
     if pot["e_skel"] is not None:
         local["e_skel"] = pot["e_skel"]
+    if timings is not None:
+        torch.cuda.synchronize(dev)
+    t_pot = time.perf_counter()
     full = {k: (sharding.gather_frames(v, T, group) if gather else v) for k, v in local.items()}
     out = _readout_dict(full["mu"].cpu(), full["peak"].cpu(), full["lik"].cpu(), engine.stride)
     for k in ("temporal", "skel", "e_temp", "e_skel"):
         if k in full:
             out[k] = full[k].cpu().numpy()
     out["shard"] = (a, b)
+    if timings is not None:
+        timings.update(stream=t_stream - t_start, potentials=t_pot - t_stream, gather=time.perf_counter() - t_pot)
     return out
 
 
