@@ -25,8 +25,11 @@ __device__ __forceinline__ uint4 pack8v(const float* f, int fp16) { return h16::
 // dy = g * [act > 0] in place + per-channel partial sums of dy (-> dbeta).  The same kernel serves plain ReLU layers and the
 // bottleneck junctions out = relu(shortcut + bn3(conv3)): dgamma no longer needs the BN output (see bn_gamma_grad_kernel in
 // wgrad_gemm_sm100.cu), so neither the shortcut tensor nor a division by gamma is involved.
+// d != nullptr: g first receives the gradient of resnet_utils.subsample (the identity shortcut of the stride-2 unit behind this
+// junction): g[n,2p,2q] += d[n,p,q] with g (N,H,W,C), d (N,P,Q,C) -- one pass instead of a scatter-add pass plus this one.
 __global__ void __launch_bounds__(256) relu_bn_bwd_kernel(uint4* __restrict__ g, const uint4* __restrict__ act, int M, int C8,
-                                                          float* __restrict__ partial, int fp16) {
+                                                          float* __restrict__ partial, int fp16, const uint4* __restrict__ d,
+                                                          int H, int W, int P, int Q) {
   const int my_cg = threadIdx.x % C8;
   const int my_r = threadIdx.x / C8;
   const int rpb = 256 / C8;
@@ -38,13 +41,22 @@ __global__ void __launch_bounds__(256) relu_bn_bwd_kernel(uint4* __restrict__ g,
     float gv[8], av[8];
     unpack8(g[idx], gv, fp16);
     unpack8(__ldg(act + idx), av, fp16);
-    float d[8];
+    if (d != nullptr) {
+      const int xx = r % W, y = (r / W) % H, n = r / (W * H);
+      if (!(xx & 1) && !(y & 1) && (y >> 1) < P && (xx >> 1) < Q) {
+        float dv[8];
+        unpack8(__ldg(d + (((size_t)n * P + (y >> 1)) * Q + (xx >> 1)) * C8 + my_cg), dv, fp16);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gv[j] += dv[j];
+      }
+    }
+    float dyv[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      d[j] = av[j] > 0.0f ? gv[j] : 0.0f;
-      S[j] += d[j];
+      dyv[j] = av[j] > 0.0f ? gv[j] : 0.0f;
+      S[j] += dyv[j];
     }
-    g[idx] = pack8v(d, fp16);
+    g[idx] = pack8v(dyv, fp16);
   }
   __shared__ float sm[256][9];
 #pragma unroll
@@ -197,6 +209,126 @@ __global__ void maxpool_bwd_kernel(const uint2* __restrict__ arg, const uint4* _
   }
 }
 
+// Root of the backward pass in ONE pass: gradient of slim.max_pool2d(3x3, stride 2, SAME) routed to the first maximum of each
+// window, conv1's ReLU mask, and the per-channel sums of the masked gradient (-> dbeta of conv1's BN).  64 channels.
+// A CTA owns an 8 x 32 tile of conv1-output pixels: it stages the (<= 11 x 35)-pixel neighbourhood of x = relu(bn(conv1)) in
+// shared memory, finds the argmax of the (<= 5 x 17) windows that touch the tile there (stage A; their pooled gradients are
+// fetched alongside), and every pixel then gathers from its <= 2 x 2 windows (stage B).  x is read ~1.5 x (halo, L2 hits), the
+// pooled gradient once, dy written once: ~0.5 GB per 10 frames of 747 x 832 instead of the 1.5 GB of argmax + gather + mask
+// passes over HBM-resident tensors.
+constexpr int kPoolTileH = 8, kPoolTileW = 32, kPoolRows = 11, kPoolCols = 35, kPoolP = 5, kPoolQ = 17;
+constexpr int kPoolBwdSmem = (kPoolRows * kPoolCols * 8 + kPoolP * kPoolQ * 8) * 16 + kPoolP * kPoolQ * 8 * 8;
+
+__global__ void __launch_bounds__(256) maxpool_relu_bwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ gout, int H,
+                                                               int W, int Ho, int Wo, int pad_t, int pad_l, uint4* __restrict__ gx,
+                                                               float* __restrict__ partial, int fp16) {
+  extern __shared__ uint4 pool_sm[];
+  uint4* xs = pool_sm;                                   // [rows][cols][8]
+  uint4* gs = pool_sm + kPoolRows * kPoolCols * 8;       // [nP][nQ][8] pooled gradients
+  uint2* as = reinterpret_cast<uint2*>(gs + kPoolP * kPoolQ * 8);   // [nP][nQ][8] argmax positions, one byte per channel
+  const int n = blockIdx.z, y0 = blockIdx.y * kPoolTileH, x0 = blockIdx.x * kPoolTileW;
+  const int y1 = min(y0 + kPoolTileH, H) - 1, x1 = min(x0 + kPoolTileW, W) - 1;
+  const int p_lo = max(0, (y0 + pad_t - 1) >> 1), p_hi = min(Ho - 1, (y1 + pad_t) >> 1);
+  const int q_lo = max(0, (x0 + pad_l - 1) >> 1), q_hi = min(Wo - 1, (x1 + pad_l) >> 1);
+  const int nP = p_hi - p_lo + 1, nQ = q_hi - q_lo + 1;
+  const int ys0 = min(2 * p_lo - pad_t, y0), xs0 = min(2 * q_lo - pad_l, x0);
+  const int rows = max(2 * p_hi - pad_t + 2, y1) - ys0 + 1, cols = max(2 * q_hi - pad_l + 2, x1) - xs0 + 1;
+  const int tid = threadIdx.x;
+  for (int it = tid; it < rows * cols * 8; it += 256) {
+    const int cg = it & 7, col = (it >> 3) % cols, row = (it >> 3) / cols;
+    const int y = ys0 + row, xx = xs0 + col;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (y >= 0 && y < H && xx >= 0 && xx < W) v = __ldg(x + (((size_t)n * H + y) * W + xx) * 8 + cg);
+    xs[it] = v;
+  }
+  __syncthreads();
+  // ---- stage A: first maximum of every window (row-major over its valid positions, strict >)
+  for (int it = tid; it < nP * nQ * 8; it += 256) {
+    const int cg = it & 7, wq = (it >> 3) % nQ, wp = (it >> 3) / nQ;
+    const int p = p_lo + wp, q = q_lo + wq;
+    float best[8];
+    uint32_t idx[8];
+    bool have = false;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int y = 2 * p - pad_t + dy;
+      if (y < 0 || y >= H) continue;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int xx = 2 * q - pad_l + dx;
+        if (xx < 0 || xx >= W) continue;
+        float v[8];
+        unpack8(xs[((y - ys0) * cols + (xx - xs0)) * 8 + cg], v, fp16);
+        if (!have) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { best[j] = v[j]; idx[j] = dy * 3 + dx; }
+          have = true;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (v[j] > best[j]) { best[j] = v[j]; idx[j] = dy * 3 + dx; }
+        }
+      }
+    }
+    uint2 o;
+    o.x = idx[0] | (idx[1] << 8) | (idx[2] << 16) | (idx[3] << 24);
+    o.y = idx[4] | (idx[5] << 8) | (idx[6] << 16) | (idx[7] << 24);
+    as[it] = o;
+    gs[it] = __ldg(gout + (((size_t)n * Ho + p) * Wo + q) * 8 + cg);
+  }
+  __syncthreads();
+  // ---- stage B: every pixel of the tile gathers from the windows that contain it, masks, stores, sums
+  float S[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) S[j] = 0.0f;
+  const int cg = tid & 7;
+#pragma unroll 2
+  for (int it = tid; it < kPoolTileH * kPoolTileW * 8; it += 256) {
+    const int col = (it >> 3) % kPoolTileW, row = (it >> 3) / kPoolTileW;
+    const int y = y0 + row, xx = x0 + col;
+    if (y >= H || xx >= W) continue;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+    const int pa = max(0, (y + pad_t - 1) >> 1), pb = min(Ho - 1, (y + pad_t) >> 1);
+    const int qa = max(0, (xx + pad_l - 1) >> 1), qb = min(Wo - 1, (xx + pad_l) >> 1);
+    for (int p = pa; p <= pb; ++p)
+      for (int q = qa; q <= qb; ++q) {
+        const uint32_t mine = (uint32_t)((y - (2 * p - pad_t)) * 3 + (xx - (2 * q - pad_l)));
+        const int w = ((p - p_lo) * nQ + (q - q_lo)) * 8 + cg;
+        const uint2 a = as[w];
+        float gv[8];
+        unpack8(gs[w], gv, fp16);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (((a.x >> (8 * j)) & 0xffu) == mine) acc[j] += gv[j];
+          if (((a.y >> (8 * j)) & 0xffu) == mine) acc[4 + j] += gv[4 + j];
+        }
+      }
+    float xv[8];
+    unpack8(xs[((y - ys0) * cols + (xx - xs0)) * 8 + cg], xv, fp16);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = xv[j] > 0.0f ? acc[j] : 0.0f;
+    const uint4 o = pack8v(acc, fp16);
+    gx[(((size_t)n * H + y) * W + xx) * 8 + cg] = o;
+    unpack8(o, acc, fp16);   // the sums are those of dy as stored (what the wgrad GEMM consumes)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) S[j] += acc[j];
+  }
+  __syncthreads();   // xs is dead: reuse it for the fixed-order column reduction
+  float* red = reinterpret_cast<float*>(pool_sm);   // [256][9]
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[tid * 9 + j] = S[j];
+  __syncthreads();
+  if (tid < 64) {
+    const int c8 = tid >> 3, j = tid & 7;
+    float acc = 0.0f;
+    for (int r = 0; r < 32; ++r) acc += red[(r * 8 + c8) * 9 + j];
+    const size_t blk = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    partial[blk * 64 + tid] = acc;
+  }
+}
+
 // out (N,H,W,C) = zero-inserted in (N,P,Q,C): out[n,2p,2q] = in[n,p,q]
 __global__ void upsample2_kernel(const uint4* __restrict__ in, int N, int P, int Q, int C8, uint4* __restrict__ out, int H,
                                  int W) {
@@ -310,10 +442,13 @@ int relu_bn_bwd_blocks(int M, int C) {
   return blocks < 1 ? 1 : blocks;
 }
 
-cudaError_t launch_relu_bn_bwd(void* g, const void* act, int M, int C, float* partial, int fp16, cudaStream_t s) {
+cudaError_t launch_relu_bn_bwd(void* g, const void* act, int M, int C, float* partial, int fp16, cudaStream_t s,
+                               const void* scatter_d, int H, int W, int P, int Q) {
   if (C % 8 || 256 % (C / 8) || C / 8 > 256) return cudaErrorInvalidValue;
+  if (scatter_d != nullptr && (H < 1 || W < 1 || M % (H * W))) return cudaErrorInvalidValue;
   const int blocks = relu_bn_bwd_blocks(M, C);
-  relu_bn_bwd_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<uint4*>(g), reinterpret_cast<const uint4*>(act), M, C / 8, partial, fp16);
+  relu_bn_bwd_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<uint4*>(g), reinterpret_cast<const uint4*>(act), M, C / 8, partial, fp16,
+                                            reinterpret_cast<const uint4*>(scatter_d), H, W, P, Q);
   return cudaGetLastError();
 }
 
@@ -337,6 +472,21 @@ cudaError_t launch_maxpool_bwd(const void* x, const void* gout, int N, int H, in
   maxpool_bwd_kernel<<<flat_grid(total, 256), 256, 0, s>>>(reinterpret_cast<const uint2*>(arg_ws),
                                                            reinterpret_cast<const uint4*>(gout), N, H, W, C / 8, Ho, Wo,
                                                            pad_t, pad_l, reinterpret_cast<uint4*>(gx), fp16);
+  return cudaGetLastError();
+}
+
+int maxpool_relu_bwd_rows(int N, int H, int W) {
+  return N * ((H + kPoolTileH - 1) / kPoolTileH) * ((W + kPoolTileW - 1) / kPoolTileW);
+}
+
+cudaError_t launch_maxpool_relu_bwd(const void* x, const void* gout, int N, int H, int W, int C, int Ho, int Wo, int pad_t,
+                                    int pad_l, void* gx, float* partial, int fp16, cudaStream_t s) {
+  if (C != 64 || pad_t < 0 || pad_t > 1 || pad_l < 0 || pad_l > 1 || N > 65535) return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(maxpool_relu_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPoolBwdSmem);
+  if (e != cudaSuccess) return e;
+  dim3 grid((W + kPoolTileW - 1) / kPoolTileW, (H + kPoolTileH - 1) / kPoolTileH, N);
+  maxpool_relu_bwd_kernel<<<grid, 256, kPoolBwdSmem, s>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(gout),
+                                                          H, W, Ho, Wo, pad_t, pad_l, reinterpret_cast<uint4*>(gx), partial, fp16);
   return cudaGetLastError();
 }
 

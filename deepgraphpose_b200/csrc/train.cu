@@ -34,6 +34,12 @@ struct BStep {
   int kind;      // profiling family: 5 = dgrad GEMM, 6 = wgrad GEMM (+ reduce), 7 = bandwidth-class backward kernel
   int launches;
   std::function<cudaError_t(cudaStream_t)> run;
+  // Hazard notes for the two-branch capture (see dgp_train_forward_backward): a wgrad step (kind 6) only READS the gradient
+  // buffer `rd` (plus forward activations, which the backward never writes) and may run on the side branch until a main-branch
+  // step WRITES that buffer (`wr`); `join` = the step consumes what the wgrads produced (rowdot -> dgamma).
+  const void* wr = nullptr;
+  const void* rd = nullptr;
+  bool join = false;
 };
 
 struct Backward {
@@ -93,6 +99,9 @@ struct TrainState {
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t ev_bwd_done = nullptr, ev_comm_done = nullptr;   // timing enabled: exposed all-reduce time
   bool bwd_ran = false;           // a backward has recorded the bucket events on some stream
+  // second branch of the captured backward: the wgrad chain (see dgp_train_forward_backward)
+  cudaStream_t side_stream = nullptr;
+  std::vector<cudaEvent_t> branch_events;
 };
 
 void comm_release(dgp_handle* h);
@@ -115,6 +124,8 @@ void train_destroy(dgp_handle* h) {
   if (ts->ev_comm_done) cudaEventDestroy(ts->ev_comm_done);
   comm_release(h);
   if (ts->comm_stream) cudaStreamDestroy(ts->comm_stream);
+  if (ts->side_stream) cudaStreamDestroy(ts->side_stream);
+  for (cudaEvent_t e : ts->branch_events) cudaEventDestroy(e);
   delete ts;
   h->train = nullptr;
 }
@@ -218,13 +229,14 @@ int add_dgrad(dgp_handle* h, Backward* bw, const ConvLayer& L, W16* wd, const vo
                          if (off >= 0) g.colsum_part = bw->bn_part + off;
                          return launch_conv_gemm(g, sms, s);
                        }});
+  bw->steps.back().wr = out;
   return DGP_OK;
 }
 
 // bn_layer: the conv's frozen BN -- the reduce also leaves <W[co, 4 kk], dW_raw[co, 4 kk]> in the layer's slice of bw->rowdot
 // (-> dgamma in the final bn_finalize_all pass), or nullptr (heads)
-int add_wgrad_params(dgp_handle* h, Backward* bw, const WgradParams& wp0, const float* rowscale, const float* mask,
-                     float* grad, size_t* ws_need, const ConvLayer* bn_layer = nullptr) {
+int add_wgrad_params(dgp_handle* h, Backward* bw, const WgradParams& wp0, const void* dy_buf, const float* rowscale,
+                     const float* mask, float* grad, size_t* ws_need, const ConvLayer* bn_layer = nullptr) {
   TrainState* ts = h->train;
   const size_t need = wgrad_workspace_bytes(wp0);
   if (need > *ws_need) *ws_need = need;
@@ -245,6 +257,7 @@ int add_wgrad_params(dgp_handle* h, Backward* bw, const WgradParams& wp0, const 
                          if (e != cudaSuccess) return e;
                          return launch_wgrad_reduce(wp, rowscale, mask, grad, 0, s, wmaster, wmaster ? bw->rowdot + rd_off : nullptr);
                        }});
+  bw->steps.back().rd = dy_buf;
   return DGP_OK;
 }
 
@@ -253,24 +266,32 @@ int add_wgrad(dgp_handle* h, Backward* bw, const ConvLayer& L, const void* x, in
   WgradParams wp;
   int rc = make_wgrad_params(h, L.scope.c_str(), L.R, L.S, L.Cin, L.Cout, L.stride, L.dil, x, N, H, W, pad_mode, dy, &wp);
   if (rc) return rc;
-  return add_wgrad_params(h, bw, wp, L.scale, nullptr, h->train->grads + L.w_off, ws_need, &L);
+  return add_wgrad_params(h, bw, wp, dy, L.scale, nullptr, h->train->grads + L.w_off, ws_need, &L);
 }
 
 // dy = g * [act > 0] in place and the dy sums of up to two layers (conv3 and the projection shortcut share dy at a junction).
 // site >= 0: the dgrad GEMM that produced g already applied the mask and writes the [ceil(M/32)][C] sums into that region of
 // bw->bn_part; otherwise a stand-alone relu_bn_bwd pass does both into a region of its own.
+struct ScatterSrc {   // pending gradient of a stride-2 identity shortcut, folded into the next stand-alone junction mask
+  const void* d = nullptr;
+  int H = 0, W = 0, P = 0, Q = 0;
+};
+
 void add_mask(dgp_handle* h, Backward* bw, void* g, const void* act, int M, int C, const ConvLayer* la, const ConvLayer* lb,
-              long long site = -1) {
+              long long site = -1, int site_rows = 0, ScatterSrc sc = ScatterSrc()) {
   int rows;
   if (site >= 0) {
-    rows = ceil_div(M, 32);
+    rows = site_rows > 0 ? site_rows : ceil_div(M, 32);
   } else {
     rows = relu_bn_bwd_blocks(M, C);
     site = (long long)bw->bn_part_floats;
     bw->bn_part_floats += (size_t)rows * C;
     const int fp16 = h->fp16;
     const long long off = site;
-    bw->steps.push_back({7, 1, [=](cudaStream_t s) { return launch_relu_bn_bwd(g, act, M, C, bw->bn_part + off, fp16, s); }});
+    bw->steps.push_back({7, 1, [=](cudaStream_t s) {
+                           return launch_relu_bn_bwd(g, act, M, C, bw->bn_part + off, fp16, s, sc.d, sc.H, sc.W, sc.P, sc.Q);
+                         }});
+    bw->steps.back().wr = g;
   }
   for (const ConvLayer* L : {la, lb}) {
     if (!L) continue;
@@ -325,6 +346,7 @@ int build_backward(dgp_handle* h, Plan* pl) {
 
   // ---- heads: col2im gather, bias gradient, wgrad, dgrad
   bw->steps.push_back({7, 1, [=](cudaStream_t s) { return launch_col2im_bwd(g_logits, g_locref, B, hf, wf, ctot, nj, dG, Kd, fp16, s); }});
+  bw->steps.back().wr = dG;
   {
     float* dbias = ts->grads + h->n_w + 2 * h->n_ch;
     const size_t npix = (size_t)B * 4 * hf * wf;
@@ -344,7 +366,7 @@ int build_backward(dgp_handle* h, Plan* pl) {
     if (rc) return rc;
     wp.Cout = Lh.Npad;
     wgrad_plan(&wp, h->num_sms);
-    if ((rc = add_wgrad_params(h, bw.get(), wp, nullptr, nullptr, ts->grads + Lh.w_off, &ws_need))) return rc;
+    if ((rc = add_wgrad_params(h, bw.get(), wp, dG, nullptr, nullptr, ts->grads + Lh.w_off, &ws_need))) return rc;
     ConvLayer D;
     D.scope = "pose/heads/dgrad"; D.R = 1; D.S = 1; D.Cin = Kd; D.Cout = 2048; D.relu = false;
     D.K = Kd; D.Npad = 2048; D.block_n = 256; D.w = ts->head_wd;
@@ -367,10 +389,12 @@ int build_backward(dgp_handle* h, Plan* pl) {
                            if (off >= 0) g.colsum_part = bwp->bn_part + off;
                            return launch_conv_gemm(g, sms, s);
                          }});
+    bw->steps.back().wr = gbuf[0];
   }
 
   // ---- bottleneck units, last to first.  G = gradient w.r.t. the unit output (then d in place).
   int gi = 0;  // index of G in gbuf
+  ScatterSrc scatter;
   for (int i = (int)h->units.size() - 1; i >= 0; --i) {
     const UnitDesc& u = h->units[i];
     const Plan::UnitBufs& ub = pl->ub[i];
@@ -383,7 +407,8 @@ int build_backward(dgp_handle* h, Plan* pl) {
     void* Gy = gbuf[(gi + 2) % 3];
     const int Mo = B * ub.Ho * ub.Wo, Mi = B * ub.H * ub.W;
     // junction
-    add_mask(h, bw.get(), G, ub.out, Mo, u.depth, &L3, Ls, g_site);
+    add_mask(h, bw.get(), G, ub.out, Mo, u.depth, &L3, Ls, g_site, 0, g_site < 0 ? scatter : ScatterSrc());
+    scatter = ScatterSrc();
     // conv3 (its dgrad's epilogue applies conv2's ReLU mask and leaves the dy sums)
     long long site = -1;
     if ((rc = add_wgrad(h, bw.get(), L3, ub.t2, B, ub.Ho, ub.Wo, 0, G, &ws_need))) return rc;
@@ -396,6 +421,7 @@ int build_backward(dgp_handle* h, Plan* pl) {
     } else {
       const int P = ub.Ho, Q = ub.Wo, H = ub.H, W = ub.W, C = u.base;
       bw->steps.push_back({7, 1, [=](cudaStream_t s) { return launch_upsample2(gt2, B, P, Q, C, gup, H, W, s); }});
+      bw->steps.back().wr = gup;
       if ((rc = add_dgrad(h, bw.get(), L2, ts->wd[u.conv2], gup, B, ub.H, ub.W, gt1, nullptr, ub.t1, &site))) return rc;
     }
     // conv1
@@ -415,7 +441,14 @@ int build_backward(dgp_handle* h, Plan* pl) {
     } else {
       if ((rc = add_dgrad(h, bw.get(), L1, ts->wd[u.conv1], gt1, B, ub.H, ub.W, Gx, nullptr))) return rc;
       const int P = ub.Ho, Q = ub.Wo, H = ub.H, W = ub.W, C = u.depth;
-      bw->steps.push_back({7, 1, [=](cudaStream_t s) { return launch_scatter_add2(G, B, P, Q, C, Gx, H, W, fp16, s); }});
+      if (i > 0 && getenv("DGP_NO_SCATTER_FUSION") == nullptr) {
+        // Gx[n,2p,2q] += G[n,p,q] rides in the previous unit's junction mask (the next step of this plan; G stays intact until
+        // then: it is that unit's third buffer, written only after its mask)
+        scatter.d = G; scatter.H = H; scatter.W = W; scatter.P = P; scatter.Q = Q;
+      } else {
+        bw->steps.push_back({7, 1, [=](cudaStream_t s) { return launch_scatter_add2(G, B, P, Q, C, Gx, H, W, fp16, s); }});
+        bw->steps.back().wr = Gx;
+      }
     }
     gi = (gi + 1) % 3;
     if (ts->early_cnt > 0 && u.shortcut >= 0 && h->layers[u.shortcut].w_off == ts->early_off) bw->early_step = (int)bw->steps.size();
@@ -428,11 +461,25 @@ int build_backward(dgp_handle* h, Plan* pl) {
     void* Gp = gbuf[gi];
     const void* c1 = pl->c1;
     const int H1 = pl->H1, W1 = pl->W1, Hp = pl->Hp, Wp = pl->Wp, pt = pl->pool_pad_t, plft = pl->pool_pad_l;
-    void* arg_ws = nullptr;
-    if ((rc = alloc_buf(h, pl, (size_t)B * Hp * Wp * 64 + 1024, &arg_ws))) return rc;
-    bw->steps.push_back({7, 2, [=](cudaStream_t s) { return launch_maxpool_bwd(c1, Gp, B, H1, W1, 64, Hp, Wp, pt, plft, arg_ws, g_c1, fp16, s); }});
     const ConvLayer& L = h->layers[h->conv1_layer];
-    add_mask(h, bw.get(), g_c1, c1, B * H1 * W1, 64, &L, nullptr);
+    if (getenv("DGP_NO_POOL_BWD_FUSION") == nullptr) {
+      // max-pool gradient + conv1's ReLU mask + dy sums in one pass (bwd_kernels.cu: maxpool_relu_bwd_kernel)
+      const long long site = (long long)bw->bn_part_floats;
+      const int rows = maxpool_relu_bwd_rows(B, H1, W1);
+      bw->bn_part_floats += (size_t)rows * 64;
+      Backward* bwp = bw.get();
+      bw->steps.push_back({7, 1, [=](cudaStream_t s) {
+                             return launch_maxpool_relu_bwd(c1, Gp, B, H1, W1, 64, Hp, Wp, pt, plft, g_c1, bwp->bn_part + site, fp16, s);
+                           }});
+      bw->steps.back().wr = g_c1;
+      add_mask(h, bw.get(), g_c1, c1, B * H1 * W1, 64, &L, nullptr, site, rows);
+    } else {
+      void* arg_ws = nullptr;
+      if ((rc = alloc_buf(h, pl, (size_t)B * Hp * Wp * 64 + 1024, &arg_ws))) return rc;
+      bw->steps.push_back({7, 2, [=](cudaStream_t s) { return launch_maxpool_bwd(c1, Gp, B, H1, W1, 64, Hp, Wp, pt, plft, arg_ws, g_c1, fp16, s); }});
+      bw->steps.back().wr = g_c1;
+      add_mask(h, bw.get(), g_c1, c1, B * H1 * W1, 64, &L, nullptr);
+    }
     WgradParams wp;
     memset(&wp, 0, sizeof(wp));
     tmap_set_fp16(h->fp16);
@@ -446,7 +493,7 @@ int build_backward(dgp_handle* h, Plan* pl) {
                          (uint64_t)pl->Hs * pl->Ws * 32, 0, 0, 0, -3, 1, (uint64_t)B * pl->Hs * pl->Ws * 32, 64);
     if (e) return fail(h, DGP_ERR_CUDA, "conv1 wgrad (x map): %s", e);
     wgrad_plan(&wp, h->num_sms);
-    if ((rc = add_wgrad_params(h, bw.get(), wp, L.scale, h->conv1_mask, ts->grads + L.w_off, &ws_need, &L))) return rc;
+    if ((rc = add_wgrad_params(h, bw.get(), wp, g_c1, L.scale, h->conv1_mask, ts->grads + L.w_off, &ws_need, &L))) return rc;
   }
   // ---- every channel's dbeta / dgamma in one pass at the end
   {
@@ -468,6 +515,7 @@ int build_backward(dgp_handle* h, Plan* pl) {
     bw->steps.push_back({7, 1, [=](cudaStream_t s) {
                            return launch_bn_finalize_all(bwp->bn_table, ngroups, bwp->bn_part, bwp->rowdot, mean, var, eps, dgam, dbet, s);
                          }});
+    bw->steps.back().join = true;
   }
   const void *p0 = ts->wgrad_ws.p, *p1 = ts->bn_partial.p;
   if ((rc = ensure(h, &ts->wgrad_ws, ws_need))) return rc;
@@ -605,12 +653,56 @@ int dgp_train_forward_backward(dgp_handle* h, const uint8_t* frames_dev, int nt,
     if (bw->graph_exec) { cudaGraphExecDestroy(bw->graph_exec); bw->graph_exec = nullptr; }
     cudaGraph_t graph = nullptr;
     CU_OK(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    // Two branches: the wgrad GEMMs only read a gradient buffer that the dgrad chain has finished writing, and nothing
+    // downstream of them is needed before the end of the pass (or the bucket boundaries of the data-parallel all-reduce), so
+    // they are captured on a side stream forked from the main branch.  A wgrad of blocks 2-3 is a short kernel (a few k-blocks
+    // per CTA after the split over pixel ranges, then a latency-bound reduce): as a parallel branch its launch latency, ramp and
+    // tail hide under the dgrad GEMMs instead of being serialised between them.  Joins: before a main-branch step that
+    // overwrites the buffer a pending wgrad reads, before every bucket event, before the final gamma/beta pass.
     cudaError_t ce = cudaSuccess;
+    const bool two = getenv("DGP_BWD_ONE_STREAM") == nullptr;
+    if (two && !ts->side_stream) ce = cudaStreamCreateWithFlags(&ts->side_stream, cudaStreamNonBlocking);
+    size_t ev_next = 0;
+    auto next_event = [&](cudaEvent_t* out) -> cudaError_t {
+      if (ev_next == ts->branch_events.size()) {
+        cudaEvent_t e = nullptr;
+        cudaError_t r = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        if (r != cudaSuccess) return r;
+        ts->branch_events.push_back(e);
+      }
+      *out = ts->branch_events[ev_next++];
+      return cudaSuccess;
+    };
+    struct Pending { const void* rd; cudaEvent_t done; };
+    std::vector<Pending> pending;   // in side-stream order: waiting for entry i covers entries 0..i
+    auto join_through = [&](size_t i) -> cudaError_t {
+      cudaError_t r = cudaStreamWaitEvent(h->stream, pending[i].done, 0);
+      pending.erase(pending.begin(), pending.begin() + i + 1);
+      return r;
+    };
     int k = 0;
     for (const BStep& st : bw->steps) {
-      ce = st.run(h->stream);
       if (ce != cudaSuccess) break;
+      if (two && st.kind == 6 && st.rd != nullptr) {
+        cudaEvent_t fork = nullptr, done = nullptr;
+        if ((ce = next_event(&fork)) != cudaSuccess || (ce = next_event(&done)) != cudaSuccess) break;
+        if ((ce = cudaEventRecord(fork, h->stream)) != cudaSuccess) break;
+        if ((ce = cudaStreamWaitEvent(ts->side_stream, fork, 0)) != cudaSuccess) break;
+        if ((ce = st.run(ts->side_stream)) != cudaSuccess) break;
+        if ((ce = cudaEventRecord(done, ts->side_stream)) != cudaSuccess) break;
+        pending.push_back({st.rd, done});
+      } else {
+        if (st.join && !pending.empty()) ce = join_through(pending.size() - 1);
+        if (ce == cudaSuccess && st.wr != nullptr)
+          for (size_t i = pending.size(); i-- > 0;)
+            if (pending[i].rd == st.wr) { ce = join_through(i); break; }
+        if (ce == cudaSuccess) ce = st.run(h->stream);
+        if (ce != cudaSuccess) break;
+      }
       ++k;
+      bool boundary = k == bw->early_step;
+      for (int b = 0; b < 3; ++b) boundary = boundary || k == bw->bucket_step[b];
+      if (boundary && !pending.empty() && (ce = join_through(pending.size() - 1)) != cudaSuccess) break;
       if (k == bw->early_step) {
         ce = cudaEventRecordWithFlags(ts->ev_early, h->stream, cudaEventRecordExternal);
         if (ce != cudaSuccess) break;
@@ -618,6 +710,10 @@ int dgp_train_forward_backward(dgp_handle* h, const uint8_t* frames_dev, int nt,
       for (int b = 0; b < 3 && ce == cudaSuccess; ++b)
         if (k == bw->bucket_step[b]) ce = cudaEventRecordWithFlags(ts->ev_bucket[b], h->stream, cudaEventRecordExternal);
       if (ce != cudaSuccess) break;
+    }
+    if (!pending.empty()) {
+      cudaError_t je = join_through(pending.size() - 1);   // every forked branch rejoins before the capture ends
+      if (ce == cudaSuccess) ce = je;
     }
     cudaError_t ee = cudaStreamEndCapture(h->stream, &graph);
     if (ce == cudaSuccess) ce = ee;
