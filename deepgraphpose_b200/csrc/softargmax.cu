@@ -113,14 +113,18 @@ __device__ __forceinline__ float dec_ordered(int b) { return __int_as_float(b >=
 // Lane l reads float4s l, l + tw, ...; `tw` <= 32 lanes are active with 4*tw % nj == 0, so a lane's four float4 slots
 // keep a fixed joint.  kSamePixel: nj % 4 == 0, the four slots belong to ONE pixel.  kShfl: the lanes that share a
 // joint are an xor-closed set (nj in {4, 8, ..., 128}) and reduce with shuffles; otherwise through a per-warp scratch.
-constexpr int kWWarps = 12;
+// Round 2: 16 warps / 27 stages (was 12 / 22).  ncu showed the kernel issue-bound at 3 warps per scheduler (62 % issue
+// utilisation, 18 % occupancy), not HBM-bound: a fourth warp per scheduler needs <= 128 registers per thread and the shared
+// memory that the per-warp reduction scratch used to take -- the scratch now lives in the stage the warp has just drained
+// (it is refilled right after the reduction instead of right before it).
+constexpr int kWWarps = 16;
 constexpr int kWThreads = kWWarps * 32;
 constexpr int kWChunkFloats = 2048;  // 8 KB
-constexpr int kWStages = 22;
+constexpr int kWStages = 27;
 constexpr int kMaxJoints = 128;
-constexpr int kWScratchFloats = 128 * 5 + kMaxJoints;   // per warp: [4*32][5] partial entries + [nj] results
-constexpr size_t kWSmemBytes = (size_t)kWStages * kWChunkFloats * 4 + (size_t)kWWarps * kWScratchFloats * 4 + 64 * 4 +
-                               kWStages * 8 + kWStages * 4 + 128;
+constexpr int kWScratchFloats = 128 * 5 + kMaxJoints;   // [4*32][5] partial entries + [nj] results, inside the drained stage
+static_assert(kWScratchFloats <= kWChunkFloats, "the reduction scratch must fit into one stage");
+constexpr size_t kWSmemBytes = (size_t)kWStages * kWChunkFloats * 4 + 64 * 4 + kWStages * 8 + kWStages * 4 + 128;
 
 // blur border weights computed from scratch (degenerate maps no larger than the kernel, where every pixel is border)
 __device__ __noinline__ void border_weights_slow(int pos, int n, int radius, float sigma, float& a, float& r) {
@@ -205,8 +209,7 @@ __global__ void __launch_bounds__(kWThreads, 1) softargmax_stream_kernel(
     int cpf, int tw, SaPartial* __restrict__ part) {
   extern __shared__ __align__(128) unsigned char st_smem[];
   float* stage = reinterpret_cast<float*>(st_smem);
-  float* scratch = stage + kWStages * kWChunkFloats;    // [kWWarps][kWScratchFloats]
-  float* btab = scratch + kWWarps * kWScratchFloats;    // border weights: [4][16] (Ah, Rh, Aw, Rw) x 2*radius entries
+  float* btab = stage + kWStages * kWChunkFloats;       // border weights: [4][16] (Ah, Rh, Aw, Rw) x 2*radius entries
   uint64_t* full = reinterpret_cast<uint64_t*>(btab + 64);
   volatile int* issued = reinterpret_cast<volatile int*>(full + kWStages);   // loads issued into each stage so far
 
@@ -220,25 +223,6 @@ __global__ void __launch_bounds__(kWThreads, 1) softargmax_stream_kernel(
       issued[s] = 0;
     }
     fence_mbar_init();
-  }
-  // border weight tables: entry i < radius is position i, entry i >= radius is position n - 2*radius + i
-  if (tid < 2 * R2 && !all_border) {
-    float knorm = 0.0f;
-    for (int d = -radius; d <= radius; ++d) knorm += expf(-0.5f * (d / sigma) * (d / sigma));
-    const int axis = tid / R2, i = tid - axis * R2;
-    const int n = axis == 0 ? H : W;
-    const int pos = i < radius ? i : n - R2 + i;
-    float a = 0.0f, r = 0.0f;
-    for (int d = -radius; d <= radius; ++d) {
-      const int dst = pos - d;
-      if (dst >= 0 && dst < n) {
-        const float k = expf(-0.5f * (d / sigma) * (d / sigma)) / knorm;
-        a += k;
-        r += k * (float)dst;
-      }
-    }
-    btab[(2 * axis) * 16 + i] = a;
-    btab[(2 * axis + 1) * 16 + i] = r;
   }
   __syncthreads();
 
@@ -263,6 +247,28 @@ __global__ void __launch_bounds__(kWThreads, 1) softargmax_stream_kernel(
   if (lane == 0)
     for (int i = warp; i < min(nloc, kWStages); i += kWWarps) issue_load_at(i, (g0 + i) / cpf, (g0 + i) % cpf);
 
+  // border weight tables: entry i < radius is position i, entry i >= radius is position n - 2*radius + i
+  if (tid < 2 * R2 && !all_border) {
+    float knorm = 0.0f;
+    for (int d = -radius; d <= radius; ++d) knorm += expf(-0.5f * (d / sigma) * (d / sigma));
+    const int axis = tid / R2, i = tid - axis * R2;
+    const int n = axis == 0 ? H : W;
+    const int pos = i < radius ? i : n - R2 + i;
+    float a = 0.0f, r = 0.0f;
+    for (int d = -radius; d <= radius; ++d) {
+      const int dst = pos - d;
+      if (dst >= 0 && dst < n) {
+        const float k = expf(-0.5f * (d / sigma) * (d / sigma)) / knorm;
+        a += k;
+        r += k * (float)dst;
+      }
+    }
+    btab[(2 * axis) * 16 + i] = a;
+    btab[(2 * axis + 1) * 16 + i] = r;
+  }
+  __syncthreads();   // (the first loads are already in flight: the table set-up hides under their latency)
+
+
   // -------------------------------------------------------------------- math warps
   constexpr bool kShfl = kP > 0;
   const float g2 = gamma * 1.4426950408889634f;
@@ -273,13 +279,23 @@ __global__ void __launch_bounds__(kWThreads, 1) softargmax_stream_kernel(
   int jq[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) jq[q] = (4 * lane + q) % nj;
+  // nj % 4 != 0 only: byte qp of peer[q] = the lane class (= its first lane) whose slot qp holds joint jq[q], 0xff if none
+  unsigned peer[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+  if constexpr (!kSamePixel) {
+    for (int q = 0; q < 4; ++q)
+      for (int qp = 0; qp < 4; ++qp)
+        for (int c = 0; c < P; ++c)
+          if ((4 * c + qp) % nj == jq[q]) {
+            peer[q] = (peer[q] & ~(0xffu << (8 * qp))) | ((unsigned)c << (8 * qp));
+            break;
+          }
+  }
   const int dP = 4 * tw / nj;                    // pixels between a lane's consecutive float4s
   const float dPr = (float)(dP / W), dPc = (float)(dP - (dP / W) * W);
   const float Wf = (float)W, invW = 1.0f / (float)W;
   const float Rf = (float)radius, HmR = (float)(H - radius), WmR = (float)(W - radius);
   constexpr int kPos = kSamePixel ? 1 : 4;       // (row, col) trackers per lane
   const f32x2 g2g2 = pk2(g2, g2), dpos = pk2(dPr, dPc), wrapfix = pk2(1.0f, -Wf);
-  float* scr = scratch + warp * kWScratchFloats;
 
   // (Ah*Aw - 1, Rh*Aw - r, Ah*Rw - c) of a border pixel: what its blur weights differ from the interior (1, r, c) by
   auto border_corr = [&](float pr, float pc, float& k0, float& kr, float& kc) {
@@ -357,21 +373,29 @@ __global__ void __launch_bounds__(kWThreads, 1) softargmax_stream_kernel(
 #pragma unroll
           for (int q = 0; q < 4; ++q) xm[q] = dec_ordered(__reduce_max_sync(cls_mask, enc_ordered(xm[q])));
         } else {
-          __syncwarp();
-          if (act) {
+          // lanes l, l + P, l + 2P, ... (< tw) hold the same four joints: rotate through them (the stage is still live, so
+          // no shared-memory scratch here)
+          float own[4] = {xm[0], xm[1], xm[2], xm[3]};
+          for (int k = P; k < tw; k += P) {
+            int src = lane + k;
+            if (src >= tw) src -= tw;
+            if (!act) src = lane;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) scr[4 * lane + q] = xm[q];
+            for (int q = 0; q < 4; ++q) xm[q] = fmaxf(xm[q], __shfl_sync(0xffffffffu, own[q], src));
           }
-          __syncwarp();
-          for (int j = lane; j < nj; j += 32) {
-            float mj = -CUDART_INF_F;
-            for (int e = j; e < 4 * tw; e += nj) mj = fmaxf(mj, scr[e]);
-            scr[640 + j] = mj;
-          }
-          __syncwarp();
+          if constexpr (!kSamePixel) {
+            // nj % 4 != 0: a joint also sits in OTHER slots of other lane classes; fetch those classes' maxima
+            const float cls[4] = {xm[0], xm[1], xm[2], xm[3]};
 #pragma unroll
-          for (int q = 0; q < 4; ++q) xm[q] = scr[640 + jq[q]];
-          __syncwarp();
+            for (int q = 0; q < 4; ++q) {
+#pragma unroll
+              for (int qp = 0; qp < 4; ++qp) {
+                const int src = (int)((peer[q] >> (8 * qp)) & 0xffu);
+                const float o = __shfl_sync(0xffffffffu, cls[qp], src == 0xff ? lane : src);
+                if (src != 0xff) xm[q] = fmaxf(xm[q], o);
+              }
+            }
+          }
         }
       }
 #pragma unroll
@@ -402,11 +426,13 @@ __global__ void __launch_bounds__(kWThreads, 1) softargmax_stream_kernel(
           const f32x2 zero2 = pk2(0.0f, 0.0f);
           // sums over joint PAIRS: (s0_0, s0_1), (s0_2, s0_3), likewise the row- and column-weighted ones
           f32x2 s0a = zero2, s0b = zero2, sra = zero2, srb = zero2, sca = zero2, scb = zero2;
-          f32x2 rr = pk2(prow[0], prow[0]), cc2 = pk2(pcol[0], pcol[0]);   // (row, row), (col, col) of the float4
-          const f32x2 drr = pk2(dPr, dPr), dcc = pk2(dPc, dPc), wrapc = pk2(-Wf, -Wf), one2 = pk2(1.0f, 1.0f);
+          // (row, col) of the lane's current float4 as SCALARS: the packed FMAs take them as broadcast operands, and the
+          // wrap at the end of a map row is a select instead of predicated 64-bit register-pair updates
+          float pr = prow[0], pc = pcol[0];
           float tm0 = -CUDART_INF_F, tm1 = -CUDART_INF_F;
           auto consume = [&](const float4& v) {
-            float t0, t1, t2, t3, pr, pc, dummy;
+            float t0, t1, t2, t3;
+            const f32x2 rr = pk2(pr, pr), cc2 = pk2(pc, pc);
             upk2(fma2(pk2(v.x, v.y), g2g2, nm01), t0, t1);
             upk2(fma2(pk2(v.z, v.w), g2g2, nm23), t2, t3);
             if (!kDlc) { tm0 = fmaxf(tm0, fmaxf(t0, t1)); tm1 = fmaxf(tm1, fmaxf(t2, t3)); }
@@ -419,8 +445,6 @@ __global__ void __launch_bounds__(kWThreads, 1) softargmax_stream_kernel(
             scb = fma2(eb, cc2, scb);
             if (kDlc) {
               if ((v.x >= thr[0]) | (v.y >= thr[1]) | (v.z >= thr[2]) | (v.w >= thr[3])) {
-                upk2(rr, pr, dummy);
-                upk2(cc2, pc, dummy);
                 const int idx = (int)pr * W + (int)pc;
                 const float xs[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -432,10 +456,11 @@ __global__ void __launch_bounds__(kWThreads, 1) softargmax_stream_kernel(
                 }
               }
             }
-            rr = add2(rr, drr);
-            cc2 = add2(cc2, dcc);
-            upk2(cc2, pc, dummy);
-            if (pc >= Wf) { cc2 = add2(cc2, wrapc); rr = add2(rr, one2); }
+            pr += dPr;
+            pc += dPc;
+            const float wrap = pc >= Wf ? 1.0f : 0.0f;   // dPc < W: at most one wrap; all values are small exact integers
+            pc = fmaf(wrap, -Wf, pc);
+            pr += wrap;
           };
           int f = lane;
           for (; f + 3 * tw < n4; f += 4 * tw) {
@@ -547,14 +572,18 @@ __global__ void __launch_bounds__(kWThreads, 1) softargmax_stream_kernel(
         if (tall >= -90.0f && tall <= 90.0f) break;
       }
     }
-    // the stage is free as soon as every lane has read its float4s: refill it
+    // the stage is free as soon as every lane has read its float4s: refill it (the scratch path first borrows it for its
+    // reduction, see below)
     __syncwarp();
-    if (lane == 0 && i + kWStages < nloc) {
-      fence_proxy_async_smem();   // order the warp's generic-proxy reads before the async-proxy write
-      int nb = b, nc = c + kWStages;
-      while (nc >= cpf) { nc -= cpf; ++nb; }
-      issue_load_at(i + kWStages, nb, nc);
-    }
+    auto refill = [&]() {
+      if (lane == 0 && i + kWStages < nloc) {
+        fence_proxy_async_smem();   // order the warp's generic-proxy accesses before the async-proxy write
+        int nb = b, nc = c + kWStages;
+        while (nc >= cpf) { nc -= cpf; ++nb; }
+        issue_load_at(i + kWStages, nb, nc);
+      }
+    };
+    if constexpr (kShfl) refill();
 
     // ---- reduce over the lanes that share a joint; one partial per (chunk, joint), fixed order -> deterministic
     SaPartial* out = part + ((size_t)b * cpf + c) * nj;
@@ -593,6 +622,7 @@ __global__ void __launch_bounds__(kWThreads, 1) softargmax_stream_kernel(
         }
       }
     } else {
+      float* scr = stage + s * kWChunkFloats;   // the drained stage
       if (act) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -616,6 +646,7 @@ __global__ void __launch_bounds__(kWThreads, 1) softargmax_stream_kernel(
         o4[1] = make_float4(bs, __int_as_float(bi), 0.0f, 0.0f);
       }
       __syncwarp();
+      refill();
     }
   }
 }
