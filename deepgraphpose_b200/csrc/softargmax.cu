@@ -105,8 +105,8 @@ __device__ __forceinline__ float dec_ordered(int b) { return __int_as_float(b >=
 // of (H, W, nj) only, so a frame's arithmetic never depends on the batch size or the grid: bit-exact batch invariance);
 // the CTA's contiguous chunk range goes through a 22-stage shared-memory ring filled by 1-D bulk async copies
 // (cp.async.bulk + mbarrier complete_tx): every byte crosses HBM -> SM exactly once and ~80 KB per SM are in flight no
-// matter what the math is doing.  Each of the 12 warps owns every 12th chunk and is fully autonomous -- no CTA-wide
-// barrier, no producer warp (the warp that drains a stage refills it):
+// matter what the math is doing.  Every warp takes the next chunk of the CTA's range from a shared counter and is otherwise
+// autonomous -- no CTA-wide barrier, no producer warp (the warp that drains a stage refills it):
 //   wait full[s] -> pass 1 (per-joint max, from shared memory) -> pass 2 (packed fp32x2: FFMA2 + EX2 + FADD2 + FFMA2 per
 //   element pair, log2 domain; blur border correction for pixels within `radius` of an edge; DLC peak candidates)
 //   -> release the stage -> warp-level reduction over the lanes that share a joint -> one partial per (chunk, joint).
@@ -124,7 +124,7 @@ constexpr int kWStages = 27;
 constexpr int kMaxJoints = 128;
 constexpr int kWScratchFloats = 128 * 5 + kMaxJoints;   // [4*32][5] partial entries + [nj] results, inside the drained stage
 static_assert(kWScratchFloats <= kWChunkFloats, "the reduction scratch must fit into one stage");
-constexpr size_t kWSmemBytes = (size_t)kWStages * kWChunkFloats * 4 + 64 * 4 + kWStages * 8 + kWStages * 4 + 128;
+constexpr size_t kWSmemBytes = (size_t)kWStages * kWChunkFloats * 4 + 64 * 4 + kWStages * 8 + kWStages * 4 + 4 + 128;
 
 // blur border weights computed from scratch (degenerate maps no larger than the kernel, where every pixel is border)
 __device__ __noinline__ void border_weights_slow(int pos, int n, int radius, float sigma, float& a, float& r) {
@@ -212,6 +212,7 @@ __global__ void __launch_bounds__(kWThreads, 1) softargmax_stream_kernel(
   float* btab = stage + kWStages * kWChunkFloats;       // border weights: [4][16] (Ah, Rh, Aw, Rw) x 2*radius entries
   uint64_t* full = reinterpret_cast<uint64_t*>(btab + 64);
   volatile int* issued = reinterpret_cast<volatile int*>(full + kWStages);   // loads issued into each stage so far
+  int* next_chunk = const_cast<int*>(issued) + kWStages;                     // next chunk of this CTA's range to hand out
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -222,6 +223,7 @@ __global__ void __launch_bounds__(kWThreads, 1) softargmax_stream_kernel(
       mbar_init(&full[s], 1);
       issued[s] = 0;
     }
+    *next_chunk = 0;
     fence_mbar_init();
   }
   __syncthreads();
@@ -323,12 +325,15 @@ __global__ void __launch_bounds__(kWThreads, 1) softargmax_stream_kernel(
   const int brr0 = R2 > 0 ? bslot / R2 : 0, bsx0 = R2 > 0 ? bslot - brr0 * R2 : 0;   // side walk: (row offset, side index)
   const int bdrr = R2 > 0 ? blanes / R2 : 0, bdsx = R2 > 0 ? blanes - bdrr * R2 : 0;
 
-  int cb = 0, cc = 0;                            // (frame, chunk in frame) of this warp's current chunk
-  if (warp < nloc) { cb = (g0 + warp) / cpf; cc = (g0 + warp) - cb * cpf; }
-  for (int i = warp; i < nloc; i += kWWarps) {
-    const int b = cb, c = cc;
-    cc += kWWarps;
-    while (cc >= cpf) { cc -= cpf; ++cb; }
+  // Chunks are handed out in order to whichever warp is free (one shared counter): the oldest load is always the next one
+  // consumed, so a warp that falls behind no longer delays the refill another warp is about to wait for.  A chunk's
+  // arithmetic does not depend on the warp that runs it.
+  for (;;) {
+    int i = 0;
+    if (lane == 0) i = atomicAdd(next_chunk, 1);
+    i = __shfl_sync(0xffffffffu, i, 0);
+    if (i >= nloc) break;
+    const int b = (g0 + i) / cpf, c = (g0 + i) - b * cpf;
     const int c0 = c * chunk_px, npx = min(chunk_px, HW - c0);
     const int n4 = npx * nj / 4;
     const int s = i % kWStages, ph = (i / kWStages) & 1;
@@ -583,7 +588,7 @@ __global__ void __launch_bounds__(kWThreads, 1) softargmax_stream_kernel(
         issue_load_at(i + kWStages, nb, nc);
       }
     };
-    if constexpr (kShfl) refill();
+    if constexpr (kSamePixel) refill();   // only the nj % 4 != 0 reduction borrows the drained stage
 
     // ---- reduce over the lanes that share a joint; one partial per (chunk, joint), fixed order -> deterministic
     SaPartial* out = part + ((size_t)b * cpf + c) * nj;
@@ -619,6 +624,59 @@ __global__ void __launch_bounds__(kWThreads, 1) softargmax_stream_kernel(
           o[0] = mout[q];
           o[4] = bsig[q];
           o[5] = __int_as_float(bidx[q]);
+        }
+      }
+    } else if constexpr (kSamePixel) {
+      // nj % 4 == 0 but the lanes of a class {c, c + P, ...} are not an xor-closed set (nj = 12, 20, 24, ...): fold the class
+      // in halves while its size is even, then rotate through what is left; lane c < P ends up with the class sums in a
+      // fixed order (deterministic) and stores its four joints.
+      float v12[12] = {s0[0], s0[1], s0[2], s0[3], sr[0], sr[1], sr[2], sr[3], sc[0], sc[1], sc[2], sc[3]};
+      int span = tw / P;
+      while ((span & 1) == 0) {
+        span >>= 1;
+        const int src = lane + span * P;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+          const float o = __shfl_sync(0xffffffffu, v12[k], src < 32 ? src : lane);
+          v12[k] += o;   // meaningful on the lanes below span * P, which read a valid partner
+        }
+        if (kDlc) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float obs = __shfl_sync(0xffffffffu, bsig[q], src < 32 ? src : lane);
+            const int obi = __shfl_sync(0xffffffffu, bidx[q], src < 32 ? src : lane);
+            if (obs > bsig[q] || (obs == bsig[q] && obi < bidx[q])) { bsig[q] = obs; bidx[q] = obi; }
+          }
+        }
+      }
+      {
+        float own[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) own[k] = v12[k];
+        const float obs0[4] = {bsig[0], bsig[1], bsig[2], bsig[3]};
+        const int obi0[4] = {bidx[0], bidx[1], bidx[2], bidx[3]};
+        for (int m = 1; m < span; ++m) {
+          int src = lane + m * P;
+          if (src >= span * P) src -= span * P;
+          if (lane >= span * P) src = lane;
+#pragma unroll
+          for (int k = 0; k < 12; ++k) v12[k] += __shfl_sync(0xffffffffu, own[k], src);
+          if (kDlc) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float obs = __shfl_sync(0xffffffffu, obs0[q], src);
+              const int obi = __shfl_sync(0xffffffffu, obi0[q], src);
+              if (obs > bsig[q] || (obs == bsig[q] && obi < bidx[q])) { bsig[q] = obs; bidx[q] = obi; }
+            }
+          }
+        }
+      }
+      if (lane < P) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float4* o4 = reinterpret_cast<float4*>(out + jq[q]);
+          o4[0] = make_float4(mout[q], v12[q], v12[4 + q], v12[8 + q]);
+          o4[1] = make_float4(bsig[q], __int_as_float(bidx[q]), 0.0f, 0.0f);
         }
       }
     } else {
@@ -694,22 +752,33 @@ __global__ void softargmax_finalize_kernel(const float* __restrict__ logits, con
     }
   }
   const float* fr = logits + (size_t)b * H * W * nj + j;
-  if (lane != 0) return;
+  // every lane holds the merged sums (xor trees): the <= 2 x 2 window of the estimate_pose read-out is fetched by lanes
+  // 0..3 in parallel (one load latency instead of four dependent ones), lane 0 then scans it in numpy's order
   const float mur = a.sr / a.s0, muc = a.sc / a.s0;  // 0/0 -> NaN, as softmax_tensor / (sum + 1e-100) in fp32
+  float win = 0.0f;
+  int rlo = 0, rhi = 0, clo = 0, chi = 0;
+  const bool want_win = (peak || lik) && mur == mur && muc == muc;
+  if (want_win) {
+    // numpy slice [floor : ceil+1] clipped to the array
+    rlo = max((int)floorf(mur), 0); rhi = min((int)ceilf(mur) + 1, H);
+    clo = max((int)floorf(muc), 0); chi = min((int)ceilf(muc) + 1, W);
+    const int r = rlo + (lane >> 1), c = clo + (lane & 1);
+    if (lane < 4 && r < rhi && c < chi) win = sigmoid_literal(fr[((size_t)r * W + c) * nj]);
+  }
+  const float w1 = __shfl_sync(0xffffffffu, win, 1), w2 = __shfl_sync(0xffffffffu, win, 2), w3 = __shfl_sync(0xffffffffu, win, 3);
+  if (lane != 0) return;
   if (mu) { mu[2 * t] = mur; mu[2 * t + 1] = muc; }
   if (norm) { norm[2 * t] = a.m; norm[2 * t + 1] = a.s0; }
 
   if (peak || lik) {
     int pr = -1, pc = -1;
     float best = CUDART_NAN_F;
-    if (mur == mur && muc == muc) {
-      // numpy slice [floor : ceil+1] clipped to the array
-      const int rlo = max((int)floorf(mur), 0), rhi = min((int)ceilf(mur) + 1, H);
-      const int clo = max((int)floorf(muc), 0), chi = min((int)ceilf(muc) + 1, W);
+    if (want_win) {
       bool have = false, have_nan = false;
       for (int r = rlo; r < rhi && !have_nan; ++r)
         for (int c = clo; c < chi; ++c) {
-          const float s = sigmoid_literal(fr[((size_t)r * W + c) * nj]);
+          const int wi = (r - rlo) * 2 + (c - clo);
+          const float s = wi == 0 ? win : (wi == 1 ? w1 : (wi == 2 ? w2 : w3));
           if (s != s) { pr = r; pc = c; best = s; have_nan = true; break; }  // np.argmax: first NaN wins
           if (!have || s > best) { best = s; pr = r; pc = c; have = true; }
         }
