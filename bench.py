@@ -443,12 +443,14 @@ def roofline_of(wl, m, steps, peaks, peak_src, args=None):
 
 
 def softargmax_roofline(local_rank, peaks):
-    """GPU-filling soft-argmax measurement (the in-step launch moves 5 MB and is latency bound): 4096 maps of each BASELINE
+    """GPU-filling soft-argmax measurement (the in-step launch moves 5 MB and is latency bound): 2-16 k maps of each BASELINE
     shape, far larger than the L2, CUDA events around 10 back-to-back stream + finalize pairs, best of 3 after warm-up."""
     from deepgraphpose_b200.engine import Engine
     out = {}
     for tag, (hs, ws, nj) in {"nj4_94x104": (94, 104, 4), "nj16_128x160": (128, 160, 16), "nj20_60x80": (60, 80, 20)}.items():
-        nmaps = 4096 if nj <= 4 else (1024 if nj == 16 else 2048)
+        # ~2.5-3 GB per call (0.5-0.7 ms of GPU time): the 10 queued calls stay device-bound even when the host threads of
+        # several ranks share cores
+        nmaps = 16384 if nj <= 4 else (2048 if nj == 16 else 8192)
         eng = Engine(nj, location_refinement=False, device=local_rank)
         x = torch.randn((nmaps, hs, ws, nj), device="cuda:%d" % local_rank) * 3.0
         for _ in range(3):
