@@ -58,7 +58,7 @@ struct LossArgs {
   float* all_markers;   // scratch (nt*nj,2): targets_all_marker
   float4* partials;     // scratch (nbv+nbh)
   float* meanflow;      // scratch ((nt-1)*nj)
-  float* flow_part;     // scratch ((nt-1)*nj * ceil(Hin/16) * 8): per row-chunk partial sums of the flow box means
+  float* flow_part;     // scratch ((nt-1)*nj * ceil(Hin/16) * 8): per row-slab partial sums of the flow box means
   float4* boxgrad;      // scratch ((nt-1)*nj): d meanflow / d (y1, x1, y2, x2) of the crop box, or nullptr (forward only)
   float* out;           // [6]
 };

@@ -14,7 +14,33 @@ namespace dgp {
 
 namespace {
 
-constexpr int kLossThreads = 256;
+constexpr int kLossThreads = 512;
+constexpr size_t kPlaneSmemMax = 200 * 1024;   // a marker's logit plane is staged in shared memory when it fits
+
+// Stage channel j of one frame's logits (stride nj floats) into shared memory with 8 independent loads in flight per thread.
+// The marker kernels make two or three passes over this plane with ~40 pixels per thread: read straight from global memory
+// every pass was a chain of dependent ~1 us loads (87 + 111 us per training step for 40 markers); staged, the passes run from
+// shared memory.  Returns the pointer / stride the passes should use.
+__device__ __forceinline__ const float* stage_plane(const float* __restrict__ x0, int HW, int nj, float* plane, int use_smem,
+                                                    int* xstride) {
+  if (!use_smem) { *xstride = nj; return x0; }
+  for (int p0 = threadIdx.x; p0 < HW; p0 += blockDim.x * 8) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int p = p0 + u * blockDim.x;
+      v[u] = p < HW ? __ldg(x0 + (size_t)p * nj) : 0.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int p = p0 + u * blockDim.x;
+      if (p < HW) plane[p] = v[u];
+    }
+  }
+  __syncthreads();
+  *xstride = 1;
+  return plane;
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -74,14 +100,16 @@ __global__ void __launch_bounds__(kLossThreads) marker_loss_kernel(
     const float* __restrict__ pred, const float* __restrict__ locref, const float* __restrict__ locref_map,
     const float* __restrict__ locref_mask, const float* __restrict__ all, const int* __restrict__ visible, int nbv,
     const int* __restrict__ hidden, int H, int W, int nj, float inv2l2, int gm2, int gm3, int locref_mse,
-    float4* __restrict__ part) {
+    float4* __restrict__ part, int use_smem) {
+  extern __shared__ float plane[];
   __shared__ float sh[kLossThreads / 32];
   const bool is_vis = (int)blockIdx.x < nbv;
   const int m = is_vis ? visible[blockIdx.x] : hidden[blockIdx.x - nbv];
   const int t = m / nj, j = m - t * nj;
   const float mur = all[2 * m], muc = all[2 * m + 1];
-  const float* x0 = pred + (size_t)t * H * W * nj + j;
   const int HW = H * W;
+  int xs_stride;
+  const float* x0 = stage_plane(pred + (size_t)t * H * W * nj + j, HW, nj, plane, use_smem, &xs_stride);
 
   // pass A: max of the Gaussian bump (+1e-5, fitdgp.py:973) and, for hidden markers, the confidence max sigmoid
   float gmax = 0.0f, cmax = -CUDART_INF_F;
@@ -89,7 +117,7 @@ __global__ void __launch_bounds__(kLossThreads) marker_loss_kernel(
     const int r = p / W, c = p - r * W;
     const float dr = (float)r - mur, dc = (float)c - muc;
     gmax = fmaxf(gmax, expf(-(dr * dr + dc * dc) * inv2l2));
-    if (!is_vis && gm2 != 0) cmax = fmaxf(cmax, sigmoidf_(x0[(size_t)p * nj]));
+    if (!is_vis && gm2 != 0) cmax = fmaxf(cmax, sigmoidf_(x0[(size_t)p * xs_stride]));
   }
   gmax = block_max(gmax, sh) + 1e-5f;
   float conf = 1.0f;
@@ -101,7 +129,7 @@ __global__ void __launch_bounds__(kLossThreads) marker_loss_kernel(
     const int r = p / W, c = p - r * W;
     const float dr = (float)r - mur, dc = (float)c - muc;
     float tg = expf(-(dr * dr + dc * dc) * inv2l2) / gmax;
-    float x = x0[(size_t)p * nj];
+    float x = x0[(size_t)p * xs_stride];
     if (!is_vis && gm2 != 0) {
       if (gm2 == 1) tg *= conf;                       // fitdgp.py:1000
       if (gm3 == 3) {                                 // confidence-scaled logits (fitdgp.py:1002-1004)
@@ -123,11 +151,12 @@ __global__ void __launch_bounds__(kLossThreads) marker_loss_kernel(
   float hub = 0.0f, mcount = 0.0f;
   if (is_vis && locref != nullptr) {
     const size_t base = (size_t)t * HW * 2 * nj + 2 * j;
+#pragma unroll 4
     for (int p = threadIdx.x; p < 2 * HW; p += blockDim.x) {
       const int pix = p >> 1, ch = p & 1;
       const size_t o = base + (size_t)pix * 2 * nj + ch;
-      const float w = locref_mask[o];
-      const float d = locref[o] - locref_map[o];
+      const float w = __ldg(locref_mask + o);
+      const float d = __ldg(locref + o) - __ldg(locref_map + o);
       const float a = fabsf(d);
       // huber_loss (k = 1), or tf.losses.mean_squared_error when dgp_cfg.locref_huber_loss is False (fitdgp.py:1053)
       const float l = locref_mse ? d * d : (a < 1.0f ? 0.5f * d * d : a - 0.5f);
@@ -140,16 +169,23 @@ __global__ void __launch_bounds__(kLossThreads) marker_loss_kernel(
   if (threadIdx.x == 0) part[blockIdx.x] = make_float4(ce, wcount, hub, mcount);
 }
 
-// mean over tf.image.crop_and_resize(flow, box, [Hin, Win]) per (t, j) (fitdgp.py:1085-1110), bilinear, extrapolation 0.
-// Grid (box, row chunk): every CTA samples kFlowRows output rows of one box and writes 5 partial sums; the finalize kernel
-// adds the chunks of a box in a fixed order (bitwise reproducible).  One CTA per box took 1.27 ms per training step at
-// 747x832 (36 boxes x 621 k samples on 36 SMs); chunked it is a 148-SM kernel.
-constexpr int kFlowRows = 16;
+// mean over tf.image.crop_and_resize(flow, box, [Hin, Win]) per (t, j) (fitdgp.py:1085-1110), bilinear, extrapolation 0, and
+// the gradient of that mean w.r.t. the box (tf CropAndResizeGradBoxes).
+// crop_and_resize samples Hin x Win points INSIDE the box (a few dozen pixels wide), so the 621 k bilinear samples of a
+// 747x832 frame land on ~10^3 source pixels.  Bilinear weights are separable: with, per source row r,
+//   Wy[r]  = sum over valid output rows yy of the weight yy puts on r          ((1 - ly) on floor(ys), ly on ceil(ys))
+//   Dy1[r] = sum over yy of (Hin-1-yy) * ([ceil(ys) == r] - [floor(ys) == r]),  Dy2[r] likewise with yy
+// (and Wx, Dx1, Dx2 per source column), the five sums are  Wy' I Wx,  Dy1' I Wx,  Wy' I Dx1,  Dy2' I Wx,  Wy' I Dx2  over the
+// box's pixels.  Round 2: replaces the sampled version (36 boxes x 621 k samples, 95 us per training step).  Grid (box, slab of
+// 16 source rows): a box that spans the whole frame is still a 148-SM kernel; CTAs past the box's last row exit with zeros.
+// Every weight is accumulated by one thread in a fixed order, block reduction and slab sum are fixed-order: reproducible.
+constexpr int kFlowRows = 16;   // source rows per CTA: grid = (box, ceil(Hin / kFlowRows)); CTAs beyond the box's rows write zeros
 __global__ void __launch_bounds__(kLossThreads) flow_box_mean_kernel(const float* __restrict__ flow, const float* __restrict__ all,
                                                                    int nt, int nj, int Hin, int Win, float stride,
                                                                    int want_grad, float* __restrict__ part) {
+  extern __shared__ float wts[];   // [3][kFlowRows] row weights, then [3][nc] column weights
   __shared__ float sh[kLossThreads / 32];
-  const int box = blockIdx.x, chunk = blockIdx.y;
+  const int box = blockIdx.x;
   const int t = box / nj, j = box - t * nj;
   const float* a0 = all + ((size_t)t * nj + j) * 2;
   const float* a1 = all + ((size_t)(t + 1) * nj + j) * 2;
@@ -161,36 +197,80 @@ __global__ void __launch_bounds__(kLossThreads) flow_box_mean_kernel(const float
   const float y1 = rmin / nx, x1 = cmin / ny, y2 = rmax / nx, x2 = cmax / ny;
   const float sy = Hin > 1 ? (y2 - y1) * (float)(Hin - 1) / (float)(Hin - 1) : 0.0f;
   const float sx = Win > 1 ? (x2 - x1) * (float)(Win - 1) / (float)(Win - 1) : 0.0f;
-  const float* img = flow + (size_t)t * Hin * Win;
-  float acc = 0.0f;
-  float gy1 = 0.0f, gx1 = 0.0f, gy2 = 0.0f, gx2 = 0.0f;  // d sum / d (y1, x1, y2, x2): tf CropAndResizeGradBoxes
-  const int row_end = min(Hin, (chunk + 1) * kFlowRows);
-  for (int yy = chunk * kFlowRows; yy < row_end; ++yy) {
-    const float ys = Hin > 1 ? y1 * (float)(Hin - 1) + (float)yy * sy : 0.5f * (y1 + y2) * (float)(Hin - 1);
-    if (ys < 0.0f || ys > (float)(Hin - 1)) continue;
-    const int yl = (int)floorf(ys), yh = min((int)ceilf(ys), Hin - 1);
-    const float ly = ys - floorf(ys);
-    const float* rl = img + (size_t)yl * Win;
-    const float* rh = img + (size_t)yh * Win;
-    for (int xx = threadIdx.x; xx < Win; xx += blockDim.x) {
-      const float xs = Win > 1 ? x1 * (float)(Win - 1) + (float)xx * sx : 0.5f * (x1 + x2) * (float)(Win - 1);
-      if (xs < 0.0f || xs > (float)(Win - 1)) continue;
-      const int xl = (int)floorf(xs), xh = min((int)ceilf(xs), Win - 1);
-      const float lx = xs - floorf(xs);
-      const float tl = __ldg(rl + xl), tr = __ldg(rl + xh), bl = __ldg(rh + xl), br = __ldg(rh + xh);
-      const float top = tl + (tr - tl) * lx, bot = bl + (br - bl) * lx;
-      acc += top + (bot - top) * ly;
-      if (want_grad) {
-        const float gy = (bl - tl) * (1.0f - lx) + (br - tr) * lx;   // d value / d in_y
-        const float gx = (tr - tl) * (1.0f - ly) + (br - bl) * ly;   // d value / d in_x
-        if (Hin > 1) { gy1 += gy * (float)(Hin - 1 - yy); gy2 += gy * (float)yy; }
-        else { gy1 += gy * 0.5f * (float)(Hin - 1); gy2 += gy * 0.5f * (float)(Hin - 1); }
-        if (Win > 1) { gx1 += gx * (float)(Win - 1 - xx); gx2 += gx * (float)xx; }
-        else { gx1 += gx * 0.5f * (float)(Win - 1); gx2 += gx * 0.5f * (float)(Win - 1); }
-      }
-    }
+  auto sample_y = [&](int yy) { return Hin > 1 ? y1 * (float)(Hin - 1) + (float)yy * sy : 0.5f * (y1 + y2) * (float)(Hin - 1); };
+  auto sample_x = [&](int xx) { return Win > 1 ? x1 * (float)(Win - 1) + (float)xx * sx : 0.5f * (x1 + x2) * (float)(Win - 1); };
+  // source rows / columns any sample can touch (a margin of one absorbs the rounding of the end points; NaN markers -> empty)
+  const float ya = fminf(sample_y(0), sample_y(Hin - 1)), yb = fmaxf(sample_y(0), sample_y(Hin - 1));
+  const float xa = fminf(sample_x(0), sample_x(Win - 1)), xb = fmaxf(sample_x(0), sample_x(Win - 1));
+  int r_lo = 0, r_hi = -1, c_lo = 0, c_hi = -1;
+  if (ya == ya && yb == yb && xa == xa && xb == xb) {
+    r_lo = max(0, (int)floorf(fmaxf(ya, 0.0f)) - 1); r_hi = min(Hin - 1, (int)ceilf(fminf(yb, (float)(Hin - 1))) + 1);
+    c_lo = max(0, (int)floorf(fmaxf(xa, 0.0f)) - 1); c_hi = min(Win - 1, (int)ceilf(fminf(xb, (float)(Win - 1))) + 1);
   }
-  float* out = part + ((size_t)box * gridDim.y + chunk) * 8;
+  // this CTA's slab of the box's source rows
+  r_lo += (int)blockIdx.y * kFlowRows;
+  r_hi = min(r_hi, r_lo + kFlowRows - 1);
+  const int nr = max(r_hi - r_lo + 1, 0), nc = nr > 0 ? max(c_hi - c_lo + 1, 0) : 0;
+  float* wy = wts;               // Wy, Dy1, Dy2
+  float* wx = wts + 3 * nr;      // Wx, Dx1, Dx2
+  // ---- phase 1: one thread per source row / column.  The sample positions ps(k) are monotone in k, so the samples whose
+  // floor (ceil) is this row form a contiguous range of k: found by bisection on the same float expression the interpolation
+  // uses, then accumulated in ascending k (fixed order).
+  for (int it = threadIdx.x; it < nr + nc; it += blockDim.x) {
+    const bool is_row = it < nr;
+    const int me = is_row ? r_lo + it : c_lo + (it - nr);
+    const int n = is_row ? Hin : Win;
+    auto ps_of = [&](int k) { return is_row ? sample_y(k) : sample_x(k); };
+    auto first_ge = [&](float v) {   // min k in [0, n] with ps(k) >= v
+      int lo = 0, hi = n;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (ps_of(mid) >= v) hi = mid; else lo = mid + 1; }
+      return lo;
+    };
+    auto first_gt = [&](float v) {   // min k in [0, n] with ps(k) > v
+      int lo = 0, hi = n;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (ps_of(mid) > v) hi = mid; else lo = mid + 1; }
+      return lo;
+    };
+    const int kv0 = first_ge(0.0f), kv1 = first_gt((float)(n - 1));   // samples inside the image: [kv0, kv1)
+    float w = 0.0f, d1 = 0.0f, d2 = 0.0f;
+    const float half = 0.5f * (float)(n - 1);
+    // floor(ps) == me
+    for (int k = max(first_ge((float)me), kv0), ke = min(first_ge((float)(me + 1)), kv1); k < ke; ++k) {
+      const float ps = ps_of(k);
+      const float l = ps - floorf(ps);
+      w += 1.0f - l;
+      d1 -= n > 1 ? (float)(n - 1 - k) : half;
+      d2 -= n > 1 ? (float)k : half;
+    }
+    // ceil(ps) == me  (ps <= n - 1 for every sample inside the image, so the clamp of the upper neighbour never bites)
+    for (int k = max(first_gt((float)(me - 1)), kv0), ke = min(first_gt((float)me), kv1); k < ke; ++k) {
+      const float ps = ps_of(k);
+      const float l = ps - floorf(ps);
+      w += l;
+      d1 += n > 1 ? (float)(n - 1 - k) : half;
+      d2 += n > 1 ? (float)k : half;
+    }
+    float* o = is_row ? wy + it : wx + (it - nr);
+    const int ld = is_row ? nr : nc;
+    o[0] = w; o[ld] = d1; o[2 * ld] = d2;
+  }
+  __syncthreads();
+  // ---- phase 2: the five weighted sums over the touched pixels
+  const float* img = flow + (size_t)t * Hin * Win;
+  float acc = 0.0f, gy1 = 0.0f, gx1 = 0.0f, gy2 = 0.0f, gx2 = 0.0f;
+  for (int p = threadIdx.x; p < nr * nc; p += blockDim.x) {
+    const int ri = p / nc, ci = p - ri * nc;
+    const float v = __ldg(img + (size_t)(r_lo + ri) * Win + (c_lo + ci));
+    const float Wy = wy[ri], Dy1 = wy[nr + ri], Dy2 = wy[2 * nr + ri];
+    const float Wx = wx[ci], Dx1 = wx[nc + ci], Dx2 = wx[2 * nc + ci];
+    const float vy = v * Wx, vx = v * Wy;
+    acc += vy * Wy;
+    gy1 += vy * Dy1;
+    gy2 += vy * Dy2;
+    gx1 += vx * Dx1;
+    gx2 += vx * Dx2;
+  }
+  float* out = part + ((size_t)box * gridDim.y + blockIdx.y) * 8;
   acc = block_sum(acc, sh);
   if (want_grad) {
     gy1 = block_sum(gy1, sh); gx1 = block_sum(gx1, sh); gy2 = block_sum(gy2, sh); gx2 = block_sum(gx2, sh);
@@ -200,16 +280,20 @@ __global__ void __launch_bounds__(kLossThreads) flow_box_mean_kernel(const float
   }
 }
 
+// fixed-order sum of a box's row slabs
 __global__ void flow_box_finalize_kernel(const float* __restrict__ part, int nchunks, int Hin, int Win, float* __restrict__ meanflow,
                                          float4* __restrict__ boxgrad) {
-  const int box = blockIdx.x * blockDim.x + threadIdx.x;
-  if (box >= (int)gridDim.x * (int)blockDim.x) return;
+  // one warp per box: lane l adds slabs l, l + 32, ... in order, then a fixed xor tree (deterministic)
+  const int box = blockIdx.x;
   float s[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int c = 0; c < nchunks; ++c) {
+  for (int c = threadIdx.x; c < nchunks; c += 32) {
     const float* q = part + ((size_t)box * nchunks + c) * 8;
 #pragma unroll
     for (int i = 0; i < 5; ++i) s[i] += q[i];
   }
+#pragma unroll
+  for (int i = 0; i < 5; ++i) s[i] = warp_sum(s[i]);
+  if (threadIdx.x != 0) return;
   const float k = 1.0f / (float)(Hin * Win);
   meanflow[box] = s[0] * k;
   if (boxgrad != nullptr) boxgrad[box] = make_float4(s[1] * k, s[2] * k, s[3] * k, s[4] * k);
@@ -222,7 +306,30 @@ __global__ void loss_finalize_kernel(const float4* __restrict__ part, int nbv, i
                                      const float* __restrict__ ws, const float* __restrict__ ws_max,
                                      const float* __restrict__ meanflow, const float* __restrict__ wt_batch, float wt,
                                      float wt_max, float stride, float n_vis_total, float n_hid_total, float wn_visible,
-                                     float wn_hidden, float locref_weight, float* __restrict__ out) {
+                                     float wn_hidden, float locref_weight, float* __restrict__ out, int use_smem) {
+  // The arithmetic is one thread's fixed-order walk (deterministic); its inputs are first staged into shared memory by the whole
+  // block, so that the walk is not a chain of ~200 dependent global loads (20 us -> a few us per training step).
+  extern __shared__ float4 fin_sm[];
+  if (use_smem) {
+    const int nb = nbv + nbh, nm2 = nt * nj * 2, nbox = meanflow != nullptr ? (nt - 1) * nj : 0;
+    float4* s_part = fin_sm;
+    float* s_all = reinterpret_cast<float*>(s_part + nb);
+    float* s_mf = s_all + nm2;
+    float* s_wtb = s_mf + nbox;
+    float* s_ws = s_wtb + (nbox > 0 ? nt - 1 : 0);
+    float* s_wsm = s_ws + nl;
+    int* s_edges = reinterpret_cast<int*>(s_wsm + nl);
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) s_part[i] = part[i];
+    for (int i = threadIdx.x; i < nm2; i += blockDim.x) s_all[i] = all[i];
+    for (int i = threadIdx.x; i < nbox; i += blockDim.x) s_mf[i] = meanflow[i];
+    if (nbox > 0)
+      for (int i = threadIdx.x; i < nt - 1; i += blockDim.x) s_wtb[i] = wt_batch[i];
+    for (int i = threadIdx.x; i < nl; i += blockDim.x) { s_ws[i] = ws[i]; s_wsm[i] = ws_max[i]; }
+    for (int i = threadIdx.x; i < 2 * nl; i += blockDim.x) s_edges[i] = edges[i];
+    __syncthreads();
+    part = s_part; all = s_all; ws = s_ws; ws_max = s_wsm; edges = s_edges;
+    if (nbox > 0) { meanflow = s_mf; wt_batch = s_wtb; }
+  }
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   float ce_v = 0.0f, cnt_v = 0.0f, hub = 0.0f, mcnt = 0.0f, ce_h = 0.0f, cnt_h = 0.0f;
   for (int i = 0; i < nbv; ++i) { ce_v += part[i].x; cnt_v += part[i].y; hub += part[i].z; mcnt += part[i].w; }
@@ -314,7 +421,8 @@ __global__ void __launch_bounds__(kLossThreads) marker_loss_bwd_kernel(
     float stride, float n_vis_total, float n_hid_total, float wn_visible, float wn_hidden, float locref_weight,
     int visible_only, const float* __restrict__ meanflow, const float4* __restrict__ boxgrad,
     const float* __restrict__ wt_batch, float wt_max, int Hin, int Win, const float* __restrict__ losses,
-    float* __restrict__ g_pred, float* __restrict__ g_locref) {
+    float* __restrict__ g_pred, float* __restrict__ g_locref, int use_smem) {
+  extern __shared__ float plane[];
   __shared__ float shf[kLossThreads / 32];
   __shared__ int shi[kLossThreads / 32];
   __shared__ float s_cnt[3];
@@ -322,15 +430,27 @@ __global__ void __launch_bounds__(kLossThreads) marker_loss_bwd_kernel(
   const int m = is_vis ? visible[blockIdx.x] : hidden[blockIdx.x - nbv];
   const int t = m / nj, j = m - t * nj;
   const int HW = H * W;
-  const float* x0 = pred + (size_t)t * HW * nj + j;
+  int xs_stride;
+  const float* x0 = stage_plane(pred + (size_t)t * HW * nj + j, HW, nj, plane, use_smem, &xs_stride);
   float* g0 = g_pred + (size_t)t * HW * nj + j;
   const float fnbv = nbv > 0 ? (float)nbv : (float)nbh;
 
-  // global normalisers from the forward partials (fixed order)
+  // global normalisers from the forward partials (fixed order; fetched by the whole block first, the sum itself stays serial)
+  __shared__ float2 s_yw[1024];
+  const int nball = nbv + nbh;
+  const bool staged = nball <= 1024;
+  if (staged)
+    for (int i = threadIdx.x; i < nball; i += blockDim.x) { const float4 q = part[i]; s_yw[i] = make_float2(q.y, q.w); }
+  __syncthreads();
   if (threadIdx.x == 0) {
     float cv = 0.0f, ch = 0.0f, mc = 0.0f;
-    for (int i = 0; i < nbv; ++i) { cv += part[i].y; mc += part[i].w; }
-    for (int i = nbv; i < nbv + nbh; ++i) ch += part[i].y;
+    if (staged) {
+      for (int i = 0; i < nbv; ++i) { cv += s_yw[i].x; mc += s_yw[i].y; }
+      for (int i = nbv; i < nball; ++i) ch += s_yw[i].x;
+    } else {
+      for (int i = 0; i < nbv; ++i) { cv += part[i].y; mc += part[i].w; }
+      for (int i = nbv; i < nball; ++i) ch += part[i].y;
+    }
     s_cnt[0] = cv; s_cnt[1] = ch; s_cnt[2] = mc;
   }
   __syncthreads();
@@ -346,7 +466,7 @@ __global__ void __launch_bounds__(kLossThreads) marker_loss_bwd_kernel(
     const float g = expf(-(dr * dr + dc * dc) * inv2l2);
     if (g > gm) { gm = g; gi = p; }
     if (!is_vis && gm2 != 0) {
-      const float sg = sigmoidf_(x0[(size_t)p * nj]);
+      const float sg = sigmoidf_(x0[(size_t)p * xs_stride]);
       if (sg > cm) { cm = sg; ci = p; }
     }
   }
@@ -362,15 +482,16 @@ __global__ void __launch_bounds__(kLossThreads) marker_loss_bwd_kernel(
       const int r = p / W, c = p - r * W;
       const float dr = (float)r - tr, dc = (float)c - tc;
       const float tg = expf(-(dr * dr + dc * dc) * inv2l2) / gm5;
-      g0[(size_t)p * nj] = kv * (sigmoidf_(x0[(size_t)p * nj]) - tg);
+      g0[(size_t)p * nj] = kv * (sigmoidf_(x0[(size_t)p * xs_stride]) - tg);
     }
     if (locref != nullptr && g_locref != nullptr) {
       const float kl = mcnt > 0.0f ? locref_weight / mcnt : 0.0f;
       const size_t base = (size_t)t * HW * 2 * nj + 2 * j;
+#pragma unroll 4
       for (int p = threadIdx.x; p < 2 * HW; p += blockDim.x) {
         const size_t o = base + (size_t)(p >> 1) * 2 * nj + (p & 1);
-        const float d = locref[o] - locref_map[o];
-        g_locref[o] = kl * locref_mask[o] * (locref_mse ? 2.0f * d : (fabsf(d) < 1.0f ? d : (d > 0.0f ? 1.0f : -1.0f)));
+        const float d = __ldg(locref + o) - __ldg(locref_map + o);
+        g_locref[o] = kl * __ldg(locref_mask + o) * (locref_mse ? 2.0f * d : (fabsf(d) < 1.0f ? d : (d > 0.0f ? 1.0f : -1.0f)));
       }
     }
     return;
@@ -393,7 +514,7 @@ __global__ void __launch_bounds__(kLossThreads) marker_loss_bwd_kernel(
     const float dr = (float)r - tr, dc = (float)c - tc;
     const float G = expf(-(dr * dr + dc * dc) * inv2l2);
     const float tg = G / gm5;
-    const float x = x0[(size_t)p * nj];
+    const float x = x0[(size_t)p * xs_stride];
     const float sg = sigmoidf_(x);
     float xl = x, D = 0.0f;
     if (scaled) {
@@ -490,7 +611,7 @@ __global__ void __launch_bounds__(kLossThreads) marker_loss_bwd_kernel(
     const int r = p / W, c = p - r * W;
     const float dr = (float)r - tr, dc = (float)c - tc;
     const float tg = expf(-(dr * dr + dc * dc) * inv2l2) / gm5;
-    const float x = x0[(size_t)p * nj];
+    const float x = x0[(size_t)p * xs_stride];
     const float sg = sigmoidf_(x);
     float direct;
     if (scaled) {
@@ -523,22 +644,35 @@ cudaError_t launch_dgp_loss(const LossArgs& a, cudaStream_t stream) {
   if (nb > 0) {
     combine_markers_kernel<<<(nb + 127) / 128, 128, 0, stream>>>(a.mu, a.targets, a.visible, a.nbv, a.hidden, a.nbh,
                                                                  a.vis_in_targets, a.all_markers);
-    marker_loss_kernel<<<nb, kLossThreads, 0, stream>>>(a.pred, a.locref, a.locref_map, a.locref_mask, a.all_markers,
-                                                        a.visible, a.nbv, a.hidden, a.H, a.W, a.nj,
-                                                        1.0f / (2.0f * a.lengthscale * a.lengthscale), a.gm2, a.gm3,
-                                                        a.locref_mse, a.partials);
+    const size_t plane_bytes = (size_t)a.H * a.W * sizeof(float);
+    const int use_smem = plane_bytes <= kPlaneSmemMax;
+    if (use_smem) {
+      cudaError_t ea = cudaFuncSetAttribute(marker_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPlaneSmemMax);
+      if (ea != cudaSuccess) return ea;
+    }
+    marker_loss_kernel<<<nb, kLossThreads, use_smem ? plane_bytes : 0, stream>>>(
+        a.pred, a.locref, a.locref_map, a.locref_mask, a.all_markers, a.visible, a.nbv, a.hidden, a.H, a.W, a.nj,
+        1.0f / (2.0f * a.lengthscale * a.lengthscale), a.gm2, a.gm3, a.locref_mse, a.partials, use_smem);
   }
   const bool temporal = a.wt > 0.0f && a.flow != nullptr && a.nt > 1;
   if (temporal) {
     const int nboxes = (a.nt - 1) * a.nj, nchunks = (a.Hin + kFlowRows - 1) / kFlowRows;
-    flow_box_mean_kernel<<<dim3(nboxes, nchunks), kLossThreads, 0, stream>>>(a.flow, a.all_markers, a.nt, a.nj, a.Hin, a.Win, a.stride,
-                                                                          a.boxgrad != nullptr, a.flow_part);
-    flow_box_finalize_kernel<<<nboxes, 1, 0, stream>>>(a.flow_part, nchunks, a.Hin, a.Win, a.meanflow, a.boxgrad);
+    const size_t wbytes = 3 * ((size_t)kFlowRows + a.Win) * sizeof(float);
+    if (wbytes > 48 * 1024) {
+      if (wbytes > kPlaneSmemMax) return cudaErrorInvalidValue;
+      cudaError_t ea = cudaFuncSetAttribute(flow_box_mean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPlaneSmemMax);
+      if (ea != cudaSuccess) return ea;
+    }
+    flow_box_mean_kernel<<<dim3(nboxes, nchunks), kLossThreads, wbytes, stream>>>(a.flow, a.all_markers, a.nt, a.nj, a.Hin, a.Win,
+                                                                                  a.stride, a.boxgrad != nullptr, a.flow_part);
+    flow_box_finalize_kernel<<<nboxes, 32, 0, stream>>>(a.flow_part, nchunks, a.Hin, a.Win, a.meanflow, a.boxgrad);
   }
-  loss_finalize_kernel<<<1, 32, 0, stream>>>(a.partials, a.nbv, a.nbh, a.all_markers, a.nt, a.nj, a.H, a.W, a.edges, a.nl,
-                                             a.ws, a.ws_max, temporal ? a.meanflow : nullptr, a.wt_batch, a.wt, a.wt_max,
-                                             a.stride, a.n_vis_total, a.n_hid_total, a.wn_visible, a.wn_hidden,
-                                             a.locref_weight, a.out);
+  const size_t fin_bytes = (size_t)nb * 16 + ((size_t)nm * 2 + (temporal ? (size_t)(a.nt - 1) * (a.nj + 1) : 0) + 4 * (size_t)a.nl) * 4 + 16;
+  const int fin_smem = fin_bytes <= 48 * 1024;
+  loss_finalize_kernel<<<1, 128, fin_smem ? fin_bytes : 0, stream>>>(
+      a.partials, a.nbv, a.nbh, a.all_markers, a.nt, a.nj, a.H, a.W, a.edges, a.nl, a.ws, a.ws_max,
+      temporal ? a.meanflow : nullptr, a.wt_batch, a.wt, a.wt_max, a.stride, a.n_vis_total, a.n_hid_total, a.wn_visible,
+      a.wn_hidden, a.locref_weight, a.out, fin_smem);
   return cudaGetLastError();
 }
 
@@ -552,13 +686,19 @@ cudaError_t launch_dgp_loss_backward(const LossArgs& a, const float* norm, float
     e = cudaMemsetAsync(g_locref, 0, (size_t)a.nt * a.H * a.W * 2 * a.nj * sizeof(float), stream);
     if (e != cudaSuccess) return e;
   }
+  const size_t plane_bytes = (size_t)a.H * a.W * sizeof(float);
+  const int use_smem = plane_bytes <= kPlaneSmemMax;
+  if (nb > 0 && use_smem) {
+    e = cudaFuncSetAttribute(marker_loss_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPlaneSmemMax);
+    if (e != cudaSuccess) return e;
+  }
   if (nb > 0)
-    marker_loss_bwd_kernel<<<nb, kLossThreads, 0, stream>>>(
+    marker_loss_bwd_kernel<<<nb, kLossThreads, use_smem ? plane_bytes : 0, stream>>>(
         a.pred, a.locref, a.locref_map, a.locref_mask, a.all_markers, a.mu, norm, a.visible, a.nbv, a.hidden, a.nbh,
         a.partials, a.nt, a.H, a.W, a.nj, 1.0f / (2.0f * a.lengthscale * a.lengthscale), a.gm2, a.gm3, a.locref_mse, gamma,
         (int)gauss_len, gauss_len, a.edges, a.nl, a.ws, a.ws_max, a.stride, a.n_vis_total, a.n_hid_total, a.wn_visible,
         a.wn_hidden, a.locref_weight, visible_only, temporal ? a.meanflow : nullptr, a.boxgrad, a.wt_batch, a.wt_max, a.Hin,
-        a.Win, a.out, g_pred, g_locref);
+        a.Win, a.out, g_pred, g_locref, use_smem);
   return cudaGetLastError();
 }
 
