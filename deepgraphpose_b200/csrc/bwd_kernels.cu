@@ -107,9 +107,11 @@ __global__ void __launch_bounds__(1024) bn_finalize_all_kernel(const BnGroup* __
   const int cl = threadIdx.x & 7, rg = threadIdx.x >> 3;
   const float* pp = part + g.part_off + g.col + cl;
   float s0 = 0.0f, s1 = 0.0f;
-  for (int b = rg; b < g.rows; b += 128) s0 += pp[(size_t)b * g.C];
+#pragma unroll 8
+  for (int b = rg; b < g.rows; b += 128) s0 += __ldg(pp + (size_t)b * g.C);   // up to ~100 independent loads per thread
   const float* rd = rowdot + g.rd_off + (size_t)cl * g.K4;
-  for (int i = rg; i < g.K4; i += 128) s1 += rd[i];
+#pragma unroll 4
+  for (int i = rg; i < g.K4; i += 128) s1 += __ldg(rd + i);
   __shared__ float sm0[128][9], sm1[128][9];
   sm0[rg][cl] = s0;
   sm1[rg][cl] = s1;
