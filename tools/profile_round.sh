@@ -25,3 +25,9 @@ DGP_TRAIN_GRAPHS=0 timeout 600 ncu --metrics gpu__time_duration.sum --clock-cont
   --log-file $O/${R}_train_launches.csv python tools/bench_train.py --steps 2 --warmup 3 > /dev/null 2>&1
 timeout 300 python tools/bench_train.py --steps 20 --warmup 3 > $O/${R}_bench_train_1gpu.json 2>>$O/bench_${R}.err
 ls -la $O | tail -20
+# 6. soft-argmax streaming kernel (GPU-filling microbenchmark of bench.py): one --set full capture per BASELINE joint count
+#    (33 stream-kernel launches per shape: 3 warm-up + 3 x 10 timed)
+for spec in nj4:5 nj16:38 nj20:71; do
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:softargmax_stream -s ${spec#*:} -c 1 \
+    -o $O/${R}_softargmax_${spec%%:*} python tools/softargmax_micro.py > /dev/null 2>&1
+done
