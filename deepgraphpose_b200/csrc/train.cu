@@ -17,6 +17,8 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <limits.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <dlfcn.h>
@@ -136,6 +138,15 @@ namespace nccl {
 typedef struct { char internal[128]; } UniqueId;     // ncclUniqueId (NCCL_UNIQUE_ID_BYTES = 128)
 typedef int (*GetUniqueIdFn)(UniqueId*);
 typedef int (*CommInitRankFn)(void**, int, UniqueId, int);
+// ncclConfig_t as of NCCL 2.14 (the prefix every later version keeps; `size` / `version` tell the library which fields are set)
+struct ConfigV21400 {
+  size_t size;
+  unsigned int magic;
+  unsigned int version;
+  int blocking, cgaClusterSize, minCTAs, maxCTAs;
+  const char* netName;
+};
+typedef int (*CommInitRankConfigFn)(void**, int, UniqueId, int, ConfigV21400*);
 typedef int (*CommDestroyFn)(void*);
 typedef int (*CommCountFn)(void*, int*);
 typedef int (*AllReduceFn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
@@ -145,6 +156,7 @@ constexpr int kFloat = 7, kSum = 0;                  // ncclFloat32, ncclSum
 struct Api {
   GetUniqueIdFn get_unique_id = nullptr;
   CommInitRankFn comm_init_rank = nullptr;
+  CommInitRankConfigFn comm_init_rank_config = nullptr;   // optional (NCCL >= 2.14)
   CommDestroyFn comm_destroy = nullptr;
   CommCountFn comm_count = nullptr;
   AllReduceFn all_reduce = nullptr;
@@ -163,6 +175,7 @@ const Api& api() {
   if (!lib) return a;
   a.get_unique_id = (GetUniqueIdFn)dlsym(lib, "ncclGetUniqueId");
   a.comm_init_rank = (CommInitRankFn)dlsym(lib, "ncclCommInitRank");
+  a.comm_init_rank_config = (CommInitRankConfigFn)dlsym(lib, "ncclCommInitRankConfig");
   a.comm_destroy = (CommDestroyFn)dlsym(lib, "ncclCommDestroy");
   a.comm_count = (CommCountFn)dlsym(lib, "ncclCommCount");
   a.all_reduce = (AllReduceFn)dlsym(lib, "ncclAllReduce");
@@ -976,7 +989,25 @@ int dgp_comm_init_rank(dgp_handle* h, const char* id128, int nranks, int rank) {
   nccl::UniqueId id;
   memcpy(id.internal, id128, 128);
   void* comm = nullptr;
-  NCCL_OK(h, nccl::api().comm_init_rank(&comm, nranks, id, rank));
+  // DGP_NCCL_MAX_CTAS > 0 caps the communicator's CTAs (ncclConfig_t::maxCTAs).  The all-reduce is hidden behind the backward
+  // pass and needs little bandwidth (94 MB in ~5 ms), so fewer CTAs could mean fewer SMs taken from the GEMMs it runs beside;
+  // measured on 2 and 8 B200 the cap (2 / 4 / 8 / 16) changes nothing (8.13-8.20 ms per step at dp8 either way: the 4 % over
+  // dp1 are the slowest of eight power-capped GPUs plus the HBM / NVLink traffic itself), so the default is NCCL's own choice.
+  int max_ctas = 0;
+  if (const char* e = getenv("DGP_NCCL_MAX_CTAS")) max_ctas = atoi(e);
+  if (max_ctas > 0 && nccl::api().comm_init_rank_config) {
+    nccl::ConfigV21400 cfg;
+    cfg.size = sizeof(cfg);
+    cfg.magic = 0xcafebeef;
+    cfg.version = 21400;                      // NCCL_VERSION(2, 14, 0)
+    cfg.blocking = cfg.cgaClusterSize = cfg.minCTAs = INT_MIN;   // NCCL_CONFIG_UNDEF_INT
+    cfg.maxCTAs = max_ctas;
+    cfg.netName = nullptr;                    // NCCL_CONFIG_UNDEF_PTR
+    const int rc_cfg = nccl::api().comm_init_rank_config(&comm, nranks, id, rank, &cfg);
+    if (rc_cfg != 0) return fail(h, DGP_ERR_CUDA, "ncclCommInitRankConfig(maxCTAs=%d): %s", max_ctas, nccl::api().err_str(rc_cfg));
+  } else {
+    NCCL_OK(h, nccl::api().comm_init_rank(&comm, nranks, id, rank));
+  }
   h->train->comm = comm;
   h->train->comm_owned = true;
   h->train->comm_world = nranks;
