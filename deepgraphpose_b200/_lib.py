@@ -45,7 +45,8 @@ class DgpLossBatch(C.Structure):
                 ("locref_mask_dev", C.c_void_p), ("visible_marker_dev", C.c_void_p), ("nbv", C.c_int32),
                 ("hidden_marker_dev", C.c_void_p), ("nbh", C.c_int32), ("visible_marker_in_targets_dev", C.c_void_p),
                 ("edges_dev", C.c_void_p), ("nl", C.c_int32), ("ws_dev", C.c_void_p), ("ws_max_dev", C.c_void_p),
-                ("vector_field_dev", C.c_void_p), ("Hin", C.c_int32), ("Win", C.c_int32), ("wt_batch_dev", C.c_void_p)]
+                ("vector_field_dev", C.c_void_p), ("Hin", C.c_int32), ("Win", C.c_int32), ("wt_batch_dev", C.c_void_p),
+                ("vector_field_ready_event", C.c_void_p)]
 
 
 class DgpCyclicSource(C.Structure):

@@ -1057,6 +1057,8 @@ int dgp_run_loss_impl(dgp_handle* h, const dgp_loss_cfg* cfg, const dgp_loss_bat
   a.boxgrad = grad_pred_dev ? boxgrad : nullptr;
   a.flow_part = flow_part;
   if (a.wt > 0.0f && a.flow != nullptr && !a.wt_batch) return fail(h, DGP_ERR_INVALID, "dgp_loss_forward: wt > 0 needs wt_batch");
+  if (b->vector_field_ready_event && b->vector_field_dev)   // the flow field comes from another stream (dgp_learn_wt overlapped)
+    CU_OK(h, cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)b->vector_field_ready_event, 0));
   CU_OK(h, launch_dgp_loss(a, (cudaStream_t)stream));
   h->launches += 4;
   if (targets_all_dev)

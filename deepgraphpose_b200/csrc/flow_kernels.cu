@@ -57,13 +57,13 @@ __global__ void gray_kernel(const uint8_t* __restrict__ frames, size_t npix, flo
 }
 
 // separable Gaussian, BORDER_REFLECT_101: dir 0 = along x, 1 = along y
+// (all per-pixel kernels below: grid = (ceil(W / 256), H, images) -- no 64-bit div / mod per pixel)
 __global__ void gauss_kernel(const float* __restrict__ src, float* __restrict__ dst, int n, int H, int W, GaussK gk, int dir) {
-  const size_t total = (size_t)n * H * W;
   const int r = gk.size / 2;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int x = (int)(i % W);
-    const int y = (int)((i / W) % H);
-    const float* img = src + (i / ((size_t)H * W)) * (size_t)H * W;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x < W) {
+    const float* img = src + (size_t)blockIdx.z * H * W;
+    const size_t i = ((size_t)blockIdx.z * H + y) * W + x;
     float acc = 0.0f;
     for (int j = 0; j < gk.size; ++j) {
       const float v = dir == 0 ? img[(size_t)y * W + reflect101(x + j - r, W)] : img[(size_t)reflect101(y + j - r, H) * W + x];
@@ -104,11 +104,10 @@ __global__ void resize_linear_kernel(const float* __restrict__ src, float* __res
 
 // polynomial expansion, vertical half: (sum g p, sum xg (below - above), sum xxg p) over the 11 rows, replicated borders
 __global__ void polyexp_v_kernel(const float* __restrict__ src, float* __restrict__ tmp3, int n, int H, int W, PolyConsts pc) {
-  const size_t total = (size_t)n * H * W;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int x = (int)(i % W);
-    const int y = (int)((i / W) % H);
-    const float* img = src + (i / ((size_t)H * W)) * (size_t)H * W;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x < W) {
+    const float* img = src + (size_t)blockIdx.z * H * W;
+    const size_t i = ((size_t)blockIdx.z * H + y) * W + x;
     float t0 = img[(size_t)y * W + x] * pc.g[kPolyN], t1 = 0.0f, t2 = 0.0f;
 #pragma unroll
     for (int k = 1; k <= kPolyN; ++k) {
@@ -126,9 +125,9 @@ __global__ void polyexp_v_kernel(const float* __restrict__ src, float* __restric
 
 // ... horizontal half and the projection onto (y, x, yy, xx, xy) (double accumulators as in the library)
 __global__ void polyexp_h_kernel(const float* __restrict__ tmp3, float* __restrict__ R, int n, int H, int W, PolyConsts pc) {
-  const size_t total = (size_t)n * H * W;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int x = (int)(i % W);
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x < W) {
+    const size_t i = ((size_t)blockIdx.z * H + blockIdx.y) * W + x;
     const float* row = tmp3 + (i - x) * 3;
     double b1 = (double)row[3 * x] * pc.g[kPolyN], b2 = 0.0, b3 = (double)row[3 * x + 1] * pc.g[kPolyN], b4 = 0.0,
            b5 = (double)row[3 * x + 2] * pc.g[kPolyN], b6 = 0.0;
@@ -158,11 +157,10 @@ __global__ void update_matrices_kernel(const float* __restrict__ R, const float*
                                        int H, int W) {
   const float border[5] = {0.14f, 0.14f, 0.4472f, 0.4472f, 0.4472f};
   const size_t plane = (size_t)H * W;
-  const size_t total = (size_t)np * plane;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int x = (int)(i % W);
-    const int y = (int)((i / W) % H);
-    const size_t p = i / plane;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x < W) {
+    const size_t p = blockIdx.z;
+    const size_t i = p * plane + (size_t)y * W + x;
     const float* R0 = R + (p * plane + (size_t)y * W + x) * 5;
     const float* R1 = R + (p + 1) * plane * 5;
     const float dx = flow[2 * i], dy = flow[2 * i + 1];
@@ -272,6 +270,8 @@ __global__ void __launch_bounds__(kBoxSeg) box_h_solve_kernel(const double* __re
   }
 }
 
+dim3 grid3(int W, int H, int n) { return dim3((unsigned)((W + 255) / 256), (unsigned)H, (unsigned)n); }
+
 int grid_for(size_t total) {
   size_t g = (total + 255) / 256;
   if (g > 148 * 32) g = 148 * 32;
@@ -341,6 +341,7 @@ size_t learn_wt_workspace_bytes(int T, int H, int W) {
 
 cudaError_t launch_learn_wt(const uint8_t* frames, int T, int H, int W, float* out, void* workspace, int* launches, cudaStream_t s) {
   if (T < 2) return cudaSuccess;
+  if (H > 65535 || T > 65535) return cudaErrorInvalidValue;   // grid.y = rows, grid.z = images
   static const PolyConsts pc = make_poly_consts();
   const size_t px = (size_t)H * W;
   char* w = static_cast<char*>(workspace);
@@ -378,11 +379,11 @@ cudaError_t launch_learn_wt(const uint8_t* frames, int T, int H, int W, float* o
     const int wl = (int)nearbyint(W * scale), hl = (int)nearbyint(H * scale);
     const size_t pl = (size_t)hl * wl;
     // per-frame: smooth at full resolution, resize, expand
-    gauss_kernel<<<grid_for(T * px), 256, 0, s>>>(gray, t1, T, H, W, gk, 0);
-    gauss_kernel<<<grid_for(T * px), 256, 0, s>>>(t1, t2, T, H, W, gk, 1);
+    gauss_kernel<<<grid3(W, H, T), 256, 0, s>>>(gray, t1, T, H, W, gk, 0);
+    gauss_kernel<<<grid3(W, H, T), 256, 0, s>>>(t1, t2, T, H, W, gk, 1);
     resize_linear_kernel<<<grid_for(T * pl), 256, 0, s>>>(t2, img, T, H, W, hl, wl, 1, 1.0f);
-    polyexp_v_kernel<<<grid_for(T * pl), 256, 0, s>>>(img, tmp3, T, hl, wl, pc);
-    polyexp_h_kernel<<<grid_for(T * pl), 256, 0, s>>>(tmp3, R, T, hl, wl, pc);
+    polyexp_v_kernel<<<grid3(wl, hl, T), 256, 0, s>>>(img, tmp3, T, hl, wl, pc);
+    polyexp_h_kernel<<<grid3(wl, hl, T), 256, 0, s>>>(tmp3, R, T, hl, wl, pc);
     nl += 5;
     // per pair: initial flow
     if (k == levels) {
@@ -393,7 +394,7 @@ cudaError_t launch_learn_wt(const uint8_t* frames, int T, int H, int W, float* o
       resize_linear_kernel<<<grid_for((size_t)(T - 1) * pl * 2), 256, 0, s>>>(flow_prev, flow, T - 1, hp, wp, hl, wl, 2, 2.0f);
       ++nl;
     }
-    update_matrices_kernel<<<grid_for((size_t)(T - 1) * pl), 256, 0, s>>>(R, flow, M, T - 1, hl, wl);
+    update_matrices_kernel<<<grid3(wl, hl, T - 1), 256, 0, s>>>(R, flow, M, T - 1, hl, wl);
     ++nl;
     for (int it = 0; it < kIters; ++it) {
       box_v_kernel<<<grid_for((size_t)(T - 1) * ((hl + kBoxRows - 1) / kBoxRows) * wl * 5), 256, 0, s>>>(M, V, T - 1, hl, wl);
@@ -403,7 +404,7 @@ cudaError_t launch_learn_wt(const uint8_t* frames, int T, int H, int W, float* o
       }
       nl += 2;
       if (it < kIters - 1) {
-        update_matrices_kernel<<<grid_for((size_t)(T - 1) * pl), 256, 0, s>>>(R, flow, M, T - 1, hl, wl);
+        update_matrices_kernel<<<grid3(wl, hl, T - 1), 256, 0, s>>>(R, flow, M, T - 1, hl, wl);
         ++nl;
       }
     }

@@ -569,6 +569,12 @@ class Engine:
         nv, nh = [int(x) for x in cnt.cpu().tolist()]
         return vm[:nv], hm[:nh], vit[:nv]
 
+    def side_stream(self):
+        """A second stream on the engine's device for feeders that may run beside the training step (learn_wt)."""
+        if getattr(self, "_side_stream", None) is None:
+            self._side_stream = torch.cuda.Stream(device=self.device)
+        return self._side_stream
+
     def learn_wt(self, frames):
         """Farneback flow magnitude |u| + |v| per consecutive frame pair (dgp_learn_wt): frames uint8 cuda (T,H,W,3) ->
         float32 cuda (T-1,H,W), the `vector_field_tf` feed of the temporal clique."""

@@ -110,7 +110,14 @@ def _loss_args(dev, feed, cfg, edges, ws, ws_max, n_frames_total, n_visible_fram
         b.edges_dev, b.nl, b.ws_dev, b.ws_max_dev = e.data_ptr(), len(edges), w1.data_ptr(), w2.data_ptr()
     wt = float(_get(cfg, "wt", 0.0))
     if wt > 0:
-        vf = f32(feed["vector_field_tf"])
+        vfeed = feed["vector_field_tf"]
+        ready = None
+        if hasattr(vfeed, "event") and hasattr(vfeed, "tensor"):     # fitdgp_util.AsyncField: produced on a side stream
+            vfeed, ready = vfeed.tensor, vfeed.event
+        vf = f32(vfeed)
+        if ready is not None:
+            keep.append(ready)
+            b.vector_field_ready_event = ready.cuda_event
         if vf.dim() != 3 or vf.shape[0] != nt - 1:
             raise ValueError("vector_field_tf must be (nt-1, Hin, Win) = (%d, ., .), got %s" % (nt - 1, tuple(vf.shape)))
         wb = f32(np.asarray(feed["wt_batch_pl"], dtype=np.float32) * np.asarray(feed["wt_batch_mask_pl"], dtype=np.float32))
@@ -376,7 +383,8 @@ def _fit_loop(data_batcher, dgp_cfg, variables, visible_frame_total, hidden_fram
         visible_marker, hidden_marker, visible_marker_in_targets = addn_batch_info
         all_frame = np.sort(list(visible_frame) + list(hidden_frame))
         visible_frame_within_batch = [int(np.where(all_frame == i)[0][0]) for i in visible_frame]
-        vector_field = learn_wt(all_data_batch, engine=engine) if wt > 0 else np.zeros((1, 1, 1))   # Farneback flow on the GPU
+        # Farneback flow on the GPU, on a side stream: it overlaps the forward pass of this step (the loss waits for its event)
+        vector_field = learn_wt(all_data_batch, engine=engine, overlap=True) if wt > 0 else np.zeros((1, 1, 1))
         feed = {
             placeholders["inputs"]: all_data_batch,
             placeholders["targets"]: joint_loc,

@@ -86,14 +86,29 @@ def make_2Dgrids(H, W, device="cuda"):
     return torch.stack([r, c], dim=2).unsqueeze(2)
 
 
-def learn_wt(all_data_batch, engine=None):
+class AsyncField:
+    """A device tensor produced on a side stream plus the event recorded behind its producer (``learn_wt(..., overlap=True)``).
+    Fed as ``vector_field_tf``, the loss waits for the event on its own stream (dgp_loss_batch.vector_field_ready_event), so the
+    Farneback flow of the batch runs beside the forward pass instead of in front of it."""
+
+    def __init__(self, tensor, event):
+        self.tensor, self.event = tensor, event
+
+    @property
+    def shape(self):
+        return self.tensor.shape
+
+
+def learn_wt(all_data_batch, engine=None, overlap=False):
     """fitdgp_util.py:454-467: optical-flow magnitude per consecutive frame pair, the ``vector_field_tf`` feed of the
     temporal clique (nt-1, H, W): OpenCV Farneback flow (pyr_scale 0.5, 3 levels, window 15, 3 iterations, poly_n 5,
     poly_sigma 1.2) on the BGR2GRAY-converted frames, |u| + |v|.
 
     With ``engine`` the whole batch runs on its GPU (``dgp_learn_wt``: all pairs per launch, ~1 ms for 10 frames of 747x832
     where cv2 needs 175 ms per pair on the host) and a float32 CUDA tensor is returned -- ``TrainSession.run`` takes it as the
-    ``vector_field_tf`` feed without a round trip.  Without it: the reference's own cv2 loop on the host."""
+    ``vector_field_tf`` feed without a round trip; ``overlap=True`` runs it on the engine's side stream and returns an
+    ``AsyncField`` (tensor + event) that the loss waits for, so the flow overlaps the forward pass of the training step.
+    Without ``engine``: the reference's own cv2 loop on the host."""
     if engine is not None:
         fr = all_data_batch
         if not isinstance(fr, torch.Tensor):
@@ -103,7 +118,19 @@ def learn_wt(all_data_batch, engine=None):
             fr = torch.from_numpy(np.ascontiguousarray(fr))
         elif fr.dtype != torch.uint8:
             fr = fr.to(torch.uint8)
-        return engine.learn_wt(fr.to(engine.device))
+        fr = fr.to(engine.device)
+        if not overlap:
+            return engine.learn_wt(fr)
+        main = torch.cuda.current_stream(engine.device)
+        side = engine.side_stream()
+        side.wait_stream(main)                 # the frames were produced (copied) on the caller's stream
+        with torch.cuda.stream(side):
+            field = engine.learn_wt(fr)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        field.record_stream(main)              # allocated under the side stream, consumed on the caller's
+        fr.record_stream(side)
+        return AsyncField(field, ev)
     import cv2
     frames = np.asarray(all_data_batch)
     gray = [cv2.cvtColor(f.astype(np.uint8), cv2.COLOR_BGR2GRAY) for f in frames]

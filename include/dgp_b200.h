@@ -200,6 +200,9 @@ typedef struct dgp_loss_batch {
   const float* ws_dev; const float* ws_max_dev;  /* (nl) from the host precompute fitdgp.py:874-892 */
   const float* vector_field_dev; int32_t Hin, Win;  /* (nt-1,Hin,Win) optical-flow magnitude, or NULL */
   const float* wt_batch_dev;    /* (nt-1) = wt_batch_pl * wt_batch_mask_pl */
+  void* vector_field_ready_event; /* optional cudaEvent_t recorded behind the producer of vector_field_dev (dgp_learn_wt on
+                                     another stream): the loss waits for it on its own stream, so the Farneback flow of the
+                                     batch overlaps the forward pass of dgp_train_forward_backward.  NULL: already ordered. */
 } dgp_loss_batch;
 
 /* Replaces the loss part of sess.run([loss, ...]) in fit_dgp (fitdgp.py:817-818, graph :947-1128): soft-argmax of

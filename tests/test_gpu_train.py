@@ -492,6 +492,36 @@ def test_training_step_with_temporal_clique():
     eng.close()
 
 
+def test_flow_field_overlapped_on_a_side_stream_gives_the_same_step():
+    """fit_dgp computes the Farneback field of the batch on the engine's side stream (learn_wt(..., overlap=True)) and feeds the
+    AsyncField: the loss waits for its event (dgp_loss_batch.vector_field_ready_event).  Losses and gradients must be bitwise
+    those of the step fed with the same field as a plain tensor."""
+    from deepgraphpose_b200 import fitdgp, fitdgp_util
+    from deepgraphpose_b200.engine import Engine
+    W, frames, batch, edges, S0, cfg0, ws, ws_max = _setup(seed=5)
+    cfg = oracle_loss.default_dgp_cfg(gm2=1, gm3=3, wt=30.0, wt_max=0.0)
+    fr = torch.from_numpy(frames).cuda()
+    eng = Engine(NJ)
+    eng.load_weights(W)
+    batch = dict(batch)
+    batch["wt_batch_pl"] = np.ones(NT - 1) * 30.0
+    batch["wt_batch_mask_pl"] = np.ones(NT - 1)
+    plain = fitdgp_util.learn_wt(fr, engine=eng)
+    assert tuple(plain.shape) == (NT - 1, fr.shape[1], fr.shape[2])
+    outs, grads = [], []
+    for overlap in (False, True, True):
+        field = fitdgp_util.learn_wt(fr, engine=eng, overlap=overlap)
+        if overlap:
+            assert isinstance(field, fitdgp_util.AsyncField)
+        got = fitdgp.train_forward_backward(eng, fr, dict(batch, vector_field_tf=field), cfg, edges, ws, ws_max, 200, 20)
+        outs.append({k: float(v) for k, v in got.items()})
+        grads.append(eng.get_variable("resnet_v1_50/block4/unit_3/bottleneck_v1/conv3/weights", "grad").copy())
+    assert outs[0]["wt_loss"] > 0.0
+    assert outs[0] == outs[1] == outs[2], outs
+    assert np.array_equal(grads[0], grads[1]) and np.array_equal(grads[0], grads[2])
+    eng.close()
+
+
 def test_tf_checkpoint_export_and_restore(tmp_path):
     """Train a step, export a TensorFlow checkpoint bundle (variables + moving statistics + Momentum slots), read it back
     with the bundle reader and restore a fresh engine from the prefix: identical scoremaps."""

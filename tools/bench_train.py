@@ -56,7 +56,8 @@ def measure(rank, local_rank, world, steps, warmup, nt, height, width, profile=T
     import argparse as _a
     args = _a.Namespace(steps=steps, warmup=warmup, nt=nt, height=height, width=width)
     import torch.distributed as dist
-    from deepgraphpose_b200 import dp, fitdgp, synthetic
+    from deepgraphpose_b200 import dp, fitdgp, fitdgp_util, synthetic
+    no_overlap = os.environ.get("DGP_NO_FLOW_OVERLAP", "0") == "1"   # A/B: learn_wt in front of the step instead of beside it
     from deepgraphpose_b200.engine import Engine, output_dims
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -133,7 +134,8 @@ def measure(rank, local_rank, world, steps, warmup, nt, height, width, profile=T
         fr = frames_pinned.to(dev, non_blocking=True)
         # wt > 0: the flow-magnitude field of THIS batch, computed on the device from the frames just copied (dgp_learn_wt: the
         # reference's learn_wt = cv2 Farneback on the host, 175 ms per frame pair)
-        b2 = batch if flow_pinned is None else dict(batch, vector_field_tf=eng.learn_wt(fr))
+        # -- on the engine's side stream, as fit_dgp does: it overlaps the forward pass, the loss waits for its event
+        b2 = batch if flow_pinned is None else dict(batch, vector_field_tf=fitdgp_util.learn_wt(fr, engine=eng, overlap=not no_overlap))
         out = fitdgp.train_forward_backward(eng, fr, b2, cfg, edges, ws, ws_max, 1000, 100, sync=False)
         scale = dp.allreduce_gradients(eng, overlap=os.environ.get("DGP_DP_OVERLAP", "1") != "0")
         eng.optimizer_step(0.005, 0.9, 10.0, scale)
@@ -192,7 +194,7 @@ def measure(rank, local_rank, world, steps, warmup, nt, height, width, profile=T
             "e2e": {"value": world * nt * e2e_steps / e2e_dt, "unit": "frames/s", "ms_per_step": 1e3 * e2e_dt / e2e_steps,
                     "h2d_bytes_per_step": int(frames_pinned.numel())
                                           + int(sum(np.asarray(v).nbytes for v in batch.values() if not isinstance(v, (int, list, torch.Tensor)))),
-                    "d2h_bytes_per_step": 24, "timing": "wall clock, frames copied from pinned host memory, the Farneback flow-magnitude field of the batch computed on the device (dgp_learn_wt) and the 6 loss values read back every step, max over ranks"},
+                    "d2h_bytes_per_step": 24, "timing": "wall clock, frames copied from pinned host memory, the Farneback flow-magnitude field of the batch computed on the device (dgp_learn_wt on a side stream beside the forward pass; the loss waits for its event) and the 6 loss values read back every step, max over ranks"},
             "ms_per_step_by_family": fam, "ms_per_step_with_events": ms_prof / args.steps,
             "tflops": {"forward_gemm": tf(flops_fwd, prof["conv_gemm"][0]), "dgrad_gemm": tf(flops_fwd, prof["dgrad_gemm"][0]),
                        "wgrad_gemm": tf(flops_fwd, prof["wgrad_gemm"][0]),
