@@ -56,3 +56,31 @@ def test_product_never_imports_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), fn
+
+
+def test_ctypes_structs_match_the_header(tmp_path):
+    """sizeof / offsetof of every struct of include/dgp_b200.h (compiled with gcc) against the ctypes mirrors in _lib.py."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    from deepgraphpose_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pairs = {"dgp_config": _lib.DgpConfig, "dgp_loss_cfg": _lib.DgpLossCfg, "dgp_loss_batch": _lib.DgpLossBatch,
+             "dgp_cyclic_source": _lib.DgpCyclicSource}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "dgp_b200.h"', "int main(void) {"]
+    for cname, ct in pairs.items():
+        lines.append('  printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in ct._fields_:
+            lines.append('  printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, ct in pairs.items():
+        assert int(got[cname]) == C.sizeof(ct), (cname, got[cname], C.sizeof(ct))
+        for fname, _ in ct._fields_:
+            assert int(got["%s.%s" % (cname, fname)]) == getattr(ct, fname).offset, (cname, fname)
