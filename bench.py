@@ -260,7 +260,7 @@ def max_over_ranks(x, world, dev):
 
 
 def measure_device(wl, steps, warmup, world, local_rank, profile=True):
-    """K device-timed steps with inputs resident in HBM (+ a second pass with per-launch CUDA events for the rooflines)."""
+    """K device-timed steps with inputs resident in HBM; the handle's event pairs around the GEMM run give the roofline."""
     sampler = ClockSampler(local_rank)
     sampler.start()
     for i in range(warmup):
@@ -269,6 +269,14 @@ def measure_device(wl, steps, warmup, world, local_rank, profile=True):
     barrier(world)
     sampler.begin()
     launches0 = wl.eng.launch_count()
+    if profile:
+        # The handle records one CUDA-event pair around every run of same-kind launches on the launching stream, IN the timed
+        # steps: the 54 conv_gemm layers of a step are one run (the pool is fused into conv1), so their total is measured with
+        # the programmatic-dependent-launch chaining of the real step intact (an event record between two layers would
+        # serialise them; tools/instep_layers.py does that on purpose for the per-layer table).  The roofline therefore
+        # describes the very steps `value` is computed from (a separate second pass ran ~1 % slower: hotter GPU).
+        wl.eng.get_profile()
+        wl.eng.set_profiling(2)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
@@ -277,26 +285,15 @@ def measure_device(wl, steps, warmup, world, local_rank, profile=True):
     e1.record()
     torch.cuda.synchronize()
     barrier(world)
-    ms = max_over_ranks(e0.elapsed_time(e1), world, wl.dev)
+    ms_local = e0.elapsed_time(e1)
+    ms = max_over_ranks(ms_local, world, wl.dev)
     launches = wl.eng.launch_count() - launches0
     clocks = sampler.stop()
     prof, ms_prof = None, None
     if profile:
-        # Second pass over the SAME K steps with CUDA events recorded by the handle on the launching stream: one pair around
-        # every run of same-kind launches -- the 54 conv_gemm layers of a step are one run (the pool is fused into conv1), so
-        # their total is measured with the programmatic-dependent-launch chaining of the real step intact (an event record
-        # between two layers would serialise them; tools/instep_layers.py does that on purpose for the per-layer table).
-        wl.eng.get_profile()
-        wl.eng.set_profiling(2)
-        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        p0.record()
-        for i in range(steps):
-            wl.step(i, world)
-        p1.record()
-        torch.cuda.synchronize()
-        ms_prof = p0.elapsed_time(p1)
         wl.eng.set_profiling(False)
         prof = wl.eng.get_profile()
+        ms_prof = ms_local
     return {"ms": ms, "launches": launches, "clocks": clocks, "prof": prof, "ms_prof": ms_prof,
             "value": world * wl.B * steps / (ms / 1e3)}
 
@@ -436,9 +433,9 @@ def roofline_of(wl, m, steps, peaks, peak_src, args=None):
             "frac": (achieved_tf / peak_tf) if achieved_tf else None, "traffic": traffic, "traffic_note": traffic_note,
             "peak_source": peak_src + ", 16-bit dense sustained (cuBLAS bf16; fp16 runs at the same tensor rate)",
             "share_of_step": gemm_ms / m["ms_prof"],
-            "timing": "CUDA events on the launching stream around each step's run of %d consecutive conv_gemm launches, in a second "
-                      "pass over the same steps (%.3f ms/step with events, %.3f without); achieved = algorithmic FLOPs of the "
-                      "timed launches / their summed duration" % (gemm_n // steps, m["ms_prof"] / steps, m["ms"] / steps),
+            "timing": "CUDA events on the launching stream around each step's run of %d consecutive conv_gemm launches, recorded "
+                      "in the timed steps themselves (%.3f ms/step); achieved = algorithmic FLOPs of the timed launches / their "
+                      "summed duration" % (gemm_n // steps, m["ms_prof"] / steps),
             "algorithmic_gflop_per_frame": wl.flops_frame / 1e9}
 
 
