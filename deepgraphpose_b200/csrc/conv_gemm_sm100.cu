@@ -857,192 +857,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         const int sub = u >> ncg_shift;
         const int colg = u & (ncg - 1);
         const int row0 = (kCta2 ? m_blk * 2 + (int)cta_rank : m_blk * msub + sub) * kBlockM + quad * 32;
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((acc * 2 + sub) * 64 + colg * 32);
-        uint32_t v[2][16];
-        ptx::tmem_ld_x16(taddr, v[0]);
-        ptx::tmem_ld_x16(taddr + 16, v[1]);
-        ptx::tmem_ld_wait();
-        if (sub == 1) {
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);   // the accumulator is in registers: the MMA may reuse it
-        }
-        const int px = sub * 128 + quad * 32 + lane;
-        uint8_t* my_row = patch + px * 128;
-#pragma unroll
-        for (int s2 = 0; s2 < 2; ++s2) {
-          uint32_t o[8];
-#pragma unroll
-          for (int i = 0; i < 8; i += 2) {
-            const float4 sc = *reinterpret_cast<const float4*>(ss + s2 * 16 + 2 * i);
-            const float4 sh = *reinterpret_cast<const float4*>(ss + 32 + s2 * 16 + 2 * i);
-            const ptx::f32x2 r0 = ptx::fma2(ptx::pk2(__uint_as_float(v[s2][2 * i]), __uint_as_float(v[s2][2 * i + 1])),
-                                            ptx::pk2(sc.x, sc.y), ptx::pk2(sh.x, sh.y));
-            const ptx::f32x2 r1 = ptx::fma2(ptx::pk2(__uint_as_float(v[s2][2 * i + 2]), __uint_as_float(v[s2][2 * i + 3])),
-                                            ptx::pk2(sc.z, sc.w), ptx::pk2(sh.z, sh.w));
-            float a0, a1, b0, b1;
-            ptx::upk2(r0, a0, a1);
-            ptx::upk2(r1, b0, b1);
-            o[i] = ptx::cvt_pack16<kFp16, true>(a0, a1);
-            o[i + 1] = ptx::cvt_pack16<kFp16, true>(b0, b1);
-          }
-          const int u = colg * 4 + 2 * s2;
-          *reinterpret_cast<uint4*>(my_row + ((u ^ (px & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
-          *reinterpret_cast<uint4*>(my_row + (((u + 1) ^ (px & 7)) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
-        }
-      }
-      ptx::named_bar_sync(bar_id, 256);
-      // interior tiles (patch origin not clamped, no window row / column outside the image): constant patch offsets
-      const bool interior = 2 * ti * R >= p.pool_pad_t && 2 * tj * Cp >= p.pool_pad_l &&
-                            2 * (ti * R + R - 1) - p.pool_pad_t + 2 < H1 && 2 * (tj * Cp + Cp - 1) - p.pool_pad_l + 2 < W1;
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        if (!pool_item[k]) continue;
-        const int i = ti * R + pi[k], j = tj * Cp + pj[k];
-        uint32_t m[4] = {0u, 0u, 0u, 0u};          // post-ReLU values are >= 0 and every window holds a valid pixel
-        if (interior) {
-#pragma unroll
-          for (int w = 0; w < 9; ++w) {
-            const int q = q0[k] + (w / 3) * Cw + w % 3;
-            const uint4 x = *reinterpret_cast<const uint4*>(patch + q * 128 + ((pv ^ (q & 7)) << 4));
-            const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-            for (int c = 0; c < 4; ++c) m[c] = max16x2<kFp16>(m[c], xs[c]);
-          }
-        } else {
-          if (i >= p.pool_H || j >= p.pool_W) continue;
-          const int ra = max(0, 2 * ti * R - p.pool_pad_t), ca = max(0, 2 * tj * Cp - p.pool_pad_l);
-#pragma unroll
-          for (int dr = 0; dr < 3; ++dr) {
-            const int rr = 2 * i - p.pool_pad_t + dr;
-            if (rr < 0 || rr >= H1) continue;
-#pragma unroll
-            for (int dc = 0; dc < 3; ++dc) {
-              const int cc = 2 * j - p.pool_pad_l + dc;
-              if (cc < 0 || cc >= W1) continue;
-              const int q = (rr - ra) * Cw + (cc - ca);
-              const uint4 x = *reinterpret_cast<const uint4*>(patch + q * 128 + ((pv ^ (q & 7)) << 4));
-              const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-              for (int c = 0; c < 4; ++c) m[c] = max16x2<kFp16>(m[c], xs[c]);
-            }
-          }
-        }
-        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.out) +
-                                              ((((size_t)img * p.pool_H + i) * p.pool_W + j) * 64 + pv * 8) * 2);
-        *dst = make_uint4(m[0], m[1], m[2], m[3]);
-      }
-      // the group's next write into this patch buffer happens after its next barrier-free phase; the barrier below keeps
-      // a fast warp from overwriting pixels a slow one is still pooling
-      ptx::named_bar_sync(bar_id, 256);
-      acc_phase ^= 1;
-      tj += d_tj;
-      if (tj >= tiles_j) { tj -= tiles_j; ++ti; }
-      ti += d_ti;
-      if (ti >= tiles_i) { ti -= tiles_i; ++img; }
-      img += d_img;
-    }
-  } else {
-    // -------------------------------------------------------------- epilogue, TMA-staged 16-bit (+ TMA residual)
-    // 16 INDEPENDENT epilogue warps, four per TMEM lane quadrant.  A tile is cut into units of 32 rows x 32 columns
-    // (one warp's TMEM rows x two tcgen05.ld.x16); the warp with column-group index cg takes units cg, cg+4, ... of
-    // the (sub-tile, column group) sequence.  Each warp owns a small ring of 2 KB staging buffers (32 rows x 64 B,
-    // SWIZZLE_64B), TMA-loads the residual tile into a buffer ahead of time, combines in place and TMA-stores the
-    // buffer: no barrier between warps anywhere in the epilogue, 16 units in flight per SM.
-    const int quad = warp & 3;
-    const int ew = warp - 2;
-    const int cg = ew >> 2;
-    const int nb = p.epi_bufs;
-    uint8_t* ebuf = smem_epi + (size_t)ew * nb * kEpiUnitBytes;
-    uint64_t* rbar = res_bar + ew * kMaxEpiBufs;
-    const bool has_res = p.residual != nullptr;
-    const int block_n = p.block_n, nnb = p.num_n_blocks;
-    const int ncg = block_n >> 5;                                   // 32-column groups per tile row: 2, 4 or 8
-    const int ncg_shift = ncg == 8 ? 3 : (ncg == 4 ? 2 : 1);
-    const int units = msub * ncg;
-    const int nsets = ncg == 8 ? 2 : 1;                             // distinct column groups this warp ever touches
-    const int PQ = p.P * p.Q;
-    float* ss = smem_ss + ew * 128;
-    int ss_n0 = -1;
-
-    // Residual prefetch cursor: walks this warp's (tile, unit) sequence nb-1 units ahead of the consumer.  All lanes
-    // keep the (uniform) cursor; lane 0 issues.
-    int pf_tile = tile0, pf_u = cg, pf_buf = 0, pf_mblk = 0, pf_n0 = 0;
-    auto pf_setup_tile = [&]() {
-      pf_mblk = pf_tile / nnb;
-      pf_n0 = (pf_tile - pf_mblk * nnb) * block_n;
-    };
-    auto issue_residual = [&]() {
-      if (pf_tile >= num_tiles) return;
-      const int sub = pf_u >> ncg_shift;
-      const int row0 = (kCta2 ? pf_mblk * 2 + (int)cta_rank : pf_mblk * msub + sub) * kBlockM + quad * 32;
-      const int col0 = pf_n0 + ((pf_u & (ncg - 1)) << 5);
-      if (lane == 0) {
-        ptx::mbar_arrive_expect_tx(&rbar[pf_buf], (uint32_t)kEpiUnitBytes);
-        if (p.res_sub == 1) {
-          ptx::tma_load_2d(ebuf + pf_buf * kEpiUnitBytes, &p.tmap_res, &rbar[pf_buf], col0, row0);
-        } else {
-          const int img = row0 / PQ;
-          const int rem = row0 - img * PQ;
-          const int pp = rem / p.Q;
-          ptx::tma_load_im2col_4d(ebuf + pf_buf * kEpiUnitBytes, &p.tmap_res, &rbar[pf_buf], col0,
-                                  (rem - pp * p.Q) * p.res_sub, pp * p.res_sub, img, 0, 0);
-        }
-      }
-      if (++pf_buf == nb) pf_buf = 0;
-      pf_u += 4;
-      if (pf_u >= units) {
-        pf_u = cg;
-        pf_tile += tstep;
-        if (pf_tile < num_tiles) pf_setup_tile();
-      }
-    };
-
-    const bool active = cg < units;  // 128-row tiles of a 64-wide layer have only two units
-    if (has_res && active) {
-      if (pf_tile < num_tiles) pf_setup_tile();
-      for (int i = 0; i < nb - 1; ++i) issue_residual();
-      __syncwarp();
-    }
-    int buf = 0;
-    uint32_t buf_phase = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = tile0; tile < num_tiles; tile += tstep) {
-      const int m_blk = tile / nnb;
-      const int n0 = (tile - m_blk * nnb) * block_n;
-      if (n0 != ss_n0 && active) {
-        if (lane < 16 * nsets) {
-          const int set = lane >> 4, is_shift = (lane >> 3) & 1, i = (lane & 7) * 4;
-          const int col = n0 + (((cg & (ncg - 1)) + 4 * set) << 5) + i;
-          const float* src = is_shift ? p.shift : p.scale;
-          const float fill = is_shift ? 0.f : 1.f;
-          const float4 val = src ? __ldg(reinterpret_cast<const float4*>(src + col)) : make_float4(fill, fill, fill, fill);
-          *reinterpret_cast<float4*>(ss + set * 64 + is_shift * 32 + i) = val;
-        }
-        __syncwarp();
-        ss_n0 = n0;
-      }
-      ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
-      ptx::tc_fence_after();
-      for (int u = cg; u < units; u += 4) {
-        const int sub = u >> ncg_shift;
-        const int colg = u & (ncg - 1);
-        const int row0 = (kCta2 ? m_blk * 2 + (int)cta_rank : m_blk * msub + sub) * kBlockM + quad * 32;
-        if (kMask) {
-          // The lane's activation row of the NEXT unit (this tile's, or the first of this warp's next tile) is pulled towards
-          // L2 now: ncu showed the masked epilogue half of its time in long-scoreboard stalls on the row fetch below, which
-          // is issued only one TMEM wait ahead of its use and has no registers to be pipelined into.
-          int nt = tile, nu = u + 4;
-          if (nu >= units) { nt = tile + tstep; nu = cg; }
-          if (nt < num_tiles) {
-            const int nm = nt / nnb, nn0 = (nt - nm * nnb) * block_n;
-            const int nrow = (kCta2 ? nm * 2 + (int)cta_rank : nm * msub + (nu >> ncg_shift)) * kBlockM + quad * 32 + lane;
-            if (nrow < p.M)
-              ptx::prefetch_l2(reinterpret_cast<const uint8_t*>(p.mask_act) +
-                               ((size_t)nrow * p.ldc + nn0 + ((nu & (ncg - 1)) << 5)) * 2);
-          }
-        }
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((acc * msub + sub) * block_n + (colg << 5));
         uint8_t* my_buf = ebuf + buf * kEpiUnitBytes;
         uint32_t v[2][16];
@@ -1053,7 +867,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           const int row = row0 + lane;
           if (row < p.M) {
             // the lane's 64-byte activation row as two 256-bit loads: every lane touches a different line, so the cost is
-            // L1 tag cycles per instruction -- half as many instructions as with 128-bit loads
+            // L1 tag cycles per instruction -- half as many instructions as with 128-bit loads.  (Pulling the next unit's rows
+            // towards L2 with prefetch.global.L2 was measured too: slightly slower.)
             const uint8_t* ap = reinterpret_cast<const uint8_t*>(p.mask_act) + ((size_t)row * p.ldc + n0 + (colg << 5)) * 2;
             ptx::ldg_nc_256(ap, act[0], act[1]);
             ptx::ldg_nc_256(ap + 32, act[2], act[3]);
