@@ -189,10 +189,25 @@ def cpu_reference_fps(n_frames, warmup=1, threads=None):
     return n_frames / dt, threads, dt
 
 
+def headline_config(B, skeleton_kind, precision, world):
+    """The `config` object of the JSON line: printed identically by both arms (the reference arm times the CPU path on the
+    workload this describes; what it sampled of it is in its `cpu_baseline.sample`)."""
+    return {"workload": WORKLOAD, "frames_per_step_per_gpu": B, "frame": [H, W, 3], "num_joints": NJ,
+            "skeleton": skeleton_kind,
+            "precision": "%s operands on tcgen05 kind::f16, fp32 accumulate / BN epilogue / logits: the mode whose GPU tests assert BASELINE.json's tolerances "
+                         "(sigmoid 1e-2, soft-argmax 0.5 px, loss 1e-3) on all four inference shapes and the training step" % precision,
+            "l2": "4 rotating input batches (%d MB) and per-layer activations (>600 MB/step) exceed the 126 MB L2" % (4 * B * H * W * 3 // 2 ** 20),
+            "batch_choice": "engine.suggest_batch: tile counts of the persistent GEMM grid land on multiples of the SM count",
+            "parallelism": "frame shards x%d, 1-frame halo all_gather" % world if world > 1 else "single GPU"}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
     per_step = 2
+    from deepgraphpose_b200.engine import suggest_batch      # pure host arithmetic: the batch size the other arm reports
+    B = args.batch if args.batch > 0 else suggest_batch(H, W, *((12, 24) if args.config == "c" else (24, 48)))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     for _ in range(max(args.warmup, 1)):
         cpu_reference_fps(1, warmup=0)
     fps, cores, dt = cpu_reference_fps(per_step * args.steps, warmup=0)
@@ -200,10 +215,10 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames_per_step": per_step, "batch": 1},
+        "config": headline_config(B, CONFIGS[args.config][3], args.precision, world),
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                         "sample": "%d frames, batch 1 as eval.py:328, CPU restatement of the reference TF1 path "
-                                   "(TF1.15 not installable: py3.12, no network)" % (per_step * args.steps)},
+                         "sample": "%d frames of that workload (%d per step), batch 1 as eval.py:328, fp32, CPU restatement of the "
+                                   "reference TF1 path (TF1.15 not installable: py3.12, no network)" % (per_step * args.steps, per_step)},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -595,13 +610,7 @@ def main():
             "metric": METRIC, "value": m["value"], "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": m["ms"] / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": B, "frame": [H, W, 3], "num_joints": NJ,
-                       "skeleton": skeleton_kind,
-                       "precision": "%s operands on tcgen05 kind::f16, fp32 accumulate / BN epilogue / logits: the mode whose GPU tests assert BASELINE.json's tolerances "
-                                    "(sigmoid 1e-2, soft-argmax 0.5 px, loss 1e-3) on all four inference shapes and the training step" % args.precision,
-                       "l2": "4 rotating input batches (%d MB) and per-layer activations (>600 MB/step) exceed the 126 MB L2" % (4 * B * H * W * 3 // 2 ** 20),
-                       "batch_choice": "engine.suggest_batch: tile counts of the persistent GEMM grid land on multiples of the SM count",
-                       "parallelism": "frame shards x%d, 1-frame halo all_gather" % world if world > 1 else "single GPU"},
+            "config": headline_config(B, skeleton_kind, args.precision, world),
             "clocks": m["clocks"],
             "e2e": e2e,
             "gpu_launches": m["launches"],
