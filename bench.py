@@ -500,7 +500,7 @@ def main():
                     help="BASELINE.json workload of the headline: b = configs[1] (default), c = configs[2], e = configs[4]")
     ap.add_argument("--precision", default=PRECISION, choices=["fp16", "bf16"])
     ap.add_argument("--e2e-frames", type=int, default=10000, help="frames per GPU of the end-to-end video (configs[1]: 10 k)")
-    ap.add_argument("--cpu-frames", type=int, default=12)
+    ap.add_argument("--cpu-frames", type=int, default=64, help="frames of the workload the CPU baseline times (about 10 s on 16 cores)")
     ap.add_argument("--no-ncu-traffic", action="store_true",
                     help="do not measure roofline.traffic with an ncu child process (falls back to profiles/r02_traffic.json)")
     ap.add_argument("--traffic-child", action="store_true", help=argparse.SUPPRESS)
