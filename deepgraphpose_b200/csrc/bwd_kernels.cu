@@ -219,38 +219,56 @@ __global__ void maxpool_bwd_kernel(const uint2* __restrict__ arg, const uint4* _
 // pooled gradient once, dy written once: ~0.5 GB per 10 frames of 747 x 832 instead of the 1.5 GB of argmax + gather + mask
 // passes over HBM-resident tensors.
 constexpr int kPoolTileH = 8, kPoolTileW = 32, kPoolRows = 11, kPoolCols = 35, kPoolP = 5, kPoolQ = 17;
-constexpr int kPoolBwdSmem = (kPoolRows * kPoolCols * 8 + kPoolP * kPoolQ * 8) * 16 + kPoolP * kPoolQ * 8 * 8;
+constexpr int kPoolBwdSmem = (kPoolRows * kPoolCols * 8 + 2 * kPoolP * kPoolQ * 8) * 16;
 
+// packed 16-bit helpers of the kernel below: per-half masks (0xFFFF where true)
+template <bool kFp16>
+__device__ __forceinline__ uint32_t gt_mask16x2(uint32_t a, uint32_t b) {
+  if (kFp16) return __hgt2_mask(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+  return __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+}
+template <bool kFp16>
+__device__ __forceinline__ float2 unpack16x2(uint32_t w) {
+  if (kFp16) return __half22float2(*reinterpret_cast<const __half2*>(&w));
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+
+// ncu (first version, profiles/r02_ncu_bwd_kernels.md): issue-bound (78 % issue utilisation, DRAM 18 %) at ~3000 instructions
+// per thread, so this version counts instructions: all index arithmetic divides by compile-time constants (fixed shared-memory
+// strides), the arg-max scan of stage A runs on packed 16-bit pairs (one mask + two selects per pair and position instead of
+// unpack + 2 x (compare, select, select)), the winner is kept as a ONE-HOT position bit per 16-bit lane so that stage B turns
+// "is this pixel the winner of that window" into shift / and / multiply on two channels at a time.
+template <bool kFp16>
 __global__ void __launch_bounds__(256) maxpool_relu_bwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ gout, int H,
                                                                int W, int Ho, int Wo, int pad_t, int pad_l, uint4* __restrict__ gx,
-                                                               float* __restrict__ partial, int fp16) {
+                                                               float* __restrict__ partial) {
   extern __shared__ uint4 pool_sm[];
-  uint4* xs = pool_sm;                                   // [rows][cols][8]
-  uint4* gs = pool_sm + kPoolRows * kPoolCols * 8;       // [nP][nQ][8] pooled gradients
-  uint2* as = reinterpret_cast<uint2*>(gs + kPoolP * kPoolQ * 8);   // [nP][nQ][8] argmax positions, one byte per channel
+  uint4* xs = pool_sm;                                   // [kPoolRows][kPoolCols][8]
+  uint4* gs = pool_sm + kPoolRows * kPoolCols * 8;       // [kPoolP][kPoolQ][8] pooled gradients
+  uint4* as = gs + kPoolP * kPoolQ * 8;                  // [kPoolP][kPoolQ][8] one-hot winner position per 16-bit lane
   const int n = blockIdx.z, y0 = blockIdx.y * kPoolTileH, x0 = blockIdx.x * kPoolTileW;
   const int y1 = min(y0 + kPoolTileH, H) - 1, x1 = min(x0 + kPoolTileW, W) - 1;
   const int p_lo = max(0, (y0 + pad_t - 1) >> 1), p_hi = min(Ho - 1, (y1 + pad_t) >> 1);
   const int q_lo = max(0, (x0 + pad_l - 1) >> 1), q_hi = min(Wo - 1, (x1 + pad_l) >> 1);
   const int nP = p_hi - p_lo + 1, nQ = q_hi - q_lo + 1;
   const int ys0 = min(2 * p_lo - pad_t, y0), xs0 = min(2 * q_lo - pad_l, x0);
-  const int rows = max(2 * p_hi - pad_t + 2, y1) - ys0 + 1, cols = max(2 * q_hi - pad_l + 2, x1) - xs0 + 1;
   const int tid = threadIdx.x;
-  for (int it = tid; it < rows * cols * 8; it += 256) {
-    const int cg = it & 7, col = (it >> 3) % cols, row = (it >> 3) / cols;
+  const int cg = tid & 7;
+  for (int it = tid; it < kPoolRows * kPoolCols * 8; it += 256) {
+    const int px = it >> 3, col = px % kPoolCols, row = px / kPoolCols;
     const int y = ys0 + row, xx = xs0 + col;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
     if (y >= 0 && y < H && xx >= 0 && xx < W) v = __ldg(x + (((size_t)n * H + y) * W + xx) * 8 + cg);
     xs[it] = v;
   }
   __syncthreads();
-  // ---- stage A: first maximum of every window (row-major over its valid positions, strict >)
-  for (int it = tid; it < nP * nQ * 8; it += 256) {
-    const int cg = it & 7, wq = (it >> 3) % nQ, wp = (it >> 3) / nQ;
+  // ---- stage A: first maximum of every window (row-major over its valid positions, strict >), packed
+  const uint32_t ninf = kFp16 ? 0xFC00FC00u : 0xFF80FF80u;
+  for (int it = tid; it < kPoolP * kPoolQ * 8; it += 256) {
+    const int wi = it >> 3, wq = wi % kPoolQ, wp = wi / kPoolQ;
+    if (wp >= nP || wq >= nQ) continue;
     const int p = p_lo + wp, q = q_lo + wq;
-    float best[8];
-    uint32_t idx[8];
-    bool have = false;
+    uint32_t best[4] = {ninf, ninf, ninf, ninf}, oh[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
     for (int dy = 0; dy < 3; ++dy) {
       const int y = 2 * p - pad_t + dy;
@@ -259,23 +277,18 @@ __global__ void __launch_bounds__(256) maxpool_relu_bwd_kernel(const uint4* __re
       for (int dx = 0; dx < 3; ++dx) {
         const int xx = 2 * q - pad_l + dx;
         if (xx < 0 || xx >= W) continue;
-        float v[8];
-        unpack8(xs[((y - ys0) * cols + (xx - xs0)) * 8 + cg], v, fp16);
-        if (!have) {
+        const uint4 v = xs[((y - ys0) * kPoolCols + (xx - xs0)) * 8 + cg];
+        const uint32_t vw[4] = {v.x, v.y, v.z, v.w};
+        const uint32_t pos2 = 0x00010001u << (dy * 3 + dx);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) { best[j] = v[j]; idx[j] = dy * 3 + dx; }
-          have = true;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (v[j] > best[j]) { best[j] = v[j]; idx[j] = dy * 3 + dx; }
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t m = gt_mask16x2<kFp16>(vw[k], best[k]);
+          best[k] = (vw[k] & m) | (best[k] & ~m);
+          oh[k] = (pos2 & m) | (oh[k] & ~m);
         }
       }
     }
-    uint2 o;
-    o.x = idx[0] | (idx[1] << 8) | (idx[2] << 16) | (idx[3] << 24);
-    o.y = idx[4] | (idx[5] << 8) | (idx[6] << 16) | (idx[7] << 24);
-    as[it] = o;
+    as[it] = make_uint4(oh[0], oh[1], oh[2], oh[3]);
     gs[it] = __ldg(gout + (((size_t)n * Ho + p) * Wo + q) * 8 + cg);
   }
   __syncthreads();
@@ -283,7 +296,6 @@ __global__ void __launch_bounds__(256) maxpool_relu_bwd_kernel(const uint4* __re
   float S[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) S[j] = 0.0f;
-  const int cg = tid & 7;
 #pragma unroll 2
   for (int it = tid; it < kPoolTileH * kPoolTileW * 8; it += 256) {
     const int col = (it >> 3) % kPoolTileW, row = (it >> 3) / kPoolTileW;
@@ -296,26 +308,31 @@ __global__ void __launch_bounds__(256) maxpool_relu_bwd_kernel(const uint4* __re
     const int qa = max(0, (xx + pad_l - 1) >> 1), qb = min(Wo - 1, (xx + pad_l) >> 1);
     for (int p = pa; p <= pb; ++p)
       for (int q = qa; q <= qb; ++q) {
-        const uint32_t mine = (uint32_t)((y - (2 * p - pad_t)) * 3 + (xx - (2 * q - pad_l)));
-        const int w = ((p - p_lo) * nQ + (q - q_lo)) * 8 + cg;
-        const uint2 a = as[w];
-        float gv[8];
-        unpack8(gs[w], gv, fp16);
+        const int mine = (y - (2 * p - pad_t)) * 3 + (xx - (2 * q - pad_l));
+        const int w = ((p - p_lo) * kPoolQ + (q - q_lo)) * 8 + cg;
+        const uint4 a = as[w], g = gs[w];
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (((a.x >> (8 * j)) & 0xffu) == mine) acc[j] += gv[j];
-          if (((a.y >> (8 * j)) & 0xffu) == mine) acc[4 + j] += gv[4 + j];
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t hit = ((aw[k] >> mine) & 0x00010001u) * 0xFFFFu;   // 0xFFFF per 16-bit lane this pixel won
+          const float2 f = unpack16x2<kFp16>(gw[k] & hit);
+          acc[2 * k] += f.x;
+          acc[2 * k + 1] += f.y;
         }
       }
-    float xv[8];
-    unpack8(xs[((y - ys0) * cols + (xx - xs0)) * 8 + cg], xv, fp16);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = xv[j] > 0.0f ? acc[j] : 0.0f;
-    const uint4 o = pack8v(acc, fp16);
+    const uint4 xv = xs[((y - ys0) * kPoolCols + (xx - xs0)) * 8 + cg];
+    uint4 o = pack8v(acc, kFp16 ? 1 : 0);
+    o.x &= gt_mask16x2<kFp16>(xv.x, 0u); o.y &= gt_mask16x2<kFp16>(xv.y, 0u);
+    o.z &= gt_mask16x2<kFp16>(xv.z, 0u); o.w &= gt_mask16x2<kFp16>(xv.w, 0u);
     gx[(((size_t)n * H + y) * W + xx) * 8 + cg] = o;
-    unpack8(o, acc, fp16);   // the sums are those of dy as stored (what the wgrad GEMM consumes)
+    // the sums are those of dy as stored (what the wgrad GEMM consumes)
+    const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
-    for (int j = 0; j < 8; ++j) S[j] += acc[j];
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = unpack16x2<kFp16>(ow[k]);
+      S[2 * k] += f.x;
+      S[2 * k + 1] += f.y;
+    }
   }
   __syncthreads();   // xs is dead: reuse it for the fixed-order column reduction
   float* red = reinterpret_cast<float*>(pool_sm);   // [256][9]
@@ -484,11 +501,19 @@ int maxpool_relu_bwd_rows(int N, int H, int W) {
 cudaError_t launch_maxpool_relu_bwd(const void* x, const void* gout, int N, int H, int W, int C, int Ho, int Wo, int pad_t,
                                     int pad_l, void* gx, float* partial, int fp16, cudaStream_t s) {
   if (C != 64 || pad_t < 0 || pad_t > 1 || pad_l < 0 || pad_l > 1 || N > 65535) return cudaErrorInvalidValue;
-  cudaError_t e = cudaFuncSetAttribute(maxpool_relu_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPoolBwdSmem);
-  if (e != cudaSuccess) return e;
   dim3 grid((W + kPoolTileW - 1) / kPoolTileW, (H + kPoolTileH - 1) / kPoolTileH, N);
-  maxpool_relu_bwd_kernel<<<grid, 256, kPoolBwdSmem, s>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(gout),
-                                                          H, W, Ho, Wo, pad_t, pad_l, reinterpret_cast<uint4*>(gx), partial, fp16);
+  cudaError_t e;
+  if (fp16) {
+    e = cudaFuncSetAttribute(maxpool_relu_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPoolBwdSmem);
+    if (e != cudaSuccess) return e;
+    maxpool_relu_bwd_kernel<true><<<grid, 256, kPoolBwdSmem, s>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(gout),
+                                                                  H, W, Ho, Wo, pad_t, pad_l, reinterpret_cast<uint4*>(gx), partial);
+  } else {
+    e = cudaFuncSetAttribute(maxpool_relu_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPoolBwdSmem);
+    if (e != cudaSuccess) return e;
+    maxpool_relu_bwd_kernel<false><<<grid, 256, kPoolBwdSmem, s>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(gout),
+                                                                   H, W, Ho, Wo, pad_t, pad_l, reinterpret_cast<uint4*>(gx), partial);
+  }
   return cudaGetLastError();
 }
 
